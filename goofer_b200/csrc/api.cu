@@ -1,0 +1,562 @@
+// api.cu -- the C ABI of libgoofer_b200.so (include/goofer_b200.h): batch orchestration, workspace
+// carving, wave scheduling, the host-buffer convenience entry point and the stage-level calls.
+//
+// There is no CPU fallback anywhere in this file: every numeric array is produced by a kernel.
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <cmath>
+#include <vector>
+#include <mutex>
+#include <algorithm>
+
+#include "gf_internal.h"
+#include "gf_kernels.h"
+
+// ------------------------------------------------------------------------------------------------
+static thread_local char g_err[512] = "";
+static thread_local GooferStats g_stats = {0, 0, 0, 0};
+
+void gf_set_error(const char *fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+extern "C" const char *goofer_last_error(void) { return g_err; }
+extern "C" int goofer_version(void) { return GOOFER_ABI_VERSION; }
+extern "C" void goofer_last_stats(GooferStats *s) { if (s) *s = g_stats; }
+
+#define GF_CUDA(call)                                                                              \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess) {                                                                   \
+            gf_set_error("%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+            return GOOFER_ERR_CUDA;                                                                \
+        }                                                                                          \
+    } while (0)
+
+// ------------------------------------------------------------------------------------------------
+// constant tables, computed in fp64 with the reference's own formulas
+// ------------------------------------------------------------------------------------------------
+static void gf_brightness(float *dst, int sr, double start_hz, double end_hz, double gain_db)
+{
+    // GOOFER.py:585-595
+    const int n = GF_NBINS;
+    const double nyq = sr / 2.0;
+    std::vector<double> f(n);
+    for (int i = 0; i < n; ++i) f[i] = (i == n - 1) ? nyq : i * (nyq / (n - 1));
+    int a = (int)(std::lower_bound(f.begin(), f.end(), start_hz) - f.begin());
+    int b = (int)(std::lower_bound(f.begin(), f.end(), end_hz) - f.begin());
+    const double top = std::pow(10.0, gain_db / 20.0);
+    for (int i = 0; i < n; ++i) {
+        double g = 1.0;
+        if (i >= a && i < b) {
+            const int m = b - a;
+            const double lin = (m <= 1) ? 0.0 : ((i - a == m - 1) ? 1.0 : (i - a) * (1.0 / (m - 1)));
+            g = 1.0 + lin * (top - 1.0);
+        } else if (i >= b) g = top;
+        dst[i] = (float)g;
+    }
+}
+
+static void gf_gauss_taps(double *dst, double sigma)
+{
+    const int r = (int)(4.0 * sigma + 0.5);
+    double norm = 0.0;
+    for (int j = 0; j <= 2 * r; ++j) { const double t = (j - r) / sigma; dst[j] = std::exp(-0.5 * t * t); norm += dst[j]; }
+    for (int j = 0; j <= 2 * r; ++j) dst[j] /= norm;
+}
+
+static std::mutex g_tab_mutex;
+static int g_tab_sr[64] = {0};
+
+int gf_tables_init(int sr)
+{
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) { gf_set_error("no CUDA device: %s", cudaGetErrorString(cudaGetLastError())); return GOOFER_ERR_CUDA; }
+    std::lock_guard<std::mutex> lk(g_tab_mutex);
+    if (dev < 64 && g_tab_sr[dev] == sr) return 0;
+    GfTables *t = new GfTables();
+    const double PI = 3.141592653589793238462643383279502884;
+    for (int m = 0; m < 512; ++m) t->tw512[m] = make_float2((float)std::cos(-2.0 * PI * m / 512.0), (float)std::sin(-2.0 * PI * m / 512.0));
+    for (int k = 0; k <= 512; ++k) t->tw1024[k] = make_float2((float)std::cos(-2.0 * PI * k / 1024.0), (float)std::sin(-2.0 * PI * k / 1024.0));
+    for (int i = 0; i < 1024; ++i) {
+        // np.hanning(M): 0.5 + 0.5 cos(pi n / (M - 1)), n = 1 - M, 3 - M, ... ; cast f32, then sqrt in f32
+        const double nn = (double)(1 - 1024 + 2 * i);
+        const float h = (float)(0.5 + 0.5 * std::cos(PI * nn / 1023.0));
+        t->win[i] = std::sqrt(h);
+        t->win2[i] = t->win[i] * t->win[i];
+    }
+    for (int i = 0; i < GF_NBINS; ++i) {
+        t->boost[i] = (float)((i == GF_NBINS - 1) ? 100.0 : i * (99.0 / 512.0) + 1.0);
+        t->freq32[i] = (float)((double)i / (1024.0 * (1.0 / (double)sr)));
+    }
+    gf_brightness(t->bright_h, sr, 2000, 3500, 3.0);
+    gf_brightness(t->bright_b, sr, 3500, 5000, 20.0);
+    gf_gauss_taps(t->g175, 1.75);
+    gf_gauss_taps(t->g05, 0.5);
+    t->sr = sr;
+    cudaError_t e = cudaMemcpyToSymbol(d_tab, t, sizeof(GfTables));
+    delete t;
+    if (e != cudaSuccess) { gf_set_error("table upload failed: %s", cudaGetErrorString(e)); return GOOFER_ERR_CUDA; }
+    if (dev < 64) g_tab_sr[dev] = sr;
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// workspace carving
+// ------------------------------------------------------------------------------------------------
+struct Bump {
+    char *base; size_t cap; size_t off;
+    void *take(size_t bytes) {
+        off = (off + 255) & ~(size_t)255;
+        void *p = base ? base + off : nullptr;
+        off += bytes;
+        return p;
+    }
+    template <typename T> T *arr(size_t n) { return (T *)take(n * sizeof(T)); }
+};
+
+static inline bool note_needs_fx(const GfNotePlan &p)
+{
+    return p.su > 0.0 || p.sj > 0.0 || p.fry_mask_on || p.sd > 0 || p.tension != 0.0;
+}
+
+struct NoteLayout {      // what one note takes from the wave region (computed identically for sizing and rendering)
+    size_t bytes;
+};
+
+// carve (or just size, when bp.base == NULL) the buffers of one note
+static void gf_carve_note(const GfNotePlan &p, Bump &bp, GfNoteDev *nd, GfPassDev *pd /* n_passes entries */, bool taps)
+{
+    const size_t n = (size_t)p.n_total;
+    const size_t tiles = (size_t)(p.T_out + GF_FT - 1) / GF_FT;
+    GfNoteDev d;
+    std::memset(&d, 0, sizeof(d));
+    d.trk_canon = bp.arr<float>(4 * (size_t)p.T_env);
+    d.trk_clean = p.any_fst ? bp.arr<float>(8 * (size_t)p.T_env) : nullptr;
+    d.envF = bp.arr<float>(tiles * GF_NBINS * GF_FT);
+    d.envN = bp.arr<float>(tiles * GF_NBINS * GF_FT);
+    d.vm = bp.arr<float>(n);
+    d.ms_short = bp.arr<float>((n + 3) / 4);
+    d.noteScal = bp.arr<double>(GF_NS_COUNT);
+    if (p.f0_jitter) d.z_sh = bp.arr<double>(n);
+    if (p.vol_jitter) { d.z_srh = bp.arr<double>(n); d.z_srb = bp.arr<double>(n); d.vjm = bp.arr<float>(n); }
+    if (p.sd > 0) d.sdm = bp.arr<float>(n);
+    if (p.pd != 0.0) d.dyn = bp.arr<float>(n);
+    if (note_needs_fx(p)) {
+        d.f0n = bp.arr<float>(n);
+        for (int k = 0; k < 4; ++k) d.fx[k] = bp.arr<float>(n);
+    }
+    (void)taps;
+    for (int k = 0; k < p.n_passes; ++k) {
+        GfPassDev q;
+        std::memset(&q, 0, sizeof(q));
+        q.kind = p.pass_kind[k];
+        q.n_total = p.n_total;
+        q.T_out = p.T_out;
+        q.f0 = bp.arr<float>(n);
+        q.pulse = bp.arr<float>(n);
+        q.harm = bp.arr<float>(n);
+        q.bre = bp.arr<float>(n);
+        q.uv = bp.arr<float>(n);
+        q.onset_cap = p.n_total / 8 + 64;
+        q.onsets = bp.arr<int4>((size_t)q.onset_cap);
+        if (k == 0 && p.add_subharm) q.sub = bp.arr<float>(n);
+        q.mask_ones = (q.kind == GF_PASS_SA);
+        if (pd) pd[k] = q;
+    }
+    if (nd) *nd = d;
+}
+
+static size_t gf_note_bytes(const GfNotePlan &p)
+{
+    Bump bp{nullptr, 0, 0};
+    gf_carve_note(p, bp, nullptr, nullptr, false);
+    return bp.off + 256;
+}
+
+static size_t gf_sources_bytes(const GooferBatch *b)
+{
+    size_t tot = 256;
+    for (int s = 0; s < b->n_sources; ++s) tot += (((size_t)std::max(b->sources[s].T, 0) * GF_ENVS_LD * sizeof(float)) + 255) & ~(size_t)255;
+    tot += (size_t)b->n_sources * sizeof(GfSourceDev) + 256;
+    return tot;
+}
+
+// per-wave bookkeeping arrays (plans, note / pass records, scalars, work lists, job lists)
+static size_t gf_wave_meta_bytes(size_t n_notes, size_t n_pass, size_t n_env_work, size_t n_frame_work, size_t n_fir)
+{
+    return n_notes * (sizeof(GfNotePlan) + sizeof(GfNoteDev)) + n_pass * (sizeof(GfPassDev) + sizeof(GfPassScal)) +
+           n_env_work * sizeof(int2) + n_frame_work * sizeof(int4) + n_fir * sizeof(GfFirJob) +
+           n_pass * 16 * sizeof(GfOnepoleJob) + 16 * 256;
+}
+
+#define GF_BLOCKS_PER_CTA 32      // output hop blocks one frame-kernel CTA owns (3 frames of halo each)
+
+static void gf_note_work_counts(const GfNotePlan &p, size_t *n_env, size_t *n_frame, size_t *n_fir)
+{
+    *n_env = (size_t)(p.T_out + GF_FT - 1) / GF_FT;
+    const int n_blocks = std::max(p.T_out, 2) - 2 + 1;
+    *n_frame = (size_t)p.n_passes * ((n_blocks + GF_BLOCKS_PER_CTA - 1) / GF_BLOCKS_PER_CTA);
+    *n_fir = 8;
+}
+
+static int gf_validate(const GooferBatch *b)
+{
+    if (!b || b->n_notes < 0 || b->n_sources < 0 || (b->n_notes && !b->notes) || (b->n_sources && !b->sources)) {
+        gf_set_error("invalid batch descriptor (NULL or negative field)");
+        return GOOFER_ERR_INVALID;
+    }
+    return GOOFER_OK;
+}
+
+static int gf_make_plans(const GooferBatch *b, std::vector<GfNotePlan> &plans)
+{
+    plans.resize(b->n_notes);
+    int bad = 0, first_bad = -1, sr = 0;
+    for (int i = 0; i < b->n_notes; ++i) {
+        if (gf_plan_note(b, i, &plans[i]) != 0) { gf_set_error("note %d: pitch-bend range outside the bend buffer", i); return GOOFER_ERR_INVALID; }
+        if (plans[i].status != GOOFER_NOTE_OK) { ++bad; if (first_bad < 0) first_bad = i; continue; }
+        if (sr == 0) sr = plans[i].sr;
+        if (plans[i].sr != sr) { gf_set_error("note %d: mixed sample rates in one batch (%d vs %d)", i, plans[i].sr, sr); return GOOFER_ERR_INVALID; }
+    }
+    if (bad) {
+        gf_set_error("%d note(s) cannot be rendered; first: note %d status %d (see goofer_plan_batch)", bad, first_bad, plans[first_bad].status);
+        return GOOFER_ERR_NOTE;
+    }
+    return GOOFER_OK;
+}
+
+extern "C" size_t goofer_workspace_bytes(const GooferBatch *b, int32_t notes_per_wave)
+{
+    if (gf_validate(b) != GOOFER_OK) return 0;
+    std::vector<GfNotePlan> plans;
+    if (gf_make_plans(b, plans) != GOOFER_OK) return 0;
+    if (notes_per_wave <= 0) notes_per_wave = 2048;
+    size_t best = 0;
+    for (int i0 = 0; i0 < b->n_notes; i0 += notes_per_wave) {
+        const int i1 = std::min(b->n_notes, i0 + notes_per_wave);
+        size_t tot = 0, np = 0, ne = 0, nf = 0, nfir = 0;
+        for (int i = i0; i < i1; ++i) {
+            tot += gf_note_bytes(plans[i]);
+            size_t a, c, d;
+            gf_note_work_counts(plans[i], &a, &c, &d);
+            ne += a; nf += c; nfir += d; np += plans[i].n_passes;
+        }
+        tot += gf_wave_meta_bytes(i1 - i0, np, ne, nf, nfir);
+        best = std::max(best, tot);
+    }
+    return gf_sources_bytes(b) + best + 4096;
+}
+
+// ------------------------------------------------------------------------------------------------
+// one wave
+// ------------------------------------------------------------------------------------------------
+struct WaveHost {
+    std::vector<GfNotePlan> plans;
+    std::vector<GfNoteDev> notes;
+    std::vector<GfPassDev> passes;
+    std::vector<int2> env_work;
+    std::vector<int4> frame_work;
+    std::vector<GfFirJob> fir;
+    std::vector<GfOnepoleJob> op_jobs;
+};
+
+template <typename T>
+static int gf_upload(Bump &bp, const std::vector<T> &v, T **dptr, cudaStream_t st)
+{
+    *dptr = bp.arr<T>(std::max<size_t>(v.size(), 1));
+    if (!v.empty()) GF_CUDA(cudaMemcpyAsync(*dptr, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice, st));
+    return GOOFER_OK;
+}
+
+int gf_post_fx(const WaveHost &wh, const GfNotePlan *d_plans, const GfNoteDev *d_notes, const GfPassDev *d_passes,
+               GfPassScal *d_scal, Bump &bp, int sr, int max_n, cudaStream_t st, int64_t *launches);
+int gf_growl(const WaveHost &wh, const GfNotePlan *d_plans, const GfNoteDev *d_notes, const GfPassDev *d_passes,
+             GfPassScal *d_scal, int max_n, cudaStream_t st, int64_t *launches);
+int gf_pitch_dyn(const WaveHost &wh, const GfNotePlan *d_plans, const GfNoteDev *d_notes, const float *bend, Bump &bp,
+                 int max_n, cudaStream_t st, int64_t *launches);
+
+static int gf_render_wave(const GooferBatch *b, const std::vector<GfNotePlan> &all, int i0, int i1, const GfSourceDev *d_srcs,
+                          Bump bp /* by value: wave region restarts every wave */, cudaStream_t st)
+{
+    WaveHost wh;
+    const int nn = i1 - i0;
+    wh.plans.assign(all.begin() + i0, all.begin() + i1);
+    wh.notes.resize(nn);
+    int sr = wh.plans[0].sr;
+    int max_n = 0;
+    size_t n_pass = 0;
+    for (int i = 0; i < nn; ++i) n_pass += wh.plans[i].n_passes;
+    wh.passes.resize(n_pass);
+    size_t pi = 0;
+    for (int i = 0; i < nn; ++i) {
+        const GfNotePlan &p = wh.plans[i];
+        max_n = std::max(max_n, p.n_total);
+        gf_carve_note(p, bp, &wh.notes[i], &wh.passes[pi], false);
+        GfNoteDev &nd = wh.notes[i];
+        nd.pass0 = (int)pi;
+        nd.out = b->out + p.out_off;
+        if (b->tap_harm && b->tap_uv && b->tap_bre) {
+            nd.tap_harm = b->tap_harm + p.out_off; nd.tap_uv = b->tap_uv + p.out_off; nd.tap_bre = b->tap_bre + p.out_off;
+        }
+        for (int k = 0; k < p.n_passes; ++k) {
+            GfPassDev &q = wh.passes[pi + k];
+            q.note = i;
+            const int slot = q.kind;                      // phi slot == pass kind (0 main, 1 su, 2 sj, 3 sa)
+            q.phi = b->phi + p.phi_off[slot];
+        }
+        // work lists
+        const int tiles = (p.T_out + GF_FT - 1) / GF_FT;
+        for (int t = 0; t < tiles; ++t) wh.env_work.push_back(make_int2(i, t));
+        const int n_blocks = std::max(p.T_out, 2) - 2 + 1;
+        for (int k = 0; k < p.n_passes; ++k)
+            for (int bb = 0; bb < n_blocks; bb += GF_BLOCKS_PER_CTA)
+                wh.frame_work.push_back(make_int4((int)(pi + k), 2 + bb, std::min(GF_BLOCKS_PER_CTA, n_blocks - bb), 0));
+        // FIR jobs (Gaussian smoothing along time)
+        {
+            GfFirJob j;
+            std::memset(&j, 0, sizeof(j));
+            j.in = nd.vm; j.in_f64 = 0; j.in_stride = 4; j.n = (p.n_total + 3) / 4; j.out = nd.ms_short; j.out_f64 = 0;
+            j.sigma = 25.0;                                // max(1, 100 / 4)   GOOFER.py:562
+            wh.fir.push_back(j);
+            if (p.vol_jitter || p.sd > 0) {
+                std::memset(&j, 0, sizeof(j));
+                j.in = nd.vm; j.in_stride = 1; j.n = p.n_total; j.sigma = 20.0;
+                if (p.vol_jitter) { j.out = nd.vjm; wh.fir.push_back(j); }          // GOOFER.py:1189
+                if (p.sd > 0) { j.out = nd.sdm; wh.fir.push_back(j); }               // SillySampler.py:1109
+            }
+            if (p.f0_jitter) {
+                std::memset(&j, 0, sizeof(j));
+                j.in = b->normals + p.nrm_off[0]; j.in_f64 = 1; j.in_stride = 1; j.n = p.n_total; j.out = nd.z_sh; j.out_f64 = 1;
+                j.sigma = (double)sr / (100.0 * 6);        // f0_jitter_speed = 100   GOOFER.py:667
+                j.maxabs = nd.noteScal + GF_NS_SHMAX;
+                wh.fir.push_back(j);
+            }
+            if (p.vol_jitter) {
+                for (int s = 0; s < 2; ++s) {
+                    std::memset(&j, 0, sizeof(j));
+                    j.in = b->normals + p.nrm_off[1 + s]; j.in_f64 = 1; j.in_stride = 1; j.n = p.n_total;
+                    j.out = s ? nd.z_srb : nd.z_srh; j.out_f64 = 1;
+                    j.sigma = (double)sr / (150.0 * 6);    // volume_jitter_speed = 150   GOOFER.py:654
+                    j.maxabs = nd.noteScal + (s ? GF_NS_SRBMAX : GF_NS_SRHMAX);
+                    wh.fir.push_back(j);
+                }
+            }
+        }
+        pi += p.n_passes;
+    }
+    // clear the per-note scalars in one go: they were carved from the wave region, zero the region's
+    // scalar blocks individually (small)
+    GfNotePlan *d_plans; GfNoteDev *d_notes; GfPassDev *d_passes; int2 *d_envw; int4 *d_framew; GfFirJob *d_fir;
+    int rc;
+    if ((rc = gf_upload(bp, wh.plans, &d_plans, st)) != GOOFER_OK) return rc;
+    if ((rc = gf_upload(bp, wh.notes, &d_notes, st)) != GOOFER_OK) return rc;
+    if ((rc = gf_upload(bp, wh.passes, &d_passes, st)) != GOOFER_OK) return rc;
+    if ((rc = gf_upload(bp, wh.env_work, &d_envw, st)) != GOOFER_OK) return rc;
+    if ((rc = gf_upload(bp, wh.frame_work, &d_framew, st)) != GOOFER_OK) return rc;
+    if ((rc = gf_upload(bp, wh.fir, &d_fir, st)) != GOOFER_OK) return rc;
+    GfPassScal *d_scal = bp.arr<GfPassScal>(n_pass);
+    if (bp.off > bp.cap) { gf_set_error("internal: wave overflows the workspace (%zu > %zu)", bp.off, bp.cap); return GOOFER_ERR_WORKSPACE; }
+    GF_CUDA(cudaMemsetAsync(d_scal, 0, n_pass * sizeof(GfPassScal), st));
+    for (int i = 0; i < nn; ++i) GF_CUDA(cudaMemsetAsync(wh.notes[i].noteScal, 0, GF_NS_COUNT * sizeof(double), st));
+
+    int64_t &L = g_stats.kernel_launches;
+    gf_launch_tracks(d_plans, d_notes, d_srcs, nn, st); ++L;
+    gf_launch_mask(d_plans, d_notes, d_srcs, nn, max_n, st); ++L;
+    {
+        double max_sigma = 25.0;
+        for (const GfFirJob &j : wh.fir) max_sigma = std::max(max_sigma, j.sigma);
+        gf_launch_fir(d_fir, (int)wh.fir.size(), max_n, max_sigma, st); ++L;
+    }
+    gf_launch_f0(d_plans, d_notes, d_passes, d_srcs, b->bend_cents, b->normals, nn, max_n, st); ++L;
+    gf_launch_walk(d_passes, d_scal, (int)n_pass, sr, st); ++L;
+    gf_launch_pulse(d_passes, d_scal, (int)n_pass, max_n, st); ++L;
+    if ((rc = gf_growl(wh, d_plans, d_notes, d_passes, d_scal, max_n, st, &L)) != GOOFER_OK) return rc;
+    gf_launch_env(d_envw, (int)wh.env_work.size(), d_plans, d_notes, d_srcs, st); ++L;
+    gf_launch_frame(d_framew, (int)wh.frame_work.size(), d_passes, d_scal, d_notes, d_plans, st); ++L;
+    gf_launch_peak(d_plans, d_notes, d_passes, d_scal, (int)n_pass, max_n, st); ++L;
+    if ((rc = gf_pitch_dyn(wh, d_plans, d_notes, b->bend_cents, bp, max_n, st, &L)) != GOOFER_OK) return rc;
+    if ((rc = gf_post_fx(wh, d_plans, d_notes, d_passes, d_scal, bp, sr, max_n, st, &L)) != GOOFER_OK) return rc;
+    gf_launch_mix(d_plans, d_notes, d_passes, d_scal, nn, max_n, st); ++L;
+    GF_CUDA(cudaGetLastError());
+    ++g_stats.waves;
+    return GOOFER_OK;
+}
+
+extern "C" int goofer_render_batch(const GooferBatch *b, void *workspace, size_t workspace_bytes, void *stream)
+{
+    int rc = gf_validate(b);
+    if (rc != GOOFER_OK) return rc;
+    g_stats.kernel_launches = 0; g_stats.waves = 0;
+    if (b->n_notes == 0) return GOOFER_OK;
+    if (!workspace || !b->out || !b->phi || !b->bend_cents) { gf_set_error("NULL workspace / out / phi / bend_cents"); return GOOFER_ERR_INVALID; }
+    std::vector<GfNotePlan> plans;
+    if ((rc = gf_make_plans(b, plans)) != GOOFER_OK) return rc;
+    for (int i = 0; i < b->n_notes; ++i) {
+        const GfNotePlan &p = plans[i];
+        for (int k = 0; k < p.n_passes; ++k) {
+            const int slot = p.pass_kind[k];
+            if (p.phi_off[slot] < 0 || p.phi_off[slot] + (int64_t)GF_NBINS * p.T_out > b->phi_total) {
+                gf_set_error("note %d: phi slot %d outside the phi buffer", i, slot);
+                return GOOFER_ERR_INVALID;
+            }
+        }
+        const int need[4] = {p.f0_jitter, p.vol_jitter, p.vol_jitter, p.sj > 0.0};
+        for (int k = 0; k < 4; ++k)
+            if (need[k] && (!b->normals || p.nrm_off[k] < 0 || p.nrm_off[k] + p.n_total > b->nrm_total)) {
+                gf_set_error("note %d: normal slot %d missing or outside the normals buffer", i, k);
+                return GOOFER_ERR_INVALID;
+            }
+        if (p.out_off < 0 || p.out_off + p.n_total > b->out_total) { gf_set_error("note %d: output range outside the out buffer", i); return GOOFER_ERR_INVALID; }
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    if ((rc = gf_tables_init(plans[0].sr)) != 0) return rc;
+
+    Bump bp{(char *)workspace, workspace_bytes, 0};
+    // ---- sources: decode / transpose once per call ----
+    std::vector<GfSourceDev> srcs(b->n_sources);
+    int max_T = 0;
+    for (int s = 0; s < b->n_sources; ++s) {
+        const GooferSource &g = b->sources[s];
+        GfSourceDev d;
+        std::memset(&d, 0, sizeof(d));
+        d.knots = g.knots_log_f16; d.hz_knots = g.hz_knots; d.dense = g.env_dense; d.mask = g.mask;
+        d.K = g.K; d.T = g.T; d.N = g.N;
+        for (int k = 0; k < 4; ++k) { d.formants[k] = g.formants[k]; d.formant_len[k] = g.formants[k] ? g.formant_len[k] : 0; }
+        if (g.T > 0) {
+            if (!d.knots && !d.dense) { gf_set_error("source %d has neither knots nor a dense envelope", s); return GOOFER_ERR_INVALID; }
+            if (d.knots && (g.K < 2 || !g.hz_knots)) { gf_set_error("source %d: knots need K >= 2 and hz_knots", s); return GOOFER_ERR_INVALID; }
+            d.envS = bp.arr<float>((size_t)g.T * GF_ENVS_LD);
+            max_T = std::max(max_T, g.T);
+        }
+        srcs[s] = d;
+    }
+    GfSourceDev *d_srcs = bp.arr<GfSourceDev>(std::max(1, b->n_sources));
+    if (bp.off > bp.cap) { gf_set_error("workspace too small for the source cache (%zu > %zu)", bp.off, bp.cap); return GOOFER_ERR_WORKSPACE; }
+    if (b->n_sources) GF_CUDA(cudaMemcpyAsync(d_srcs, srcs.data(), srcs.size() * sizeof(GfSourceDev), cudaMemcpyHostToDevice, st));
+    gf_launch_src_env(d_srcs, b->n_sources, max_T, st); ++g_stats.kernel_launches;
+
+    // ---- waves: greedy packing into what is left of the workspace ----
+    const size_t wave_cap = workspace_bytes - bp.off;
+    int i0 = 0;
+    while (i0 < b->n_notes) {
+        size_t tot = 0, np = 0, ne = 0, nf = 0, nfir = 0;
+        int i1 = i0;
+        while (i1 < b->n_notes) {
+            size_t a, c, d;
+            gf_note_work_counts(plans[i1], &a, &c, &d);
+            const size_t nb = gf_note_bytes(plans[i1]);
+            const size_t meta = gf_wave_meta_bytes(i1 - i0 + 1, np + plans[i1].n_passes, ne + a, nf + c, nfir + d);
+            if (tot + nb + meta + 4096 > wave_cap) break;
+            tot += nb; np += plans[i1].n_passes; ne += a; nf += c; nfir += d;
+            ++i1;
+        }
+        if (i1 == i0) {
+            gf_set_error("workspace too small: note %d alone needs %zu bytes, %zu available", i0, gf_note_bytes(plans[i0]), wave_cap);
+            return GOOFER_ERR_WORKSPACE;
+        }
+        Bump wave{(char *)workspace + bp.off, wave_cap, 0};
+        if ((rc = gf_render_wave(b, plans, i0, i1, d_srcs, wave, st)) != GOOFER_OK) return rc;
+        // host-side work lists are reused by the next wave only after this one was enqueued; the
+        // device regions are reused in stream order, so no extra synchronisation is needed
+        i0 = i1;
+    }
+    return GOOFER_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// stage-level entry points
+// ------------------------------------------------------------------------------------------------
+extern "C" int goofer_stft_batch(const float *x, int32_t n_sig, int32_t n, float *S_out, void *stream)
+{
+    if (!x || !S_out || n_sig < 0 || n < 2) { gf_set_error("goofer_stft_batch: invalid arguments"); return GOOFER_ERR_INVALID; }
+    int rc = gf_tables_init(44100);
+    if (rc) return rc;
+    if (n_sig == 0) return GOOFER_OK;
+    gf_launch_stft(x, n_sig, n, (float2 *)S_out, (cudaStream_t)stream);
+    GF_CUDA(cudaGetLastError());
+    return GOOFER_OK;
+}
+
+extern "C" int goofer_istft_batch(const float *S, int32_t n_sig, int32_t T, int32_t length, float *y_out, void *stream)
+{
+    if (!S || !y_out || n_sig < 0 || T < 1 || length < 0) { gf_set_error("goofer_istft_batch: invalid arguments"); return GOOFER_ERR_INVALID; }
+    int rc = gf_tables_init(44100);
+    if (rc) return rc;
+    if (n_sig == 0 || length == 0) return GOOFER_OK;
+    if (length < GF_HOP * (T - 1)) { gf_set_error("goofer_istft_batch: length %d shorter than hop * (T - 1) = %d is not supported", length, GF_HOP * (T - 1)); return GOOFER_ERR_INVALID; }
+    gf_launch_istft((const float2 *)S, n_sig, T, length, y_out, (cudaStream_t)stream);
+    GF_CUDA(cudaGetLastError());
+    return GOOFER_OK;
+}
+
+extern "C" size_t goofer_pulse_work_bytes(int32_t n_sig, int32_t n)
+{
+    if (n_sig < 0 || n < 0) return 0;
+    const size_t cap = (size_t)n / 8 + 64;
+    return (size_t)n_sig * (sizeof(GfPassDev) + sizeof(GfPassScal) + cap * sizeof(int4) + 512) + 1024;
+}
+
+extern "C" int goofer_pulse_train_batch(const float *f0, int32_t n_sig, int32_t n, int32_t sr, float *pulse_out, void *work, void *stream)
+{
+    if (!f0 || !pulse_out || !work || n_sig < 0 || n < 1 || sr <= 0) { gf_set_error("goofer_pulse_train_batch: invalid arguments"); return GOOFER_ERR_INVALID; }
+    if (n_sig == 0) return GOOFER_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    Bump bp{(char *)work, goofer_pulse_work_bytes(n_sig, n), 0};
+    std::vector<GfPassDev> ps(n_sig);
+    const int cap = n / 8 + 64;
+    for (int s = 0; s < n_sig; ++s) {
+        GfPassDev q;
+        std::memset(&q, 0, sizeof(q));
+        q.n_total = n; q.T_out = 1 + n / GF_HOP;
+        q.f0 = const_cast<float *>(f0) + (size_t)s * n;
+        q.pulse = pulse_out + (size_t)s * n;
+        q.onset_cap = cap;
+        q.onsets = bp.arr<int4>(cap);
+        ps[s] = q;
+    }
+    GfPassDev *d_ps = bp.arr<GfPassDev>(n_sig);
+    GfPassScal *d_sc = bp.arr<GfPassScal>(n_sig);
+    GF_CUDA(cudaMemcpyAsync(d_ps, ps.data(), ps.size() * sizeof(GfPassDev), cudaMemcpyHostToDevice, st));
+    GF_CUDA(cudaMemsetAsync(d_sc, 0, n_sig * sizeof(GfPassScal), st));
+    gf_launch_walk(d_ps, d_sc, n_sig, sr, st);
+    gf_launch_pulse(d_ps, d_sc, n_sig, n, st);
+    GF_CUDA(cudaGetLastError());
+    std::vector<GfPassScal> sc(n_sig);
+    GF_CUDA(cudaMemcpyAsync(sc.data(), d_sc, n_sig * sizeof(GfPassScal), cudaMemcpyDeviceToHost, st));
+    GF_CUDA(cudaStreamSynchronize(st));
+    for (int s = 0; s < n_sig; ++s)
+        if (sc[s].err) { gf_set_error("goofer_pulse_train_batch: signal %d has more than n/8+64 pulse onsets (mean f0 above sr/8)", s); return GOOFER_ERR_INVALID; }
+    return GOOFER_OK;
+}
+
+extern "C" int goofer_onepole_batch(const float *x, const float *f0, int32_t n_sig, int32_t n, int32_t sr, double cutoff_factor,
+                                    int32_t order, int32_t btype, float *y_out, void *stream)
+{
+    if (!x || !f0 || !y_out || n_sig < 0 || n < 0 || sr <= 0) { gf_set_error("goofer_onepole_batch: invalid arguments"); return GOOFER_ERR_INVALID; }
+    if (n_sig == 0 || n == 0) return GOOFER_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    float *alpha = nullptr;
+    GfOnepoleJob *d_jobs = nullptr;
+    GF_CUDA(cudaMallocAsync(&alpha, (size_t)n_sig * n * sizeof(float), st));
+    GF_CUDA(cudaMallocAsync(&d_jobs, (size_t)n_sig * sizeof(GfOnepoleJob), st));
+    std::vector<GfOnepoleJob> jobs(n_sig);
+    for (int s = 0; s < n_sig; ++s) {
+        GfOnepoleJob j;
+        std::memset(&j, 0, sizeof(j));
+        j.x = x + (size_t)s * n; j.f0 = f0 + (size_t)s * n; j.y = y_out + (size_t)s * n; j.alpha = alpha + (size_t)s * n;
+        j.n = n; j.order = order; j.highpass = btype != 0; j.smooth_f0 = 1; j.cutoff_factor = cutoff_factor; j.sr = sr;
+        jobs[s] = j;
+    }
+    GF_CUDA(cudaMemcpyAsync(d_jobs, jobs.data(), jobs.size() * sizeof(GfOnepoleJob), cudaMemcpyHostToDevice, st));
+    gf_launch_onepole(d_jobs, n_sig, st);
+    GF_CUDA(cudaGetLastError());
+    GF_CUDA(cudaFreeAsync(alpha, st));
+    GF_CUDA(cudaFreeAsync(d_jobs, st));
+    return GOOFER_OK;
+}

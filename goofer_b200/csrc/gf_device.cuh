@@ -1,0 +1,145 @@
+// gf_device.cuh -- device-side records, constant tables and small helpers shared by the kernels.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "gf_hd.h"
+#include "gf_plan.h"
+
+// ---- constant tables (GOOFER.py:12-46 get_cached_window/freqs/boost/brightness; :241-261 taps) ----
+struct GfTables {
+    float2 tw512[512];      // exp(-2 pi i m / 512)
+    float2 tw1024[513];     // exp(-2 pi i k / 1024)
+    float win[1024];        // sqrt(hanning(1024)) in f32          GOOFER.py:16
+    float win2[1024];       // win * win (f32)                      GOOFER.py:386
+    float boost[513];       // linspace(1, 100, 513) f32            GOOFER.py:33
+    float bright_h[513];    // +3 dB 2-3.5 kHz                      GOOFER.py:42
+    float bright_b[513];    // +20 dB 3.5-5 kHz                     GOOFER.py:43
+    float freq32[513];      // rfftfreq f32                         GOOFER.py:24
+    double g175[15];        // Gaussian sigma 1.75 (env4breath)     GOOFER.py:993
+    double g05[5];          // Gaussian sigma 0.5 (brightness blur) GOOFER.py:1143
+    int sr;
+};
+
+// the library is built as ONE translation unit (goofer_b200.cu includes every k_*.cu)
+__device__ GfTables d_tab;
+
+// one voicebank source as the kernels see it
+struct GfSourceDev {
+    const uint16_t *knots;  // (K, T) f16 or NULL
+    const float *hz_knots;  // (K,)
+    const float *dense;     // (513, T) f32 or NULL
+    const float *mask;      // (N,)
+    const double *formants[4];
+    float *envS;            // workspace: (T, GF_ENVS_LD) frame-major decoded envelope
+    int K, T, N;
+    int formant_len[4];
+};
+#define GF_ENVS_LD 520
+
+// per-(note, pass) buffers and device-written scalars
+struct GfPassDev {
+    int note;               // index of the note in the wave
+    int kind;               // GF_PASS_*
+    int n_total, T_out;
+    float *f0;              // (n_total,) f32 excitation f0 of this pass
+    float *pulse;           // (n_total,)
+    float *sub;             // sg layer, raw sum (main pass, add_subharm) or NULL
+    float *harm, *bre, *uv; // raw OLA streams (n_total,)
+    int4 *onsets;           // (i, T0, f32 bits of last_valid_f0, f32 bits of table max)
+    int onset_cap;
+    const float *phi;       // (513, T_out) f32
+    int mask_ones;          // sa pass: voicing mask == 1
+};
+
+struct GfPassScal {         // zeroed per wave, written by the device
+    unsigned int mag_bits;  // max(|S * hp| + 1e-8)            GOOFER.py:1121
+    unsigned int peak_bits; // max|harm + uv + bre|            GOOFER.py:1210
+    unsigned int submax_bits;
+    int n_onsets;
+    int max_T0;
+    int err;
+    int n_sub_events;
+    int pad;
+};
+
+struct GfNoteDev {
+    float *trk_canon;       // (4, T_env) f32
+    float *trk_clean;       // (4, T_env) f32 (fst) or NULL
+    float *envF, *envN;     // [tile][513][GF_FT] f32 : shaped envelope / noise envelope on the STFT frame grid
+    float *vm;              // (n_total,) f32(mask_new)
+    float *f0n;             // (n_total,) f32(f0_new): cutoff driver of the post-FX filters, or NULL
+    float *ms_short;        // (ceil(n/4),) f32: gaussian-smoothed decimated mask   GOOFER.py:556-563
+    double *z_sh;           // (n_total,) smoothed sh noise (f0 jitter) or NULL
+    double *z_srh, *z_srb;  // smoothed sr noise
+    float *vjm;             // gauss(vm, 20) (sr)
+    float *sdm;             // gauss(mask_new, 20) (sd)
+    float *dyn;             // pd gain curve
+    float *fx[4];           // scratch streams for the post-FX filters
+    double *noteScal;       // small per-note double scalars (maxima, rms)
+    float *out;             // (n_total,) final output
+    float *tap_harm, *tap_uv, *tap_bre;
+    int pass0;              // first entry of this note in the pass arrays
+};
+
+enum { GF_NS_SHMAX = 0, GF_NS_SRHMAX, GF_NS_SRBMAX, GF_NS_R0, GF_NS_R1, GF_NS_PDREF, GF_NS_COUNT = 8 };
+
+// ---- job records of the generic kernels ----
+struct GfFirJob {
+    const void *in;  int in_f64;  int in_stride;  int n;
+    void *out;       int out_f64;
+    double sigma;
+    double *maxabs;         // atomicMax target for max(|y| + 1e-6) (bits of a non-negative double) or NULL
+    int in_cast_f32;        // round the input to f32 first
+    int pad;
+};
+
+struct GfOnepoleJob {
+    const float *x;         // input (n,)
+    const float *f0;        // (n,) f32 cutoff driver (already 5-tap smoothed by the caller when needed) or NULL => const
+    float *y;               // output (n,) (may alias x)
+    float *alpha;           // scratch (n,)
+    int n;
+    int order;
+    int highpass;
+    int smooth_f0;          // apply the 5-tap edge-padded moving average first (SillySampler.py:107-113)
+    double cutoff_factor;
+    double f0_const;        // used when f0 == NULL
+    double f0_floor;        // max(f0, floor) applied to the driver first (su/sj: 120)  SillySampler.py:1052
+    int sr;
+    int pad;
+};
+
+// ---- small helpers ------------------------------------------------------------------------------
+__device__ __forceinline__ int gf_reflect(int q, int n)
+{
+    // numpy 'reflect' padding as a periodic extension (period 2(n-1)); n == 1 degenerates to 0
+    if (n <= 1) return 0;
+    const int per = 2 * (n - 1);
+    q %= per;
+    if (q < 0) q += per;
+    return q < n ? q : per - q;
+}
+
+__device__ __forceinline__ void gf_atomic_max_pos(unsigned int *addr, float v)
+{
+    atomicMax(addr, __float_as_uint(v));     // v >= 0: IEEE bit patterns order like unsigned ints
+}
+
+__device__ __forceinline__ float gf_warp_max(float v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+__device__ __forceinline__ double gf_warp_sum(double v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ float gf_warp_sumf(float v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}

@@ -1,0 +1,111 @@
+// gf_fft.cuh -- 1024-point real FFT / inverse real FFT as a 512-point complex radix-8 Stockham
+// transform plus the even/odd split, written per *thread* so that 64 threads cooperate on one
+// transform through shared memory (three radix-8 passes, two exchanges).
+//
+// Replaces numpy's pocketfft calls in /root/reference/GOOFER.py:370 (np.fft.rfft, float32 in =>
+// complex64 out on numpy >= 2) and GOOFER.py:400 (np.fft.irfft, n = 1024).
+//
+// Every function is __host__ __device__ so that tests/cpu_emul can drive the very same index
+// arithmetic with a serial loop over "threads" (test-only; the product never runs it on the CPU).
+#pragma once
+#include "gf_hd.h"
+
+#define GF_FFT_N 512            // complex points
+#define GF_FFT_THREADS 64       // threads per transform (one radix-8 butterfly each per pass)
+
+// padded index for the 512-float2 exchange buffer: keeps the stride-8 / stride-64 scatter of the
+// Stockham passes off a single bank pair
+GF_HD int gf_fpad(int i) { return i + (i >> 5); }
+#define GF_FFT_BUF (512 + 16)   // float2 elements per padded transform buffer
+
+GF_HD float2 gf_cmul(float2 a, float2 b) { return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
+GF_HD float2 gf_cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
+GF_HD float2 gf_csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
+GF_HD float2 gf_conj(float2 a) { return make_float2(a.x, -a.y); }
+
+// multiply by -i (forward) or +i (inverse)
+template <bool INV> GF_HD float2 gf_rot(float2 a) { return INV ? make_float2(-a.y, a.x) : make_float2(a.y, -a.x); }
+
+template <bool INV> GF_HD void gf_dft4(float2 b0, float2 b1, float2 b2, float2 b3, float2 &y0, float2 &y1, float2 &y2, float2 &y3)
+{
+    float2 c0 = gf_cadd(b0, b2), c2 = gf_csub(b0, b2), c1 = gf_cadd(b1, b3), c3 = gf_rot<INV>(gf_csub(b1, b3));
+    y0 = gf_cadd(c0, c1); y2 = gf_csub(c0, c1); y1 = gf_cadd(c2, c3); y3 = gf_csub(c2, c3);
+}
+
+// in-register 8-point DFT, natural order in and out
+template <bool INV> GF_HD void gf_dft8(float2 *v)
+{
+    const float h = 0.70710678118654752440f;
+    float2 a0 = gf_cadd(v[0], v[4]), a4 = gf_csub(v[0], v[4]);
+    float2 a1 = gf_cadd(v[1], v[5]), a5 = gf_csub(v[1], v[5]);
+    float2 a2 = gf_cadd(v[2], v[6]), a6 = gf_csub(v[2], v[6]);
+    float2 a3 = gf_cadd(v[3], v[7]), a7 = gf_csub(v[3], v[7]);
+    if (INV) {
+        a5 = make_float2((a5.x - a5.y) * h, (a5.x + a5.y) * h);
+        a7 = make_float2(-(a7.x + a7.y) * h, (a7.x - a7.y) * h);
+    } else {
+        a5 = make_float2((a5.x + a5.y) * h, (a5.y - a5.x) * h);
+        a7 = make_float2((a7.y - a7.x) * h, -(a7.x + a7.y) * h);
+    }
+    a6 = gf_rot<INV>(a6);
+    gf_dft4<INV>(a0, a1, a2, a3, v[0], v[2], v[4], v[6]);
+    gf_dft4<INV>(a4, a5, a6, a7, v[1], v[3], v[5], v[7]);
+}
+
+// One Stockham radix-8 pass of the 512-point transform for thread j (0..63).
+//   NS = 1, 8, 64 for the three passes.  tw512[m] = exp(-2 pi i m / 512), m < 512.
+// Reads buf[j + 64 r]; the caller must barrier between gf_fft_pass_load and gf_fft_pass_store when
+// running in place.
+template <bool INV, int NS> GF_HD void gf_fft_pass_load(int j, const float2 *buf, const float2 *tw512, float2 *v)
+{
+#pragma unroll
+    for (int r = 0; r < 8; ++r) v[r] = buf[gf_fpad(j + 64 * r)];
+    if (NS > 1) {
+        const int k = j & (NS - 1);
+        const int step = k * (64 / NS);          // twiddle exponent for r = 1 (in 512ths of a turn)
+#pragma unroll
+        for (int r = 1; r < 8; ++r) {
+            float2 w = tw512[r * step];
+            if (INV) w.y = -w.y;
+            v[r] = gf_cmul(v[r], w);
+        }
+    }
+    gf_dft8<INV>(v);
+}
+
+template <int NS> GF_HD void gf_fft_pass_store(int j, float2 *buf, const float2 *v)
+{
+    const int k = j & (NS - 1);
+    const int j0 = ((j - k) << 3) + k;
+#pragma unroll
+    for (int r = 0; r < 8; ++r) buf[gf_fpad(j0 + r * NS)] = v[r];
+}
+
+// ---- even/odd split --------------------------------------------------------------------------
+// tw1024[k] = exp(-2 pi i k / 1024), k <= 512.
+//
+// Forward: z[n] = x[2n] + i x[2n+1], Z = FFT512(z).  For the bin pair (k, 512 - k), 0 <= k <= 256:
+GF_HD void gf_rfft_split(float2 Zk, float2 Zm /* Z[(512-k) & 511] */, float2 w /* tw1024[k] */, float2 &Xk, float2 &Xm)
+{
+    // E = (Zk + conj Zm)/2, O = -i (Zk - conj Zm)/2 ; X[k] = E + w O ; X[512-k] = conj(E - w O)
+    float2 E = make_float2(0.5f * (Zk.x + Zm.x), 0.5f * (Zk.y - Zm.y));
+    float2 D = make_float2(0.5f * (Zk.x - Zm.x), 0.5f * (Zk.y + Zm.y));
+    float2 O = make_float2(D.y, -D.x);
+    float2 wO = gf_cmul(w, O);
+    Xk = gf_cadd(E, wO);
+    Xm = gf_conj(gf_csub(E, wO));
+}
+
+// Inverse: from the Hermitian half-spectrum pair (X[k], X[512-k]) build Z[k], Z[512-k] such that
+// IFFT512(Z) (unnormalised) * (1/512) = x[2n] + i x[2n+1] with numpy irfft scaling (1/1024 overall).
+// The imaginary parts of X[0] and X[512] must be zeroed by the caller (pocketfft c2r ignores them).
+GF_HD void gf_irfft_merge(float2 Xk, float2 Xm, float2 w /* tw1024[k] */, float2 &Zk, float2 &Zm)
+{
+    // E = (Xk + conj Xm)/2 ; O = conj(w) (Xk - conj Xm)/2 ; Z[k] = E + i O ; Z[512-k] = conj(E - i O) ... (k != 512-k)
+    float2 E = make_float2(0.5f * (Xk.x + Xm.x), 0.5f * (Xk.y - Xm.y));
+    float2 D = make_float2(0.5f * (Xk.x - Xm.x), 0.5f * (Xk.y + Xm.y));
+    float2 O = gf_cmul(gf_conj(w), D);
+    float2 iO = make_float2(-O.y, O.x);
+    Zk = gf_cadd(E, iO);
+    Zm = gf_conj(gf_csub(E, iO));
+}

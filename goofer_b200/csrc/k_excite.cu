@@ -1,0 +1,268 @@
+// k_excite.cu -- excitation: target f0 curve, bit-faithful glottal pulse onsets, LF pulse rendering.
+//
+//   gf_f0_kernel      target pitch + vocal-fry f0 + per-pass f0      SillySampler.py:836-855, 884-934,
+//                     1038-1041 (su), 1062-1067 (sj); GOOFER.py:989, 1069-1071 (sh jitter)
+//   gf_walk_kernel    pulse_train_numba's sequential fp64 phase walk GOOFER.py:479-493, 534-554
+//   gf_pulse_kernel   LF pulse tables + overlap-add as a gather       GOOFER.py:495-552
+//
+// The onset walk is the one place where rounding order is part of the result (SURVEY.md section 0
+// fact 4): the phase is accumulated sample by sample in fp64, left to right, exactly like the
+// reference; only the crossing *detection* is done in parallel (floor of the running totals).
+#include "gf_device.cuh"
+#include "gf_maps.cuh"
+
+#define GF_PI_D 3.141592653589793
+
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ double gf_midi_at(const GfNotePlan &pl, const float *__restrict__ bend, int i)
+{
+    // SillySampler.py:836-853; interp1d == np.interp here because the query is clipped to the knots
+    const double add = (double)pl.pitch_midi;
+    const double tadd = pl.t_cents ? ((double)pl.t_cents / 100.0) : 0.0;
+    auto semi = [&](int k) {
+        double s = (double)bend[k] / 100.0 + add;
+        if (pl.t_cents) s = s + tadd;
+        return s;
+    };
+    if (pl.bend_len == 1) return semi(0);
+    const double dt = 60.0 / (pl.tempo * 96.0);
+    const int last = pl.bend_len - 1;
+    double x = (double)i / (double)pl.sr;
+    const double xl = (double)last * dt;
+    x = fmin(fmax(x, 0.0), xl);
+    if (x >= xl) return semi(last);
+    int j = (int)(x / dt);
+    if (j > last - 1) j = last - 1;
+    while (j > 0 && (double)j * dt > x) --j;
+    while (j < last - 1 && (double)(j + 1) * dt <= x) ++j;
+    const double x0 = (double)j * dt, x1 = (double)(j + 1) * dt;
+    const double y0 = semi(j), y1 = semi(j + 1);
+    if (x0 == x) return y0;
+    const double slope = __ddiv_rn(y1 - y0, x1 - x0);
+    return __dadd_rn(__dmul_rn(slope, x - x0), y0);
+}
+
+__global__ void __launch_bounds__(256)
+gf_f0_kernel(const GfNotePlan *__restrict__ plans, const GfNoteDev *__restrict__ notes, const GfPassDev *__restrict__ passes,
+             const GfSourceDev *__restrict__ srcs, const float *__restrict__ bend_all, const double *__restrict__ normals)
+{
+    const GfNotePlan &pl = plans[blockIdx.y];
+    const GfNoteDev nd = notes[blockIdx.y];
+    const float *mask_src = srcs[pl.src].mask;
+    const float *bend = bend_all + pl.bend_off;
+    const int n = pl.n_total;
+    double sh_scale = 0.0;
+    if (pl.f0_jitter) sh_scale = nd.noteScal[GF_NS_SHMAX];
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const double m = gf_mask_new(pl, mask_src, i);
+        const double midi = gf_midi_at(pl, bend, i);
+        const double hz = 440.0 * pow(2.0, (midi - 69.0) / 12.0);
+        double f0 = m * hz;
+        // ---- vocal fry f0 override (SillySampler.py:890-934) ----
+        if (pl.fry_L > 0) {
+            const double base = pl.vh * (m > 0.0 ? 1.0 : 0.0);
+            const int L = pl.fry_L, glide = pl.fry_glide, cst = pl.fry_const;
+            if (pl.vf > 0) {
+                if (i < cst) f0 = base;
+                else if (i < L) { const double w = gf_lin01(i - cst, glide); f0 = (1.0 - w) * base + w * f0; }
+            } else {
+                const int s = n - L;
+                if (i >= s + glide) f0 = base;
+                else if (i >= s) { const double w = gf_lin10(i - s, glide); f0 = (1.0 - w) * base + w * f0; }
+            }
+        }
+        if (nd.f0n) nd.f0n[i] = (float)f0;
+        for (int p = 0; p < pl.n_passes; ++p) {
+            const GfPassDev &ps = passes[nd.pass0 + p];
+            float v;
+            switch (ps.kind) {
+            case GF_PASS_MAIN: {
+                v = (float)f0;
+                if (pl.f0_jitter) {
+                    // GOOFER.py:666-669, 1070-1071: f0 (f32) *= 1 + (jitter - 1) * mask, evaluated in fp64
+                    const double z = nd.z_sh[i] / sh_scale;
+                    const double jit = 1.0 + z * pl.f0_jitter_strength;
+                    v = (float)((double)v * (1.0 + ((jit - 1.0) * (double)(float)m)));
+                }
+                break;
+            }
+            case GF_PASS_SU: v = (float)(f0 * 0.5); break;
+            case GF_PASS_SJ: {
+                const double z = 0.0 + (pl.sj * pl.sj) * normals[pl.nrm_off[3] + i];     // SillySampler.py:1064
+                v = (float)(f0 * (0.5 * pow(2.0, z)));
+                break;
+            }
+            default: v = (float)f0; break;
+            }
+            ps.f0[i] = v;
+        }
+    }
+}
+
+void gf_launch_f0(const GfNotePlan *plans, const GfNoteDev *notes, const GfPassDev *passes, const GfSourceDev *srcs,
+                  const float *bend, const double *normals, int n_notes, int max_n, cudaStream_t st)
+{
+    if (n_notes <= 0) return;
+    dim3 grid(min(64, (max_n + 255) / 256), n_notes);
+    gf_f0_kernel<<<grid, 256, 0, st>>>(plans, notes, passes, srcs, bend, normals);
+}
+
+// ------------------------------------------------------------------------------------------------
+// LF pulse sample (GOOFER.py:507-522), before the per-table max normalisation
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float gf_lf_value(int j, double T, int T0)
+{
+    const double Ra = 0.02, Rg = 1.7, Rk = 0.8;
+    const double Tp = Ra * T;
+    const double Tc = __dadd_rn(Tp, __dmul_rn(Rk, T - Tp));
+    const double ti = __ddiv_rn(__dmul_rn((double)j, T), (double)T0);
+    double v;
+    if (ti < Tp) {
+        const double s = sin(__ddiv_rn(__dmul_rn(GF_PI_D, ti), __dadd_rn(__dmul_rn(2.0, Tp), 1e-12)));
+        v = s * s;
+    } else if (ti < Tc) {
+        const double tau = __ddiv_rn(ti - Tp, __dadd_rn(Tc - Tp, 1e-12));
+        v = exp(-Rg * tau) * cos(GF_PI_D * tau / 2.0);
+    } else v = 0.0;
+    return (float)v;
+}
+
+// max |table| : the rise is increasing and the fall decreasing, so the peak sits at the transition
+__device__ __forceinline__ float gf_lf_table_max(double T, int T0)
+{
+    int jc = (int)(0.02 * (double)T0);
+    float m = 0.0f;
+    for (int j = jc - 1; j <= jc + 2; ++j)
+        if (j >= 0 && j < T0) m = fmaxf(m, fabsf(gf_lf_value(j, T, T0)));
+    return m;
+}
+
+#define GF_WALK_WARPS 4
+__global__ void __launch_bounds__(32 * GF_WALK_WARPS)
+gf_walk_kernel(const GfPassDev *__restrict__ passes, GfPassScal *scal, int n_pass, int sr_i)
+{
+    __shared__ double s_inc[GF_WALK_WARPS][32];
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int pi = blockIdx.x * GF_WALK_WARPS + w;
+    if (pi >= n_pass) return;
+    const GfPassDev ps = passes[pi];
+    const int n = ps.n_total;
+    const double sr = (double)sr_i;
+    double total = 0.0;
+    long long fired = 0;                // next_k - 1
+    float lv_carry = 160.0f;            // last_valid_f0 (GOOFER.py:477)
+    int count = 0, max_T0 = 0;
+    for (int base = 0; base < n; base += 32) {
+        const int i = base + lane;
+        const float f = (i < n) ? ps.f0[i] : 0.0f;
+        s_inc[w][lane] = (i < n) ? __ddiv_rn((double)f, sr) : 0.0;
+        __syncwarp();
+        // sequential left-to-right fp64 accumulation (every lane runs the same chain; lane k keeps total_k)
+        double run = total, mine = 0.0;
+#pragma unroll
+        for (int k = 0; k < 32; ++k) {
+            run = __dadd_rn(run, s_inc[w][k]);
+            if (k == lane) mine = run;
+        }
+        total = run;
+        __syncwarp();
+        // pulses fired up to and including sample i = running max of floor(total)
+        long long m = (long long)floor(mine);
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const long long v = __shfl_up_sync(0xffffffffu, m, o);
+            if (lane >= o) m = max(m, v);
+        }
+        m = max(m, fired);
+        long long prev = __shfl_up_sync(0xffffffffu, m, 1);
+        if (lane == 0) prev = fired;
+        const int cnt = (i < n) ? (int)(m - prev) : 0;
+        fired = __shfl_sync(0xffffffffu, m, 31);
+        // last f0 > 1e-6 at or before sample i
+        const bool valid = (i < n) && ((double)f > 1e-6);
+        const unsigned bal = __ballot_sync(0xffffffffu, valid);
+        const unsigned below = bal & ((2u << lane) - 1u);
+        const float cand = __shfl_sync(0xffffffffu, f, below ? (31 - __clz(below)) : 0);
+        const float lvf = below ? cand : lv_carry;
+        const float newc = __shfl_sync(0xffffffffu, f, bal ? (31 - __clz(bal)) : 0);
+        if (bal) lv_carry = newc;
+        int T0 = 0;
+        float tmax = 1.0f;
+        double lv = (double)lvf;
+        if (cnt > 0) {
+            if (!(lv > 1e-6)) lv = 1e-6;
+            const double T = __ddiv_rn(1.0, lv);
+            T0 = (int)rint(__dmul_rn(sr, T));
+            T0 = T0 < 3 ? 3 : (T0 > 8192 ? 8192 : T0);
+            tmax = gf_lf_table_max(T, T0);
+        }
+        int incl = cnt;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int v = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += v;
+        }
+        const int tile_total = __shfl_sync(0xffffffffu, incl, 31);
+        int slot = count + incl - cnt;
+        for (int c = 0; c < cnt; ++c, ++slot)
+            if (slot < ps.onset_cap) ps.onsets[slot] = make_int4(i, T0, __float_as_int((float)lv), __float_as_int(tmax));
+        count += tile_total;
+        int tm = T0;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) tm = max(tm, __shfl_xor_sync(0xffffffffu, tm, o));
+        max_T0 = max(max_T0, tm);
+    }
+    if (lane == 0) {
+        scal[pi].n_onsets = min(count, ps.onset_cap);
+        scal[pi].max_T0 = max_T0;
+        if (count > ps.onset_cap) scal[pi].err = 1;
+    }
+}
+
+void gf_launch_walk(const GfPassDev *passes, GfPassScal *scal, int n_pass, int sr, cudaStream_t st)
+{
+    if (n_pass <= 0) return;
+    gf_walk_kernel<<<(n_pass + GF_WALK_WARPS - 1) / GF_WALK_WARPS, 32 * GF_WALK_WARPS, 0, st>>>(passes, scal, n_pass, sr);
+}
+
+// ------------------------------------------------------------------------------------------------
+// pulse[i] = sum over the onsets whose table covers i, in onset order (f32 adds)  GOOFER.py:542-552
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+gf_pulse_kernel(const GfPassDev *__restrict__ passes, const GfPassScal *__restrict__ scal)
+{
+    const GfPassDev ps = passes[blockIdx.y];
+    const int n = ps.n_total;
+    const int count = scal[blockIdx.y].n_onsets;
+    const int max_T0 = scal[blockIdx.y].max_T0;
+    const int4 *__restrict__ on = ps.onsets;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        int lo = 0, hi = count;                 // number of onsets with index <= i
+        while (lo < hi) { const int mid = (lo + hi) >> 1; if (on[mid].x <= i) lo = mid + 1; else hi = mid; }
+        const int last = lo - 1;
+        float acc = 0.0f;
+        if (last >= 0) {
+            int e0 = last;
+            while (e0 > 0 && i - on[e0 - 1].x < max_T0) --e0;
+            for (int e = e0; e <= last; ++e) {
+                const int4 o = on[e];
+                const int d = i - o.x;
+                if (d < o.y) {
+                    const double T = __ddiv_rn(1.0, (double)__int_as_float(o.z));
+                    const float raw = gf_lf_value(d, T, o.y);
+                    const float mx = __int_as_float(o.w);
+                    const float val = (mx > 0.0f) ? (float)((double)raw / (double)mx) : raw;
+                    acc += val;
+                }
+            }
+        }
+        ps.pulse[i] = acc;
+    }
+}
+
+void gf_launch_pulse(const GfPassDev *passes, const GfPassScal *scal, int n_pass, int max_n, cudaStream_t st)
+{
+    if (n_pass <= 0) return;
+    dim3 grid(min(64, (max_n + 255) / 256), n_pass);
+    gf_pulse_kernel<<<grid, 256, 0, st>>>(passes, scal);
+}

@@ -1,0 +1,246 @@
+// k_frame.cu -- the fused frame kernel: STFT of the excitation -> spectral shaping -> three inverse
+// FFTs -> windowed overlap-add, without the spectrogram ever leaving the SM.
+//
+// Replaces, per gf.synthesize call (/root/reference/GOOFER.py):
+//   :1099        stft(pulse)                                   (:355-370)
+//   :1101-1114   sigmoid high-pass at the frame f0
+//   :1115-1129   env frame match, S / max|S| * env * boost     (1/max|S| is a scalar: applied later)
+//   :1131-1144   voiced frames: brightness curve + 5-tap Gaussian along frequency
+//   :1146        istft -> harmonic                             (:392-413, :372-390)
+//   :1148-1176   U = exp(i phi); S_uv = U * env4breath; S_breath = S_uv * hp; brightness; 2 x istft
+// One CTA owns a run of output hop blocks of one (note, pass); it recomputes the 3 frames of halo.
+#include "gf_frame.cuh"
+
+#define GF_RND 4                      // frames per round (= FFT lanes)
+#define GF_FRAME_THREADS (64 * GF_RND)
+#define GF_STAG_LD 516
+
+struct GfFrameSmem {
+    GfFrameTables tab;
+    float2 z[3][GF_RND][GF_FFT_BUF];          // [0] harmonic, [1] breath, [2] unvoiced (also the forward buffer)
+    float2 stag[2][GF_RND][GF_STAG_LD];       // pre-blur harmonic / breath spectra of voiced frames
+    float ring[3][GF_RING];
+    float f0fr[GF_RND];
+    int voiced[GF_RND];
+    float red[GF_FRAME_THREADS / 32];
+};
+
+size_t gf_frame_smem_bytes() { return sizeof(GfFrameSmem); }
+int gf_frame_threads() { return GF_FRAME_THREADS; }
+
+__device__ __forceinline__ float gf_hp_sigmoid(float f, float f0)
+{
+    // GOOFER.py:1111  1 / (1 + exp(-clip((f - f0) / 5, -60, 60)))  (all f32)
+    float a = (f - f0) / 5.0f;
+    a = fminf(fmaxf(a, -60.0f), 60.0f);
+    return 1.0f / (1.0f + expf(-a));
+}
+
+__device__ __forceinline__ float2 gf_gauss5(const float2 *row, int k, const float *g)
+{
+    // numpy 'reflect' at both ends of the 513-bin axis; GOOFER.py:241-261 with sigma 0.5
+    float2 acc = make_float2(0.f, 0.f);
+#pragma unroll
+    for (int j = 0; j < 5; ++j) {
+        int q = k + j - 2;
+        q = q < 0 ? -q : (q > 512 ? 1024 - q : q);
+        const float2 x = row[q];
+        acc.x = fmaf(g[j], x.x, acc.x);
+        acc.y = fmaf(g[j], x.y, acc.y);
+    }
+    return acc;
+}
+
+// work item: x = pass index (into the wave's pass arrays), y = first owned block, z = block count
+__global__ void __launch_bounds__(GF_FRAME_THREADS)
+gf_frame_kernel(const int4 *__restrict__ work, const GfPassDev *__restrict__ passes, GfPassScal *scal,
+                const GfNoteDev *__restrict__ notes, const GfNotePlan *__restrict__ plans)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    GfFrameSmem &sm = *reinterpret_cast<GfFrameSmem *>(smem_raw);
+    const int4 wk = work[blockIdx.x];
+    const GfPassDev ps = passes[wk.x];
+    const GfNoteDev nd = notes[ps.note];
+    const GfNotePlan &pl = plans[ps.note];
+    const int n = ps.n_total, T = ps.T_out;
+    const int b0 = wk.y, nb = wk.z;
+    const int tid = threadIdx.x;
+
+    gf_stage_tables(&sm.tab);
+    for (int i = tid; i < 3 * GF_RING; i += blockDim.x) (&sm.ring[0][0])[i] = 0.0f;
+    float g5[5];
+#pragma unroll
+    for (int j = 0; j < 5; ++j) g5[j] = (float)d_tab.g05[j];
+
+    const int t_begin = max(0, b0 - 3), t_end = min(T - 1, b0 + nb - 1);
+    const int n_f0 = (n + GF_HOP - 1) / GF_HOP;          // len(f0[::256])
+    const float *pulse = ps.pulse;
+    const float *sub = ps.sub;
+    const float *vm = nd.vm;
+    double sub_scale = 0.0;
+    if (sub) {
+        const float mx = __uint_as_float(scal[wk.x].submax_bits);
+        sub_scale = ((double)mx > 1e-6) ? pl.subharm_weight / (double)mx : pl.subharm_weight;
+    }
+    float local_max = 0.0f;
+    __syncthreads();
+
+    for (int t0 = t_begin; t0 <= t_end; t0 += GF_RND) {
+        const int nf = min(GF_RND, t_end - t0 + 1);
+        // ---- 1. frame the excitation (pulse + growl layer) ----
+        if (sub) {
+            gf_load_frames(&sm.z[2][0][0], t0, nf, n, sm.tab.win, [&](int i) {
+                // GOOFER.py:724-736: sub *= mask; sub /= max; sub *= weight; pulse (f32) += sub (f64)
+                return (float)((double)pulse[i] + ((double)sub[i] * (double)vm[i]) * sub_scale);
+            });
+        } else {
+            gf_load_frames(&sm.z[2][0][0], t0, nf, n, sm.tab.win, [&](int i) { return pulse[i]; });
+        }
+        if (tid < nf) {
+            const int fi = min(t0 + tid, n_f0 - 1) * GF_HOP;      // f0[::hop] edge-padded   GOOFER.py:1104-1106
+            sm.f0fr[tid] = ps.f0[fi];
+            sm.voiced[tid] = ps.mask_ones ? 1 : (vm[fi] > 0.0f);  // GOOFER.py:1132-1136
+        }
+        __syncthreads();
+        // ---- 2. forward FFT ----
+        gf_cta_fft512<false>(&sm.z[2][0][0], nf, sm.tab.tw512);
+        // ---- 3. shaping, per bin pair (k, 512 - k) ----
+        for (int idx = tid; idx < nf * 256; idx += blockDim.x) {
+            const int k = idx / nf, f = idx - k * nf;
+            const int t = t0 + f;
+            const int km = 512 - k;
+            const float f0f = sm.f0fr[f];
+            const bool vo = sm.voiced[f] != 0;
+            float2 *zf = &sm.z[2][f][0];
+            const size_t tile = (size_t)(t / GF_FT) * (GF_NBINS * GF_FT) + (t % GF_FT);
+            const float *eF = nd.envF + tile, *eN = nd.envN + tile;
+            const float *ph = ps.phi + t;
+            const int nbin = (k == 0) ? 3 : 2;
+            float2 H[3], B[3], V[3];
+            int bins[3] = {k, km, 256};
+            float2 S[3];
+            {
+                const float2 Zk = zf[gf_fpad(k)], Zm = zf[gf_fpad(km & 511)];
+                gf_rfft_split(Zk, Zm, sm.tab.tw1024[k], S[0], S[1]);
+                if (k == 0) {
+                    const float2 Zq = zf[gf_fpad(256)];
+                    float2 dummy;
+                    gf_rfft_split(Zq, Zq, sm.tab.tw1024[256], S[2], dummy);
+                }
+            }
+#pragma unroll
+            for (int q = 0; q < 3; ++q) {
+                if (q < nbin) {
+                    const int bq = bins[q];
+                    const float hp = gf_hp_sigmoid(d_tab.freq32[bq], f0f);
+                    float2 s = make_float2(S[q].x * hp, S[q].y * hp);
+                    local_max = fmaxf(local_max, hypotf(s.x, s.y) + 1e-8f);
+                    const float ef = eF[(size_t)bq * GF_FT], en = eN[(size_t)bq * GF_FT];
+                    const float bo = d_tab.boost[bq];
+                    float2 h = make_float2(s.x * ef * bo, s.y * ef * bo);
+                    float sn, cs;
+                    sincosf(ph[(size_t)bq * T], &sn, &cs);
+                    float2 v = make_float2(cs * en, sn * en);
+                    float2 b = make_float2(v.x * hp, v.y * hp);
+                    if (vo) {
+                        const float bh = d_tab.bright_h[bq], bb = d_tab.bright_b[bq];
+                        h.x *= bh; h.y *= bh; b.x *= bb; b.y *= bb;
+                        sm.stag[0][f][bq] = h;
+                        sm.stag[1][f][bq] = b;
+                    }
+                    H[q] = h; B[q] = b; V[q] = v;
+                }
+            }
+            // pocketfft c2r ignores the imaginary parts of DC and Nyquist
+            if (k == 0) { V[0].y = 0.f; V[1].y = 0.f; H[0].y = 0.f; H[1].y = 0.f; B[0].y = 0.f; B[1].y = 0.f; }
+            float2 Zk, Zm;
+            gf_irfft_merge(V[0], V[1], sm.tab.tw1024[k], Zk, Zm);
+            zf[gf_fpad(k)] = Zk;
+            if (k != 0) zf[gf_fpad(km)] = Zm;
+            if (k == 0) {
+                gf_irfft_merge(V[2], V[2], sm.tab.tw1024[256], Zk, Zm);
+                zf[gf_fpad(256)] = Zk;
+            }
+            if (!vo) {
+                gf_irfft_merge(H[0], H[1], sm.tab.tw1024[k], Zk, Zm);
+                sm.z[0][f][gf_fpad(k)] = Zk;
+                if (k != 0) sm.z[0][f][gf_fpad(km)] = Zm;
+                gf_irfft_merge(B[0], B[1], sm.tab.tw1024[k], Zk, Zm);
+                sm.z[1][f][gf_fpad(k)] = Zk;
+                if (k != 0) sm.z[1][f][gf_fpad(km)] = Zm;
+                if (k == 0) {
+                    gf_irfft_merge(H[2], H[2], sm.tab.tw1024[256], Zk, Zm);
+                    sm.z[0][f][gf_fpad(256)] = Zk;
+                    gf_irfft_merge(B[2], B[2], sm.tab.tw1024[256], Zk, Zm);
+                    sm.z[1][f][gf_fpad(256)] = Zk;
+                }
+            }
+        }
+        __syncthreads();
+        // ---- 4. voiced frames: 5-tap Gaussian along frequency, then merge ----
+        for (int idx = tid; idx < nf * 256; idx += blockDim.x) {
+            const int k = idx / nf, f = idx - k * nf;
+            if (!sm.voiced[f]) continue;
+            const int km = 512 - k;
+#pragma unroll
+            for (int s = 0; s < 2; ++s) {
+                const float2 *row = &sm.stag[s][f][0];
+                float2 Xk = gf_gauss5(row, k, g5), Xm = gf_gauss5(row, km, g5);
+                if (k == 0) { Xk.y = 0.f; Xm.y = 0.f; }
+                float2 Zk, Zm;
+                gf_irfft_merge(Xk, Xm, sm.tab.tw1024[k], Zk, Zm);
+                sm.z[s][f][gf_fpad(k)] = Zk;
+                if (k != 0) sm.z[s][f][gf_fpad(km)] = Zm;
+                if (k == 0) {
+                    const float2 Xq = gf_gauss5(row, 256, g5);
+                    gf_irfft_merge(Xq, Xq, sm.tab.tw1024[256], Zk, Zm);
+                    sm.z[s][f][gf_fpad(256)] = Zk;
+                }
+            }
+        }
+        __syncthreads();
+        // ---- 5. inverse FFTs (stream-major: transform q = s * GF_RND + f) ----
+        if (nf == GF_RND) {
+            gf_cta_fft512<true>(&sm.z[0][0][0], 3 * GF_RND, sm.tab.tw512);
+        } else {
+            for (int s = 0; s < 3; ++s) gf_cta_fft512<true>(&sm.z[s][0][0], nf, sm.tab.tw512);
+        }
+        // ---- 6. overlap-add ----
+        for (int s = 0; s < 3; ++s) gf_ola_add(sm.ring[s], &sm.z[s][0][0], t0, nf, sm.tab.win);
+        __syncthreads();
+        // ---- 7. emit finished blocks ----
+        const int last_blk = (t0 + nf - 1 == T - 1) ? T : (t0 + nf - 1);
+        for (int b = t0; b <= last_blk; ++b) {
+            const bool own = (b >= b0 && b < b0 + nb && b >= 2);
+            gf_ola_emit(sm.ring[0], b, T, n, ps.harm, own);
+            gf_ola_emit(sm.ring[1], b, T, n, ps.bre, own);
+            gf_ola_emit(sm.ring[2], b, T, n, ps.uv, own);
+        }
+        __syncthreads();
+    }
+    // zero tail of istft: samples 256 (T - 1) .. n - 1     GOOFER.py:407-409
+    if (b0 + nb > T) {
+        for (int i = GF_HOP * (T - 1) + tid; i < n; i += blockDim.x) { ps.harm[i] = 0.f; ps.bre[i] = 0.f; ps.uv[i] = 0.f; }
+    }
+    // max(|S| + 1e-8) over the whole (note, pass)          GOOFER.py:1121
+    local_max = gf_warp_max(local_max);
+    if ((tid & 31) == 0) sm.red[tid >> 5] = local_max;
+    __syncthreads();
+    if (tid == 0) {
+        float m = 0.f;
+        for (int w = 0; w < GF_FRAME_THREADS / 32; ++w) m = fmaxf(m, sm.red[w]);
+        gf_atomic_max_pos(&scal[wk.x].mag_bits, m);
+    }
+}
+
+void gf_launch_frame(const int4 *work, int n_work, const GfPassDev *passes, GfPassScal *scal, const GfNoteDev *notes,
+                     const GfNotePlan *plans, cudaStream_t st)
+{
+    if (n_work <= 0) return;
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaFuncSetAttribute(gf_frame_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(GfFrameSmem));
+        attr_set = true;
+    }
+    gf_frame_kernel<<<n_work, GF_FRAME_THREADS, sizeof(GfFrameSmem), st>>>(work, passes, scal, notes, plans);
+}

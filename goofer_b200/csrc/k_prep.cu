@@ -1,0 +1,564 @@
+// k_prep.cu -- feature preparation kernels (everything GooferResampler.resample does to the envelope,
+// mask and formant tracks before it calls gf.synthesize, plus synthesize's own envelope warps).
+//
+//   gf_src_env_kernel   gf.decode_env_from_knots                       GOOFER.py:149-168 (84-95)
+//   gf_tracks_kernel    formant tracks: loop / stretch / canon / sanitise+smooth
+//                                                                       SillySampler.py:714-763, 776-792, 242-283
+//   gf_env_kernel       br tilt :503-515, es :518-551, fw :554-574, loop/velocity maps :625-788,
+//                       fst bells :808-832, fry warp :967-995; then synthesize's env4breath blur
+//                       GOOFER.py:993, F1-F4 warp :1004-1014 (:805-875), g shift :1016-1017 (:618-627)
+//   gf_mask_kernel      mask_new (tile + velocity stretch)             SillySampler.py:699-712, 788
+//   gf_fir_kernel       gaussian_filter1d along time (numpy-'reflect')  GOOFER.py:241-261
+#include <cuda_fp16.h>
+#include "gf_device.cuh"
+#include "gf_maps.cuh"
+
+// ------------------------------------------------------------------------------------------------
+// source envelope: knots (K, T) f16 log-values -> dense (T, 520) f32, frame-major
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float gf_half_bits_to_float(uint16_t h)
+{
+    return __half2float(__ushort_as_half(h));
+}
+
+__global__ void __launch_bounds__(256) gf_src_env_kernel(const GfSourceDev *__restrict__ srcs)
+{
+    __shared__ float tile[32][33];
+    const GfSourceDev s = srcs[blockIdx.y];
+    const int t0 = blockIdx.x * 32;
+    if (t0 >= s.T) return;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const double fstep = 1024.0 * (1.0 / (double)d_tab.sr);     // rfftfreq: k / (n * d)
+    for (int bc = 0; bc < GF_NBINS; bc += 32) {
+        for (int i = ty; i < 32; i += 8) {
+            const int b = bc + i, t = t0 + tx;
+            float v = 0.0f;
+            if (b < GF_NBINS && t < s.T) {
+                if (s.knots) {
+                    // precompute_interp_matrix (GOOFER.py:84-95): 2-tap lerp between mel knots, all f32
+                    const float f = (float)((double)b / fstep);
+                    int lo = 0, hi = s.K;                       // searchsorted(hz, f, side='right')
+                    while (lo < hi) { int mid = (lo + hi) >> 1; if (s.hz_knots[mid] <= f) lo = mid + 1; else hi = mid; }
+                    int idx = lo - 1;
+                    idx = idx < 0 ? 0 : (idx > s.K - 2 ? s.K - 2 : idx);
+                    const float x0 = s.hz_knots[idx], x1 = s.hz_knots[idx + 1];
+                    const float w1 = (f - x0) / fmaxf(x1 - x0, 1e-12f);
+                    const float w0 = 1.0f - w1;
+                    const float k0 = gf_half_bits_to_float(s.knots[(size_t)idx * s.T + t]);
+                    const float k1 = gf_half_bits_to_float(s.knots[(size_t)(idx + 1) * s.T + t]);
+                    v = expf(fmaf(w1, k1, w0 * k0));
+                } else {
+                    v = s.dense[(size_t)b * s.T + t];
+                }
+            }
+            tile[i][tx] = v;
+        }
+        __syncthreads();
+        for (int i = ty; i < 32; i += 8) {
+            const int t = t0 + i, b = bc + tx;
+            if (t < s.T && b < GF_NBINS) s.envS[(size_t)t * GF_ENVS_LD + b] = tile[tx][i];
+        }
+        __syncthreads();
+    }
+}
+
+void gf_launch_src_env(const GfSourceDev *srcs, int n_src, int max_T, cudaStream_t st)
+{
+    if (n_src <= 0 || max_T <= 0) return;
+    dim3 grid((max_T + 31) / 32, n_src);
+    gf_src_env_kernel<<<grid, 256, 0, st>>>(srcs);
+}
+
+// ------------------------------------------------------------------------------------------------
+// formant tracks
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ double gf_gauss_tap(int j, int radius, double sigma, double norm)
+{
+    const double t = (double)(j - radius) / sigma;
+    return exp(-0.5 * t * t) / norm;
+}
+
+__global__ void __launch_bounds__(128)
+gf_tracks_kernel(const GfNotePlan *__restrict__ plans, const GfNoteDev *__restrict__ notes, const GfSourceDev *__restrict__ srcs)
+{
+    const GfNotePlan &pl = plans[blockIdx.x];
+    const GfNoteDev nd = notes[blockIdx.x];
+    const GfSourceDev &sc = srcs[pl.src];
+    const int T = pl.T_env;
+    __shared__ int any_bad, any_good;
+    __shared__ double taps[33];
+    if (threadIdx.x < 33) {
+        double norm = 0.0;
+        for (int j = 0; j < 33; ++j) { const double t = (double)(j - 16) / 4.0; norm += exp(-0.5 * t * t); }
+        taps[threadIdx.x] = gf_gauss_tap(threadIdx.x, 16, 4.0, norm);
+    }
+    const float min_hz[4] = {120.0f, 300.0f, 1500.0f, 2000.0f};
+    const float max_hz = (float)((double)pl.sr * 0.48);
+    for (int k = 0; k < 4; ++k) {
+        float *canon = nd.trk_canon + (size_t)k * T;
+        const GfTrackSlices sl = gf_track_slices(pl, k);
+        for (int t = threadIdx.x; t < T; t += blockDim.x)
+            canon[t] = gf_track_canon(pl, sl, sc.formants[k], k, t);
+        if (!nd.trk_clean) continue;
+        // sanitize_smooth_formant (SillySampler.py:264-283)
+        float *tmp = nd.trk_clean + (size_t)(4 + k) * T;     // scratch rows 4..7
+        float *clean = nd.trk_clean + (size_t)k * T;
+        if (threadIdx.x == 0) { any_bad = 0; any_good = 0; }
+        __syncthreads();
+        for (int t = threadIdx.x; t < T; t += blockDim.x) {
+            const float x = canon[t];
+            const bool bad = !isfinite(x) || x < min_hz[k] || x > max_hz;
+            if (bad) any_bad = 1; else any_good = 1;
+        }
+        __syncthreads();
+        const bool hb = any_bad != 0, hg = any_good != 0;
+        for (int t = threadIdx.x; t < T; t += blockDim.x) {
+            float x = canon[t];
+            if (hb) {
+                if (!hg) x = 300.0f;
+                else {
+                    auto is_bad = [&](int q) { const float y = canon[q]; return !isfinite(y) || y < min_hz[k] || y > max_hz; };
+                    if (is_bad(t)) {
+                        // interp1d(good_idx, x[good], 'linear', extrapolate) at t   (GOOFER.py:173-239)
+                        int gl = t - 1; while (gl >= 0 && is_bad(gl)) --gl;
+                        int gr = t + 1; while (gr < T && is_bad(gr)) ++gr;
+                        double r;
+                        if (gl >= 0 && gr < T) {
+                            const double y0 = canon[gl], y1 = canon[gr];
+                            r = ((y1 - y0) / ((double)(float)gr - (double)(float)gl)) * ((double)(float)t - (double)(float)gl) + y0;
+                        } else if (gl < 0) {
+                            int g2 = gr + 1; while (g2 < T && is_bad(g2)) ++g2;
+                            if (g2 >= T) r = canon[gr];
+                            else {
+                                const double sl_ = ((double)canon[g2] - (double)canon[gr]) / ((double)(float)g2 - (double)(float)gr + 1e-10);
+                                r = (double)canon[gr] + sl_ * ((double)(float)t - (double)(float)gr);
+                            }
+                        } else {
+                            int g2 = gl - 1; while (g2 >= 0 && is_bad(g2)) --g2;
+                            if (g2 < 0) r = canon[gl];
+                            else {
+                                const double sr_ = ((double)canon[gl] - (double)canon[g2]) / ((double)(float)gl - (double)(float)g2 + 1e-10);
+                                r = (double)canon[gl] + sr_ * ((double)(float)t - (double)(float)gl);
+                            }
+                        }
+                        x = (float)r;
+                    }
+                }
+            }
+            tmp[t] = x;
+        }
+        __syncthreads();
+        for (int t = threadIdx.x; t < T; t += blockDim.x) {
+            double a = 0.0;
+            for (int j = 0; j < 33; ++j) a += taps[j] * (double)tmp[gf_reflect(t + j - 16, T)];
+            clean[t] = (float)a;
+        }
+        __syncthreads();
+    }
+}
+
+void gf_launch_tracks(const GfNotePlan *plans, const GfNoteDev *notes, const GfSourceDev *srcs, int n_notes, cudaStream_t st)
+{
+    if (n_notes > 0) gf_tracks_kernel<<<n_notes, 128, 0, st>>>(plans, notes, srcs);
+}
+
+// ------------------------------------------------------------------------------------------------
+// envelope: one warp per output frame, eight frames (one tile) per CTA
+// ------------------------------------------------------------------------------------------------
+#define GF_ENV_WARPS GF_FT
+#define GF_ROW_LD 520
+#define GF_EPL 17           // bins per lane: 513 = 16 * 32 + 1
+#define GF_MAX_ES_TAPS 57   // sigma <= 7 -> radius 28
+
+struct GfEnvSmem {
+    float rows[GF_ENV_WARPS][2][GF_ROW_LD];
+    float tileF[GF_NBINS][GF_FT];
+    float tileN[GF_NBINS][GF_FT];
+    float tilt[GF_ROW_LD];
+    double es_taps[GF_MAX_ES_TAPS];
+};
+
+// np.interp on the uniform grid freqs[i] = i * step (i <= 512, freqs[512] = nyq) with the linear
+// extrapolation of GOOFER.py:173-239 outside [0, nyq]
+__device__ __forceinline__ float gf_grid_interp(const float *row, double x, double step, double nyq)
+{
+    if (x < 0.0) {
+        const double sl = ((double)row[1] - (double)row[0]) / (step - 0.0 + 1e-10);
+        return (float)((double)row[0] + sl * (x - 0.0));
+    }
+    if (x > nyq) {
+        const double x1 = 511.0 * step;
+        const double sr_ = ((double)row[512] - (double)row[511]) / (nyq - x1 + 1e-10);
+        return (float)((double)row[512] + sr_ * (x - nyq));
+    }
+    int j = (int)(x / step);
+    if (j > 512) j = 512;
+    auto fq = [&](int i) { return i == 512 ? nyq : (double)i * step; };
+    while (j > 0 && fq(j) > x) --j;
+    while (j < 512 && fq(j + 1) <= x) ++j;
+    if (j >= 512) return row[512];
+    const double x0 = fq(j);
+    if (x0 == x) return row[j];
+    const double slope = ((double)row[j + 1] - (double)row[j]) / (fq(j + 1) - x0);
+    return (float)(slope * (x - x0) + (double)row[j]);
+}
+
+__global__ void __launch_bounds__(32 * GF_ENV_WARPS)
+gf_env_kernel(const int2 *__restrict__ work, const GfNotePlan *__restrict__ plans, const GfNoteDev *__restrict__ notes,
+              const GfSourceDev *__restrict__ srcs)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    GfEnvSmem &sm = *reinterpret_cast<GfEnvSmem *>(smem_raw);
+    const int2 wk = work[blockIdx.x];                 // x = note (in wave), y = tile index
+    const GfNotePlan &pl = plans[wk.x];
+    const GfNoteDev nd = notes[wk.x];
+    const GfSourceDev &sc = srcs[pl.src];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int sr = pl.sr;
+    const double nyq = (double)sr / 2.0;
+    const double step = nyq / 512.0;
+
+    const bool do_tilt = pl.brightness_env != 1.0;
+    const bool do_es = pl.es != 0.0;
+    const bool do_fw = pl.fw != 0.0;
+    int es_radius = 0;
+    if (do_tilt) {
+        // SillySampler.py:506-510: f32 linspace(1e-6, nyq), clip(f / nyq, .02, 1) ** alpha, / (mean + 1e-12)
+        // (mean via a CTA-wide fp64 sum; numpy's f32 pairwise mean differs by < 1e-7 relative)
+        const float alpha = (float)fmin(fmax(pl.brightness_env - 1.0, -0.9), 1.0);
+        const float nyqf = (float)((double)sr * 0.5);
+        __shared__ double red[GF_ENV_WARPS];
+        double part = 0.0;
+        for (int b = threadIdx.x; b < GF_NBINS; b += blockDim.x) {
+            const double fv = (b == GF_NBINS - 1) ? (double)sr * 0.5 : (double)b * (((double)sr * 0.5 - 1e-6) / 512.0) + 1e-6;
+            float nf = (float)fv / nyqf;
+            nf = fminf(fmaxf(nf, 0.02f), 1.0f);
+            const float tv = powf(nf, alpha);
+            sm.tilt[b] = tv;
+            part += (double)tv;
+        }
+        part = gf_warp_sum(part);
+        if (lane == 0) red[warp] = part;
+        __syncthreads();
+        double tot = 0.0;
+        for (int w = 0; w < GF_ENV_WARPS; ++w) tot += red[w];
+        const float mean = (float)(tot / (double)GF_NBINS);
+        for (int b = threadIdx.x; b < GF_NBINS; b += blockDim.x) sm.tilt[b] = sm.tilt[b] / (mean + 1e-12f);
+    }
+    if (do_es) {
+        const double s = fabs(pl.es);
+        const double sigma = pl.es < 0.0 ? (1.0 + 6.0 * s) : (0.8 + 4.0 * s);
+        es_radius = (int)(4.0 * sigma + 0.5);
+        if (threadIdx.x < 2 * es_radius + 1) {
+            double norm = 0.0;
+            for (int j = 0; j <= 2 * es_radius; ++j) { const double t = (double)(j - es_radius) / sigma; norm += exp(-0.5 * t * t); }
+            sm.es_taps[threadIdx.x] = gf_gauss_tap(threadIdx.x, es_radius, sigma, norm);
+        }
+    }
+    __syncthreads();
+
+    const int t = wk.y * GF_FT + warp;
+    if (t < pl.T_out) {
+        const int te = min(t, pl.T_env - 1);              // GOOFER.py:1115-1119 trim / edge-pad to the STFT grid
+        float *rA = sm.rows[warp][0], *rB = sm.rows[warp][1];
+        GfMix mix;
+        gf_env_mix(pl, te, mix);
+        double acc[GF_EPL];
+#pragma unroll
+        for (int e = 0; e < GF_EPL; ++e) acc[e] = 0.0;
+        for (int m = 0; m < mix.n; ++m) {
+            const float *src = sc.envS + (size_t)gf_src_frame(pl, mix.f[m]) * GF_ENVS_LD;
+            float *cur = rA, *oth = rB;
+            for (int e = 0; e < GF_EPL; ++e) {
+                const int b = lane + 32 * e;
+                if (b < GF_NBINS) cur[b] = do_tilt ? src[b] * sm.tilt[b] : src[b];
+            }
+            __syncwarp();
+            if (do_es) {
+                // SillySampler.py:518-551
+                const double s = fabs(pl.es);
+                double sum0 = 0.0, sum1 = 0.0;
+                double mod[GF_EPL];
+                for (int e = 0; e < GF_EPL; ++e) {
+                    const int b = lane + 32 * e;
+                    mod[e] = 0.0;
+                    if (b < GF_NBINS) {
+                        double blur = 0.0;
+                        for (int j = 0; j <= 2 * es_radius; ++j) {
+                            int q = b + j - es_radius;
+                            q = q < 0 ? -q : (q > 512 ? 1024 - q : q);
+                            blur += sm.es_taps[j] * (double)cur[q];
+                        }
+                        const double x = (double)cur[b];
+                        mod[e] = pl.es < 0.0 ? blur : fmax(0.0, x + (5.0 * s) * (x - blur));
+                        sum0 += x;
+                        sum1 += mod[e];
+                    }
+                }
+                sum0 = gf_warp_sum(sum0);
+                sum1 = gf_warp_sum(sum1);
+                const float m0 = (float)(sum0 / (double)GF_NBINS);
+                const double m1 = sum1 / (double)GF_NBINS;
+                const double ratio = (double)m0 / (m1 + 1e-12);
+                for (int e = 0; e < GF_EPL; ++e) {
+                    const int b = lane + 32 * e;
+                    if (b < GF_NBINS) { float y = (float)(mod[e] * ratio); oth[b] = pl.es < 0.0 ? fmaxf(0.0f, y) : y; }
+                }
+                __syncwarp();
+                float *sw = cur; cur = oth; oth = sw;
+            }
+            const double wm = mix.w[m];
+            for (int e = 0; e < GF_EPL; ++e) {
+                const int b = lane + 32 * e;
+                if (b < GF_NBINS) {
+                    float y;
+                    if (do_fw) {
+                        // SillySampler.py:555-569
+                        double pos = ((double)b - 513.0 / 2.0) * (1.0 + pl.fw) + 513.0 / 2.0;
+                        pos = fmin(fmax(pos, 0.0), 512.0);
+                        const int lo = (int)floor(pos);
+                        const int hi = min(lo + 1, 512);
+                        const double fr = pos - (double)lo;
+                        y = (float)((1.0 - fr) * (double)cur[lo] + fr * (double)cur[hi]);
+                    } else y = cur[b];
+                    acc[e] += wm * (double)y;
+                }
+            }
+            __syncwarp();
+        }
+        // ---- fst bells (SillySampler.py:808-832), f32 ----
+        if (pl.any_fst) {
+            const float sig[4] = {100.0f, 200.0f, 350.0f, 500.0f};
+            float gain[GF_EPL];
+#pragma unroll
+            for (int e = 0; e < GF_EPL; ++e) gain[e] = 1.0f;
+            for (int k = 0; k < 4; ++k) {
+                const double sk = pl.fst[k];
+                if (fabs(sk) < 1e-6) continue;
+                const float Fk = nd.trk_clean[(size_t)k * pl.T_env + te];
+                if (!isfinite(Fk) || !(Fk > 50.0f) || !((double)Fk < (double)sr * 0.5)) continue;
+                const float sv = (float)((1.0 + sk) - 1.0);
+                for (int e = 0; e < GF_EPL; ++e) {
+                    const int b = lane + 32 * e;
+                    const float fb = (b == 512) ? (float)nyq : (float)((double)b * step);
+                    const float d = (fb - Fk) / sig[k];
+                    const float w = expf(-0.5f * (d * d));
+                    gain[e] *= 1.0f + sv * w;
+                }
+            }
+#pragma unroll
+            for (int e = 0; e < GF_EPL; ++e) acc[e] *= (double)gain[e];
+        }
+        float *cur = rA, *oth = rB;
+        for (int e = 0; e < GF_EPL; ++e) {
+            const int b = lane + 32 * e;
+            if (b < GF_NBINS) cur[b] = (float)acc[e];
+        }
+        __syncwarp();
+        // ---- vocal-fry envelope compression (SillySampler.py:967-995) ----
+        if (pl.fry_mask_on) {
+            const int c = min(pl.n_total - 1, te * GF_HOP + GF_HOP / 2);
+            float wfr = 0.0f;
+            if (c >= pl.fry_a && c < pl.fry_b) {
+                double m = 1.0;
+                const int fade = pl.fry_fade;
+                if (fade > 0) {
+                    const int a1 = min(pl.fry_b, pl.fry_a + fade), b0 = max(pl.fry_a, pl.fry_b - fade);
+                    if (c < a1) m *= (double)(float)gf_lin01(c - pl.fry_a, a1 - pl.fry_a);
+                    float mf = (float)m;
+                    if (c >= b0) mf = (float)((double)mf * gf_lin10(c - b0, pl.fry_b - b0));
+                    m = (double)mf;
+                }
+                wfr = (float)m;
+            }
+            if (wfr > 1e-6f) {
+                const double s = 1.0 - (double)wfr * (1.0 - 0.92);
+                if (!(fabs(s - 1.0) < 1e-6)) {
+                    for (int e = 0; e < GF_EPL; ++e) {
+                        const int b = lane + 32 * e;
+                        if (b < GF_NBINS) {
+                            double sp = fmin(fmax((double)b / s, 0.0), 512.0);
+                            const int lo = (int)floor(sp);
+                            const int hi = min(lo + 1, 512);
+                            const double fr = sp - (double)lo;
+                            oth[b] = (float)((1.0 - fr) * (double)cur[lo] + fr * (double)cur[hi]);
+                        }
+                    }
+                    __syncwarp();
+                    float *sw = cur; cur = oth; oth = sw;
+                }
+            }
+        }
+        // ---- env4breath: Gaussian sigma 1.75 of env_new (GOOFER.py:993), before the formant warps ----
+        for (int e = 0; e < GF_EPL; ++e) {
+            const int b = lane + 32 * e;
+            if (b < GF_NBINS) {
+                double a = 0.0;
+#pragma unroll
+                for (int j = 0; j < 15; ++j) {
+                    int q = b + j - 7;
+                    q = q < 0 ? -q : (q > 512 ? 1024 - q : q);
+                    a += d_tab.g175[j] * (double)cur[q];
+                }
+                sm.tileN[b][warp] = (float)a;
+            }
+        }
+        // ---- F1..F4 warp (GOOFER.py:840-875) ----
+        if (pl.any_F_shift) {
+            double xs[6], xd[6];
+            int nk = 0;
+            xs[nk] = 0.0; xd[nk] = 0.0; ++nk;
+            for (int k = 0; k < 4; ++k) {
+                const double fo = (double)nd.trk_canon[(size_t)k * pl.T_env + te];
+                const double fs = fo * pl.F_shift[k];
+                if (fo > 50.0 && fo < nyq && fs > 50.0) { xs[nk] = fo; xd[nk] = fs; ++nk; }
+            }
+            xs[nk] = nyq; xd[nk] = nyq; ++nk;
+            for (int e = 0; e < GF_EPL; ++e) {
+                const int b = lane + 32 * e;
+                if (b < GF_NBINS) {
+                    const double x = (b == 512) ? nyq : (double)b * step;
+                    // np.interp(x, xd, xs) (linear search semantics) -- x is always inside [xd[0], xd[-1]] = [0, nyq]
+                    double wf;
+                    if (x > xd[nk - 1]) wf = xs[nk - 1];
+                    else if (x < xd[0]) wf = xs[0];
+                    else {
+                        int i = 0;
+                        while (i < nk && x >= xd[i]) ++i;
+                        const int j = i - 1;
+                        if (j >= nk - 1) wf = xs[nk - 1];
+                        else if (xd[j] == x) wf = xs[j];
+                        else {
+                            const double slope = (xs[j + 1] - xs[j]) / (xd[j + 1] - xd[j]);
+                            wf = slope * (x - xd[j]) + xs[j];
+                        }
+                    }
+                    oth[b] = gf_grid_interp(cur, wf, step, nyq);
+                }
+            }
+            __syncwarp();
+            float *sw = cur; cur = oth; oth = sw;
+        }
+        // ---- g: shift all formants (GOOFER.py:618-627) ----
+        if (pl.formant_shift != 1.0) {
+            for (int e = 0; e < GF_EPL; ++e) {
+                const int b = lane + 32 * e;
+                if (b < GF_NBINS) {
+                    const double x = (b == 512) ? nyq : (double)b * step;
+                    const double q = fmin(fmax(x / pl.formant_shift, 0.0), nyq);
+                    oth[b] = gf_grid_interp(cur, q, step, nyq);
+                }
+            }
+            __syncwarp();
+            float *sw = cur; cur = oth; oth = sw;
+        }
+        for (int e = 0; e < GF_EPL; ++e) {
+            const int b = lane + 32 * e;
+            if (b < GF_NBINS) sm.tileF[b][warp] = cur[b];
+        }
+    } else {
+        for (int e = 0; e < GF_EPL; ++e) {
+            const int b = lane + 32 * e;
+            if (b < GF_NBINS) { sm.tileF[b][warp] = 0.0f; sm.tileN[b][warp] = 0.0f; }
+        }
+    }
+    __syncthreads();
+    const size_t base = (size_t)wk.y * (GF_NBINS * GF_FT);
+    const float *tf = &sm.tileF[0][0], *tn = &sm.tileN[0][0];
+    for (int i = threadIdx.x; i < GF_NBINS * GF_FT; i += blockDim.x) {
+        nd.envF[base + i] = tf[i];
+        nd.envN[base + i] = tn[i];
+    }
+}
+
+void gf_launch_env(const int2 *work, int n_work, const GfNotePlan *plans, const GfNoteDev *notes, const GfSourceDev *srcs,
+                   cudaStream_t st)
+{
+    if (n_work <= 0) return;
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaFuncSetAttribute(gf_env_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(GfEnvSmem));
+        attr_set = true;
+    }
+    gf_env_kernel<<<n_work, 32 * GF_ENV_WARPS, sizeof(GfEnvSmem), st>>>(work, plans, notes, srcs);
+}
+
+// ------------------------------------------------------------------------------------------------
+// mask_new -> vm (f32), and the decimated + smoothed mask of smooth_mask_ds (GOOFER.py:556-563)
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+gf_mask_kernel(const GfNotePlan *__restrict__ plans, const GfNoteDev *__restrict__ notes, const GfSourceDev *__restrict__ srcs)
+{
+    const GfNotePlan &pl = plans[blockIdx.y];
+    const GfNoteDev nd = notes[blockIdx.y];
+    const float *mask_src = srcs[pl.src].mask;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < pl.n_total; i += gridDim.x * blockDim.x)
+        nd.vm[i] = (float)gf_mask_new(pl, mask_src, i);
+}
+
+void gf_launch_mask(const GfNotePlan *plans, const GfNoteDev *notes, const GfSourceDev *srcs, int n_notes, int max_n, cudaStream_t st)
+{
+    if (n_notes <= 0) return;
+    dim3 grid(min(64, (max_n + 255) / 256), n_notes);
+    gf_mask_kernel<<<grid, 256, 0, st>>>(plans, notes, srcs);
+}
+
+// ------------------------------------------------------------------------------------------------
+// generic Gaussian FIR along time with numpy-'reflect' padding, fp64 accumulation
+//   job: in (f32 or f64, strided), out (f32 or f64), n, sigma ; optional max(|y| + 1e-6) reduction
+// ------------------------------------------------------------------------------------------------
+
+#define GF_FIR_TILE 1024
+__global__ void __launch_bounds__(256) gf_fir_kernel(const GfFirJob *__restrict__ jobs)
+{
+    extern __shared__ double fsm[];
+    const GfFirJob jb = jobs[blockIdx.y];
+    const int n = jb.n;
+    const int start = blockIdx.x * GF_FIR_TILE;
+    if (start >= n) return;
+    const int radius = (int)(4.0 * jb.sigma + 0.5);
+    double *taps = fsm;                           // 2 r + 1
+    double *tile = fsm + (2 * radius + 1);        // GF_FIR_TILE + 2 r
+    __shared__ double norm_s;
+    if (threadIdx.x == 0) {
+        double norm = 0.0;
+        for (int j = 0; j <= 2 * radius; ++j) { const double t = (double)(j - radius) / jb.sigma; norm += exp(-0.5 * t * t); }
+        norm_s = norm;
+    }
+    __syncthreads();
+    for (int j = threadIdx.x; j <= 2 * radius; j += blockDim.x) taps[j] = gf_gauss_tap(j, radius, jb.sigma, norm_s);
+    const int cnt = min(GF_FIR_TILE, n - start);
+    for (int i = threadIdx.x; i < cnt + 2 * radius; i += blockDim.x) {
+        const int q = gf_reflect(start + i - radius, n);
+        double v = jb.in_f64 ? ((const double *)jb.in)[(size_t)q * jb.in_stride] : (double)((const float *)jb.in)[(size_t)q * jb.in_stride];
+        if (jb.in_cast_f32) v = (double)(float)v;
+        tile[i] = v;
+    }
+    __syncthreads();
+    double mx = 0.0;
+    for (int i = threadIdx.x; i < cnt; i += blockDim.x) {
+        double a = 0.0;
+        for (int j = 0; j <= 2 * radius; ++j) a += taps[j] * tile[i + j];
+        if (jb.out_f64) ((double *)jb.out)[start + i] = a; else ((float *)jb.out)[start + i] = (float)a;
+        mx = fmax(mx, fabs(a) + 1e-6);
+    }
+    if (jb.maxabs) {
+        for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+        if ((threadIdx.x & 31) == 0)
+            atomicMax((unsigned long long *)jb.maxabs, (unsigned long long)__double_as_longlong(mx));
+    }
+}
+
+void gf_launch_fir(const GfFirJob *jobs, int n_jobs, int max_n, double max_sigma, cudaStream_t st)
+{
+    if (n_jobs <= 0 || max_n <= 0) return;
+    const int radius = (int)(4.0 * max_sigma + 0.5);
+    const size_t smem = sizeof(double) * (size_t)(2 * radius + 1 + GF_FIR_TILE + 2 * radius);
+    static size_t attr = 0;
+    if (smem > attr) {
+        cudaFuncSetAttribute(gf_fir_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        attr = smem;
+    }
+    dim3 grid((max_n + GF_FIR_TILE - 1) / GF_FIR_TILE, n_jobs);
+    gf_fir_kernel<<<grid, 256, smem, st>>>(jobs);
+}

@@ -1,0 +1,238 @@
+// k_tail.cu -- time-domain tail of gf.synthesize and of GooferResampler.resample.
+//
+//   gf_peak_kernel     GOOFER.py:1179-1193, 1210: mask cross-fade gains, sr volume jitter, peak
+//   gf_mix_kernel      GOOFER.py:1208-1218 normalise; SillySampler.py:1143-1182 V/B/U mix, sa blend, pd
+//   gf_onepole_kernel  SillySampler.py:95-174 dynamic one-pole cascades (su, sj, fry, st)
+#include "gf_device.cuh"
+#include "gf_maps.cuh"
+
+// smooth_mask_ds (GOOFER.py:556-569): lerp of the smoothed decimated mask back to sample rate on
+// float32 linspace abscissae, evaluated in fp64 like np.interp, result f32
+__device__ __forceinline__ float gf_ms_at(const float *__restrict__ s, int M, int i, int N)
+{
+    if (M == 1) return s[0];
+    const double x = (double)(float)gf_lin01(i, N);
+    auto xo = [&](int j) { return (double)(float)gf_lin01(j, M); };
+    if (x >= 1.0) return s[M - 1];
+    int j = (int)(x * (double)(M - 1));
+    if (j > M - 2) j = M - 2;
+    while (j > 0 && xo(j) > x) --j;
+    while (j < M - 2 && xo(j + 1) <= x) ++j;
+    const double x0 = xo(j);
+    if (x0 == x) return s[j];
+    const double slope = ((double)s[j + 1] - (double)s[j]) / (xo(j + 1) - x0);
+    return (float)(slope * (x - x0) + (double)s[j]);
+}
+
+struct GfStreams { float h, b, u; };
+
+// the three streams of one synthesize pass before the peak normalisation
+__device__ __forceinline__ GfStreams gf_pass_streams(const GfNotePlan &pl, const GfNoteDev &nd, const GfPassDev &ps,
+                                                     const GfPassScal &sc, int i)
+{
+    GfStreams r;
+    const float mag = __uint_as_float(sc.mag_bits);
+    r.h = ps.harm[i] / mag;                                   // S / max|S| (GOOFER.py:1121-1128), applied after the iSTFT
+    if (ps.mask_ones) {                                       // sa pass: mask == 1, strengths 1 (SillySampler.py:1156-1170)
+        r.b = ps.bre[i];
+        r.u = 0.0f * ps.uv[i];
+    } else {
+        const int N = pl.n_total, M = (N + 3) / 4;
+        const float ms = gf_ms_at(nd.ms_short, M, i, N);
+        r.b = ps.bre[i] * ms * 0.1f;
+        r.u = ps.uv[i] * (1.0f - ms) * 0.75f;
+    }
+    if (ps.kind == GF_PASS_MAIN && pl.vol_jitter) {
+        // GOOFER.py:1185-1191 (create_volume_jitter :638-659 without vibrato)
+        const double zh = nd.z_srh[i] / nd.noteScal[GF_NS_SRHMAX];
+        const double zb = nd.z_srb[i] / nd.noteScal[GF_NS_SRBMAX];
+        const double hj = 1.0 + zh * pl.vol_jitter_strength;
+        const double bj = 1.0 + zb * (pl.vol_jitter_strength * 2);
+        const double vj = (double)nd.vjm[i];
+        r.h = (float)((double)r.h * (1.0 + (hj - 1.0) * vj));
+        r.b = (float)((double)r.b * (1.0 + (bj - 1.0) * vj));
+    }
+    return r;
+}
+
+__global__ void __launch_bounds__(256)
+gf_peak_kernel(const GfNotePlan *__restrict__ plans, const GfNoteDev *__restrict__ notes, const GfPassDev *__restrict__ passes,
+               GfPassScal *scal)
+{
+    const int pi = blockIdx.y;
+    const GfPassDev ps = passes[pi];
+    const GfNotePlan &pl = plans[ps.note];
+    const GfNoteDev nd = notes[ps.note];
+    const GfPassScal sc = scal[pi];
+    float mx = 0.0f;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < ps.n_total; i += gridDim.x * blockDim.x) {
+        const GfStreams s = gf_pass_streams(pl, nd, ps, sc, i);
+        mx = fmaxf(mx, fabsf((s.h + s.u) + s.b));
+    }
+    mx = gf_warp_max(mx);
+    if ((threadIdx.x & 31) == 0 && mx > 0.0f) gf_atomic_max_pos(&scal[pi].peak_bits, mx);
+}
+
+void gf_launch_peak(const GfNotePlan *plans, const GfNoteDev *notes, const GfPassDev *passes, GfPassScal *scal, int n_pass,
+                    int max_n, cudaStream_t st)
+{
+    if (n_pass <= 0) return;
+    dim3 grid(min(32, (max_n + 255) / 256), n_pass);
+    gf_peak_kernel<<<grid, 256, 0, st>>>(plans, notes, passes, scal);
+}
+
+__device__ __forceinline__ float gf_pass_gain(const GfNotePlan &pl, const GfPassScal &sc)
+{
+    // GOOFER.py:1208-1213
+    const float pk = __uint_as_float(sc.peak_bits) + 1e-12f;
+    const double nrm = fmin(fmax(pl.normalize, 0.0), 1.0);
+    return (float)pow(1.0 / (double)pk, nrm);
+}
+
+// stage 1 of the tail: normalised streams of every pass -> fx scratch (only for notes that need the
+// sequential filters); stage 2: mix.  Notes without filters go straight through gf_mix_kernel.
+__global__ void __launch_bounds__(256)
+gf_mix_kernel(const GfNotePlan *__restrict__ plans, const GfNoteDev *__restrict__ notes, const GfPassDev *__restrict__ passes,
+              const GfPassScal *__restrict__ scal)
+{
+    const GfNotePlan &pl = plans[blockIdx.y];
+    const GfNoteDev nd = notes[blockIdx.y];
+    const int n = pl.n_total;
+    const GfPassDev &p0 = passes[nd.pass0];
+    const GfPassScal &s0 = scal[nd.pass0];
+    const float g0 = gf_pass_gain(pl, s0);
+    int p_sa = -1;
+    for (int p = 1; p < pl.n_passes; ++p)
+        if (pl.pass_kind[p] == GF_PASS_SA) p_sa = nd.pass0 + p;
+    float g_sa = 0.0f;
+    if (p_sa >= 0) g_sa = gf_pass_gain(pl, scal[p_sa]);
+    const bool fx = nd.fx[0] != nullptr;                  // harm / bre already post-processed into fx[0] / fx[1]
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const GfStreams s = gf_pass_streams(pl, nd, p0, s0, i);
+        float h = s.h * g0, b = s.b * g0;
+        const float u = s.u * g0;
+        if (nd.tap_harm) { nd.tap_harm[i] = h; nd.tap_uv[i] = u; nd.tap_bre[i] = b; }
+        double hd, bd;
+        if (fx) { hd = (double)nd.fx[0][i] * (double)nd.noteScal[GF_NS_R1]; bd = (double)nd.fx[1][i] * (double)nd.noteScal[GF_NS_R1]; h = (float)hd; b = (float)bd; }
+        // SillySampler.py:1143-1151: harm * V (np.float64) + bre * B (f32) + uv * U (f32), * volume
+        double out = (((double)h * pl.V + (double)(b * (float)pl.B)) + (double)(u * (float)pl.U)) * pl.volume;
+        if (p_sa >= 0) {
+            // SillySampler.py:1153-1172
+            const GfStreams a = gf_pass_streams(pl, nd, passes[p_sa], scal[p_sa], i);
+            const float au = a.u * g_sa, ab = a.b * g_sa;
+            out = out * (1.0 - pl.sa) + ((double)((au + ab) * (float)pl.volume)) * pl.sa;
+        }
+        if (nd.dyn) out = out * (double)nd.dyn[i];
+        nd.out[i] = (float)out;
+    }
+}
+
+void gf_launch_mix(const GfNotePlan *plans, const GfNoteDev *notes, const GfPassDev *passes, const GfPassScal *scal,
+                   int n_notes, int max_n, cudaStream_t st)
+{
+    if (n_notes <= 0) return;
+    dim3 grid(min(32, (max_n + 255) / 256), n_notes);
+    gf_mix_kernel<<<grid, 256, 0, st>>>(plans, notes, passes, scal);
+}
+
+// ------------------------------------------------------------------------------------------------
+// dynamic_butter_filter (SillySampler.py:95-174): `order` cascaded one-pole sections whose
+// coefficient follows f0 per sample.  One warp per signal; each lane owns a contiguous chunk.  Per
+// section: (1) every lane composes the affine map of its chunk, (2) the 32 maps are scanned,
+// (3) every lane replays its chunk from the right initial state.  f32 throughout like the reference.
+// ------------------------------------------------------------------------------------------------
+
+__global__ void __launch_bounds__(32) gf_onepole_kernel(const GfOnepoleJob *__restrict__ jobs)
+{
+    const GfOnepoleJob jb = jobs[blockIdx.x];
+    const int n = jb.n, lane = threadIdx.x;
+    if (n <= 0) return;
+    const double srd = (double)jb.sr;
+    // ---- per-sample coefficient (SillySampler.py:128-152), f32 stores like the numba kernel ----
+    bool any_pos_l = false;
+    for (int i = lane; i < n; i += 32) {
+        float f = jb.f0 ? jb.f0[i] : (float)jb.f0_const;
+        if (jb.f0_floor > 0.0) f = fmaxf(f, (float)jb.f0_floor);
+        any_pos_l |= (f > 0.0f);
+    }
+    const bool any_pos = __any_sync(0xffffffffu, any_pos_l);
+    auto drv = [&](int i) {
+        i = i < 0 ? 0 : (i > n - 1 ? n - 1 : i);
+        float f = jb.f0 ? jb.f0[i] : (float)jb.f0_const;
+        if (jb.f0_floor > 0.0) f = fmaxf(f, (float)jb.f0_floor);
+        return f;
+    };
+    for (int i = lane; i < n; i += 32) {
+        float f0s;
+        if (jb.smooth_f0 && any_pos) {
+            // np.convolve(pad(f0, 2, 'edge'), ones(5)/5, 'valid') in f32
+            const float k = 1.0f / 5.0f;
+            float a = 0.0f;
+            // np.convolve accumulates sum_j k[j] * x[i + 4 - j]: order of terms j = 0..4
+            for (int j = 0; j < 5; ++j) a = fmaf(k, drv(i + 2 - j), a);
+            f0s = a;
+        } else f0s = drv(i);
+        float fc = (f0s > 0.0f) ? (float)((double)f0s * jb.cutoff_factor) : (float)jb.cutoff_factor;
+        fc = fmaxf(fc, jb.highpass ? 20.0f : 60.0f);
+        fc = (float)fmin((double)fc, 0.45 * srd);
+        const double w = (2.0 * 3.141592653589793) * (double)fc;
+        jb.alpha[i] = (float)(jb.highpass ? srd / (w + srd) : w / (w + srd));
+    }
+    __syncwarp();
+    const int chunk = (n + 31) / 32;
+    const int c0 = min(n, lane * chunk), c1 = min(n, c0 + chunk);
+    for (int pass = 0; pass < max(1, jb.order); ++pass) {
+        const float *src = (pass == 0) ? jb.x : jb.y;
+        // (1) affine map of the chunk: y_end = A * y_start + B
+        float A = 1.0f, B = 0.0f;
+        // x[c0 - 1] is read before any lane stores this pass's output (y may alias the input)
+        const float xp_first = (n > 0) ? ((c0 > 0 && c0 < n) ? src[c0 - 1] : src[0]) : 0.0f;
+        if (!jb.highpass) {
+            for (int i = c0; i < c1; ++i) {
+                const float a = jb.alpha[i], x = src[i];
+                // y = y + a (x - y) = (1 - a) y + a x
+                A = (1.0f - a) * A;
+                B = fmaf(a, x - B, B);
+            }
+        } else {
+            float xp = xp_first;
+            for (int i = c0; i < c1; ++i) {
+                const float a = jb.alpha[i], x = src[i];
+                // y = a (y + x - xp)
+                A = a * A;
+                B = a * ((B - xp) + x);
+                xp = x;
+            }
+        }
+        // (2) exclusive scan of the maps across lanes -> state entering each chunk
+        float sA = A, sB = B;
+        for (int o = 1; o < 32; o <<= 1) {
+            const float pA = __shfl_up_sync(0xffffffffu, sA, o), pB = __shfl_up_sync(0xffffffffu, sB, o);
+            if (lane >= o) { sB = fmaf(sA, pB, sB); sA = sA * pA; }
+        }
+        float y = __shfl_up_sync(0xffffffffu, sB, 1);      // zero initial state => state = B of the prefix
+        if (lane == 0) y = 0.0f;
+        // (3) replay
+        if (!jb.highpass) {
+            for (int i = c0; i < c1; ++i) {
+                const float a = jb.alpha[i], x = src[i];
+                y = fmaf(a, x - y, y);
+                jb.y[i] = y;
+            }
+        } else {
+            float xp = xp_first;
+            for (int i = c0; i < c1; ++i) {
+                const float a = jb.alpha[i], x = src[i];
+                y = a * ((y - xp) + x);
+                xp = x;
+                jb.y[i] = y;
+            }
+        }
+        __syncwarp();
+    }
+}
+
+void gf_launch_onepole(const GfOnepoleJob *jobs, int n_jobs, cudaStream_t st)
+{
+    if (n_jobs > 0) gf_onepole_kernel<<<n_jobs, 32, 0, st>>>(jobs);
+}
