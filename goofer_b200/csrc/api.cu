@@ -4,6 +4,7 @@
 // There is no CPU fallback anywhere in this file: every numeric array is produced by a kernel.
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <cmath>
 #include <vector>
@@ -35,6 +36,22 @@ extern "C" void goofer_last_stats(GooferStats *s) { if (s) *s = g_stats; }
         if (e_ != cudaSuccess) {                                                                   \
             gf_set_error("%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
             return GOOFER_ERR_CUDA;                                                                \
+        }                                                                                          \
+    } while (0)
+
+// GOOFER_DEBUG_SYNC=1: synchronise after every launch and name the kernel that failed (bring-up aid)
+static bool gf_debug_sync()
+{
+    static int v = -1;
+    if (v < 0) { const char *e = getenv("GOOFER_DEBUG_SYNC"); v = (e && e[0] == '1') ? 1 : 0; }
+    return v == 1;
+}
+#define GF_STEP(name)                                                                              \
+    do {                                                                                           \
+        if (gf_debug_sync()) {                                                                     \
+            cudaError_t e_ = cudaStreamSynchronize(st);                                            \
+            if (e_ == cudaSuccess) e_ = cudaGetLastError();                                        \
+            if (e_ != cudaSuccess) { gf_set_error("kernel %s failed: %s", name, cudaGetErrorString(e_)); return GOOFER_ERR_CUDA; } \
         }                                                                                          \
     } while (0)
 
@@ -112,7 +129,9 @@ int gf_tables_init(int sr)
 struct Bump {
     char *base; size_t cap; size_t off;
     void *take(size_t bytes) {
-        off = (off + 255) & ~(size_t)255;
+        // align the absolute address (base itself may sit at any offset inside the caller's workspace)
+        const size_t mis = base ? (size_t)((uintptr_t)base & 255) : 0;
+        off = ((off + mis + 255) & ~(size_t)255) - mis;
         void *p = base ? base + off : nullptr;
         off += bytes;
         return p;
@@ -366,23 +385,23 @@ static int gf_render_wave(const GooferBatch *b, const std::vector<GfNotePlan> &a
     for (int i = 0; i < nn; ++i) GF_CUDA(cudaMemsetAsync(wh.notes[i].noteScal, 0, GF_NS_COUNT * sizeof(double), st));
 
     int64_t &L = g_stats.kernel_launches;
-    gf_launch_tracks(d_plans, d_notes, d_srcs, nn, st); ++L;
-    gf_launch_mask(d_plans, d_notes, d_srcs, nn, max_n, st); ++L;
+    gf_launch_tracks(d_plans, d_notes, d_srcs, nn, st); ++L; GF_STEP("tracks");
+    gf_launch_mask(d_plans, d_notes, d_srcs, nn, max_n, st); ++L; GF_STEP("mask");
     {
         double max_sigma = 25.0;
         for (const GfFirJob &j : wh.fir) max_sigma = std::max(max_sigma, j.sigma);
-        gf_launch_fir(d_fir, (int)wh.fir.size(), max_n, max_sigma, st); ++L;
+        gf_launch_fir(d_fir, (int)wh.fir.size(), max_n, max_sigma, st); ++L; GF_STEP("fir");
     }
-    gf_launch_f0(d_plans, d_notes, d_passes, d_srcs, b->bend_cents, b->normals, nn, max_n, st); ++L;
-    gf_launch_walk(d_passes, d_scal, (int)n_pass, sr, st); ++L;
-    gf_launch_pulse(d_passes, d_scal, (int)n_pass, max_n, st); ++L;
+    gf_launch_f0(d_plans, d_notes, d_passes, d_srcs, b->bend_cents, b->normals, nn, max_n, st); ++L; GF_STEP("f0");
+    gf_launch_walk(d_passes, d_scal, (int)n_pass, sr, st); ++L; GF_STEP("walk");
+    gf_launch_pulse(d_passes, d_scal, (int)n_pass, max_n, st); ++L; GF_STEP("pulse");
     if ((rc = gf_growl(wh, d_plans, d_notes, d_passes, d_scal, max_n, st, &L)) != GOOFER_OK) return rc;
-    gf_launch_env(d_envw, (int)wh.env_work.size(), d_plans, d_notes, d_srcs, st); ++L;
-    gf_launch_frame(d_framew, (int)wh.frame_work.size(), d_passes, d_scal, d_notes, d_plans, st); ++L;
-    gf_launch_peak(d_plans, d_notes, d_passes, d_scal, (int)n_pass, max_n, st); ++L;
+    gf_launch_env(d_envw, (int)wh.env_work.size(), d_plans, d_notes, d_srcs, st); ++L; GF_STEP("env");
+    gf_launch_frame(d_framew, (int)wh.frame_work.size(), d_passes, d_scal, d_notes, d_plans, st); ++L; GF_STEP("frame");
+    gf_launch_peak(d_plans, d_notes, d_passes, d_scal, (int)n_pass, max_n, st); ++L; GF_STEP("peak");
     if ((rc = gf_pitch_dyn(wh, d_plans, d_notes, b->bend_cents, bp, max_n, st, &L)) != GOOFER_OK) return rc;
     if ((rc = gf_post_fx(wh, d_plans, d_notes, d_passes, d_scal, bp, sr, max_n, st, &L)) != GOOFER_OK) return rc;
-    gf_launch_mix(d_plans, d_notes, d_passes, d_scal, nn, max_n, st); ++L;
+    gf_launch_mix(d_plans, d_notes, d_passes, d_scal, nn, max_n, st); ++L; GF_STEP("mix");
     GF_CUDA(cudaGetLastError());
     ++g_stats.waves;
     return GOOFER_OK;
@@ -439,9 +458,11 @@ extern "C" int goofer_render_batch(const GooferBatch *b, void *workspace, size_t
     GfSourceDev *d_srcs = bp.arr<GfSourceDev>(std::max(1, b->n_sources));
     if (bp.off > bp.cap) { gf_set_error("workspace too small for the source cache (%zu > %zu)", bp.off, bp.cap); return GOOFER_ERR_WORKSPACE; }
     if (b->n_sources) GF_CUDA(cudaMemcpyAsync(d_srcs, srcs.data(), srcs.size() * sizeof(GfSourceDev), cudaMemcpyHostToDevice, st));
-    gf_launch_src_env(d_srcs, b->n_sources, max_T, st); ++g_stats.kernel_launches;
+    gf_launch_src_env(d_srcs, b->n_sources, max_T, st); ++g_stats.kernel_launches; GF_STEP("src_env");
 
     // ---- waves: greedy packing into what is left of the workspace ----
+    bp.off = (bp.off + 255) & ~(size_t)255;
+    if (bp.off >= workspace_bytes) { gf_set_error("workspace too small for the source cache"); return GOOFER_ERR_WORKSPACE; }
     const size_t wave_cap = workspace_bytes - bp.off;
     int i0 = 0;
     while (i0 < b->n_notes) {
