@@ -81,6 +81,7 @@ EXPORTS = [
     "goofer_version", "goofer_last_error", "goofer_plan_batch", "goofer_workspace_bytes", "goofer_render_batch",
     "goofer_render_batch_host", "goofer_host_release", "goofer_last_stats", "goofer_stft_batch", "goofer_istft_batch",
     "goofer_pulse_work_bytes", "goofer_pulse_train_batch", "goofer_onepole_batch", "goofer_debug_plan",
+    "goofer_profile", "goofer_profile_summary",
 ]
 
 
@@ -123,6 +124,9 @@ def load():
     L.goofer_onepole_batch.argtypes = [vp, vp, i32, i32, i32, dbl, i32, i32, vp, vp]
     L.goofer_debug_plan.restype = C.c_int
     L.goofer_debug_plan.argtypes = [C.POINTER(GooferBatch), i32, vp, sz]
+    L.goofer_profile.restype = None
+    L.goofer_profile.argtypes = [C.c_int]
+    L.goofer_profile_summary.restype = C.c_char_p
     _lib = L
     return L
 
@@ -137,3 +141,18 @@ def last_stats() -> dict:
     load().goofer_last_stats(C.byref(s))
     return {"kernel_launches": int(s.kernel_launches), "h2d_bytes": int(s.h2d_bytes), "d2h_bytes": int(s.d2h_bytes),
             "waves": int(s.waves)}
+
+
+def profile(enable: bool) -> None:
+    load().goofer_profile(1 if enable else 0)
+
+
+def profile_summary() -> dict:
+    """{kernel: (launches, total_ms)} since profile(True)."""
+    txt = load().goofer_profile_summary().decode()
+    out = {}
+    for part in txt.split(";"):
+        if part:
+            name, cnt, ms = part.split(":")
+            out[name] = (int(cnt), float(ms))
+    return out

@@ -8,6 +8,7 @@
 #include <cstring>
 #include <cmath>
 #include <vector>
+#include <string>
 #include <mutex>
 #include <algorithm>
 
@@ -46,8 +47,66 @@ static bool gf_debug_sync()
     if (v < 0) { const char *e = getenv("GOOFER_DEBUG_SYNC"); v = (e && e[0] == '1') ? 1 : 0; }
     return v == 1;
 }
+
+// per-kernel device timing (goofer_profile): one CUDA event after every launch, on the launching stream
+struct GfProf {
+    bool on = false;
+    std::vector<cudaEvent_t> pool;
+    std::vector<const char *> names;
+    size_t used = 0;
+    std::string summary;
+};
+static thread_local GfProf g_prof;
+
+static void gf_prof_mark(const char *name, cudaStream_t st)
+{
+    if (!g_prof.on) return;
+    if (g_prof.used == g_prof.pool.size()) {
+        cudaEvent_t e;
+        if (cudaEventCreate(&e) != cudaSuccess) return;
+        g_prof.pool.push_back(e);
+    }
+    cudaEventRecord(g_prof.pool[g_prof.used], st);
+    if (g_prof.names.size() <= g_prof.used) g_prof.names.push_back(name); else g_prof.names[g_prof.used] = name;
+    ++g_prof.used;
+}
+
+extern "C" void goofer_profile(int enable)
+{
+    g_prof.on = enable != 0;
+    g_prof.used = 0;
+}
+
+// "name:launches:total_ms;..." over every render call since goofer_profile(1); synchronises on the last event
+extern "C" const char *goofer_profile_summary(void)
+{
+    g_prof.summary.clear();
+    if (g_prof.used < 2) return g_prof.summary.c_str();
+    cudaEventSynchronize(g_prof.pool[g_prof.used - 1]);
+    std::vector<const char *> order;
+    std::vector<double> tot;
+    std::vector<long> cnt;
+    for (size_t i = 1; i < g_prof.used; ++i) {
+        const char *nm = g_prof.names[i];
+        if (std::strcmp(nm, "begin") == 0) continue;
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, g_prof.pool[i - 1], g_prof.pool[i]) != cudaSuccess) continue;
+        size_t k = 0;
+        while (k < order.size() && std::strcmp(order[k], nm) != 0) ++k;
+        if (k == order.size()) { order.push_back(nm); tot.push_back(0.0); cnt.push_back(0); }
+        tot[k] += ms; ++cnt[k];
+    }
+    char buf[128];
+    for (size_t k = 0; k < order.size(); ++k) {
+        snprintf(buf, sizeof(buf), "%s:%ld:%.6f;", order[k], cnt[k], tot[k]);
+        g_prof.summary += buf;
+    }
+    return g_prof.summary.c_str();
+}
+
 #define GF_STEP(name)                                                                              \
     do {                                                                                           \
+        gf_prof_mark(name, st);                                                                    \
         if (gf_debug_sync()) {                                                                     \
             cudaError_t e_ = cudaStreamSynchronize(st);                                            \
             if (e_ == cudaSuccess) e_ = cudaGetLastError();                                        \
@@ -435,6 +494,7 @@ extern "C" int goofer_render_batch(const GooferBatch *b, void *workspace, size_t
     }
     cudaStream_t st = (cudaStream_t)stream;
     if ((rc = gf_tables_init(plans[0].sr)) != 0) return rc;
+    gf_prof_mark("begin", st);
 
     Bump bp{(char *)workspace, workspace_bytes, 0};
     // ---- sources: decode / transpose once per call ----

@@ -355,6 +355,41 @@ class AssembledBatch:
             d.normals, d.nrm_total = None, 0
         d.out_total = self.out_total
 
+    def pin(self) -> "AssembledBatch":
+        """Move every host array the C library reads or writes into page-locked memory (torch owns it),
+        so that goofer_render_batch_host's copies run at PCIe speed and asynchronously."""
+        import torch
+        keep = self._pinned = []
+
+        def pinned(a: np.ndarray) -> np.ndarray:
+            t = torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
+            keep.append(t)
+            return t.numpy()
+
+        d = self.desc
+        self.phi = pinned(self.phi)
+        d.phi = self.phi.ctypes.data
+        self.bend = pinned(self.bend)
+        d.bend_cents = self.bend.ctypes.data
+        if self.normals is not None:
+            self.normals = pinned(self.normals)
+            d.normals = self.normals.ctypes.data
+        for i, s in enumerate(self.batch.sources):
+            g = self.src_arr[i]
+            if s.knots_log is not None:
+                g.knots_log_f16 = pinned(s.knots_log.view(np.int16)).ctypes.data
+                g.hz_knots = pinned(s.hz_knots).ctypes.data
+            if s.env_dense is not None:
+                g.env_dense = pinned(s.env_dense).ctypes.data
+            g.mask = pinned(s.mask).ctypes.data
+            for k in range(4):
+                tr = s.formants.get(k + 1)
+                if tr is not None and tr.size:
+                    g.formants[k] = pinned(tr).ctypes.data
+        n_out = 4 if self.taps else 1
+        self._out_bufs = [pinned(np.empty(max(1, self.out_total), dtype=np.float32)) for _ in range(n_out)]
+        return self
+
     def split(self, flat: np.ndarray) -> List[np.ndarray]:
         outs, off = [], 0
         for inf in self.infos:
@@ -365,12 +400,13 @@ class AssembledBatch:
     # ---- host-buffer entry point (numpy in, numpy out; copies inside the C library) ---------------
     def render_host(self):
         lib = capi.load()
-        out = np.empty(max(1, self.out_total), dtype=np.float32)
+        bufs = getattr(self, "_out_bufs", None)
+        out = bufs[0] if bufs else np.empty(max(1, self.out_total), dtype=np.float32)
         d = self.desc
         d.out = out.ctypes.data
         tap_arrays = None
         if self.taps:
-            tap_arrays = [np.empty_like(out) for _ in range(3)]
+            tap_arrays = bufs[1:4] if bufs else [np.empty_like(out) for _ in range(3)]
             d.tap_harm, d.tap_uv, d.tap_bre = (a.ctypes.data for a in tap_arrays)
         else:
             d.tap_harm = d.tap_uv = d.tap_bre = None

@@ -160,6 +160,13 @@ typedef struct GooferStats {
 } GooferStats;
 void goofer_last_stats(GooferStats *s);
 
+/* Per-kernel device timing for bench.py's roofline line: after goofer_profile(1) every kernel launch of
+ * goofer_render_batch on this thread is followed by a CUDA event on the launching stream;
+ * goofer_profile_summary() waits for the last one and returns "kernel:launches:total_ms;..." accumulated
+ * since the enable call (thread-local storage, valid until the next call). */
+void goofer_profile(int enable);
+const char *goofer_profile_summary(void);
+
 /* ---- stage-level entry points (device pointers; used by the Python mirror of gf.* and by tests) ---- */
 
 /* gf.stft (GOOFER.py:355-370): x (n_sig, n) f32 rows -> S (n_sig, 513, T) complex64 interleaved,
