@@ -224,10 +224,22 @@ static void gf_carve_note(const GfNotePlan &p, Bump &bp, GfNoteDev *nd, GfPassDe
     if (p.f0_jitter) d.z_sh = bp.arr<double>(n);
     if (p.vol_jitter) { d.z_srh = bp.arr<double>(n); d.z_srb = bp.arr<double>(n); d.vjm = bp.arr<float>(n); }
     if (p.sd > 0) d.sdm = bp.arr<float>(n);
-    if (p.pd != 0.0) d.dyn = bp.arr<float>(n);
+    if (p.pd != 0.0) { d.pd_in = bp.arr<float>(n); d.pd_dev = bp.arr<double>(n); d.pd_gm = bp.arr<float>(n); }
     if (note_needs_fx(p)) {
         d.f0n = bp.arr<float>(n);
         for (int k = 0; k < 4; ++k) d.fx[k] = bp.arr<float>(n);
+        for (int k = 0; k < 2; ++k) d.alpha[k] = bp.arr<float>(n);
+    }
+    if (p.add_subharm) {
+        d.sg_f0 = bp.arr<float>(n);
+        d.sg_cap = p.n_total / 4 + 64;
+        d.sg_ev_i = bp.arr<int>((size_t)d.sg_cap);
+        d.sg_ev_f = bp.arr<double>((size_t)d.sg_cap);
+        d.sg_rep = bp.arr<int>((size_t)d.sg_cap);
+        int m = 128;
+        while (m < 2 * d.sg_cap) m <<= 1;
+        d.sg_tab_n = m;
+        d.sg_tab = bp.arr<int2>((size_t)m);
     }
     (void)taps;
     for (int k = 0; k < p.n_passes; ++k) {
@@ -270,7 +282,7 @@ static size_t gf_wave_meta_bytes(size_t n_notes, size_t n_pass, size_t n_env_wor
 {
     return n_notes * (sizeof(GfNotePlan) + sizeof(GfNoteDev)) + n_pass * (sizeof(GfPassDev) + sizeof(GfPassScal)) +
            n_env_work * sizeof(int2) + n_frame_work * sizeof(int4) + n_fir * sizeof(GfFirJob) +
-           n_pass * 16 * sizeof(GfOnepoleJob) + 16 * 256;
+           n_pass * 16 * sizeof(GfOnepoleJob) + n_notes * (3 * sizeof(int) + 2 * sizeof(GfFirJob)) + 32 * 256;
 }
 
 #define GF_BLOCKS_PER_CTA 32      // output hop blocks one frame-kernel CTA owns (3 frames of halo each)
@@ -355,9 +367,9 @@ static int gf_upload(Bump &bp, const std::vector<T> &v, T **dptr, cudaStream_t s
 int gf_post_fx(const WaveHost &wh, const GfNotePlan *d_plans, const GfNoteDev *d_notes, const GfPassDev *d_passes,
                GfPassScal *d_scal, Bump &bp, int sr, int max_n, cudaStream_t st, int64_t *launches);
 int gf_growl(const WaveHost &wh, const GfNotePlan *d_plans, const GfNoteDev *d_notes, const GfPassDev *d_passes,
-             GfPassScal *d_scal, int max_n, cudaStream_t st, int64_t *launches);
-int gf_pitch_dyn(const WaveHost &wh, const GfNotePlan *d_plans, const GfNoteDev *d_notes, const float *bend, Bump &bp,
-                 int max_n, cudaStream_t st, int64_t *launches);
+             GfPassScal *d_scal, Bump &bp, int max_n, cudaStream_t st, int64_t *launches);
+int gf_pitch_dyn(const WaveHost &wh, const GfNotePlan *d_plans, const GfNoteDev *d_notes, Bump &bp, int sr, int max_n,
+                 cudaStream_t st, int64_t *launches);
 
 static int gf_render_wave(const GooferBatch *b, const std::vector<GfNotePlan> &all, int i0, int i1, const GfSourceDev *d_srcs,
                           Bump bp /* by value: wave region restarts every wave */, cudaStream_t st)
@@ -454,11 +466,11 @@ static int gf_render_wave(const GooferBatch *b, const std::vector<GfNotePlan> &a
     gf_launch_f0(d_plans, d_notes, d_passes, d_srcs, b->bend_cents, b->normals, nn, max_n, st); ++L; GF_STEP("f0");
     gf_launch_walk(d_passes, d_scal, (int)n_pass, sr, st); ++L; GF_STEP("walk");
     gf_launch_pulse(d_passes, d_scal, (int)n_pass, max_n, st); ++L; GF_STEP("pulse");
-    if ((rc = gf_growl(wh, d_plans, d_notes, d_passes, d_scal, max_n, st, &L)) != GOOFER_OK) return rc;
+    if ((rc = gf_growl(wh, d_plans, d_notes, d_passes, d_scal, bp, max_n, st, &L)) != GOOFER_OK) return rc;
     gf_launch_env(d_envw, (int)wh.env_work.size(), d_plans, d_notes, d_srcs, st); ++L; GF_STEP("env");
     gf_launch_frame(d_framew, (int)wh.frame_work.size(), d_passes, d_scal, d_notes, d_plans, st); ++L; GF_STEP("frame");
     gf_launch_peak(d_plans, d_notes, d_passes, d_scal, (int)n_pass, max_n, st); ++L; GF_STEP("peak");
-    if ((rc = gf_pitch_dyn(wh, d_plans, d_notes, b->bend_cents, bp, max_n, st, &L)) != GOOFER_OK) return rc;
+    if ((rc = gf_pitch_dyn(wh, d_plans, d_notes, bp, sr, max_n, st, &L)) != GOOFER_OK) return rc;
     if ((rc = gf_post_fx(wh, d_plans, d_notes, d_passes, d_scal, bp, sr, max_n, st, &L)) != GOOFER_OK) return rc;
     gf_launch_mix(d_plans, d_notes, d_passes, d_scal, nn, max_n, st); ++L; GF_STEP("mix");
     GF_CUDA(cudaGetLastError());

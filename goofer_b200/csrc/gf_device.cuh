@@ -59,7 +59,7 @@ struct GfPassScal {         // zeroed per wave, written by the device
     int max_T0;
     int err;
     int n_sub_events;
-    int pad;
+    int sub_max_len;        // longest growl pulse (samples)
 };
 
 struct GfNoteDev {
@@ -73,15 +73,25 @@ struct GfNoteDev {
     double *z_srh, *z_srb;  // smoothed sr noise
     float *vjm;             // gauss(vm, 20) (sr)
     float *sdm;             // gauss(mask_new, 20) (sd)
-    float *dyn;             // pd gain curve
-    float *fx[4];           // scratch streams for the post-FX filters
+    float *pd_in;           // pd: f32(midi - base)                     SillySampler.py:860-866
+    double *pd_dev;         // pd: gaussian-smoothed bend deviation (fp64)
+    float *pd_gm;           // pd: gauss(mask_new, 441)                  SillySampler.py:880
+    float *fx[4];           // post-FX streams: [0] harm, [1] bre, [2] / [3] layer or filter scratch
+    float *alpha[2];        // per-sample filter coefficients of the two concurrent one-pole jobs
+    // sg (growl) layer: modulated f0, event list, first-occurrence pulse bank  GOOFER.py:700-766
+    float *sg_f0;           // (n_total,) f32 apply_subharm_vibrato(f0)
+    int *sg_ev_i;           // (sg_cap,) event sample index
+    double *sg_ev_f;        // (sg_cap,) event sub_f0
+    int *sg_rep;            // (sg_cap,) index of the first event with the same '%.2f' key
+    int2 *sg_tab;           // (sg_tab_n,) open-addressing table: x = key, y = first event index
+    int sg_cap, sg_tab_n;
     double *noteScal;       // small per-note double scalars (maxima, rms)
     float *out;             // (n_total,) final output
     float *tap_harm, *tap_uv, *tap_bre;
     int pass0;              // first entry of this note in the pass arrays
 };
 
-enum { GF_NS_SHMAX = 0, GF_NS_SRHMAX, GF_NS_SRBMAX, GF_NS_R0, GF_NS_R1, GF_NS_PDREF, GF_NS_COUNT = 8 };
+enum { GF_NS_SHMAX = 0, GF_NS_SRHMAX, GF_NS_SRBMAX, GF_NS_R0, GF_NS_R1, GF_NS_PDREF, GF_NS_COUNT = 8 };   // R0 / R1: sums of squares
 
 // ---- job records of the generic kernels ----
 struct GfFirJob {
@@ -118,6 +128,34 @@ __device__ __forceinline__ int gf_reflect(int q, int n)
     q %= per;
     if (q < 0) q += per;
     return q < n ? q : per - q;
+}
+
+// np.linspace(0, 1, num)[i] / np.linspace(1, 0, num)[i] in fp64 (numpy: i * step + start, endpoint exact)
+__device__ __forceinline__ double gf_dlin01(int i, int num)
+{
+    if (num <= 1) return 0.0;
+    if (i == num - 1) return 1.0;
+    return (double)i * (1.0 / (double)(num - 1));
+}
+__device__ __forceinline__ double gf_dlin10(int i, int num)
+{
+    if (num <= 1) return 1.0;
+    if (i == num - 1) return 0.0;
+    return (double)i * (-1.0 / (double)(num - 1)) + 1.0;
+}
+
+// vocal-fry mask value at sample c (SillySampler.py:937-965): ones on [fry_a, fry_b) with 10 ms linear ramps (f32)
+__device__ __forceinline__ float gf_fry_at(const GfNotePlan &pl, int c)
+{
+    if (!pl.fry_mask_on || c < pl.fry_a || c >= pl.fry_b) return 0.0f;
+    float mf = 1.0f;
+    const int fade = pl.fry_fade;
+    if (fade > 0) {
+        const int a1 = min(pl.fry_b, pl.fry_a + fade), b0 = max(pl.fry_a, pl.fry_b - fade);
+        if (c < a1) mf = (float)gf_dlin01(c - pl.fry_a, a1 - pl.fry_a);
+        if (c >= b0) mf = (float)((double)mf * gf_dlin10(c - b0, pl.fry_b - b0));
+    }
+    return mf;
 }
 
 __device__ __forceinline__ void gf_atomic_max_pos(unsigned int *addr, float v)

@@ -72,6 +72,11 @@ gf_f0_kernel(const GfNotePlan *__restrict__ plans, const GfNoteDev *__restrict__
             }
         }
         if (nd.f0n) nd.f0n[i] = (float)f0;
+        if (nd.pd_in) {
+            // SillySampler.py:860-865: bend relative to the note (+ t), as float32
+            const double base = (double)pl.pitch_midi + ((double)pl.t_cents / 100.0);
+            nd.pd_in[i] = (float)(midi - base);
+        }
         for (int p = 0; p < pl.n_passes; ++p) {
             const GfPassDev &ps = passes[nd.pass0 + p];
             float v;

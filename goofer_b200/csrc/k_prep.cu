@@ -358,19 +358,7 @@ gf_env_kernel(const int2 *__restrict__ work, const GfNotePlan *__restrict__ plan
         // ---- vocal-fry envelope compression (SillySampler.py:967-995) ----
         if (pl.fry_mask_on) {
             const int c = min(pl.n_total - 1, te * GF_HOP + GF_HOP / 2);
-            float wfr = 0.0f;
-            if (c >= pl.fry_a && c < pl.fry_b) {
-                double m = 1.0;
-                const int fade = pl.fry_fade;
-                if (fade > 0) {
-                    const int a1 = min(pl.fry_b, pl.fry_a + fade), b0 = max(pl.fry_a, pl.fry_b - fade);
-                    if (c < a1) m *= (double)(float)gf_lin01(c - pl.fry_a, a1 - pl.fry_a);
-                    float mf = (float)m;
-                    if (c >= b0) mf = (float)((double)mf * gf_lin10(c - b0, pl.fry_b - b0));
-                    m = (double)mf;
-                }
-                wfr = (float)m;
-            }
+            const float wfr = gf_fry_at(pl, c);
             if (wfr > 1e-6f) {
                 const double s = 1.0 - (double)wfr * (1.0 - 0.92);
                 if (!(fabs(s - 1.0) < 1e-6)) {

@@ -107,13 +107,19 @@ gf_mix_kernel(const GfNotePlan *__restrict__ plans, const GfNoteDev *__restrict_
     float g_sa = 0.0f;
     if (p_sa >= 0) g_sa = gf_pass_gain(pl, scal[p_sa]);
     const bool fx = nd.fx[0] != nullptr;                  // harm / bre already post-processed into fx[0] / fx[1]
+    double fx_scale = 1.0;
+    if (fx && pl.tension != 0.0) {
+        // SillySampler.py:1136-1140 (gf.rms GOOFER.py:170-171)
+        const double r0 = sqrt(nd.noteScal[GF_NS_R0] / (double)n + 1e-12), r1 = sqrt(nd.noteScal[GF_NS_R1] / (double)n + 1e-12);
+        if (r1 > 0.0) fx_scale = r0 / r1;
+    }
+    const double pd_ref = nd.pd_dev ? nd.noteScal[GF_NS_PDREF] : 1.0;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         const GfStreams s = gf_pass_streams(pl, nd, p0, s0, i);
         float h = s.h * g0, b = s.b * g0;
         const float u = s.u * g0;
         if (nd.tap_harm) { nd.tap_harm[i] = h; nd.tap_uv[i] = u; nd.tap_bre[i] = b; }
-        double hd, bd;
-        if (fx) { hd = (double)nd.fx[0][i] * (double)nd.noteScal[GF_NS_R1]; bd = (double)nd.fx[1][i] * (double)nd.noteScal[GF_NS_R1]; h = (float)hd; b = (float)bd; }
+        if (fx) { h = (float)((double)nd.fx[0][i] * fx_scale); b = (float)((double)nd.fx[1][i] * fx_scale); }
         // SillySampler.py:1143-1151: harm * V (np.float64) + bre * B (f32) + uv * U (f32), * volume
         double out = (((double)h * pl.V + (double)(b * (float)pl.B)) + (double)(u * (float)pl.U)) * pl.volume;
         if (p_sa >= 0) {
@@ -122,7 +128,15 @@ gf_mix_kernel(const GfNotePlan *__restrict__ plans, const GfNoteDev *__restrict_
             const float au = a.u * g_sa, ab = a.b * g_sa;
             out = out * (1.0 - pl.sa) + ((double)((au + ab) * (float)pl.volume)) * pl.sa;
         }
-        if (nd.dyn) out = out * (double)nd.dyn[i];
+        if (nd.pd_dev) {
+            // SillySampler.py:869-881, 1174-1182
+            const double v = fmin(fmax(nd.pd_dev[i] / pd_ref, -1.0), 1.0);
+            const double db = (12.0 * fabs(pl.pd)) * (pl.pd > 0.0 ? v : -v);
+            float dynf = (float)pow(10.0, db / 20.0);
+            dynf = fminf(fmaxf(dynf, 1e-3f), 1e3f);
+            const double dyn = 1.0 + (double)(dynf - 1.0f) * (double)nd.pd_gm[i];
+            out = out * dyn;
+        }
         nd.out[i] = (float)out;
     }
 }
