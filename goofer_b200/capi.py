@@ -81,7 +81,7 @@ EXPORTS = [
     "goofer_version", "goofer_last_error", "goofer_plan_batch", "goofer_workspace_bytes", "goofer_render_batch",
     "goofer_render_batch_host", "goofer_host_release", "goofer_last_stats", "goofer_stft_batch", "goofer_istft_batch",
     "goofer_pulse_work_bytes", "goofer_pulse_train_batch", "goofer_onepole_batch", "goofer_debug_plan",
-    "goofer_profile", "goofer_profile_summary",
+    "goofer_profile", "goofer_profile_summary", "goofer_struct_size",
 ]
 
 
@@ -124,6 +124,12 @@ def load():
     L.goofer_onepole_batch.argtypes = [vp, vp, i32, i32, i32, dbl, i32, i32, vp, vp]
     L.goofer_debug_plan.restype = C.c_int
     L.goofer_debug_plan.argtypes = [C.POINTER(GooferBatch), i32, vp, sz]
+    L.goofer_struct_size.restype = sz
+    L.goofer_struct_size.argtypes = [C.c_int]
+    for which, rec in enumerate((GooferSource, GooferNote, GooferNotePlanInfo, GooferBatch, GooferStats)):
+        if int(L.goofer_struct_size(which)) != C.sizeof(rec):
+            raise ImportError(f"ABI mismatch: sizeof({rec.__name__}) is {C.sizeof(rec)} in capi.py but "
+                              f"{int(L.goofer_struct_size(which))} in libgoofer_b200.so")
     L.goofer_profile.restype = None
     L.goofer_profile.argtypes = [C.c_int]
     L.goofer_profile_summary.restype = C.c_char_p

@@ -30,6 +30,17 @@ void gf_set_error(const char *fmt, ...)
 extern "C" const char *goofer_last_error(void) { return g_err; }
 extern "C" int goofer_version(void) { return GOOFER_ABI_VERSION; }
 extern "C" void goofer_last_stats(GooferStats *s) { if (s) *s = g_stats; }
+extern "C" size_t goofer_struct_size(int which)
+{
+    switch (which) {
+    case 0: return sizeof(GooferSource);
+    case 1: return sizeof(GooferNote);
+    case 2: return sizeof(GooferNotePlanInfo);
+    case 3: return sizeof(GooferBatch);
+    case 4: return sizeof(GooferStats);
+    default: return 0;
+    }
+}
 
 #define GF_CUDA(call)                                                                              \
     do {                                                                                           \

@@ -1,0 +1,55 @@
+"""Note sharding across ranks.
+
+Notes are independent units -- the reference renders one note per process (SillySampler.sh:9) -- so a
+render batch is partitioned by note over the GPUs of a box with NO collective on the data path.  The only
+communication is the optional gather of per-rank results (object / padded tensor all_gather through
+torch.distributed: NCCL on GPUs, gloo in the CPU tests).
+"""
+from __future__ import annotations
+
+from typing import List, Sequence
+
+
+def contiguous_range(n_notes: int, rank: int, world: int) -> range:
+    """Contiguous, balanced-by-count slice of note indices of `rank` (first `n % world` ranks get one more)."""
+    if world <= 0 or not (0 <= rank < world):
+        raise ValueError(f"bad rank {rank} / world {world}")
+    base, extra = divmod(int(n_notes), world)
+    start = rank * base + min(rank, extra)
+    return range(start, start + base + (1 if rank < extra else 0))
+
+
+def note_cost(info: dict) -> int:
+    """Relative cost of a note: output samples x synth passes (a full-flag note runs gf.synthesize up to
+    four times, SillySampler.py:1006,1041,1067,1156)."""
+    return int(info["n_total"]) * int(info["n_passes"])
+
+
+def balanced_partition(costs: Sequence[int], world: int) -> List[List[int]]:
+    """Greedy longest-processing-time partition of note indices into `world` bins of near-equal cost.
+    Deterministic: ties go to the lowest rank; indices inside a bin stay in ascending order."""
+    if world <= 0:
+        raise ValueError("world must be positive")
+    bins: List[List[int]] = [[] for _ in range(world)]
+    load = [0] * world
+    for i in sorted(range(len(costs)), key=lambda k: (-int(costs[k]), k)):
+        r = min(range(world), key=lambda q: (load[q], q))
+        bins[r].append(i)
+        load[r] += int(costs[i])
+    for b in bins:
+        b.sort()
+    return bins
+
+
+def gather_outputs(local_indices: Sequence[int], local_outputs: Sequence, group=None) -> dict:
+    """All-gather {note index: output array} over the process group (no-op without torch.distributed)."""
+    import torch.distributed as dist
+    mine = {int(i): o for i, o in zip(local_indices, local_outputs)}
+    if not (dist.is_available() and dist.is_initialized()):
+        return mine
+    parts = [None] * dist.get_world_size(group)
+    dist.all_gather_object(parts, mine, group=group)
+    out = {}
+    for p in parts:
+        out.update(p)
+    return out

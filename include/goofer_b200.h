@@ -132,6 +132,9 @@ typedef struct GooferBatch {
 
 int goofer_version(void);
 const char *goofer_last_error(void);
+/* sizeof() of the ABI records as this library was compiled, for binding self-checks:
+ * 0 GooferSource, 1 GooferNote, 2 GooferNotePlanInfo, 3 GooferBatch, 4 GooferStats (0 for anything else) */
+size_t goofer_struct_size(int which);
 
 /* Planning only (CPU, no CUDA): fills info[n_notes].  Mirrors the integer/length bookkeeping of
  * SillySampler.py:453-500, 625-635, 766-788. Source pointers are not dereferenced. */

@@ -25,6 +25,10 @@ import contextlib
 import numpy as np
 
 REFERENCE_DIR = os.environ.get("GOOFER_REFERENCE_DIR", "/root/reference")
+# numba reads its configuration when it is first imported: cache=True at GOOFER.py:473 would otherwise
+# write __pycache__/*.nbi into the (read-only) reference tree
+os.environ.setdefault("NUMBA_CACHE_DIR", os.path.join(tempfile.gettempdir(), "goofer_numba_cache"))
+sys.dont_write_bytecode = True
 
 _state = {"loaded": False, "gf": None, "ss": None}
 

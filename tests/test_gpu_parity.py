@@ -1,0 +1,257 @@
+"""GPU (-m gpu): the CUDA path, called through the C ABI, against the oracle on identical inputs and identical
+host-supplied noise buffers.  Tolerances are BASELINE.json's: max-abs sample error <= 1e-4 of full scale
+(full scale = 1.0) and log-spectral distance <= 0.05 dB (floor -100 dB re the reference peak)."""
+import os
+
+import numpy as np
+import pytest
+
+import bench_data
+from goofer_b200 import capi, host, ops
+from oracle import dsp, resampler
+from tests import cases
+
+pytestmark = pytest.mark.gpu
+MAX_ABS, MAX_LSD = 1e-4, 0.05
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+@pytest.fixture(scope="module")
+def torch_cuda(lib):
+    import torch
+    assert torch.cuda.is_available(), "-m gpu tests need a CUDA device; goofer_b200 has no CPU fallback"
+    return torch
+
+
+def render_one(sf, cli, taps=False, device=True):
+    b = host.Batch()
+    b.add_source(sf)
+    b.add_note(host.NoteArgs.from_cli(0, cli))
+    ab = b.assemble(host.SeededNoise(cases.SEED_BASE, cases.SEED_LEGACY), taps=taps)
+    if not device:
+        return ab.render_host()
+    db = ab.to_device("cuda:0")
+    db.render()
+    outs = db.outputs()
+    if taps:
+        return outs, [ab.split(t[:ab.out_total].cpu().numpy()) for t in db.tap]
+    return outs
+
+
+# ---- stage level ------------------------------------------------------------------------------------------
+def test_stft_istft_stage(torch_cuda):
+    torch = torch_cuda
+    g = np.load(os.path.join(GOLD, "stages.npz"))
+    rng = np.random.default_rng(3)
+    for n in (4096, 44100, 300, 257):
+        x = (0.3 * rng.standard_normal((3, n))).astype(np.float32)
+        if n == 4096:
+            x[0] = g["stft_x"]
+        S = ops.stft(torch.from_numpy(x).cuda()).cpu().numpy()
+        for k in range(3):
+            ref = dsp.stft(x[k])
+            assert S[k].shape == ref.shape
+            assert np.max(np.abs(S[k] - ref)) <= 2e-6 * np.max(np.abs(ref))
+        if n == 4096:
+            assert np.max(np.abs(S[0] - g["stft_S"])) <= 2e-6 * np.max(np.abs(g["stft_S"]))     # reference's own output
+        T = S.shape[2]
+        Sr = (rng.standard_normal((2, 513, T)) + 1j * rng.standard_normal((2, 513, T))).astype(np.complex64)
+        for length in (256 * (T - 1), 256 * (T - 1) + 44, n):
+            if length < 256 * (T - 1):
+                continue
+            y = ops.istft(torch.from_numpy(Sr).cuda(), length).cpu().numpy()
+            for k in range(2):
+                ref = dsp.istft(Sr[k], length=length)
+                assert np.max(np.abs(y[k] - ref)) <= 2e-6 * max(1.0, np.max(np.abs(ref)))
+    y = ops.istft(torch.from_numpy(g["istft_S"]).cuda(), 4300).cpu().numpy()
+    assert np.max(np.abs(y - g["istft_y"])) <= 2e-6 * np.max(np.abs(g["istft_y"]))
+    # round trip: istft(stft(x)) == x away from the edges
+    x = (0.3 * rng.standard_normal(20000)).astype(np.float32)
+    xr = ops.istft(ops.stft(torch.from_numpy(x).cuda()), 20000).cpu().numpy()
+    assert np.max(np.abs(xr[:19900] - x[:19900])) <= 5e-6
+
+
+def test_pulse_train_onsets_bit_exact(torch_cuda):
+    """Rounding-tie pitches: a single moved onset shows up as an O(1) error."""
+    torch = torch_cuda
+    g = np.load(os.path.join(GOLD, "stages.npz"))
+    rows = []
+    for hz in g["tie_pitches"]:
+        f0 = np.full(2 * 44100, hz, dtype=np.float32)
+        f0[:3000] = 0.0
+        rows.append(f0)
+    rows.append(np.concatenate([np.linspace(90.0, 700.0, 44100), np.linspace(700.0, 60.0, 44100)]).astype(np.float32))
+    f0 = np.stack(rows)
+    got = ops.pulse_train(torch.from_numpy(f0).cuda(), 44100).cpu().numpy()
+    for k in range(f0.shape[0]):
+        ref = dsp.pulse_train(f0[k], 44100)
+        assert np.max(np.abs(got[k] - ref)) <= 2e-6, f"row {k}"
+    for k in range(len(g["tie_pitches"])):
+        assert np.max(np.abs(got[k][:8192] - g[f"pulse_head_{k}"])) <= 2e-6
+
+
+def test_onepole_stage(torch_cuda):
+    torch = torch_cuda
+    g = np.load(os.path.join(GOLD, "stages.npz"))
+    x, f0 = torch.from_numpy(g["op_x"]).cuda(), torch.from_numpy(g["op_f0"]).cuda()
+    lp = ops.onepole(x, f0, 44100, 1.4, order=3, btype="lowpass").cpu().numpy()
+    hp = ops.onepole(x, f0, 44100, 1.0, order=6, btype="highpass").cpu().numpy()
+    assert np.max(np.abs(lp - g["op_lp3"])) <= 2e-6 and np.max(np.abs(hp - g["op_hp6"])) <= 2e-6
+    rng = np.random.default_rng(5)
+    xs = (0.2 * rng.standard_normal((4, 30000))).astype(np.float32)
+    fs = np.abs(rng.standard_normal((4, 30000)) * 200 + 300).astype(np.float32)
+    fs[1, :5000] = 0
+    for order, bt, cf in ((1, "lowpass", 2.0), (5, "lowpass", 1.25), (4, "highpass", 0.6), (6, "highpass", 4.0)):
+        got = ops.onepole(torch.from_numpy(xs).cuda(), torch.from_numpy(fs).cuda(), 44100, cf, order=order, btype=bt).cpu().numpy()
+        for k in range(4):
+            ref = dsp.dyn_onepole(xs[k], fs[k], 44100, cf, order=order, btype=bt)
+            assert np.max(np.abs(got[k] - ref)) <= 5e-6
+
+
+# ---- whole notes ------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("case", cases.CASES, ids=[c[0] for c in cases.CASES])
+def test_render_case(case, torch_cuda):
+    name, si, secs, cli = case
+    feat, sf = cases.source_for(si, secs)
+    ref = cases.oracle_render(feat, cli)
+    got = render_one(sf, cli)[0].astype(np.float64)
+    assert got.shape == ref.shape
+    assert np.max(np.abs(got - ref)) <= MAX_ABS
+    assert cases.lsd_db(ref, got) <= MAX_LSD
+    gold = np.load(os.path.join(GOLD, "render_cases.npz"))
+    g32 = gold[f"out_{name}"].astype(np.float64)
+    cmp = got if len(got) <= 50000 else got[::int(gold["long_stride"][0])]
+    assert np.max(np.abs(cmp - g32)) <= MAX_ABS          # the reference's own output, committed
+
+
+def test_host_entry_point_and_taps(torch_cuda):
+    name, si, secs, cli = cases.CASES[2]
+    feat, sf = cases.source_for(si, secs)
+    taps = {}
+    ref = cases.oracle_render(feat, cli, taps=taps)
+    outs, tp = render_one(sf, cli, taps=True, device=False)
+    assert np.max(np.abs(outs[0].astype(np.float64) - ref)) <= MAX_ABS
+    gold = np.load(os.path.join(GOLD, "render_cases.npz"))
+    for key, arr in zip(("harm", "uv", "bre"), tp):
+        assert np.max(np.abs(arr[0] - gold[f"tap_{key}_{name}"])) <= MAX_ABS, key
+    st = capi.last_stats()
+    assert st["kernel_launches"] >= 10 and st["h2d_bytes"] > 0 and st["d2h_bytes"] == 4 * 4 * len(ref)
+
+
+def _workload_batch(workload, idx, n_sources=8):
+    b = host.Batch()
+    feats = [bench_data.make_source(s) for s in range(n_sources)]
+    for f in feats:
+        b.add_source(host.SourceFeatures.from_knot_pack(f, f["mask"], f["formants"], f["sr"], f["ylen"]))
+    for i in idx:
+        src, cli = bench_data.note_cli(i, workload, n_sources=n_sources)
+        b.add_note(host.NoteArgs.from_cli(src, cli))
+    noise = host.SeededNoise(base_seed=lambda j: 20000 + 16 * idx[j], legacy_seed=lambda j: 777 + idx[j])
+    return b, feats, noise
+
+
+def _oracle_workload_note(workload, i, feats, n_sources=8):
+    src, cli = bench_data.note_cli(i, workload, n_sources=n_sources)
+    f = feats[src]
+    env = dsp.decode_knots({"knot_vals_log": f["knot_vals_log"], "hz_knots": f["hz_knots"], "n_fft": 1024, "sr": 44100, "n_bins": 513})
+    feat = resampler.Features(env=env, mask=f["mask"], formants=f["formants"], sr=f["sr"], ylen=f["ylen"])
+    spec = resampler.NoteSpec.from_cli(*cli)
+    return resampler.resample(feat, spec, lambda n, T: resampler.noise_for_note(spec, n, T, 20000 + 16 * i, 777 + i))
+
+
+@pytest.mark.parametrize("workload,count,check", [("c2", 96, 12), ("c3", 24, 8)])
+def test_batch_against_oracle(workload, count, check, torch_cuda):
+    """BASELINE.json configs[1] / [2] parameterisation: a batch rendered in one call; a spread of its notes
+    is compared with the oracle, every note must be finite."""
+    idx = list(range(count))
+    b, feats, noise = _workload_batch(workload, idx)
+    db = b.assemble(noise).to_device("cuda:0")
+    db.render()
+    outs = db.outputs()
+    assert all(np.all(np.isfinite(o)) for o in outs)
+    worst = 0.0
+    for i in idx[:: max(1, count // check)]:
+        ref = _oracle_workload_note(workload, i, feats)
+        err = float(np.max(np.abs(outs[i].astype(np.float64) - ref)))
+        worst = max(worst, err)
+        assert err <= MAX_ABS, f"{workload} note {i}: {err}"
+        assert cases.lsd_db(ref, outs[i].astype(np.float64)) <= MAX_LSD
+    print(f"{workload}: worst max-abs {worst:.2e}")
+
+
+def test_batch_invariance_determinism_and_waves(torch_cuda):
+    """A note renders to the same bits alone, inside a batch, on a second run, and when a small workspace
+    forces the batch through several waves."""
+    import ctypes as C
+    torch = torch_cuda
+    idx = list(range(40))
+    b, feats, noise = _workload_batch("c3", idx)
+    ab = b.assemble(noise)
+    db = ab.to_device("cuda:0")
+    a = db.render().clone()
+    b2 = db.render().clone()
+    assert torch.equal(a, b2)
+    full = db.outputs()
+    # several waves: a workspace that only fits a few notes at a time
+    lib = capi.load()
+    small = int(lib.goofer_workspace_bytes(C.byref(db.desc), 4))
+    assert small < db.workspace.numel()
+    db.workspace = torch.empty(small, dtype=torch.uint8, device="cuda:0")
+    db.render()
+    torch.cuda.synchronize()
+    assert capi.last_stats()["waves"] > 1
+    waved = db.outputs()
+    for x, y in zip(full, waved):
+        assert np.array_equal(x, y)
+    # alone
+    for i in (0, 7, 23):
+        bb, _, nz = _workload_batch("c3", [i])
+        d1 = bb.assemble(nz).to_device("cuda:0")
+        d1.render()
+        assert np.array_equal(d1.outputs()[0], full[i])
+
+
+def test_properties_at_full_size(torch_cuda):
+    """BASELINE.json configs[1] at its full size (1,024 notes): size-independent properties."""
+    idx = list(range(1024))
+    b, feats, noise = _workload_batch("c2", idx, n_sources=64)
+    db = b.assemble(noise).to_device("cuda:0")
+    db.render()
+    outs = db.outputs()
+    peaks = np.array([np.max(np.abs(o)) for o in outs])
+    assert np.all(np.isfinite(peaks))
+    # P absent => every synth pass is peak-normalised to 1 (GOOFER.py:1208-1218); V = B = U = volume = 1
+    assert np.max(np.abs(peaks - 1.0)) <= 1e-5
+    # istft leaves the last n - 256 * (T - 1) samples exactly zero (GOOFER.py:407-409)
+    assert all(np.all(o[256 * 172:] == 0.0) for o in outs)
+    # volume is linear: the same note at volume 50 is half the note at volume 100
+    src, cli = bench_data.note_cli(5, "c2")
+    f = feats[src]
+    sf = host.SourceFeatures.from_knot_pack(f, f["mask"], f["formants"], f["sr"], f["ylen"])
+    halves = []
+    for vol in ("100", "50"):
+        c = list(cli)
+        c[7] = vol
+        bb = host.Batch()
+        bb.add_source(sf)
+        bb.add_note(host.NoteArgs.from_cli(0, c))
+        d = bb.assemble(host.SeededNoise(20000 + 16 * 5, 777 + 5)).to_device("cuda:0")
+        d.render()
+        halves.append(d.outputs()[0].astype(np.float64))
+    assert np.max(np.abs(halves[0] * 0.5 - halves[1])) <= 1e-7
+    assert np.array_equal(halves[0].astype(np.float32), outs[5])
+
+
+def test_error_paths(torch_cuda):
+    import ctypes as C
+    feat, sf = cases.source_for(0, 1.0)
+    b = host.Batch()
+    b.add_source(sf)
+    b.add_note(host.NoteArgs.from_cli(0, ["C4"]))
+    db = b.assemble(host.SeededNoise()).to_device("cuda:0")
+    lib = capi.load()
+    rc = lib.goofer_render_batch(C.byref(db.desc), db.workspace.data_ptr(), 1024, None)
+    assert rc == capi.ERR_WORKSPACE and b"workspace" in lib.goofer_last_error()
+    db.desc.phi_total = 10
+    rc = lib.goofer_render_batch(C.byref(db.desc), db.workspace.data_ptr(), db.workspace.numel(), None)
+    assert rc == capi.ERR_INVALID

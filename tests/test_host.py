@@ -1,0 +1,82 @@
+"""CPU: host-side parsing mirrors SillySampler.GooferResampler.__init__ (checked against the oracle's own
+restatement, which is pinned to the reference), .goofy loading, sharding helpers, bench workloads."""
+import os
+
+import numpy as np
+import pytest
+
+import bench_data
+from goofer_b200 import capi, host, shard
+from oracle import resampler
+
+
+def test_flag_regex_and_case_rules():
+    s = "g-20fa10/fb-10B20Mt50xyz5ES40Pd-30fstA7l2"
+    assert host.parse_flags(s) == resampler.parse_flag_string(s)
+    nt, _ = host.NoteArgs.from_cli(0, ["C4", "100", s]).to_struct(0)
+    fl = dict(zip(capi.FLAG_NAMES, nt.flag))
+    present = {n for i, n in enumerate(capi.FLAG_NAMES) if (nt.present >> i) & 1}
+    assert fl["g"] == -20 and fl["fa"] == 10 and fl["fb"] == -10 and fl["B"] == 20
+    assert fl["es"] == 40 and "es" in present          # case-insensitive lookup (SillySampler.py:384)
+    assert fl["pd"] == -30 and fl["L"] == 2 and fl["fsta"] == 7
+    assert "t" not in present                           # 'Mt' is its own (unknown) flag
+    with pytest.raises(TypeError):
+        host.NoteArgs.from_cli(0, ["C4", "100", "g_B5"]).to_struct(0)     # "g" without a number: None / 200.0 in the reference
+
+
+@pytest.mark.parametrize("s", ["AA", "AAAB#3#ACADAFAIALAOAQASATATASAQAOALAIAFADACAB#20#", "AA///+/9/7/5/3#30#/5/9AA#40#", "", "//#5#"])
+def test_pitch_string(s):
+    assert np.array_equal(host.pitch_string_to_cents(s), resampler.bend_cents(s))
+
+
+def test_note_names_and_roundtrip():
+    for nm in ("C4", "A3", "G#5", "C#-1", "B7"):
+        assert host.note_to_midi(nm) == resampler.midi_of(nm)
+    for m in range(24, 100):
+        assert host.note_to_midi(bench_data.midi_to_name(m)) == m
+    cents = np.array([0, 1, -1, 2047, -2048, 30, -30])
+    assert np.array_equal(host.pitch_string_to_cents(bench_data.cents_to_pitch_string(cents)), cents.astype(np.float32))
+    with pytest.raises(ValueError):
+        host.note_to_midi("H2")
+
+
+def test_load_goofy_reads_the_reference_format(tmp_path):
+    # the layout gf.save_features writes (GOOFER.py:287-317): npz, fp16 knots, pickled formant dict
+    src = bench_data.make_source(3)
+    path = os.path.join(tmp_path, "x_features.goofy")
+    with open(path, "wb") as fh:
+        np.savez_compressed(fh, mode=np.array(["knots"]), knot_vals_log=src["knot_vals_log"], hz_knots=src["hz_knots"],
+                            n_bins=np.array([513]), n_fft=np.array([1024]), f0_interp=np.zeros(8, np.float16),
+                            voicing_mask=src["mask"].astype(np.float16), formants=np.array(src["formants"], dtype=object),
+                            sr=np.array([44100]), y_len=np.array([src["ylen"]]))
+    sf = host.load_goofy(path)
+    assert sf.knots_log.dtype == np.float16 and sf.knots_log.shape == src["knot_vals_log"].shape
+    assert sf.sr == 44100 and sf.ylen == src["ylen"] and set(sf.formants) == {1, 2, 3, 4}
+    assert np.array_equal(sf.mask, src["mask"])
+
+
+def test_shard_helpers():
+    for n, w in ((10, 3), (1024, 8), (5, 8), (0, 2)):
+        got = [i for r in range(w) for i in shard.contiguous_range(n, r, w)]
+        assert got == list(range(n))
+        sizes = [len(shard.contiguous_range(n, r, w)) for r in range(w)]
+        assert max(sizes) - min(sizes) <= 1
+    costs = [4, 1, 1, 1, 1, 4, 2, 2]
+    bins = shard.balanced_partition(costs, 2)
+    assert sorted(i for b in bins for i in b) == list(range(8))
+    assert abs(sum(costs[i] for i in bins[0]) - sum(costs[i] for i in bins[1])) <= 1
+    with pytest.raises(ValueError):
+        shard.contiguous_range(4, 2, 2)
+
+
+def test_bench_workloads_plan(lib):
+    b = host.Batch()
+    for s in range(8):
+        f = bench_data.make_source(s)
+        b.add_source(host.SourceFeatures.from_knot_pack(f, f["mask"], f["formants"], f["sr"], f["ylen"]))
+    for i in range(16):
+        src, cli = bench_data.note_cli(i, "c3", n_sources=8)
+        b.add_note(host.NoteArgs.from_cli(src, cli))
+    ab = b.assemble(host.SeededNoise())
+    assert all(inf["n_total"] == 44100 and inf["t_out"] == 173 for inf in ab.infos)
+    assert bench_data.algorithmic_bytes({"need_phi": [1, 0, 0, 0], "need_nrm": [0] * 4, "t_out": 173, "n_total": 44100}, 172, 44100) == 1063492
