@@ -231,7 +231,6 @@ static void gf_carve_note(const GfNotePlan &p, Bump &bp, GfNoteDev *nd, GfPassDe
     d.envN = bp.arr<float>(tiles * GF_NBINS * GF_FT);
     d.vm = bp.arr<float>(n);
     d.ms_short = bp.arr<float>((n + 3) / 4);
-    d.noteScal = bp.arr<double>(GF_NS_COUNT);
     if (p.f0_jitter) d.z_sh = bp.arr<double>(n);
     if (p.vol_jitter) { d.z_srh = bp.arr<double>(n); d.z_srb = bp.arr<double>(n); d.vjm = bp.arr<float>(n); }
     if (p.sd > 0) d.sdm = bp.arr<float>(n);
@@ -291,7 +290,7 @@ static size_t gf_sources_bytes(const GooferBatch *b)
 // per-wave bookkeeping arrays (plans, note / pass records, scalars, work lists, job lists)
 static size_t gf_wave_meta_bytes(size_t n_notes, size_t n_pass, size_t n_env_work, size_t n_frame_work, size_t n_fir)
 {
-    return n_notes * (sizeof(GfNotePlan) + sizeof(GfNoteDev)) + n_pass * (sizeof(GfPassDev) + sizeof(GfPassScal)) +
+    return n_notes * (sizeof(GfNotePlan) + sizeof(GfNoteDev) + GF_NS_COUNT * sizeof(double)) + n_pass * (sizeof(GfPassDev) + sizeof(GfPassScal)) +
            n_env_work * sizeof(int2) + n_frame_work * sizeof(int4) + n_fir * sizeof(GfFirJob) +
            n_pass * 16 * sizeof(GfOnepoleJob) + n_notes * (3 * sizeof(int) + 2 * sizeof(GfFirJob)) + 32 * 256;
 }
@@ -367,12 +366,58 @@ struct WaveHost {
     std::vector<GfOnepoleJob> op_jobs;
 };
 
+// Metadata (plans, records, work lists, job lists) is staged in a thread-local page-locked arena so that
+// the uploads are truly asynchronous: a pageable source would make cudaMemcpyAsync wait for the stream.
+struct GfPinned { char *base = nullptr; size_t cap = 0, off = 0; };
+static thread_local GfPinned g_pin;
+
+static void *gf_pin_take(size_t bytes)
+{
+    bytes = (bytes + 255) & ~(size_t)255;
+    if (g_pin.off + bytes > g_pin.cap) {
+        // wrap (or grow): every copy that read the arena must have completed
+        cudaDeviceSynchronize();
+        if (bytes > g_pin.cap) {
+            if (g_pin.base) cudaFreeHost(g_pin.base);
+            g_pin.base = nullptr;
+            g_pin.cap = std::max(bytes * 2, (size_t)64 << 20);
+            if (cudaMallocHost((void **)&g_pin.base, g_pin.cap) != cudaSuccess) { g_pin.base = nullptr; g_pin.cap = 0; return nullptr; }
+        }
+        g_pin.off = 0;
+    }
+    void *p = g_pin.base + g_pin.off;
+    g_pin.off += bytes;
+    return p;
+}
+
+// The staged bytes are pulled in by a kernel that reads the (device-mapped) pinned arena directly, NOT by
+// cudaMemcpyAsync: a DMA copy would queue behind whatever bulk transfer occupies the H2D copy engine (the
+// host entry point streams hundreds of MB of noise phases on another stream) and stall the whole wave.
+__global__ void __launch_bounds__(256) gf_meta_copy_kernel(uint4 *__restrict__ dst, const uint4 *__restrict__ src, size_t n16)
+{
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += (size_t)gridDim.x * blockDim.x) dst[i] = src[i];
+}
+
+static int gf_meta_copy(void *dst, const void *stage, size_t bytes, cudaStream_t st)
+{
+    const size_t n16 = (bytes + 15) / 16;            // both sides are 256-byte aligned and padded
+    const int blocks = (int)std::min<size_t>((n16 + 255) / 256, 64);
+    gf_meta_copy_kernel<<<blocks, 256, 0, st>>>((uint4 *)dst, (const uint4 *)stage, n16);
+    GF_CUDA(cudaGetLastError());
+    return GOOFER_OK;
+}
+
 template <typename T>
 static int gf_upload(Bump &bp, const std::vector<T> &v, T **dptr, cudaStream_t st)
 {
     *dptr = bp.arr<T>(std::max<size_t>(v.size(), 1));
-    if (!v.empty()) GF_CUDA(cudaMemcpyAsync(*dptr, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice, st));
-    return GOOFER_OK;
+    if (v.empty() || !bp.base) return GOOFER_OK;
+    if (bp.off > bp.cap) { gf_set_error("internal: metadata overflows the workspace (%zu > %zu)", bp.off, bp.cap); return GOOFER_ERR_WORKSPACE; }
+    const size_t bytes = v.size() * sizeof(T);
+    void *stage = gf_pin_take(bytes);
+    if (!stage) { gf_set_error("cudaMallocHost failed for the metadata staging arena"); return GOOFER_ERR_CUDA; }
+    std::memcpy(stage, v.data(), bytes);
+    return gf_meta_copy(*dptr, stage, bytes, st);
 }
 
 int gf_post_fx(const WaveHost &wh, const GfNotePlan *d_plans, const GfNoteDev *d_notes, const GfPassDev *d_passes,
@@ -383,7 +428,7 @@ int gf_pitch_dyn(const WaveHost &wh, const GfNotePlan *d_plans, const GfNoteDev 
                  cudaStream_t st, int64_t *launches);
 
 static int gf_render_wave(const GooferBatch *b, const std::vector<GfNotePlan> &all, int i0, int i1, const GfSourceDev *d_srcs,
-                          Bump bp /* by value: wave region restarts every wave */, cudaStream_t st)
+                          Bump bp /* by value: wave region restarts every wave */, cudaStream_t st, cudaEvent_t phi_ready)
 {
     WaveHost wh;
     const int nn = i1 - i0;
@@ -395,11 +440,14 @@ static int gf_render_wave(const GooferBatch *b, const std::vector<GfNotePlan> &a
     for (int i = 0; i < nn; ++i) n_pass += wh.plans[i].n_passes;
     wh.passes.resize(n_pass);
     size_t pi = 0;
+    // per-note double scalars (maxima, rms sums, percentile): one block, one memset
+    double *d_nscal = bp.arr<double>((size_t)nn * GF_NS_COUNT);
     for (int i = 0; i < nn; ++i) {
         const GfNotePlan &p = wh.plans[i];
         max_n = std::max(max_n, p.n_total);
         gf_carve_note(p, bp, &wh.notes[i], &wh.passes[pi], false);
         GfNoteDev &nd = wh.notes[i];
+        nd.noteScal = d_nscal + (size_t)i * GF_NS_COUNT;
         nd.pass0 = (int)pi;
         nd.out = b->out + p.out_off;
         if (b->tap_harm && b->tap_uv && b->tap_bre) {
@@ -451,8 +499,6 @@ static int gf_render_wave(const GooferBatch *b, const std::vector<GfNotePlan> &a
         }
         pi += p.n_passes;
     }
-    // clear the per-note scalars in one go: they were carved from the wave region, zero the region's
-    // scalar blocks individually (small)
     GfNotePlan *d_plans; GfNoteDev *d_notes; GfPassDev *d_passes; int2 *d_envw; int4 *d_framew; GfFirJob *d_fir;
     int rc;
     if ((rc = gf_upload(bp, wh.plans, &d_plans, st)) != GOOFER_OK) return rc;
@@ -464,7 +510,7 @@ static int gf_render_wave(const GooferBatch *b, const std::vector<GfNotePlan> &a
     GfPassScal *d_scal = bp.arr<GfPassScal>(n_pass);
     if (bp.off > bp.cap) { gf_set_error("internal: wave overflows the workspace (%zu > %zu)", bp.off, bp.cap); return GOOFER_ERR_WORKSPACE; }
     GF_CUDA(cudaMemsetAsync(d_scal, 0, n_pass * sizeof(GfPassScal), st));
-    for (int i = 0; i < nn; ++i) GF_CUDA(cudaMemsetAsync(wh.notes[i].noteScal, 0, GF_NS_COUNT * sizeof(double), st));
+    GF_CUDA(cudaMemsetAsync(d_nscal, 0, (size_t)nn * GF_NS_COUNT * sizeof(double), st));
 
     int64_t &L = g_stats.kernel_launches;
     gf_launch_tracks(d_plans, d_notes, d_srcs, nn, st); ++L; GF_STEP("tracks");
@@ -479,6 +525,7 @@ static int gf_render_wave(const GooferBatch *b, const std::vector<GfNotePlan> &a
     gf_launch_pulse(d_passes, d_scal, (int)n_pass, max_n, st); ++L; GF_STEP("pulse");
     if ((rc = gf_growl(wh, d_plans, d_notes, d_passes, d_scal, bp, max_n, st, &L)) != GOOFER_OK) return rc;
     gf_launch_env(d_envw, (int)wh.env_work.size(), d_plans, d_notes, d_srcs, st); ++L; GF_STEP("env");
+    if (phi_ready) GF_CUDA(cudaStreamWaitEvent(st, phi_ready, 0));     // the first kernel that reads the noise phases
     gf_launch_frame(d_framew, (int)wh.frame_work.size(), d_passes, d_scal, d_notes, d_plans, st); ++L; GF_STEP("frame");
     gf_launch_peak(d_plans, d_notes, d_passes, d_scal, (int)n_pass, max_n, st); ++L; GF_STEP("peak");
     if ((rc = gf_pitch_dyn(wh, d_plans, d_notes, bp, sr, max_n, st, &L)) != GOOFER_OK) return rc;
@@ -489,7 +536,15 @@ static int gf_render_wave(const GooferBatch *b, const std::vector<GfNotePlan> &a
     return GOOFER_OK;
 }
 
+static int gf_render_batch_ex(const GooferBatch *b, void *workspace, size_t workspace_bytes, void *stream, cudaEvent_t phi_ready);
+
 extern "C" int goofer_render_batch(const GooferBatch *b, void *workspace, size_t workspace_bytes, void *stream)
+{
+    return gf_render_batch_ex(b, workspace, workspace_bytes, stream, nullptr);
+}
+
+// phi_ready (optional): event after which b->phi is valid; only the frame kernel waits for it
+static int gf_render_batch_ex(const GooferBatch *b, void *workspace, size_t workspace_bytes, void *stream, cudaEvent_t phi_ready)
 {
     int rc = gf_validate(b);
     if (rc != GOOFER_OK) return rc;
@@ -540,7 +595,12 @@ extern "C" int goofer_render_batch(const GooferBatch *b, void *workspace, size_t
     }
     GfSourceDev *d_srcs = bp.arr<GfSourceDev>(std::max(1, b->n_sources));
     if (bp.off > bp.cap) { gf_set_error("workspace too small for the source cache (%zu > %zu)", bp.off, bp.cap); return GOOFER_ERR_WORKSPACE; }
-    if (b->n_sources) GF_CUDA(cudaMemcpyAsync(d_srcs, srcs.data(), srcs.size() * sizeof(GfSourceDev), cudaMemcpyHostToDevice, st));
+    if (b->n_sources) {
+        void *stage = gf_pin_take(srcs.size() * sizeof(GfSourceDev));
+        if (!stage) { gf_set_error("cudaMallocHost failed for the metadata staging arena"); return GOOFER_ERR_CUDA; }
+        std::memcpy(stage, srcs.data(), srcs.size() * sizeof(GfSourceDev));
+        if ((rc = gf_meta_copy(d_srcs, stage, srcs.size() * sizeof(GfSourceDev), st)) != GOOFER_OK) return rc;
+    }
     gf_launch_src_env(d_srcs, b->n_sources, max_T, st); ++g_stats.kernel_launches; GF_STEP("src_env");
 
     // ---- waves: greedy packing into what is left of the workspace ----
@@ -565,7 +625,7 @@ extern "C" int goofer_render_batch(const GooferBatch *b, void *workspace, size_t
             return GOOFER_ERR_WORKSPACE;
         }
         Bump wave{(char *)workspace + bp.off, wave_cap, 0};
-        if ((rc = gf_render_wave(b, plans, i0, i1, d_srcs, wave, st)) != GOOFER_OK) return rc;
+        if ((rc = gf_render_wave(b, plans, i0, i1, d_srcs, wave, st, phi_ready)) != GOOFER_OK) return rc;
         // host-side work lists are reused by the next wave only after this one was enqueued; the
         // device regions are reused in stream order, so no extra synchronisation is needed
         i0 = i1;

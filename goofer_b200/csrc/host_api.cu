@@ -2,11 +2,14 @@
 // caller that owns numpy arrays passes).  Copies sources, noise and bends in, renders, copies the
 // output back; device and pinned staging buffers are cached per host thread.
 #include <cstdlib>
+#include <cstdint>
+#include <climits>
 
 struct GfHostCache {
     void *dev = nullptr;  size_t dev_cap = 0;
     void *ws = nullptr;   size_t ws_cap = 0;
-    cudaStream_t st = nullptr;
+    cudaStream_t st = nullptr, st_in = nullptr, st_out = nullptr;     // compute, H2D, D2H
+    std::vector<cudaEvent_t> ev;
 };
 static thread_local GfHostCache g_hc;
 
@@ -24,21 +27,32 @@ extern "C" void goofer_host_release(void)
 {
     if (g_hc.dev) cudaFree(g_hc.dev);
     if (g_hc.ws) cudaFree(g_hc.ws);
+    for (cudaEvent_t e : g_hc.ev) cudaEventDestroy(e);
     if (g_hc.st) cudaStreamDestroy(g_hc.st);
+    if (g_hc.st_in) cudaStreamDestroy(g_hc.st_in);
+    if (g_hc.st_out) cudaStreamDestroy(g_hc.st_out);
     g_hc = GfHostCache();
 }
 
+// Notes are rendered in a few large chunks.  Only the frame kernel reads the noise phases (2/3 of the input
+// bytes), so chunk c's phases stream in on st_in while its preparation kernels (tracks, f0, walk, pulse, env)
+// already run on st; chunk c's output leaves on st_out while chunk c+1 computes (PCIe is full duplex).
 extern "C" int goofer_render_batch_host(const GooferBatch *b)
 {
     int rc = gf_validate(b);
     if (rc != GOOFER_OK) return rc;
-    g_stats.h2d_bytes = 0; g_stats.d2h_bytes = 0;
+    g_stats.h2d_bytes = 0; g_stats.d2h_bytes = 0; g_stats.kernel_launches = 0; g_stats.waves = 0;
     if (b->n_notes == 0) return GOOFER_OK;
     if (!b->out || !b->phi || !b->bend_cents) { gf_set_error("NULL out / phi / bend_cents"); return GOOFER_ERR_INVALID; }
     if (!g_hc.st) GF_CUDA(cudaStreamCreateWithFlags(&g_hc.st, cudaStreamNonBlocking));
-    cudaStream_t st = g_hc.st;
+    if (!g_hc.st_in) GF_CUDA(cudaStreamCreateWithFlags(&g_hc.st_in, cudaStreamNonBlocking));
+    if (!g_hc.st_out) GF_CUDA(cudaStreamCreateWithFlags(&g_hc.st_out, cudaStreamNonBlocking));
+    cudaStream_t st = g_hc.st, st_in = g_hc.st_in, st_out = g_hc.st_out;
 
-    // ---- device image of every input array ----
+    std::vector<GfNotePlan> plans;
+    if ((rc = gf_make_plans(b, plans)) != GOOFER_OK) return rc;
+
+    // ---- device image of every input array (same element offsets as on the host) ----
     Bump sz{nullptr, 0, 0};
     auto carve = [&](Bump &bp, GooferBatch &db, std::vector<GooferSource> &ds) {
         for (int s = 0; s < b->n_sources; ++s) {
@@ -69,8 +83,14 @@ extern "C" int goofer_render_batch_host(const GooferBatch *b)
 
     auto h2d = [&](const void *dst, const void *src, size_t bytes) -> int {
         if (!bytes) return GOOFER_OK;
-        GF_CUDA(cudaMemcpyAsync(const_cast<void *>(dst), src, bytes, cudaMemcpyHostToDevice, st));
+        GF_CUDA(cudaMemcpyAsync(const_cast<void *>(dst), src, bytes, cudaMemcpyHostToDevice, st_in));
         g_stats.h2d_bytes += (int64_t)bytes;
+        return GOOFER_OK;
+    };
+    auto d2h = [&](void *dst, const void *src, size_t bytes) -> int {
+        if (!bytes) return GOOFER_OK;
+        GF_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, st_out));
+        g_stats.d2h_bytes += (int64_t)bytes;
         return GOOFER_OK;
     };
     for (int s = 0; s < b->n_sources; ++s) {
@@ -84,23 +104,78 @@ extern "C" int goofer_render_batch_host(const GooferBatch *b)
             if (g.formants[k] && (rc = h2d(d.formants[k], g.formants[k], sizeof(double) * (size_t)g.formant_len[k]))) return rc;
     }
     if ((rc = h2d(db.bend_cents, b->bend_cents, sizeof(float) * (size_t)b->bend_total))) return rc;
-    if ((rc = h2d(db.phi, b->phi, sizeof(float) * (size_t)b->phi_total))) return rc;
-    if (b->normals && (rc = h2d(db.normals, b->normals, sizeof(double) * (size_t)b->nrm_total))) return rc;
 
-    const size_t want = goofer_workspace_bytes(&db, 0);
+    // ---- chunks ----
+    int chunk = b->n_notes >= 256 ? (b->n_notes + 1) / 2 : b->n_notes;
+    {
+        const char *e = getenv("GOOFER_HOST_CHUNK");
+        if (e && atoi(e) > 0) chunk = atoi(e);
+    }
+    const int n_chunks = (b->n_notes + chunk - 1) / chunk;
+    const size_t want = goofer_workspace_bytes(&db, chunk);
     if (want == 0) return GOOFER_ERR_NOTE;
     if ((rc = gf_hc_reserve(&g_hc.ws, &g_hc.ws_cap, want)) != GOOFER_OK) return rc;
-    if ((rc = goofer_render_batch(&db, g_hc.ws, g_hc.ws_cap, st)) != GOOFER_OK) return rc;
-
-    auto d2h = [&](void *dst, const void *src, size_t bytes) -> int {
-        GF_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, st));
-        g_stats.d2h_bytes += (int64_t)bytes;
-        return GOOFER_OK;
-    };
-    if ((rc = d2h(b->out, db.out, sizeof(float) * (size_t)b->out_total))) return rc;
-    if (b->tap_harm && (rc = d2h(b->tap_harm, db.tap_harm, sizeof(float) * (size_t)b->out_total))) return rc;
-    if (b->tap_uv && (rc = d2h(b->tap_uv, db.tap_uv, sizeof(float) * (size_t)b->out_total))) return rc;
-    if (b->tap_bre && (rc = d2h(b->tap_bre, db.tap_bre, sizeof(float) * (size_t)b->out_total))) return rc;
+    while ((int)g_hc.ev.size() < 3 * n_chunks) {
+        cudaEvent_t e;
+        GF_CUDA(cudaEventCreate(&e));
+        g_hc.ev.push_back(e);
+    }
+    int64_t launches = 0;
+    int waves = 0;
+    for (int c = 0; c < n_chunks; ++c) {
+        const int i0 = c * chunk, i1 = std::min(b->n_notes, i0 + chunk);
+        // element ranges of this chunk's noise and output inside the concatenated buffers
+        int64_t plo = INT64_MAX, phi_hi = 0, nlo = INT64_MAX, nhi = 0, olo = INT64_MAX, ohi = 0;
+        for (int i = i0; i < i1; ++i) {
+            const GfNotePlan &p = plans[i];
+            for (int k = 0; k < p.n_passes; ++k) {
+                const int64_t o = p.phi_off[p.pass_kind[k]];
+                if (o < 0) { gf_set_error("note %d: phi slot %d not supplied", i, p.pass_kind[k]); return GOOFER_ERR_INVALID; }
+                plo = std::min(plo, o); phi_hi = std::max(phi_hi, o + (int64_t)GF_NBINS * p.T_out);
+            }
+            const int need[4] = {p.f0_jitter, p.vol_jitter, p.vol_jitter, p.sj > 0.0};
+            for (int k = 0; k < 4; ++k)
+                if (need[k]) {
+                    if (p.nrm_off[k] < 0) { gf_set_error("note %d: normal slot %d not supplied", i, k); return GOOFER_ERR_INVALID; }
+                    nlo = std::min(nlo, p.nrm_off[k]); nhi = std::max(nhi, p.nrm_off[k] + (int64_t)p.n_total);
+                }
+            olo = std::min(olo, p.out_off); ohi = std::max(ohi, p.out_off + (int64_t)p.n_total);
+        }
+        if (plo < 0 || phi_hi > b->phi_total || (nhi > 0 && (!b->normals || nlo < 0 || nhi > b->nrm_total)) || olo < 0 || ohi > b->out_total) {
+            gf_set_error("chunk %d: noise / output offsets outside their buffers", c);
+            return GOOFER_ERR_INVALID;
+        }
+        if (nhi > nlo && (rc = h2d(db.normals + nlo, b->normals + nlo, sizeof(double) * (size_t)(nhi - nlo)))) return rc;
+        GF_CUDA(cudaEventRecord(g_hc.ev[3 * c], st_in));             // sources, bends, this chunk's normals
+        if ((rc = h2d(db.phi + plo, b->phi + plo, sizeof(float) * (size_t)(phi_hi - plo)))) return rc;
+        GF_CUDA(cudaEventRecord(g_hc.ev[3 * c + 1], st_in));         // this chunk's phases
+        GF_CUDA(cudaStreamWaitEvent(st, g_hc.ev[3 * c], 0));
+        GooferBatch cb = db;
+        cb.notes = b->notes + i0;
+        cb.n_notes = i1 - i0;
+        if ((rc = gf_render_batch_ex(&cb, g_hc.ws, g_hc.ws_cap, st, g_hc.ev[3 * c + 1])) != GOOFER_OK) return rc;
+        launches += g_stats.kernel_launches;
+        waves += g_stats.waves;
+        GF_CUDA(cudaEventRecord(g_hc.ev[3 * c + 2], st));
+        GF_CUDA(cudaStreamWaitEvent(st_out, g_hc.ev[3 * c + 2], 0));
+        const size_t ob = sizeof(float) * (size_t)(ohi - olo);
+        if ((rc = d2h(b->out + olo, db.out + olo, ob))) return rc;
+        if (b->tap_harm && (rc = d2h(b->tap_harm + olo, db.tap_harm + olo, ob))) return rc;
+        if (b->tap_uv && (rc = d2h(b->tap_uv + olo, db.tap_uv + olo, ob))) return rc;
+        if (b->tap_bre && (rc = d2h(b->tap_bre + olo, db.tap_bre + olo, ob))) return rc;
+    }
+    g_stats.kernel_launches = launches;
+    g_stats.waves = waves;
+    GF_CUDA(cudaStreamSynchronize(st_out));
     GF_CUDA(cudaStreamSynchronize(st));
+    if (getenv("GOOFER_HOST_TRACE")) {
+        for (int c = 0; c < n_chunks; ++c) {
+            float a = 0, bq = 0, cq = 0;
+            cudaEventElapsedTime(&a, g_hc.ev[0], g_hc.ev[3 * c]);
+            cudaEventElapsedTime(&bq, g_hc.ev[0], g_hc.ev[3 * c + 1]);
+            cudaEventElapsedTime(&cq, g_hc.ev[0], g_hc.ev[3 * c + 2]);
+            fprintf(stderr, "[host trace] chunk %d: small-in %.3f ms, phi-in %.3f ms, compute-done %.3f ms (since first event)\n", c, a, bq, cq);
+        }
+    }
     return GOOFER_OK;
 }

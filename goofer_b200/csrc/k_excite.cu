@@ -10,6 +10,7 @@
 // reference; only the crossing *detection* is done in parallel (floor of the running totals).
 #include "gf_device.cuh"
 #include "gf_maps.cuh"
+#include <climits>
 
 #define GF_PI_D 3.141592653589793
 
@@ -142,92 +143,137 @@ __device__ __forceinline__ float gf_lf_table_max(double T, int T0)
     return m;
 }
 
-#define GF_WALK_WARPS 4
+#define GF_WALK_WARPS 2
+#define GF_WALK_U 4                   // 32-sample groups per iteration (loads of the next iteration are in flight)
+
+// one 32-sample group: lane L owns sample base + L.  `total` enters as the phase before the group and leaves
+// as the phase after it; returns this lane's running total.  Every lane runs the same left-to-right fp64
+// chain (bit-exact with the reference's scalar loop); the increments are staged through shared memory.
+__device__ __forceinline__ double gf_walk_chain(double *s_inc, double inc, int lane, double &total)
+{
+    s_inc[lane] = inc;
+    __syncwarp();
+    double run = total, mine = 0.0;
+    const double2 *s2 = reinterpret_cast<const double2 *>(s_inc);
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+        const double2 v = s2[k];
+        run = __dadd_rn(run, v.x);
+        if (lane == 2 * k) mine = run;
+        run = __dadd_rn(run, v.y);
+        if (lane == 2 * k + 1) mine = run;
+    }
+    total = run;
+    __syncwarp();
+    return mine;
+}
+
 __global__ void __launch_bounds__(32 * GF_WALK_WARPS)
 gf_walk_kernel(const GfPassDev *__restrict__ passes, GfPassScal *scal, int n_pass, int sr_i)
 {
-    __shared__ double s_inc[GF_WALK_WARPS][32];
+    __shared__ __align__(16) double s_inc[GF_WALK_WARPS][32];
     const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int pi = blockIdx.x * GF_WALK_WARPS + w;
     if (pi >= n_pass) return;
     const GfPassDev ps = passes[pi];
     const int n = ps.n_total;
     const double sr = (double)sr_i;
+    const float *__restrict__ f0 = ps.f0;
     double total = 0.0;
-    long long fired = 0;                // next_k - 1
+    int fired = 0;                      // next_k - 1
     float lv_carry = 160.0f;            // last_valid_f0 (GOOFER.py:477)
-    int count = 0, max_T0 = 0;
-    for (int base = 0; base < n; base += 32) {
-        const int i = base + lane;
-        const float f = (i < n) ? ps.f0[i] : 0.0f;
-        s_inc[w][lane] = (i < n) ? __ddiv_rn((double)f, sr) : 0.0;
-        __syncwarp();
-        // sequential left-to-right fp64 accumulation (every lane runs the same chain; lane k keeps total_k)
-        double run = total, mine = 0.0;
+    int count = 0;
+    float fcur[GF_WALK_U], fnext[GF_WALK_U];
 #pragma unroll
-        for (int k = 0; k < 32; ++k) {
-            run = __dadd_rn(run, s_inc[w][k]);
-            if (k == lane) mine = run;
-        }
-        total = run;
-        __syncwarp();
-        // pulses fired up to and including sample i = running max of floor(total)
-        long long m = (long long)floor(mine);
+    for (int u = 0; u < GF_WALK_U; ++u) { const int i = 32 * u + lane; fcur[u] = (i < n) ? f0[i] : 0.0f; }
+    for (int base = 0; base < n; base += 32 * GF_WALK_U) {
 #pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const long long v = __shfl_up_sync(0xffffffffu, m, o);
-            if (lane >= o) m = max(m, v);
+        for (int u = 0; u < GF_WALK_U; ++u) {
+            const int i = base + 32 * (GF_WALK_U + u) + lane;
+            fnext[u] = (i < n) ? f0[i] : 0.0f;
         }
-        m = max(m, fired);
-        long long prev = __shfl_up_sync(0xffffffffu, m, 1);
-        if (lane == 0) prev = fired;
-        const int cnt = (i < n) ? (int)(m - prev) : 0;
-        fired = __shfl_sync(0xffffffffu, m, 31);
-        // last f0 > 1e-6 at or before sample i
-        const bool valid = (i < n) && ((double)f > 1e-6);
-        const unsigned bal = __ballot_sync(0xffffffffu, valid);
-        const unsigned below = bal & ((2u << lane) - 1u);
-        const float cand = __shfl_sync(0xffffffffu, f, below ? (31 - __clz(below)) : 0);
-        const float lvf = below ? cand : lv_carry;
-        const float newc = __shfl_sync(0xffffffffu, f, bal ? (31 - __clz(bal)) : 0);
-        if (bal) lv_carry = newc;
-        int T0 = 0;
-        float tmax = 1.0f;
-        double lv = (double)lvf;
-        if (cnt > 0) {
-            if (!(lv > 1e-6)) lv = 1e-6;
-            const double T = __ddiv_rn(1.0, lv);
-            T0 = (int)rint(__dmul_rn(sr, T));
-            T0 = T0 < 3 ? 3 : (T0 > 8192 ? 8192 : T0);
-            tmax = gf_lf_table_max(T, T0);
-        }
-        int incl = cnt;
+        double inc[GF_WALK_U];
 #pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const int v = __shfl_up_sync(0xffffffffu, incl, o);
-            if (lane >= o) incl += v;
-        }
-        const int tile_total = __shfl_sync(0xffffffffu, incl, 31);
-        int slot = count + incl - cnt;
-        for (int c = 0; c < cnt; ++c, ++slot)
-            if (slot < ps.onset_cap) ps.onsets[slot] = make_int4(i, T0, __float_as_int((float)lv), __float_as_int(tmax));
-        count += tile_total;
-        int tm = T0;
+        for (int u = 0; u < GF_WALK_U; ++u) inc[u] = __ddiv_rn((double)fcur[u], sr);     // 0 beyond n
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) tm = max(tm, __shfl_xor_sync(0xffffffffu, tm, o));
-        max_T0 = max(max_T0, tm);
+        for (int u = 0; u < GF_WALK_U; ++u) {
+            const int i = base + 32 * u + lane;
+            const float f = fcur[u];
+            const double mine = gf_walk_chain(s_inc[w], inc[u], lane, total);
+            // pulses fired up to and including sample i = running max of floor(total)
+            int m = (i < n) ? (int)floor(mine) : INT_MIN;
+            const int gmax = __reduce_max_sync(0xffffffffu, m);
+            const bool valid = (i < n) && ((double)f > 1e-6);
+            const unsigned bal = __ballot_sync(0xffffffffu, valid);
+            if (gmax > fired) {
+                // rare path: at least one onset in this group
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const int v = __shfl_up_sync(0xffffffffu, m, o);
+                    if (lane >= o) m = max(m, v);
+                }
+                m = max(m, fired);
+                int prev = __shfl_up_sync(0xffffffffu, m, 1);
+                if (lane == 0) prev = fired;
+                const int cnt = (i < n) ? (m - prev) : 0;
+                // last f0 > 1e-6 at or before sample i
+                const unsigned below = bal & ((2u << lane) - 1u);
+                const float cand = __shfl_sync(0xffffffffu, f, below ? (31 - __clz(below)) : 0);
+                const float lvf = below ? cand : lv_carry;
+                int incl = cnt;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const int v = __shfl_up_sync(0xffffffffu, incl, o);
+                    if (lane >= o) incl += v;
+                }
+                int slot = count + incl - cnt;
+                for (int c = 0; c < cnt; ++c, ++slot)
+                    if (slot < ps.onset_cap) ps.onsets[slot] = make_int4(i, 0, __float_as_int(lvf), 0);   // T0 / table max: gf_onset_kernel
+                count += __shfl_sync(0xffffffffu, incl, 31);
+                fired = max(fired, gmax);
+            }
+            if (bal) lv_carry = __shfl_sync(0xffffffffu, f, 31 - __clz(bal));
+        }
+#pragma unroll
+        for (int u = 0; u < GF_WALK_U; ++u) fcur[u] = fnext[u];
     }
     if (lane == 0) {
         scal[pi].n_onsets = min(count, ps.onset_cap);
-        scal[pi].max_T0 = max_T0;
         if (count > ps.onset_cap) scal[pi].err = 1;
     }
+}
+
+// per onset: period length T0 = round(sr / last_valid_f0) clipped to [3, 8192] (GOOFER.py:495-499, Python
+// round = half to even) and the peak of its LF table (GOOFER.py:524-528); thread per onset
+__global__ void __launch_bounds__(128)
+gf_onset_kernel(const GfPassDev *__restrict__ passes, GfPassScal *scal, int sr_i)
+{
+    const GfPassDev ps = passes[blockIdx.y];
+    const int count = scal[blockIdx.y].n_onsets;
+    const double sr = (double)sr_i;
+    int mx = 0;
+    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < count; e += gridDim.x * blockDim.x) {
+        int4 o = ps.onsets[e];
+        double lv = (double)__int_as_float(o.z);
+        if (!(lv > 1e-6)) lv = 1e-6;
+        const double T = __ddiv_rn(1.0, lv);
+        int T0 = (int)rint(__dmul_rn(sr, T));
+        T0 = T0 < 3 ? 3 : (T0 > 8192 ? 8192 : T0);
+        o.y = T0;
+        o.z = __float_as_int((float)lv);
+        o.w = __float_as_int(gf_lf_table_max(T, T0));
+        ps.onsets[e] = o;
+        mx = max(mx, T0);
+    }
+    mx = __reduce_max_sync(0xffffffffu, mx);
+    if ((threadIdx.x & 31) == 0 && mx > 0) atomicMax(&scal[blockIdx.y].max_T0, mx);
 }
 
 void gf_launch_walk(const GfPassDev *passes, GfPassScal *scal, int n_pass, int sr, cudaStream_t st)
 {
     if (n_pass <= 0) return;
     gf_walk_kernel<<<(n_pass + GF_WALK_WARPS - 1) / GF_WALK_WARPS, 32 * GF_WALK_WARPS, 0, st>>>(passes, scal, n_pass, sr);
+    gf_onset_kernel<<<dim3(4, n_pass), 128, 0, st>>>(passes, scal, sr);
 }
 
 // ------------------------------------------------------------------------------------------------
