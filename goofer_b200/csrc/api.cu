@@ -222,13 +222,12 @@ struct NoteLayout {      // what one note takes from the wave region (computed i
 static void gf_carve_note(const GfNotePlan &p, Bump &bp, GfNoteDev *nd, GfPassDev *pd /* n_passes entries */, bool taps)
 {
     const size_t n = (size_t)p.n_total;
-    const size_t tiles = (size_t)(p.T_out + GF_FT - 1) / GF_FT;
     GfNoteDev d;
     std::memset(&d, 0, sizeof(d));
     d.trk_canon = bp.arr<float>(4 * (size_t)p.T_env);
     d.trk_clean = p.any_fst ? bp.arr<float>(8 * (size_t)p.T_env) : nullptr;
-    d.envF = bp.arr<float>(tiles * GF_NBINS * GF_FT);
-    d.envN = bp.arr<float>(tiles * GF_NBINS * GF_FT);
+    d.envF = bp.arr<float>((size_t)p.T_out * GF_ENVS_LD);
+    d.envN = bp.arr<float>((size_t)p.T_out * GF_ENVS_LD);
     d.vm = bp.arr<float>(n);
     d.ms_short = bp.arr<float>((n + 3) / 4);
     if (p.f0_jitter) d.z_sh = bp.arr<double>(n);

@@ -112,8 +112,7 @@ gf_frame_kernel(const int4 *__restrict__ work, const GfPassDev *__restrict__ pas
             const float f0f = sm.f0fr[f];
             const bool vo = sm.voiced[f] != 0;
             float2 *zf = &sm.z[2][f][0];
-            const size_t tile = (size_t)(t / GF_FT) * (GF_NBINS * GF_FT) + (t % GF_FT);
-            const float *eF = nd.envF + tile, *eN = nd.envN + tile;
+            const float *eF = nd.envF + (size_t)t * GF_ENVS_LD, *eN = nd.envN + (size_t)t * GF_ENVS_LD;
             const float *ph = ps.phi + t;
             const int nbin = (k == 0) ? 3 : 2;
             float2 H[3], B[3], V[3];
@@ -135,7 +134,7 @@ gf_frame_kernel(const int4 *__restrict__ work, const GfPassDev *__restrict__ pas
                     const float hp = gf_hp_sigmoid(d_tab.freq32[bq], f0f);
                     float2 s = make_float2(S[q].x * hp, S[q].y * hp);
                     local_max = fmaxf(local_max, hypotf(s.x, s.y) + 1e-8f);
-                    const float ef = eF[(size_t)bq * GF_FT], en = eN[(size_t)bq * GF_FT];
+                    const float ef = eF[bq], en = eN[bq];
                     const float bo = d_tab.boost[bq];
                     float2 h = make_float2(s.x * ef * bo, s.y * ef * bo);
                     float sn, cs;

@@ -163,24 +163,53 @@ void gf_launch_tracks(const GfNotePlan *plans, const GfNoteDev *notes, const GfS
 }
 
 // ------------------------------------------------------------------------------------------------
-// envelope: one warp per output frame, eight frames (one tile) per CTA
+// envelope: one warp per output frame, eight frames per CTA.  Lane L owns the 17 contiguous bins
+// [17 L, 17 L + 17) (513 = 30 * 17 + 3: lane 30 owns three bins, lane 31 none), which makes every FIR a
+// register-tiled sliding window over a reflect-padded shared-memory row (stride 17 is conflict free).
+// Values are f32 like the arrays the reference stores; positions / abscissae stay fp64.
 // ------------------------------------------------------------------------------------------------
 #define GF_ENV_WARPS GF_FT
-#define GF_ROW_LD 520
-#define GF_EPL 17           // bins per lane: 513 = 16 * 32 + 1
-#define GF_MAX_ES_TAPS 57   // sigma <= 7 -> radius 28
+#define GF_EPL 17           // bins per lane
+#define GF_ROW_L 32         // left padding of a row (reflect halo, radius <= 28)
+#define GF_ROW_LEN 600      // 32 + 513 + 55: the FIR windows of the last lanes read up to bin index 561
+#define GF_MAX_ES_TAPS 64   // radius <= 28 -> 57 taps, zero-padded to a multiple of 8
 
 struct GfEnvSmem {
-    float rows[GF_ENV_WARPS][2][GF_ROW_LD];
-    float tileF[GF_NBINS][GF_FT];
-    float tileN[GF_NBINS][GF_FT];
-    float tilt[GF_ROW_LD];
-    double es_taps[GF_MAX_ES_TAPS];
+    float rows[GF_ENV_WARPS][2][GF_ROW_LEN];
+    float tilt[GF_ENVS_LD];
+    float es_taps[GF_MAX_ES_TAPS];
 };
 
-// np.interp on the uniform grid freqs[i] = i * step (i <= 512, freqs[512] = nyq) with the linear
-// extrapolation of GOOFER.py:173-239 outside [0, nyq]
-__device__ __forceinline__ float gf_grid_interp(const float *row, double x, double step, double nyq)
+// fill the reflect halo of a row whose bins 0..512 are valid (numpy 'reflect': edge sample not repeated)
+__device__ __forceinline__ void gf_row_halo(float *row /* -> bin 0 */, int lane, int radius)
+{
+    for (int q = lane + 1; q <= radius; q += 32) { row[-q] = row[q]; row[512 + q] = row[512 - q]; }
+    __syncwarp();
+}
+
+// sliding-window FIR with runtime radius: out[e] = sum_j taps[j] * row[b0 + e + j - radius], taps zero-padded to x8
+__device__ __forceinline__ void gf_fir_rt(const float *row, int b0, const float *taps, int radius, float *out)
+{
+#pragma unroll
+    for (int e = 0; e < GF_EPL; ++e) out[e] = 0.0f;
+    const int ntap = 2 * radius + 1;
+    for (int j0 = 0; j0 < ntap; j0 += 8) {
+        float win[GF_EPL + 7];
+        const float *p = row + b0 + j0 - radius;
+#pragma unroll
+        for (int q = 0; q < GF_EPL + 7; ++q) win[q] = p[q];
+#pragma unroll
+        for (int jj = 0; jj < 8; ++jj) {
+            const float w = taps[j0 + jj];
+#pragma unroll
+            for (int e = 0; e < GF_EPL; ++e) out[e] = fmaf(w, win[e + jj], out[e]);
+        }
+    }
+}
+
+// np.interp on the uniform grid freqs[i] = i * step (freqs[512] = nyq) with the linear extrapolation of
+// GOOFER.py:173-239 outside [0, nyq]
+__device__ __forceinline__ float gf_grid_interp(const float *row, double x, double step, double inv_step, double nyq)
 {
     if (x < 0.0) {
         const double sl = ((double)row[1] - (double)row[0]) / (step - 0.0 + 1e-10);
@@ -191,19 +220,19 @@ __device__ __forceinline__ float gf_grid_interp(const float *row, double x, doub
         const double sr_ = ((double)row[512] - (double)row[511]) / (nyq - x1 + 1e-10);
         return (float)((double)row[512] + sr_ * (x - nyq));
     }
-    int j = (int)(x / step);
+    int j = (int)(x * inv_step);
     if (j > 512) j = 512;
     auto fq = [&](int i) { return i == 512 ? nyq : (double)i * step; };
     while (j > 0 && fq(j) > x) --j;
     while (j < 512 && fq(j + 1) <= x) ++j;
     if (j >= 512) return row[512];
     const double x0 = fq(j);
-    if (x0 == x) return row[j];
-    const double slope = ((double)row[j + 1] - (double)row[j]) / (fq(j + 1) - x0);
-    return (float)(slope * (x - x0) + (double)row[j]);
+    const double y0 = (double)row[j];
+    const double t = (x - x0) * inv_step;
+    return (float)fma((double)row[j + 1] - y0, t, y0);
 }
 
-__global__ void __launch_bounds__(32 * GF_ENV_WARPS)
+__global__ void __launch_bounds__(32 * GF_ENV_WARPS, 2)
 gf_env_kernel(const int2 *__restrict__ work, const GfNotePlan *__restrict__ plans, const GfNoteDev *__restrict__ notes,
               const GfSourceDev *__restrict__ srcs)
 {
@@ -217,6 +246,7 @@ gf_env_kernel(const int2 *__restrict__ work, const GfNotePlan *__restrict__ plan
     const int sr = pl.sr;
     const double nyq = (double)sr / 2.0;
     const double step = nyq / 512.0;
+    const double inv_step = 1.0 / step;
 
     const bool do_tilt = pl.brightness_env != 1.0;
     const bool do_es = pl.es != 0.0;
@@ -224,7 +254,6 @@ gf_env_kernel(const int2 *__restrict__ work, const GfNotePlan *__restrict__ plan
     int es_radius = 0;
     if (do_tilt) {
         // SillySampler.py:506-510: f32 linspace(1e-6, nyq), clip(f / nyq, .02, 1) ** alpha, / (mean + 1e-12)
-        // (mean via a CTA-wide fp64 sum; numpy's f32 pairwise mean differs by < 1e-7 relative)
         const float alpha = (float)fmin(fmax(pl.brightness_env - 1.0, -0.9), 1.0);
         const float nyqf = (float)((double)sr * 0.5);
         __shared__ double red[GF_ENV_WARPS];
@@ -249,214 +278,206 @@ gf_env_kernel(const int2 *__restrict__ work, const GfNotePlan *__restrict__ plan
         const double s = fabs(pl.es);
         const double sigma = pl.es < 0.0 ? (1.0 + 6.0 * s) : (0.8 + 4.0 * s);
         es_radius = (int)(4.0 * sigma + 0.5);
-        if (threadIdx.x < 2 * es_radius + 1) {
-            double norm = 0.0;
-            for (int j = 0; j <= 2 * es_radius; ++j) { const double t = (double)(j - es_radius) / sigma; norm += exp(-0.5 * t * t); }
-            sm.es_taps[threadIdx.x] = gf_gauss_tap(threadIdx.x, es_radius, sigma, norm);
+        if (threadIdx.x < GF_MAX_ES_TAPS) {
+            float tv = 0.0f;
+            if (threadIdx.x < 2 * es_radius + 1) {
+                double norm = 0.0;
+                for (int j = 0; j <= 2 * es_radius; ++j) { const double t = (double)(j - es_radius) / sigma; norm += exp(-0.5 * t * t); }
+                tv = (float)gf_gauss_tap(threadIdx.x, es_radius, sigma, norm);
+            }
+            sm.es_taps[threadIdx.x] = tv;
         }
     }
     __syncthreads();
 
     const int t = wk.y * GF_FT + warp;
-    if (t < pl.T_out) {
-        const int te = min(t, pl.T_env - 1);              // GOOFER.py:1115-1119 trim / edge-pad to the STFT grid
-        float *rA = sm.rows[warp][0], *rB = sm.rows[warp][1];
-        GfMix mix;
-        gf_env_mix(pl, te, mix);
-        double acc[GF_EPL];
+    if (t >= pl.T_out) return;
+    const int te = min(t, pl.T_env - 1);                  // GOOFER.py:1115-1119 trim / edge-pad to the STFT grid
+    float *rA = sm.rows[warp][0] + GF_ROW_L, *rB = sm.rows[warp][1] + GF_ROW_L;
+    // the FIR windows also touch cells outside [-radius, 512 + radius] (zero-padded taps, idle lanes): they
+    // must hold finite values, 0 * NaN left over from an earlier kernel would poison the sums
+    for (int q = lane; q < 2 * GF_ROW_LEN; q += 32) sm.rows[warp][0][q] = 0.0f;
+    __syncwarp();
+    const int b0 = min(GF_EPL * lane, 510);               // lane 31 owns nothing: it shadows lane 30 (reads stay inside the row)
+    const int nown = (lane == 31) ? 0 : min(GF_EPL, GF_NBINS - b0);   // bins this lane owns
+
+    GfMix mix;
+    gf_env_mix(pl, te, mix);
+    float acc[GF_EPL];
 #pragma unroll
-        for (int e = 0; e < GF_EPL; ++e) acc[e] = 0.0;
-        for (int m = 0; m < mix.n; ++m) {
-            const float *src = sc.envS + (size_t)gf_src_frame(pl, mix.f[m]) * GF_ENVS_LD;
-            float *cur = rA, *oth = rB;
+    for (int e = 0; e < GF_EPL; ++e) acc[e] = 0.0f;
+    for (int m = 0; m < mix.n; ++m) {
+        const float *src = sc.envS + (size_t)gf_src_frame(pl, mix.f[m]) * GF_ENVS_LD;
+        float *cur = rA, *oth = rB;
+        for (int b = lane; b < GF_NBINS; b += 32) cur[b] = do_tilt ? src[b] * sm.tilt[b] : src[b];
+        __syncwarp();
+        if (do_es) {
+            // SillySampler.py:518-551: blur (es<0) or unsharp mask (es>0) along frequency, then per-frame mean match
+            gf_row_halo(cur, lane, es_radius);
+            float mod[GF_EPL];
+            gf_fir_rt(cur, b0, sm.es_taps, es_radius, mod);
+            const float s5 = (float)(5.0 * fabs(pl.es));
+            float sum0 = 0.0f, sum1 = 0.0f;
+#pragma unroll
             for (int e = 0; e < GF_EPL; ++e) {
-                const int b = lane + 32 * e;
-                if (b < GF_NBINS) cur[b] = do_tilt ? src[b] * sm.tilt[b] : src[b];
-            }
-            __syncwarp();
-            if (do_es) {
-                // SillySampler.py:518-551
-                const double s = fabs(pl.es);
-                double sum0 = 0.0, sum1 = 0.0;
-                double mod[GF_EPL];
-                for (int e = 0; e < GF_EPL; ++e) {
-                    const int b = lane + 32 * e;
-                    mod[e] = 0.0;
-                    if (b < GF_NBINS) {
-                        double blur = 0.0;
-                        for (int j = 0; j <= 2 * es_radius; ++j) {
-                            int q = b + j - es_radius;
-                            q = q < 0 ? -q : (q > 512 ? 1024 - q : q);
-                            blur += sm.es_taps[j] * (double)cur[q];
-                        }
-                        const double x = (double)cur[b];
-                        mod[e] = pl.es < 0.0 ? blur : fmax(0.0, x + (5.0 * s) * (x - blur));
-                        sum0 += x;
-                        sum1 += mod[e];
-                    }
+                if (e < nown) {
+                    const float x = cur[b0 + e];
+                    if (pl.es > 0.0) mod[e] = fmaxf(0.0f, fmaf(s5, x - mod[e], x));
+                    sum0 += x;
+                    sum1 += mod[e];
                 }
-                sum0 = gf_warp_sum(sum0);
-                sum1 = gf_warp_sum(sum1);
-                const float m0 = (float)(sum0 / (double)GF_NBINS);
-                const double m1 = sum1 / (double)GF_NBINS;
-                const double ratio = (double)m0 / (m1 + 1e-12);
+            }
+            const double t0 = gf_warp_sum((double)sum0), t1 = gf_warp_sum((double)sum1);
+            const float m0 = (float)(t0 / (double)GF_NBINS);
+            const double m1 = t1 / (double)GF_NBINS;
+            const float ratio = (float)((double)m0 / (m1 + 1e-12));
+#pragma unroll
+            for (int e = 0; e < GF_EPL; ++e)
+                if (e < nown) { const float y = mod[e] * ratio; oth[b0 + e] = pl.es < 0.0 ? fmaxf(0.0f, y) : y; }
+            __syncwarp();
+            float *sw = cur; cur = oth; oth = sw;
+        }
+        const float wm = (float)mix.w[m];
+        if (do_fw) {
+            // SillySampler.py:555-569: resample at (b - 256.5) (1 + fw) + 256.5, clipped, 2-tap lerp
+#pragma unroll
+            for (int e = 0; e < GF_EPL; ++e) {
+                if (e < nown) {
+                    double pos = ((double)(b0 + e) - 513.0 / 2.0) * (1.0 + pl.fw) + 513.0 / 2.0;
+                    pos = fmin(fmax(pos, 0.0), 512.0);
+                    const int lo = (int)pos;
+                    const int hi = min(lo + 1, 512);
+                    const float fr = (float)(pos - (double)lo);
+                    acc[e] = fmaf(wm, fmaf(fr, cur[hi] - cur[lo], cur[lo]), acc[e]);
+                }
+            }
+        } else {
+#pragma unroll
+            for (int e = 0; e < GF_EPL; ++e)
+                if (e < nown) acc[e] = fmaf(wm, cur[b0 + e], acc[e]);
+        }
+        __syncwarp();
+    }
+    // ---- fst bells (SillySampler.py:808-832), f32 ----
+    if (pl.any_fst) {
+        const float sig[4] = {100.0f, 200.0f, 350.0f, 500.0f};
+        for (int k = 0; k < 4; ++k) {
+            const double sk = pl.fst[k];
+            if (fabs(sk) < 1e-6) continue;
+            const float Fk = nd.trk_clean[(size_t)k * pl.T_env + te];
+            if (!isfinite(Fk) || !(Fk > 50.0f) || !((double)Fk < (double)sr * 0.5)) continue;
+            const float sv = (float)((1.0 + sk) - 1.0);
+            const float isg = 1.0f / sig[k];
+#pragma unroll
+            for (int e = 0; e < GF_EPL; ++e) {
+                const int b = b0 + e;
+                const float fb = (b >= 512) ? (float)nyq : (float)((double)b * step);
+                const float d = (fb - Fk) * isg;
+                acc[e] *= fmaf(sv, __expf(-0.5f * (d * d)), 1.0f);
+            }
+        }
+    }
+    float *cur = rA, *oth = rB;
+#pragma unroll
+    for (int e = 0; e < GF_EPL; ++e)
+        if (e < nown) cur[b0 + e] = acc[e];
+    __syncwarp();
+    // ---- vocal-fry envelope compression (SillySampler.py:967-995) ----
+    if (pl.fry_mask_on) {
+        const int c = min(pl.n_total - 1, te * GF_HOP + GF_HOP / 2);
+        const float wfr = gf_fry_at(pl, c);
+        if (wfr > 1e-6f) {
+            const double s = 1.0 - (double)wfr * (1.0 - 0.92);
+            if (!(fabs(s - 1.0) < 1e-6)) {
+                const double inv_s = 1.0 / s;
+#pragma unroll
                 for (int e = 0; e < GF_EPL; ++e) {
-                    const int b = lane + 32 * e;
-                    if (b < GF_NBINS) { float y = (float)(mod[e] * ratio); oth[b] = pl.es < 0.0 ? fmaxf(0.0f, y) : y; }
+                    if (e < nown) {
+                        const double sp = fmin(fmax((double)(b0 + e) * inv_s, 0.0), 512.0);
+                        const int lo = (int)sp;
+                        const int hi = min(lo + 1, 512);
+                        const float fr = (float)(sp - (double)lo);
+                        oth[b0 + e] = fmaf(fr, cur[hi] - cur[lo], cur[lo]);
+                    }
                 }
                 __syncwarp();
                 float *sw = cur; cur = oth; oth = sw;
             }
-            const double wm = mix.w[m];
-            for (int e = 0; e < GF_EPL; ++e) {
-                const int b = lane + 32 * e;
-                if (b < GF_NBINS) {
-                    float y;
-                    if (do_fw) {
-                        // SillySampler.py:555-569
-                        double pos = ((double)b - 513.0 / 2.0) * (1.0 + pl.fw) + 513.0 / 2.0;
-                        pos = fmin(fmax(pos, 0.0), 512.0);
-                        const int lo = (int)floor(pos);
-                        const int hi = min(lo + 1, 512);
-                        const double fr = pos - (double)lo;
-                        y = (float)((1.0 - fr) * (double)cur[lo] + fr * (double)cur[hi]);
-                    } else y = cur[b];
-                    acc[e] += wm * (double)y;
-                }
-            }
-            __syncwarp();
         }
-        // ---- fst bells (SillySampler.py:808-832), f32 ----
-        if (pl.any_fst) {
-            const float sig[4] = {100.0f, 200.0f, 350.0f, 500.0f};
-            float gain[GF_EPL];
+    }
+    // ---- env4breath: Gaussian sigma 1.75 of env_new (GOOFER.py:993), before the formant warps ----
+    {
+        gf_row_halo(cur, lane, 7);
+        float g[15];
 #pragma unroll
-            for (int e = 0; e < GF_EPL; ++e) gain[e] = 1.0f;
-            for (int k = 0; k < 4; ++k) {
-                const double sk = pl.fst[k];
-                if (fabs(sk) < 1e-6) continue;
-                const float Fk = nd.trk_clean[(size_t)k * pl.T_env + te];
-                if (!isfinite(Fk) || !(Fk > 50.0f) || !((double)Fk < (double)sr * 0.5)) continue;
-                const float sv = (float)((1.0 + sk) - 1.0);
-                for (int e = 0; e < GF_EPL; ++e) {
-                    const int b = lane + 32 * e;
-                    const float fb = (b == 512) ? (float)nyq : (float)((double)b * step);
-                    const float d = (fb - Fk) / sig[k];
-                    const float w = expf(-0.5f * (d * d));
-                    gain[e] *= 1.0f + sv * w;
-                }
-            }
+        for (int j = 0; j < 15; ++j) g[j] = (float)d_tab.g175[j];
+        float win[GF_EPL + 14];
 #pragma unroll
-            for (int e = 0; e < GF_EPL; ++e) acc[e] *= (double)gain[e];
-        }
-        float *cur = rA, *oth = rB;
+        for (int q = 0; q < GF_EPL + 14; ++q) win[q] = cur[b0 - 7 + q];
+#pragma unroll
         for (int e = 0; e < GF_EPL; ++e) {
-            const int b = lane + 32 * e;
-            if (b < GF_NBINS) cur[b] = (float)acc[e];
+            float a = 0.0f;
+#pragma unroll
+            for (int j = 0; j < 15; ++j) a = fmaf(g[j], win[e + j], a);
+            if (e < nown) oth[b0 + e] = a;
         }
         __syncwarp();
-        // ---- vocal-fry envelope compression (SillySampler.py:967-995) ----
-        if (pl.fry_mask_on) {
-            const int c = min(pl.n_total - 1, te * GF_HOP + GF_HOP / 2);
-            const float wfr = gf_fry_at(pl, c);
-            if (wfr > 1e-6f) {
-                const double s = 1.0 - (double)wfr * (1.0 - 0.92);
-                if (!(fabs(s - 1.0) < 1e-6)) {
-                    for (int e = 0; e < GF_EPL; ++e) {
-                        const int b = lane + 32 * e;
-                        if (b < GF_NBINS) {
-                            double sp = fmin(fmax((double)b / s, 0.0), 512.0);
-                            const int lo = (int)floor(sp);
-                            const int hi = min(lo + 1, 512);
-                            const double fr = sp - (double)lo;
-                            oth[b] = (float)((1.0 - fr) * (double)cur[lo] + fr * (double)cur[hi]);
-                        }
-                    }
-                    __syncwarp();
-                    float *sw = cur; cur = oth; oth = sw;
-                }
-            }
+        float *dstN = nd.envN + (size_t)t * GF_ENVS_LD;
+        for (int b = lane; b < GF_NBINS; b += 32) dstN[b] = oth[b];
+        __syncwarp();
+    }
+    // ---- F1..F4 warp (GOOFER.py:840-875) ----
+    if (pl.any_F_shift) {
+        double xs[6], xd[6], sl[5];
+        int nk = 0;
+        xs[nk] = 0.0; xd[nk] = 0.0; ++nk;
+        for (int k = 0; k < 4; ++k) {
+            const double fo = (double)nd.trk_canon[(size_t)k * pl.T_env + te];
+            const double fs = fo * pl.F_shift[k];
+            if (fo > 50.0 && fo < nyq && fs > 50.0) { xs[nk] = fo; xd[nk] = fs; ++nk; }
         }
-        // ---- env4breath: Gaussian sigma 1.75 of env_new (GOOFER.py:993), before the formant warps ----
-        for (int e = 0; e < GF_EPL; ++e) {
-            const int b = lane + 32 * e;
-            if (b < GF_NBINS) {
-                double a = 0.0;
+        xs[nk] = nyq; xd[nk] = nyq; ++nk;
+        for (int j = 0; j + 1 < nk; ++j) sl[j] = (xs[j + 1] - xs[j]) / (xd[j + 1] - xd[j]);
 #pragma unroll
-                for (int j = 0; j < 15; ++j) {
-                    int q = b + j - 7;
-                    q = q < 0 ? -q : (q > 512 ? 1024 - q : q);
-                    a += d_tab.g175[j] * (double)cur[q];
-                }
-                sm.tileN[b][warp] = (float)a;
-            }
-        }
-        // ---- F1..F4 warp (GOOFER.py:840-875) ----
-        if (pl.any_F_shift) {
-            double xs[6], xd[6];
-            int nk = 0;
-            xs[nk] = 0.0; xd[nk] = 0.0; ++nk;
-            for (int k = 0; k < 4; ++k) {
-                const double fo = (double)nd.trk_canon[(size_t)k * pl.T_env + te];
-                const double fs = fo * pl.F_shift[k];
-                if (fo > 50.0 && fo < nyq && fs > 50.0) { xs[nk] = fo; xd[nk] = fs; ++nk; }
-            }
-            xs[nk] = nyq; xd[nk] = nyq; ++nk;
-            for (int e = 0; e < GF_EPL; ++e) {
-                const int b = lane + 32 * e;
-                if (b < GF_NBINS) {
-                    const double x = (b == 512) ? nyq : (double)b * step;
-                    // np.interp(x, xd, xs) (linear search semantics) -- x is always inside [xd[0], xd[-1]] = [0, nyq]
-                    double wf;
-                    if (x > xd[nk - 1]) wf = xs[nk - 1];
-                    else if (x < xd[0]) wf = xs[0];
-                    else {
-                        int i = 0;
-                        while (i < nk && x >= xd[i]) ++i;
-                        const int j = i - 1;
-                        if (j >= nk - 1) wf = xs[nk - 1];
-                        else if (xd[j] == x) wf = xs[j];
-                        else {
-                            const double slope = (xs[j + 1] - xs[j]) / (xd[j + 1] - xd[j]);
-                            wf = slope * (x - xd[j]) + xs[j];
-                        }
-                    }
-                    oth[b] = gf_grid_interp(cur, wf, step, nyq);
-                }
-            }
-            __syncwarp();
-            float *sw = cur; cur = oth; oth = sw;
-        }
-        // ---- g: shift all formants (GOOFER.py:618-627) ----
-        if (pl.formant_shift != 1.0) {
-            for (int e = 0; e < GF_EPL; ++e) {
-                const int b = lane + 32 * e;
-                if (b < GF_NBINS) {
-                    const double x = (b == 512) ? nyq : (double)b * step;
-                    const double q = fmin(fmax(x / pl.formant_shift, 0.0), nyq);
-                    oth[b] = gf_grid_interp(cur, q, step, nyq);
-                }
-            }
-            __syncwarp();
-            float *sw = cur; cur = oth; oth = sw;
-        }
         for (int e = 0; e < GF_EPL; ++e) {
-            const int b = lane + 32 * e;
-            if (b < GF_NBINS) sm.tileF[b][warp] = cur[b];
+            if (e < nown) {
+                const int b = b0 + e;
+                const double x = (b == 512) ? nyq : (double)b * step;
+                // np.interp(x, xd, xs) -- x is always inside [xd[0], xd[-1]] = [0, nyq]
+                double wf;
+                if (x > xd[nk - 1]) wf = xs[nk - 1];
+                else if (x < xd[0]) wf = xs[0];
+                else {
+                    int i = 0;
+                    while (i < nk && x >= xd[i]) ++i;
+                    const int j = i - 1;
+                    if (j >= nk - 1) wf = xs[nk - 1];
+                    else if (xd[j] == x) wf = xs[j];
+                    else wf = sl[j] * (x - xd[j]) + xs[j];
+                }
+                oth[b] = gf_grid_interp(cur, wf, step, inv_step, nyq);
+            }
         }
-    } else {
+        __syncwarp();
+        float *sw = cur; cur = oth; oth = sw;
+    }
+    // ---- g: shift all formants (GOOFER.py:618-627) ----
+    if (pl.formant_shift != 1.0) {
+        const double inv_r = 1.0 / pl.formant_shift;
+#pragma unroll
         for (int e = 0; e < GF_EPL; ++e) {
-            const int b = lane + 32 * e;
-            if (b < GF_NBINS) { sm.tileF[b][warp] = 0.0f; sm.tileN[b][warp] = 0.0f; }
+            if (e < nown) {
+                const int b = b0 + e;
+                const double x = (b == 512) ? nyq : (double)b * step;
+                const double q = fmin(fmax(x * inv_r, 0.0), nyq);
+                oth[b] = gf_grid_interp(cur, q, step, inv_step, nyq);
+            }
         }
+        __syncwarp();
+        float *sw = cur; cur = oth; oth = sw;
     }
-    __syncthreads();
-    const size_t base = (size_t)wk.y * (GF_NBINS * GF_FT);
-    const float *tf = &sm.tileF[0][0], *tn = &sm.tileN[0][0];
-    for (int i = threadIdx.x; i < GF_NBINS * GF_FT; i += blockDim.x) {
-        nd.envF[base + i] = tf[i];
-        nd.envN[base + i] = tn[i];
-    }
+    float *dstF = nd.envF + (size_t)t * GF_ENVS_LD;
+    for (int b = lane; b < GF_NBINS; b += 32) dstF[b] = cur[b];
 }
 
 void gf_launch_env(const int2 *work, int n_work, const GfNotePlan *plans, const GfNoteDev *notes, const GfSourceDev *srcs,
