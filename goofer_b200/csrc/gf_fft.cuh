@@ -16,7 +16,8 @@
 // padded index for the 512-float2 exchange buffer: keeps the stride-8 / stride-64 scatter of the
 // Stockham passes off a single bank pair
 GF_HD int gf_fpad(int i) { return i + (i >> 5); }
-#define GF_FFT_BUF (512 + 16)   // float2 elements per padded transform buffer
+#define GF_FFT_BUF (512 + 20)   // float2 elements per padded transform buffer; 532 mod 16 == 4 puts consecutive
+                                // transforms 8 banks apart, so (bin, frame)-interleaved accesses do not collide
 
 GF_HD float2 gf_cmul(float2 a, float2 b) { return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
 GF_HD float2 gf_cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }

@@ -53,8 +53,9 @@ __device__ __forceinline__ void gf_load_frames(float2 *bufs, int t0, int nf, int
     for (int idx = threadIdx.x; idx < nf * 512; idx += blockDim.x) {
         const int f = idx >> 9, m = idx & 511;
         const int p = GF_HOP * (t0 + f) + 2 * m - GF_NFFT / 2;
-        const float x0 = load(gf_reflect(p, n)) * win[2 * m];
-        const float x1 = load(gf_reflect(p + 1, n)) * win[2 * m + 1];
+        const bool inside = (p >= 0) && (p + 1 < n);         // reflect only near the two ends
+        const float x0 = load(inside ? p : gf_reflect(p, n)) * win[2 * m];
+        const float x1 = load(inside ? p + 1 : gf_reflect(p + 1, n)) * win[2 * m + 1];
         bufs[(size_t)f * GF_FFT_BUF + gf_fpad(m)] = make_float2(x0, x1);
     }
 }

@@ -16,7 +16,8 @@
 #define GF_STAG_LD 516
 
 struct GfFrameSmem {
-    GfFrameTables tab;
+    float2 tw512[512];                        // the FFT passes hit these every butterfly; window and split twiddles
+                                              // come from d_tab through L1 (keeps the CTA at <= 113 KB: two per SM)
     float2 z[3][GF_RND][GF_FFT_BUF];          // [0] harmonic, [1] breath, [2] unvoiced (also the forward buffer)
     float2 stag[2][GF_RND][GF_STAG_LD];       // pre-blur harmonic / breath spectra of voiced frames
     float ring[3][GF_RING];
@@ -33,7 +34,7 @@ __device__ __forceinline__ float gf_hp_sigmoid(float f, float f0)
     // GOOFER.py:1111  1 / (1 + exp(-clip((f - f0) / 5, -60, 60)))  (all f32)
     float a = (f - f0) / 5.0f;
     a = fminf(fmaxf(a, -60.0f), 60.0f);
-    return 1.0f / (1.0f + expf(-a));
+    return __fdividef(1.0f, 1.0f + __expf(-a));
 }
 
 __device__ __forceinline__ float2 gf_gauss5(const float2 *row, int k, const float *g)
@@ -52,7 +53,7 @@ __device__ __forceinline__ float2 gf_gauss5(const float2 *row, int k, const floa
 }
 
 // work item: x = pass index (into the wave's pass arrays), y = first owned block, z = block count
-__global__ void __launch_bounds__(GF_FRAME_THREADS)
+__global__ void __launch_bounds__(GF_FRAME_THREADS, 2)
 gf_frame_kernel(const int4 *__restrict__ work, const GfPassDev *__restrict__ passes, GfPassScal *scal,
                 const GfNoteDev *__restrict__ notes, const GfNotePlan *__restrict__ plans)
 {
@@ -66,7 +67,9 @@ gf_frame_kernel(const int4 *__restrict__ work, const GfPassDev *__restrict__ pas
     const int b0 = wk.y, nb = wk.z;
     const int tid = threadIdx.x;
 
-    gf_stage_tables(&sm.tab);
+    for (int i = tid; i < 512; i += blockDim.x) sm.tw512[i] = d_tab.tw512[i];
+    const float *__restrict__ win = d_tab.win;
+    const float2 *__restrict__ tw1024 = d_tab.tw1024;
     for (int i = tid; i < 3 * GF_RING; i += blockDim.x) (&sm.ring[0][0])[i] = 0.0f;
     float g5[5];
 #pragma unroll
@@ -89,12 +92,12 @@ gf_frame_kernel(const int4 *__restrict__ work, const GfPassDev *__restrict__ pas
         const int nf = min(GF_RND, t_end - t0 + 1);
         // ---- 1. frame the excitation (pulse + growl layer) ----
         if (sub) {
-            gf_load_frames(&sm.z[2][0][0], t0, nf, n, sm.tab.win, [&](int i) {
+            gf_load_frames(&sm.z[2][0][0], t0, nf, n, win, [&](int i) {
                 // GOOFER.py:724-736: sub *= mask; sub /= max; sub *= weight; pulse (f32) += sub (f64)
                 return (float)((double)pulse[i] + ((double)sub[i] * (double)vm[i]) * sub_scale);
             });
         } else {
-            gf_load_frames(&sm.z[2][0][0], t0, nf, n, sm.tab.win, [&](int i) { return pulse[i]; });
+            gf_load_frames(&sm.z[2][0][0], t0, nf, n, win, [&](int i) { return pulse[i]; });
         }
         if (tid < nf) {
             const int fi = min(t0 + tid, n_f0 - 1) * GF_HOP;      // f0[::hop] edge-padded   GOOFER.py:1104-1106
@@ -103,10 +106,11 @@ gf_frame_kernel(const int4 *__restrict__ work, const GfPassDev *__restrict__ pas
         }
         __syncthreads();
         // ---- 2. forward FFT ----
-        gf_cta_fft512<false>(&sm.z[2][0][0], nf, sm.tab.tw512);
+        gf_cta_fft512<false>(&sm.z[2][0][0], nf, sm.tw512);
         // ---- 3. shaping, per bin pair (k, 512 - k) ----
         for (int idx = tid; idx < nf * 256; idx += blockDim.x) {
-            const int k = idx / nf, f = idx - k * nf;
+            int k, f;
+            if (nf == GF_RND) { k = idx >> 2; f = idx & 3; } else { k = idx / nf; f = idx - k * nf; }
             const int t = t0 + f;
             const int km = 512 - k;
             const float f0f = sm.f0fr[f];
@@ -120,11 +124,11 @@ gf_frame_kernel(const int4 *__restrict__ work, const GfPassDev *__restrict__ pas
             float2 S[3];
             {
                 const float2 Zk = zf[gf_fpad(k)], Zm = zf[gf_fpad(km & 511)];
-                gf_rfft_split(Zk, Zm, sm.tab.tw1024[k], S[0], S[1]);
+                gf_rfft_split(Zk, Zm, tw1024[k], S[0], S[1]);
                 if (k == 0) {
                     const float2 Zq = zf[gf_fpad(256)];
                     float2 dummy;
-                    gf_rfft_split(Zq, Zq, sm.tab.tw1024[256], S[2], dummy);
+                    gf_rfft_split(Zq, Zq, tw1024[256], S[2], dummy);
                 }
             }
 #pragma unroll
@@ -133,13 +137,14 @@ gf_frame_kernel(const int4 *__restrict__ work, const GfPassDev *__restrict__ pas
                     const int bq = bins[q];
                     const float hp = gf_hp_sigmoid(d_tab.freq32[bq], f0f);
                     float2 s = make_float2(S[q].x * hp, S[q].y * hp);
-                    local_max = fmaxf(local_max, hypotf(s.x, s.y) + 1e-8f);
+                    local_max = fmaxf(local_max, fmaf(s.x, s.x, s.y * s.y));      // max |S|^2: sqrt taken once at the end
                     const float ef = eF[bq], en = eN[bq];
                     const float bo = d_tab.boost[bq];
                     float2 h = make_float2(s.x * ef * bo, s.y * ef * bo);
+                    // U = cos(phi) + i sin(phi), phi in [0, 2 pi): evaluated at phi - pi where the fast path is accurate
                     float sn, cs;
-                    sincosf(ph[(size_t)bq * T], &sn, &cs);
-                    float2 v = make_float2(cs * en, sn * en);
+                    __sincosf(ph[(size_t)bq * T] - 3.14159274f, &sn, &cs);
+                    float2 v = make_float2(-cs * en, -sn * en);
                     float2 b = make_float2(v.x * hp, v.y * hp);
                     if (vo) {
                         const float bh = d_tab.bright_h[bq], bb = d_tab.bright_b[bq];
@@ -153,24 +158,24 @@ gf_frame_kernel(const int4 *__restrict__ work, const GfPassDev *__restrict__ pas
             // pocketfft c2r ignores the imaginary parts of DC and Nyquist
             if (k == 0) { V[0].y = 0.f; V[1].y = 0.f; H[0].y = 0.f; H[1].y = 0.f; B[0].y = 0.f; B[1].y = 0.f; }
             float2 Zk, Zm;
-            gf_irfft_merge(V[0], V[1], sm.tab.tw1024[k], Zk, Zm);
+            gf_irfft_merge(V[0], V[1], tw1024[k], Zk, Zm);
             zf[gf_fpad(k)] = Zk;
             if (k != 0) zf[gf_fpad(km)] = Zm;
             if (k == 0) {
-                gf_irfft_merge(V[2], V[2], sm.tab.tw1024[256], Zk, Zm);
+                gf_irfft_merge(V[2], V[2], tw1024[256], Zk, Zm);
                 zf[gf_fpad(256)] = Zk;
             }
             if (!vo) {
-                gf_irfft_merge(H[0], H[1], sm.tab.tw1024[k], Zk, Zm);
+                gf_irfft_merge(H[0], H[1], tw1024[k], Zk, Zm);
                 sm.z[0][f][gf_fpad(k)] = Zk;
                 if (k != 0) sm.z[0][f][gf_fpad(km)] = Zm;
-                gf_irfft_merge(B[0], B[1], sm.tab.tw1024[k], Zk, Zm);
+                gf_irfft_merge(B[0], B[1], tw1024[k], Zk, Zm);
                 sm.z[1][f][gf_fpad(k)] = Zk;
                 if (k != 0) sm.z[1][f][gf_fpad(km)] = Zm;
                 if (k == 0) {
-                    gf_irfft_merge(H[2], H[2], sm.tab.tw1024[256], Zk, Zm);
+                    gf_irfft_merge(H[2], H[2], tw1024[256], Zk, Zm);
                     sm.z[0][f][gf_fpad(256)] = Zk;
-                    gf_irfft_merge(B[2], B[2], sm.tab.tw1024[256], Zk, Zm);
+                    gf_irfft_merge(B[2], B[2], tw1024[256], Zk, Zm);
                     sm.z[1][f][gf_fpad(256)] = Zk;
                 }
             }
@@ -178,7 +183,8 @@ gf_frame_kernel(const int4 *__restrict__ work, const GfPassDev *__restrict__ pas
         __syncthreads();
         // ---- 4. voiced frames: 5-tap Gaussian along frequency, then merge ----
         for (int idx = tid; idx < nf * 256; idx += blockDim.x) {
-            const int k = idx / nf, f = idx - k * nf;
+            int k, f;
+            if (nf == GF_RND) { k = idx >> 2; f = idx & 3; } else { k = idx / nf; f = idx - k * nf; }
             if (!sm.voiced[f]) continue;
             const int km = 512 - k;
 #pragma unroll
@@ -187,12 +193,12 @@ gf_frame_kernel(const int4 *__restrict__ work, const GfPassDev *__restrict__ pas
                 float2 Xk = gf_gauss5(row, k, g5), Xm = gf_gauss5(row, km, g5);
                 if (k == 0) { Xk.y = 0.f; Xm.y = 0.f; }
                 float2 Zk, Zm;
-                gf_irfft_merge(Xk, Xm, sm.tab.tw1024[k], Zk, Zm);
+                gf_irfft_merge(Xk, Xm, tw1024[k], Zk, Zm);
                 sm.z[s][f][gf_fpad(k)] = Zk;
                 if (k != 0) sm.z[s][f][gf_fpad(km)] = Zm;
                 if (k == 0) {
                     const float2 Xq = gf_gauss5(row, 256, g5);
-                    gf_irfft_merge(Xq, Xq, sm.tab.tw1024[256], Zk, Zm);
+                    gf_irfft_merge(Xq, Xq, tw1024[256], Zk, Zm);
                     sm.z[s][f][gf_fpad(256)] = Zk;
                 }
             }
@@ -200,12 +206,12 @@ gf_frame_kernel(const int4 *__restrict__ work, const GfPassDev *__restrict__ pas
         __syncthreads();
         // ---- 5. inverse FFTs (stream-major: transform q = s * GF_RND + f) ----
         if (nf == GF_RND) {
-            gf_cta_fft512<true>(&sm.z[0][0][0], 3 * GF_RND, sm.tab.tw512);
+            gf_cta_fft512<true>(&sm.z[0][0][0], 3 * GF_RND, sm.tw512);
         } else {
-            for (int s = 0; s < 3; ++s) gf_cta_fft512<true>(&sm.z[s][0][0], nf, sm.tab.tw512);
+            for (int s = 0; s < 3; ++s) gf_cta_fft512<true>(&sm.z[s][0][0], nf, sm.tw512);
         }
         // ---- 6. overlap-add ----
-        for (int s = 0; s < 3; ++s) gf_ola_add(sm.ring[s], &sm.z[s][0][0], t0, nf, sm.tab.win);
+        for (int s = 0; s < 3; ++s) gf_ola_add(sm.ring[s], &sm.z[s][0][0], t0, nf, win);
         __syncthreads();
         // ---- 7. emit finished blocks ----
         const int last_blk = (t0 + nf - 1 == T - 1) ? T : (t0 + nf - 1);
@@ -228,7 +234,7 @@ gf_frame_kernel(const int4 *__restrict__ work, const GfPassDev *__restrict__ pas
     if (tid == 0) {
         float m = 0.f;
         for (int w = 0; w < GF_FRAME_THREADS / 32; ++w) m = fmaxf(m, sm.red[w]);
-        gf_atomic_max_pos(&scal[wk.x].mag_bits, m);
+        gf_atomic_max_pos(&scal[wk.x].mag_bits, sqrtf(m) + 1e-8f);
     }
 }
 
