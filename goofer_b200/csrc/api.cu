@@ -230,6 +230,7 @@ static void gf_carve_note(const GfNotePlan &p, Bump &bp, GfNoteDev *nd, GfPassDe
     d.envN = bp.arr<float>((size_t)p.T_out * GF_ENVS_LD);
     d.vm = bp.arr<float>(n);
     d.ms_short = bp.arr<float>((n + 3) / 4);
+    d.ms = bp.arr<float>(n);
     if (p.f0_jitter) d.z_sh = bp.arr<double>(n);
     if (p.vol_jitter) { d.z_srh = bp.arr<double>(n); d.z_srb = bp.arr<double>(n); d.vjm = bp.arr<float>(n); }
     if (p.sd > 0) d.sdm = bp.arr<float>(n);

@@ -69,6 +69,7 @@ struct GfNoteDev {
     float *vm;              // (n_total,) f32(mask_new)
     float *f0n;             // (n_total,) f32(f0_new): cutoff driver of the post-FX filters, or NULL
     float *ms_short;        // (ceil(n/4),) f32: gaussian-smoothed decimated mask   GOOFER.py:556-563
+    float *ms;              // (n_total,) f32: smooth_mask_ds result (lerp of ms_short)  GOOFER.py:564-569
     double *z_sh;           // (n_total,) smoothed sh noise (f0 jitter) or NULL
     double *z_srh, *z_srb;  // smoothed sr noise
     float *vjm;             // gauss(vm, 20) (sr)
@@ -156,6 +157,25 @@ __device__ __forceinline__ float gf_fry_at(const GfNotePlan &pl, int c)
         if (c >= b0) mf = (float)((double)mf * gf_dlin10(c - b0, pl.fry_b - b0));
     }
     return mf;
+}
+
+// smooth_mask_ds (GOOFER.py:556-569): lerp of the smoothed decimated mask back to sample rate on float32
+// linspace abscissae (their f32 rounding moves the lerp weight by up to 7e-4, so it is reproduced), result f32
+__device__ __forceinline__ float gf_ms_at(const float *__restrict__ s, int M, int i, int N)
+{
+    if (M == 1) return s[0];
+    const float x = (float)gf_dlin01(i, N);
+    if (x >= 1.0f) return s[M - 1];
+    int j = (int)(x * (float)(M - 1));
+    if (j > M - 2) j = M - 2;
+    float x0 = (float)gf_dlin01(j, M);
+    while (j > 0 && x0 > x) { --j; x0 = (float)gf_dlin01(j, M); }
+    float x1 = (float)gf_dlin01(j + 1, M);
+    while (j < M - 2 && x1 <= x) { ++j; x0 = x1; x1 = (float)gf_dlin01(j + 1, M); }
+    if (x0 == x) return s[j];
+    // np.interp: slope * (x - x0) + y0 in fp64; the two differences are exact, one f32 division suffices
+    const float t = (x - x0) / (x1 - x0);
+    return (float)fma((double)s[j + 1] - (double)s[j], (double)t, (double)s[j]);
 }
 
 __device__ __forceinline__ void gf_atomic_max_pos(unsigned int *addr, float v)

@@ -54,10 +54,17 @@ gf_f0_kernel(const GfNotePlan *__restrict__ plans, const GfNoteDev *__restrict__
     const int n = pl.n_total;
     double sh_scale = 0.0;
     if (pl.f0_jitter) sh_scale = nd.noteScal[GF_NS_SHMAX];
+    // 440 * 2 ** ((midi - 69) / 12): exp2 instead of pow (exact for the integer exponents of the A notes, where
+    // the pulse onsets sit on rounding ties; elsewhere the two differ by at most an ulp of the fp64 value)
+    const bool flat = pl.bend_len == 1;
+    const double midi_flat = flat ? gf_midi_at(pl, bend, 0) : 0.0;
+    const double hz_flat = flat ? 440.0 * exp2((midi_flat - 69.0) / 12.0) : 0.0;
+    const int M = (n + 3) / 4;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         const double m = gf_mask_new(pl, mask_src, i);
-        const double midi = gf_midi_at(pl, bend, i);
-        const double hz = 440.0 * pow(2.0, (midi - 69.0) / 12.0);
+        const double midi = flat ? midi_flat : gf_midi_at(pl, bend, i);
+        const double hz = flat ? hz_flat : 440.0 * exp2((midi - 69.0) / 12.0);
+        nd.ms[i] = gf_ms_at(nd.ms_short, M, i, n);
         double f0 = m * hz;
         // ---- vocal fry f0 override (SillySampler.py:890-934) ----
         if (pl.fry_L > 0) {
@@ -244,7 +251,9 @@ gf_walk_kernel(const GfPassDev *__restrict__ passes, GfPassScal *scal, int n_pas
 }
 
 // per onset: period length T0 = round(sr / last_valid_f0) clipped to [3, 8192] (GOOFER.py:495-499, Python
-// round = half to even) and the peak of its LF table (GOOFER.py:524-528); thread per onset
+// round = half to even), the peak of its LF table (GOOFER.py:524-528) and the two branch points of the table
+// (first j with ti >= Tp, first j with ti >= Tc -- decided with the reference's own fp64 expressions, because
+// 0.02 * T0 is an integer for T0 = 50 k and the comparison then sits on a rounding tie); thread per onset
 __global__ void __launch_bounds__(128)
 gf_onset_kernel(const GfPassDev *__restrict__ passes, GfPassScal *scal, int sr_i)
 {
@@ -259,8 +268,17 @@ gf_onset_kernel(const GfPassDev *__restrict__ passes, GfPassScal *scal, int sr_i
         const double T = __ddiv_rn(1.0, lv);
         int T0 = (int)rint(__dmul_rn(sr, T));
         T0 = T0 < 3 ? 3 : (T0 > 8192 ? 8192 : T0);
+        const double Tp = 0.02 * T;
+        const double Tc = __dadd_rn(Tp, __dmul_rn(0.8, T - Tp));
+        auto ti = [&](int j) { return __ddiv_rn(__dmul_rn((double)j, T), (double)T0); };
+        int jp = max(0, (int)(0.02 * (double)T0) - 1);
+        while (jp < T0 && ti(jp) < Tp) ++jp;
+        while (jp > 0 && !(ti(jp - 1) < Tp)) --jp;
+        int jc = max(jp, (int)(0.804 * (double)T0) - 1);
+        while (jc < T0 && ti(jc) < Tc) ++jc;
+        while (jc > jp && !(ti(jc - 1) < Tc)) --jc;
         o.y = T0;
-        o.z = __float_as_int((float)lv);
+        o.z = jp | (jc << 16);
         o.w = __float_as_int(gf_lf_table_max(T, T0));
         ps.onsets[e] = o;
         mx = max(mx, T0);
@@ -278,42 +296,85 @@ void gf_launch_walk(const GfPassDev *passes, GfPassScal *scal, int n_pass, int s
 
 // ------------------------------------------------------------------------------------------------
 // pulse[i] = sum over the onsets whose table covers i, in onset order (f32 adds)  GOOFER.py:542-552
+// One CTA per 256-sample tile: two binary searches find the onsets that can reach the tile, their records are
+// staged in shared memory, every thread sums the tables covering its sample.  The LF table value is
+// evaluated in f32 from (j, T0) alone: T cancels in ti / Tp and (ti - Tp) / (Tc - Tp) up to the 1e-12
+// guards (< 1e-8 relative, like the reference's own 5-slot table cache, which reuses one T per T0).
 // ------------------------------------------------------------------------------------------------
+#define GF_PULSE_CAP 128
+__device__ __forceinline__ float gf_lf_value_f32(int d, int jp, int jc, float r_rise, float r_fall, float inv_max)
+{
+    float v = 0.0f;
+    if (d < jp) { const float s = sinf((float)d * r_rise); v = s * s; }
+    else if (d < jc) {
+        const float tau = fmaf((float)d, r_fall, -(0.02f / 0.784f));
+        v = expf(-1.7f * tau) * cosf(1.57079637f * tau);
+    }
+    return v * inv_max;
+}
+
 __global__ void __launch_bounds__(256)
 gf_pulse_kernel(const GfPassDev *__restrict__ passes, const GfPassScal *__restrict__ scal)
 {
+    __shared__ int s_x[GF_PULSE_CAP], s_T0[GF_PULSE_CAP], s_j[GF_PULSE_CAP];
+    __shared__ float s_r1[GF_PULSE_CAP], s_r2[GF_PULSE_CAP], s_im[GF_PULSE_CAP];
+    __shared__ int s_rng[2];
     const GfPassDev ps = passes[blockIdx.y];
     const int n = ps.n_total;
     const int count = scal[blockIdx.y].n_onsets;
     const int max_T0 = scal[blockIdx.y].max_T0;
     const int4 *__restrict__ on = ps.onsets;
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        int lo = 0, hi = count;                 // number of onsets with index <= i
-        while (lo < hi) { const int mid = (lo + hi) >> 1; if (on[mid].x <= i) lo = mid + 1; else hi = mid; }
-        const int last = lo - 1;
-        float acc = 0.0f;
-        if (last >= 0) {
-            int e0 = last;
-            while (e0 > 0 && i - on[e0 - 1].x < max_T0) --e0;
-            for (int e = e0; e <= last; ++e) {
-                const int4 o = on[e];
-                const int d = i - o.x;
-                if (d < o.y) {
-                    const double T = __ddiv_rn(1.0, (double)__int_as_float(o.z));
-                    const float raw = gf_lf_value(d, T, o.y);
-                    const float mx = __int_as_float(o.w);
-                    const float val = (mx > 0.0f) ? (float)((double)raw / (double)mx) : raw;
-                    acc += val;
-                }
+    for (int s0 = blockIdx.x * 256; s0 < n; s0 += gridDim.x * 256) {
+        if (threadIdx.x < 2) {
+            // [0]: onsets with x <= s0 - max_T0 can no longer reach the tile; [1]: onsets with x <= s0 + 255
+            const int key = threadIdx.x == 0 ? s0 - max_T0 : s0 + 255;
+            int lo = 0, hi = count;
+            while (lo < hi) { const int mid = (lo + hi) >> 1; if (on[mid].x <= key) lo = mid + 1; else hi = mid; }
+            s_rng[threadIdx.x] = lo;
+        }
+        __syncthreads();
+        const int e0 = s_rng[0], e1 = s_rng[1];
+        const int ne = e1 - e0;
+        const bool staged = ne <= GF_PULSE_CAP;
+        if (staged) {
+            for (int q = threadIdx.x; q < ne; q += blockDim.x) {
+                const int4 o = on[e0 + q];
+                s_x[q] = o.x; s_T0[q] = o.y; s_j[q] = o.z;
+                s_r1[q] = 1.57079637f / (0.02f * (float)o.y);
+                s_r2[q] = 1.0f / (0.784f * (float)o.y);
+                const float mxv = __int_as_float(o.w);
+                s_im[q] = mxv > 0.0f ? 1.0f / mxv : 1.0f;
             }
         }
-        ps.pulse[i] = acc;
+        __syncthreads();
+        const int i = s0 + threadIdx.x;
+        if (i < n) {
+            float acc = 0.0f;
+            if (staged) {
+                for (int q = 0; q < ne; ++q) {
+                    const int d = i - s_x[q];
+                    if (d >= 0 && d < s_T0[q]) acc += gf_lf_value_f32(d, s_j[q] & 0xffff, s_j[q] >> 16, s_r1[q], s_r2[q], s_im[q]);
+                }
+            } else {
+                for (int e = e0; e < e1; ++e) {
+                    const int4 o = on[e];
+                    const int d = i - o.x;
+                    if (d >= 0 && d < o.y) {
+                        const float mxv = __int_as_float(o.w);
+                        acc += gf_lf_value_f32(d, o.z & 0xffff, o.z >> 16, 1.57079637f / (0.02f * (float)o.y),
+                                               1.0f / (0.784f * (float)o.y), mxv > 0.0f ? 1.0f / mxv : 1.0f);
+                    }
+                }
+            }
+            ps.pulse[i] = acc;
+        }
+        __syncthreads();
     }
 }
 
 void gf_launch_pulse(const GfPassDev *passes, const GfPassScal *scal, int n_pass, int max_n, cudaStream_t st)
 {
     if (n_pass <= 0) return;
-    dim3 grid(min(64, (max_n + 255) / 256), n_pass);
+    dim3 grid(min(256, (max_n + 255) / 256), n_pass);
     gf_pulse_kernel<<<grid, 256, 0, st>>>(passes, scal);
 }

@@ -518,10 +518,65 @@ void gf_launch_mask(const GfNotePlan *plans, const GfNoteDev *notes, const GfSou
 // ------------------------------------------------------------------------------------------------
 
 #define GF_FIR_TILE 1024
+
+__device__ __forceinline__ bool gf_fir_is_f32(const GfFirJob &jb)
+{
+    return !jb.in_f64 && !jb.out_f64 && !jb.maxabs && !jb.in_cast_f32;
+}
+
+// f32 -> f32 jobs (voicing-mask smoothing: sigma 25 on the decimated mask, sigma 20, sigma 441): the same
+// register-tiled sliding window as the envelope kernel, 17 outputs per thread, f32 taps and accumulation
+#define GF_F32_THREADS 128
+#define GF_F32_TILE (GF_EPL * GF_F32_THREADS)
+__global__ void __launch_bounds__(GF_F32_THREADS) gf_fir32_kernel(const GfFirJob *__restrict__ jobs)
+{
+    extern __shared__ __align__(16) float f32sm[];
+    __shared__ double red[GF_F32_THREADS / 32];
+    const GfFirJob jb = jobs[blockIdx.y];
+    if (!gf_fir_is_f32(jb)) return;
+    const int n = jb.n;
+    const int start = blockIdx.x * GF_F32_TILE;
+    if (start >= n) return;
+    const int radius = (int)(4.0 * jb.sigma + 0.5);
+    const int ntap8 = ((2 * radius + 1 + 7) & ~7) + 8;
+    float *taps = f32sm;                                  // ntap8
+    float *row = taps + ntap8;                            // radius + GF_F32_TILE + radius + 16
+    float *outb = row + (2 * radius + GF_F32_TILE + 16);  // GF_F32_TILE
+    double part = 0.0;
+    for (int j = threadIdx.x; j <= 2 * radius; j += blockDim.x) { const double t = (double)(j - radius) / jb.sigma; part += exp(-0.5 * t * t); }
+    part = gf_warp_sum(part);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = part;
+    __syncthreads();
+    double norm = 0.0;
+    for (int w = 0; w < GF_F32_THREADS / 32; ++w) norm += red[w];
+    for (int j = threadIdx.x; j < ntap8; j += blockDim.x) taps[j] = (j <= 2 * radius) ? (float)gf_gauss_tap(j, radius, jb.sigma, norm) : 0.0f;
+    const float *in = (const float *)jb.in;
+    const int span = 2 * radius + GF_F32_TILE + 16;
+    for (int i = threadIdx.x; i < span; i += blockDim.x) {
+        const int p = start + i - radius;
+        float v = 0.0f;
+        if (p < n + radius) {
+            const int q = (p >= 0 && p < n) ? p : gf_reflect(p, n);
+            v = in[(size_t)q * jb.in_stride];
+        }
+        row[i] = v;
+    }
+    __syncthreads();
+    float out[GF_EPL];
+    gf_fir_rt(row + radius, GF_EPL * threadIdx.x, taps, radius, out);
+#pragma unroll
+    for (int e = 0; e < GF_EPL; ++e) outb[GF_EPL * threadIdx.x + e] = out[e];
+    __syncthreads();
+    float *dst = (float *)jb.out;
+    const int cnt = min(GF_F32_TILE, n - start);
+    for (int i = threadIdx.x; i < cnt; i += blockDim.x) dst[start + i] = outb[i];
+}
+
 __global__ void __launch_bounds__(256) gf_fir_kernel(const GfFirJob *__restrict__ jobs)
 {
     extern __shared__ double fsm[];
     const GfFirJob jb = jobs[blockIdx.y];
+    if (gf_fir_is_f32(jb)) return;                // handled by gf_fir32_kernel
     const int n = jb.n;
     const int start = blockIdx.x * GF_FIR_TILE;
     if (start >= n) return;
@@ -570,4 +625,13 @@ void gf_launch_fir(const GfFirJob *jobs, int n_jobs, int max_n, double max_sigma
     }
     dim3 grid((max_n + GF_FIR_TILE - 1) / GF_FIR_TILE, n_jobs);
     gf_fir_kernel<<<grid, 256, smem, st>>>(jobs);
+    // f32 jobs
+    const size_t smem32 = sizeof(float) * (size_t)((((2 * radius + 1 + 7) & ~7) + 8) + (2 * radius + GF_F32_TILE + 16) + GF_F32_TILE);
+    static size_t attr32 = 0;
+    if (smem32 > attr32) {
+        cudaFuncSetAttribute(gf_fir32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem32);
+        attr32 = smem32;
+    }
+    dim3 grid32((max_n + GF_F32_TILE - 1) / GF_F32_TILE, n_jobs);
+    gf_fir32_kernel<<<grid32, GF_F32_THREADS, smem32, st>>>(jobs);
 }

@@ -6,24 +6,6 @@
 #include "gf_device.cuh"
 #include "gf_maps.cuh"
 
-// smooth_mask_ds (GOOFER.py:556-569): lerp of the smoothed decimated mask back to sample rate on
-// float32 linspace abscissae, evaluated in fp64 like np.interp, result f32
-__device__ __forceinline__ float gf_ms_at(const float *__restrict__ s, int M, int i, int N)
-{
-    if (M == 1) return s[0];
-    const double x = (double)(float)gf_lin01(i, N);
-    auto xo = [&](int j) { return (double)(float)gf_lin01(j, M); };
-    if (x >= 1.0) return s[M - 1];
-    int j = (int)(x * (double)(M - 1));
-    if (j > M - 2) j = M - 2;
-    while (j > 0 && xo(j) > x) --j;
-    while (j < M - 2 && xo(j + 1) <= x) ++j;
-    const double x0 = xo(j);
-    if (x0 == x) return s[j];
-    const double slope = ((double)s[j + 1] - (double)s[j]) / (xo(j + 1) - x0);
-    return (float)(slope * (x - x0) + (double)s[j]);
-}
-
 struct GfStreams { float h, b, u; };
 
 // the three streams of one synthesize pass before the peak normalisation
@@ -37,8 +19,7 @@ __device__ __forceinline__ GfStreams gf_pass_streams(const GfNotePlan &pl, const
         r.b = ps.bre[i];
         r.u = 0.0f * ps.uv[i];
     } else {
-        const int N = pl.n_total, M = (N + 3) / 4;
-        const float ms = gf_ms_at(nd.ms_short, M, i, N);
+        const float ms = nd.ms[i];                            // smooth_mask_ds, expanded once by gf_f0_kernel
         r.b = ps.bre[i] * ms * 0.1f;
         r.u = ps.uv[i] * (1.0f - ms) * 0.75f;
     }
