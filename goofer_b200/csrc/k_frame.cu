@@ -20,7 +20,7 @@ struct GfFrameSmem {
                                               // come from d_tab through L1 (keeps the CTA at <= 113 KB: two per SM)
     float2 z[3][GF_RND][GF_FFT_BUF];          // [0] harmonic, [1] breath, [2] unvoiced (also the forward buffer)
     float2 stag[2][GF_RND][GF_STAG_LD];       // pre-blur harmonic / breath spectra of voiced frames
-    float ring[3][GF_RING];
+    float carry[3][3][GF_HOP];                // per stream: the three hop blocks still waiting for later frames
     float f0fr[GF_RND];
     int voiced[GF_RND];
     float red[GF_FRAME_THREADS / 32];
@@ -52,6 +52,54 @@ __device__ __forceinline__ float2 gf_gauss5(const float2 *row, int k, const floa
     return acc;
 }
 
+// One round of the windowed overlap-add for one stream (GOOFER.py:372-390, 402-411).  Frames t0 .. t0+NF-1 sit
+// in `bufs` as unnormalised inverse-FFT output (scale 1/512).  Thread `tid` owns sample column tid of every hop
+// block: it adds the NF x 4 windowed contributions in ascending frame order (like _overlap_add), divides the
+// finished blocks by their win^2 sum, writes them, and carries the three unfinished blocks to the next round.
+template <int NF>
+__device__ __forceinline__ void gf_ola_round(float (*carry)[GF_HOP], const float2 *bufs, const float *__restrict__ win,
+                                             int t0, int T, int n_out, float *__restrict__ out, int b0, int nb, bool last)
+{
+    const int r = threadIdx.x;
+    float acc[NF + 3];
+#pragma unroll
+    for (int m = 0; m < 3; ++m) acc[m] = carry[m][r];
+#pragma unroll
+    for (int m = 3; m < NF + 3; ++m) acc[m] = 0.0f;
+    float w[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) w[q] = win[GF_HOP * q + r];
+#pragma unroll
+    for (int f = 0; f < NF; ++f) {
+        const float *zf = reinterpret_cast<const float *>(bufs + (size_t)f * GF_FFT_BUF);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int j = GF_HOP * q + r;
+            const float v = zf[2 * gf_fpad(j >> 1) + (j & 1)] * (1.0f / 512.0f);
+            acc[f + q] = __fadd_rn(acc[f + q], __fmul_rn(v, w[q]));
+        }
+    }
+    const int n_emit = last ? NF + 1 : NF;                 // the final frame also finishes block T
+#pragma unroll
+    for (int m = 0; m < NF + 1; ++m) {
+        const int b = t0 + m;
+        if (m < n_emit && b >= b0 && b < b0 + nb && b >= 2) {
+            float ws = 0.0f;
+#pragma unroll
+            for (int q = 3; q >= 0; --q) {                 // frames b-3 .. b ascending
+                const int t = b - q;
+                if (t >= 0 && t < T) ws = __fadd_rn(ws, d_tab.win2[GF_HOP * q + r]);
+            }
+            float y = acc[m];
+            if ((double)ws > 1e-9) y = y / ws;
+            const int i = GF_HOP * (b - 2) + r;
+            if (i < n_out) out[i] = y;
+        }
+    }
+#pragma unroll
+    for (int m = 0; m < 3; ++m) carry[m][r] = acc[NF + m];
+}
+
 // work item: x = pass index (into the wave's pass arrays), y = first owned block, z = block count
 __global__ void __launch_bounds__(GF_FRAME_THREADS, 2)
 gf_frame_kernel(const int4 *__restrict__ work, const GfPassDev *__restrict__ passes, GfPassScal *scal,
@@ -70,7 +118,7 @@ gf_frame_kernel(const int4 *__restrict__ work, const GfPassDev *__restrict__ pas
     for (int i = tid; i < 512; i += blockDim.x) sm.tw512[i] = d_tab.tw512[i];
     const float *__restrict__ win = d_tab.win;
     const float2 *__restrict__ tw1024 = d_tab.tw1024;
-    for (int i = tid; i < 3 * GF_RING; i += blockDim.x) (&sm.ring[0][0])[i] = 0.0f;
+    for (int i = tid; i < 9 * GF_HOP; i += blockDim.x) (&sm.carry[0][0][0])[i] = 0.0f;
     float g5[5];
 #pragma unroll
     for (int j = 0; j < 5; ++j) g5[j] = (float)d_tab.g05[j];
@@ -210,16 +258,23 @@ gf_frame_kernel(const int4 *__restrict__ work, const GfPassDev *__restrict__ pas
         } else {
             for (int s = 0; s < 3; ++s) gf_cta_fft512<true>(&sm.z[s][0][0], nf, sm.tw512);
         }
-        // ---- 6. overlap-add ----
-        for (int s = 0; s < 3; ++s) gf_ola_add(sm.ring[s], &sm.z[s][0][0], t0, nf, win);
-        __syncthreads();
-        // ---- 7. emit finished blocks ----
-        const int last_blk = (t0 + nf - 1 == T - 1) ? T : (t0 + nf - 1);
-        for (int b = t0; b <= last_blk; ++b) {
-            const bool own = (b >= b0 && b < b0 + nb && b >= 2);
-            gf_ola_emit(sm.ring[0], b, T, n, ps.harm, own);
-            gf_ola_emit(sm.ring[1], b, T, n, ps.bre, own);
-            gf_ola_emit(sm.ring[2], b, T, n, ps.uv, own);
+        // ---- 6. overlap-add + emit: thread `tid` owns column tid of every hop block ----
+        {
+            float *outs[3] = {ps.harm, ps.bre, ps.uv};
+            const bool last = (t0 + nf - 1 == T - 1);
+            if (nf == GF_RND) {
+#pragma unroll
+                for (int s = 0; s < 3; ++s) gf_ola_round<GF_RND>(sm.carry[s], &sm.z[s][0][0], win, t0, T, n, outs[s], b0, nb, last);
+            } else if (nf == 3) {
+#pragma unroll
+                for (int s = 0; s < 3; ++s) gf_ola_round<3>(sm.carry[s], &sm.z[s][0][0], win, t0, T, n, outs[s], b0, nb, last);
+            } else if (nf == 2) {
+#pragma unroll
+                for (int s = 0; s < 3; ++s) gf_ola_round<2>(sm.carry[s], &sm.z[s][0][0], win, t0, T, n, outs[s], b0, nb, last);
+            } else {
+#pragma unroll
+                for (int s = 0; s < 3; ++s) gf_ola_round<1>(sm.carry[s], &sm.z[s][0][0], win, t0, T, n, outs[s], b0, nb, last);
+            }
         }
         __syncthreads();
     }
