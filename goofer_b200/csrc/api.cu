@@ -226,6 +226,7 @@ static void gf_carve_note(const GfNotePlan &p, Bump &bp, GfNoteDev *nd, GfPassDe
     std::memset(&d, 0, sizeof(d));
     d.trk_canon = bp.arr<float>(4 * (size_t)p.T_env);
     d.trk_clean = p.any_fst ? bp.arr<float>(8 * (size_t)p.T_env) : nullptr;
+    d.env_aux = bp.arr<float>(1040 + 64);
     d.envF = bp.arr<float>((size_t)p.T_out * GF_ENVS_LD);
     d.envN = bp.arr<float>((size_t)p.T_out * GF_ENVS_LD);
     d.vm = bp.arr<float>(n);

@@ -65,6 +65,7 @@ struct GfPassScal {         // zeroed per wave, written by the device
 struct GfNoteDev {
     float *trk_canon;       // (4, T_env) f32
     float *trk_clean;       // (4, T_env) f32 (fst) or NULL
+    float *env_aux;         // per-note tables of the envelope kernel (br tilt, f32 bin frequencies, es taps)
     float *envF, *envN;     // (T_out, GF_ENVS_LD) f32 frame-major: shaped envelope / noise envelope on the STFT frame grid
     float *vm;              // (n_total,) f32(mask_new)
     float *f0n;             // (n_total,) f32(f0_new): cutoff driver of the post-FX filters, or NULL

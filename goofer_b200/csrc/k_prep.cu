@@ -69,6 +69,13 @@ void gf_launch_src_env(const GfSourceDev *srcs, int n_src, int max_T, cudaStream
     gf_src_env_kernel<<<grid, 256, 0, st>>>(srcs);
 }
 
+#define GF_MAX_ES_TAPS 64   // es radius <= 28 -> 57 taps, zero-padded to a multiple of 8
+// layout of GfNoteDev.env_aux (f32): per-note tables shared by all the envelope-kernel CTAs of the note
+#define GF_AUX_TILT 0
+#define GF_AUX_FREQ 520
+#define GF_AUX_TAPS 1040
+#define GF_AUX_LEN (1040 + GF_MAX_ES_TAPS)
+
 // ------------------------------------------------------------------------------------------------
 // formant tracks
 // ------------------------------------------------------------------------------------------------
@@ -91,6 +98,48 @@ gf_tracks_kernel(const GfNotePlan *__restrict__ plans, const GfNoteDev *__restri
         double norm = 0.0;
         for (int j = 0; j < 33; ++j) { const double t = (double)(j - 16) / 4.0; norm += exp(-0.5 * t * t); }
         taps[threadIdx.x] = gf_gauss_tap(threadIdx.x, 16, 4.0, norm);
+    }
+    // ---- per-note tables of the envelope kernel: br tilt, es taps, f32 bin frequencies ----
+    {
+        __shared__ double red[4];
+        float *aux = nd.env_aux;
+        const int sr = pl.sr;
+        const double nyq = (double)sr / 2.0, step = nyq / 512.0;
+        for (int b = threadIdx.x; b < GF_NBINS; b += blockDim.x)
+            aux[GF_AUX_FREQ + b] = (b == 512) ? (float)nyq : (float)((double)b * step);      // linspace(0, sr/2, 513) f32
+        if (pl.brightness_env != 1.0) {
+            // SillySampler.py:506-510: f32 linspace(1e-6, nyq), clip(f / nyq, .02, 1) ** alpha, / (mean + 1e-12)
+            const float alpha = (float)fmin(fmax(pl.brightness_env - 1.0, -0.9), 1.0);
+            const float nyqf = (float)((double)sr * 0.5);
+            double part = 0.0;
+            float tv[5];
+            int cnt = 0;
+            for (int b = threadIdx.x; b < GF_NBINS; b += blockDim.x, ++cnt) {
+                const double fv = (b == GF_NBINS - 1) ? (double)sr * 0.5 : (double)b * (((double)sr * 0.5 - 1e-6) / 512.0) + 1e-6;
+                float nf = (float)fv / nyqf;
+                nf = fminf(fmaxf(nf, 0.02f), 1.0f);
+                tv[cnt] = powf(nf, alpha);
+                part += (double)tv[cnt];
+            }
+            part = gf_warp_sum(part);
+            if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = part;
+            __syncthreads();
+            const float mean = (float)((red[0] + red[1] + red[2] + red[3]) / (double)GF_NBINS);
+            cnt = 0;
+            for (int b = threadIdx.x; b < GF_NBINS; b += blockDim.x, ++cnt) aux[GF_AUX_TILT + b] = tv[cnt] / (mean + 1e-12f);
+        }
+        if (pl.es != 0.0 && threadIdx.x < GF_MAX_ES_TAPS) {
+            const double s = fabs(pl.es);
+            const double sigma = pl.es < 0.0 ? (1.0 + 6.0 * s) : (0.8 + 4.0 * s);
+            const int radius = (int)(4.0 * sigma + 0.5);
+            float t = 0.0f;
+            if (threadIdx.x < 2 * radius + 1) {
+                double norm = 0.0;
+                for (int j = 0; j <= 2 * radius; ++j) { const double q = (double)(j - radius) / sigma; norm += exp(-0.5 * q * q); }
+                t = (float)gf_gauss_tap(threadIdx.x, radius, sigma, norm);
+            }
+            aux[GF_AUX_TAPS + threadIdx.x] = t;
+        }
     }
     const float min_hz[4] = {120.0f, 300.0f, 1500.0f, 2000.0f};
     const float max_hz = (float)((double)pl.sr * 0.48);
@@ -172,11 +221,11 @@ void gf_launch_tracks(const GfNotePlan *plans, const GfNoteDev *notes, const GfS
 #define GF_EPL 17           // bins per lane
 #define GF_ROW_L 32         // left padding of a row (reflect halo, radius <= 28)
 #define GF_ROW_LEN 600      // 32 + 513 + 55: the FIR windows of the last lanes read up to bin index 561
-#define GF_MAX_ES_TAPS 64   // radius <= 28 -> 57 taps, zero-padded to a multiple of 8
 
 struct GfEnvSmem {
     float rows[GF_ENV_WARPS][2][GF_ROW_LEN];
     float tilt[GF_ENVS_LD];
+    float freq[GF_ENVS_LD];
     float es_taps[GF_MAX_ES_TAPS];
 };
 
@@ -252,42 +301,17 @@ gf_env_kernel(const int2 *__restrict__ work, const GfNotePlan *__restrict__ plan
     const bool do_es = pl.es != 0.0;
     const bool do_fw = pl.fw != 0.0;
     int es_radius = 0;
-    if (do_tilt) {
-        // SillySampler.py:506-510: f32 linspace(1e-6, nyq), clip(f / nyq, .02, 1) ** alpha, / (mean + 1e-12)
-        const float alpha = (float)fmin(fmax(pl.brightness_env - 1.0, -0.9), 1.0);
-        const float nyqf = (float)((double)sr * 0.5);
-        __shared__ double red[GF_ENV_WARPS];
-        double part = 0.0;
-        for (int b = threadIdx.x; b < GF_NBINS; b += blockDim.x) {
-            const double fv = (b == GF_NBINS - 1) ? (double)sr * 0.5 : (double)b * (((double)sr * 0.5 - 1e-6) / 512.0) + 1e-6;
-            float nf = (float)fv / nyqf;
-            nf = fminf(fmaxf(nf, 0.02f), 1.0f);
-            const float tv = powf(nf, alpha);
-            sm.tilt[b] = tv;
-            part += (double)tv;
-        }
-        part = gf_warp_sum(part);
-        if (lane == 0) red[warp] = part;
-        __syncthreads();
-        double tot = 0.0;
-        for (int w = 0; w < GF_ENV_WARPS; ++w) tot += red[w];
-        const float mean = (float)(tot / (double)GF_NBINS);
-        for (int b = threadIdx.x; b < GF_NBINS; b += blockDim.x) sm.tilt[b] = sm.tilt[b] / (mean + 1e-12f);
-    }
     if (do_es) {
         const double s = fabs(pl.es);
         const double sigma = pl.es < 0.0 ? (1.0 + 6.0 * s) : (0.8 + 4.0 * s);
         es_radius = (int)(4.0 * sigma + 0.5);
-        if (threadIdx.x < GF_MAX_ES_TAPS) {
-            float tv = 0.0f;
-            if (threadIdx.x < 2 * es_radius + 1) {
-                double norm = 0.0;
-                for (int j = 0; j <= 2 * es_radius; ++j) { const double t = (double)(j - es_radius) / sigma; norm += exp(-0.5 * t * t); }
-                tv = (float)gf_gauss_tap(threadIdx.x, es_radius, sigma, norm);
-            }
-            sm.es_taps[threadIdx.x] = tv;
-        }
     }
+    // per-note tables prepared by gf_tracks_kernel
+    for (int b = threadIdx.x; b < GF_NBINS; b += blockDim.x) {
+        sm.freq[b] = nd.env_aux[GF_AUX_FREQ + b];
+        if (do_tilt) sm.tilt[b] = nd.env_aux[GF_AUX_TILT + b];
+    }
+    if (do_es && threadIdx.x < GF_MAX_ES_TAPS) sm.es_taps[threadIdx.x] = nd.env_aux[GF_AUX_TAPS + threadIdx.x];
     __syncthreads();
 
     const int t = wk.y * GF_FT + warp;
@@ -370,9 +394,7 @@ gf_env_kernel(const int2 *__restrict__ work, const GfNotePlan *__restrict__ plan
             const float isg = 1.0f / sig[k];
 #pragma unroll
             for (int e = 0; e < GF_EPL; ++e) {
-                const int b = b0 + e;
-                const float fb = (b >= 512) ? (float)nyq : (float)((double)b * step);
-                const float d = (fb - Fk) * isg;
+                const float d = (sm.freq[min(b0 + e, 512)] - Fk) * isg;
                 acc[e] *= fmaf(sv, __expf(-0.5f * (d * d)), 1.0f);
             }
         }
@@ -438,6 +460,9 @@ gf_env_kernel(const int2 *__restrict__ work, const GfNotePlan *__restrict__ plan
         }
         xs[nk] = nyq; xd[nk] = nyq; ++nk;
         for (int j = 0; j + 1 < nk; ++j) sl[j] = (xs[j + 1] - xs[j]) / (xd[j + 1] - xd[j]);
+        bool mono = true;
+        for (int j = 0; j + 1 < nk; ++j) mono = mono && (xd[j] <= xd[j + 1]);
+        int i = 0;
 #pragma unroll
         for (int e = 0; e < GF_EPL; ++e) {
             if (e < nown) {
@@ -448,7 +473,7 @@ gf_env_kernel(const int2 *__restrict__ work, const GfNotePlan *__restrict__ plan
                 if (x > xd[nk - 1]) wf = xs[nk - 1];
                 else if (x < xd[0]) wf = xs[0];
                 else {
-                    int i = 0;
+                    if (!mono) i = 0;                     // x ascends with e: the bracket only moves right
                     while (i < nk && x >= xd[i]) ++i;
                     const int j = i - 1;
                     if (j >= nk - 1) wf = xs[nk - 1];
