@@ -209,6 +209,7 @@ def run_native(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        os.environ["NCCL_DEBUG"] = os.environ.get("GOOFER_NCCL_DEBUG", "WARN")      # keep stdout to the one JSON line
         dist.init_process_group("nccl", device_id=dev)
     capi.load()
 
