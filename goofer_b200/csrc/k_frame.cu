@@ -52,6 +52,81 @@ __device__ __forceinline__ float2 gf_gauss5(const float2 *row, int k, const floa
     return acc;
 }
 
+struct GfShapeIn { float ef[2], en[2], ph[2]; };        // envF, envN, phi at bins (k, 512 - k) of one frame
+
+// spectral shaping of one bin of one frame (GOOFER.py:1101-1173): high-pass sigmoid, envelope, boost, noise
+// phases, brightness curves of voiced frames.  Returns harmonic / breath / unvoiced bins.
+__device__ __forceinline__ void gf_shape_bin(int bq, float2 S, float f0f, bool vo, float ef, float en, float phi,
+                                             float2 &h, float2 &b, float2 &v, float &local_max)
+{
+    const float hp = gf_hp_sigmoid(d_tab.freq32[bq], f0f);
+    const float2 s = make_float2(S.x * hp, S.y * hp);
+    local_max = fmaxf(local_max, fmaf(s.x, s.x, s.y * s.y));      // max |S|^2: sqrt taken once at the end
+    const float bo = d_tab.boost[bq];
+    h = make_float2(s.x * ef * bo, s.y * ef * bo);
+    // U = cos(phi) + i sin(phi), phi in [0, 2 pi): evaluated at phi - pi where the fast path is accurate
+    float sn, cs;
+    __sincosf(phi - 3.14159274f, &sn, &cs);
+    v = make_float2(-cs * en, -sn * en);
+    b = make_float2(v.x * hp, v.y * hp);
+    if (vo) {
+        const float bh = d_tab.bright_h[bq], bb = d_tab.bright_b[bq];
+        h.x *= bh; h.y *= bh; b.x *= bb; b.y *= bb;
+    }
+}
+
+__device__ __forceinline__ void gf_shape_pair(GfFrameSmem &sm, int k, int f, float f0f, bool vo, const GfShapeIn &in,
+                                              const float2 *__restrict__ tw1024, float &local_max)
+{
+    const int km = 512 - k;
+    float2 *zf = &sm.z[2][f][0];
+    const float2 w = tw1024[k];
+    float2 S0, S1;
+    gf_rfft_split(zf[gf_fpad(k)], zf[gf_fpad(km & 511)], w, S0, S1);
+    float2 H0, H1, B0, B1, V0, V1;
+    gf_shape_bin(k, S0, f0f, vo, in.ef[0], in.en[0], in.ph[0], H0, B0, V0, local_max);
+    gf_shape_bin(km, S1, f0f, vo, in.ef[1], in.en[1], in.ph[1], H1, B1, V1, local_max);
+    if (vo) {
+        sm.stag[0][f][k] = H0; sm.stag[0][f][km] = H1;
+        sm.stag[1][f][k] = B0; sm.stag[1][f][km] = B1;
+    }
+    // pocketfft c2r ignores the imaginary parts of DC and Nyquist
+    if (k == 0) { V0.y = 0.f; V1.y = 0.f; H0.y = 0.f; H1.y = 0.f; B0.y = 0.f; B1.y = 0.f; }
+    float2 Zk, Zm;
+    gf_irfft_merge(V0, V1, w, Zk, Zm);
+    zf[gf_fpad(k)] = Zk;
+    if (k != 0) zf[gf_fpad(km)] = Zm;
+    if (!vo) {
+        gf_irfft_merge(H0, H1, w, Zk, Zm);
+        sm.z[0][f][gf_fpad(k)] = Zk;
+        if (k != 0) sm.z[0][f][gf_fpad(km)] = Zm;
+        gf_irfft_merge(B0, B1, w, Zk, Zm);
+        sm.z[1][f][gf_fpad(k)] = Zk;
+        if (k != 0) sm.z[1][f][gf_fpad(km)] = Zm;
+    }
+}
+
+// bin 256 (pairs with itself)
+__device__ __forceinline__ void gf_shape_mid(GfFrameSmem &sm, int f, float f0f, bool vo, float ef, float en, float phi,
+                                             const float2 *__restrict__ tw1024, float &local_max)
+{
+    float2 *zf = &sm.z[2][f][0];
+    const float2 w = tw1024[256];
+    const float2 Zq = zf[gf_fpad(256)];
+    float2 S, dummy, H, B, V, Zk, Zm;
+    gf_rfft_split(Zq, Zq, w, S, dummy);
+    gf_shape_bin(256, S, f0f, vo, ef, en, phi, H, B, V, local_max);
+    gf_irfft_merge(V, V, w, Zk, Zm);
+    zf[gf_fpad(256)] = Zk;
+    if (vo) { sm.stag[0][f][256] = H; sm.stag[1][f][256] = B; }
+    else {
+        gf_irfft_merge(H, H, w, Zk, Zm);
+        sm.z[0][f][gf_fpad(256)] = Zk;
+        gf_irfft_merge(B, B, w, Zk, Zm);
+        sm.z[1][f][gf_fpad(256)] = Zk;
+    }
+}
+
 // One round of the windowed overlap-add for one stream (GOOFER.py:372-390, 402-411).  Frames t0 .. t0+NF-1 sit
 // in `bufs` as unnormalised inverse-FFT output (scale 1/512).  Thread `tid` owns sample column tid of every hop
 // block: it adds the NF x 4 windowed contributions in ascending frame order (like _overlap_add), divides the
@@ -119,9 +194,6 @@ gf_frame_kernel(const int4 *__restrict__ work, const GfPassDev *__restrict__ pas
     const float *__restrict__ win = d_tab.win;
     const float2 *__restrict__ tw1024 = d_tab.tw1024;
     for (int i = tid; i < 9 * GF_HOP; i += blockDim.x) (&sm.carry[0][0][0])[i] = 0.0f;
-    float g5[5];
-#pragma unroll
-    for (int j = 0; j < 5; ++j) g5[j] = (float)d_tab.g05[j];
 
     const int t_begin = max(0, b0 - 3), t_end = min(T - 1, b0 + nb - 1);
     const int n_f0 = (n + GF_HOP - 1) / GF_HOP;          // len(f0[::256])
@@ -155,81 +227,47 @@ gf_frame_kernel(const int4 *__restrict__ work, const GfPassDev *__restrict__ pas
         __syncthreads();
         // ---- 2. forward FFT ----
         gf_cta_fft512<false>(&sm.z[2][0][0], nf, sm.tw512);
-        // ---- 3. shaping, per bin pair (k, 512 - k) ----
-        for (int idx = tid; idx < nf * 256; idx += blockDim.x) {
-            int k, f;
-            if (nf == GF_RND) { k = idx >> 2; f = idx & 3; } else { k = idx / nf; f = idx - k * nf; }
-            const int t = t0 + f;
-            const int km = 512 - k;
-            const float f0f = sm.f0fr[f];
-            const bool vo = sm.voiced[f] != 0;
-            float2 *zf = &sm.z[2][f][0];
+        // ---- 3. shaping, per bin pair (k, 512 - k); bin 256 pairs with itself and goes to threads 0..nf-1 ----
+        if (nf == GF_RND) {
+            // item m of this thread: k = (tid >> 2) + 64 m, frame f = tid & 3.  All global operands of the four
+            // items are requested up front (24 loads in flight per thread) before any of them is consumed.
+            const int f = tid & 3, t = t0 + f;
             const float *eF = nd.envF + (size_t)t * GF_ENVS_LD, *eN = nd.envN + (size_t)t * GF_ENVS_LD;
             const float *ph = ps.phi + t;
-            const int nbin = (k == 0) ? 3 : 2;
-            float2 H[3], B[3], V[3];
-            int bins[3] = {k, km, 256};
-            float2 S[3];
-            {
-                const float2 Zk = zf[gf_fpad(k)], Zm = zf[gf_fpad(km & 511)];
-                gf_rfft_split(Zk, Zm, tw1024[k], S[0], S[1]);
-                if (k == 0) {
-                    const float2 Zq = zf[gf_fpad(256)];
-                    float2 dummy;
-                    gf_rfft_split(Zq, Zq, tw1024[256], S[2], dummy);
-                }
-            }
+            GfShapeIn in[4];
 #pragma unroll
-            for (int q = 0; q < 3; ++q) {
-                if (q < nbin) {
-                    const int bq = bins[q];
-                    const float hp = gf_hp_sigmoid(d_tab.freq32[bq], f0f);
-                    float2 s = make_float2(S[q].x * hp, S[q].y * hp);
-                    local_max = fmaxf(local_max, fmaf(s.x, s.x, s.y * s.y));      // max |S|^2: sqrt taken once at the end
-                    const float ef = eF[bq], en = eN[bq];
-                    const float bo = d_tab.boost[bq];
-                    float2 h = make_float2(s.x * ef * bo, s.y * ef * bo);
-                    // U = cos(phi) + i sin(phi), phi in [0, 2 pi): evaluated at phi - pi where the fast path is accurate
-                    float sn, cs;
-                    __sincosf(ph[(size_t)bq * T] - 3.14159274f, &sn, &cs);
-                    float2 v = make_float2(-cs * en, -sn * en);
-                    float2 b = make_float2(v.x * hp, v.y * hp);
-                    if (vo) {
-                        const float bh = d_tab.bright_h[bq], bb = d_tab.bright_b[bq];
-                        h.x *= bh; h.y *= bh; b.x *= bb; b.y *= bb;
-                        sm.stag[0][f][bq] = h;
-                        sm.stag[1][f][bq] = b;
-                    }
-                    H[q] = h; B[q] = b; V[q] = v;
-                }
+            for (int m = 0; m < 4; ++m) {
+                const int k = (tid >> 2) + 64 * m, km = 512 - k;
+                in[m].ef[0] = eF[k];  in[m].ef[1] = eF[km];
+                in[m].en[0] = eN[k];  in[m].en[1] = eN[km];
+                in[m].ph[0] = ph[(size_t)k * T];  in[m].ph[1] = ph[(size_t)km * T];
             }
-            // pocketfft c2r ignores the imaginary parts of DC and Nyquist
-            if (k == 0) { V[0].y = 0.f; V[1].y = 0.f; H[0].y = 0.f; H[1].y = 0.f; B[0].y = 0.f; B[1].y = 0.f; }
-            float2 Zk, Zm;
-            gf_irfft_merge(V[0], V[1], tw1024[k], Zk, Zm);
-            zf[gf_fpad(k)] = Zk;
-            if (k != 0) zf[gf_fpad(km)] = Zm;
-            if (k == 0) {
-                gf_irfft_merge(V[2], V[2], tw1024[256], Zk, Zm);
-                zf[gf_fpad(256)] = Zk;
+            const float f0f = sm.f0fr[f];
+            const bool vo = sm.voiced[f] != 0;
+#pragma unroll
+            for (int m = 0; m < 4; ++m) gf_shape_pair(sm, (tid >> 2) + 64 * m, f, f0f, vo, in[m], tw1024, local_max);
+        } else {
+            for (int idx = tid; idx < nf * 256; idx += blockDim.x) {
+                const int k = idx / nf, f = idx - k * nf, km = 512 - k, t = t0 + f;
+                const float *eF = nd.envF + (size_t)t * GF_ENVS_LD, *eN = nd.envN + (size_t)t * GF_ENVS_LD;
+                const float *ph = ps.phi + t;
+                GfShapeIn in;
+                in.ef[0] = eF[k];  in.ef[1] = eF[km];
+                in.en[0] = eN[k];  in.en[1] = eN[km];
+                in.ph[0] = ph[(size_t)k * T];  in.ph[1] = ph[(size_t)km * T];
+                gf_shape_pair(sm, k, f, sm.f0fr[f], sm.voiced[f] != 0, in, tw1024, local_max);
             }
-            if (!vo) {
-                gf_irfft_merge(H[0], H[1], tw1024[k], Zk, Zm);
-                sm.z[0][f][gf_fpad(k)] = Zk;
-                if (k != 0) sm.z[0][f][gf_fpad(km)] = Zm;
-                gf_irfft_merge(B[0], B[1], tw1024[k], Zk, Zm);
-                sm.z[1][f][gf_fpad(k)] = Zk;
-                if (k != 0) sm.z[1][f][gf_fpad(km)] = Zm;
-                if (k == 0) {
-                    gf_irfft_merge(H[2], H[2], tw1024[256], Zk, Zm);
-                    sm.z[0][f][gf_fpad(256)] = Zk;
-                    gf_irfft_merge(B[2], B[2], tw1024[256], Zk, Zm);
-                    sm.z[1][f][gf_fpad(256)] = Zk;
-                }
-            }
+        }
+        if (tid < nf) {
+            const int f = tid, t = t0 + f;
+            gf_shape_mid(sm, f, sm.f0fr[f], sm.voiced[f] != 0, nd.envF[(size_t)t * GF_ENVS_LD + 256],
+                         nd.envN[(size_t)t * GF_ENVS_LD + 256], ps.phi[(size_t)256 * T + t], tw1024, local_max);
         }
         __syncthreads();
         // ---- 4. voiced frames: 5-tap Gaussian along frequency, then merge ----
+        float g5[5];
+#pragma unroll
+        for (int j = 0; j < 5; ++j) g5[j] = (float)d_tab.g05[j];
         for (int idx = tid; idx < nf * 256; idx += blockDim.x) {
             int k, f;
             if (nf == GF_RND) { k = idx >> 2; f = idx & 3; } else { k = idx / nf; f = idx - k * nf; }
