@@ -59,8 +59,10 @@ template <bool INV> GF_HD void gf_dft8(float2 *v)
 // running in place.
 template <bool INV, int NS> GF_HD void gf_fft_pass_load(int j, const float2 *buf, const float2 *tw512, float2 *v)
 {
+    // gf_fpad(j + 64 r) == gf_fpad(j) + 66 r for j < 64: one base, immediate offsets
+    const float2 *src = buf + gf_fpad(j);
 #pragma unroll
-    for (int r = 0; r < 8; ++r) v[r] = buf[gf_fpad(j + 64 * r)];
+    for (int r = 0; r < 8; ++r) v[r] = src[66 * r];
     if (NS > 1) {
         const int k = j & (NS - 1);
         const int step = k * (64 / NS);          // twiddle exponent for r = 1 (in 512ths of a turn)
@@ -76,10 +78,23 @@ template <bool INV, int NS> GF_HD void gf_fft_pass_load(int j, const float2 *buf
 
 template <int NS> GF_HD void gf_fft_pass_store(int j, float2 *buf, const float2 *v)
 {
-    const int k = j & (NS - 1);
-    const int j0 = ((j - k) << 3) + k;
+    // padded index of j0 + r NS with j0 = 8 (j - k) + k, k = j mod NS, written with compile-time offsets:
+    //   NS = 1 : 8 j + r, all eight in the same 32-group            -> base + r
+    //   NS = 8 : 64 (j >> 3) + k + 8 r, crosses one 32-group at r=4 -> base + 8 r + (r >= 4)
+    //   NS = 64: j + 64 r                                            -> base + 66 r
+    if (NS == 1) {
+        float2 *dst = buf + 8 * j + (j >> 2);
 #pragma unroll
-    for (int r = 0; r < 8; ++r) buf[gf_fpad(j0 + r * NS)] = v[r];
+        for (int r = 0; r < 8; ++r) dst[r] = v[r];
+    } else if (NS == 8) {
+        float2 *dst = buf + 66 * (j >> 3) + (j & 7);
+#pragma unroll
+        for (int r = 0; r < 8; ++r) dst[8 * r + (r >= 4 ? 1 : 0)] = v[r];
+    } else {
+        float2 *dst = buf + gf_fpad(j);
+#pragma unroll
+        for (int r = 0; r < 8; ++r) dst[66 * r] = v[r];
+    }
 }
 
 // ---- even/odd split --------------------------------------------------------------------------

@@ -60,6 +60,29 @@ __device__ __forceinline__ void gf_load_frames(float2 *bufs, int t0, int nf, int
     }
 }
 
+// same for exactly four frames and 256 threads: the sixteen loads of a thread are issued before the first
+// windowed value is stored (the compiler cannot hoist generic loads over shared-memory stores on its own)
+template <typename LoadFn>
+__device__ __forceinline__ void gf_load_frames4(float2 *bufs, int t0, int n, const float *win, LoadFn load)
+{
+    float x0[8], x1[8];
+#pragma unroll
+    for (int it = 0; it < 8; ++it) {
+        const int idx = threadIdx.x + 256 * it;
+        const int f = idx >> 9, m = idx & 511;
+        const int p = GF_HOP * (t0 + f) + 2 * m - GF_NFFT / 2;
+        const bool inside = (p >= 0) && (p + 1 < n);
+        x0[it] = load(inside ? p : gf_reflect(p, n));
+        x1[it] = load(inside ? p + 1 : gf_reflect(p + 1, n));
+    }
+#pragma unroll
+    for (int it = 0; it < 8; ++it) {
+        const int idx = threadIdx.x + 256 * it;
+        const int f = idx >> 9, m = idx & 511;
+        bufs[(size_t)f * GF_FFT_BUF + gf_fpad(m)] = make_float2(x0[it] * win[2 * m], x1[it] * win[2 * m + 1]);
+    }
+}
+
 // ---- overlap-add ring -----------------------------------------------------------------------
 // Padded-signal hop block b holds samples [256 b, 256 b + 256); frame t adds into blocks t..t+3.
 // The ring keeps 8 block slots (slot = b & 7) per stream.

@@ -160,17 +160,17 @@ __device__ __forceinline__ double gf_walk_chain(double *s_inc, double inc, int l
 {
     s_inc[lane] = inc;
     __syncwarp();
-    double run = total, mine = 0.0;
+    // lane L adds increments 0..L to the incoming phase, one after the other: the same additions in the same
+    // order as the reference's scalar loop up to sample L
+    double mine = total;
     const double2 *s2 = reinterpret_cast<const double2 *>(s_inc);
 #pragma unroll
     for (int k = 0; k < 16; ++k) {
         const double2 v = s2[k];
-        run = __dadd_rn(run, v.x);
-        if (lane == 2 * k) mine = run;
-        run = __dadd_rn(run, v.y);
-        if (lane == 2 * k + 1) mine = run;
+        if (lane >= 2 * k) mine = __dadd_rn(mine, v.x);
+        if (lane >= 2 * k + 1) mine = __dadd_rn(mine, v.y);
     }
-    total = run;
+    total = __shfl_sync(0xffffffffu, mine, 31);
     __syncwarp();
     return mine;
 }
@@ -213,30 +213,43 @@ gf_walk_kernel(const GfPassDev *__restrict__ passes, GfPassScal *scal, int n_pas
             const bool valid = (i < n) && ((double)f > 1e-6);
             const unsigned bal = __ballot_sync(0xffffffffu, valid);
             if (gmax > fired) {
-                // rare path: at least one onset in this group
-#pragma unroll
-                for (int o = 1; o < 32; o <<= 1) {
-                    const int v = __shfl_up_sync(0xffffffffu, m, o);
-                    if (lane >= o) m = max(m, v);
-                }
-                m = max(m, fired);
+                // at least one onset in this group
                 int prev = __shfl_up_sync(0xffffffffu, m, 1);
                 if (lane == 0) prev = fired;
-                const int cnt = (i < n) ? (m - prev) : 0;
+                const bool simple = (i >= n) || (m >= prev && m - prev <= 1 && m >= fired);
+                int cnt;
+                int slot;
+                if (__all_sync(0xffffffffu, simple)) {
+                    // common case (f0 >= 0, at most one pulse per sample): floor(total) is its own running maximum
+                    cnt = (i < n) ? (m - prev) : 0;
+                    const unsigned fm = __ballot_sync(0xffffffffu, cnt > 0);
+                    slot = count + __popc(fm & ((1u << lane) - 1u));
+                    count += __popc(fm);
+                } else {
+#pragma unroll
+                    for (int o = 1; o < 32; o <<= 1) {
+                        const int v = __shfl_up_sync(0xffffffffu, m, o);
+                        if (lane >= o) m = max(m, v);
+                    }
+                    m = max(m, fired);
+                    prev = __shfl_up_sync(0xffffffffu, m, 1);
+                    if (lane == 0) prev = fired;
+                    cnt = (i < n) ? (m - prev) : 0;
+                    int incl = cnt;
+#pragma unroll
+                    for (int o = 1; o < 32; o <<= 1) {
+                        const int v = __shfl_up_sync(0xffffffffu, incl, o);
+                        if (lane >= o) incl += v;
+                    }
+                    slot = count + incl - cnt;
+                    count += __shfl_sync(0xffffffffu, incl, 31);
+                }
                 // last f0 > 1e-6 at or before sample i
                 const unsigned below = bal & ((2u << lane) - 1u);
                 const float cand = __shfl_sync(0xffffffffu, f, below ? (31 - __clz(below)) : 0);
                 const float lvf = below ? cand : lv_carry;
-                int incl = cnt;
-#pragma unroll
-                for (int o = 1; o < 32; o <<= 1) {
-                    const int v = __shfl_up_sync(0xffffffffu, incl, o);
-                    if (lane >= o) incl += v;
-                }
-                int slot = count + incl - cnt;
                 for (int c = 0; c < cnt; ++c, ++slot)
                     if (slot < ps.onset_cap) ps.onsets[slot] = make_int4(i, 0, __float_as_int(lvf), 0);   // T0 / table max: gf_onset_kernel
-                count += __shfl_sync(0xffffffffu, incl, 31);
                 fired = max(fired, gmax);
             }
             if (bal) lv_carry = __shfl_sync(0xffffffffu, f, 31 - __clz(bal));

@@ -216,6 +216,8 @@ gf_frame_kernel(const int4 *__restrict__ work, const GfPassDev *__restrict__ pas
                 // GOOFER.py:724-736: sub *= mask; sub /= max; sub *= weight; pulse (f32) += sub (f64)
                 return (float)((double)pulse[i] + ((double)sub[i] * (double)vm[i]) * sub_scale);
             });
+        } else if (nf == GF_RND) {
+            gf_load_frames4(&sm.z[2][0][0], t0, n, win, [&](int i) { return pulse[i]; });
         } else {
             gf_load_frames(&sm.z[2][0][0], t0, nf, n, win, [&](int i) { return pulse[i]; });
         }
