@@ -232,6 +232,7 @@ static void gf_carve_note(const GfNotePlan &p, Bump &bp, GfNoteDev *nd, GfPassDe
     d.vm = bp.arr<float>(n);
     d.ms_short = bp.arr<float>((n + 3) / 4);
     d.ms = bp.arr<float>(n);
+    d.ms_one = bp.arr<unsigned char>((n + 255) / 256 + 4);
     if (p.f0_jitter) d.z_sh = bp.arr<double>(n);
     if (p.vol_jitter) { d.z_srh = bp.arr<double>(n); d.z_srb = bp.arr<double>(n); d.vjm = bp.arr<float>(n); }
     if (p.sd > 0) d.sdm = bp.arr<float>(n);
@@ -296,13 +297,21 @@ static size_t gf_wave_meta_bytes(size_t n_notes, size_t n_pass, size_t n_env_wor
            n_pass * 16 * sizeof(GfOnepoleJob) + n_notes * (3 * sizeof(int) + 2 * sizeof(GfFirJob)) + 32 * 256;
 }
 
-#define GF_BLOCKS_PER_CTA 32      // output hop blocks one frame-kernel CTA owns (3 frames of halo each)
+#define GF_BLOCKS_PER_CTA 64      // at most this many output hop blocks per frame-kernel CTA (3 frames of halo each)
+
+// balanced split of a note's hop blocks: as few CTAs as the cap allows, equal shares
+static inline int gf_blocks_per_cta(int n_blocks)
+{
+    const int parts = (n_blocks + GF_BLOCKS_PER_CTA - 1) / GF_BLOCKS_PER_CTA;
+    return (n_blocks + parts - 1) / std::max(parts, 1);
+}
 
 static void gf_note_work_counts(const GfNotePlan &p, size_t *n_env, size_t *n_frame, size_t *n_fir)
 {
     *n_env = (size_t)(p.T_out + GF_FT - 1) / GF_FT;
     const int n_blocks = std::max(p.T_out, 2) - 2 + 1;
-    *n_frame = (size_t)p.n_passes * ((n_blocks + GF_BLOCKS_PER_CTA - 1) / GF_BLOCKS_PER_CTA);
+    const int bpc = gf_blocks_per_cta(n_blocks);
+    *n_frame = (size_t)p.n_passes * ((n_blocks + bpc - 1) / bpc);
     *n_fir = 8;
 }
 
@@ -464,9 +473,10 @@ static int gf_render_wave(const GooferBatch *b, const std::vector<GfNotePlan> &a
         const int tiles = (p.T_out + GF_FT - 1) / GF_FT;
         for (int t = 0; t < tiles; ++t) wh.env_work.push_back(make_int2(i, t));
         const int n_blocks = std::max(p.T_out, 2) - 2 + 1;
+        const int bpc = gf_blocks_per_cta(n_blocks);
         for (int k = 0; k < p.n_passes; ++k)
-            for (int bb = 0; bb < n_blocks; bb += GF_BLOCKS_PER_CTA)
-                wh.frame_work.push_back(make_int4((int)(pi + k), 2 + bb, std::min(GF_BLOCKS_PER_CTA, n_blocks - bb), 0));
+            for (int bb = 0; bb < n_blocks; bb += bpc)
+                wh.frame_work.push_back(make_int4((int)(pi + k), 2 + bb, std::min(bpc, n_blocks - bb), 0));
         // FIR jobs (Gaussian smoothing along time)
         {
             GfFirJob j;

@@ -71,6 +71,7 @@ struct GfNoteDev {
     float *f0n;             // (n_total,) f32(f0_new): cutoff driver of the post-FX filters, or NULL
     float *ms_short;        // (ceil(n/4),) f32: gaussian-smoothed decimated mask   GOOFER.py:556-563
     float *ms;              // (n_total,) f32: smooth_mask_ds result (lerp of ms_short)  GOOFER.py:564-569
+    unsigned char *ms_one;  // (ceil(n/256),) 1 where ms == 1 on the whole hop block [256 b, 256 b + 256)
     double *z_sh;           // (n_total,) smoothed sh noise (f0 jitter) or NULL
     double *z_srh, *z_srb;  // smoothed sr noise
     float *vjm;             // gauss(vm, 20) (sr)

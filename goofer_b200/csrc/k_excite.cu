@@ -43,7 +43,7 @@ __device__ __forceinline__ double gf_midi_at(const GfNotePlan &pl, const float *
     return __dadd_rn(__dmul_rn(slope, x - x0), y0);
 }
 
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 4)
 gf_f0_kernel(const GfNotePlan *__restrict__ plans, const GfNoteDev *__restrict__ notes, const GfPassDev *__restrict__ passes,
              const GfSourceDev *__restrict__ srcs, const float *__restrict__ bend_all, const double *__restrict__ normals)
 {
@@ -60,11 +60,19 @@ gf_f0_kernel(const GfNotePlan *__restrict__ plans, const GfNoteDev *__restrict__
     const double midi_flat = flat ? gf_midi_at(pl, bend, 0) : 0.0;
     const double hz_flat = flat ? 440.0 * exp2((midi_flat - 69.0) / 12.0) : 0.0;
     const int M = (n + 3) / 4;
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        const double m = gf_mask_new(pl, mask_src, i);
+    for (int base = blockIdx.x * blockDim.x; base < n; base += gridDim.x * blockDim.x) {
+        const int i = base + threadIdx.x;
+        // smooth_mask_ds (GOOFER.py:564-569) + per hop block: is the smoothed mask exactly 1 everywhere?  Where it
+        // is, aper_uv * (1 - mask) vanishes identically and the frame kernel skips the unvoiced stream.
+        float msv = 1.0f;
+        if (i < n) { msv = gf_ms_at(nd.ms_short, M, i, n); nd.ms[i] = msv; }
+        const int all_one = __syncthreads_and(msv == 1.0f);
+        if (threadIdx.x == 0) nd.ms_one[base >> 8] = (unsigned char)all_one;
+        if (i >= n) continue;
+        // without the velocity stretch mask_new is a plain copy of source samples: vm (f32) holds it exactly
+        const double m = pl.vel_active ? gf_mask_new(pl, mask_src, i) : (double)nd.vm[i];
         const double midi = flat ? midi_flat : gf_midi_at(pl, bend, i);
         const double hz = flat ? hz_flat : 440.0 * exp2((midi - 69.0) / 12.0);
-        nd.ms[i] = gf_ms_at(nd.ms_short, M, i, n);
         double f0 = m * hz;
         // ---- vocal fry f0 override (SillySampler.py:890-934) ----
         if (pl.fry_L > 0) {
@@ -116,7 +124,7 @@ void gf_launch_f0(const GfNotePlan *plans, const GfNoteDev *notes, const GfPassD
                   const float *bend, const double *normals, int n_notes, int max_n, cudaStream_t st)
 {
     if (n_notes <= 0) return;
-    dim3 grid(min(64, (max_n + 255) / 256), n_notes);
+    dim3 grid(min(192, (max_n + 255) / 256), n_notes);
     gf_f0_kernel<<<grid, 256, 0, st>>>(plans, notes, passes, srcs, bend, normals);
 }
 

@@ -23,6 +23,7 @@ struct GfFrameSmem {
     float carry[3][3][GF_HOP];                // per stream: the three hop blocks still waiting for later frames
     float f0fr[GF_RND];
     int voiced[GF_RND];
+    int uvskip[GF_RND];                       // frame lies where the smoothed mask is exactly 1: aper_uv * (1 - mask) == 0
     float red[GF_FRAME_THREADS / 32];
 };
 
@@ -75,7 +76,7 @@ __device__ __forceinline__ void gf_shape_bin(int bq, float2 S, float f0f, bool v
     }
 }
 
-__device__ __forceinline__ void gf_shape_pair(GfFrameSmem &sm, int k, int f, float f0f, bool vo, const GfShapeIn &in,
+__device__ __forceinline__ void gf_shape_pair(GfFrameSmem &sm, int k, int f, float f0f, bool vo, bool uv_on, const GfShapeIn &in,
                                               const float2 *__restrict__ tw1024, float &local_max)
 {
     const int km = 512 - k;
@@ -93,9 +94,11 @@ __device__ __forceinline__ void gf_shape_pair(GfFrameSmem &sm, int k, int f, flo
     // pocketfft c2r ignores the imaginary parts of DC and Nyquist
     if (k == 0) { V0.y = 0.f; V1.y = 0.f; H0.y = 0.f; H1.y = 0.f; B0.y = 0.f; B1.y = 0.f; }
     float2 Zk, Zm;
-    gf_irfft_merge(V0, V1, w, Zk, Zm);
-    zf[gf_fpad(k)] = Zk;
-    if (k != 0) zf[gf_fpad(km)] = Zm;
+    if (uv_on) {
+        gf_irfft_merge(V0, V1, w, Zk, Zm);
+        zf[gf_fpad(k)] = Zk;
+        if (k != 0) zf[gf_fpad(km)] = Zm;
+    }
     if (!vo) {
         gf_irfft_merge(H0, H1, w, Zk, Zm);
         sm.z[0][f][gf_fpad(k)] = Zk;
@@ -107,7 +110,7 @@ __device__ __forceinline__ void gf_shape_pair(GfFrameSmem &sm, int k, int f, flo
 }
 
 // bin 256 (pairs with itself)
-__device__ __forceinline__ void gf_shape_mid(GfFrameSmem &sm, int f, float f0f, bool vo, float ef, float en, float phi,
+__device__ __forceinline__ void gf_shape_mid(GfFrameSmem &sm, int f, float f0f, bool vo, bool uv_on, float ef, float en, float phi,
                                              const float2 *__restrict__ tw1024, float &local_max)
 {
     float2 *zf = &sm.z[2][f][0];
@@ -116,8 +119,10 @@ __device__ __forceinline__ void gf_shape_mid(GfFrameSmem &sm, int f, float f0f, 
     float2 S, dummy, H, B, V, Zk, Zm;
     gf_rfft_split(Zq, Zq, w, S, dummy);
     gf_shape_bin(256, S, f0f, vo, ef, en, phi, H, B, V, local_max);
-    gf_irfft_merge(V, V, w, Zk, Zm);
-    zf[gf_fpad(256)] = Zk;
+    if (uv_on) {
+        gf_irfft_merge(V, V, w, Zk, Zm);
+        zf[gf_fpad(256)] = Zk;
+    }
     if (vo) { sm.stag[0][f][256] = H; sm.stag[1][f][256] = B; }
     else {
         gf_irfft_merge(H, H, w, Zk, Zm);
@@ -133,7 +138,8 @@ __device__ __forceinline__ void gf_shape_mid(GfFrameSmem &sm, int f, float f0f, 
 // finished blocks by their win^2 sum, writes them, and carries the three unfinished blocks to the next round.
 template <int NF>
 __device__ __forceinline__ void gf_ola_round(float (*carry)[GF_HOP], const float2 *bufs, const float *__restrict__ win,
-                                             int t0, int T, int n_out, float *__restrict__ out, int b0, int nb, bool last)
+                                             int t0, int T, int n_out, float *__restrict__ out, int b0, int nb, bool last,
+                                             bool no_input)
 {
     const int r = threadIdx.x;
     float acc[NF + 3];
@@ -146,6 +152,7 @@ __device__ __forceinline__ void gf_ola_round(float (*carry)[GF_HOP], const float
     for (int q = 0; q < 4; ++q) w[q] = win[GF_HOP * q + r];
 #pragma unroll
     for (int f = 0; f < NF; ++f) {
+        if (no_input) break;                               // skipped stream: only flush what earlier rounds carried
         const float *zf = reinterpret_cast<const float *>(bufs + (size_t)f * GF_FFT_BUF);
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
@@ -225,10 +232,18 @@ gf_frame_kernel(const int4 *__restrict__ work, const GfPassDev *__restrict__ pas
             const int fi = min(t0 + tid, n_f0 - 1) * GF_HOP;      // f0[::hop] edge-padded   GOOFER.py:1104-1106
             sm.f0fr[tid] = ps.f0[fi];
             sm.voiced[tid] = ps.mask_ones ? 1 : (vm[fi] > 0.0f);  // GOOFER.py:1132-1136
+            // samples of frame t live in hop blocks t-2 .. t+1 of the output
+            int one = 1;
+            const int nblk = (n + GF_HOP - 1) / GF_HOP;
+            for (int bb = t0 + tid - 2; bb <= t0 + tid + 1; ++bb)
+                if (bb >= 0 && bb < nblk) one &= (int)nd.ms_one[bb];
+            sm.uvskip[tid] = ps.mask_ones ? 1 : one;          // sa pass: uv is multiplied by 0 (SillySampler.py:1156-1170)
         }
         __syncthreads();
         // ---- 2. forward FFT ----
         gf_cta_fft512<false>(&sm.z[2][0][0], nf, sm.tw512);
+        bool uv_on = false;                                   // uniform: the round computes the unvoiced stream unless every frame may skip it
+        for (int q = 0; q < nf; ++q) uv_on = uv_on || (sm.uvskip[q] == 0);
         // ---- 3. shaping, per bin pair (k, 512 - k); bin 256 pairs with itself and goes to threads 0..nf-1 ----
         if (nf == GF_RND) {
             // item m of this thread: k = (tid >> 2) + 64 m, frame f = tid & 3.  All global operands of the four
@@ -247,7 +262,7 @@ gf_frame_kernel(const int4 *__restrict__ work, const GfPassDev *__restrict__ pas
             const float f0f = sm.f0fr[f];
             const bool vo = sm.voiced[f] != 0;
 #pragma unroll
-            for (int m = 0; m < 4; ++m) gf_shape_pair(sm, (tid >> 2) + 64 * m, f, f0f, vo, in[m], tw1024, local_max);
+            for (int m = 0; m < 4; ++m) gf_shape_pair(sm, (tid >> 2) + 64 * m, f, f0f, vo, uv_on, in[m], tw1024, local_max);
         } else {
             for (int idx = tid; idx < nf * 256; idx += blockDim.x) {
                 const int k = idx / nf, f = idx - k * nf, km = 512 - k, t = t0 + f;
@@ -257,12 +272,12 @@ gf_frame_kernel(const int4 *__restrict__ work, const GfPassDev *__restrict__ pas
                 in.ef[0] = eF[k];  in.ef[1] = eF[km];
                 in.en[0] = eN[k];  in.en[1] = eN[km];
                 in.ph[0] = ph[(size_t)k * T];  in.ph[1] = ph[(size_t)km * T];
-                gf_shape_pair(sm, k, f, sm.f0fr[f], sm.voiced[f] != 0, in, tw1024, local_max);
+                gf_shape_pair(sm, k, f, sm.f0fr[f], sm.voiced[f] != 0, uv_on, in, tw1024, local_max);
             }
         }
         if (tid < nf) {
             const int f = tid, t = t0 + f;
-            gf_shape_mid(sm, f, sm.f0fr[f], sm.voiced[f] != 0, nd.envF[(size_t)t * GF_ENVS_LD + 256],
+            gf_shape_mid(sm, f, sm.f0fr[f], sm.voiced[f] != 0, uv_on, nd.envF[(size_t)t * GF_ENVS_LD + 256],
                          nd.envN[(size_t)t * GF_ENVS_LD + 256], ps.phi[(size_t)256 * T + t], tw1024, local_max);
         }
         __syncthreads();
@@ -293,10 +308,11 @@ gf_frame_kernel(const int4 *__restrict__ work, const GfPassDev *__restrict__ pas
         }
         __syncthreads();
         // ---- 5. inverse FFTs (stream-major: transform q = s * GF_RND + f) ----
+        const int n_streams = uv_on ? 3 : 2;
         if (nf == GF_RND) {
-            gf_cta_fft512<true>(&sm.z[0][0][0], 3 * GF_RND, sm.tw512);
+            gf_cta_fft512<true>(&sm.z[0][0][0], n_streams * GF_RND, sm.tw512);
         } else {
-            for (int s = 0; s < 3; ++s) gf_cta_fft512<true>(&sm.z[s][0][0], nf, sm.tw512);
+            for (int s = 0; s < n_streams; ++s) gf_cta_fft512<true>(&sm.z[s][0][0], nf, sm.tw512);
         }
         // ---- 6. overlap-add + emit: thread `tid` owns column tid of every hop block ----
         {
@@ -304,16 +320,16 @@ gf_frame_kernel(const int4 *__restrict__ work, const GfPassDev *__restrict__ pas
             const bool last = (t0 + nf - 1 == T - 1);
             if (nf == GF_RND) {
 #pragma unroll
-                for (int s = 0; s < 3; ++s) gf_ola_round<GF_RND>(sm.carry[s], &sm.z[s][0][0], win, t0, T, n, outs[s], b0, nb, last);
+                for (int s = 0; s < 3; ++s) gf_ola_round<GF_RND>(sm.carry[s], &sm.z[s][0][0], win, t0, T, n, outs[s], b0, nb, last, s == 2 && !uv_on);
             } else if (nf == 3) {
 #pragma unroll
-                for (int s = 0; s < 3; ++s) gf_ola_round<3>(sm.carry[s], &sm.z[s][0][0], win, t0, T, n, outs[s], b0, nb, last);
+                for (int s = 0; s < 3; ++s) gf_ola_round<3>(sm.carry[s], &sm.z[s][0][0], win, t0, T, n, outs[s], b0, nb, last, s == 2 && !uv_on);
             } else if (nf == 2) {
 #pragma unroll
-                for (int s = 0; s < 3; ++s) gf_ola_round<2>(sm.carry[s], &sm.z[s][0][0], win, t0, T, n, outs[s], b0, nb, last);
+                for (int s = 0; s < 3; ++s) gf_ola_round<2>(sm.carry[s], &sm.z[s][0][0], win, t0, T, n, outs[s], b0, nb, last, s == 2 && !uv_on);
             } else {
 #pragma unroll
-                for (int s = 0; s < 3; ++s) gf_ola_round<1>(sm.carry[s], &sm.z[s][0][0], win, t0, T, n, outs[s], b0, nb, last);
+                for (int s = 0; s < 3; ++s) gf_ola_round<1>(sm.carry[s], &sm.z[s][0][0], win, t0, T, n, outs[s], b0, nb, last, s == 2 && !uv_on);
             }
         }
         __syncthreads();

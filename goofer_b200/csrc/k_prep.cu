@@ -577,20 +577,25 @@ __global__ void __launch_bounds__(GF_F32_THREADS) gf_fir32_kernel(const GfFirJob
     for (int j = threadIdx.x; j < ntap8; j += blockDim.x) taps[j] = (j <= 2 * radius) ? (float)gf_gauss_tap(j, radius, jb.sigma, norm) : 0.0f;
     const float *in = (const float *)jb.in;
     const int span = 2 * radius + GF_F32_TILE + 16;
+    const float first = in[(size_t)gf_reflect(start - radius, n) * jb.in_stride];
+    bool same = true;
     for (int i = threadIdx.x; i < span; i += blockDim.x) {
         const int p = start + i - radius;
         float v = 0.0f;
         if (p < n + radius) {
             const int q = (p >= 0 && p < n) ? p : gf_reflect(p, n);
             v = in[(size_t)q * jb.in_stride];
+            same = same && (v == first);
         }
         row[i] = v;
     }
-    __syncthreads();
+    // a normalised kernel maps a constant stretch to that constant: exactly so in the reference's fp64
+    // (sum of taps = 1 within 1e-16, rounded to f32), within 1e-7 in f32 -- return the exact value
+    const int constant = __syncthreads_and(same);
     float out[GF_EPL];
     gf_fir_rt(row + radius, GF_EPL * threadIdx.x, taps, radius, out);
 #pragma unroll
-    for (int e = 0; e < GF_EPL; ++e) outb[GF_EPL * threadIdx.x + e] = out[e];
+    for (int e = 0; e < GF_EPL; ++e) outb[GF_EPL * threadIdx.x + e] = constant ? first : out[e];
     __syncthreads();
     float *dst = (float *)jb.out;
     const int cnt = min(GF_F32_TILE, n - start);
