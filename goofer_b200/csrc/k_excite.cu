@@ -43,7 +43,7 @@ __device__ __forceinline__ double gf_midi_at(const GfNotePlan &pl, const float *
     return __dadd_rn(__dmul_rn(slope, x - x0), y0);
 }
 
-__global__ void __launch_bounds__(256, 4)
+__global__ void __launch_bounds__(256)
 gf_f0_kernel(const GfNotePlan *__restrict__ plans, const GfNoteDev *__restrict__ notes, const GfPassDev *__restrict__ passes,
              const GfSourceDev *__restrict__ srcs, const float *__restrict__ bend_all, const double *__restrict__ normals)
 {
@@ -124,7 +124,7 @@ void gf_launch_f0(const GfNotePlan *plans, const GfNoteDev *notes, const GfPassD
                   const float *bend, const double *normals, int n_notes, int max_n, cudaStream_t st)
 {
     if (n_notes <= 0) return;
-    dim3 grid(min(192, (max_n + 255) / 256), n_notes);
+    dim3 grid(min(48, (max_n + 255) / 256), n_notes);
     gf_f0_kernel<<<grid, 256, 0, st>>>(plans, notes, passes, srcs, bend, normals);
 }
 
