@@ -269,16 +269,13 @@ __device__ __forceinline__ float gf_grid_interp(const float *row, double x, doub
         const double sr_ = ((double)row[512] - (double)row[511]) / (nyq - x1 + 1e-10);
         return (float)((double)row[512] + sr_ * (x - nyq));
     }
-    int j = (int)(x * inv_step);
-    if (j > 512) j = 512;
-    auto fq = [&](int i) { return i == 512 ? nyq : (double)i * step; };
-    while (j > 0 && fq(j) > x) --j;
-    while (j < 512 && fq(j + 1) <= x) ++j;
-    if (j >= 512) return row[512];
-    const double x0 = fq(j);
+    // piece-wise linear interpolation is continuous, so a bracket that is off by one at a grid point (x * inv_step
+    // rounds across an integer) yields the same value: no fix-up of j is needed, and t comes from the same product
+    const double u = x * inv_step;
+    int j = (int)u;
+    if (j > 511) j = 511;
     const double y0 = (double)row[j];
-    const double t = (x - x0) * inv_step;
-    return (float)fma((double)row[j + 1] - y0, t, y0);
+    return (float)fma((double)row[j + 1] - y0, u - (double)j, y0);
 }
 
 __global__ void __launch_bounds__(32 * GF_ENV_WARPS, 2)
@@ -306,6 +303,22 @@ gf_env_kernel(const int2 *__restrict__ work, const GfNotePlan *__restrict__ plan
         const double sigma = pl.es < 0.0 ? (1.0 + 6.0 * s) : (0.8 + 4.0 * s);
         es_radius = (int)(4.0 * sigma + 0.5);
     }
+    // the first source frame of this warp's output frame is requested before anything else: its latency hides
+    // behind the table loads and the barrier
+    const int t = wk.y * GF_FT + warp;
+    const bool live = t < pl.T_out;
+    const int te = live ? min(t, pl.T_env - 1) : 0;       // GOOFER.py:1115-1119 trim / edge-pad to the STFT grid
+    GfMix mix;
+    mix.n = 0;
+    float pre[GF_EPL];
+#pragma unroll
+    for (int e = 0; e < GF_EPL; ++e) pre[e] = 0.0f;
+    if (live) {
+        gf_env_mix(pl, te, mix);
+        const float *src0 = sc.envS + (size_t)gf_src_frame(pl, mix.f[0]) * GF_ENVS_LD;
+#pragma unroll
+        for (int e = 0; e < GF_EPL; ++e) { const int b = lane + 32 * e; if (b < GF_NBINS) pre[e] = src0[b]; }
+    }
     // per-note tables prepared by gf_tracks_kernel
     for (int b = threadIdx.x; b < GF_NBINS; b += blockDim.x) {
         sm.freq[b] = nd.env_aux[GF_AUX_FREQ + b];
@@ -314,9 +327,7 @@ gf_env_kernel(const int2 *__restrict__ work, const GfNotePlan *__restrict__ plan
     if (do_es && threadIdx.x < GF_MAX_ES_TAPS) sm.es_taps[threadIdx.x] = nd.env_aux[GF_AUX_TAPS + threadIdx.x];
     __syncthreads();
 
-    const int t = wk.y * GF_FT + warp;
-    if (t >= pl.T_out) return;
-    const int te = min(t, pl.T_env - 1);                  // GOOFER.py:1115-1119 trim / edge-pad to the STFT grid
+    if (!live) return;
     float *rA = sm.rows[warp][0] + GF_ROW_L, *rB = sm.rows[warp][1] + GF_ROW_L;
     // the FIR windows also touch cells outside [-radius, 512 + radius] (zero-padded taps, idle lanes): they
     // must hold finite values, 0 * NaN left over from an earlier kernel would poison the sums
@@ -325,15 +336,18 @@ gf_env_kernel(const int2 *__restrict__ work, const GfNotePlan *__restrict__ plan
     const int b0 = min(GF_EPL * lane, 510);               // lane 31 owns nothing: it shadows lane 30 (reads stay inside the row)
     const int nown = (lane == 31) ? 0 : min(GF_EPL, GF_NBINS - b0);   // bins this lane owns
 
-    GfMix mix;
-    gf_env_mix(pl, te, mix);
     float acc[GF_EPL];
 #pragma unroll
     for (int e = 0; e < GF_EPL; ++e) acc[e] = 0.0f;
     for (int m = 0; m < mix.n; ++m) {
         const float *src = sc.envS + (size_t)gf_src_frame(pl, mix.f[m]) * GF_ENVS_LD;
         float *cur = rA, *oth = rB;
-        for (int b = lane; b < GF_NBINS; b += 32) cur[b] = do_tilt ? src[b] * sm.tilt[b] : src[b];
+        if (m == 0) {
+#pragma unroll
+            for (int e = 0; e < GF_EPL; ++e) { const int b = lane + 32 * e; if (b < GF_NBINS) cur[b] = do_tilt ? pre[e] * sm.tilt[b] : pre[e]; }
+        } else {
+            for (int b = lane; b < GF_NBINS; b += 32) cur[b] = do_tilt ? src[b] * sm.tilt[b] : src[b];
+        }
         __syncwarp();
         if (do_es) {
             // SillySampler.py:518-551: blur (es<0) or unsharp mask (es>0) along frequency, then per-frame mean match
@@ -384,19 +398,31 @@ gf_env_kernel(const int2 *__restrict__ work, const GfNotePlan *__restrict__ plan
     }
     // ---- fst bells (SillySampler.py:808-832), f32 ----
     if (pl.any_fst) {
-        const float sig[4] = {100.0f, 200.0f, 350.0f, 500.0f};
-        for (int k = 0; k < 4; ++k) {
-            const double sk = pl.fst[k];
-            if (fabs(sk) < 1e-6) continue;
-            const float Fk = nd.trk_clean[(size_t)k * pl.T_env + te];
-            if (!isfinite(Fk) || !(Fk > 50.0f) || !((double)Fk < (double)sr * 0.5)) continue;
-            const float sv = (float)((1.0 + sk) - 1.0);
-            const float isg = 1.0f / sig[k];
+        float Fk[4], isg[4], sv[4];
 #pragma unroll
-            for (int e = 0; e < GF_EPL; ++e) {
-                const float d = (sm.freq[min(b0 + e, 512)] - Fk) * isg;
-                acc[e] *= fmaf(sv, __expf(-0.5f * (d * d)), 1.0f);
+        for (int k = 0; k < 4; ++k) {
+            const float sig = (k == 0) ? 100.0f : (k == 1) ? 200.0f : (k == 2) ? 350.0f : 500.0f;
+            const double sk = pl.fst[k];
+            float fk = 0.0f;
+            bool on = !(fabs(sk) < 1e-6);
+            if (on) {
+                fk = nd.trk_clean[(size_t)k * pl.T_env + te];
+                on = isfinite(fk) && (fk > 50.0f) && ((double)fk < (double)sr * 0.5);
             }
+            Fk[k] = fk;
+            isg[k] = 1.0f / sig;
+            sv[k] = on ? (float)((1.0 + sk) - 1.0) : 0.0f;      // an inactive formant multiplies by exactly 1
+        }
+#pragma unroll
+        for (int e = 0; e < GF_EPL; ++e) {
+            const float fb = sm.freq[min(b0 + e, 512)];
+            float gain = 1.0f;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const float d = (fb - Fk[k]) * isg[k];
+                gain *= fmaf(sv[k], __expf(-0.5f * (d * d)), 1.0f);
+            }
+            acc[e] *= gain;
         }
     }
     float *cur = rA, *oth = rB;
