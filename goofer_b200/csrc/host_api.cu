@@ -54,16 +54,22 @@ extern "C" int goofer_render_batch_host(const GooferBatch *b)
 
     // ---- device image of every input array (same element offsets as on the host) ----
     Bump sz{nullptr, 0, 0};
+    const void *small_dev = nullptr;
     auto carve = [&](Bump &bp, GooferBatch &db, std::vector<GooferSource> &ds) {
+        for (int s = 0; s < b->n_sources; ++s) ds[s] = b->sources[s];
+        // small arrays back to back, each padded to 256 bytes (Bump aligns every array to 256)
+        bool first = true;
         for (int s = 0; s < b->n_sources; ++s) {
             const GooferSource &g = b->sources[s];
-            GooferSource d = g;
-            if (g.knots_log_f16) d.knots_log_f16 = bp.arr<uint16_t>((size_t)g.K * g.T);
-            if (g.hz_knots) d.hz_knots = bp.arr<float>((size_t)g.K);
-            if (g.env_dense) d.env_dense = bp.arr<float>((size_t)GF_NBINS * g.T);
-            if (g.mask) d.mask = bp.arr<float>((size_t)g.N);
-            for (int k = 0; k < 4; ++k) if (g.formants[k]) d.formants[k] = bp.arr<double>((size_t)g.formant_len[k]);
-            ds[s] = d;
+            if (g.hz_knots) { ds[s].hz_knots = bp.arr<float>((size_t)g.K); if (first) { small_dev = ds[s].hz_knots; first = false; } }
+            for (int k = 0; k < 4; ++k)
+                if (g.formants[k]) { ds[s].formants[k] = bp.arr<double>((size_t)g.formant_len[k]); if (first) { small_dev = ds[s].formants[k]; first = false; } }
+        }
+        for (int s = 0; s < b->n_sources; ++s) {
+            const GooferSource &g = b->sources[s];
+            if (g.knots_log_f16) ds[s].knots_log_f16 = bp.arr<uint16_t>((size_t)g.K * g.T);
+            if (g.env_dense) ds[s].env_dense = bp.arr<float>((size_t)GF_NBINS * g.T);
+            if (g.mask) ds[s].mask = bp.arr<float>((size_t)g.N);
         }
         db.bend_cents = bp.arr<float>((size_t)b->bend_total);
         db.phi = bp.arr<float>((size_t)b->phi_total);
@@ -93,15 +99,35 @@ extern "C" int goofer_render_batch_host(const GooferBatch *b)
         g_stats.d2h_bytes += (int64_t)bytes;
         return GOOFER_OK;
     };
+    // The small per-source arrays (mel-knot frequencies, four formant tracks: a few KB each) are gathered in the
+    // pinned staging arena and go up as ONE copy -- hundreds of tiny cudaMemcpyAsync calls cost more host time
+    // than the transfer itself.  They were carved back to back (see `carve`), so one device range covers them.
+    {
+        size_t small_bytes = 0;
+        for (int s = 0; s < b->n_sources; ++s) {
+            const GooferSource &g = b->sources[s];
+            if (g.hz_knots) small_bytes += (sizeof(float) * (size_t)g.K + 255) & ~(size_t)255;
+            for (int k = 0; k < 4; ++k) if (g.formants[k]) small_bytes += (sizeof(double) * (size_t)g.formant_len[k] + 255) & ~(size_t)255;
+        }
+        if (small_bytes) {
+            char *stage = (char *)gf_pin_take(small_bytes);
+            if (!stage) { gf_set_error("cudaMallocHost failed for the source staging arena"); return GOOFER_ERR_CUDA; }
+            size_t off = 0;
+            for (int s = 0; s < b->n_sources; ++s) {
+                const GooferSource &g = b->sources[s];
+                if (g.hz_knots) { std::memcpy(stage + off, g.hz_knots, sizeof(float) * (size_t)g.K); off += (sizeof(float) * (size_t)g.K + 255) & ~(size_t)255; }
+                for (int k = 0; k < 4; ++k)
+                    if (g.formants[k]) { std::memcpy(stage + off, g.formants[k], sizeof(double) * (size_t)g.formant_len[k]); off += (sizeof(double) * (size_t)g.formant_len[k] + 255) & ~(size_t)255; }
+            }
+            if ((rc = h2d(small_dev, stage, small_bytes))) return rc;
+        }
+    }
     for (int s = 0; s < b->n_sources; ++s) {
         const GooferSource &g = b->sources[s];
         const GooferSource &d = ds[s];
         if (g.knots_log_f16 && (rc = h2d(d.knots_log_f16, g.knots_log_f16, sizeof(uint16_t) * (size_t)g.K * g.T))) return rc;
-        if (g.hz_knots && (rc = h2d(d.hz_knots, g.hz_knots, sizeof(float) * (size_t)g.K))) return rc;
         if (g.env_dense && (rc = h2d(d.env_dense, g.env_dense, sizeof(float) * (size_t)GF_NBINS * g.T))) return rc;
         if (g.mask && (rc = h2d(d.mask, g.mask, sizeof(float) * (size_t)g.N))) return rc;
-        for (int k = 0; k < 4; ++k)
-            if (g.formants[k] && (rc = h2d(d.formants[k], g.formants[k], sizeof(double) * (size_t)g.formant_len[k]))) return rc;
     }
     if ((rc = h2d(db.bend_cents, b->bend_cents, sizeof(float) * (size_t)b->bend_total))) return rc;
 
