@@ -430,15 +430,19 @@ static int gf_upload(Bump &bp, const std::vector<T> &v, T **dptr, cudaStream_t s
     return gf_meta_copy(*dptr, stage, bytes, st);
 }
 
-int gf_post_fx(const WaveHost &wh, const GfNotePlan *d_plans, const GfNoteDev *d_notes, const GfPassDev *d_passes,
+int gf_post_fx(const WaveHost &wh, int n0, int n1, const GfNotePlan *d_plans, const GfNoteDev *d_notes, const GfPassDev *d_passes,
                GfPassScal *d_scal, Bump &bp, int sr, int max_n, cudaStream_t st, int64_t *launches);
 int gf_growl(const WaveHost &wh, const GfNotePlan *d_plans, const GfNoteDev *d_notes, const GfPassDev *d_passes,
              GfPassScal *d_scal, Bump &bp, int max_n, cudaStream_t st, int64_t *launches);
-int gf_pitch_dyn(const WaveHost &wh, const GfNotePlan *d_plans, const GfNoteDev *d_notes, Bump &bp, int sr, int max_n,
-                 cudaStream_t st, int64_t *launches);
+int gf_pitch_dyn(const WaveHost &wh, int n0, int n1, const GfNotePlan *d_plans, const GfNoteDev *d_notes, Bump &bp, int sr,
+                 int max_n, cudaStream_t st, int64_t *launches);
+
+// A part = a run of consecutive notes of the batch whose noise phases arrive together (host entry point):
+// the frame kernel of the part waits for `phi_ready`, `done` is recorded after the part's mix kernel.
+struct GfPart { int note_end; cudaEvent_t phi_ready; cudaEvent_t done; };
 
 static int gf_render_wave(const GooferBatch *b, const std::vector<GfNotePlan> &all, int i0, int i1, const GfSourceDev *d_srcs,
-                          Bump bp /* by value: wave region restarts every wave */, cudaStream_t st, cudaEvent_t phi_ready)
+                          Bump bp /* by value: wave region restarts every wave */, cudaStream_t st, const GfPart *parts, int n_parts)
 {
     WaveHost wh;
     const int nn = i1 - i0;
@@ -536,26 +540,49 @@ static int gf_render_wave(const GooferBatch *b, const std::vector<GfNotePlan> &a
     gf_launch_pulse(d_passes, d_scal, (int)n_pass, max_n, st); ++L; GF_STEP("pulse");
     if ((rc = gf_growl(wh, d_plans, d_notes, d_passes, d_scal, bp, max_n, st, &L)) != GOOFER_OK) return rc;
     gf_launch_env(d_envw, (int)wh.env_work.size(), d_plans, d_notes, d_srcs, st); ++L; GF_STEP("env");
-    if (phi_ready) GF_CUDA(cudaStreamWaitEvent(st, phi_ready, 0));     // the first kernel that reads the noise phases
-    gf_launch_frame(d_framew, (int)wh.frame_work.size(), d_passes, d_scal, d_notes, d_plans, st); ++L; GF_STEP("frame");
-    gf_launch_peak(d_plans, d_notes, d_passes, d_scal, (int)n_pass, max_n, st); ++L; GF_STEP("peak");
-    if ((rc = gf_pitch_dyn(wh, d_plans, d_notes, bp, sr, max_n, st, &L)) != GOOFER_OK) return rc;
-    if ((rc = gf_post_fx(wh, d_plans, d_notes, d_passes, d_scal, bp, sr, max_n, st, &L)) != GOOFER_OK) return rc;
-    gf_launch_mix(d_plans, d_notes, d_passes, d_scal, nn, max_n, st); ++L; GF_STEP("mix");
+    // ---- phase-dependent tail, part by part: frame -> peak -> pd / post-FX -> mix ----
+    {
+        std::vector<int> first_work(nn + 1, 0), first_pass(nn + 1, 0);     // per note: first frame-work item / first pass
+        {
+            size_t w = 0, q = 0;
+            for (int i = 0; i < nn; ++i) {
+                first_work[i] = (int)w; first_pass[i] = (int)q;
+                while (w < wh.frame_work.size() && wh.passes[wh.frame_work[w].x].note == i) ++w;
+                q += wh.plans[i].n_passes;
+            }
+            first_work[nn] = (int)w; first_pass[nn] = (int)q;
+        }
+        const GfPart whole = {i1, nullptr, nullptr};
+        const GfPart *pp = n_parts > 0 ? parts : &whole;
+        const int np = n_parts > 0 ? n_parts : 1;
+        int prev_end = 0;
+        for (int k = 0; k < np; ++k) {
+            const int a = std::max(prev_end, i0) - i0, e = std::min(pp[k].note_end, i1) - i0;     // notes [a, e) of this wave
+            prev_end = pp[k].note_end;
+            if (e <= a) continue;
+            if (pp[k].phi_ready) GF_CUDA(cudaStreamWaitEvent(st, pp[k].phi_ready, 0));             // first kernel that reads the noise phases
+            gf_launch_frame(d_framew + first_work[a], first_work[e] - first_work[a], d_passes, d_scal, d_notes, d_plans, st); ++L; GF_STEP("frame");
+            gf_launch_peak(d_plans, d_notes, d_passes, d_scal, first_pass[a], first_pass[e] - first_pass[a], max_n, st); ++L; GF_STEP("peak");
+            if ((rc = gf_pitch_dyn(wh, a, e, d_plans, d_notes, bp, sr, max_n, st, &L)) != GOOFER_OK) return rc;
+            if ((rc = gf_post_fx(wh, a, e, d_plans, d_notes, d_passes, d_scal, bp, sr, max_n, st, &L)) != GOOFER_OK) return rc;
+            gf_launch_mix(d_plans, d_notes, d_passes, d_scal, a, e - a, max_n, st); ++L; GF_STEP("mix");
+            if (pp[k].done && pp[k].note_end <= i1) GF_CUDA(cudaEventRecord(pp[k].done, st));
+        }
+    }
     GF_CUDA(cudaGetLastError());
     ++g_stats.waves;
     return GOOFER_OK;
 }
 
-static int gf_render_batch_ex(const GooferBatch *b, void *workspace, size_t workspace_bytes, void *stream, cudaEvent_t phi_ready);
+static int gf_render_batch_ex(const GooferBatch *b, void *workspace, size_t workspace_bytes, void *stream, const GfPart *parts, int n_parts);
 
 extern "C" int goofer_render_batch(const GooferBatch *b, void *workspace, size_t workspace_bytes, void *stream)
 {
-    return gf_render_batch_ex(b, workspace, workspace_bytes, stream, nullptr);
+    return gf_render_batch_ex(b, workspace, workspace_bytes, stream, nullptr, 0);
 }
 
-// phi_ready (optional): event after which b->phi is valid; only the frame kernel waits for it
-static int gf_render_batch_ex(const GooferBatch *b, void *workspace, size_t workspace_bytes, void *stream, cudaEvent_t phi_ready)
+// parts (optional): see GfPart; only the frame kernels wait for the noise phases
+static int gf_render_batch_ex(const GooferBatch *b, void *workspace, size_t workspace_bytes, void *stream, const GfPart *parts, int n_parts)
 {
     int rc = gf_validate(b);
     if (rc != GOOFER_OK) return rc;
@@ -636,7 +663,7 @@ static int gf_render_batch_ex(const GooferBatch *b, void *workspace, size_t work
             return GOOFER_ERR_WORKSPACE;
         }
         Bump wave{(char *)workspace + bp.off, wave_cap, 0};
-        if ((rc = gf_render_wave(b, plans, i0, i1, d_srcs, wave, st, phi_ready)) != GOOFER_OK) return rc;
+        if ((rc = gf_render_wave(b, plans, i0, i1, d_srcs, wave, st, parts, n_parts)) != GOOFER_OK) return rc;
         // host-side work lists are reused by the next wave only after this one was enqueued; the
         // device regions are reused in stream order, so no extra synchronisation is needed
         i0 = i1;

@@ -34,9 +34,10 @@ extern "C" void goofer_host_release(void)
     g_hc = GfHostCache();
 }
 
-// Notes are rendered in a few large chunks.  Only the frame kernel reads the noise phases (2/3 of the input
-// bytes), so chunk c's phases stream in on st_in while its preparation kernels (tracks, f0, walk, pulse, env)
-// already run on st; chunk c's output leaves on st_out while chunk c+1 computes (PCIe is full duplex).
+// Only the frame kernel reads the noise phases (2/3 of the input bytes).  The batch is rendered ONCE: the
+// preparation kernels (tracks, f0, walk, pulse, env) of all notes run at full width while the phases stream in on
+// st_in; frame / peak / mix then go part by part (a part = a run of notes whose phases arrived together), and a
+// part's output leaves on st_out while the next part computes (PCIe is full duplex).
 extern "C" int goofer_render_batch_host(const GooferBatch *b)
 {
     int rc = gf_validate(b);
@@ -131,60 +132,69 @@ extern "C" int goofer_render_batch_host(const GooferBatch *b)
     }
     if ((rc = h2d(db.bend_cents, b->bend_cents, sizeof(float) * (size_t)b->bend_total))) return rc;
 
-    // ---- chunks ----
-    int chunk = b->n_notes >= 256 ? (b->n_notes + 1) / 2 : b->n_notes;
+    // ---- parts: runs of consecutive notes whose phases travel together ----
+    int chunk = b->n_notes >= 512 ? (b->n_notes + 3) / 4 : (b->n_notes >= 128 ? (b->n_notes + 1) / 2 : b->n_notes);
     {
         const char *e = getenv("GOOFER_HOST_CHUNK");
         if (e && atoi(e) > 0) chunk = atoi(e);
     }
     const int n_chunks = (b->n_notes + chunk - 1) / chunk;
-    const size_t want = goofer_workspace_bytes(&db, chunk);
+    const size_t want = goofer_workspace_bytes(&db, 0);
     if (want == 0) return GOOFER_ERR_NOTE;
     if ((rc = gf_hc_reserve(&g_hc.ws, &g_hc.ws_cap, want)) != GOOFER_OK) return rc;
-    while ((int)g_hc.ev.size() < 3 * n_chunks) {
+    while ((int)g_hc.ev.size() < 2 * n_chunks + 1) {
         cudaEvent_t e;
         GF_CUDA(cudaEventCreate(&e));
         g_hc.ev.push_back(e);
     }
-    int64_t launches = 0;
-    int waves = 0;
+    // element ranges of every part's noise and output inside the concatenated buffers
+    struct Range { int64_t plo, phi, nlo, nhi, olo, ohi; };
+    std::vector<Range> rg(n_chunks);
     for (int c = 0; c < n_chunks; ++c) {
         const int i0 = c * chunk, i1 = std::min(b->n_notes, i0 + chunk);
-        // element ranges of this chunk's noise and output inside the concatenated buffers
-        int64_t plo = INT64_MAX, phi_hi = 0, nlo = INT64_MAX, nhi = 0, olo = INT64_MAX, ohi = 0;
+        Range r = {INT64_MAX, 0, INT64_MAX, 0, INT64_MAX, 0};
         for (int i = i0; i < i1; ++i) {
             const GfNotePlan &p = plans[i];
             for (int k = 0; k < p.n_passes; ++k) {
                 const int64_t o = p.phi_off[p.pass_kind[k]];
                 if (o < 0) { gf_set_error("note %d: phi slot %d not supplied", i, p.pass_kind[k]); return GOOFER_ERR_INVALID; }
-                plo = std::min(plo, o); phi_hi = std::max(phi_hi, o + (int64_t)GF_NBINS * p.T_out);
+                r.plo = std::min(r.plo, o); r.phi = std::max(r.phi, o + (int64_t)GF_NBINS * p.T_out);
             }
             const int need[4] = {p.f0_jitter, p.vol_jitter, p.vol_jitter, p.sj > 0.0};
             for (int k = 0; k < 4; ++k)
                 if (need[k]) {
                     if (p.nrm_off[k] < 0) { gf_set_error("note %d: normal slot %d not supplied", i, k); return GOOFER_ERR_INVALID; }
-                    nlo = std::min(nlo, p.nrm_off[k]); nhi = std::max(nhi, p.nrm_off[k] + (int64_t)p.n_total);
+                    r.nlo = std::min(r.nlo, p.nrm_off[k]); r.nhi = std::max(r.nhi, p.nrm_off[k] + (int64_t)p.n_total);
                 }
-            olo = std::min(olo, p.out_off); ohi = std::max(ohi, p.out_off + (int64_t)p.n_total);
+            r.olo = std::min(r.olo, p.out_off); r.ohi = std::max(r.ohi, p.out_off + (int64_t)p.n_total);
         }
-        if (plo < 0 || phi_hi > b->phi_total || (nhi > 0 && (!b->normals || nlo < 0 || nhi > b->nrm_total)) || olo < 0 || ohi > b->out_total) {
-            gf_set_error("chunk %d: noise / output offsets outside their buffers", c);
+        if (r.plo < 0 || r.phi > b->phi_total || (r.nhi > 0 && (!b->normals || r.nlo < 0 || r.nhi > b->nrm_total)) || r.olo < 0 || r.ohi > b->out_total) {
+            gf_set_error("part %d: noise / output offsets outside their buffers", c);
             return GOOFER_ERR_INVALID;
         }
-        if (nhi > nlo && (rc = h2d(db.normals + nlo, b->normals + nlo, sizeof(double) * (size_t)(nhi - nlo)))) return rc;
-        GF_CUDA(cudaEventRecord(g_hc.ev[3 * c], st_in));             // sources, bends, this chunk's normals
-        if ((rc = h2d(db.phi + plo, b->phi + plo, sizeof(float) * (size_t)(phi_hi - plo)))) return rc;
-        GF_CUDA(cudaEventRecord(g_hc.ev[3 * c + 1], st_in));         // this chunk's phases
-        GF_CUDA(cudaStreamWaitEvent(st, g_hc.ev[3 * c], 0));
-        GooferBatch cb = db;
-        cb.notes = b->notes + i0;
-        cb.n_notes = i1 - i0;
-        if ((rc = gf_render_batch_ex(&cb, g_hc.ws, g_hc.ws_cap, st, g_hc.ev[3 * c + 1])) != GOOFER_OK) return rc;
-        launches += g_stats.kernel_launches;
-        waves += g_stats.waves;
-        GF_CUDA(cudaEventRecord(g_hc.ev[3 * c + 2], st));
-        GF_CUDA(cudaStreamWaitEvent(st_out, g_hc.ev[3 * c + 2], 0));
-        const size_t ob = sizeof(float) * (size_t)(ohi - olo);
+        rg[c] = r;
+    }
+    // uploads: normals of every part (the preparation kernels of the whole batch need them), then the phases part by part
+    for (int c = 0; c < n_chunks; ++c)
+        if (rg[c].nhi > rg[c].nlo && (rc = h2d(db.normals + rg[c].nlo, b->normals + rg[c].nlo, sizeof(double) * (size_t)(rg[c].nhi - rg[c].nlo)))) return rc;
+    GF_CUDA(cudaEventRecord(g_hc.ev[2 * n_chunks], st_in));          // sources, bends, normals
+    std::vector<GfPart> parts(n_chunks);
+    for (int c = 0; c < n_chunks; ++c) {
+        if ((rc = h2d(db.phi + rg[c].plo, b->phi + rg[c].plo, sizeof(float) * (size_t)(rg[c].phi - rg[c].plo)))) return rc;
+        GF_CUDA(cudaEventRecord(g_hc.ev[2 * c], st_in));             // this part's phases
+        parts[c].note_end = std::min(b->n_notes, (c + 1) * chunk);
+        parts[c].phi_ready = g_hc.ev[2 * c];
+        parts[c].done = g_hc.ev[2 * c + 1];
+    }
+    GF_CUDA(cudaStreamWaitEvent(st, g_hc.ev[2 * n_chunks], 0));
+    // one render of the whole batch: preparation kernels run once at full width; frame / peak / mix go part by part
+    if ((rc = gf_render_batch_ex(&db, g_hc.ws, g_hc.ws_cap, st, parts.data(), n_chunks)) != GOOFER_OK) return rc;
+    const int64_t launches = g_stats.kernel_launches;
+    const int waves = g_stats.waves;
+    for (int c = 0; c < n_chunks; ++c) {
+        GF_CUDA(cudaStreamWaitEvent(st_out, g_hc.ev[2 * c + 1], 0));
+        const int64_t olo = rg[c].olo;
+        const size_t ob = sizeof(float) * (size_t)(rg[c].ohi - olo);
         if ((rc = d2h(b->out + olo, db.out + olo, ob))) return rc;
         if (b->tap_harm && (rc = d2h(b->tap_harm + olo, db.tap_harm + olo, ob))) return rc;
         if (b->tap_uv && (rc = d2h(b->tap_uv + olo, db.tap_uv + olo, ob))) return rc;
@@ -196,11 +206,10 @@ extern "C" int goofer_render_batch_host(const GooferBatch *b)
     GF_CUDA(cudaStreamSynchronize(st));
     if (getenv("GOOFER_HOST_TRACE")) {
         for (int c = 0; c < n_chunks; ++c) {
-            float a = 0, bq = 0, cq = 0;
-            cudaEventElapsedTime(&a, g_hc.ev[0], g_hc.ev[3 * c]);
-            cudaEventElapsedTime(&bq, g_hc.ev[0], g_hc.ev[3 * c + 1]);
-            cudaEventElapsedTime(&cq, g_hc.ev[0], g_hc.ev[3 * c + 2]);
-            fprintf(stderr, "[host trace] chunk %d: small-in %.3f ms, phi-in %.3f ms, compute-done %.3f ms (since first event)\n", c, a, bq, cq);
+            float a = 0, bq = 0;
+            cudaEventElapsedTime(&a, g_hc.ev[2 * n_chunks], g_hc.ev[2 * c]);
+            cudaEventElapsedTime(&bq, g_hc.ev[2 * n_chunks], g_hc.ev[2 * c + 1]);
+            fprintf(stderr, "[host trace] part %d: phases in at %.3f ms, mixed at %.3f ms (since the small inputs arrived)\n", c, a, bq);
         }
     }
     return GOOFER_OK;

@@ -312,12 +312,12 @@ gf_pd_ref_kernel(const int *__restrict__ list, const GfNotePlan *__restrict__ pl
     }
 }
 
-int gf_pitch_dyn(const WaveHost &wh, const GfNotePlan *d_plans, const GfNoteDev *d_notes, Bump &bp, int sr, int max_n,
-                 cudaStream_t st, int64_t *launches)
+int gf_pitch_dyn(const WaveHost &wh, int n0, int n1, const GfNotePlan *d_plans, const GfNoteDev *d_notes, Bump &bp, int sr,
+                 int max_n, cudaStream_t st, int64_t *launches)
 {
     std::vector<int> list;
     std::vector<GfFirJob> jobs;
-    for (size_t i = 0; i < wh.plans.size(); ++i) {
+    for (size_t i = (size_t)n0; i < (size_t)n1; ++i) {
         const GfNotePlan &p = wh.plans[i];
         if (p.pd == 0.0) continue;
         list.push_back((int)i);
@@ -458,13 +458,13 @@ static GfOnepoleJob gf_job(const float *x, const float *f0, float *y, float *alp
     return j;
 }
 
-int gf_post_fx(const WaveHost &wh, const GfNotePlan *d_plans, const GfNoteDev *d_notes, const GfPassDev *d_passes,
+int gf_post_fx(const WaveHost &wh, int n0, int n1, const GfNotePlan *d_plans, const GfNoteDev *d_notes, const GfPassDev *d_passes,
                GfPassScal *d_scal, Bump &bp, int sr, int max_n, cudaStream_t st, int64_t *launches)
 {
     (void)max_n;
     std::vector<int> list;
     std::vector<GfOnepoleJob> jA, jB, jC;
-    for (size_t i = 0; i < wh.plans.size(); ++i) {
+    for (size_t i = (size_t)n0; i < (size_t)n1; ++i) {
         const GfNotePlan &p = wh.plans[i];
         const GfNoteDev &nd = wh.notes[i];
         if (!nd.fx[0]) continue;

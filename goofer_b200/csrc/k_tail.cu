@@ -38,9 +38,9 @@ __device__ __forceinline__ GfStreams gf_pass_streams(const GfNotePlan &pl, const
 
 __global__ void __launch_bounds__(256)
 gf_peak_kernel(const GfNotePlan *__restrict__ plans, const GfNoteDev *__restrict__ notes, const GfPassDev *__restrict__ passes,
-               GfPassScal *scal)
+               GfPassScal *scal, int pass0)
 {
-    const int pi = blockIdx.y;
+    const int pi = pass0 + blockIdx.y;
     const GfPassDev ps = passes[pi];
     const GfNotePlan &pl = plans[ps.note];
     const GfNoteDev nd = notes[ps.note];
@@ -54,12 +54,12 @@ gf_peak_kernel(const GfNotePlan *__restrict__ plans, const GfNoteDev *__restrict
     if ((threadIdx.x & 31) == 0 && mx > 0.0f) gf_atomic_max_pos(&scal[pi].peak_bits, mx);
 }
 
-void gf_launch_peak(const GfNotePlan *plans, const GfNoteDev *notes, const GfPassDev *passes, GfPassScal *scal, int n_pass,
-                    int max_n, cudaStream_t st)
+void gf_launch_peak(const GfNotePlan *plans, const GfNoteDev *notes, const GfPassDev *passes, GfPassScal *scal, int pass0,
+                    int n_pass, int max_n, cudaStream_t st)
 {
     if (n_pass <= 0) return;
     dim3 grid(min(32, (max_n + 255) / 256), n_pass);
-    gf_peak_kernel<<<grid, 256, 0, st>>>(plans, notes, passes, scal);
+    gf_peak_kernel<<<grid, 256, 0, st>>>(plans, notes, passes, scal, pass0);
 }
 
 __device__ __forceinline__ float gf_pass_gain(const GfNotePlan &pl, const GfPassScal &sc)
@@ -74,10 +74,10 @@ __device__ __forceinline__ float gf_pass_gain(const GfNotePlan &pl, const GfPass
 // sequential filters); stage 2: mix.  Notes without filters go straight through gf_mix_kernel.
 __global__ void __launch_bounds__(256)
 gf_mix_kernel(const GfNotePlan *__restrict__ plans, const GfNoteDev *__restrict__ notes, const GfPassDev *__restrict__ passes,
-              const GfPassScal *__restrict__ scal)
+              const GfPassScal *__restrict__ scal, int note0)
 {
-    const GfNotePlan &pl = plans[blockIdx.y];
-    const GfNoteDev nd = notes[blockIdx.y];
+    const GfNotePlan &pl = plans[note0 + blockIdx.y];
+    const GfNoteDev nd = notes[note0 + blockIdx.y];
     const int n = pl.n_total;
     const GfPassDev &p0 = passes[nd.pass0];
     const GfPassScal &s0 = scal[nd.pass0];
@@ -123,11 +123,11 @@ gf_mix_kernel(const GfNotePlan *__restrict__ plans, const GfNoteDev *__restrict_
 }
 
 void gf_launch_mix(const GfNotePlan *plans, const GfNoteDev *notes, const GfPassDev *passes, const GfPassScal *scal,
-                   int n_notes, int max_n, cudaStream_t st)
+                   int note0, int n_notes, int max_n, cudaStream_t st)
 {
     if (n_notes <= 0) return;
     dim3 grid(min(32, (max_n + 255) / 256), n_notes);
-    gf_mix_kernel<<<grid, 256, 0, st>>>(plans, notes, passes, scal);
+    gf_mix_kernel<<<grid, 256, 0, st>>>(plans, notes, passes, scal, note0);
 }
 
 // ------------------------------------------------------------------------------------------------
