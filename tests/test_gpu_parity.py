@@ -255,3 +255,39 @@ def test_error_paths(torch_cuda):
     db.desc.phi_total = 10
     rc = lib.goofer_render_batch(C.byref(db.desc), db.workspace.data_ptr(), db.workspace.numel(), None)
     assert rc == capi.ERR_INVALID
+
+
+# ---- BASELINE.json configs[3]: long-note sustain, 4 s source stretched to 16 s -----------------------------------
+@pytest.mark.parametrize("flags", ["L0", "L1", "L2R1", "L0R1"])
+def test_long_note_sustain(flags, torch_cuda):
+    """4 s source, length 16000 ms, consonant 150 ms: n_total = 705,600 + prefix, T_out ~ 2,757 frames."""
+    feat, sf = cases.source_for(3, 4.0)            # fricative-initial source
+    cli = ["G3", "100", flags, "30", "16000", "150", "200", "100", "0", "!120", "AA#200#AIAQAY#300#AQAIAA"]
+    ref = cases.oracle_render(feat, cli)
+    assert len(ref) > 700000
+    got = render_one(sf, cli)[0].astype(np.float64)
+    assert got.shape == ref.shape
+    assert np.max(np.abs(got - ref)) <= MAX_ABS
+    assert cases.lsd_db(ref, got) <= MAX_LSD
+
+
+def test_cli_drop_in(tmp_path, torch_cuda):
+    """python -m goofer_b200.cli with the reference's 13 arguments: reads <stem>_features.goofy, writes PCM16."""
+    import wave
+    from goofer_b200 import cli
+    src = bench_data.make_source(1)
+    stem = os.path.join(tmp_path, "voice_a")
+    with open(stem + "_features.goofy", "wb") as fh:
+        np.savez_compressed(fh, mode=np.array(["knots"]), knot_vals_log=src["knot_vals_log"], hz_knots=src["hz_knots"],
+                            n_bins=np.array([513]), n_fft=np.array([1024]), f0_interp=np.zeros(8, np.float16),
+                            voicing_mask=src["mask"].astype(np.float16), formants=np.array(src["formants"], dtype=object),
+                            sr=np.array([44100]), y_len=np.array([src["ylen"]]))
+    out = os.path.join(tmp_path, "out.wav")
+    argv = [stem + ".wav", out, "C4", "100", "g-10br20", "0", "1000", "0", "0", "100", "0", "!120", "AA"]
+    assert cli.main(argv) == 0
+    with wave.open(out, "rb") as w:
+        assert w.getframerate() == 44100 and w.getsampwidth() == 2 and w.getnframes() == 44100
+        pcm = np.frombuffer(w.readframes(44100), dtype="<i2")
+    assert np.max(np.abs(pcm)) >= 32000               # P absent: peak-normalised
+    assert cli.main(argv[:5]) == 1                      # fewer than 13 arguments: usage + exit code 1
+    assert cli.main([os.path.join(tmp_path, "missing.wav")] + argv[1:]) == 1

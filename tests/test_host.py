@@ -80,3 +80,9 @@ def test_bench_workloads_plan(lib):
     ab = b.assemble(host.SeededNoise())
     assert all(inf["n_total"] == 44100 and inf["t_out"] == 173 for inf in ab.infos)
     assert bench_data.algorithmic_bytes({"need_phi": [1, 0, 0, 0], "need_nrm": [0] * 4, "t_out": 173, "n_total": 44100}, 172, 44100) == 1063492
+
+
+def test_cli_argument_errors_without_gpu(tmp_path):
+    from goofer_b200 import cli
+    assert cli.main(["a.wav", "b.wav", "C4"]) == 1                       # TypeError path: usage text, exit code 1
+    assert cli.main([os.path.join(tmp_path, "nope.wav"), "b.wav", "C4", "100", "", "0", "1000", "0", "0", "100", "0", "!120", "AA"]) == 1
