@@ -43,6 +43,33 @@ __device__ __forceinline__ double gf_midi_at(const GfNotePlan &pl, const float *
     return __dadd_rn(__dmul_rn(slope, x - x0), y0);
 }
 
+// gf_midi_at with its operands passed by value (nothing is re-read from the plan record inside the sample loop)
+__device__ __forceinline__ double gf_midi_at_fast(const float *__restrict__ bend, int bend_len, double add, int t_cents,
+                                                  double tempo, int sr, int i)
+{
+    const double tadd = t_cents ? ((double)t_cents / 100.0) : 0.0;
+    auto semi = [&](int k) {
+        double s = (double)bend[k] / 100.0 + add;
+        if (t_cents) s = s + tadd;
+        return s;
+    };
+    const double dt = 60.0 / (tempo * 96.0);
+    const int last = bend_len - 1;
+    double x = (double)i / (double)sr;
+    const double xl = (double)last * dt;
+    x = fmin(fmax(x, 0.0), xl);
+    if (x >= xl) return semi(last);
+    int j = (int)(x / dt);
+    if (j > last - 1) j = last - 1;
+    while (j > 0 && (double)j * dt > x) --j;
+    while (j < last - 1 && (double)(j + 1) * dt <= x) ++j;
+    const double x0 = (double)j * dt, x1 = (double)(j + 1) * dt;
+    const double y0 = semi(j), y1 = semi(j + 1);
+    if (x0 == x) return y0;
+    const double slope = __ddiv_rn(y1 - y0, x1 - x0);
+    return __dadd_rn(__dmul_rn(slope, x - x0), y0);
+}
+
 __global__ void __launch_bounds__(256)
 gf_f0_kernel(const GfNotePlan *__restrict__ plans, const GfNoteDev *__restrict__ notes, const GfPassDev *__restrict__ passes,
              const GfSourceDev *__restrict__ srcs, const float *__restrict__ bend_all, const double *__restrict__ normals)
@@ -60,6 +87,41 @@ gf_f0_kernel(const GfNotePlan *__restrict__ plans, const GfNoteDev *__restrict__
     const double midi_flat = flat ? gf_midi_at(pl, bend, 0) : 0.0;
     const double hz_flat = flat ? 440.0 * exp2((midi_flat - 69.0) / 12.0) : 0.0;
     const int M = (n + 3) / 4;
+    // per-pass outputs, loaded once (they used to be re-read from the pass records for every sample)
+    const int npass = pl.n_passes;
+    float *pf0[GF_MAX_PASSES];
+    int pkind[GF_MAX_PASSES];
+#pragma unroll
+    for (int p = 0; p < GF_MAX_PASSES; ++p) {
+        pf0[p] = (p < npass) ? passes[nd.pass0 + p].f0 : nullptr;
+        pkind[p] = (p < npass) ? passes[nd.pass0 + p].kind : -1;
+    }
+    // ---- common case (c1 / c2 / c5 notes): one pass, no velocity stretch, fry, jitter or pitch dynamics ----
+    const bool simple = npass == 1 && !pl.vel_active && pl.fry_L <= 0 && !pl.f0_jitter && !nd.f0n && !nd.pd_in;
+    if (simple) {
+        float *__restrict__ out_f0 = pf0[0];
+        float *__restrict__ out_ms = nd.ms;
+        const float *__restrict__ vm = nd.vm;
+        const float *__restrict__ mshort = nd.ms_short;
+        unsigned char *__restrict__ ms_one = nd.ms_one;
+        const int sr_i = pl.sr;
+        for (int base = blockIdx.x * blockDim.x; base < n; base += gridDim.x * blockDim.x) {
+            const int i = base + threadIdx.x;
+            float msv = 1.0f;
+            if (i < n) { msv = gf_ms_at(mshort, M, i, n); out_ms[i] = msv; }
+            const int all_one = __syncthreads_and(msv == 1.0f);
+            if (threadIdx.x == 0) ms_one[base >> 8] = (unsigned char)all_one;
+            if (i >= n) continue;
+            const double m = (double)vm[i];
+            double hz = hz_flat;
+            if (!flat) {
+                const double midi = gf_midi_at_fast(bend, pl.bend_len, (double)pl.pitch_midi, pl.t_cents, pl.tempo, sr_i, i);
+                hz = 440.0 * exp2((midi - 69.0) / 12.0);
+            }
+            out_f0[i] = (float)(m * hz);
+        }
+        return;
+    }
     for (int base = blockIdx.x * blockDim.x; base < n; base += gridDim.x * blockDim.x) {
         const int i = base + threadIdx.x;
         // smooth_mask_ds (GOOFER.py:564-569) + per hop block: is the smoothed mask exactly 1 everywhere?  Where it
@@ -93,10 +155,11 @@ gf_f0_kernel(const GfNotePlan *__restrict__ plans, const GfNoteDev *__restrict__
             const double base = (double)pl.pitch_midi + ((double)pl.t_cents / 100.0);
             nd.pd_in[i] = (float)(midi - base);
         }
-        for (int p = 0; p < pl.n_passes; ++p) {
-            const GfPassDev &ps = passes[nd.pass0 + p];
+#pragma unroll
+        for (int p = 0; p < GF_MAX_PASSES; ++p) {
+            if (p >= npass) break;
             float v;
-            switch (ps.kind) {
+            switch (pkind[p]) {
             case GF_PASS_MAIN: {
                 v = (float)f0;
                 if (pl.f0_jitter) {
@@ -115,7 +178,7 @@ gf_f0_kernel(const GfNotePlan *__restrict__ plans, const GfNoteDev *__restrict__
             }
             default: v = (float)f0; break;
             }
-            ps.f0[i] = v;
+            pf0[p][i] = v;
         }
     }
 }
@@ -322,7 +385,8 @@ void gf_launch_walk(const GfPassDev *passes, GfPassScal *scal, int n_pass, int s
 // evaluated in f32 from (j, T0) alone: T cancels in ti / Tp and (ti - Tp) / (Tc - Tp) up to the 1e-12
 // guards (< 1e-8 relative, like the reference's own 5-slot table cache, which reuses one T per T0).
 // ------------------------------------------------------------------------------------------------
-#define GF_PULSE_CAP 128
+#define GF_PULSE_CAP 512
+#define GF_PULSE_CHUNKS 16            // CTAs per (note, pass): each owns a contiguous run of 256-sample tiles
 __device__ __forceinline__ float gf_lf_value_f32(int d, int jp, int jc, float r_rise, float r_fall, float inv_max)
 {
     float v = 0.0f;
@@ -345,57 +409,63 @@ gf_pulse_kernel(const GfPassDev *__restrict__ passes, const GfPassScal *__restri
     const int count = scal[blockIdx.y].n_onsets;
     const int max_T0 = scal[blockIdx.y].max_T0;
     const int4 *__restrict__ on = ps.onsets;
-    for (int s0 = blockIdx.x * 256; s0 < n; s0 += gridDim.x * 256) {
-        if (threadIdx.x < 2) {
-            // [0]: onsets with x <= s0 - max_T0 can no longer reach the tile; [1]: onsets with x <= s0 + 255
-            const int key = threadIdx.x == 0 ? s0 - max_T0 : s0 + 255;
-            int lo = 0, hi = count;
-            while (lo < hi) { const int mid = (lo + hi) >> 1; if (on[mid].x <= key) lo = mid + 1; else hi = mid; }
-            s_rng[threadIdx.x] = lo;
+    const int tiles = (n + 255) / 256;
+    const int per = (tiles + gridDim.x - 1) / gridDim.x;
+    const int c_begin = blockIdx.x * per * 256, c_end = min(n, c_begin + per * 256);
+    if (c_begin >= n) return;
+    // onsets that can reach this CTA's run of samples: two binary searches in global memory, once
+    if (threadIdx.x < 2) {
+        const int key = threadIdx.x == 0 ? c_begin - max_T0 : c_end - 1;
+        int lo = 0, hi = count;
+        while (lo < hi) { const int mid = (lo + hi) >> 1; if (on[mid].x <= key) lo = mid + 1; else hi = mid; }
+        s_rng[threadIdx.x] = lo;
+    }
+    __syncthreads();
+    const int e0 = s_rng[0], e1 = s_rng[1];
+    const int ne = e1 - e0;
+    const bool staged = ne <= GF_PULSE_CAP;
+    if (staged) {
+        for (int q = threadIdx.x; q < ne; q += blockDim.x) {
+            const int4 o = on[e0 + q];
+            s_x[q] = o.x; s_T0[q] = o.y; s_j[q] = o.z;
+            s_r1[q] = 1.57079637f / (0.02f * (float)o.y);
+            s_r2[q] = 1.0f / (0.784f * (float)o.y);
+            const float mxv = __int_as_float(o.w);
+            s_im[q] = mxv > 0.0f ? 1.0f / mxv : 1.0f;
         }
-        __syncthreads();
-        const int e0 = s_rng[0], e1 = s_rng[1];
-        const int ne = e1 - e0;
-        const bool staged = ne <= GF_PULSE_CAP;
-        if (staged) {
-            for (int q = threadIdx.x; q < ne; q += blockDim.x) {
-                const int4 o = on[e0 + q];
-                s_x[q] = o.x; s_T0[q] = o.y; s_j[q] = o.z;
-                s_r1[q] = 1.57079637f / (0.02f * (float)o.y);
-                s_r2[q] = 1.0f / (0.784f * (float)o.y);
-                const float mxv = __int_as_float(o.w);
-                s_im[q] = mxv > 0.0f ? 1.0f / mxv : 1.0f;
-            }
-        }
-        __syncthreads();
+    }
+    __syncthreads();
+    int q_lo = 0, q_hi = 0;                   // staged onsets [q_lo, q_hi) can reach the current tile (both only move right)
+    for (int s0 = c_begin; s0 < c_end; s0 += 256) {
         const int i = s0 + threadIdx.x;
-        if (i < n) {
-            float acc = 0.0f;
-            if (staged) {
-                for (int q = 0; q < ne; ++q) {
+        float acc = 0.0f;
+        if (staged) {
+            while (q_hi < ne && s_x[q_hi] <= s0 + 255) ++q_hi;
+            while (q_lo < q_hi && s_x[q_lo] + max_T0 <= s0) ++q_lo;
+            if (i < n) {
+                for (int q = q_lo; q < q_hi; ++q) {
                     const int d = i - s_x[q];
                     if (d >= 0 && d < s_T0[q]) acc += gf_lf_value_f32(d, s_j[q] & 0xffff, s_j[q] >> 16, s_r1[q], s_r2[q], s_im[q]);
                 }
-            } else {
-                for (int e = e0; e < e1; ++e) {
-                    const int4 o = on[e];
-                    const int d = i - o.x;
-                    if (d >= 0 && d < o.y) {
-                        const float mxv = __int_as_float(o.w);
-                        acc += gf_lf_value_f32(d, o.z & 0xffff, o.z >> 16, 1.57079637f / (0.02f * (float)o.y),
-                                               1.0f / (0.784f * (float)o.y), mxv > 0.0f ? 1.0f / mxv : 1.0f);
-                    }
+            }
+        } else if (i < n) {
+            for (int e = e0; e < e1; ++e) {
+                const int4 o = on[e];
+                const int d = i - o.x;
+                if (d >= 0 && d < o.y) {
+                    const float mxv = __int_as_float(o.w);
+                    acc += gf_lf_value_f32(d, o.z & 0xffff, o.z >> 16, 1.57079637f / (0.02f * (float)o.y),
+                                           1.0f / (0.784f * (float)o.y), mxv > 0.0f ? 1.0f / mxv : 1.0f);
                 }
             }
-            ps.pulse[i] = acc;
         }
-        __syncthreads();
+        if (i < n) ps.pulse[i] = acc;
     }
 }
 
 void gf_launch_pulse(const GfPassDev *passes, const GfPassScal *scal, int n_pass, int max_n, cudaStream_t st)
 {
     if (n_pass <= 0) return;
-    dim3 grid(min(256, (max_n + 255) / 256), n_pass);
+    dim3 grid(min(GF_PULSE_CHUNKS, (max_n + 255) / 256), n_pass);
     gf_pulse_kernel<<<grid, 256, 0, st>>>(passes, scal);
 }
