@@ -45,6 +45,33 @@ __device__ __forceinline__ void gf_cta_fft512(float2 *bufs, int n_xf, const floa
     }
 }
 
+// NQ transforms per 64-thread lane (n_xf = NQ * lanes), all advanced through a pass before the CTA synchronises:
+// six barriers for the whole batch instead of six per group of `lanes` transforms
+template <bool INV, int NQ>
+__device__ __forceinline__ void gf_cta_fft512_multi(float2 *bufs, const float2 *tw512)
+{
+    const int lane = threadIdx.x >> 6, j = threadIdx.x & 63, n_lanes = blockDim.x >> 6;
+    float2 v[NQ][8];
+#pragma unroll
+    for (int q = 0; q < NQ; ++q) gf_fft_pass_load<INV, 1>(j, bufs + (size_t)(lane + q * n_lanes) * GF_FFT_BUF, tw512, v[q]);
+    __syncthreads();
+#pragma unroll
+    for (int q = 0; q < NQ; ++q) gf_fft_pass_store<1>(j, bufs + (size_t)(lane + q * n_lanes) * GF_FFT_BUF, v[q]);
+    __syncthreads();
+#pragma unroll
+    for (int q = 0; q < NQ; ++q) gf_fft_pass_load<INV, 8>(j, bufs + (size_t)(lane + q * n_lanes) * GF_FFT_BUF, tw512, v[q]);
+    __syncthreads();
+#pragma unroll
+    for (int q = 0; q < NQ; ++q) gf_fft_pass_store<8>(j, bufs + (size_t)(lane + q * n_lanes) * GF_FFT_BUF, v[q]);
+    __syncthreads();
+#pragma unroll
+    for (int q = 0; q < NQ; ++q) gf_fft_pass_load<INV, 64>(j, bufs + (size_t)(lane + q * n_lanes) * GF_FFT_BUF, tw512, v[q]);
+    __syncthreads();
+#pragma unroll
+    for (int q = 0; q < NQ; ++q) gf_fft_pass_store<64>(j, bufs + (size_t)(lane + q * n_lanes) * GF_FFT_BUF, v[q]);
+    __syncthreads();
+}
+
 // frame `t` of the reflect-padded signal x (length n), sqrt-Hann windowed, packed as
 // z[m] = x[2m] + i x[2m+1] into a padded FFT buffer.  GOOFER.py:355-369
 template <typename LoadFn>

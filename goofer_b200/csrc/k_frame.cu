@@ -310,7 +310,8 @@ gf_frame_kernel(const int4 *__restrict__ work, const GfPassDev *__restrict__ pas
         // ---- 5. inverse FFTs (stream-major: transform q = s * GF_RND + f) ----
         const int n_streams = uv_on ? 3 : 2;
         if (nf == GF_RND) {
-            gf_cta_fft512<true>(&sm.z[0][0][0], n_streams * GF_RND, sm.tw512);
+            if (uv_on) gf_cta_fft512_multi<true, 3>(&sm.z[0][0][0], sm.tw512);
+            else gf_cta_fft512_multi<true, 2>(&sm.z[0][0][0], sm.tw512);
         } else {
             for (int s = 0; s < n_streams; ++s) gf_cta_fft512<true>(&sm.z[s][0][0], nf, sm.tw512);
         }
