@@ -82,6 +82,7 @@ EXPORTS = [
     "goofer_render_batch_host", "goofer_host_release", "goofer_last_stats", "goofer_stft_batch", "goofer_istft_batch",
     "goofer_pulse_work_bytes", "goofer_pulse_train_batch", "goofer_onepole_batch", "goofer_debug_plan",
     "goofer_profile", "goofer_profile_summary", "goofer_struct_size",
+    "goofer_analyse_work_bytes", "goofer_analyse_batch",
 ]
 
 
@@ -124,6 +125,10 @@ def load():
     L.goofer_onepole_batch.argtypes = [vp, vp, i32, i32, i32, dbl, i32, i32, vp, vp]
     L.goofer_debug_plan.restype = C.c_int
     L.goofer_debug_plan.argtypes = [C.POINTER(GooferBatch), i32, vp, sz]
+    L.goofer_analyse_work_bytes.restype = sz
+    L.goofer_analyse_work_bytes.argtypes = [i32, i32]
+    L.goofer_analyse_batch.restype = C.c_int
+    L.goofer_analyse_batch.argtypes = [vp, i32, i32, i32, vp, vp, vp, vp, vp]
     L.goofer_struct_size.restype = sz
     L.goofer_struct_size.argtypes = [C.c_int]
     for which, rec in enumerate((GooferSource, GooferNote, GooferNotePlanInfo, GooferBatch, GooferStats)):

@@ -8,3 +8,4 @@
 #include "api.cu"
 #include "k_fx.cu"
 #include "host_api.cu"
+#include "k_analyse.cu"

@@ -4,6 +4,7 @@
     istft(S, length)    gf.istft              GOOFER.py:392-413
     pulse_train(f0, sr) gf.pulse_train_numba  GOOFER.py:473-554
     onepole(...)        dynamic_butter_filter SillySampler.py:95-174
+    analyse_envelope(y) envelope half of gf.extract_features + gf.compress_env_to_knots  GOOFER.py:940-946, 97-147
 torch is used for device memory and the stream only.
 """
 from __future__ import annotations
@@ -77,3 +78,26 @@ def onepole(x, f0, sr: int, cutoff_factor: float, order: int = 4, btype: str = "
         capi.check(lib.goofer_onepole_batch(x2.data_ptr(), f2.data_ptr(), B, n, int(sr), float(cutoff_factor), int(order),
                                             0 if btype == "lowpass" else 1, y.data_ptr(), _stream(x2)))
     return y[0] if x.dim() == 1 else y
+
+
+def analyse_envelope(y, sr: int = 44100):
+    """y: (n,) or (B, n) float32 CUDA tensor of source waveforms -> list of knot packs
+    {"mode", "knot_vals_log" (K, T) float16, "hz_knots" (K,) float32, "n_bins", "n_fft", "sr"} -- what
+    gf.compress_env_to_knots returns and gf.save_features stores (numpy arrays on the host)."""
+    import numpy as np
+    import torch
+    lib = capi.load()
+    y2 = _as2d(y).contiguous().float()
+    B, n = y2.shape
+    T = 1 + n // HOP
+    knots = torch.empty((B, 192, T), dtype=torch.float16, device=y.device)
+    hz = torch.empty((B, 192), dtype=torch.float32, device=y.device)
+    K = torch.empty((B,), dtype=torch.int32, device=y.device)
+    work = torch.empty(int(lib.goofer_analyse_work_bytes(B, n)), dtype=torch.uint8, device=y.device)
+    with torch.cuda.device(y.device):
+        capi.check(lib.goofer_analyse_batch(y2.data_ptr(), B, n, int(sr), knots.data_ptr(), hz.data_ptr(), K.data_ptr(),
+                                            work.data_ptr(), _stream(y2)))
+    Kh = K.cpu().numpy()
+    knots_h, hz_h = knots.cpu().numpy(), hz.cpu().numpy()
+    return [{"mode": "knots", "knot_vals_log": np.ascontiguousarray(knots_h[b, :Kh[b]]), "hz_knots": np.ascontiguousarray(hz_h[b, :Kh[b]]),
+             "n_bins": N_BINS, "n_fft": N_FFT, "sr": int(sr)} for b in range(B)]

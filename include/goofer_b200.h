@@ -13,6 +13,8 @@
  *   goofer_stft_batch / goofer_istft_batch     replace GOOFER.py:355-370 / :392-413 (+ :372-390)
  *   goofer_pulse_train_batch                   replaces GOOFER.py:473-554
  *   goofer_onepole_batch                       replaces SillySampler.py:95-174
+ *   goofer_analyse_batch                       envelope half of gf.extract_features + gf.compress_env_to_knots
+ *                                              (GOOFER.py:940-946, 968, 97-147) -- the step before the render path
  *
  * Conventions: plain pointers and sizes only; every function returns 0 on success or a negative
  * GooferStatus; nothing throws; the library allocates no device memory (the caller passes a
@@ -185,6 +187,15 @@ int goofer_pulse_train_batch(const float *f0, int32_t n_sig, int32_t n, int32_t 
 /* dynamic_butter_filter (SillySampler.py:95-174): x, f0 (n_sig, n) f32; btype 0 lowpass / 1 highpass. */
 int goofer_onepole_batch(const float *x, const float *f0, int32_t n_sig, int32_t n, int32_t sr,
                          double cutoff_factor, int32_t order, int32_t btype, float *y_out, void *stream);
+
+/* ---- analysis front-end: the spectral-envelope half of gf.extract_features (GOOFER.py:940-946, 968) and
+ * compress_env_to_knots (GOOFER.py:97-147).  y (n_sig, n) f32 waveforms -> per signal the arrays gf.save_features
+ * stores: K_out[s] in {32, 48, .. 192}, hz_out (n_sig, 192) f32 (first K valid), knots_out (n_sig, 192, T) IEEE half
+ * log-envelope knots (first K rows valid), T = 1 + n // 256.  f0 / voicing / formants come from Praat in the
+ * reference and stay with the caller.  Device pointers; work: >= goofer_analyse_work_bytes(n_sig, n) bytes. */
+size_t goofer_analyse_work_bytes(int32_t n_sig, int32_t n);
+int goofer_analyse_batch(const float *y, int32_t n_sig, int32_t n, int32_t sr, uint16_t *knots_out, float *hz_out,
+                         int32_t *K_out, void *work, void *stream);
 
 #ifdef __cplusplus
 }

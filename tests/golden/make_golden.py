@@ -118,6 +118,19 @@ def stages():
     env = gf.decode_env_from_knots(pack)
     out["knots_log"], out["hz_knots"] = pack["knot_vals_log"], pack["hz_knots"]
     out["knots_env_cols"] = np.asarray(env, dtype=np.float32)[:, ::16]
+    # --- analysis front-end: the envelope half of extract_features + compress_env_to_knots (GOOFER.py:940-946, 97-147) ---
+    for tag, idx in (("an_a", 2), ("an_b", 3), ("an_silence", -1)):
+        yv = np.zeros(20000, dtype=np.float32) if idx < 0 else sources.make_source(idx, 1.0)[0].astype(np.float32)
+        S0 = gf.stft(yv, 1024, 256, win)
+        env_spec = gf.gaussian_filter1d(np.abs(S0) + 1e-8, sigma=2.0, axis=0)
+        packr = gf.compress_env_to_knots(env_spec, sr=44100, n_fft=1024, eps=1e-2, K_start=32, K_step=16, K_max=192)
+        out[f"{tag}_src"] = np.array([idx])
+        out[f"{tag}_K"] = np.array([packr["knot_vals_log"].shape[0]])
+        out[f"{tag}_hz"] = packr["hz_knots"]
+        out[f"{tag}_knots"] = packr["knot_vals_log"]
+        env_o, pack_o = dsp.analyse_envelope(yv, 44100)
+        assert pack_o["knot_vals_log"].shape == packr["knot_vals_log"].shape, "oracle chose a different K than the reference"
+        assert np.array_equal(pack_o["hz_knots"], packr["hz_knots"]) and np.array_equal(pack_o["knot_vals_log"], packr["knot_vals_log"])
     np.savez_compressed(os.path.join(HERE, "stages.npz"), **out)
     print("stages written")
 

@@ -291,3 +291,36 @@ def test_cli_drop_in(tmp_path, torch_cuda):
     assert np.max(np.abs(pcm)) >= 32000               # P absent: peak-normalised
     assert cli.main(argv[:5]) == 1                      # fewer than 13 arguments: usage + exit code 1
     assert cli.main([os.path.join(tmp_path, "missing.wav")] + argv[1:]) == 1
+
+
+def test_analysis_front_end_gpu(torch_cuda):
+    """goofer_analyse_batch against the reference's own stft + gaussian_filter1d + compress_env_to_knots output
+    (tests/golden/stages.npz) and against the oracle on a batch."""
+    from oracle import sources
+    torch = torch_cuda
+    g = np.load(os.path.join(GOLD, "stages.npz"))
+    ys = [sources.make_source(int(g[f"{t}_src"][0]), 1.0)[0].astype(np.float32) for t in ("an_a", "an_b")]
+    packs = ops.analyse_envelope(torch.from_numpy(np.stack(ys)).cuda(), 44100)
+    for tag, y, pack in zip(("an_a", "an_b"), ys, packs):
+        assert pack["knot_vals_log"].shape == g[f"{tag}_knots"].shape and pack["knot_vals_log"].dtype == np.float16
+        # numpy's float32 power (SIMD) is not correctly rounded: 10 ** x differs from powf by one ulp in ~20 % of the
+        # knots, which 700 * (10 ** x - 1) turns into <= 0.002 Hz; the knot bins (round(hz / 43.07)) are identical
+        assert np.max(np.abs(pack["hz_knots"] - g[f"{tag}_hz"])) <= 4e-3
+        a, r = pack["knot_vals_log"].astype(np.float32), g[f"{tag}_knots"].astype(np.float32)
+        assert np.max(np.abs(a - r)) <= 2e-3 * np.max(np.abs(r))                 # at most one f16 ulp apart
+        assert np.mean(pack["knot_vals_log"].view(np.uint16) == g[f"{tag}_knots"].view(np.uint16)) > 0.99
+        # decoded envelopes agree (the render path consumes exactly this)
+        env_a = dsp.decode_knots(pack)
+        env_r = dsp.decode_knots({"knot_vals_log": g[f"{tag}_knots"], "hz_knots": g[f"{tag}_hz"], "n_fft": 1024, "sr": 44100, "n_bins": 513})
+        assert np.max(np.abs(env_a - env_r) / env_r) <= 5e-3          # one f16 ulp of a log value near 5 is 0.4 %
+    sil = ops.analyse_envelope(torch.zeros(20000, device="cuda"), 44100)[0]
+    assert sil["knot_vals_log"].shape[0] == 32 == int(g["an_silence_K"][0])
+    assert np.array_equal(sil["knot_vals_log"].view(np.uint16), g["an_silence_knots"].view(np.uint16))
+    # ragged / short inputs
+    rng = np.random.default_rng(11)
+    for n in (300, 5000):
+        y = (0.2 * rng.standard_normal(n)).astype(np.float32)
+        p = ops.analyse_envelope(torch.from_numpy(y).cuda(), 44100)[0]
+        _, po = dsp.analyse_envelope(y, 44100)
+        assert p["knot_vals_log"].shape == po["knot_vals_log"].shape
+        assert np.max(np.abs(p["knot_vals_log"].astype(np.float32) - po["knot_vals_log"].astype(np.float32))) <= 2e-2

@@ -74,3 +74,18 @@ def test_onepole_gauss_knots(gold_stages):
     env = dsp.decode_knots({"knot_vals_log": g["knots_log"], "hz_knots": g["hz_knots"], "n_fft": 1024, "sr": 44100, "n_bins": 513})
     ref = g["knots_env_cols"]
     assert np.max(np.abs(env[:, ::16] - ref) / ref) <= 1e-5
+
+
+def test_analysis_front_end(gold_stages):
+    """Envelope half of gf.extract_features + gf.compress_env_to_knots (GOOFER.py:940-946, 97-147)."""
+    from oracle import sources
+    g = gold_stages
+    for tag in ("an_a", "an_b", "an_silence"):
+        idx = int(g[f"{tag}_src"][0])
+        y = np.zeros(20000, np.float32) if idx < 0 else sources.make_source(idx, 1.0)[0].astype(np.float32)
+        env, pack = dsp.analyse_envelope(y, 44100)
+        assert pack["knot_vals_log"].shape[0] == int(g[f"{tag}_K"][0])
+        assert np.array_equal(pack["hz_knots"], g[f"{tag}_hz"])
+        d = np.abs(pack["knot_vals_log"].astype(np.float32) - g[f"{tag}_knots"].astype(np.float32))
+        assert np.max(d) <= 2e-3 * np.max(np.abs(g[f"{tag}_knots"].astype(np.float32)))     # one f16 ulp
+    assert int(g["an_silence_K"][0]) == 32
