@@ -237,21 +237,22 @@ __device__ __forceinline__ void gf_row_halo(float *row /* -> bin 0 */, int lane,
 }
 
 // sliding-window FIR with runtime radius: out[e] = sum_j taps[j] * row[b0 + e + j - radius], taps zero-padded to x8
-__device__ __forceinline__ void gf_fir_rt(const float *row, int b0, const float *taps, int radius, float *out)
+template <typename T>
+__device__ __forceinline__ void gf_fir_rt(const T *row, int b0, const T *taps, int radius, T *out)
 {
 #pragma unroll
-    for (int e = 0; e < GF_EPL; ++e) out[e] = 0.0f;
+    for (int e = 0; e < GF_EPL; ++e) out[e] = (T)0;
     const int ntap = 2 * radius + 1;
     for (int j0 = 0; j0 < ntap; j0 += 8) {
-        float win[GF_EPL + 7];
-        const float *p = row + b0 + j0 - radius;
+        T win[GF_EPL + 7];
+        const T *p = row + b0 + j0 - radius;
 #pragma unroll
         for (int q = 0; q < GF_EPL + 7; ++q) win[q] = p[q];
 #pragma unroll
         for (int jj = 0; jj < 8; ++jj) {
-            const float w = taps[j0 + jj];
+            const T w = taps[j0 + jj];
 #pragma unroll
-            for (int e = 0; e < GF_EPL; ++e) out[e] = fmaf(w, win[e + jj], out[e]);
+            for (int e = 0; e < GF_EPL; ++e) out[e] = fma(w, win[e + jj], out[e]);
         }
     }
 }
@@ -353,7 +354,7 @@ gf_env_kernel(const int2 *__restrict__ work, const GfNotePlan *__restrict__ plan
             // SillySampler.py:518-551: blur (es<0) or unsharp mask (es>0) along frequency, then per-frame mean match
             gf_row_halo(cur, lane, es_radius);
             float mod[GF_EPL];
-            gf_fir_rt(cur, b0, sm.es_taps, es_radius, mod);
+            gf_fir_rt<float>(cur, b0, sm.es_taps, es_radius, mod);
             const float s5 = (float)(5.0 * fabs(pl.es));
             float sum0 = 0.0f, sum1 = 0.0f;
 #pragma unroll
@@ -572,7 +573,9 @@ void gf_launch_mask(const GfNotePlan *plans, const GfNoteDev *notes, const GfSou
 
 __device__ __forceinline__ bool gf_fir_is_f32(const GfFirJob &jb)
 {
-    return !jb.in_f64 && !jb.out_f64 && !jb.maxabs && !jb.in_cast_f32;
+    // f32 input without a max-abs reduction: f32 taps / accumulation (the output may still be stored as fp64: the
+    // pitch-dynamics deviation curve, whose 3,529-tap smoothing only feeds a clipped gain in dB)
+    return !jb.in_f64 && !jb.maxabs && !jb.in_cast_f32;
 }
 
 // f32 -> f32 jobs (voicing-mask smoothing: sigma 25 on the decimated mask, sigma 20, sigma 441): the same
@@ -619,48 +622,65 @@ __global__ void __launch_bounds__(GF_F32_THREADS) gf_fir32_kernel(const GfFirJob
     // (sum of taps = 1 within 1e-16, rounded to f32), within 1e-7 in f32 -- return the exact value
     const int constant = __syncthreads_and(same);
     float out[GF_EPL];
-    gf_fir_rt(row + radius, GF_EPL * threadIdx.x, taps, radius, out);
+    gf_fir_rt<float>(row + radius, GF_EPL * threadIdx.x, taps, radius, out);
 #pragma unroll
     for (int e = 0; e < GF_EPL; ++e) outb[GF_EPL * threadIdx.x + e] = constant ? first : out[e];
     __syncthreads();
-    float *dst = (float *)jb.out;
     const int cnt = min(GF_F32_TILE, n - start);
-    for (int i = threadIdx.x; i < cnt; i += blockDim.x) dst[start + i] = outb[i];
+    if (jb.out_f64) {
+        double *dst = (double *)jb.out;
+        for (int i = threadIdx.x; i < cnt; i += blockDim.x) dst[start + i] = (double)outb[i];
+    } else {
+        float *dst = (float *)jb.out;
+        for (int i = threadIdx.x; i < cnt; i += blockDim.x) dst[start + i] = outb[i];
+    }
 }
 
-__global__ void __launch_bounds__(256) gf_fir_kernel(const GfFirJob *__restrict__ jobs)
+// fp64 jobs (sh / sr jitter curves: the result scales f0, so the taps and the accumulation stay fp64): the same
+// register-tiled sliding window, 17 outputs per thread
+__global__ void __launch_bounds__(GF_F32_THREADS) gf_fir_kernel(const GfFirJob *__restrict__ jobs)
 {
     extern __shared__ double fsm[];
+    __shared__ double red[GF_F32_THREADS / 32];
     const GfFirJob jb = jobs[blockIdx.y];
     if (gf_fir_is_f32(jb)) return;                // handled by gf_fir32_kernel
     const int n = jb.n;
-    const int start = blockIdx.x * GF_FIR_TILE;
+    const int start = blockIdx.x * GF_F32_TILE;
     if (start >= n) return;
     const int radius = (int)(4.0 * jb.sigma + 0.5);
-    double *taps = fsm;                           // 2 r + 1
-    double *tile = fsm + (2 * radius + 1);        // GF_FIR_TILE + 2 r
-    __shared__ double norm_s;
-    if (threadIdx.x == 0) {
-        double norm = 0.0;
-        for (int j = 0; j <= 2 * radius; ++j) { const double t = (double)(j - radius) / jb.sigma; norm += exp(-0.5 * t * t); }
-        norm_s = norm;
+    const int ntap8 = ((2 * radius + 1 + 7) & ~7) + 8;
+    double *taps = fsm;                                   // ntap8
+    double *row = taps + ntap8;                           // radius + tile + radius + 16
+    double part = 0.0;
+    for (int j = threadIdx.x; j <= 2 * radius; j += blockDim.x) { const double t = (double)(j - radius) / jb.sigma; part += exp(-0.5 * t * t); }
+    part = gf_warp_sum(part);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = part;
+    __syncthreads();
+    double norm = 0.0;
+    for (int w = 0; w < GF_F32_THREADS / 32; ++w) norm += red[w];
+    for (int j = threadIdx.x; j < ntap8; j += blockDim.x) taps[j] = (j <= 2 * radius) ? gf_gauss_tap(j, radius, jb.sigma, norm) : 0.0;
+    const int span = 2 * radius + GF_F32_TILE + 16;
+    for (int i = threadIdx.x; i < span; i += blockDim.x) {
+        const int p = start + i - radius;
+        double v = 0.0;
+        if (p < n + radius) {
+            const int q = (p >= 0 && p < n) ? p : gf_reflect(p, n);
+            v = jb.in_f64 ? ((const double *)jb.in)[(size_t)q * jb.in_stride] : (double)((const float *)jb.in)[(size_t)q * jb.in_stride];
+            if (jb.in_cast_f32) v = (double)(float)v;
+        }
+        row[i] = v;
     }
     __syncthreads();
-    for (int j = threadIdx.x; j <= 2 * radius; j += blockDim.x) taps[j] = gf_gauss_tap(j, radius, jb.sigma, norm_s);
-    const int cnt = min(GF_FIR_TILE, n - start);
-    for (int i = threadIdx.x; i < cnt + 2 * radius; i += blockDim.x) {
-        const int q = gf_reflect(start + i - radius, n);
-        double v = jb.in_f64 ? ((const double *)jb.in)[(size_t)q * jb.in_stride] : (double)((const float *)jb.in)[(size_t)q * jb.in_stride];
-        if (jb.in_cast_f32) v = (double)(float)v;
-        tile[i] = v;
-    }
-    __syncthreads();
+    double out[GF_EPL];
+    gf_fir_rt<double>(row + radius, GF_EPL * threadIdx.x, taps, radius, out);
     double mx = 0.0;
-    for (int i = threadIdx.x; i < cnt; i += blockDim.x) {
-        double a = 0.0;
-        for (int j = 0; j <= 2 * radius; ++j) a += taps[j] * tile[i + j];
-        if (jb.out_f64) ((double *)jb.out)[start + i] = a; else ((float *)jb.out)[start + i] = (float)a;
-        mx = fmax(mx, fabs(a) + 1e-6);
+#pragma unroll
+    for (int e = 0; e < GF_EPL; ++e) {
+        const int i = start + GF_EPL * threadIdx.x + e;
+        if (i < n) {
+            if (jb.out_f64) ((double *)jb.out)[i] = out[e]; else ((float *)jb.out)[i] = (float)out[e];
+            mx = fmax(mx, fabs(out[e]) + 1e-6);
+        }
     }
     if (jb.maxabs) {
         for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
@@ -673,14 +693,14 @@ void gf_launch_fir(const GfFirJob *jobs, int n_jobs, int max_n, double max_sigma
 {
     if (n_jobs <= 0 || max_n <= 0) return;
     const int radius = (int)(4.0 * max_sigma + 0.5);
-    const size_t smem = sizeof(double) * (size_t)(2 * radius + 1 + GF_FIR_TILE + 2 * radius);
+    const size_t smem = sizeof(double) * (size_t)((((2 * radius + 1 + 7) & ~7) + 8) + (2 * radius + GF_F32_TILE + 16));
     static size_t attr = 0;
     if (smem > attr) {
         cudaFuncSetAttribute(gf_fir_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         attr = smem;
     }
-    dim3 grid((max_n + GF_FIR_TILE - 1) / GF_FIR_TILE, n_jobs);
-    gf_fir_kernel<<<grid, 256, smem, st>>>(jobs);
+    dim3 grid((max_n + GF_F32_TILE - 1) / GF_F32_TILE, n_jobs);
+    gf_fir_kernel<<<grid, GF_F32_THREADS, smem, st>>>(jobs);
     // f32 jobs
     const size_t smem32 = sizeof(float) * (size_t)((((2 * radius + 1 + 7) & ~7) + 8) + (2 * radius + GF_F32_TILE + 16) + GF_F32_TILE);
     static size_t attr32 = 0;

@@ -137,6 +137,23 @@ void gf_launch_mix(const GfNotePlan *plans, const GfNoteDev *notes, const GfPass
 // (3) every lane replays its chunk from the right initial state.  f32 throughout like the reference.
 // ------------------------------------------------------------------------------------------------
 
+// walk a lane's chunk eight samples at a time: the sixteen loads of a batch are in flight together (the
+// recurrence itself is serial, the memory latency no longer is); the body may store to position i (y may alias x:
+// the batch was loaded before its first store)
+template <typename Body>
+__device__ __forceinline__ void gf_chunk8(int c0, int c1, const float *__restrict__ alpha, const float *src, Body body)
+{
+    int i = c0;
+    for (; i + 8 <= c1; i += 8) {
+        float a[8], x[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) { a[k] = alpha[i + k]; x[k] = src[i + k]; }
+#pragma unroll
+        for (int k = 0; k < 8; ++k) body(a[k], x[k], i + k);
+    }
+    for (; i < c1; ++i) body(alpha[i], src[i], i);
+}
+
 __global__ void __launch_bounds__(32) gf_onepole_kernel(const GfOnepoleJob *__restrict__ jobs)
 {
     const GfOnepoleJob jb = jobs[blockIdx.x];
@@ -183,21 +200,12 @@ __global__ void __launch_bounds__(32) gf_onepole_kernel(const GfOnepoleJob *__re
         // x[c0 - 1] is read before any lane stores this pass's output (y may alias the input)
         const float xp_first = (n > 0) ? ((c0 > 0 && c0 < n) ? src[c0 - 1] : src[0]) : 0.0f;
         if (!jb.highpass) {
-            for (int i = c0; i < c1; ++i) {
-                const float a = jb.alpha[i], x = src[i];
-                // y = y + a (x - y) = (1 - a) y + a x
-                A = (1.0f - a) * A;
-                B = fmaf(a, x - B, B);
-            }
+            // y = y + a (x - y) = (1 - a) y + a x
+            gf_chunk8(c0, c1, jb.alpha, src, [&](float a, float x, int) { A = (1.0f - a) * A; B = fmaf(a, x - B, B); });
         } else {
             float xp = xp_first;
-            for (int i = c0; i < c1; ++i) {
-                const float a = jb.alpha[i], x = src[i];
-                // y = a (y + x - xp)
-                A = a * A;
-                B = a * ((B - xp) + x);
-                xp = x;
-            }
+            // y = a (y + x - xp)
+            gf_chunk8(c0, c1, jb.alpha, src, [&](float a, float x, int) { A = a * A; B = a * ((B - xp) + x); xp = x; });
         }
         // (2) exclusive scan of the maps across lanes -> state entering each chunk
         float sA = A, sB = B;
@@ -208,20 +216,12 @@ __global__ void __launch_bounds__(32) gf_onepole_kernel(const GfOnepoleJob *__re
         float y = __shfl_up_sync(0xffffffffu, sB, 1);      // zero initial state => state = B of the prefix
         if (lane == 0) y = 0.0f;
         // (3) replay
+        float *dst = jb.y;
         if (!jb.highpass) {
-            for (int i = c0; i < c1; ++i) {
-                const float a = jb.alpha[i], x = src[i];
-                y = fmaf(a, x - y, y);
-                jb.y[i] = y;
-            }
+            gf_chunk8(c0, c1, jb.alpha, src, [&](float a, float x, int i) { y = fmaf(a, x - y, y); dst[i] = y; });
         } else {
             float xp = xp_first;
-            for (int i = c0; i < c1; ++i) {
-                const float a = jb.alpha[i], x = src[i];
-                y = a * ((y - xp) + x);
-                xp = x;
-                jb.y[i] = y;
-            }
+            gf_chunk8(c0, c1, jb.alpha, src, [&](float a, float x, int i) { y = a * ((y - xp) + x); xp = x; dst[i] = y; });
         }
         __syncwarp();
     }
