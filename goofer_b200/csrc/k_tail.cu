@@ -132,9 +132,9 @@ void gf_launch_mix(const GfNotePlan *plans, const GfNoteDev *notes, const GfPass
 
 // ------------------------------------------------------------------------------------------------
 // dynamic_butter_filter (SillySampler.py:95-174): `order` cascaded one-pole sections whose
-// coefficient follows f0 per sample.  One warp per signal; each lane owns a contiguous chunk.  Per
-// section: (1) every lane composes the affine map of its chunk, (2) the 32 maps are scanned,
-// (3) every lane replays its chunk from the right initial state.  f32 throughout like the reference.
+// coefficient follows f0 per sample.  One CTA per signal; each thread owns a contiguous chunk.  Per
+// section: (1) every thread composes the affine map of its chunk, (2) the 256 maps are scanned,
+// (3) every thread replays its chunk from the right initial state.  f32 throughout like the reference.
 // ------------------------------------------------------------------------------------------------
 
 // walk a lane's chunk eight samples at a time: the sixteen loads of a batch are in flight together (the
@@ -154,27 +154,29 @@ __device__ __forceinline__ void gf_chunk8(int c0, int c1, const float *__restric
     for (; i < c1; ++i) body(alpha[i], src[i], i);
 }
 
-__global__ void __launch_bounds__(32) gf_onepole_kernel(const GfOnepoleJob *__restrict__ jobs)
+#define GF_OP_THREADS 256
+__global__ void __launch_bounds__(GF_OP_THREADS) gf_onepole_kernel(const GfOnepoleJob *__restrict__ jobs)
 {
+    __shared__ float wA[GF_OP_THREADS / 32], wB[GF_OP_THREADS / 32];
     const GfOnepoleJob jb = jobs[blockIdx.x];
-    const int n = jb.n, lane = threadIdx.x;
+    const int n = jb.n, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (n <= 0) return;
     const double srd = (double)jb.sr;
     // ---- per-sample coefficient (SillySampler.py:128-152), f32 stores like the numba kernel ----
     bool any_pos_l = false;
-    for (int i = lane; i < n; i += 32) {
+    for (int i = tid; i < n; i += GF_OP_THREADS) {
         float f = jb.f0 ? jb.f0[i] : (float)jb.f0_const;
         if (jb.f0_floor > 0.0) f = fmaxf(f, (float)jb.f0_floor);
         any_pos_l |= (f > 0.0f);
     }
-    const bool any_pos = __any_sync(0xffffffffu, any_pos_l);
+    const bool any_pos = __syncthreads_or(any_pos_l) != 0;
     auto drv = [&](int i) {
         i = i < 0 ? 0 : (i > n - 1 ? n - 1 : i);
         float f = jb.f0 ? jb.f0[i] : (float)jb.f0_const;
         if (jb.f0_floor > 0.0) f = fmaxf(f, (float)jb.f0_floor);
         return f;
     };
-    for (int i = lane; i < n; i += 32) {
+    for (int i = tid; i < n; i += GF_OP_THREADS) {
         float f0s;
         if (jb.smooth_f0 && any_pos) {
             // np.convolve(pad(f0, 2, 'edge'), ones(5)/5, 'valid') in f32
@@ -190,15 +192,16 @@ __global__ void __launch_bounds__(32) gf_onepole_kernel(const GfOnepoleJob *__re
         const double w = (2.0 * 3.141592653589793) * (double)fc;
         jb.alpha[i] = (float)(jb.highpass ? srd / (w + srd) : w / (w + srd));
     }
-    __syncwarp();
-    const int chunk = (n + 31) / 32;
-    const int c0 = min(n, lane * chunk), c1 = min(n, c0 + chunk);
+    __syncthreads();
+    // thread t owns samples [c0, c1); per section: (1) compose the affine map of the chunk, (2) scan the 256 maps
+    // (warp shuffles + one shared-memory hop), (3) replay the chunk from the right initial state
+    const int chunk = (n + GF_OP_THREADS - 1) / GF_OP_THREADS;
+    const int c0 = min(n, tid * chunk), c1 = min(n, c0 + chunk);
     for (int pass = 0; pass < max(1, jb.order); ++pass) {
         const float *src = (pass == 0) ? jb.x : jb.y;
-        // (1) affine map of the chunk: y_end = A * y_start + B
         float A = 1.0f, B = 0.0f;
-        // x[c0 - 1] is read before any lane stores this pass's output (y may alias the input)
-        const float xp_first = (n > 0) ? ((c0 > 0 && c0 < n) ? src[c0 - 1] : src[0]) : 0.0f;
+        // x[c0 - 1] is read before any thread stores this section's output (y may alias the input): barrier below
+        const float xp_first = (c0 > 0 && c0 < n) ? src[c0 - 1] : src[0];
         if (!jb.highpass) {
             // y = y + a (x - y) = (1 - a) y + a x
             gf_chunk8(c0, c1, jb.alpha, src, [&](float a, float x, int) { A = (1.0f - a) * A; B = fmaf(a, x - B, B); });
@@ -207,15 +210,21 @@ __global__ void __launch_bounds__(32) gf_onepole_kernel(const GfOnepoleJob *__re
             // y = a (y + x - xp)
             gf_chunk8(c0, c1, jb.alpha, src, [&](float a, float x, int) { A = a * A; B = a * ((B - xp) + x); xp = x; });
         }
-        // (2) exclusive scan of the maps across lanes -> state entering each chunk
+        // inclusive scan inside the warp: (sA, sB) = map of chunks [warp start .. this thread]
         float sA = A, sB = B;
+#pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
             const float pA = __shfl_up_sync(0xffffffffu, sA, o), pB = __shfl_up_sync(0xffffffffu, sB, o);
             if (lane >= o) { sB = fmaf(sA, pB, sB); sA = sA * pA; }
         }
-        float y = __shfl_up_sync(0xffffffffu, sB, 1);      // zero initial state => state = B of the prefix
-        if (lane == 0) y = 0.0f;
-        // (3) replay
+        if (lane == 31) { wA[warp] = sA; wB[warp] = sB; }
+        __syncthreads();                                  // also orders the xp_first reads before the stores below
+        // state entering this warp: zero initial state pushed through the maps of the earlier warps
+        float y = 0.0f;
+        for (int w = 0; w < warp; ++w) y = fmaf(wA[w], y, wB[w]);
+        // ... and through the earlier chunks of this warp
+        const float eA = __shfl_up_sync(0xffffffffu, sA, 1), eB = __shfl_up_sync(0xffffffffu, sB, 1);
+        if (lane > 0) y = fmaf(eA, y, eB);
         float *dst = jb.y;
         if (!jb.highpass) {
             gf_chunk8(c0, c1, jb.alpha, src, [&](float a, float x, int i) { y = fmaf(a, x - y, y); dst[i] = y; });
@@ -223,11 +232,11 @@ __global__ void __launch_bounds__(32) gf_onepole_kernel(const GfOnepoleJob *__re
             float xp = xp_first;
             gf_chunk8(c0, c1, jb.alpha, src, [&](float a, float x, int i) { y = a * ((y - xp) + x); xp = x; dst[i] = y; });
         }
-        __syncwarp();
+        __syncthreads();
     }
 }
 
 void gf_launch_onepole(const GfOnepoleJob *jobs, int n_jobs, cudaStream_t st)
 {
-    if (n_jobs > 0) gf_onepole_kernel<<<n_jobs, 32, 0, st>>>(jobs);
+    if (n_jobs > 0) gf_onepole_kernel<<<n_jobs, GF_OP_THREADS, 0, st>>>(jobs);
 }
