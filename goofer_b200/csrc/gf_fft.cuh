@@ -13,9 +13,13 @@
 #define GF_FFT_N 512            // complex points
 #define GF_FFT_THREADS 64       // threads per transform (one radix-8 butterfly each per pass)
 
-// padded index for the 512-float2 exchange buffer: keeps the stride-8 / stride-64 scatter of the
-// Stockham passes off a single bank pair
-GF_HD int gf_fpad(int i) { return i + (i >> 5); }
+// swizzled index for the 512-float2 exchange buffer.  A shared-memory wavefront serves 16 float2 slots; the
+// Stockham passes touch the buffer with stride 1 (loads, last store), stride 8 (first store) and 8-runs 64 apart
+// (second store).  XOR-ing the low four index bits with bits 3..6 makes all three patterns conflict free:
+//   stride 1 : 16 consecutive i -> {0..7} ^ c and {8..15} ^ (c + 1), disjoint halves
+//   stride 8 : i = 8 j + r     -> low bits r ^ (j & 7), bit 3 = (j & 1) ^ (j >> 3 & 1): a bijection of j & 15
+//   8-runs   : i = 64 g + k + 8 r -> low bits k ^ r, bit 3 = (r ^ g) & 1: the two runs of a half-warp differ in bit 3
+GF_HD int gf_fpad(int i) { return i ^ ((i >> 3) & 15); }
 #define GF_FFT_BUF (512 + 20)   // float2 elements per padded transform buffer; 532 mod 16 == 4 puts consecutive
                                 // transforms 8 banks apart, so (bin, frame)-interleaved accesses do not collide
 
@@ -59,10 +63,10 @@ template <bool INV> GF_HD void gf_dft8(float2 *v)
 // running in place.
 template <bool INV, int NS> GF_HD void gf_fft_pass_load(int j, const float2 *buf, const float2 *tw512, float2 *v)
 {
-    // gf_fpad(j + 64 r) == gf_fpad(j) + 66 r for j < 64: one base, immediate offsets
-    const float2 *src = buf + gf_fpad(j);
+    // gf_fpad(j + 64 r) == 64 r + (gf_fpad(j) ^ (8 (r & 1))) for j < 64: two bases, immediate offsets
+    const float2 *src0 = buf + gf_fpad(j), *src1 = buf + (gf_fpad(j) ^ 8);
 #pragma unroll
-    for (int r = 0; r < 8; ++r) v[r] = src[66 * r];
+    for (int r = 0; r < 8; ++r) v[r] = (r & 1) ? src1[64 * r] : src0[64 * r];
     if (NS > 1) {
         const int k = j & (NS - 1);
         const int step = k * (64 / NS);          // twiddle exponent for r = 1 (in 512ths of a turn)
@@ -78,22 +82,24 @@ template <bool INV, int NS> GF_HD void gf_fft_pass_load(int j, const float2 *buf
 
 template <int NS> GF_HD void gf_fft_pass_store(int j, float2 *buf, const float2 *v)
 {
-    // padded index of j0 + r NS with j0 = 8 (j - k) + k, k = j mod NS, written with compile-time offsets:
-    //   NS = 1 : 8 j + r, all eight in the same 32-group            -> base + r
-    //   NS = 8 : 64 (j >> 3) + k + 8 r, crosses one 32-group at r=4 -> base + 8 r + (r >= 4)
-    //   NS = 64: j + 64 r                                            -> base + 66 r
+    // swizzled index of j0 + r NS with j0 = 8 (j - k) + k, k = j mod NS
     if (NS == 1) {
-        float2 *dst = buf + 8 * j + (j >> 2);
+        // i = 8 j + r: low three bits r ^ (j & 7), bit 3 of 8 j flipped by bit 3 of j
+        float2 *dst = buf + ((8 * j) ^ (j & 8));
+        const int x = j & 7;
 #pragma unroll
-        for (int r = 0; r < 8; ++r) dst[r] = v[r];
+        for (int r = 0; r < 8; ++r) dst[r ^ x] = v[r];
     } else if (NS == 8) {
-        float2 *dst = buf + 66 * (j >> 3) + (j & 7);
+        // i = 64 g + k + 8 r (g = j >> 3, k = j & 7): low three bits k ^ r, bit 3 = (r ^ g) & 1, bits 4..5 = r >> 1
+        const int g = j >> 3, k = j & 7;
+        float2 *dst = buf + 64 * g;
+        const int gx = (g & 1) << 3;
 #pragma unroll
-        for (int r = 0; r < 8; ++r) dst[8 * r + (r >= 4 ? 1 : 0)] = v[r];
+        for (int r = 0; r < 8; ++r) dst[(((k ^ r) + ((r >> 1) << 4)) ^ ((r & 1) << 3)) ^ gx] = v[r];
     } else {
-        float2 *dst = buf + gf_fpad(j);
+        float2 *dst0 = buf + gf_fpad(j), *dst1 = buf + (gf_fpad(j) ^ 8);
 #pragma unroll
-        for (int r = 0; r < 8; ++r) dst[66 * r] = v[r];
+        for (int r = 0; r < 8; ++r) { if (r & 1) dst1[64 * r] = v[r]; else dst0[64 * r] = v[r]; }
     }
 }
 
