@@ -58,7 +58,7 @@ void gf_launch_peak(const GfNotePlan *plans, const GfNoteDev *notes, const GfPas
                     int n_pass, int max_n, cudaStream_t st)
 {
     if (n_pass <= 0) return;
-    dim3 grid(min(32, (max_n + 255) / 256), n_pass);
+    dim3 grid(min(8, (max_n + 255) / 256), n_pass);         // few fat CTAs: the per-thread record loads amortise over ~20 samples
     gf_peak_kernel<<<grid, 256, 0, st>>>(plans, notes, passes, scal, pass0);
 }
 
@@ -126,7 +126,7 @@ void gf_launch_mix(const GfNotePlan *plans, const GfNoteDev *notes, const GfPass
                    int note0, int n_notes, int max_n, cudaStream_t st)
 {
     if (n_notes <= 0) return;
-    dim3 grid(min(32, (max_n + 255) / 256), n_notes);
+    dim3 grid(min(8, (max_n + 255) / 256), n_notes);
     gf_mix_kernel<<<grid, 256, 0, st>>>(plans, notes, passes, scal, note0);
 }
 
