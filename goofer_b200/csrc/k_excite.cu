@@ -11,6 +11,7 @@
 #include "gf_device.cuh"
 #include "gf_maps.cuh"
 #include <climits>
+#include <cstdlib>
 
 #define GF_PI_D 3.141592653589793
 
@@ -187,7 +188,9 @@ void gf_launch_f0(const GfNotePlan *plans, const GfNoteDev *notes, const GfPassD
                   const float *bend, const double *normals, int n_notes, int max_n, cudaStream_t st)
 {
     if (n_notes <= 0) return;
-    dim3 grid(min(48, (max_n + 255) / 256), n_notes);
+    // few fat CTAs per note (the per-CTA prologue reads three records) unless the batch is too small to fill the GPU
+    const int gx = max(8, min(64, (1184 + n_notes - 1) / n_notes));
+    dim3 grid(min(gx, (max_n + 255) / 256), n_notes);
     gf_f0_kernel<<<grid, 256, 0, st>>>(plans, notes, passes, srcs, bend, normals);
 }
 
