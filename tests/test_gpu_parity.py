@@ -324,3 +324,79 @@ def test_analysis_front_end_gpu(torch_cuda):
         _, po = dsp.analyse_envelope(y, 44100)
         assert p["knot_vals_log"].shape == po["knot_vals_log"].shape
         assert np.max(np.abs(p["knot_vals_log"].astype(np.float32) - po["knot_vals_log"].astype(np.float32))) <= 2e-2
+
+
+# ---- randomised argument fuzz: ragged lengths, extreme flags, both feature modes --------------------------------
+def _fuzz_cli(rng):
+    pitch = bench_data.midi_to_name(int(rng.integers(36, 84)))
+    vel = str(int(rng.choice([0, 50, 100, 100, 100, 150, 200])))
+    offset = int(rng.integers(0, 300))
+    length = int(rng.choice([60, 150, 400, 900, 1500, 3000]))
+    consonant = int(rng.choice([0, 0, 40, 120, 250]))
+    cutoff = int(rng.choice([0, 50, 200, -300, -600]))
+    volume = str(int(rng.choice([100, 100, 60, 130])))
+    tempo = "!" + str(int(rng.choice([60, 120, 180, 240])))
+    n_ticks = int(rng.integers(1, 400))
+    bend = "AA" if rng.random() < 0.4 else bench_data.cents_to_pitch_string(np.round(80 * np.sin(np.arange(n_ticks) / 9.0 + rng.random())).astype(int))
+    fl = []
+    pool = {"g": (-100, 100), "fa": (-9, 9), "fb": (-9, 9), "fc": (-9, 9), "fd": (-9, 9), "fw": (-100, 100), "fst": (-100, 100),
+            "fsta": (-50, 50), "fstd": (-50, 50), "br": (-100, 100), "es": (-100, 100), "V": (0, 100), "B": (-100, 100),
+            "U": (-100, 100), "P": (0, 100), "t": (-50, 50), "L": (0, 2), "R": (0, 1), "FV": (0, 1), "sd": (0, 100), "st": (-100, 100),
+            "su": (0, 100), "sa": (0, 100), "vf": (-100, 100), "pd": (-100, 100), "sr": (0, 100)}
+    for k in rng.choice(list(pool), size=int(rng.integers(0, 9)), replace=False):
+        lo, hi = pool[k]
+        fl.append(f"{k}{int(rng.integers(lo, hi + 1))}")
+    return [pitch, vel, "".join(fl), str(offset), str(length), str(consonant), str(cutoff), volume, "0", tempo, bend]
+
+
+def test_fuzzed_arguments(torch_cuda):
+    """48 seeded random argument lists (ragged lengths 60 ms .. 3 s, velocity 0 .. 200, negative cutoffs, every
+    loop / reverse mode, extreme flag values) on knot-coded AND dense-envelope sources, rendered as ONE batch.
+    Notes the reference cannot render (empty tail: ZeroDivisionError) must be rejected by the planner too."""
+    rng = np.random.default_rng(2024)
+    feats, sfs = [], []
+    for si in range(4):
+        feat, sf = cases.source_for(si, 1.0)
+        if si % 2:                                     # 'full' mode: dense (513, T) envelope instead of knots
+            sf = host.SourceFeatures.from_dense(feat.env, feat.mask, feat.formants, feat.sr, feat.ylen)
+        feats.append(feat)
+        sfs.append(sf)
+    notes, refs = [], []
+    lib = capi.load()
+    tried = rejected = 0
+    while len(notes) < 48:
+        si = int(rng.integers(0, 4))
+        cli = _fuzz_cli(rng)
+        tried += 1
+        spec = resampler.NoteSpec.from_cli(*cli)
+        seed = 5000 + tried
+        try:
+            ref = resampler.resample(feats[si], spec, lambda n, T: resampler.noise_for_note(spec, n, T, seed, seed + 1))
+        except ZeroDivisionError:
+            b = host.Batch()
+            b.add_source(sfs[si])
+            b.add_note(host.NoteArgs.from_cli(0, cli))
+            with pytest.raises(capi.GooferError):
+                b.assemble(host.SeededNoise())
+            rejected += 1
+            continue
+        if len(ref) < 2:
+            continue
+        notes.append((si, cli, seed))
+        refs.append(ref)
+    b = host.Batch()
+    for sf in sfs:
+        b.add_source(sf)
+    for si, cli, seed in notes:
+        b.add_note(host.NoteArgs.from_cli(si, cli))
+    seeds = [s for _, _, s in notes]
+    db = b.assemble(host.SeededNoise(base_seed=lambda j: seeds[j], legacy_seed=lambda j: seeds[j] + 1)).to_device("cuda:0")
+    db.render()
+    outs = db.outputs()
+    worst = 0.0
+    for k, (ref, got) in enumerate(zip(refs, outs)):
+        assert got.shape == ref.shape, notes[k]
+        err = float(np.max(np.abs(got.astype(np.float64) - ref))) if len(ref) else 0.0
+        worst = max(worst, err)
+        assert err <= MAX_ABS, (notes[k], err)
+    print(f"fuzz: {len(notes)} notes, {rejected} rejected by both, worst max-abs {worst:.2e}")
