@@ -257,6 +257,17 @@ __device__ __forceinline__ void gf_fir_rt(const T *row, int b0, const T *taps, i
     }
 }
 
+// linear interpolation of a 513-bin row at fractional bin position u in [0, 512]: the position is fp64, the lerp f32
+// (the reference evaluates slope * (x - x0) + y0 in fp64 and stores f32: at most one f32 ulp apart)
+__device__ __forceinline__ float gf_grid_lerp(const float *row, double u)
+{
+    int j = (int)u;
+    if (j > 511) j = 511;
+    const float t = (float)(u - (double)j);
+    const float y0 = row[j];
+    return fmaf(t, row[j + 1] - y0, y0);
+}
+
 // np.interp on the uniform grid freqs[i] = i * step (freqs[512] = nyq) with the linear extrapolation of
 // GOOFER.py:173-239 outside [0, nyq]
 __device__ __forceinline__ float gf_grid_interp(const float *row, double x, double step, double inv_step, double nyq)
@@ -272,11 +283,7 @@ __device__ __forceinline__ float gf_grid_interp(const float *row, double x, doub
     }
     // piece-wise linear interpolation is continuous, so a bracket that is off by one at a grid point (x * inv_step
     // rounds across an integer) yields the same value: no fix-up of j is needed, and t comes from the same product
-    const double u = x * inv_step;
-    int j = (int)u;
-    if (j > 511) j = 511;
-    const double y0 = (double)row[j];
-    return (float)fma((double)row[j + 1] - y0, u - (double)j, y0);
+    return gf_grid_lerp(row, x * inv_step);
 }
 
 __global__ void __launch_bounds__(32 * GF_ENV_WARPS, 2)
@@ -519,10 +526,9 @@ gf_env_kernel(const int2 *__restrict__ work, const GfNotePlan *__restrict__ plan
 #pragma unroll
         for (int e = 0; e < GF_EPL; ++e) {
             if (e < nown) {
+                // freqs / ratio on the freqs grid: in bins that is b / ratio, clipped to [0, 512]
                 const int b = b0 + e;
-                const double x = (b == 512) ? nyq : (double)b * step;
-                const double q = fmin(fmax(x * inv_r, 0.0), nyq);
-                oth[b] = gf_grid_interp(cur, q, step, inv_step, nyq);
+                oth[b] = gf_grid_lerp(cur, fmin(fmax((double)b * inv_r, 0.0), 512.0));
             }
         }
         __syncwarp();
