@@ -81,6 +81,14 @@ def test_pulse_train_onsets_bit_exact(torch_cuda):
         f0[:3000] = 0.0
         rows.append(f0)
     rows.append(np.concatenate([np.linspace(90.0, 700.0, 44100), np.linspace(700.0, 60.0, 44100)]).astype(np.float32))
+    # the phase walk is a scan of integer parity maps (tests/test_walk_scan_cpu.py): gaps, tiny and negative
+    # increments, a negative running total, increments larger than the total
+    rng = np.random.default_rng(9)
+    rows.append((330 * (rng.random(88200) > 0.3)).astype(np.float32))
+    rows.append(np.concatenate([1e-5 * rng.random(30000), np.full(58200, 523.25)]).astype(np.float32))
+    rows.append((220 * (1 + 1.5 * np.sin(np.arange(88200) / 50.0))).astype(np.float32))
+    rows.append(np.concatenate([np.full(500, -80.0), np.full(87700, 300.0)]).astype(np.float32))
+    rows.append(np.concatenate([np.full(40000, 0.001), np.full(48200, 1200.0)]).astype(np.float32))
     f0 = np.stack(rows)
     got = ops.pulse_train(torch.from_numpy(f0).cuda(), 44100).cpu().numpy()
     for k in range(f0.shape[0]):
