@@ -39,7 +39,7 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
-    ap.add_argument("--workload", default="c2", choices=["c1", "c2", "c3", "c5"])
+    ap.add_argument("--workload", default="c2", choices=["c1", "c2", "c3", "c4", "c5"])
     ap.add_argument("--notes", type=int, default=1024, help="notes per rank per step")
     ap.add_argument("--cpu-sample", type=int, default=96, help="notes of the workload timed on the CPU (0 = skip)")
     ap.add_argument("--no-e2e", action="store_true")
@@ -49,7 +49,7 @@ def parse_args():
 def workload_config(args, n_gpus):
     import bench_data
     return {"workload": f"{args.workload}: {bench_data.WORKLOADS[args.workload]}", "notes_per_gpu": args.notes,
-            "global_notes": args.notes * n_gpus, "note_seconds": 1.0, "sample_rate": 44100, "n_sources": 64,
+            "global_notes": args.notes * n_gpus, "note_seconds": 16.0 if args.workload == "c4" else 1.0, "sample_rate": 44100, "n_sources": 64,
             "parallelism": f"notes sharded over {n_gpus} rank(s), no collective on the data path",
             "l2_policy": "inputs larger than L2 (noise phases alone are 4*513*173 B per note)"}
 
@@ -58,6 +58,7 @@ def workload_config(args, n_gpus):
 # CPU legs (the ONLY place bench.py touches oracle/): cpu_baseline of the native arm, and --impl reference
 # ------------------------------------------------------------------------------------------------------
 _ORC = {}
+_ORC_SECONDS = [1.0]
 
 
 def _oracle_feat(src_idx):
@@ -66,7 +67,7 @@ def _oracle_feat(src_idx):
     from oracle.resampler import Features
     f = _ORC.get(src_idx)
     if f is None:
-        s = bench_data.make_source(src_idx)
+        s = bench_data.make_source(src_idx, _ORC_SECONDS[0])
         env = dsp.decode_knots({"knot_vals_log": s["knot_vals_log"], "hz_knots": s["hz_knots"], "n_fft": 1024,
                                 "sr": s["sr"], "n_bins": 513})
         f = Features(env=env, mask=s["mask"], formants=s["formants"], sr=s["sr"], ylen=s["ylen"])
@@ -79,7 +80,8 @@ def _oracle_note(job):
     workload, i = job
     import bench_data
     from oracle import resampler
-    src, cli = bench_data.note_cli(i, workload)
+    _ORC_SECONDS[0] = bench_data.SOURCE_SECONDS.get(workload, 1.0)
+    src, cli = bench_data.note_cli(i, workload, n_sources=8 if workload == "c4" else 64)
     spec = resampler.NoteSpec.from_cli(*cli)
     out = resampler.resample(_oracle_feat(src), spec,
                              lambda n, T: resampler.noise_for_note(spec, n, T, 20000 + 16 * i, 777 + i))
@@ -183,12 +185,13 @@ def build_batch(args, rank):
     import bench_data
     from goofer_b200 import host
     b = host.Batch()
-    feats = [bench_data.make_source(s) for s in range(64)]
+    n_src = 8 if args.workload == "c4" else 64
+    feats = [bench_data.make_source(s, bench_data.SOURCE_SECONDS.get(args.workload, 1.0)) for s in range(n_src)]
     for f in feats:
         b.add_source(host.SourceFeatures.from_knot_pack(f, f["mask"], f["formants"], f["sr"], f["ylen"]))
     first = rank * args.notes
     for j in range(args.notes):
-        src, cli = bench_data.note_cli(first + j, args.workload)
+        src, cli = bench_data.note_cli(first + j, args.workload, n_sources=n_src)
         b.add_note(host.NoteArgs.from_cli(src, cli))
     noise = host.SeededNoise(base_seed=lambda j: 20000 + 16 * (first + j), legacy_seed=lambda j: 777 + first + j)
     ab = b.assemble(noise)

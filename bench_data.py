@@ -109,15 +109,22 @@ def note_cli(i: int, workload: str, n_sources: int = 64):
         flags = formant_flags(i) if (workload == "c2" or i % 2) else ""
     elif workload == "c3":
         flags = full_flags(i)
+    elif workload == "c4":
+        # long-note sustain: 4 s sources stretched to 16 s, loop modes L0 / L1 / L2 x R0 / R1
+        flags = f"L{i % 3}" + ("R1" if (i // 3) % 2 else "")
+        return i % n_sources, [pitch, "100", flags, "30", "16000", "150", "200", "100", "0", "!120", "AA" if i % 2 == 0 else _vibrato_string(i, 16.2)]
     else:
         raise ValueError(workload)
     return i % n_sources, [pitch, "100", flags, "0", "1000", "0", "0", "100", "0", "!120", bend]
 
 
+SOURCE_SECONDS = {"c4": 4.0}
+
 WORKLOADS = {
     "c1": "SillySampler single-note CLI resample: 1 s synthetic 44.1 kHz vowel, default flags",
     "c2": "batch of 1,024 synthetic 1 s notes, formant flags g/fa-fd/fw/fst/br/es",
     "c3": "full-flag stress batch: B/U/V mix + sh/sr/sg/sd/sj/sa/su + vf vocal fry, fixed-seed noise",
+    "c4": "long-note sustain: 4 s source stretched to 16 s with L0/L1/L2 loop modes and R1 reverse",
     "c5": "whole-voicebank sweep: default+formant flags, notes sharded across ranks",
 }
 

@@ -225,34 +225,64 @@ __device__ __forceinline__ float gf_lf_table_max(double T, int T0)
 }
 
 #define GF_WALK_WARPS 2
-#define GF_WALK_U 4                   // 32-sample groups per iteration (loads of the next iteration are in flight)
+#define GF_WALK_S 8                   // samples per lane on the fast path (a warp advances 256 samples per step)
 
-// one 32-sample group: lane L owns sample base + L.  `total` enters as the phase before the group and leaves
-// as the phase after it; returns this lane's running total.  Every lane runs the same left-to-right fp64
-// chain (bit-exact with the reference's scalar loop); the increments are staged through shared memory.
-__device__ __forceinline__ double gf_walk_chain(double *s_inc, double inc, int lane, double &total)
+// ------------------------------------------------------------------------------------------------
+// Phase walk of pulse_train_numba (GOOFER.py:479-493): total_phase += f0[i] / sr in fp64, sample by sample; a pulse
+// fires whenever the running total passes the next integer.  The sequential rounding is part of the result (rounding
+// ties on every A note), but the chain does not have to be EXECUTED serially
+// (44,100 dependent DADDs per second of audio, ~36 cycles each):
+//
+//   While the exponent e of the running total is fixed, total = M * 2^(e-52) with an integer mantissa M, and adding
+//   the increment m_k * 2^(e_k-52) in round-to-nearest-even gives   M' = M + q_k + c_k + t_k * ((M + q_k) & 1)
+//   with s = e - e_k, q_k = m_k >> s, r_k = the s bits shifted out, c_k = [r_k > half], t_k = [r_k == half].
+//   Each step is therefore a map  M -> M + delta[M & 1]  with a pair (delta[0], delta[1]) that depends only on the
+//   increment.  Such maps are closed under composition, (a then b)[p] = a[p] + b[(p + a[p]) & 1], so the running
+//   mantissas come out of a scan of integer pairs -- bit for bit what the scalar fp64 loop produces, ties included.
+//   Only the steps that change the exponent (about 16 per note: the total crosses a power of two), the first
+//   non-zero increment and negative increments are executed as real fp64 additions.
+//
+// Fast path: 8 consecutive samples per lane (local composition), one warp scan per 256 samples.  A block that holds
+// an exponent event is redone on the slow path: one sample per lane, the event sample added in fp64.
+// The same arithmetic in Python integers, checked against the scalar loop: tools/experiments/walk_scan_proto.py.
+// ------------------------------------------------------------------------------------------------
+struct GfDelta { unsigned long long d0, d1; };        // M -> M + (M & 1 ? d1 : d0)
+
+__device__ __forceinline__ GfDelta gf_delta_then(const GfDelta &a, const GfDelta &b)
 {
-    s_inc[lane] = inc;
-    __syncwarp();
-    // lane L adds increments 0..L to the incoming phase, one after the other: the same additions in the same
-    // order as the reference's scalar loop up to sample L
-    double mine = total;
-    const double2 *s2 = reinterpret_cast<const double2 *>(s_inc);
-#pragma unroll
-    for (int k = 0; k < 16; ++k) {
-        const double2 v = s2[k];
-        if (lane >= 2 * k) mine = __dadd_rn(mine, v.x);
-        if (lane >= 2 * k + 1) mine = __dadd_rn(mine, v.y);
+    GfDelta r;
+    r.d0 = a.d0 + ((a.d0 & 1ull) ? b.d1 : b.d0);                   // parity of 0 + a.d0
+    r.d1 = a.d1 + (((1ull + a.d1) & 1ull) ? b.d1 : b.d0);          // parity of 1 + a.d1
+    return r;
+}
+
+// delta pair of one increment under the exponent e of the running total; returns true when the step needs a real
+// fp64 addition instead (negative / subnormal increment, no positive normal total yet, increment above the total)
+__device__ __forceinline__ bool gf_walk_delta(double inc, bool started, bool raw_mode, int e, GfDelta &d)
+{
+    d.d0 = 0ull; d.d1 = 0ull;
+    const long long ib = __double_as_longlong(inc);
+    if ((ib << 1) == 0) return false;                              // +-0: identity
+    const int efield = (int)((ib >> 52) & 0x7ff);
+    const int s = e - (efield - 1023);
+    if (ib < 0 || efield == 0 || !started || raw_mode || s < 0) return true;
+    if (s < 64) {
+        const unsigned long long mk = ((unsigned long long)ib & ((1ull << 52) - 1ull)) | (1ull << 52);
+        const unsigned long long q = mk >> s;
+        unsigned long long c = 0ull, t = 0ull;
+        if (s > 0) {
+            const unsigned long long r = mk & ((1ull << s) - 1ull), half = 1ull << (s - 1);
+            c = r > half; t = r == half;
+        }
+        d.d0 = q + c + (t & q);                                    // (0 + q) & 1
+        d.d1 = q + c + (t & (q + 1ull));                           // (1 + q) & 1
     }
-    total = __shfl_sync(0xffffffffu, mine, 31);
-    __syncwarp();
-    return mine;
+    return false;
 }
 
 __global__ void __launch_bounds__(32 * GF_WALK_WARPS)
 gf_walk_kernel(const GfPassDev *__restrict__ passes, GfPassScal *scal, int n_pass, int sr_i)
 {
-    __shared__ __align__(16) double s_inc[GF_WALK_WARPS][32];
     const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int pi = blockIdx.x * GF_WALK_WARPS + w;
     if (pi >= n_pass) return;
@@ -260,76 +290,174 @@ gf_walk_kernel(const GfPassDev *__restrict__ passes, GfPassScal *scal, int n_pas
     const int n = ps.n_total;
     const double sr = (double)sr_i;
     const float *__restrict__ f0 = ps.f0;
-    double total = 0.0;
+    const unsigned long long MANT = (1ull << 52) - 1ull, ONE53 = 1ull << 53;
+    // running total = started ? M * 2^(e - 52) : (raw_mode ? raw : 0).  raw_mode: the total is negative or subnormal
+    // (only possible with f0 jitter beyond 100 % at the very start of a note) and every sample is a real fp64 add
+    bool started = false, raw_mode = false;
+    double raw = 0.0;
+    unsigned long long M = 0ull;
+    int e = 0;
     int fired = 0;                      // next_k - 1
     float lv_carry = 160.0f;            // last_valid_f0 (GOOFER.py:477)
     int count = 0;
-    float fcur[GF_WALK_U], fnext[GF_WALK_U];
+    const bool aligned16 = (reinterpret_cast<size_t>(f0) & 15) == 0;
+
+    for (int blk = 0; blk < n; blk += 32 * GF_WALK_S) {
+        const int blk_end = min(n, blk + 32 * GF_WALK_S);
+        // ================= fast path: 8 consecutive samples per lane =================
+        bool fast_ok = started && !raw_mode;
+        if (fast_ok) {
+            const int i0 = blk + GF_WALK_S * lane;
+            float f[GF_WALK_S];
+            if (blk + 32 * GF_WALK_S <= n && aligned16) {
+                const float4 a = *reinterpret_cast<const float4 *>(f0 + i0), b4 = *reinterpret_cast<const float4 *>(f0 + i0 + 4);
+                f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = b4.x; f[5] = b4.y; f[6] = b4.z; f[7] = b4.w;
+            } else {
 #pragma unroll
-    for (int u = 0; u < GF_WALK_U; ++u) { const int i = 32 * u + lane; fcur[u] = (i < n) ? f0[i] : 0.0f; }
-    for (int base = 0; base < n; base += 32 * GF_WALK_U) {
+                for (int j = 0; j < GF_WALK_S; ++j) f[j] = (i0 + j < n) ? f0[i0 + j] : 0.0f;
+            }
+            GfDelta d[GF_WALK_S];
+            bool ev = false;
 #pragma unroll
-        for (int u = 0; u < GF_WALK_U; ++u) {
-            const int i = base + 32 * (GF_WALK_U + u) + lane;
-            fnext[u] = (i < n) ? f0[i] : 0.0f;
-        }
-        double inc[GF_WALK_U];
+            for (int j = 0; j < GF_WALK_S; ++j) ev |= gf_walk_delta(__ddiv_rn((double)f[j], sr), true, false, e, d[j]);
+            GfDelta G = d[0];
 #pragma unroll
-        for (int u = 0; u < GF_WALK_U; ++u) inc[u] = __ddiv_rn((double)fcur[u], sr);     // 0 beyond n
+            for (int j = 1; j < GF_WALK_S; ++j) G = gf_delta_then(G, d[j]);
+            // inclusive scan of the per-lane maps, then the map from the block start to this lane's first sample
+            GfDelta F = G;
 #pragma unroll
-        for (int u = 0; u < GF_WALK_U; ++u) {
-            const int i = base + 32 * u + lane;
-            const float f = fcur[u];
-            const double mine = gf_walk_chain(s_inc[w], inc[u], lane, total);
-            // pulses fired up to and including sample i = running max of floor(total)
-            int m = (i < n) ? (int)floor(mine) : INT_MIN;
-            const int gmax = __reduce_max_sync(0xffffffffu, m);
-            const bool valid = (i < n) && ((double)f > 1e-6);
-            const unsigned bal = __ballot_sync(0xffffffffu, valid);
-            if (gmax > fired) {
-                // at least one onset in this group
-                int prev = __shfl_up_sync(0xffffffffu, m, 1);
-                if (lane == 0) prev = fired;
-                const bool simple = (i >= n) || (m >= prev && m - prev <= 1 && m >= fired);
-                int cnt;
-                int slot;
-                if (__all_sync(0xffffffffu, simple)) {
-                    // common case (f0 >= 0, at most one pulse per sample): floor(total) is its own running maximum
-                    cnt = (i < n) ? (m - prev) : 0;
-                    const unsigned fm = __ballot_sync(0xffffffffu, cnt > 0);
-                    slot = count + __popc(fm & ((1u << lane) - 1u));
-                    count += __popc(fm);
-                } else {
+            for (int o = 1; o < 32; o <<= 1) {
+                GfDelta a;
+                a.d0 = __shfl_up_sync(0xffffffffu, F.d0, o);
+                a.d1 = __shfl_up_sync(0xffffffffu, F.d1, o);
+                if (lane >= o) F = gf_delta_then(a, F);
+            }
+            GfDelta E;
+            E.d0 = __shfl_up_sync(0xffffffffu, F.d0, 1);
+            E.d1 = __shfl_up_sync(0xffffffffu, F.d1, 1);
+            if (lane == 0) { E.d0 = 0ull; E.d1 = 0ull; }
+            unsigned long long Mj = M + ((M & 1ull) ? E.d1 : E.d0);
+            const int sh = 52 - e;
+            int mprev_lane;                                      // floor(total) before this lane's first sample
+            int m[GF_WALK_S];
 #pragma unroll
-                    for (int o = 1; o < 32; o <<= 1) {
-                        const int v = __shfl_up_sync(0xffffffffu, m, o);
-                        if (lane >= o) m = max(m, v);
-                    }
-                    m = max(m, fired);
-                    prev = __shfl_up_sync(0xffffffffu, m, 1);
-                    if (lane == 0) prev = fired;
-                    cnt = (i < n) ? (m - prev) : 0;
-                    int incl = cnt;
+            for (int j = 0; j < GF_WALK_S; ++j) {
+                Mj += (Mj & 1ull) ? d[j].d1 : d[j].d0;
+                m[j] = max((e >= 0) ? (int)(Mj >> sh) : 0, fired);       // running max (the total may have dipped earlier)
+            }
+            const bool carry = Mj >= ONE53;                      // mantissas only grow on this path: the last one decides
+            fast_ok = !__any_sync(0xffffffffu, ev || carry);
+            if (fast_ok) {
+                mprev_lane = __shfl_up_sync(0xffffffffu, m[GF_WALK_S - 1], 1);
+                if (lane == 0) mprev_lane = fired;
+                const int lane_cnt = m[GF_WALK_S - 1] - mprev_lane;          // onsets inside this lane's run (totals never decrease here)
+                // last f0 > 1e-6 before this lane's run
+                float lastv = 0.0f; bool hasv = false;
+#pragma unroll
+                for (int j = 0; j < GF_WALK_S; ++j) if ((i0 + j < n) && ((double)f[j] > 1e-6)) { lastv = f[j]; hasv = true; }
+                const unsigned hv = __ballot_sync(0xffffffffu, hasv);
+                const unsigned below = hv & ((1u << lane) - 1u);
+                const float prior = __shfl_sync(0xffffffffu, lastv, below ? (31 - __clz(below)) : 0);
+                float lv = below ? prior : lv_carry;
+                const int tot_cnt = __shfl_sync(0xffffffffu, m[GF_WALK_S - 1], 31) - fired;
+                if (tot_cnt > 0) {
+                    int incl = lane_cnt;
 #pragma unroll
                     for (int o = 1; o < 32; o <<= 1) {
                         const int v = __shfl_up_sync(0xffffffffu, incl, o);
                         if (lane >= o) incl += v;
                     }
-                    slot = count + incl - cnt;
-                    count += __shfl_sync(0xffffffffu, incl, 31);
+                    int slot = count + incl - lane_cnt;
+                    int mp = mprev_lane;
+#pragma unroll
+                    for (int j = 0; j < GF_WALK_S; ++j) {
+                        if ((i0 + j < n) && ((double)f[j] > 1e-6)) lv = f[j];
+                        for (int c = mp; c < m[j]; ++c, ++slot)
+                            if (slot < ps.onset_cap) ps.onsets[slot] = make_int4(i0 + j, 0, __float_as_int(lv), 0);   // T0 / table max: gf_onset_kernel
+                        mp = m[j];
+                    }
+                    count += tot_cnt;
+                    fired += tot_cnt;
                 }
+                if (hv) lv_carry = __shfl_sync(0xffffffffu, lastv, 31 - __clz(hv));
+                M = __shfl_sync(0xffffffffu, Mj, 31);
+                continue;
+            }
+        }
+        // ================= slow path: one sample per lane, exponent events as real fp64 additions =================
+        int base = blk;
+        while (base < blk_end) {
+            const int i = base + lane;
+            const int cnt_lanes = min(32, blk_end - base);
+            const float f = (lane < cnt_lanes) ? f0[i] : 0.0f;
+            const double inc = __ddiv_rn((double)f, sr);
+            GfDelta d;
+            const bool ev = gf_walk_delta(inc, started, raw_mode, e, d) && (lane < cnt_lanes);
+            if (lane >= cnt_lanes) { d.d0 = 0ull; d.d1 = 0ull; }
+            GfDelta F = d;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                GfDelta a;
+                a.d0 = __shfl_up_sync(0xffffffffu, F.d0, o);
+                a.d1 = __shfl_up_sync(0xffffffffu, F.d1, o);
+                if (lane >= o) F = gf_delta_then(a, F);
+            }
+            const unsigned long long Mk = M + ((M & 1ull) ? F.d1 : F.d0);
+            const bool carry = started && Mk >= ONE53;
+            const unsigned evmask = __ballot_sync(0xffffffffu, (lane < cnt_lanes) && (ev || carry));
+            const int first = evmask ? (__ffs(evmask) - 1) : 32;      // lane of the first event (32: none)
+            const int last_lane = evmask ? first : cnt_lanes - 1;      // last sample handled in this round
+            int m = INT_MIN;                                           // floor(running total) of lanes < first
+            if (lane < first && lane < cnt_lanes) m = (started && e >= 0) ? (int)(Mk >> (52 - e)) : 0;
+            if (first > 0 && started) M = __shfl_sync(0xffffffffu, Mk, min(first, cnt_lanes) - 1);
+            if (evmask) {
+                // the event sample: one real fp64 addition (every lane computes the same values)
+                const double prev = raw_mode ? raw
+                                  : (started ? __longlong_as_double((long long)(((unsigned long long)(e + 1023) << 52) | (M & MANT))) : 0.0);
+                const double tot = __dadd_rn(prev, __shfl_sync(0xffffffffu, inc, first));
+                const long long tb = __double_as_longlong(tot);
+                const int tf = (int)((tb >> 52) & 0x7ff);
+                if (tb > 0 && tf != 0) { started = true; raw_mode = false; M = ((unsigned long long)tb & MANT) | (1ull << 52); e = tf - 1023; }
+                else if ((tb << 1) == 0) { started = false; raw_mode = false; M = 0ull; e = 0; }
+                else { started = false; raw_mode = true; raw = tot; M = 0ull; e = 0; }
+                if (lane == first) m = (int)floor(tot);
+            }
+            // ---- onsets of lanes <= last_lane: pulses fired up to and including a sample = running max of floor(total) ----
+            const bool in_round = lane <= last_lane && lane < cnt_lanes;
+            if (!in_round) m = INT_MIN;
+            const int gmax = __reduce_max_sync(0xffffffffu, m);
+            const bool valid = in_round && ((double)f > 1e-6);
+            const unsigned bal = __ballot_sync(0xffffffffu, valid);
+            if (gmax > fired) {
+                int mm = m;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const int v = __shfl_up_sync(0xffffffffu, mm, o);
+                    if (lane >= o) mm = max(mm, v);
+                }
+                mm = max(mm, fired);
+                int prevm = __shfl_up_sync(0xffffffffu, mm, 1);
+                if (lane == 0) prevm = fired;
+                const int cnt = in_round ? (mm - prevm) : 0;
+                int incl = cnt;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const int v = __shfl_up_sync(0xffffffffu, incl, o);
+                    if (lane >= o) incl += v;
+                }
+                int slot = count + incl - cnt;
+                count += __shfl_sync(0xffffffffu, incl, 31);
                 // last f0 > 1e-6 at or before sample i
                 const unsigned below = bal & ((2u << lane) - 1u);
                 const float cand = __shfl_sync(0xffffffffu, f, below ? (31 - __clz(below)) : 0);
                 const float lvf = below ? cand : lv_carry;
                 for (int c = 0; c < cnt; ++c, ++slot)
-                    if (slot < ps.onset_cap) ps.onsets[slot] = make_int4(i, 0, __float_as_int(lvf), 0);   // T0 / table max: gf_onset_kernel
+                    if (slot < ps.onset_cap) ps.onsets[slot] = make_int4(i, 0, __float_as_int(lvf), 0);
                 fired = max(fired, gmax);
             }
             if (bal) lv_carry = __shfl_sync(0xffffffffu, f, 31 - __clz(bal));
+            base += last_lane + 1;
         }
-#pragma unroll
-        for (int u = 0; u < GF_WALK_U; ++u) fcur[u] = fnext[u];
     }
     if (lane == 0) {
         scal[pi].n_onsets = min(count, ps.onset_cap);
@@ -389,7 +517,7 @@ void gf_launch_walk(const GfPassDev *passes, GfPassScal *scal, int n_pass, int s
 // guards (< 1e-8 relative, like the reference's own 5-slot table cache, which reuses one T per T0).
 // ------------------------------------------------------------------------------------------------
 #define GF_PULSE_CAP 512
-#define GF_PULSE_CHUNKS 16            // CTAs per (note, pass): each owns a contiguous run of 256-sample tiles
+#define GF_PULSE_SPAN 4096            // samples per CTA: a contiguous run of 256-sample tiles whose onsets are staged once
 __device__ __forceinline__ float gf_lf_value_f32(int d, int jp, int jc, float r_rise, float r_fall, float inv_max)
 {
     float v = 0.0f;
@@ -469,6 +597,6 @@ gf_pulse_kernel(const GfPassDev *__restrict__ passes, const GfPassScal *__restri
 void gf_launch_pulse(const GfPassDev *passes, const GfPassScal *scal, int n_pass, int max_n, cudaStream_t st)
 {
     if (n_pass <= 0) return;
-    dim3 grid(min(GF_PULSE_CHUNKS, (max_n + 255) / 256), n_pass);
+    dim3 grid((max_n + GF_PULSE_SPAN - 1) / GF_PULSE_SPAN, n_pass);
     gf_pulse_kernel<<<grid, 256, 0, st>>>(passes, scal);
 }
