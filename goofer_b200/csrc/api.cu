@@ -536,7 +536,7 @@ static int gf_render_wave(const GooferBatch *b, const std::vector<GfNotePlan> &a
         gf_launch_fir(d_fir, (int)wh.fir.size(), max_n, max_sigma, st); ++L; GF_STEP("fir");
     }
     gf_launch_f0(d_plans, d_notes, d_passes, d_srcs, b->bend_cents, b->normals, nn, max_n, st); ++L; GF_STEP("f0");
-    gf_launch_walk(d_passes, d_scal, (int)n_pass, sr, st); ++L; GF_STEP("walk");
+    gf_launch_walk(d_passes, d_scal, (int)n_pass, max_n, sr, st); ++L; GF_STEP("walk");
     gf_launch_pulse(d_passes, d_scal, (int)n_pass, max_n, st); ++L; GF_STEP("pulse");
     if ((rc = gf_growl(wh, d_plans, d_notes, d_passes, d_scal, bp, max_n, st, &L)) != GOOFER_OK) return rc;
     gf_launch_env(d_envw, (int)wh.env_work.size(), d_plans, d_notes, d_srcs, st); ++L; GF_STEP("env");
@@ -726,7 +726,7 @@ extern "C" int goofer_pulse_train_batch(const float *f0, int32_t n_sig, int32_t 
     GfPassScal *d_sc = bp.arr<GfPassScal>(n_sig);
     GF_CUDA(cudaMemcpyAsync(d_ps, ps.data(), ps.size() * sizeof(GfPassDev), cudaMemcpyHostToDevice, st));
     GF_CUDA(cudaMemsetAsync(d_sc, 0, n_sig * sizeof(GfPassScal), st));
-    gf_launch_walk(d_ps, d_sc, n_sig, sr, st);
+    gf_launch_walk(d_ps, d_sc, n_sig, n, sr, st);
     gf_launch_pulse(d_ps, d_sc, n_sig, n, st);
     GF_CUDA(cudaGetLastError());
     std::vector<GfPassScal> sc(n_sig);

@@ -224,7 +224,6 @@ __device__ __forceinline__ float gf_lf_table_max(double T, int T0)
     return m;
 }
 
-#define GF_WALK_WARPS 2
 #define GF_WALK_S 8                   // samples per lane on the fast path (a warp advances 256 samples per step)
 
 // ------------------------------------------------------------------------------------------------
@@ -280,11 +279,17 @@ __device__ __forceinline__ bool gf_walk_delta(double inc, bool started, bool raw
     return false;
 }
 
+template <int GF_WALK_WARPS>
 __global__ void __launch_bounds__(32 * GF_WALK_WARPS)
 gf_walk_kernel(const GfPassDev *__restrict__ passes, GfPassScal *scal, int n_pass, int sr_i)
 {
+    // one CTA of GF_WALK_WARPS warps per (note, pass): the scan is associative, so a block of
+    // GF_WALK_WARPS x 256 samples is advanced per step.  Every warp keeps an identical copy of the walk state.
+    __shared__ GfDelta s_tot[GF_WALK_WARPS];
+    __shared__ int s_mlast[GF_WALK_WARPS], s_bad[GF_WALK_WARPS], s_hasv[GF_WALK_WARPS];
+    __shared__ float s_lastv[GF_WALK_WARPS];
     const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int pi = blockIdx.x * GF_WALK_WARPS + w;
+    const int pi = blockIdx.x;
     if (pi >= n_pass) return;
     const GfPassDev ps = passes[pi];
     const int n = ps.n_total;
@@ -301,15 +306,16 @@ gf_walk_kernel(const GfPassDev *__restrict__ passes, GfPassScal *scal, int n_pas
     float lv_carry = 160.0f;            // last_valid_f0 (GOOFER.py:477)
     int count = 0;
     const bool aligned16 = (reinterpret_cast<size_t>(f0) & 15) == 0;
+    const int BLK = 32 * GF_WALK_S * GF_WALK_WARPS;
 
-    for (int blk = 0; blk < n; blk += 32 * GF_WALK_S) {
-        const int blk_end = min(n, blk + 32 * GF_WALK_S);
-        // ================= fast path: 8 consecutive samples per lane =================
+    for (int blk = 0; blk < n; blk += BLK) {
+        const int blk_end = min(n, blk + BLK);
+        // ================= fast path: 8 consecutive samples per lane, GF_WALK_WARPS x 256 samples per step =================
         bool fast_ok = started && !raw_mode;
         if (fast_ok) {
-            const int i0 = blk + GF_WALK_S * lane;
+            const int i0 = blk + 32 * GF_WALK_S * w + GF_WALK_S * lane;
             float f[GF_WALK_S];
-            if (blk + 32 * GF_WALK_S <= n && aligned16) {
+            if (i0 + GF_WALK_S <= n && aligned16) {
                 const float4 a = *reinterpret_cast<const float4 *>(f0 + i0), b4 = *reinterpret_cast<const float4 *>(f0 + i0 + 4);
                 f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = b4.x; f[5] = b4.y; f[6] = b4.z; f[7] = b4.w;
             } else {
@@ -323,7 +329,7 @@ gf_walk_kernel(const GfPassDev *__restrict__ passes, GfPassScal *scal, int n_pas
             GfDelta G = d[0];
 #pragma unroll
             for (int j = 1; j < GF_WALK_S; ++j) G = gf_delta_then(G, d[j]);
-            // inclusive scan of the per-lane maps, then the map from the block start to this lane's first sample
+            // inclusive scan of the per-lane maps inside the warp
             GfDelta F = G;
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) {
@@ -332,42 +338,68 @@ gf_walk_kernel(const GfPassDev *__restrict__ passes, GfPassScal *scal, int n_pas
                 a.d1 = __shfl_up_sync(0xffffffffu, F.d1, o);
                 if (lane >= o) F = gf_delta_then(a, F);
             }
-            GfDelta E;
-            E.d0 = __shfl_up_sync(0xffffffffu, F.d0, 1);
-            E.d1 = __shfl_up_sync(0xffffffffu, F.d1, 1);
-            if (lane == 0) { E.d0 = 0ull; E.d1 = 0ull; }
+            float lastv = 0.0f; bool hasv = false;
+#pragma unroll
+            for (int j = 0; j < GF_WALK_S; ++j) if ((i0 + j < n) && ((double)f[j] > 1e-6)) { lastv = f[j]; hasv = true; }
+            const unsigned hv = __ballot_sync(0xffffffffu, hasv);
+            const bool any_ev = __any_sync(0xffffffffu, ev);
+            if (lane == 31) s_tot[w] = F;
+            if (lane == 0) {
+                s_bad[w] = any_ev;
+                s_hasv[w] = hv != 0u;
+            }
+            if (hv && lane == 31 - __clz(hv)) s_lastv[w] = lastv;
+            __syncthreads();
+            // map from the block start to this lane's first sample: earlier warps, then the earlier lanes of this warp
+            GfDelta E; E.d0 = 0ull; E.d1 = 0ull;
+            for (int q = 0; q < w; ++q) E = gf_delta_then(E, s_tot[q]);
+            GfDelta T = E;                                        // ... and to the end of the block (all warps)
+            for (int q = w; q < GF_WALK_WARPS; ++q) T = gf_delta_then(T, s_tot[q]);
+            {
+                GfDelta p;
+                p.d0 = __shfl_up_sync(0xffffffffu, F.d0, 1);
+                p.d1 = __shfl_up_sync(0xffffffffu, F.d1, 1);
+                if (lane > 0) E = gf_delta_then(E, p);
+            }
+            bool bad = false;
+            float lv_prior = lv_carry;                            // last valid f0 before this warp's samples
+            for (int q = 0; q < GF_WALK_WARPS; ++q) {
+                bad |= s_bad[q] != 0;
+                if (q < w && s_hasv[q]) lv_prior = s_lastv[q];
+            }
+            float lv_block = lv_carry;
+            for (int q = 0; q < GF_WALK_WARPS; ++q) if (s_hasv[q]) lv_block = s_lastv[q];
             unsigned long long Mj = M + ((M & 1ull) ? E.d1 : E.d0);
             const int sh = 52 - e;
-            int mprev_lane;                                      // floor(total) before this lane's first sample
             int m[GF_WALK_S];
 #pragma unroll
             for (int j = 0; j < GF_WALK_S; ++j) {
                 Mj += (Mj & 1ull) ? d[j].d1 : d[j].d0;
                 m[j] = max((e >= 0) ? (int)(Mj >> sh) : 0, fired);       // running max (the total may have dipped earlier)
             }
-            const bool carry = Mj >= ONE53;                      // mantissas only grow on this path: the last one decides
-            fast_ok = !__any_sync(0xffffffffu, ev || carry);
+            const unsigned long long Mend = M + ((M & 1ull) ? T.d1 : T.d0);
+            bad |= Mend >= ONE53;                                 // mantissas only grow on this path: the block's last one decides
+            __syncthreads();                                      // s_tot / s_bad are rewritten below and in the next block
+            if (lane == 31) s_mlast[w] = m[GF_WALK_S - 1];
+            __syncthreads();
+            fast_ok = !bad;
             if (fast_ok) {
-                mprev_lane = __shfl_up_sync(0xffffffffu, m[GF_WALK_S - 1], 1);
-                if (lane == 0) mprev_lane = fired;
+                const int mprev_warp = (w == 0) ? fired : s_mlast[w - 1];
+                const int m_end = s_mlast[GF_WALK_WARPS - 1];
+                int mprev_lane = __shfl_up_sync(0xffffffffu, m[GF_WALK_S - 1], 1);
+                if (lane == 0) mprev_lane = mprev_warp;
                 const int lane_cnt = m[GF_WALK_S - 1] - mprev_lane;          // onsets inside this lane's run (totals never decrease here)
-                // last f0 > 1e-6 before this lane's run
-                float lastv = 0.0f; bool hasv = false;
-#pragma unroll
-                for (int j = 0; j < GF_WALK_S; ++j) if ((i0 + j < n) && ((double)f[j] > 1e-6)) { lastv = f[j]; hasv = true; }
-                const unsigned hv = __ballot_sync(0xffffffffu, hasv);
                 const unsigned below = hv & ((1u << lane) - 1u);
                 const float prior = __shfl_sync(0xffffffffu, lastv, below ? (31 - __clz(below)) : 0);
-                float lv = below ? prior : lv_carry;
-                const int tot_cnt = __shfl_sync(0xffffffffu, m[GF_WALK_S - 1], 31) - fired;
-                if (tot_cnt > 0) {
+                float lv = below ? prior : lv_prior;
+                if (m_end > fired) {
                     int incl = lane_cnt;
 #pragma unroll
                     for (int o = 1; o < 32; o <<= 1) {
                         const int v = __shfl_up_sync(0xffffffffu, incl, o);
                         if (lane >= o) incl += v;
                     }
-                    int slot = count + incl - lane_cnt;
+                    int slot = count + (mprev_warp - fired) + incl - lane_cnt;
                     int mp = mprev_lane;
 #pragma unroll
                     for (int j = 0; j < GF_WALK_S; ++j) {
@@ -376,13 +408,15 @@ gf_walk_kernel(const GfPassDev *__restrict__ passes, GfPassScal *scal, int n_pas
                             if (slot < ps.onset_cap) ps.onsets[slot] = make_int4(i0 + j, 0, __float_as_int(lv), 0);   // T0 / table max: gf_onset_kernel
                         mp = m[j];
                     }
-                    count += tot_cnt;
-                    fired += tot_cnt;
+                    count += m_end - fired;
+                    fired = m_end;
                 }
-                if (hv) lv_carry = __shfl_sync(0xffffffffu, lastv, 31 - __clz(hv));
-                M = __shfl_sync(0xffffffffu, Mj, 31);
+                lv_carry = lv_block;
+                M = Mend;
+                __syncthreads();                                  // s_mlast is reused by the next block
                 continue;
             }
+            __syncthreads();
         }
         // ================= slow path: one sample per lane, exponent events as real fp64 additions =================
         int base = blk;
@@ -452,14 +486,14 @@ gf_walk_kernel(const GfPassDev *__restrict__ passes, GfPassScal *scal, int n_pas
                 const float cand = __shfl_sync(0xffffffffu, f, below ? (31 - __clz(below)) : 0);
                 const float lvf = below ? cand : lv_carry;
                 for (int c = 0; c < cnt; ++c, ++slot)
-                    if (slot < ps.onset_cap) ps.onsets[slot] = make_int4(i, 0, __float_as_int(lvf), 0);
+                    if (w == 0 && slot < ps.onset_cap) ps.onsets[slot] = make_int4(i, 0, __float_as_int(lvf), 0);
                 fired = max(fired, gmax);
             }
             if (bal) lv_carry = __shfl_sync(0xffffffffu, f, 31 - __clz(bal));
             base += last_lane + 1;
         }
     }
-    if (lane == 0) {
+    if (threadIdx.x == 0) {
         scal[pi].n_onsets = min(count, ps.onset_cap);
         if (count > ps.onset_cap) scal[pi].err = 1;
     }
@@ -502,10 +536,15 @@ gf_onset_kernel(const GfPassDev *__restrict__ passes, GfPassScal *scal, int sr_i
     if ((threadIdx.x & 31) == 0 && mx > 0) atomicMax(&scal[blockIdx.y].max_T0, mx);
 }
 
-void gf_launch_walk(const GfPassDev *passes, GfPassScal *scal, int n_pass, int sr, cudaStream_t st)
+void gf_launch_walk(const GfPassDev *passes, GfPassScal *scal, int n_pass, int max_n, int sr, cudaStream_t st)
 {
     if (n_pass <= 0) return;
-    gf_walk_kernel<<<(n_pass + GF_WALK_WARPS - 1) / GF_WALK_WARPS, 32 * GF_WALK_WARPS, 0, st>>>(passes, scal, n_pass, sr);
+    // One warp per note is latency bound (a few hundred dependent steps per 256 samples) and costs the fewest issue
+    // slots: right when there are enough notes to fill the GPU.  Four warps per note cut the latency by ~3x but
+    // repeat the slow path in every warp: right for few and / or long notes.
+    const bool wide = n_pass <= 384 || (max_n >= 4 * 44100 && n_pass <= 1024);
+    if (wide) gf_walk_kernel<4><<<n_pass, 128, 0, st>>>(passes, scal, n_pass, sr);
+    else gf_walk_kernel<1><<<n_pass, 32, 0, st>>>(passes, scal, n_pass, sr);
     gf_onset_kernel<<<dim3(4, n_pass), 128, 0, st>>>(passes, scal, sr);
 }
 
