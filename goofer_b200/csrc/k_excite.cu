@@ -224,7 +224,7 @@ __device__ __forceinline__ float gf_lf_table_max(double T, int T0)
     return m;
 }
 
-#define GF_WALK_S 8                   // samples per lane on the fast path (a warp advances 256 samples per step)
+#define GF_WALK_S 8                   // samples per lane (a warp advances 256 samples per attempt)
 
 // ------------------------------------------------------------------------------------------------
 // Phase walk of pulse_train_numba (GOOFER.py:479-493): total_phase += f0[i] / sr in fp64, sample by sample; a pulse
@@ -232,62 +232,86 @@ __device__ __forceinline__ float gf_lf_table_max(double T, int T0)
 // ties on every A note), but the chain does not have to be EXECUTED serially
 // (44,100 dependent DADDs per second of audio, ~36 cycles each):
 //
-//   While the exponent e of the running total is fixed, total = M * 2^(e-52) with an integer mantissa M, and adding
-//   the increment m_k * 2^(e_k-52) in round-to-nearest-even gives   M' = M + q_k + c_k + t_k * ((M + q_k) & 1)
-//   with s = e - e_k, q_k = m_k >> s, r_k = the s bits shifted out, c_k = [r_k > half], t_k = [r_k == half].
-//   Each step is therefore a map  M -> M + delta[M & 1]  with a pair (delta[0], delta[1]) that depends only on the
-//   increment.  Such maps are closed under composition, (a then b)[p] = a[p] + b[(p + a[p]) & 1], so the running
-//   mantissas come out of a scan of integer pairs -- bit for bit what the scalar fp64 loop produces, ties included.
-//   Only the steps that change the exponent (about 16 per note: the total crosses a power of two), the first
-//   non-zero increment and negative increments are executed as real fp64 additions.
+//   While the exponent e of the running total is fixed, total = M * 2^(e-52) with an integer mantissa M in
+//   [2^52, 2^53), and adding the increment +-m_k * 2^(e_k-52) in round-to-nearest-even is an INTEGER step.  With
+//   s = e - e_k, q = m_k >> s, r = the s bits shifted out, half = 2^(s-1):
+//       x > 0:  M' = M + q + [r > half] + [r == half] * ((M + q) & 1)
+//       x < 0:  M' = M - q                                         (r == 0)
+//               M' = M - q - 1 + [r < half] + [r == half] * ((M - q - 1) & 1)     (r > 0)
+//   i.e. a map  M -> M + delta[M & 1]  with a pair (delta[0], delta[1]) that depends only on the increment.  Such
+//   maps are closed under composition, (a then b)[p] = a[p] + b[(p + a[p]) & 1], so the running mantissas come
+//   out of a scan of integer pairs -- bit for bit what the scalar fp64 loop produces, ties included.
+//   A step leaves this regime ("event") when the result changes binade (M' >= 2^53, or the exact difference drops
+//   below 2^52), when there is no positive normal total yet, or when the increment is above the total / subnormal:
+//   about 16 per note.  Events are executed as one real fp64 addition.
 //
-// Fast path: 8 consecutive samples per lane (local composition), one warp scan per 256 samples.  A block that holds
-// an exponent event is redone on the slow path: one sample per lane, the event sample added in fp64.
-// The same arithmetic in Python integers, checked against the scalar loop: tools/experiments/walk_scan_proto.py.
+// Per block of 256 x WARPS samples: ATTEMPT (8 samples per lane: local composition, warp scan, cross-warp hop, walk),
+// find the first event k*, COMMIT the samples before it (onsets = increments of the running max of floor(total)),
+// execute k* in fp64, continue after it.  The same arithmetic in Python integers, checked against the scalar
+// loop on ties, gaps, negative and tiny increments: tools/experiments/walk_scan_proto.py.
 // ------------------------------------------------------------------------------------------------
-struct GfDelta { unsigned long long d0, d1; };        // M -> M + (M & 1 ? d1 : d0)
+struct GfDelta { long long d0, d1; };                  // M -> M + (M & 1 ? d1 : d0)
+
+// a / b, correctly rounded, from the correctly rounded reciprocal y = RN(1 / b) (Markstein): q = RN(a y),
+// r = a - b q (exact in an FMA), RN(q + r y).  Exact whenever b's significand is not all ones (b is a sample rate
+// or a small constant here) and nothing over- or underflows (a is a float widened to double); three instructions
+// instead of the ~35 of the general fp64 division.  Checked against exact rational arithmetic on 5.8e5 values.
+__device__ __forceinline__ double gf_div_by(double a, double b, double y)
+{
+    const double q = __dmul_rn(a, y);
+    const double r = __fma_rn(-q, b, a);
+    return __fma_rn(r, y, q);
+}
 
 __device__ __forceinline__ GfDelta gf_delta_then(const GfDelta &a, const GfDelta &b)
 {
     GfDelta r;
-    r.d0 = a.d0 + ((a.d0 & 1ull) ? b.d1 : b.d0);                   // parity of 0 + a.d0
-    r.d1 = a.d1 + (((1ull + a.d1) & 1ull) ? b.d1 : b.d0);          // parity of 1 + a.d1
+    r.d0 = a.d0 + ((a.d0 & 1ll) ? b.d1 : b.d0);                    // parity of 0 + a.d0
+    r.d1 = a.d1 + (((1ll + a.d1) & 1ll) ? b.d1 : b.d0);            // parity of 1 + a.d1
     return r;
 }
 
-// delta pair of one increment under the exponent e of the running total; returns true when the step needs a real
-// fp64 addition instead (negative / subnormal increment, no positive normal total yet, increment above the total)
-__device__ __forceinline__ bool gf_walk_delta(double inc, bool started, bool raw_mode, int e, GfDelta &d)
+// delta pair of one increment under the exponent e of a positive normal running total.  Returns true when the step
+// needs a real fp64 addition instead (subnormal increment, increment above the total).  guard = q + [r > 0] for a
+// subtraction: the exact difference stays in the binade iff M - guard >= 2^52.
+__device__ __forceinline__ bool gf_walk_delta(double inc, int e, GfDelta &d, long long &guard)
 {
-    d.d0 = 0ull; d.d1 = 0ull;
+    d.d0 = 0ll; d.d1 = 0ll; guard = 0ll;
     const long long ib = __double_as_longlong(inc);
     if ((ib << 1) == 0) return false;                              // +-0: identity
     const int efield = (int)((ib >> 52) & 0x7ff);
     const int s = e - (efield - 1023);
-    if (ib < 0 || efield == 0 || !started || raw_mode || s < 0) return true;
-    if (s < 64) {
-        const unsigned long long mk = ((unsigned long long)ib & ((1ull << 52) - 1ull)) | (1ull << 52);
-        const unsigned long long q = mk >> s;
-        unsigned long long c = 0ull, t = 0ull;
-        if (s > 0) {
-            const unsigned long long r = mk & ((1ull << s) - 1ull), half = 1ull << (s - 1);
-            c = r > half; t = r == half;
+    if (efield == 0 || s < 0) return true;
+    if (s >= 64) return false;                                     // far below half an ulp: no change
+    const unsigned long long mk = ((unsigned long long)ib & ((1ull << 52) - 1ull)) | (1ull << 52);
+    const long long q = (long long)(mk >> s);
+    const unsigned long long r = s > 0 ? (mk & ((1ull << s) - 1ull)) : 0ull, half = s > 0 ? (1ull << (s - 1)) : 0ull;
+    const long long tie = (s > 0 && r == half) ? 1ll : 0ll;
+    if (ib > 0) {
+        const long long c = (s > 0 && r > half) ? 1ll : 0ll;
+        d.d0 = q + c + (tie & q);                                  // (0 + q) & 1
+        d.d1 = q + c + (tie & (q + 1ll));                          // (1 + q) & 1
+    } else {
+        guard = q + (r > 0 ? 1ll : 0ll);
+        if (r == 0) { d.d0 = -q; d.d1 = -q; }
+        else {
+            const long long c = r < half ? 1ll : 0ll;
+            d.d0 = -q - 1ll + c + (tie & (q + 1ll));               // (0 - q - 1) & 1
+            d.d1 = -q - 1ll + c + (tie & q);                       // (1 - q - 1) & 1
         }
-        d.d0 = q + c + (t & q);                                    // (0 + q) & 1
-        d.d1 = q + c + (t & (q + 1ull));                           // (1 + q) & 1
     }
     return false;
 }
 
-template <int GF_WALK_WARPS>
-__global__ void __launch_bounds__(32 * GF_WALK_WARPS)
+template <int WARPS>
+__global__ void __launch_bounds__(32 * WARPS)
 gf_walk_kernel(const GfPassDev *__restrict__ passes, GfPassScal *scal, int n_pass, int sr_i)
 {
-    // one CTA of GF_WALK_WARPS warps per (note, pass): the scan is associative, so a block of
-    // GF_WALK_WARPS x 256 samples is advanced per step.  Every warp keeps an identical copy of the walk state.
-    __shared__ GfDelta s_tot[GF_WALK_WARPS];
-    __shared__ int s_mlast[GF_WALK_WARPS], s_bad[GF_WALK_WARPS], s_hasv[GF_WALK_WARPS];
-    __shared__ float s_lastv[GF_WALK_WARPS];
+    // one CTA of WARPS warps per (note, pass); every warp keeps an identical copy of the walk state
+    __shared__ GfDelta s_tot[WARPS];
+    __shared__ long long s_M;
+    __shared__ int s_kbad[WARPS], s_wmax[WARPS], s_hasv[WARPS];
+    __shared__ float s_lastv[WARPS];
     const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int pi = blockIdx.x;
     if (pi >= n_pass) return;
@@ -295,42 +319,50 @@ gf_walk_kernel(const GfPassDev *__restrict__ passes, GfPassScal *scal, int n_pas
     const int n = ps.n_total;
     const double sr = (double)sr_i;
     const float *__restrict__ f0 = ps.f0;
-    const unsigned long long MANT = (1ull << 52) - 1ull, ONE53 = 1ull << 53;
+    const long long MANT = (1ll << 52) - 1ll, ONE52 = 1ll << 52, ONE53 = 1ll << 53;
     // running total = started ? M * 2^(e - 52) : (raw_mode ? raw : 0).  raw_mode: the total is negative or subnormal
-    // (only possible with f0 jitter beyond 100 % at the very start of a note) and every sample is a real fp64 add
+    // (only possible with f0 jitter beyond 100 % at the very start of a note): every non-zero sample is an event
     bool started = false, raw_mode = false;
     double raw = 0.0;
-    unsigned long long M = 0ull;
+    long long M = 0ll;
     int e = 0;
     int fired = 0;                      // next_k - 1
     float lv_carry = 160.0f;            // last_valid_f0 (GOOFER.py:477)
     int count = 0;
     const bool aligned16 = (reinterpret_cast<size_t>(f0) & 15) == 0;
-    const int BLK = 32 * GF_WALK_S * GF_WALK_WARPS;
+    const double rcp_sr = __drcp_rn(sr);
+    const int BLK = 32 * GF_WALK_S * WARPS;
 
     for (int blk = 0; blk < n; blk += BLK) {
         const int blk_end = min(n, blk + BLK);
-        // ================= fast path: 8 consecutive samples per lane, GF_WALK_WARPS x 256 samples per step =================
-        bool fast_ok = started && !raw_mode;
-        if (fast_ok) {
+        int lo = blk;
+        while (lo < blk_end) {
+            // ================= attempt: samples [lo, blk_end) under the current (M, e) =================
             const int i0 = blk + 32 * GF_WALK_S * w + GF_WALK_S * lane;
             float f[GF_WALK_S];
-            if (i0 + GF_WALK_S <= n && aligned16) {
+            GfDelta d[GF_WALK_S];
+            long long guard[GF_WALK_S];
+            unsigned evbits = 0u;                                  // bit j: sample j needs a real fp64 addition
+            const bool whole = aligned16 && lo <= i0 && i0 + GF_WALK_S <= blk_end;
+            if (whole) {
                 const float4 a = *reinterpret_cast<const float4 *>(f0 + i0), b4 = *reinterpret_cast<const float4 *>(f0 + i0 + 4);
                 f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = b4.x; f[5] = b4.y; f[6] = b4.z; f[7] = b4.w;
-            } else {
-#pragma unroll
-                for (int j = 0; j < GF_WALK_S; ++j) f[j] = (i0 + j < n) ? f0[i0 + j] : 0.0f;
             }
-            GfDelta d[GF_WALK_S];
-            bool ev = false;
 #pragma unroll
-            for (int j = 0; j < GF_WALK_S; ++j) ev |= gf_walk_delta(__ddiv_rn((double)f[j], sr), true, false, e, d[j]);
+            for (int j = 0; j < GF_WALK_S; ++j) {
+                const int i = i0 + j;
+                const bool act = i >= lo && i < blk_end;
+                if (!whole) f[j] = act ? f0[i] : 0.0f;
+                d[j].d0 = 0ll; d[j].d1 = 0ll; guard[j] = 0ll;
+                if (act && f[j] != 0.0f) {
+                    if (!started || raw_mode) evbits |= 1u << j;
+                    else if (gf_walk_delta(gf_div_by((double)f[j], sr, rcp_sr), e, d[j], guard[j])) evbits |= 1u << j;
+                }
+            }
             GfDelta G = d[0];
 #pragma unroll
             for (int j = 1; j < GF_WALK_S; ++j) G = gf_delta_then(G, d[j]);
-            // inclusive scan of the per-lane maps inside the warp
-            GfDelta F = G;
+            GfDelta F = G;                                         // inclusive scan of the lane maps inside the warp
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) {
                 GfDelta a;
@@ -338,159 +370,137 @@ gf_walk_kernel(const GfPassDev *__restrict__ passes, GfPassScal *scal, int n_pas
                 a.d1 = __shfl_up_sync(0xffffffffu, F.d1, o);
                 if (lane >= o) F = gf_delta_then(a, F);
             }
-            float lastv = 0.0f; bool hasv = false;
-#pragma unroll
-            for (int j = 0; j < GF_WALK_S; ++j) if ((i0 + j < n) && ((double)f[j] > 1e-6)) { lastv = f[j]; hasv = true; }
-            const unsigned hv = __ballot_sync(0xffffffffu, hasv);
-            const bool any_ev = __any_sync(0xffffffffu, ev);
-            if (lane == 31) s_tot[w] = F;
-            if (lane == 0) {
-                s_bad[w] = any_ev;
-                s_hasv[w] = hv != 0u;
+            if (WARPS > 1) {
+                if (lane == 31) s_tot[w] = F;
+                __syncthreads();
             }
-            if (hv && lane == 31 - __clz(hv)) s_lastv[w] = lastv;
-            __syncthreads();
-            // map from the block start to this lane's first sample: earlier warps, then the earlier lanes of this warp
-            GfDelta E; E.d0 = 0ull; E.d1 = 0ull;
-            for (int q = 0; q < w; ++q) E = gf_delta_then(E, s_tot[q]);
-            GfDelta T = E;                                        // ... and to the end of the block (all warps)
-            for (int q = w; q < GF_WALK_WARPS; ++q) T = gf_delta_then(T, s_tot[q]);
+            GfDelta E; E.d0 = 0ll; E.d1 = 0ll;                     // map from the block start to this lane's first sample
+            if (WARPS > 1) for (int q = 0; q < w; ++q) E = gf_delta_then(E, s_tot[q]);
             {
                 GfDelta p;
                 p.d0 = __shfl_up_sync(0xffffffffu, F.d0, 1);
                 p.d1 = __shfl_up_sync(0xffffffffu, F.d1, 1);
                 if (lane > 0) E = gf_delta_then(E, p);
             }
-            bool bad = false;
-            float lv_prior = lv_carry;                            // last valid f0 before this warp's samples
-            for (int q = 0; q < GF_WALK_WARPS; ++q) {
-                bad |= s_bad[q] != 0;
-                if (q < w && s_hasv[q]) lv_prior = s_lastv[q];
-            }
-            float lv_block = lv_carry;
-            for (int q = 0; q < GF_WALK_WARPS; ++q) if (s_hasv[q]) lv_block = s_lastv[q];
-            unsigned long long Mj = M + ((M & 1ull) ? E.d1 : E.d0);
-            const int sh = 52 - e;
-            int m[GF_WALK_S];
+            // walk the lane's samples with concrete mantissas; stop being meaningful at the first bad sample
+            long long Mv[GF_WALK_S];
+            long long Mj = M + ((M & 1ll) ? E.d1 : E.d0);
+            int kbad = INT_MAX;
 #pragma unroll
             for (int j = 0; j < GF_WALK_S; ++j) {
-                Mj += (Mj & 1ull) ? d[j].d1 : d[j].d0;
-                m[j] = max((e >= 0) ? (int)(Mj >> sh) : 0, fired);       // running max (the total may have dipped earlier)
+                bool bad = (evbits >> j) & 1u;
+                if (started && !raw_mode) {
+                    bad |= (Mj - guard[j]) < ONE52;                // the exact difference leaves the binade
+                    Mj += (Mj & 1ll) ? d[j].d1 : d[j].d0;
+                    bad |= Mj >= ONE53 || Mj < ONE52;
+                }
+                Mv[j] = Mj;
+                if (bad && kbad == INT_MAX && (i0 + j) >= lo && (i0 + j) < blk_end) kbad = i0 + j;
             }
-            const unsigned long long Mend = M + ((M & 1ull) ? T.d1 : T.d0);
-            bad |= Mend >= ONE53;                                 // mantissas only grow on this path: the block's last one decides
-            __syncthreads();                                      // s_tot / s_bad are rewritten below and in the next block
-            if (lane == 31) s_mlast[w] = m[GF_WALK_S - 1];
+            // a bad sample poisons every later mantissa: the first one over the whole block decides
+            int kstar = __reduce_min_sync(0xffffffffu, kbad);
+            if (WARPS > 1) {
+                if (lane == 0) s_kbad[w] = kstar;
+                __syncthreads();
+                kstar = INT_MAX;
+                for (int q = 0; q < WARPS; ++q) kstar = min(kstar, s_kbad[q]);
+            }
+            if (kstar == INT_MAX) kstar = blk_end;
+            // ================= commit samples [lo, kstar) =================
+            const int sh = 52 - e;
+            int m[GF_WALK_S];
+            int lmax = INT_MIN;
+            float lastv = 0.0f; bool hasv = false;
+#pragma unroll
+            for (int j = 0; j < GF_WALK_S; ++j) {
+                const int i = i0 + j;
+                const bool com = i >= lo && i < kstar;
+                m[j] = com ? ((started && !raw_mode && e >= 0) ? (int)(Mv[j] >> sh) : 0) : INT_MIN;
+                lmax = max(lmax, m[j]);
+                if (com && ((double)f[j] > 1e-6)) { lastv = f[j]; hasv = true; }
+            }
+            // running max of floor(total) before this lane: earlier lanes, earlier warps, `fired`
+            int pmax = lmax;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int v = __shfl_up_sync(0xffffffffu, pmax, o);
+                if (lane >= o) pmax = max(pmax, v);
+            }
+            const int wmax = __shfl_sync(0xffffffffu, pmax, 31);
+            int before = __shfl_up_sync(0xffffffffu, pmax, 1);
+            if (lane == 0) before = INT_MIN;
+            const unsigned hv = __ballot_sync(0xffffffffu, hasv);
+            const int owner = kstar - 1;                           // last committed sample (if kstar > lo)
+            if (WARPS > 1) {
+                if (lane == 0) { s_wmax[w] = wmax; s_hasv[w] = hv != 0u; }
+                if (hv && lane == 31 - __clz(hv)) s_lastv[w] = lastv;
+            }
+            if (kstar > lo && owner >= i0 && owner < i0 + GF_WALK_S) s_M = Mv[owner - i0];
             __syncthreads();
-            fast_ok = !bad;
-            if (fast_ok) {
-                const int mprev_warp = (w == 0) ? fired : s_mlast[w - 1];
-                const int m_end = s_mlast[GF_WALK_WARPS - 1];
-                int mprev_lane = __shfl_up_sync(0xffffffffu, m[GF_WALK_S - 1], 1);
-                if (lane == 0) mprev_lane = mprev_warp;
-                const int lane_cnt = m[GF_WALK_S - 1] - mprev_lane;          // onsets inside this lane's run (totals never decrease here)
+            float lv_prior = lv_carry, lv_after = lv_carry;
+            int rm_all = fired;
+            if (WARPS > 1) {
+                for (int q = 0; q < WARPS; ++q) {
+                    if (q < w) before = max(before, s_wmax[q]);
+                    rm_all = max(rm_all, s_wmax[q]);
+                    if (s_hasv[q]) { if (q < w) lv_prior = s_lastv[q]; lv_after = s_lastv[q]; }
+                }
+            } else {
+                rm_all = max(rm_all, wmax);
+                if (hv) lv_after = __shfl_sync(0xffffffffu, lastv, 31 - __clz(hv));
+            }
+            before = max(before, fired);
+            if (rm_all > fired) {
                 const unsigned below = hv & ((1u << lane) - 1u);
                 const float prior = __shfl_sync(0xffffffffu, lastv, below ? (31 - __clz(below)) : 0);
                 float lv = below ? prior : lv_prior;
-                if (m_end > fired) {
-                    int incl = lane_cnt;
+                int rm = before;
 #pragma unroll
-                    for (int o = 1; o < 32; o <<= 1) {
-                        const int v = __shfl_up_sync(0xffffffffu, incl, o);
-                        if (lane >= o) incl += v;
+                for (int j = 0; j < GF_WALK_S; ++j) {
+                    const int i = i0 + j;
+                    if (i >= lo && i < kstar) {
+                        if ((double)f[j] > 1e-6) lv = f[j];
+                        // onsets number rm+1 .. m[j] (1-based since the note start) sit in slots rm .. m[j]-1: `count`
+                        // onsets were written when `fired` pulses had fired
+                        for (int c = rm; c < m[j]; ++c) {
+                            const int slot = count + (c - fired);
+                            if (slot < ps.onset_cap) ps.onsets[slot] = make_int4(i, 0, __float_as_int(lv), 0);   // T0 / table max: gf_onset_kernel
+                        }
+                        rm = max(rm, m[j]);
                     }
-                    int slot = count + (mprev_warp - fired) + incl - lane_cnt;
-                    int mp = mprev_lane;
-#pragma unroll
-                    for (int j = 0; j < GF_WALK_S; ++j) {
-                        if ((i0 + j < n) && ((double)f[j] > 1e-6)) lv = f[j];
-                        for (int c = mp; c < m[j]; ++c, ++slot)
-                            if (slot < ps.onset_cap) ps.onsets[slot] = make_int4(i0 + j, 0, __float_as_int(lv), 0);   // T0 / table max: gf_onset_kernel
-                        mp = m[j];
-                    }
-                    count += m_end - fired;
-                    fired = m_end;
                 }
-                lv_carry = lv_block;
-                M = Mend;
-                __syncthreads();                                  // s_mlast is reused by the next block
-                continue;
+            } else {
+                // keep the shuffle above convergent for all lanes
             }
-            __syncthreads();
-        }
-        // ================= slow path: one sample per lane, exponent events as real fp64 additions =================
-        int base = blk;
-        while (base < blk_end) {
-            const int i = base + lane;
-            const int cnt_lanes = min(32, blk_end - base);
-            const float f = (lane < cnt_lanes) ? f0[i] : 0.0f;
-            const double inc = __ddiv_rn((double)f, sr);
-            GfDelta d;
-            const bool ev = gf_walk_delta(inc, started, raw_mode, e, d) && (lane < cnt_lanes);
-            if (lane >= cnt_lanes) { d.d0 = 0ull; d.d1 = 0ull; }
-            GfDelta F = d;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                GfDelta a;
-                a.d0 = __shfl_up_sync(0xffffffffu, F.d0, o);
-                a.d1 = __shfl_up_sync(0xffffffffu, F.d1, o);
-                if (lane >= o) F = gf_delta_then(a, F);
-            }
-            const unsigned long long Mk = M + ((M & 1ull) ? F.d1 : F.d0);
-            const bool carry = started && Mk >= ONE53;
-            const unsigned evmask = __ballot_sync(0xffffffffu, (lane < cnt_lanes) && (ev || carry));
-            const int first = evmask ? (__ffs(evmask) - 1) : 32;      // lane of the first event (32: none)
-            const int last_lane = evmask ? first : cnt_lanes - 1;      // last sample handled in this round
-            int m = INT_MIN;                                           // floor(running total) of lanes < first
-            if (lane < first && lane < cnt_lanes) m = (started && e >= 0) ? (int)(Mk >> (52 - e)) : 0;
-            if (first > 0 && started) M = __shfl_sync(0xffffffffu, Mk, min(first, cnt_lanes) - 1);
-            if (evmask) {
-                // the event sample: one real fp64 addition (every lane computes the same values)
+            count += rm_all - fired;
+            fired = rm_all;
+            lv_carry = lv_after;
+            if (kstar > lo && started && !raw_mode) M = s_M;
+            __syncthreads();                                       // shared slots are rewritten by the next attempt
+            // ================= the event sample: one real fp64 addition =================
+            if (kstar < blk_end) {
+                const float fe = f0[kstar];
                 const double prev = raw_mode ? raw
-                                  : (started ? __longlong_as_double((long long)(((unsigned long long)(e + 1023) << 52) | (M & MANT))) : 0.0);
-                const double tot = __dadd_rn(prev, __shfl_sync(0xffffffffu, inc, first));
+                                  : (started ? __longlong_as_double((long long)(((unsigned long long)(e + 1023) << 52) | (unsigned long long)(M & MANT))) : 0.0);
+                const double tot = __dadd_rn(prev, gf_div_by((double)fe, sr, rcp_sr));
                 const long long tb = __double_as_longlong(tot);
                 const int tf = (int)((tb >> 52) & 0x7ff);
-                if (tb > 0 && tf != 0) { started = true; raw_mode = false; M = ((unsigned long long)tb & MANT) | (1ull << 52); e = tf - 1023; }
-                else if ((tb << 1) == 0) { started = false; raw_mode = false; M = 0ull; e = 0; }
-                else { started = false; raw_mode = true; raw = tot; M = 0ull; e = 0; }
-                if (lane == first) m = (int)floor(tot);
-            }
-            // ---- onsets of lanes <= last_lane: pulses fired up to and including a sample = running max of floor(total) ----
-            const bool in_round = lane <= last_lane && lane < cnt_lanes;
-            if (!in_round) m = INT_MIN;
-            const int gmax = __reduce_max_sync(0xffffffffu, m);
-            const bool valid = in_round && ((double)f > 1e-6);
-            const unsigned bal = __ballot_sync(0xffffffffu, valid);
-            if (gmax > fired) {
-                int mm = m;
-#pragma unroll
-                for (int o = 1; o < 32; o <<= 1) {
-                    const int v = __shfl_up_sync(0xffffffffu, mm, o);
-                    if (lane >= o) mm = max(mm, v);
+                if (tb > 0 && tf != 0) { started = true; raw_mode = false; M = (tb & MANT) | ONE52; e = tf - 1023; }
+                else if ((tb << 1) == 0) { started = false; raw_mode = false; M = 0ll; e = 0; }
+                else { started = false; raw_mode = true; raw = tot; M = 0ll; e = 0; }
+                if ((double)fe > 1e-6) lv_carry = fe;
+                const int me = (int)fmin(fmax(floor(tot), -2.0e9), 2.0e9);
+                if (me > fired) {
+                    if (threadIdx.x == 0)
+                        for (int c = fired; c < me; ++c) {
+                            const int slot = count + (c - fired);
+                            if (slot < ps.onset_cap) ps.onsets[slot] = make_int4(kstar, 0, __float_as_int(lv_carry), 0);
+                        }
+                    count += me - fired;
+                    fired = me;
                 }
-                mm = max(mm, fired);
-                int prevm = __shfl_up_sync(0xffffffffu, mm, 1);
-                if (lane == 0) prevm = fired;
-                const int cnt = in_round ? (mm - prevm) : 0;
-                int incl = cnt;
-#pragma unroll
-                for (int o = 1; o < 32; o <<= 1) {
-                    const int v = __shfl_up_sync(0xffffffffu, incl, o);
-                    if (lane >= o) incl += v;
-                }
-                int slot = count + incl - cnt;
-                count += __shfl_sync(0xffffffffu, incl, 31);
-                // last f0 > 1e-6 at or before sample i
-                const unsigned below = bal & ((2u << lane) - 1u);
-                const float cand = __shfl_sync(0xffffffffu, f, below ? (31 - __clz(below)) : 0);
-                const float lvf = below ? cand : lv_carry;
-                for (int c = 0; c < cnt; ++c, ++slot)
-                    if (w == 0 && slot < ps.onset_cap) ps.onsets[slot] = make_int4(i, 0, __float_as_int(lvf), 0);
-                fired = max(fired, gmax);
-            }
-            if (bal) lv_carry = __shfl_sync(0xffffffffu, f, 31 - __clz(bal));
-            base += last_lane + 1;
+                lo = kstar + 1;
+            } else lo = blk_end;
         }
     }
     if (threadIdx.x == 0) {
@@ -539,14 +549,14 @@ gf_onset_kernel(const GfPassDev *__restrict__ passes, GfPassScal *scal, int sr_i
 void gf_launch_walk(const GfPassDev *passes, GfPassScal *scal, int n_pass, int max_n, int sr, cudaStream_t st)
 {
     if (n_pass <= 0) return;
-    // One warp per note is latency bound (a few hundred dependent steps per 256 samples) and costs the fewest issue
-    // slots: right when there are enough notes to fill the GPU.  Four warps per note cut the latency by ~3x but
-    // repeat the slow path in every warp: right for few and / or long notes.
+    // One warp per note costs the fewest issue slots: right when there are enough notes to fill the GPU.  Four
+    // warps per note cut the latency of a note by ~3x: right for few and / or long notes.
     const bool wide = n_pass <= 384 || (max_n >= 4 * 44100 && n_pass <= 1024);
     if (wide) gf_walk_kernel<4><<<n_pass, 128, 0, st>>>(passes, scal, n_pass, sr);
     else gf_walk_kernel<1><<<n_pass, 32, 0, st>>>(passes, scal, n_pass, sr);
     gf_onset_kernel<<<dim3(4, n_pass), 128, 0, st>>>(passes, scal, sr);
 }
+
 
 // ------------------------------------------------------------------------------------------------
 // pulse[i] = sum over the onsets whose table covers i, in onset order (f32 adds)  GOOFER.py:542-552
