@@ -549,10 +549,15 @@ gf_onset_kernel(const GfPassDev *__restrict__ passes, GfPassScal *scal, int sr_i
 void gf_launch_walk(const GfPassDev *passes, GfPassScal *scal, int n_pass, int max_n, int sr, cudaStream_t st)
 {
     if (n_pass <= 0) return;
-    // One warp per note costs the fewest issue slots: right when there are enough notes to fill the GPU.  Four
-    // warps per note cut the latency of a note by ~3x: right for few and / or long notes.
-    const bool wide = n_pass <= 384 || (max_n >= 4 * 44100 && n_pass <= 1024);
-    if (wide) gf_walk_kernel<4><<<n_pass, 128, 0, st>>>(passes, scal, n_pass, sr);
+    // One warp per note costs the fewest issue slots: right when there are enough notes to fill the GPU.  Two or
+    // four warps per note cut the latency of a note: right for few and / or long notes (measured at 1,024 one-second
+    // notes: 0.82 / 0.66 / 0.69 ms with 1 / 2 / 4 warps).
+    static int force = -1;
+    if (force < 0) { const char *e = getenv("GOOFER_WALK_WARPS"); force = e ? atoi(e) : 0; }
+    int nw = (n_pass <= 512 || (max_n >= 4 * 44100 && n_pass <= 1024)) ? 4 : (n_pass <= 4096 ? 2 : 1);
+    if (force == 1 || force == 2 || force == 4) nw = force;
+    if (nw == 4) gf_walk_kernel<4><<<n_pass, 128, 0, st>>>(passes, scal, n_pass, sr);
+    else if (nw == 2) gf_walk_kernel<2><<<n_pass, 64, 0, st>>>(passes, scal, n_pass, sr);
     else gf_walk_kernel<1><<<n_pass, 32, 0, st>>>(passes, scal, n_pass, sr);
     gf_onset_kernel<<<dim3(4, n_pass), 128, 0, st>>>(passes, scal, sr);
 }
