@@ -14,6 +14,18 @@
 #include <cstdlib>
 
 #define GF_PI_D 3.141592653589793
+#define GF_RCP12 0.083333333333333329          // RN(1 / 12)
+
+// a / b, correctly rounded, from the correctly rounded reciprocal y = RN(1 / b) (Markstein): q = RN(a y),
+// r = a - b q (exact in an FMA), RN(q + r y).  Exact whenever b's significand is not all ones (b is a sample rate
+// or a small constant here) and nothing over- or underflows (a is a float widened to double); three instructions
+// instead of the ~35 of the general fp64 division.  Checked against exact rational arithmetic on 5.8e5 values.
+__device__ __forceinline__ double gf_div_by(double a, double b, double y)
+{
+    const double q = __dmul_rn(a, y);
+    const double r = __fma_rn(-q, b, a);
+    return __fma_rn(r, y, q);
+}
 
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ double gf_midi_at(const GfNotePlan &pl, const float *__restrict__ bend, int i)
@@ -21,19 +33,20 @@ __device__ __forceinline__ double gf_midi_at(const GfNotePlan &pl, const float *
     // SillySampler.py:836-853; interp1d == np.interp here because the query is clipped to the knots
     const double add = (double)pl.pitch_midi;
     const double tadd = pl.t_cents ? ((double)pl.t_cents / 100.0) : 0.0;
+    const double rcp100 = 0.01;                                    // RN(1 / 100)
     auto semi = [&](int k) {
-        double s = (double)bend[k] / 100.0 + add;
+        double s = gf_div_by((double)bend[k], 100.0, rcp100) + add;
         if (pl.t_cents) s = s + tadd;
         return s;
     };
     if (pl.bend_len == 1) return semi(0);
     const double dt = 60.0 / (pl.tempo * 96.0);
     const int last = pl.bend_len - 1;
-    double x = (double)i / (double)pl.sr;
+    double x = gf_div_by((double)i, (double)pl.sr, __drcp_rn((double)pl.sr));
     const double xl = (double)last * dt;
     x = fmin(fmax(x, 0.0), xl);
     if (x >= xl) return semi(last);
-    int j = (int)(x / dt);
+    int j = (int)(x * __drcp_rn(dt));                              // bracket estimate, fixed up below
     if (j > last - 1) j = last - 1;
     while (j > 0 && (double)j * dt > x) --j;
     while (j < last - 1 && (double)(j + 1) * dt <= x) ++j;
@@ -50,17 +63,17 @@ __device__ __forceinline__ double gf_midi_at_fast(const float *__restrict__ bend
 {
     const double tadd = t_cents ? ((double)t_cents / 100.0) : 0.0;
     auto semi = [&](int k) {
-        double s = (double)bend[k] / 100.0 + add;
+        double s = gf_div_by((double)bend[k], 100.0, 0.01) + add;
         if (t_cents) s = s + tadd;
         return s;
     };
     const double dt = 60.0 / (tempo * 96.0);
     const int last = bend_len - 1;
-    double x = (double)i / (double)sr;
+    double x = gf_div_by((double)i, (double)sr, __drcp_rn((double)sr));
     const double xl = (double)last * dt;
     x = fmin(fmax(x, 0.0), xl);
     if (x >= xl) return semi(last);
-    int j = (int)(x / dt);
+    int j = (int)(x * __drcp_rn(dt));                              // bracket estimate, fixed up below
     if (j > last - 1) j = last - 1;
     while (j > 0 && (double)j * dt > x) --j;
     while (j < last - 1 && (double)(j + 1) * dt <= x) ++j;
@@ -117,7 +130,7 @@ gf_f0_kernel(const GfNotePlan *__restrict__ plans, const GfNoteDev *__restrict__
             double hz = hz_flat;
             if (!flat) {
                 const double midi = gf_midi_at_fast(bend, pl.bend_len, (double)pl.pitch_midi, pl.t_cents, pl.tempo, sr_i, i);
-                hz = 440.0 * exp2((midi - 69.0) / 12.0);
+                hz = 440.0 * exp2(gf_div_by(midi - 69.0, 12.0, GF_RCP12));
             }
             out_f0[i] = (float)(m * hz);
         }
@@ -135,7 +148,7 @@ gf_f0_kernel(const GfNotePlan *__restrict__ plans, const GfNoteDev *__restrict__
         // without the velocity stretch mask_new is a plain copy of source samples: vm (f32) holds it exactly
         const double m = pl.vel_active ? gf_mask_new(pl, mask_src, i) : (double)nd.vm[i];
         const double midi = flat ? midi_flat : gf_midi_at(pl, bend, i);
-        const double hz = flat ? hz_flat : 440.0 * exp2((midi - 69.0) / 12.0);
+        const double hz = flat ? hz_flat : 440.0 * exp2(gf_div_by(midi - 69.0, 12.0, GF_RCP12));
         double f0 = m * hz;
         // ---- vocal fry f0 override (SillySampler.py:890-934) ----
         if (pl.fry_L > 0) {
@@ -248,20 +261,10 @@ __device__ __forceinline__ float gf_lf_table_max(double T, int T0)
 // Per block of 256 x WARPS samples: ATTEMPT (8 samples per lane: local composition, warp scan, cross-warp hop, walk),
 // find the first event k*, COMMIT the samples before it (onsets = increments of the running max of floor(total)),
 // execute k* in fp64, continue after it.  The same arithmetic in Python integers, checked against the scalar
-// loop on ties, gaps, negative and tiny increments: tools/experiments/walk_scan_proto.py.
+// loop on ties, gaps, negative and tiny increments: tests/test_walk_arith_cpu.py.
 // ------------------------------------------------------------------------------------------------
 struct GfDelta { long long d0, d1; };                  // M -> M + (M & 1 ? d1 : d0)
 
-// a / b, correctly rounded, from the correctly rounded reciprocal y = RN(1 / b) (Markstein): q = RN(a y),
-// r = a - b q (exact in an FMA), RN(q + r y).  Exact whenever b's significand is not all ones (b is a sample rate
-// or a small constant here) and nothing over- or underflows (a is a float widened to double); three instructions
-// instead of the ~35 of the general fp64 division.  Checked against exact rational arithmetic on 5.8e5 values.
-__device__ __forceinline__ double gf_div_by(double a, double b, double y)
-{
-    const double q = __dmul_rn(a, y);
-    const double r = __fma_rn(-q, b, a);
-    return __fma_rn(r, y, q);
-}
 
 __device__ __forceinline__ GfDelta gf_delta_then(const GfDelta &a, const GfDelta &b)
 {

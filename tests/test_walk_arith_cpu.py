@@ -1,0 +1,160 @@
+"""CPU: the integer arithmetic behind gf_walk_kernel (goofer_b200/csrc/k_excite.cu), restated with Python integers
+and exact rationals and checked against the scalar fp64 loop of pulse_train_numba (GOOFER.py:479-493).
+
+1. While the exponent e of the running total is fixed, one round-to-nearest-even addition of an increment is the
+   integer map M -> M + delta[M & 1] (positive AND negative increments); the maps compose associatively, so the
+   running mantissas come out of a scan.  Steps that leave the binade ("events", ~16 per note) are real additions.
+2. Division by the sample rate with the correctly rounded reciprocal (Markstein): q = RN(a y), r = a - b q,
+   RN(q + r y) equals RN(a / b)."""
+import fractions
+import struct
+
+import numpy as np
+import pytest
+
+F = fractions.Fraction
+ONE52, ONE53 = 1 << 52, 1 << 53
+
+
+def _split(x):
+    b = struct.unpack("<Q", struct.pack("<d", abs(float(x))))[0]
+    e, m = (b >> 52) & 0x7FF, b & (ONE52 - 1)
+    if e == 0:
+        return (0, None) if m == 0 else (None, None)
+    return m | ONE52, e - 1023
+
+
+def delta(x, e):
+    """(d0, d1, guard, is_event) of gf_walk_delta for a positive normal running total with exponent e."""
+    if x == 0:
+        return 0, 0, 0, False
+    mk, ek = _split(x)
+    if mk is None or e - ek < 0:
+        return 0, 0, 0, True
+    s = e - ek
+    if s >= 64:
+        return 0, 0, 0, False
+    q, r = mk >> s, mk & ((1 << s) - 1)
+    half = (1 << (s - 1)) if s > 0 else 0
+    tie = 1 if (s > 0 and r == half) else 0
+    if x > 0:
+        c = 1 if (s > 0 and r > half) else 0
+        return q + c + tie * (q & 1), q + c + tie * ((q + 1) & 1), 0, False
+    guard = q + (1 if r > 0 else 0)
+    if r == 0:
+        return -q, -q, guard, False
+    c = 1 if r < half else 0
+    return -q - 1 + c + tie * ((q + 1) & 1), -q - 1 + c + tie * (q & 1), guard, False
+
+
+def then(a, b):
+    return a[0] + b[(0 + a[0]) & 1], a[1] + b[(1 + a[1]) & 1]
+
+
+def walk(inc, block=256):
+    """attempt / commit loop of the kernel (scan written as a Hillis-Steele pass over the block)."""
+    n = len(inc)
+    out = np.zeros(n)
+    started, raw_mode, raw, M, e = False, False, 0.0, 0, 0
+    attempts = events = 0
+    for blk in range(0, n, block):
+        blk_end, lo = min(n, blk + block), blk
+        while lo < blk_end:
+            attempts += 1
+            cnt = blk_end - lo
+            maps, guards, evs = [], [], []
+            for k in range(lo, blk_end):
+                x = inc[k]
+                if not started or raw_mode:
+                    maps.append((0, 0)); guards.append(0); evs.append(x != 0)
+                else:
+                    d0, d1, g, ev = delta(x, e)
+                    maps.append((d0, d1)); guards.append(g); evs.append(ev)
+            Fs = list(maps)
+            o = 1
+            while o < cnt:
+                Fs = [Fs[k] if k < o else then(Fs[k - o], Fs[k]) for k in range(cnt)]
+                o <<= 1
+            kstar, Mv = blk_end, []
+            for k in range(cnt):
+                Mprev = M if k == 0 else M + Fs[k - 1][M & 1]
+                Mk = M + Fs[k][M & 1]
+                bad = evs[k]
+                if started and not raw_mode:
+                    bad = bad or (Mprev - guards[k] < ONE52) or Mk >= ONE53 or Mk < ONE52
+                if bad:
+                    kstar = lo + k
+                    break
+                Mv.append(Mk)
+            for j in range(kstar - lo):
+                out[lo + j] = raw if raw_mode else (Mv[j] * 2.0 ** (e - 52) if started else 0.0)
+            if kstar > lo and started and not raw_mode:
+                M = Mv[-1]
+            if kstar < blk_end:
+                prev = raw if raw_mode else (M * 2.0 ** (e - 52) if started else 0.0)
+                tot = prev + inc[kstar]                               # the one real fp64 addition
+                out[kstar] = tot
+                events += 1
+                mk, ek = _split(tot) if tot > 0 else (None, None)
+                if tot > 0 and mk:
+                    started, raw_mode, M, e = True, False, mk, ek
+                elif tot == 0:
+                    started, raw_mode, M = False, False, 0
+                else:
+                    started, raw_mode, raw, M = False, True, tot, 0
+                lo = kstar + 1
+            else:
+                lo = blk_end
+    return out, attempts, events
+
+
+def scalar(inc):
+    out = np.zeros(len(inc))
+    t = 0.0
+    for i, x in enumerate(inc):
+        t = t + x
+        out[i] = t
+    return out
+
+
+def _cases():
+    rng = np.random.default_rng(1)
+    c = {}
+    for hz in (110.0, 220.0, 440.0, 50.0, 261.6255653005986):
+        f = np.full(12000, hz, dtype=np.float32)
+        f[:1500] = 0
+        c[f"flat {hz:g}"] = f.astype(np.float64) / 44100.0
+    c["vibrato"] = (220 * 2 ** (0.3 * np.sin(np.arange(16000) / 800.0) / 12)).astype(np.float32).astype(np.float64) / 44100.0
+    c["glide"] = np.linspace(60, 900, 12000).astype(np.float32).astype(np.float64) / 44100.0
+    c["gappy"] = (330 * (rng.random(12000) > 0.3)).astype(np.float32).astype(np.float64) / 44100.0
+    c["tiny"] = (1e-5 * rng.random(8000)).astype(np.float32).astype(np.float64) / 44100.0
+    c["negative jitter"] = (220 * (1 + 2.0 * np.clip(rng.standard_normal(12000), -1, 1))).astype(np.float32).astype(np.float64) / 44100.0
+    c["negative start"] = np.concatenate([np.full(300, -80.0), np.full(4000, 300.0)]).astype(np.float32).astype(np.float64) / 44100.0
+    c["saw"] = np.tile(np.concatenate([np.full(300, 500.0), np.full(290, -500.0)]), 12).astype(np.float32).astype(np.float64) / 44100.0
+    c["binary fractions"] = np.tile(np.array([0.5, 0.25, 0.125, -0.25]), 1500)
+    # subtracting between a quarter and half an ulp from an exact power of two lands in the finer binade below
+    c["power of two"] = np.array([1.0, -1.5 * 2.0 ** -54, 0.0, 2.0 ** -60, 1.0, -2.0 ** -54, -2.0 ** -55, -1.2 * 2.0 ** -53, 3.0, -0.75 * 2.0 ** -52] * 40)
+    return c
+
+
+@pytest.mark.parametrize("name", list(_cases()))
+def test_parity_map_scan_equals_the_scalar_fp64_chain(name):
+    inc = _cases()[name]
+    got, attempts, events = walk(inc)
+    assert np.array_equal(got, scalar(inc)), name
+    if name.startswith("flat") or name in ("vibrato", "glide", "gappy"):
+        assert events <= 24                       # one real addition per power of two the total crosses
+
+
+def test_markstein_division_by_the_sample_rate_is_exact():
+    rng = np.random.default_rng(0)
+    vals = np.concatenate([rng.uniform(20, 2000, 20000).astype(np.float32), (rng.uniform(0, 1, 5000) ** 4 * 1e-3).astype(np.float32),
+                           np.arange(1, 3001, dtype=np.float32), -rng.uniform(1, 900, 3000).astype(np.float32),
+                           np.array([1e-30, 3e-38, 1e30, 65504.0, 0.5, 1.0, 44100.0, 22050.0, 1e-5], dtype=np.float32)])
+    for b in (44100.0, 48000.0, 100.0, 12.0):
+        y = float(F(1) / F(b))
+        for f in vals[:: (1 if b == 44100.0 else 7)].tolist():
+            a = F(f)
+            q0 = float(a * F(y))
+            r = float(a - F(b) * F(q0))
+            assert float(F(q0) + F(r) * F(y)) == float(a / F(b)), (f, b)
