@@ -19,34 +19,44 @@ __device__ __forceinline__ void gf_stage_tables(GfFrameTables *st)
     for (int i = threadIdx.x; i < 1024; i += blockDim.x) st->win[i] = d_tab.win[i];
 }
 
-// All threads of the CTA call this together.  `n_xf` transforms live at bufs + q * GF_FFT_BUF
-// (q < n_xf); lane = threadIdx.x / 64 works on transforms lane, lane + n_lanes, ...
+// barrier among the 64 threads (two warps) that share one transform: named barrier 1 + lane.  The Stockham passes of
+// a transform only exchange data inside its own 64-thread lane, so the CTA-wide barrier is only needed where the
+// thread-to-data mapping changes (before the first pass -- the caller's barrier -- and after the last store).
+__device__ __forceinline__ void gf_lane_sync(int lane)
+{
+    asm volatile("bar.sync %0, 64;" ::"r"(lane + 1) : "memory");
+}
+
+// All threads of the CTA call this together, after a CTA-wide barrier that made the input visible.  `n_xf` transforms
+// live at bufs + q * GF_FFT_BUF (q < n_xf); lane = threadIdx.x / 64 works on transforms lane, lane + n_lanes, ...
 template <bool INV>
 __device__ __forceinline__ void gf_cta_fft512(float2 *bufs, int n_xf, const float2 *tw512)
 {
     const int lane = threadIdx.x >> 6, j = threadIdx.x & 63, n_lanes = blockDim.x >> 6;
     for (int q0 = 0; q0 < n_xf; q0 += n_lanes) {
         const int q = q0 + lane;
-        const bool on = q < n_xf;
+        const bool on = q < n_xf;                            // uniform over the 64-thread lane
         float2 *buf = bufs + (size_t)q * GF_FFT_BUF;
         float2 v[8];
-        if (on) gf_fft_pass_load<INV, 1>(j, buf, tw512, v);
-        __syncthreads();
-        if (on) gf_fft_pass_store<1>(j, buf, v);
-        __syncthreads();
-        if (on) gf_fft_pass_load<INV, 8>(j, buf, tw512, v);
-        __syncthreads();
-        if (on) gf_fft_pass_store<8>(j, buf, v);
-        __syncthreads();
-        if (on) gf_fft_pass_load<INV, 64>(j, buf, tw512, v);
-        __syncthreads();
-        if (on) gf_fft_pass_store<64>(j, buf, v);
-        __syncthreads();
+        if (on) {
+            gf_fft_pass_load<INV, 1>(j, buf, tw512, v);
+            gf_lane_sync(lane);
+            gf_fft_pass_store<1>(j, buf, v);
+            gf_lane_sync(lane);
+            gf_fft_pass_load<INV, 8>(j, buf, tw512, v);
+            gf_lane_sync(lane);
+            gf_fft_pass_store<8>(j, buf, v);
+            gf_lane_sync(lane);
+            gf_fft_pass_load<INV, 64>(j, buf, tw512, v);
+            gf_lane_sync(lane);
+            gf_fft_pass_store<64>(j, buf, v);
+        }
     }
+    __syncthreads();
 }
 
-// NQ transforms per 64-thread lane (n_xf = NQ * lanes), all advanced through a pass before the CTA synchronises:
-// six barriers for the whole batch instead of six per group of `lanes` transforms
+// NQ transforms per 64-thread lane (n_xf = NQ * lanes), all advanced through a pass before the lane synchronises:
+// five two-warp barriers and one CTA-wide barrier for the whole batch
 template <bool INV, int NQ>
 __device__ __forceinline__ void gf_cta_fft512_multi(float2 *bufs, const float2 *tw512)
 {
@@ -54,19 +64,19 @@ __device__ __forceinline__ void gf_cta_fft512_multi(float2 *bufs, const float2 *
     float2 v[NQ][8];
 #pragma unroll
     for (int q = 0; q < NQ; ++q) gf_fft_pass_load<INV, 1>(j, bufs + (size_t)(lane + q * n_lanes) * GF_FFT_BUF, tw512, v[q]);
-    __syncthreads();
+    gf_lane_sync(lane);
 #pragma unroll
     for (int q = 0; q < NQ; ++q) gf_fft_pass_store<1>(j, bufs + (size_t)(lane + q * n_lanes) * GF_FFT_BUF, v[q]);
-    __syncthreads();
+    gf_lane_sync(lane);
 #pragma unroll
     for (int q = 0; q < NQ; ++q) gf_fft_pass_load<INV, 8>(j, bufs + (size_t)(lane + q * n_lanes) * GF_FFT_BUF, tw512, v[q]);
-    __syncthreads();
+    gf_lane_sync(lane);
 #pragma unroll
     for (int q = 0; q < NQ; ++q) gf_fft_pass_store<8>(j, bufs + (size_t)(lane + q * n_lanes) * GF_FFT_BUF, v[q]);
-    __syncthreads();
+    gf_lane_sync(lane);
 #pragma unroll
     for (int q = 0; q < NQ; ++q) gf_fft_pass_load<INV, 64>(j, bufs + (size_t)(lane + q * n_lanes) * GF_FFT_BUF, tw512, v[q]);
-    __syncthreads();
+    gf_lane_sync(lane);
 #pragma unroll
     for (int q = 0; q < NQ; ++q) gf_fft_pass_store<64>(j, bufs + (size_t)(lane + q * n_lanes) * GF_FFT_BUF, v[q]);
     __syncthreads();

@@ -14,9 +14,9 @@ void gf_launch_pulse(const GfPassDev *passes, const GfPassScal *scal, int n_pass
 void gf_launch_frame(const int4 *work, int n_work, const GfPassDev *passes, GfPassScal *scal, const GfNoteDev *notes,
                      const GfNotePlan *plans, cudaStream_t st);
 void gf_launch_peak(const GfNotePlan *plans, const GfNoteDev *notes, const GfPassDev *passes, GfPassScal *scal, int pass0,
-                    int n_pass, int max_n, cudaStream_t st);
+                    int n_pass, int max_n, bool any_simple, bool any_general, cudaStream_t st);
 void gf_launch_mix(const GfNotePlan *plans, const GfNoteDev *notes, const GfPassDev *passes, const GfPassScal *scal,
-                   int note0, int n_notes, int max_n, cudaStream_t st);
+                   int note0, int n_notes, int max_n, bool any_simple, bool any_general, cudaStream_t st);
 void gf_launch_onepole(const GfOnepoleJob *jobs, int n_jobs, cudaStream_t st);
 size_t gf_frame_smem_bytes();
 

@@ -33,7 +33,11 @@ int gf_frame_threads() { return GF_FRAME_THREADS; }
 __device__ __forceinline__ float gf_hp_sigmoid(float f, float f0)
 {
     // GOOFER.py:1111  1 / (1 + exp(-clip((f - f0) / 5, -60, 60)))  (all f32)
-    float a = (f - f0) / 5.0f;
+    // (f - f0) / 5 correctly rounded in three instructions (Markstein: q = RN(a y), r = a - 5 q exact, RN(q + r y) with
+    // y = RN(1 / 5); |a| <= 22,050 or 0, nothing under- or overflows)
+    const float d = f - f0;
+    const float q = d * 0.2f;
+    float a = fmaf(fmaf(-q, 5.0f, d), 0.2f, q);
     a = fminf(fmaxf(a, -60.0f), 60.0f);
     return __fdividef(1.0f, 1.0f + __expf(-a));
 }
@@ -42,6 +46,16 @@ __device__ __forceinline__ float2 gf_gauss5(const float2 *row, int k, const floa
 {
     // numpy 'reflect' at both ends of the 513-bin axis; GOOFER.py:241-261 with sigma 0.5
     float2 acc = make_float2(0.f, 0.f);
+    if (k >= 2 && k <= 510) {                                 // interior: no reflection, immediate offsets
+        const float2 *p = row + (k - 2);
+#pragma unroll
+        for (int j = 0; j < 5; ++j) {
+            const float2 x = p[j];
+            acc.x = fmaf(g[j], x.x, acc.x);
+            acc.y = fmaf(g[j], x.y, acc.y);
+        }
+        return acc;
+    }
 #pragma unroll
     for (int j = 0; j < 5; ++j) {
         int q = k + j - 2;
@@ -139,7 +153,7 @@ __device__ __forceinline__ void gf_shape_mid(GfFrameSmem &sm, int f, float f0f, 
 template <int NF>
 __device__ __forceinline__ void gf_ola_round(float (*carry)[GF_HOP], const float2 *bufs, const float *__restrict__ win,
                                              int t0, int T, int n_out, float *__restrict__ out, int b0, int nb, bool last,
-                                             bool no_input)
+                                             bool no_input, const unsigned char *__restrict__ blk_dead, bool all_dead, float ws_full)
 {
     const int r = threadIdx.x;
     float acc[NF + 3];
@@ -166,16 +180,21 @@ __device__ __forceinline__ void gf_ola_round(float (*carry)[GF_HOP], const float
     for (int m = 0; m < NF + 1; ++m) {
         const int b = t0 + m;
         if (m < n_emit && b >= b0 && b < b0 + nb && b >= 2) {
-            float ws = 0.0f;
+            float ws = ws_full;                            // all four covering frames exist: the sum is the same for every block
+            if (b < 3 || b >= T) {
+                ws = 0.0f;
 #pragma unroll
-            for (int q = 3; q >= 0; --q) {                 // frames b-3 .. b ascending
-                const int t = b - q;
-                if (t >= 0 && t < T) ws = __fadd_rn(ws, d_tab.win2[GF_HOP * q + r]);
+                for (int q = 3; q >= 0; --q) {             // frames b-3 .. b ascending
+                    const int t = b - q;
+                    if (t >= 0 && t < T) ws = __fadd_rn(ws, d_tab.win2[GF_HOP * q + r]);
+                }
             }
             float y = acc[m];
-            if ((double)ws > 1e-9) y = y / ws;
+            if (ws > 1e-9f) y = y / ws;                    // (double) ws > 1e-9: RN_f32(1e-9) < 1e-9, so the f32 compare selects the same floats
             const int i = GF_HOP * (b - 2) + r;
-            if (i < n_out) out[i] = y;
+            // blocks of the unvoiced stream that nobody reads (gain (1 - mask) * 0.75 == 0 on the whole block) are not stored
+            const bool dead = all_dead || (blk_dead && blk_dead[b - 2]);
+            if (i < n_out && !dead) out[i] = y;
         }
     }
 #pragma unroll
@@ -213,6 +232,10 @@ gf_frame_kernel(const int4 *__restrict__ work, const GfPassDev *__restrict__ pas
         sub_scale = ((double)mx > 1e-6) ? pl.subharm_weight / (double)mx : pl.subharm_weight;
     }
     float local_max = 0.0f;
+    // win^2 sum of an interior hop block (frames b-3 .. b all exist), summed in ascending frame order like the general path
+    float ws_full = 0.0f;
+#pragma unroll
+    for (int q = 3; q >= 0; --q) ws_full = __fadd_rn(ws_full, d_tab.win2[GF_HOP * q + tid]);
     __syncthreads();
 
     for (int t0 = t_begin; t0 <= t_end; t0 += GF_RND) {
@@ -321,23 +344,23 @@ gf_frame_kernel(const int4 *__restrict__ work, const GfPassDev *__restrict__ pas
             const bool last = (t0 + nf - 1 == T - 1);
             if (nf == GF_RND) {
 #pragma unroll
-                for (int s = 0; s < 3; ++s) gf_ola_round<GF_RND>(sm.carry[s], &sm.z[s][0][0], win, t0, T, n, outs[s], b0, nb, last, s == 2 && !uv_on);
+                for (int s = 0; s < 3; ++s) gf_ola_round<GF_RND>(sm.carry[s], &sm.z[s][0][0], win, t0, T, n, outs[s], b0, nb, last, s == 2 && !uv_on, s == 2 ? nd.ms_one : nullptr, s == 2 && ps.mask_ones, ws_full);
             } else if (nf == 3) {
 #pragma unroll
-                for (int s = 0; s < 3; ++s) gf_ola_round<3>(sm.carry[s], &sm.z[s][0][0], win, t0, T, n, outs[s], b0, nb, last, s == 2 && !uv_on);
+                for (int s = 0; s < 3; ++s) gf_ola_round<3>(sm.carry[s], &sm.z[s][0][0], win, t0, T, n, outs[s], b0, nb, last, s == 2 && !uv_on, s == 2 ? nd.ms_one : nullptr, s == 2 && ps.mask_ones, ws_full);
             } else if (nf == 2) {
 #pragma unroll
-                for (int s = 0; s < 3; ++s) gf_ola_round<2>(sm.carry[s], &sm.z[s][0][0], win, t0, T, n, outs[s], b0, nb, last, s == 2 && !uv_on);
+                for (int s = 0; s < 3; ++s) gf_ola_round<2>(sm.carry[s], &sm.z[s][0][0], win, t0, T, n, outs[s], b0, nb, last, s == 2 && !uv_on, s == 2 ? nd.ms_one : nullptr, s == 2 && ps.mask_ones, ws_full);
             } else {
 #pragma unroll
-                for (int s = 0; s < 3; ++s) gf_ola_round<1>(sm.carry[s], &sm.z[s][0][0], win, t0, T, n, outs[s], b0, nb, last, s == 2 && !uv_on);
+                for (int s = 0; s < 3; ++s) gf_ola_round<1>(sm.carry[s], &sm.z[s][0][0], win, t0, T, n, outs[s], b0, nb, last, s == 2 && !uv_on, s == 2 ? nd.ms_one : nullptr, s == 2 && ps.mask_ones, ws_full);
             }
         }
         __syncthreads();
     }
     // zero tail of istft: samples 256 (T - 1) .. n - 1     GOOFER.py:407-409
     if (b0 + nb > T) {
-        for (int i = GF_HOP * (T - 1) + tid; i < n; i += blockDim.x) { ps.harm[i] = 0.f; ps.bre[i] = 0.f; ps.uv[i] = 0.f; }
+        for (int i = GF_HOP * (T - 1) + tid; i < n; i += blockDim.x) { ps.harm[i] = 0.f; ps.bre[i] = 0.f; ps.uv[i] = 0.f; }   // (the 68-sample tail: always stored)
     }
     // max(|S| + 1e-8) over the whole (note, pass)          GOOFER.py:1121
     local_max = gf_warp_max(local_max);

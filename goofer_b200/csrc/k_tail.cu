@@ -8,22 +8,24 @@
 
 struct GfStreams { float h, b, u; };
 
-// the three streams of one synthesize pass before the peak normalisation
-__device__ __forceinline__ GfStreams gf_pass_streams(const GfNotePlan &pl, const GfNoteDev &nd, const GfPassDev &ps,
-                                                     const GfPassScal &sc, int i)
+// gains of one sample of one synthesize pass before the peak normalisation (GOOFER.py:1121-1128, 1179-1191).
+// `ms` is the smoothed mask at the sample (ignored by the sa pass); the unvoiced stream is only read where its
+// gain (1 - ms) * 0.75 is not exactly zero: the frame kernel does not store it elsewhere.
+// SIMPLE: a note with one synthesize pass and no volume jitter (see gf_note_tail_simple): those branches compile out.
+template <bool SIMPLE = false>
+__device__ __forceinline__ GfStreams gf_pass_gains(const GfNotePlan &pl, const GfNoteDev &nd, const GfPassDev &ps, float mag,
+                                                   float hraw, float braw, float uraw, float ms, int i)
 {
     GfStreams r;
-    const float mag = __uint_as_float(sc.mag_bits);
-    r.h = ps.harm[i] / mag;                                   // S / max|S| (GOOFER.py:1121-1128), applied after the iSTFT
-    if (ps.mask_ones) {                                       // sa pass: mask == 1, strengths 1 (SillySampler.py:1156-1170)
-        r.b = ps.bre[i];
-        r.u = 0.0f * ps.uv[i];
+    r.h = hraw / mag;                                         // S / max|S| (GOOFER.py:1121-1128), applied after the iSTFT
+    if (!SIMPLE && ps.mask_ones) {                                       // sa pass: mask == 1, strengths 1 (SillySampler.py:1156-1170)
+        r.b = braw;
+        r.u = 0.0f;
     } else {
-        const float ms = nd.ms[i];                            // smooth_mask_ds, expanded once by gf_f0_kernel
-        r.b = ps.bre[i] * ms * 0.1f;
-        r.u = ps.uv[i] * (1.0f - ms) * 0.75f;
+        r.b = braw * ms * 0.1f;
+        r.u = (ms == 1.0f) ? 0.0f : uraw * (1.0f - ms) * 0.75f;
     }
-    if (ps.kind == GF_PASS_MAIN && pl.vol_jitter) {
+    if (!SIMPLE && ps.kind == GF_PASS_MAIN && pl.vol_jitter) {
         // GOOFER.py:1185-1191 (create_volume_jitter :638-659 without vibrato)
         const double zh = nd.z_srh[i] / nd.noteScal[GF_NS_SRHMAX];
         const double zb = nd.z_srb[i] / nd.noteScal[GF_NS_SRBMAX];
@@ -36,6 +38,53 @@ __device__ __forceinline__ GfStreams gf_pass_streams(const GfNotePlan &pl, const
     return r;
 }
 
+// the three streams of one synthesize pass before the peak normalisation, one sample
+__device__ __forceinline__ GfStreams gf_pass_streams(const GfNotePlan &pl, const GfNoteDev &nd, const GfPassDev &ps,
+                                                     const GfPassScal &sc, int i)
+{
+    const float ms = ps.mask_ones ? 1.0f : nd.ms[i];          // smooth_mask_ds, expanded once by gf_f0_kernel
+    const float uraw = (ps.mask_ones || ms == 1.0f) ? 0.0f : ps.uv[i];
+    return gf_pass_gains(pl, nd, ps, __uint_as_float(sc.mag_bits), ps.harm[i], ps.bre[i], uraw, ms, i);
+}
+
+// four consecutive samples starting at i (a multiple of 4; the workspace arrays are 256-byte aligned): one 16-byte
+// load per array when all four exist, element loads at the ragged end
+__device__ __forceinline__ void gf_ld4(const float *__restrict__ p, int i, int cnt, float (&v)[4])
+{
+    if (cnt == 4) {
+        const float4 q = *reinterpret_cast<const float4 *>(p + i);
+        v[0] = q.x; v[1] = q.y; v[2] = q.z; v[3] = q.w;
+    } else {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) v[k] = (k < cnt) ? p[i + k] : 0.0f;
+    }
+}
+
+template <bool SIMPLE>
+__device__ __forceinline__ void gf_pass_streams4(const GfNotePlan &pl, const GfNoteDev &nd, const GfPassDev &ps, float mag,
+                                                 int i, int cnt, GfStreams (&out)[4])
+{
+    float h[4], b[4], u[4] = {0.f, 0.f, 0.f, 0.f}, ms[4] = {1.f, 1.f, 1.f, 1.f};
+    gf_ld4(ps.harm, i, cnt, h);
+    gf_ld4(ps.bre, i, cnt, b);
+    if (SIMPLE || !ps.mask_ones) {
+        gf_ld4(nd.ms, i, cnt, ms);
+        if (cnt < 4 || !(ms[0] == 1.0f && ms[1] == 1.0f && ms[2] == 1.0f && ms[3] == 1.0f)) gf_ld4(ps.uv, i, cnt, u);
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+        if (k < cnt) out[k] = gf_pass_gains<SIMPLE>(pl, nd, ps, mag, h[k], b[k], u[k], ms[k], i + k);
+}
+
+// The common note (c1 / c2 / c5: one pass, no sr jitter, no post-FX, no pitch dynamics, no stage taps) takes lean
+// instantiations of the peak and mix kernels (fewer registers, no dead branches); everything else the general ones.
+// The host evaluates the same predicate on the plans (gf_note_tail_simple in api.cu) to decide which to launch.
+__device__ __forceinline__ bool gf_tail_simple(const GfNotePlan &pl, const GfNoteDev &nd)
+{
+    return pl.n_passes == 1 && !pl.vol_jitter && nd.fx[0] == nullptr && nd.pd_dev == nullptr && nd.tap_harm == nullptr;
+}
+
+template <bool SIMPLE>
 __global__ void __launch_bounds__(256)
 gf_peak_kernel(const GfNotePlan *__restrict__ plans, const GfNoteDev *__restrict__ notes, const GfPassDev *__restrict__ passes,
                GfPassScal *scal, int pass0)
@@ -44,22 +93,29 @@ gf_peak_kernel(const GfNotePlan *__restrict__ plans, const GfNoteDev *__restrict
     const GfPassDev ps = passes[pi];
     const GfNotePlan &pl = plans[ps.note];
     const GfNoteDev nd = notes[ps.note];
-    const GfPassScal sc = scal[pi];
+    if (gf_tail_simple(pl, nd) != SIMPLE) return;
+    const float mag = __uint_as_float(scal[pi].mag_bits);
+    const int n = ps.n_total;
     float mx = 0.0f;
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < ps.n_total; i += gridDim.x * blockDim.x) {
-        const GfStreams s = gf_pass_streams(pl, nd, ps, sc, i);
-        mx = fmaxf(mx, fabsf((s.h + s.u) + s.b));
+    for (int i = 4 * (blockIdx.x * blockDim.x + threadIdx.x); i < n; i += 4 * gridDim.x * blockDim.x) {
+        const int cnt = min(4, n - i);
+        GfStreams s[4];
+        gf_pass_streams4<SIMPLE>(pl, nd, ps, mag, i, cnt, s);
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+            if (k < cnt) mx = fmaxf(mx, fabsf((s[k].h + s[k].u) + s[k].b));
     }
     mx = gf_warp_max(mx);
     if ((threadIdx.x & 31) == 0 && mx > 0.0f) gf_atomic_max_pos(&scal[pi].peak_bits, mx);
 }
 
 void gf_launch_peak(const GfNotePlan *plans, const GfNoteDev *notes, const GfPassDev *passes, GfPassScal *scal, int pass0,
-                    int n_pass, int max_n, cudaStream_t st)
+                    int n_pass, int max_n, bool any_simple, bool any_general, cudaStream_t st)
 {
     if (n_pass <= 0) return;
-    dim3 grid(min(8, (max_n + 255) / 256), n_pass);         // few fat CTAs: the per-thread record loads amortise over ~20 samples
-    gf_peak_kernel<<<grid, 256, 0, st>>>(plans, notes, passes, scal, pass0);
+    dim3 grid(min(8, (max_n + 1023) / 1024), n_pass);       // few fat CTAs: the per-thread record loads amortise over ~20 samples
+    if (any_simple) gf_peak_kernel<true><<<grid, 256, 0, st>>>(plans, notes, passes, scal, pass0);
+    if (any_general) gf_peak_kernel<false><<<grid, 256, 0, st>>>(plans, notes, passes, scal, pass0);
 }
 
 __device__ __forceinline__ float gf_pass_gain(const GfNotePlan &pl, const GfPassScal &sc)
@@ -67,67 +123,104 @@ __device__ __forceinline__ float gf_pass_gain(const GfNotePlan &pl, const GfPass
     // GOOFER.py:1208-1213
     const float pk = __uint_as_float(sc.peak_bits) + 1e-12f;
     const double nrm = fmin(fmax(pl.normalize, 0.0), 1.0);
+    if (nrm == 1.0) return (float)(1.0 / (double)pk);       // pow(x, 1.0) == x exactly (IEEE pow)
     return (float)pow(1.0 / (double)pk, nrm);
 }
 
 // stage 1 of the tail: normalised streams of every pass -> fx scratch (only for notes that need the
 // sequential filters); stage 2: mix.  Notes without filters go straight through gf_mix_kernel.
+template <bool SIMPLE>
 __global__ void __launch_bounds__(256)
 gf_mix_kernel(const GfNotePlan *__restrict__ plans, const GfNoteDev *__restrict__ notes, const GfPassDev *__restrict__ passes,
               const GfPassScal *__restrict__ scal, int note0)
 {
     const GfNotePlan &pl = plans[note0 + blockIdx.y];
     const GfNoteDev nd = notes[note0 + blockIdx.y];
+    if (gf_tail_simple(pl, nd) != SIMPLE) return;
     const int n = pl.n_total;
     const GfPassDev &p0 = passes[nd.pass0];
-    const GfPassScal &s0 = scal[nd.pass0];
-    const float g0 = gf_pass_gain(pl, s0);
+    const float mag0 = __uint_as_float(scal[nd.pass0].mag_bits);
+    const float g0 = gf_pass_gain(pl, scal[nd.pass0]);
     int p_sa = -1;
-    for (int p = 1; p < pl.n_passes; ++p)
-        if (pl.pass_kind[p] == GF_PASS_SA) p_sa = nd.pass0 + p;
-    float g_sa = 0.0f;
-    if (p_sa >= 0) g_sa = gf_pass_gain(pl, scal[p_sa]);
-    const bool fx = nd.fx[0] != nullptr;                  // harm / bre already post-processed into fx[0] / fx[1]
+    if (!SIMPLE)
+        for (int p = 1; p < pl.n_passes; ++p)
+            if (pl.pass_kind[p] == GF_PASS_SA) p_sa = nd.pass0 + p;
+    float g_sa = 0.0f, mag_sa = 1.0f;
+    if (p_sa >= 0) { g_sa = gf_pass_gain(pl, scal[p_sa]); mag_sa = __uint_as_float(scal[p_sa].mag_bits); }
+    const bool fx = !SIMPLE && nd.fx[0] != nullptr;       // harm / bre already post-processed into fx[0] / fx[1]
     double fx_scale = 1.0;
     if (fx && pl.tension != 0.0) {
         // SillySampler.py:1136-1140 (gf.rms GOOFER.py:170-171)
         const double r0 = sqrt(nd.noteScal[GF_NS_R0] / (double)n + 1e-12), r1 = sqrt(nd.noteScal[GF_NS_R1] / (double)n + 1e-12);
         if (r1 > 0.0) fx_scale = r0 / r1;
     }
-    const double pd_ref = nd.pd_dev ? nd.noteScal[GF_NS_PDREF] : 1.0;
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        const GfStreams s = gf_pass_streams(pl, nd, p0, s0, i);
-        float h = s.h * g0, b = s.b * g0;
-        const float u = s.u * g0;
-        if (nd.tap_harm) { nd.tap_harm[i] = h; nd.tap_uv[i] = u; nd.tap_bre[i] = b; }
-        if (fx) { h = (float)((double)nd.fx[0][i] * fx_scale); b = (float)((double)nd.fx[1][i] * fx_scale); }
-        // SillySampler.py:1143-1151: harm * V (np.float64) + bre * B (f32) + uv * U (f32), * volume
-        double out = (((double)h * pl.V + (double)(b * (float)pl.B)) + (double)(u * (float)pl.U)) * pl.volume;
-        if (p_sa >= 0) {
-            // SillySampler.py:1153-1172
-            const GfStreams a = gf_pass_streams(pl, nd, passes[p_sa], scal[p_sa], i);
-            const float au = a.u * g_sa, ab = a.b * g_sa;
-            out = out * (1.0 - pl.sa) + ((double)((au + ab) * (float)pl.volume)) * pl.sa;
+    const bool pd_on = !SIMPLE && nd.pd_dev != nullptr;
+    const bool taps = !SIMPLE && nd.tap_harm != nullptr;
+    const double pd_ref = pd_on ? nd.noteScal[GF_NS_PDREF] : 1.0;
+    // scalars of the note, read once (the stores below may alias the plan record as far as the compiler knows)
+    const double V = pl.V, volume = pl.volume, sa = pl.sa, pdv = pl.pd;
+    const float Bf = (float)pl.B, Uf = (float)pl.U, volf = (float)pl.volume;
+    // the caller's output (and tap) arrays start at any element offset: 16-byte stores only when aligned
+    const bool out_vec = (((uintptr_t)nd.out) & 15) == 0;
+    const bool tap_vec = taps && ((((uintptr_t)nd.tap_harm) | ((uintptr_t)nd.tap_uv) | ((uintptr_t)nd.tap_bre)) & 15) == 0;
+    for (int i = 4 * (blockIdx.x * blockDim.x + threadIdx.x); i < n; i += 4 * gridDim.x * blockDim.x) {
+        const int cnt = min(4, n - i);
+        GfStreams s[4], a[4];
+        gf_pass_streams4<SIMPLE>(pl, nd, p0, mag0, i, cnt, s);
+        if (p_sa >= 0) gf_pass_streams4<false>(pl, nd, passes[p_sa], mag_sa, i, cnt, a);
+        float o[4], th[4], tu[4], tb[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            if (k >= cnt) { o[k] = th[k] = tu[k] = tb[k] = 0.0f; continue; }
+            float h = s[k].h * g0, b = s[k].b * g0;
+            const float u = s[k].u * g0;
+            th[k] = h; tu[k] = u; tb[k] = b;
+            if (fx) { h = (float)((double)nd.fx[0][i + k] * fx_scale); b = (float)((double)nd.fx[1][i + k] * fx_scale); }
+            // SillySampler.py:1143-1151: harm * V (np.float64) + bre * B (f32) + uv * U (f32), * volume
+            double out = (((double)h * V + (double)(b * Bf)) + (double)(u * Uf)) * volume;
+            if (p_sa >= 0) {
+                // SillySampler.py:1153-1172
+                const float au = a[k].u * g_sa, ab = a[k].b * g_sa;
+                out = out * (1.0 - sa) + ((double)((au + ab) * volf)) * sa;
+            }
+            if (pd_on) {
+                // SillySampler.py:869-881, 1174-1182
+                const double v = fmin(fmax(nd.pd_dev[i + k] / pd_ref, -1.0), 1.0);
+                const double db = (12.0 * fabs(pdv)) * (pdv > 0.0 ? v : -v);
+                float dynf = (float)pow(10.0, db / 20.0);
+                dynf = fminf(fmaxf(dynf, 1e-3f), 1e3f);
+                const double dyn = 1.0 + (double)(dynf - 1.0f) * (double)nd.pd_gm[i + k];
+                out = out * dyn;
+            }
+            o[k] = (float)out;
         }
-        if (nd.pd_dev) {
-            // SillySampler.py:869-881, 1174-1182
-            const double v = fmin(fmax(nd.pd_dev[i] / pd_ref, -1.0), 1.0);
-            const double db = (12.0 * fabs(pl.pd)) * (pl.pd > 0.0 ? v : -v);
-            float dynf = (float)pow(10.0, db / 20.0);
-            dynf = fminf(fmaxf(dynf, 1e-3f), 1e3f);
-            const double dyn = 1.0 + (double)(dynf - 1.0f) * (double)nd.pd_gm[i];
-            out = out * dyn;
+        if (taps) {
+            if (cnt == 4 && tap_vec) {
+                *reinterpret_cast<float4 *>(nd.tap_harm + i) = make_float4(th[0], th[1], th[2], th[3]);
+                *reinterpret_cast<float4 *>(nd.tap_uv + i) = make_float4(tu[0], tu[1], tu[2], tu[3]);
+                *reinterpret_cast<float4 *>(nd.tap_bre + i) = make_float4(tb[0], tb[1], tb[2], tb[3]);
+            } else {
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                    if (k < cnt) { nd.tap_harm[i + k] = th[k]; nd.tap_uv[i + k] = tu[k]; nd.tap_bre[i + k] = tb[k]; }
+            }
         }
-        nd.out[i] = (float)out;
+        if (cnt == 4 && out_vec) *reinterpret_cast<float4 *>(nd.out + i) = make_float4(o[0], o[1], o[2], o[3]);
+        else {
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+                if (k < cnt) nd.out[i + k] = o[k];
+        }
     }
 }
 
 void gf_launch_mix(const GfNotePlan *plans, const GfNoteDev *notes, const GfPassDev *passes, const GfPassScal *scal,
-                   int note0, int n_notes, int max_n, cudaStream_t st)
+                   int note0, int n_notes, int max_n, bool any_simple, bool any_general, cudaStream_t st)
 {
     if (n_notes <= 0) return;
-    dim3 grid(min(8, (max_n + 255) / 256), n_notes);
-    gf_mix_kernel<<<grid, 256, 0, st>>>(plans, notes, passes, scal, note0);
+    dim3 grid(min(8, (max_n + 1023) / 1024), n_notes);
+    if (any_simple) gf_mix_kernel<true><<<grid, 256, 0, st>>>(plans, notes, passes, scal, note0);
+    if (any_general) gf_mix_kernel<false><<<grid, 256, 0, st>>>(plans, notes, passes, scal, note0);
 }
 
 // ------------------------------------------------------------------------------------------------
