@@ -4,6 +4,7 @@
 #include <cstdlib>
 #include <cstdint>
 #include <climits>
+#include <ctime>
 
 struct GfHostCache {
     void *dev = nullptr;  size_t dev_cap = 0;
@@ -21,6 +22,43 @@ static int gf_hc_reserve(void **p, size_t *cap, size_t need)
     GF_CUDA(cudaMalloc(p, need));
     *cap = need;
     return GOOFER_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Gather copy of many medium-sized page-locked host arrays (a voicebank's knot packs and voicing masks: two arrays of
+// 60-180 KB per source) into device memory by ONE kernel that reads the host memory directly over PCIe, instead of one
+// cudaMemcpyAsync per array (~5 us of host time each: 130 calls held the preparation kernels back by 0.7 ms).
+// One CTA per 16 KB block of one array.
+// ------------------------------------------------------------------------------------------------
+struct GfPullJob { const char *src; char *dst; unsigned long long bytes; unsigned int first_block; unsigned int pad; };
+#define GF_PULL_BLOCK 16384
+
+__global__ void __launch_bounds__(256) gf_pull_kernel(const GfPullJob *__restrict__ jobs, int n_jobs)
+{
+    // job of this CTA: last one whose first_block <= blockIdx.x
+    int lo = 0, hi = n_jobs - 1;
+    while (lo < hi) {
+        const int mid = (lo + hi + 1) >> 1;
+        if (jobs[mid].first_block <= blockIdx.x) lo = mid; else hi = mid - 1;
+    }
+    const GfPullJob jb = jobs[lo];
+    const unsigned long long off = (unsigned long long)(blockIdx.x - jb.first_block) * GF_PULL_BLOCK;
+    const unsigned long long cnt = min((unsigned long long)GF_PULL_BLOCK, jb.bytes - off);
+    const char *src = jb.src + off;
+    char *dst = jb.dst + off;
+    if ((((uintptr_t)src | (uintptr_t)dst) & 15) == 0) {
+        const int n16 = (int)(cnt >> 4);
+        const uint4 *s4 = reinterpret_cast<const uint4 *>(src);
+        uint4 *d4 = reinterpret_cast<uint4 *>(dst);
+        uint4 v[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) { const int i = threadIdx.x + 256 * k; if (i < n16) v[k] = s4[i]; }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) { const int i = threadIdx.x + 256 * k; if (i < n16) d4[i] = v[k]; }
+        for (int i = (n16 << 4) + threadIdx.x; i < (int)cnt; i += 256) dst[i] = src[i];
+    } else {
+        for (int i = threadIdx.x; i < (int)cnt; i += 256) dst[i] = src[i];
+    }
 }
 
 extern "C" void goofer_host_release(void)
@@ -49,6 +87,15 @@ extern "C" int goofer_render_batch_host(const GooferBatch *b)
     if (!g_hc.st_in) GF_CUDA(cudaStreamCreateWithFlags(&g_hc.st_in, cudaStreamNonBlocking));
     if (!g_hc.st_out) GF_CUDA(cudaStreamCreateWithFlags(&g_hc.st_out, cudaStreamNonBlocking));
     cudaStream_t st = g_hc.st, st_in = g_hc.st_in, st_out = g_hc.st_out;
+    const bool trace = getenv("GOOFER_HOST_TRACE") != nullptr;
+    auto now_ms = []() { timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return 1e3 * (double)ts.tv_sec + 1e-6 * (double)ts.tv_nsec; };
+    const double h0 = trace ? now_ms() : 0.0;
+    double h_first_copy = 0.0, h_enqueued = 0.0;
+    static thread_local cudaEvent_t ev_t0 = nullptr, ev_d2h[64] = {nullptr};
+    if (trace) {
+        if (!ev_t0) cudaEventCreate(&ev_t0);
+        cudaEventRecord(ev_t0, st_in);
+    }
 
     std::vector<GfNotePlan> plans;
     if ((rc = gf_make_plans(b, plans)) != GOOFER_OK) return rc;
@@ -56,6 +103,7 @@ extern "C" int goofer_render_batch_host(const GooferBatch *b)
     // ---- device image of every input array (same element offsets as on the host) ----
     Bump sz{nullptr, 0, 0};
     const void *small_dev = nullptr;
+    GfPullJob *pull_tab = nullptr;
     auto carve = [&](Bump &bp, GooferBatch &db, std::vector<GooferSource> &ds) {
         for (int s = 0; s < b->n_sources; ++s) ds[s] = b->sources[s];
         // small arrays back to back, each padded to 256 bytes (Bump aligns every array to 256)
@@ -79,6 +127,7 @@ extern "C" int goofer_render_batch_host(const GooferBatch *b)
         db.tap_harm = b->tap_harm ? bp.arr<float>((size_t)b->out_total) : nullptr;
         db.tap_uv = b->tap_uv ? bp.arr<float>((size_t)b->out_total) : nullptr;
         db.tap_bre = b->tap_bre ? bp.arr<float>((size_t)b->out_total) : nullptr;
+        pull_tab = bp.arr<GfPullJob>((size_t)3 * b->n_sources + 8);
     };
     GooferBatch db = *b;
     std::vector<GooferSource> ds(b->n_sources);
@@ -100,6 +149,7 @@ extern "C" int goofer_render_batch_host(const GooferBatch *b)
         g_stats.d2h_bytes += (int64_t)bytes;
         return GOOFER_OK;
     };
+    if (trace) h_first_copy = now_ms();
     // The small per-source arrays (mel-knot frequencies, four formant tracks: a few KB each) are gathered in the
     // pinned staging arena and go up as ONE copy -- hundreds of tiny cudaMemcpyAsync calls cost more host time
     // than the transfer itself.  They were carved back to back (see `carve`), so one device range covers them.
@@ -123,22 +173,76 @@ extern "C" int goofer_render_batch_host(const GooferBatch *b)
             if ((rc = h2d(small_dev, stage, small_bytes))) return rc;
         }
     }
-    for (int s = 0; s < b->n_sources; ++s) {
-        const GooferSource &g = b->sources[s];
-        const GooferSource &d = ds[s];
-        if (g.knots_log_f16 && (rc = h2d(d.knots_log_f16, g.knots_log_f16, sizeof(uint16_t) * (size_t)g.K * g.T))) return rc;
-        if (g.env_dense && (rc = h2d(d.env_dense, g.env_dense, sizeof(float) * (size_t)GF_NBINS * g.T))) return rc;
-        if (g.mask && (rc = h2d(d.mask, g.mask, sizeof(float) * (size_t)g.N))) return rc;
+    // source envelopes, voicing masks, bends: one gather kernel when every array is page-locked (see gf_pull_kernel),
+    // else one copy-engine transfer per array
+    {
+        struct Cp { const void *dst, *src; size_t bytes; };
+        std::vector<Cp> cps;
+        for (int s = 0; s < b->n_sources; ++s) {
+            const GooferSource &g = b->sources[s];
+            const GooferSource &d = ds[s];
+            if (g.knots_log_f16) cps.push_back({d.knots_log_f16, g.knots_log_f16, sizeof(uint16_t) * (size_t)g.K * g.T});
+            if (g.env_dense) cps.push_back({d.env_dense, g.env_dense, sizeof(float) * (size_t)GF_NBINS * g.T});
+            if (g.mask) cps.push_back({d.mask, g.mask, sizeof(float) * (size_t)g.N});
+        }
+        cps.push_back({db.bend_cents, b->bend_cents, sizeof(float) * (size_t)b->bend_total});
+        bool pull = cps.size() > 8 && !getenv("GOOFER_HOST_NO_PULL");
+        std::vector<GfPullJob> jobs;
+        unsigned int blocks = 0;
+        for (size_t i = 0; pull && i < cps.size(); ++i) {
+            if (!cps[i].bytes) continue;
+            cudaPointerAttributes at;
+            if (cudaPointerGetAttributes(&at, cps[i].src) != cudaSuccess || at.type != cudaMemoryTypeHost || !at.devicePointer) {
+                cudaGetLastError();
+                pull = false;
+                break;
+            }
+            jobs.push_back({(const char *)at.devicePointer, (char *)const_cast<void *>(cps[i].dst), (unsigned long long)cps[i].bytes, blocks, 0u});
+            blocks += (unsigned int)((cps[i].bytes + GF_PULL_BLOCK - 1) / GF_PULL_BLOCK);
+        }
+        if (pull && !jobs.empty()) {
+            GfPullJob *stage = (GfPullJob *)gf_pin_take(jobs.size() * sizeof(GfPullJob));
+            if (!stage) { gf_set_error("cudaMallocHost failed for the gather table"); return GOOFER_ERR_CUDA; }
+            std::memcpy(stage, jobs.data(), jobs.size() * sizeof(GfPullJob));
+            if ((rc = gf_meta_copy(pull_tab, stage, jobs.size() * sizeof(GfPullJob), st)) != GOOFER_OK) return rc;
+            gf_pull_kernel<<<blocks, 256, 0, st>>>(pull_tab, (int)jobs.size());   // compute stream: the preparation kernels follow it
+            GF_CUDA(cudaGetLastError());
+            for (const Cp &c : cps) g_stats.h2d_bytes += (int64_t)c.bytes;
+        } else {
+            for (const Cp &c : cps)
+                if ((rc = h2d(c.dst, c.src, c.bytes))) return rc;
+        }
     }
-    if ((rc = h2d(db.bend_cents, b->bend_cents, sizeof(float) * (size_t)b->bend_total))) return rc;
 
     // ---- parts: runs of consecutive notes whose phases travel together ----
-    int chunk = b->n_notes >= 512 ? (b->n_notes + 3) / 4 : (b->n_notes >= 128 ? (b->n_notes + 1) / 2 : b->n_notes);
+    // Measured on B200 (c2, 1,024 notes): the phase upload (7.3 ms at 52 GB/s) and the compute stream (7.8 ms) finish
+    // together; what follows the last phase byte is the last part's frame / peak / mix and its download, so equal
+    // quarters (9.3 ms) beat both fewer parts and a graded 50 / 25 / 15 / 10 split (10.0 ms: its 5.1 ms first mix holds
+    // the download pipeline back).  GOOFER_HOST_CHUNK = uniform parts of that many notes; GOOFER_HOST_PARTS =
+    // comma-separated cumulative fractions.
+    std::vector<int> ends;                                 // note_end of every part, ascending, last == n_notes
     {
-        const char *e = getenv("GOOFER_HOST_CHUNK");
-        if (e && atoi(e) > 0) chunk = atoi(e);
+        const int nn = b->n_notes;
+        const char *e = getenv("GOOFER_HOST_CHUNK"), *f = getenv("GOOFER_HOST_PARTS");
+        if (e && atoi(e) > 0) {
+            for (int i = atoi(e); i < nn; i += atoi(e)) ends.push_back(i);
+        } else if (f && f[0]) {
+            for (const char *q = f; *q;) {
+                char *nx = nullptr;
+                const double fr = strtod(q, &nx);
+                if (nx == q) break;
+                const int v = (int)(fr * nn);
+                if (v > (ends.empty() ? 0 : ends.back()) && v < nn) ends.push_back(v);
+                q = (*nx == ',') ? nx + 1 : nx;
+            }
+        } else if (nn >= 512) {
+            ends = {nn / 4, nn / 2, (3 * nn) / 4};
+        } else if (nn >= 128) {
+            ends = {nn / 2};
+        }
+        ends.push_back(nn);
     }
-    const int n_chunks = (b->n_notes + chunk - 1) / chunk;
+    const int n_chunks = (int)ends.size();
     const size_t want = goofer_workspace_bytes(&db, 0);
     if (want == 0) return GOOFER_ERR_NOTE;
     if ((rc = gf_hc_reserve(&g_hc.ws, &g_hc.ws_cap, want)) != GOOFER_OK) return rc;
@@ -151,7 +255,7 @@ extern "C" int goofer_render_batch_host(const GooferBatch *b)
     struct Range { int64_t plo, phi, nlo, nhi, olo, ohi; };
     std::vector<Range> rg(n_chunks);
     for (int c = 0; c < n_chunks; ++c) {
-        const int i0 = c * chunk, i1 = std::min(b->n_notes, i0 + chunk);
+        const int i0 = c ? ends[c - 1] : 0, i1 = ends[c];
         Range r = {INT64_MAX, 0, INT64_MAX, 0, INT64_MAX, 0};
         for (int i = i0; i < i1; ++i) {
             const GfNotePlan &p = plans[i];
@@ -182,7 +286,7 @@ extern "C" int goofer_render_batch_host(const GooferBatch *b)
     for (int c = 0; c < n_chunks; ++c) {
         if ((rc = h2d(db.phi + rg[c].plo, b->phi + rg[c].plo, sizeof(float) * (size_t)(rg[c].phi - rg[c].plo)))) return rc;
         GF_CUDA(cudaEventRecord(g_hc.ev[2 * c], st_in));             // this part's phases
-        parts[c].note_end = std::min(b->n_notes, (c + 1) * chunk);
+        parts[c].note_end = ends[c];
         parts[c].phi_ready = g_hc.ev[2 * c];
         parts[c].done = g_hc.ev[2 * c + 1];
     }
@@ -191,6 +295,7 @@ extern "C" int goofer_render_batch_host(const GooferBatch *b)
     if ((rc = gf_render_batch_ex(&db, g_hc.ws, g_hc.ws_cap, st, parts.data(), n_chunks)) != GOOFER_OK) return rc;
     const int64_t launches = g_stats.kernel_launches;
     const int waves = g_stats.waves;
+    if (trace) h_enqueued = now_ms();
     for (int c = 0; c < n_chunks; ++c) {
         GF_CUDA(cudaStreamWaitEvent(st_out, g_hc.ev[2 * c + 1], 0));
         const int64_t olo = rg[c].olo;
@@ -199,17 +304,28 @@ extern "C" int goofer_render_batch_host(const GooferBatch *b)
         if (b->tap_harm && (rc = d2h(b->tap_harm + olo, db.tap_harm + olo, ob))) return rc;
         if (b->tap_uv && (rc = d2h(b->tap_uv + olo, db.tap_uv + olo, ob))) return rc;
         if (b->tap_bre && (rc = d2h(b->tap_bre + olo, db.tap_bre + olo, ob))) return rc;
+        if (trace && c < 64) {
+            if (!ev_d2h[c]) cudaEventCreate(&ev_d2h[c]);
+            cudaEventRecord(ev_d2h[c], st_out);
+        }
     }
     g_stats.kernel_launches = launches;
     g_stats.waves = waves;
     GF_CUDA(cudaStreamSynchronize(st_out));
     GF_CUDA(cudaStreamSynchronize(st));
-    if (getenv("GOOFER_HOST_TRACE")) {
+    if (trace) {
+        const double h_done = now_ms();
+        float small = 0;
+        cudaEventElapsedTime(&small, ev_t0, g_hc.ev[2 * n_chunks]);
+        fprintf(stderr, "[host trace] host: first copy issued at %.3f ms, everything enqueued at %.3f ms, synchronised at %.3f ms; "
+                        "device: small inputs in at %.3f ms after the H2D stream started\n",
+                h_first_copy - h0, h_enqueued - h0, h_done - h0, small);
         for (int c = 0; c < n_chunks; ++c) {
-            float a = 0, bq = 0;
-            cudaEventElapsedTime(&a, g_hc.ev[2 * n_chunks], g_hc.ev[2 * c]);
-            cudaEventElapsedTime(&bq, g_hc.ev[2 * n_chunks], g_hc.ev[2 * c + 1]);
-            fprintf(stderr, "[host trace] part %d: phases in at %.3f ms, mixed at %.3f ms (since the small inputs arrived)\n", c, a, bq);
+            float a = 0, bq = 0, dq = 0;
+            cudaEventElapsedTime(&a, ev_t0, g_hc.ev[2 * c]);
+            cudaEventElapsedTime(&bq, ev_t0, g_hc.ev[2 * c + 1]);
+            if (c < 64) cudaEventElapsedTime(&dq, ev_t0, ev_d2h[c]);
+            fprintf(stderr, "[host trace] part %d: phases in at %.3f ms, mixed at %.3f ms, downloaded at %.3f ms\n", c, a, bq, dq);
         }
     }
     return GOOFER_OK;
