@@ -193,6 +193,23 @@ int gf_tables_init(int sr)
     gf_brightness(t->bright_b, sr, 3500, 5000, 20.0);
     gf_gauss_taps(t->g175, 1.75);
     gf_gauss_taps(t->g05, 0.5);
+    {
+        // time-domain image of the 5-tap blur and the taps of its inverse (k_frame.cu gf_blur_edges)
+        std::vector<double> G(1024), ginv(1024);
+        for (int n = 0; n < 1024; ++n)
+            G[n] = t->g05[2] + 2.0 * t->g05[1] * std::cos(2.0 * PI * n / 1024.0) + 2.0 * t->g05[0] * std::cos(4.0 * PI * n / 1024.0);
+        for (int j = 0; j < 32; ++j) {
+            double a = 0.0;
+            for (int n = 0; n < 1024; ++n) a += std::cos(2.0 * PI * (double)j * n / 1024.0) / G[n];
+            ginv[j] = a / 1024.0;
+        }
+        for (int n = 0; n < 1024; ++n) t->winG[n] = (float)((double)t->win[n] * G[n]);
+        for (int k = 0; k < 16; ++k) {
+            // ginv is even: ginv[-j] = ginv[j]
+            t->bq1[k] = (float)(ginv[std::abs(k - 1)] - ginv[k + 1]);
+            t->bq2[k] = (float)(ginv[std::abs(k - 2)] - ginv[k + 2]);
+        }
+    }
     t->sr = sr;
     cudaError_t e = cudaMemcpyToSymbol(d_tab, t, sizeof(GfTables));
     delete t;

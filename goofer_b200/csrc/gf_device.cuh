@@ -17,6 +17,8 @@ struct GfTables {
     float freq32[513];      // rfftfreq f32                         GOOFER.py:24
     double g175[15];        // Gaussian sigma 1.75 (env4breath)     GOOFER.py:993
     double g05[5];          // Gaussian sigma 0.5 (brightness blur) GOOFER.py:1143
+    float winG[1024];       // win * G, G = time-domain image of the sigma-0.5 blur (k_frame.cu gf_blur_edges)
+    float bq1[16], bq2[16]; // edge-correction taps of that blur, index = bin 1..12
     int sr;
 };
 

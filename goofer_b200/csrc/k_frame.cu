@@ -13,13 +13,13 @@
 
 #define GF_RND 4                      // frames per round (= FFT lanes)
 #define GF_FRAME_THREADS (64 * GF_RND)
-#define GF_STAG_LD 516
+#define GF_BLUR_K 12                  // reach of the edge correction of the time-domain blur (see gf_blur_edges)
 
 struct GfFrameSmem {
     float2 tw512[512];                        // the FFT passes hit these every butterfly; window and split twiddles
                                               // come from d_tab through L1 (keeps the CTA at <= 113 KB: two per SM)
     float2 z[3][GF_RND][GF_FFT_BUF];          // [0] harmonic, [1] breath, [2] unvoiced (also the forward buffer)
-    float2 stag[2][GF_RND][GF_STAG_LD];       // pre-blur harmonic / breath spectra of voiced frames
+    float edge[2][GF_RND][4];                 // voiced frames, harmonic / breath: Im X[0], Im X[1], Im X[512], Im X[511] before the blur
     float carry[3][3][GF_HOP];                // per stream: the three hop blocks still waiting for later frames
     float f0fr[GF_RND];
     int voiced[GF_RND];
@@ -40,31 +40,6 @@ __device__ __forceinline__ float gf_hp_sigmoid(float f, float f0)
     float a = fmaf(fmaf(-q, 5.0f, d), 0.2f, q);
     a = fminf(fmaxf(a, -60.0f), 60.0f);
     return __fdividef(1.0f, 1.0f + __expf(-a));
-}
-
-__device__ __forceinline__ float2 gf_gauss5(const float2 *row, int k, const float *g)
-{
-    // numpy 'reflect' at both ends of the 513-bin axis; GOOFER.py:241-261 with sigma 0.5
-    float2 acc = make_float2(0.f, 0.f);
-    if (k >= 2 && k <= 510) {                                 // interior: no reflection, immediate offsets
-        const float2 *p = row + (k - 2);
-#pragma unroll
-        for (int j = 0; j < 5; ++j) {
-            const float2 x = p[j];
-            acc.x = fmaf(g[j], x.x, acc.x);
-            acc.y = fmaf(g[j], x.y, acc.y);
-        }
-        return acc;
-    }
-#pragma unroll
-    for (int j = 0; j < 5; ++j) {
-        int q = k + j - 2;
-        q = q < 0 ? -q : (q > 512 ? 1024 - q : q);
-        const float2 x = row[q];
-        acc.x = fmaf(g[j], x.x, acc.x);
-        acc.y = fmaf(g[j], x.y, acc.y);
-    }
-    return acc;
 }
 
 struct GfShapeIn { float ef[2], en[2], ph[2]; };        // envF, envN, phi at bins (k, 512 - k) of one frame
@@ -101,9 +76,10 @@ __device__ __forceinline__ void gf_shape_pair(GfFrameSmem &sm, int k, int f, flo
     float2 H0, H1, B0, B1, V0, V1;
     gf_shape_bin(k, S0, f0f, vo, in.ef[0], in.en[0], in.ph[0], H0, B0, V0, local_max);
     gf_shape_bin(km, S1, f0f, vo, in.ef[1], in.en[1], in.ph[1], H1, B1, V1, local_max);
-    if (vo) {
-        sm.stag[0][f][k] = H0; sm.stag[0][f][km] = H1;
-        sm.stag[1][f][k] = B0; sm.stag[1][f][km] = B1;
+    if (vo && k <= 1) {
+        // inputs of the blur's edge terms (gf_blur_edges): taken before the DC / Nyquist imaginary parts are dropped
+        sm.edge[0][f][k] = H0.y; sm.edge[0][f][2 + k] = H1.y;
+        sm.edge[1][f][k] = B0.y; sm.edge[1][f][2 + k] = B1.y;
     }
     // pocketfft c2r ignores the imaginary parts of DC and Nyquist
     if (k == 0) { V0.y = 0.f; V1.y = 0.f; H0.y = 0.f; H1.y = 0.f; B0.y = 0.f; B1.y = 0.f; }
@@ -113,14 +89,12 @@ __device__ __forceinline__ void gf_shape_pair(GfFrameSmem &sm, int k, int f, flo
         zf[gf_fpad(k)] = Zk;
         if (k != 0) zf[gf_fpad(km)] = Zm;
     }
-    if (!vo) {
-        gf_irfft_merge(H0, H1, w, Zk, Zm);
-        sm.z[0][f][gf_fpad(k)] = Zk;
-        if (k != 0) sm.z[0][f][gf_fpad(km)] = Zm;
-        gf_irfft_merge(B0, B1, w, Zk, Zm);
-        sm.z[1][f][gf_fpad(k)] = Zk;
-        if (k != 0) sm.z[1][f][gf_fpad(km)] = Zm;
-    }
+    gf_irfft_merge(H0, H1, w, Zk, Zm);
+    sm.z[0][f][gf_fpad(k)] = Zk;
+    if (k != 0) sm.z[0][f][gf_fpad(km)] = Zm;
+    gf_irfft_merge(B0, B1, w, Zk, Zm);
+    sm.z[1][f][gf_fpad(k)] = Zk;
+    if (k != 0) sm.z[1][f][gf_fpad(km)] = Zm;
 }
 
 // bin 256 (pairs with itself)
@@ -137,13 +111,41 @@ __device__ __forceinline__ void gf_shape_mid(GfFrameSmem &sm, int f, float f0f, 
         gf_irfft_merge(V, V, w, Zk, Zm);
         zf[gf_fpad(256)] = Zk;
     }
-    if (vo) { sm.stag[0][f][256] = H; sm.stag[1][f][256] = B; }
-    else {
-        gf_irfft_merge(H, H, w, Zk, Zm);
-        sm.z[0][f][gf_fpad(256)] = Zk;
-        gf_irfft_merge(B, B, w, Zk, Zm);
-        sm.z[1][f][gf_fpad(256)] = Zk;
-    }
+    gf_irfft_merge(H, H, w, Zk, Zm);
+    sm.z[0][f][gf_fpad(256)] = Zk;
+    gf_irfft_merge(B, B, w, Zk, Zm);
+    sm.z[1][f][gf_fpad(256)] = Zk;
+}
+
+// Brightness blur of the voiced frames (GOOFER.py:1143, 1171: 5-tap Gaussian, sigma 0.5, along the 513 bins of the
+// complex spectrum, numpy 'reflect' ends) WITHOUT a pass over the spectrum.  A symmetric convolution along frequency
+// of a Hermitian spectrum is a multiplication in time:  irfft(g * X) = G . irfft(X),
+//     G[n] = g[2] + 2 g[1] cos(2 pi n / 1024) + 2 g[0] cos(4 pi n / 1024)  in [0.57, 1],
+// which folds into the synthesis window of the overlap-add (d_tab.winG = win . G).  The reference's blur differs from
+// the Hermitian one only at the two ends: (i) 'reflect' continues the half spectrum with X[1], X[2] where the
+// Hermitian extension has their conjugates, (ii) it smears the imaginary parts of X[0] and X[512] (non-zero for the
+// noise spectra; irfft itself ignores them) into bins 1, 2, 510, 511.  Both are purely imaginary terms
+//     dY[1] = i (2 g0 Im X[1] + g1 Im X[0]),  dY[2] = i g0 Im X[0]     (mirrored at the top with X[512], X[511]);
+// pushed back through the inverse of the blur (taps q1, q2 = differences of IDFT(1 / G), decaying 7.4 x per bin,
+// < 3e-9 at 12 bins) they become imaginary additions to bins 1..12 and 500..511 of the pre-blur spectrum.  In exact
+// arithmetic the result equals the reference's (checked in numpy to 2e-14); rounding differs at the 1e-7 level.
+__device__ __forceinline__ void gf_blur_edges(GfFrameSmem &sm, int nf, const float2 *__restrict__ tw1024)
+{
+    const int tid = threadIdx.x;
+    const int k = 1 + tid % GF_BLUR_K, rest = tid / GF_BLUR_K, s = rest & 1, f = rest >> 1;
+    if (f >= nf || !sm.voiced[f]) return;
+    const float *e = sm.edge[s][f];
+    const float g0 = (float)d_tab.g05[0], g1 = (float)d_tab.g05[1];
+    const float p1 = 2.0f * g0 * e[1] + g1 * e[0], p2 = g0 * e[0];
+    const float p1t = 2.0f * g0 * e[3] + g1 * e[2], p2t = g0 * e[2];
+    const float q1 = d_tab.bq1[k], q2 = d_tab.bq2[k];
+    const float2 dXk = make_float2(0.0f, p1 * q1 + p2 * q2), dXm = make_float2(0.0f, p1t * q1 + p2t * q2);
+    float2 Zk, Zm;
+    gf_irfft_merge(dXk, dXm, tw1024[k], Zk, Zm);
+    float2 *z = &sm.z[s][f][0];
+    float2 &a = z[gf_fpad(k)], &b = z[gf_fpad(512 - k)];
+    a = gf_cadd(a, Zk);
+    b = gf_cadd(b, Zm);
 }
 
 // One round of the windowed overlap-add for one stream (GOOFER.py:372-390, 402-411).  Frames t0 .. t0+NF-1 sit
@@ -153,7 +155,8 @@ __device__ __forceinline__ void gf_shape_mid(GfFrameSmem &sm, int f, float f0f, 
 template <int NF>
 __device__ __forceinline__ void gf_ola_round(float (*carry)[GF_HOP], const float2 *bufs, const float *__restrict__ win,
                                              int t0, int T, int n_out, float *__restrict__ out, int b0, int nb, bool last,
-                                             bool no_input, const unsigned char *__restrict__ blk_dead, bool all_dead, float ws_full)
+                                             bool no_input, const unsigned char *__restrict__ blk_dead, bool all_dead, float ws_full,
+                                             const int *voiced /* per frame: use the blur-carrying window winG; NULL: never */)
 {
     const int r = threadIdx.x;
     float acc[NF + 3];
@@ -161,18 +164,19 @@ __device__ __forceinline__ void gf_ola_round(float (*carry)[GF_HOP], const float
     for (int m = 0; m < 3; ++m) acc[m] = carry[m][r];
 #pragma unroll
     for (int m = 3; m < NF + 3; ++m) acc[m] = 0.0f;
-    float w[4];
+    float w[4], wg[4];
 #pragma unroll
-    for (int q = 0; q < 4; ++q) w[q] = win[GF_HOP * q + r];
+    for (int q = 0; q < 4; ++q) { w[q] = win[GF_HOP * q + r]; wg[q] = voiced ? d_tab.winG[GF_HOP * q + r] : 0.0f; }
 #pragma unroll
     for (int f = 0; f < NF; ++f) {
         if (no_input) break;                               // skipped stream: only flush what earlier rounds carried
         const float *zf = reinterpret_cast<const float *>(bufs + (size_t)f * GF_FFT_BUF);
+        const bool blur = voiced && voiced[f];
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
             const int j = GF_HOP * q + r;
             const float v = zf[2 * gf_fpad(j >> 1) + (j & 1)] * (1.0f / 512.0f);
-            acc[f + q] = __fadd_rn(acc[f + q], __fmul_rn(v, w[q]));
+            acc[f + q] = __fadd_rn(acc[f + q], __fmul_rn(v, blur ? wg[q] : w[q]));
         }
     }
     const int n_emit = last ? NF + 1 : NF;                 // the final frame also finishes block T
@@ -304,31 +308,8 @@ gf_frame_kernel(const int4 *__restrict__ work, const GfPassDev *__restrict__ pas
                          nd.envN[(size_t)t * GF_ENVS_LD + 256], ps.phi[(size_t)256 * T + t], tw1024, local_max);
         }
         __syncthreads();
-        // ---- 4. voiced frames: 5-tap Gaussian along frequency, then merge ----
-        float g5[5];
-#pragma unroll
-        for (int j = 0; j < 5; ++j) g5[j] = (float)d_tab.g05[j];
-        for (int idx = tid; idx < nf * 256; idx += blockDim.x) {
-            int k, f;
-            if (nf == GF_RND) { k = idx >> 2; f = idx & 3; } else { k = idx / nf; f = idx - k * nf; }
-            if (!sm.voiced[f]) continue;
-            const int km = 512 - k;
-#pragma unroll
-            for (int s = 0; s < 2; ++s) {
-                const float2 *row = &sm.stag[s][f][0];
-                float2 Xk = gf_gauss5(row, k, g5), Xm = gf_gauss5(row, km, g5);
-                if (k == 0) { Xk.y = 0.f; Xm.y = 0.f; }
-                float2 Zk, Zm;
-                gf_irfft_merge(Xk, Xm, tw1024[k], Zk, Zm);
-                sm.z[s][f][gf_fpad(k)] = Zk;
-                if (k != 0) sm.z[s][f][gf_fpad(km)] = Zm;
-                if (k == 0) {
-                    const float2 Xq = gf_gauss5(row, 256, g5);
-                    gf_irfft_merge(Xq, Xq, tw1024[256], Zk, Zm);
-                    sm.z[s][f][gf_fpad(256)] = Zk;
-                }
-            }
-        }
+        // ---- 4. voiced frames: edge terms of the brightness blur (the blur itself rides on the synthesis window) ----
+        gf_blur_edges(sm, nf, tw1024);
         __syncthreads();
         // ---- 5. inverse FFTs (stream-major: transform q = s * GF_RND + f) ----
         const int n_streams = uv_on ? 3 : 2;
@@ -344,16 +325,16 @@ gf_frame_kernel(const int4 *__restrict__ work, const GfPassDev *__restrict__ pas
             const bool last = (t0 + nf - 1 == T - 1);
             if (nf == GF_RND) {
 #pragma unroll
-                for (int s = 0; s < 3; ++s) gf_ola_round<GF_RND>(sm.carry[s], &sm.z[s][0][0], win, t0, T, n, outs[s], b0, nb, last, s == 2 && !uv_on, s == 2 ? nd.ms_one : nullptr, s == 2 && ps.mask_ones, ws_full);
+                for (int s = 0; s < 3; ++s) gf_ola_round<GF_RND>(sm.carry[s], &sm.z[s][0][0], win, t0, T, n, outs[s], b0, nb, last, s == 2 && !uv_on, s == 2 ? nd.ms_one : nullptr, s == 2 && ps.mask_ones, ws_full, s < 2 ? sm.voiced : nullptr);
             } else if (nf == 3) {
 #pragma unroll
-                for (int s = 0; s < 3; ++s) gf_ola_round<3>(sm.carry[s], &sm.z[s][0][0], win, t0, T, n, outs[s], b0, nb, last, s == 2 && !uv_on, s == 2 ? nd.ms_one : nullptr, s == 2 && ps.mask_ones, ws_full);
+                for (int s = 0; s < 3; ++s) gf_ola_round<3>(sm.carry[s], &sm.z[s][0][0], win, t0, T, n, outs[s], b0, nb, last, s == 2 && !uv_on, s == 2 ? nd.ms_one : nullptr, s == 2 && ps.mask_ones, ws_full, s < 2 ? sm.voiced : nullptr);
             } else if (nf == 2) {
 #pragma unroll
-                for (int s = 0; s < 3; ++s) gf_ola_round<2>(sm.carry[s], &sm.z[s][0][0], win, t0, T, n, outs[s], b0, nb, last, s == 2 && !uv_on, s == 2 ? nd.ms_one : nullptr, s == 2 && ps.mask_ones, ws_full);
+                for (int s = 0; s < 3; ++s) gf_ola_round<2>(sm.carry[s], &sm.z[s][0][0], win, t0, T, n, outs[s], b0, nb, last, s == 2 && !uv_on, s == 2 ? nd.ms_one : nullptr, s == 2 && ps.mask_ones, ws_full, s < 2 ? sm.voiced : nullptr);
             } else {
 #pragma unroll
-                for (int s = 0; s < 3; ++s) gf_ola_round<1>(sm.carry[s], &sm.z[s][0][0], win, t0, T, n, outs[s], b0, nb, last, s == 2 && !uv_on, s == 2 ? nd.ms_one : nullptr, s == 2 && ps.mask_ones, ws_full);
+                for (int s = 0; s < 3; ++s) gf_ola_round<1>(sm.carry[s], &sm.z[s][0][0], win, t0, T, n, outs[s], b0, nb, last, s == 2 && !uv_on, s == 2 ? nd.ms_one : nullptr, s == 2 && ps.mask_ones, ws_full, s < 2 ? sm.voiced : nullptr);
             }
         }
         __syncthreads();

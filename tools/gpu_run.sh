@@ -1,10 +1,10 @@
 set -x
-python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu54.log 2>&1; echo "pytest rc=$?"
-tail -3 gpurun_out/pytest_gpu54.log
-python bench.py --steps 10 --warmup 3 --cpu-sample 0 > gpurun_out/bench54.log 2> gpurun_out/bench54.err; echo rc=$?
+python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu55.log 2>&1; echo "pytest rc=$?"
+tail -3 gpurun_out/pytest_gpu55.log
+python bench.py --steps 10 --warmup 3 --cpu-sample 0 > gpurun_out/bench55.log 2> gpurun_out/bench55.err; echo rc=$?
 python - <<'PY'
 import json
-for f in ("bench54",):
+for f in ("bench55",):
     d=json.load(open(f"gpurun_out/{f}.log"))
     print(f, d["value"], d["ms_per_step"], d.get("e2e",{}).get("ms_per_step"), d["gpu_launches"], d["roofline"]["kernels_ms_per_step"])
 PY
@@ -31,5 +31,5 @@ del os.environ["GOOFER_HOST_NO_PULL"]
 os.environ["GOOFER_HOST_TRACE"] = "1"
 ab.render_host(); ab.render_host()
 PY
-python /tmp/probe.py > gpurun_out/e2e54.log 2>&1
-grep -v "^\[host" gpurun_out/e2e54.log; tail -5 gpurun_out/e2e54.log
+python /tmp/probe.py > gpurun_out/e2e55.log 2>&1
+grep -v "^\[host" gpurun_out/e2e55.log; tail -5 gpurun_out/e2e55.log
