@@ -13,6 +13,9 @@
 
 #define GF_RND 4                      // frames per round (= FFT lanes)
 #define GF_FRAME_THREADS (64 * GF_RND)
+#ifndef GF_FRAME_CTAS
+#define GF_FRAME_CTAS 3                // resident CTAs per SM the register allocation aims at (65 KB of shared memory each)
+#endif
 #define GF_BLUR_K 12                  // reach of the edge correction of the time-domain blur (see gf_blur_edges)
 
 struct GfFrameSmem {
@@ -206,7 +209,7 @@ __device__ __forceinline__ void gf_ola_round(float (*carry)[GF_HOP], const float
 }
 
 // work item: x = pass index (into the wave's pass arrays), y = first owned block, z = block count
-__global__ void __launch_bounds__(GF_FRAME_THREADS, 2)
+__global__ void __launch_bounds__(GF_FRAME_THREADS, GF_FRAME_CTAS)
 gf_frame_kernel(const int4 *__restrict__ work, const GfPassDev *__restrict__ passes, GfPassScal *scal,
                 const GfNoteDev *__restrict__ notes, const GfNotePlan *__restrict__ plans)
 {
