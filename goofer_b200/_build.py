@@ -8,7 +8,8 @@ import subprocess
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB_DIR = os.path.join(HERE, "_lib")
-LIB_PATH = os.path.join(LIB_DIR, "libgoofer_b200.so")
+# GOOFER_B200_LIB: load another build of the same sources (tools/build_variants.py: tuning experiments on the GPU box)
+LIB_PATH = os.environ.get("GOOFER_B200_LIB") or os.path.join(LIB_DIR, "libgoofer_b200.so")
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "--extended-lambda",
@@ -31,6 +32,8 @@ def _newest_source_mtime() -> float:
 
 def build(force: bool = False, verbose: bool = False) -> str:
     """Compile the CUDA library in-tree.  Needs nvcc (cross-compiles without a GPU)."""
+    if os.environ.get("GOOFER_B200_LIB"):
+        return LIB_PATH
     if not force and os.path.exists(LIB_PATH) and os.path.getmtime(LIB_PATH) >= _newest_source_mtime():
         return LIB_PATH
     nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"

@@ -322,7 +322,10 @@ static size_t gf_wave_meta_bytes(size_t n_notes, size_t n_pass, size_t n_env_wor
            n_pass * 16 * sizeof(GfOnepoleJob) + n_notes * (3 * sizeof(int) + 2 * sizeof(GfFirJob)) + 32 * 256;
 }
 
-#define GF_BLOCKS_PER_CTA 64      // at most this many output hop blocks per frame-kernel CTA (3 frames of halo each)
+#ifndef GF_BLOCKS_PER_CTA
+#define GF_BLOCKS_PER_CTA 90      // at most this many output hop blocks per frame-kernel CTA (3 frames of halo each); a 1 s note
+                                  // (172 blocks) splits in 2 x 86: 1.97 -> 1.89 ms against 3 x 58 (cap 64)
+#endif
 
 // balanced split of a note's hop blocks: as few CTAs as the cap allows, equal shares
 static inline int gf_blocks_per_cta(int n_blocks)

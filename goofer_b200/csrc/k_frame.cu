@@ -277,22 +277,28 @@ gf_frame_kernel(const int4 *__restrict__ work, const GfPassDev *__restrict__ pas
         // ---- 3. shaping, per bin pair (k, 512 - k); bin 256 pairs with itself and goes to threads 0..nf-1 ----
         if (nf == GF_RND) {
             // item m of this thread: k = (tid >> 2) + 64 m, frame f = tid & 3.  All global operands of the four
-            // items are requested up front (24 loads in flight per thread) before any of them is consumed.
+            // items of a batch are requested up front (12 loads in flight per thread) before any of them is consumed.
             const int f = tid & 3, t = t0 + f;
             const float *eF = nd.envF + (size_t)t * GF_ENVS_LD, *eN = nd.envN + (size_t)t * GF_ENVS_LD;
             const float *ph = ps.phi + t;
-            GfShapeIn in[4];
-#pragma unroll
-            for (int m = 0; m < 4; ++m) {
-                const int k = (tid >> 2) + 64 * m, km = 512 - k;
-                in[m].ef[0] = eF[k];  in[m].ef[1] = eF[km];
-                in[m].en[0] = eN[k];  in[m].en[1] = eN[km];
-                in[m].ph[0] = ph[(size_t)k * T];  in[m].ph[1] = ph[(size_t)km * T];
-            }
+#ifndef GF_SHAPE_BATCH
+#define GF_SHAPE_BATCH 2              // bin pairs whose global operands are requested together (6 loads each)
+#endif
             const float f0f = sm.f0fr[f];
             const bool vo = sm.voiced[f] != 0;
 #pragma unroll
-            for (int m = 0; m < 4; ++m) gf_shape_pair(sm, (tid >> 2) + 64 * m, f, f0f, vo, uv_on, in[m], tw1024, local_max);
+            for (int m0 = 0; m0 < 4; m0 += GF_SHAPE_BATCH) {
+                GfShapeIn in[GF_SHAPE_BATCH];
+#pragma unroll
+                for (int m = 0; m < GF_SHAPE_BATCH; ++m) {
+                    const int k = (tid >> 2) + 64 * (m0 + m), km = 512 - k;
+                    in[m].ef[0] = eF[k];  in[m].ef[1] = eF[km];
+                    in[m].en[0] = eN[k];  in[m].en[1] = eN[km];
+                    in[m].ph[0] = ph[(size_t)k * T];  in[m].ph[1] = ph[(size_t)km * T];
+                }
+#pragma unroll
+                for (int m = 0; m < GF_SHAPE_BATCH; ++m) gf_shape_pair(sm, (tid >> 2) + 64 * (m0 + m), f, f0f, vo, uv_on, in[m], tw1024, local_max);
+            }
         } else {
             for (int idx = tid; idx < nf * 256; idx += blockDim.x) {
                 const int k = idx / nf, f = idx - k * nf, km = 512 - k, t = t0 + f;

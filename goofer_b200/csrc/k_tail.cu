@@ -84,8 +84,11 @@ __device__ __forceinline__ bool gf_tail_simple(const GfNotePlan &pl, const GfNot
     return pl.n_passes == 1 && !pl.vol_jitter && nd.fx[0] == nullptr && nd.pd_dev == nullptr && nd.tap_harm == nullptr;
 }
 
+#ifndef GF_TAIL_CTAS
+#define GF_TAIL_CTAS 6                // register cap 40: both kernels wait on HBM loads
+#endif
 template <bool SIMPLE>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, GF_TAIL_CTAS)
 gf_peak_kernel(const GfNotePlan *__restrict__ plans, const GfNoteDev *__restrict__ notes, const GfPassDev *__restrict__ passes,
                GfPassScal *scal, int pass0)
 {
@@ -130,7 +133,7 @@ __device__ __forceinline__ float gf_pass_gain(const GfNotePlan &pl, const GfPass
 // stage 1 of the tail: normalised streams of every pass -> fx scratch (only for notes that need the
 // sequential filters); stage 2: mix.  Notes without filters go straight through gf_mix_kernel.
 template <bool SIMPLE>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, GF_TAIL_CTAS)
 gf_mix_kernel(const GfNotePlan *__restrict__ plans, const GfNoteDev *__restrict__ notes, const GfPassDev *__restrict__ passes,
               const GfPassScal *__restrict__ scal, int note0)
 {

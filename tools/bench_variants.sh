@@ -1,0 +1,19 @@
+# bench every variant library in goofer_b200/_lib/variants/ (kernel-only, no e2e, no CPU leg) and print one line each
+for f in goofer_b200/_lib/variants/*.so; do
+  n=$(basename $f .so)
+  GOOFER_B200_LIB=$PWD/$f python bench.py --steps 8 --warmup 3 --cpu-sample 0 --no-e2e > gpurun_out/var_$n.log 2> gpurun_out/var_$n.err
+  python - "$n" <<'PY'
+import json, sys
+n = sys.argv[1]
+try:
+    d = json.load(open(f"gpurun_out/var_{n}.log"))
+    k = d["roofline"]["kernels_ms_per_step"]
+    print(f"{n:12s} {d['ms_per_step']:.3f} ms  " + " ".join(f"{a}={b:.3f}" for a, b in k.items()))
+except Exception as e:
+    print(n, "FAILED", e)
+PY
+done
+# parity of the pulse stage for the fast-intrinsics variant, when present
+if [ -f goofer_b200/_lib/variants/pulsefast.so ]; then
+  GOOFER_B200_LIB=$PWD/goofer_b200/_lib/variants/pulsefast.so python -m pytest tests -m gpu -x -q 2>&1 | tail -3
+fi
