@@ -215,11 +215,11 @@ extern "C" int goofer_render_batch_host(const GooferBatch *b)
     }
 
     // ---- parts: runs of consecutive notes whose phases travel together ----
-    // Measured on B200 (c2, 1,024 notes): the phase upload (7.3 ms at 52 GB/s) and the compute stream (7.8 ms) finish
-    // together; what follows the last phase byte is the last part's frame / peak / mix and its download, so equal
-    // quarters (9.3 ms) beat both fewer parts and a graded 50 / 25 / 15 / 10 split (10.0 ms: its 5.1 ms first mix holds
-    // the download pipeline back).  GOOFER_HOST_CHUNK = uniform parts of that many notes; GOOFER_HOST_PARTS =
-    // comma-separated cumulative fractions.
+    // Measured on B200 (c2, 1,024 notes, 5.7 ms of kernels): the phase upload takes 7.4 ms (380 MB at 52 GB/s) and the
+    // download 4.5 ms (180 MB at ~40 GB/s while the upload runs); the first output exists only after the preparation
+    // kernels of the whole batch (~4 ms).  Small equal parts start the download early and leave little to do after the
+    // last phase byte: 8 parts 8.7 ms, 4 parts 9.3 ms, graded 50/25/15/10 10.0 ms.  GOOFER_HOST_CHUNK = uniform parts of
+    // that many notes; GOOFER_HOST_PARTS = comma-separated cumulative fractions.
     std::vector<int> ends;                                 // note_end of every part, ascending, last == n_notes
     {
         const int nn = b->n_notes;
@@ -235,6 +235,8 @@ extern "C" int goofer_render_batch_host(const GooferBatch *b)
                 if (v > (ends.empty() ? 0 : ends.back()) && v < nn) ends.push_back(v);
                 q = (*nx == ',') ? nx + 1 : nx;
             }
+        } else if (nn >= 1024) {
+            for (int k = 1; k < 8; ++k) ends.push_back((int)((int64_t)nn * k / 8));
         } else if (nn >= 512) {
             ends = {nn / 4, nn / 2, (3 * nn) / 4};
         } else if (nn >= 128) {
