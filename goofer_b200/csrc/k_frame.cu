@@ -169,7 +169,8 @@ __device__ __forceinline__ void gf_ola_round(float (*carry)[GF_HOP], const float
     for (int m = 3; m < NF + 3; ++m) acc[m] = 0.0f;
     float w[4], wg[4];
 #pragma unroll
-    for (int q = 0; q < 4; ++q) { w[q] = win[GF_HOP * q + r]; wg[q] = voiced ? d_tab.winG[GF_HOP * q + r] : 0.0f; }
+    // the 1/512 of the unnormalised inverse FFT is folded into the window: scaling by a power of two commutes with rounding
+    for (int q = 0; q < 4; ++q) { w[q] = win[GF_HOP * q + r] * (1.0f / 512.0f); wg[q] = voiced ? d_tab.winG[GF_HOP * q + r] * (1.0f / 512.0f) : 0.0f; }
 #pragma unroll
     for (int f = 0; f < NF; ++f) {
         if (no_input) break;                               // skipped stream: only flush what earlier rounds carried
@@ -178,7 +179,7 @@ __device__ __forceinline__ void gf_ola_round(float (*carry)[GF_HOP], const float
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
             const int j = GF_HOP * q + r;
-            const float v = zf[2 * gf_fpad(j >> 1) + (j & 1)] * (1.0f / 512.0f);
+            const float v = zf[2 * gf_fpad(j >> 1) + (j & 1)];
             acc[f + q] = __fadd_rn(acc[f + q], __fmul_rn(v, blur ? wg[q] : w[q]));
         }
     }
