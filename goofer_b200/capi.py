@@ -62,6 +62,7 @@ class GooferBatch(C.Structure):
         ("normals", C.c_void_p), ("nrm_total", C.c_int64),
         ("out", C.c_void_p), ("out_total", C.c_int64),
         ("tap_harm", C.c_void_p), ("tap_uv", C.c_void_p), ("tap_bre", C.c_void_p),
+        ("out_pcm16", C.c_void_p),
     ]
 
 

@@ -35,8 +35,20 @@ def feature_path(in_wav) -> Path:
     return p.with_name(f"{p.stem}_features.goofy")
 
 
+def pcm16_like_soundfile(samples: np.ndarray) -> np.ndarray:
+    """float -> int16 the way `sf.write(path.wav, x, sr)` does it (SillySampler.py:1185): python-soundfile turns
+    libsndfile's clipping on, and pcm.c d2s_clip_array then computes saturate(lrint(x * 2^31)) >> 16.  Host-side
+    restatement of the device encoder (k_tail.cu gf_pcm16); the CLI itself receives PCM from the device."""
+    s = np.asarray(samples, dtype=np.float64) * 2147483648.0
+    v = np.rint(np.clip(s, -2147483648.0, 2147483647.0)).astype(np.int64) >> 16
+    v = np.where(s >= 2147483647.0, 0x7FFF, v)
+    return np.clip(v, -0x8000, 0x7FFF).astype("<i2")
+
+
 def write_wav_pcm16(path, samples: np.ndarray, sr: int) -> None:
-    pcm = np.clip(np.rint(np.asarray(samples, dtype=np.float64) * 32767.0), -32768, 32767).astype("<i2")
+    """Write a mono 16-bit wav; `samples` is int16 PCM (from the device) or float (encoded like soundfile would)."""
+    a = np.asarray(samples)
+    pcm = a.astype("<i2") if a.dtype == np.int16 else pcm16_like_soundfile(a)
     with wave.open(str(path), "wb") as w:
         w.setnchannels(1)
         w.setsampwidth(2)
@@ -44,8 +56,9 @@ def write_wav_pcm16(path, samples: np.ndarray, sr: int) -> None:
         w.writeframes(pcm.tobytes())
 
 
-def render_notes(arg_lists: Sequence[Sequence[str]], noise=None, device: str = "cuda:0") -> List[np.ndarray]:
-    """Render many resampler invocations (each the 13 CLI strings) as ONE batch; returns the sample arrays."""
+def render_notes(arg_lists: Sequence[Sequence[str]], noise=None, device: str = "cuda:0", pcm16: bool = False) -> List[np.ndarray]:
+    """Render many resampler invocations (each the 13 CLI strings) as ONE batch; returns the sample arrays
+    (float32, or int16 PCM encoded on the device with pcm16=True)."""
     batch = host.Batch()
     src_index = {}
     for args in arg_lists:
@@ -60,8 +73,10 @@ def render_notes(arg_lists: Sequence[Sequence[str]], noise=None, device: str = "
         batch.add_note(host.NoteArgs.from_cli(src_index[key], list(args[2:13])))
     ab = batch.assemble(noise or host.FreshNoise())
     db = ab.to_device(device)
+    if pcm16:
+        db.enable_pcm16()
     db.render()
-    return db.outputs()
+    return db.outputs_pcm16() if pcm16 else db.outputs()
 
 
 def main(argv: Sequence[str]) -> int:
@@ -74,7 +89,7 @@ def main(argv: Sequence[str]) -> int:
             raise TypeError(f"Expected 13 arguments but got {len(args)}")
         logging.info("Loading cached features")
         logging.info("Synthesizing")
-        out = render_notes([args[:13]])[0]
+        out = render_notes([args[:13]], pcm16=True)[0]
         sr = host.load_goofy(feature_path(args[0])).sr
         logging.info(f"Writing {args[1]}")
         write_wav_pcm16(args[1], out, sr)

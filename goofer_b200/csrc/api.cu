@@ -549,7 +549,8 @@ static int gf_render_wave(const GooferBatch *b, const std::vector<GfNotePlan> &a
         GfNoteDev &nd = wh.notes[i];
         nd.noteScal = d_nscal + (size_t)i * GF_NS_COUNT;
         nd.pass0 = (int)pi;
-        nd.out = b->out + p.out_off;
+        nd.out = b->out ? b->out + p.out_off : nullptr;
+        nd.pcm = b->out_pcm16 ? b->out_pcm16 + p.out_off : nullptr;
         if (b->tap_harm && b->tap_uv && b->tap_bre) {
             nd.tap_harm = b->tap_harm + p.out_off; nd.tap_uv = b->tap_uv + p.out_off; nd.tap_bre = b->tap_bre + p.out_off;
         }
@@ -704,7 +705,7 @@ static int gf_render_batch_ex(const GooferBatch *b, void *workspace, size_t work
     if (rc != GOOFER_OK) return rc;
     g_stats.kernel_launches = 0; g_stats.waves = 0;
     if (b->n_notes == 0) return GOOFER_OK;
-    if (!workspace || !b->out || !b->phi || !b->bend_cents) { gf_set_error("NULL workspace / out / phi / bend_cents"); return GOOFER_ERR_INVALID; }
+    if (!workspace || (!b->out && !b->out_pcm16) || !b->phi || !b->bend_cents) { gf_set_error("NULL workspace / out (and out_pcm16) / phi / bend_cents"); return GOOFER_ERR_INVALID; }
     std::vector<GfNotePlan> plans;
     if ((rc = gf_make_plans(b, plans)) != GOOFER_OK) return rc;
     for (int i = 0; i < b->n_notes; ++i) {

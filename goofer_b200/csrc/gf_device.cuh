@@ -91,7 +91,8 @@ struct GfNoteDev {
     int2 *sg_tab;           // (sg_tab_n,) open-addressing table: x = key, y = first event index
     int sg_cap, sg_tab_n;
     double *noteScal;       // small per-note double scalars (maxima, rms)
-    float *out;             // (n_total,) final output
+    float *out;             // (n_total,) final output (or NULL when only PCM is wanted)
+    short *pcm;             // (n_total,) 16-bit PCM of the final output or NULL
     float *tap_harm, *tap_uv, *tap_bre;
     int pass0;              // first entry of this note in the pass arrays
 };

@@ -82,7 +82,7 @@ extern "C" int goofer_render_batch_host(const GooferBatch *b)
     if (rc != GOOFER_OK) return rc;
     g_stats.h2d_bytes = 0; g_stats.d2h_bytes = 0; g_stats.kernel_launches = 0; g_stats.waves = 0;
     if (b->n_notes == 0) return GOOFER_OK;
-    if (!b->out || !b->phi || !b->bend_cents) { gf_set_error("NULL out / phi / bend_cents"); return GOOFER_ERR_INVALID; }
+    if ((!b->out && !b->out_pcm16) || !b->phi || !b->bend_cents) { gf_set_error("NULL out (and out_pcm16) / phi / bend_cents"); return GOOFER_ERR_INVALID; }
     if (!g_hc.st) GF_CUDA(cudaStreamCreateWithFlags(&g_hc.st, cudaStreamNonBlocking));
     if (!g_hc.st_in) GF_CUDA(cudaStreamCreateWithFlags(&g_hc.st_in, cudaStreamNonBlocking));
     if (!g_hc.st_out) GF_CUDA(cudaStreamCreateWithFlags(&g_hc.st_out, cudaStreamNonBlocking));
@@ -123,7 +123,8 @@ extern "C" int goofer_render_batch_host(const GooferBatch *b)
         db.bend_cents = bp.arr<float>((size_t)b->bend_total);
         db.phi = bp.arr<float>((size_t)b->phi_total);
         db.normals = b->normals ? bp.arr<double>((size_t)b->nrm_total) : nullptr;
-        db.out = bp.arr<float>((size_t)b->out_total);
+        db.out = b->out ? bp.arr<float>((size_t)b->out_total) : nullptr;
+        db.out_pcm16 = b->out_pcm16 ? bp.arr<int16_t>((size_t)b->out_total) : nullptr;
         db.tap_harm = b->tap_harm ? bp.arr<float>((size_t)b->out_total) : nullptr;
         db.tap_uv = b->tap_uv ? bp.arr<float>((size_t)b->out_total) : nullptr;
         db.tap_bre = b->tap_bre ? bp.arr<float>((size_t)b->out_total) : nullptr;
@@ -302,7 +303,8 @@ extern "C" int goofer_render_batch_host(const GooferBatch *b)
         GF_CUDA(cudaStreamWaitEvent(st_out, g_hc.ev[2 * c + 1], 0));
         const int64_t olo = rg[c].olo;
         const size_t ob = sizeof(float) * (size_t)(rg[c].ohi - olo);
-        if ((rc = d2h(b->out + olo, db.out + olo, ob))) return rc;
+        if (b->out && (rc = d2h(b->out + olo, db.out + olo, ob))) return rc;
+        if (b->out_pcm16 && (rc = d2h(b->out_pcm16 + olo, db.out_pcm16 + olo, ob / 2))) return rc;
         if (b->tap_harm && (rc = d2h(b->tap_harm + olo, db.tap_harm + olo, ob))) return rc;
         if (b->tap_uv && (rc = d2h(b->tap_uv + olo, db.tap_uv + olo, ob))) return rc;
         if (b->tap_bre && (rc = d2h(b->tap_bre + olo, db.tap_bre + olo, ob))) return rc;

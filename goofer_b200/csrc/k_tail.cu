@@ -130,6 +130,17 @@ __device__ __forceinline__ float gf_pass_gain(const GfNotePlan &pl, const GfPass
     return (float)pow(1.0 / (double)pk, nrm);
 }
 
+// 16-bit PCM of one output sample the way SillySampler.py:1185 stores it: sf.write(.wav) -> libsndfile PCM_16 with
+// clipping enabled by python-soundfile (SFC_SET_CLIPPING): pcm.c d2s_clip_array scales by 2^31, saturates, rounds to
+// nearest (lrint, ties to even) and keeps the high 16 bits.  x * 2^31 is exact in fp64 for an f32 x.
+__device__ __forceinline__ short gf_pcm16(float x)
+{
+    const double s = (double)x * 2147483648.0;
+    if (s >= 2147483647.0) return (short)0x7fff;
+    if (s <= -2147483648.0) return (short)-0x8000;
+    return (short)(__double2ll_rn(s) >> 16);              // NaN -> 0
+}
+
 // stage 1 of the tail: normalised streams of every pass -> fx scratch (only for notes that need the
 // sequential filters); stage 2: mix.  Notes without filters go straight through gf_mix_kernel.
 template <bool SIMPLE>
@@ -165,6 +176,7 @@ gf_mix_kernel(const GfNotePlan *__restrict__ plans, const GfNoteDev *__restrict_
     const float Bf = (float)pl.B, Uf = (float)pl.U, volf = (float)pl.volume;
     // the caller's output (and tap) arrays start at any element offset: 16-byte stores only when aligned
     const bool out_vec = (((uintptr_t)nd.out) & 15) == 0;
+    const bool pcm_vec = (((uintptr_t)nd.pcm) & 7) == 0;
     const bool tap_vec = taps && ((((uintptr_t)nd.tap_harm) | ((uintptr_t)nd.tap_uv) | ((uintptr_t)nd.tap_bre)) & 15) == 0;
     for (int i = 4 * (blockIdx.x * blockDim.x + threadIdx.x); i < n; i += 4 * gridDim.x * blockDim.x) {
         const int cnt = min(4, n - i);
@@ -208,11 +220,24 @@ gf_mix_kernel(const GfNotePlan *__restrict__ plans, const GfNoteDev *__restrict_
                     if (k < cnt) { nd.tap_harm[i + k] = th[k]; nd.tap_uv[i + k] = tu[k]; nd.tap_bre[i + k] = tb[k]; }
             }
         }
-        if (cnt == 4 && out_vec) *reinterpret_cast<float4 *>(nd.out + i) = make_float4(o[0], o[1], o[2], o[3]);
-        else {
+        if (nd.out) {
+            if (cnt == 4 && out_vec) *reinterpret_cast<float4 *>(nd.out + i) = make_float4(o[0], o[1], o[2], o[3]);
+            else {
 #pragma unroll
-            for (int k = 0; k < 4; ++k)
-                if (k < cnt) nd.out[i + k] = o[k];
+                for (int k = 0; k < 4; ++k)
+                    if (k < cnt) nd.out[i + k] = o[k];
+            }
+        }
+        if (nd.pcm) {
+            short q[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) q[k] = gf_pcm16(o[k]);
+            if (cnt == 4 && pcm_vec) *reinterpret_cast<short4 *>(nd.pcm + i) = make_short4(q[0], q[1], q[2], q[3]);
+            else {
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                    if (k < cnt) nd.pcm[i + k] = q[k];
+            }
         }
     }
 }

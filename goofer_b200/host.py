@@ -388,6 +388,7 @@ class AssembledBatch:
                     g.formants[k] = pinned(tr).ctypes.data
         n_out = 4 if self.taps else 1
         self._out_bufs = [pinned(np.empty(max(1, self.out_total), dtype=np.float32)) for _ in range(n_out)]
+        self._pcm_buf = pinned(np.empty(max(1, self.out_total), dtype=np.int16))
         return self
 
     def split(self, flat: np.ndarray) -> List[np.ndarray]:
@@ -398,8 +399,24 @@ class AssembledBatch:
         return outs
 
     # ---- host-buffer entry point (numpy in, numpy out; copies inside the C library) ---------------
-    def render_host(self):
+    def render_host(self, pcm16: bool = False):
+        """numpy in, numpy out through goofer_render_batch_host.  pcm16=True returns the notes as int16 PCM encoded
+        on the device (what SillySampler.py:1185 writes to the .wav) and downloads half the bytes."""
         lib = capi.load()
+        if pcm16:
+            if self.taps:
+                raise ValueError("stage taps are f32: render with pcm16=False")
+            pcm = getattr(self, "_pcm_buf", None)
+            if pcm is None:
+                pcm = self._pcm_buf = np.empty(max(1, self.out_total), dtype=np.int16)
+            d = self.desc
+            d.out, d.out_pcm16 = None, pcm.ctypes.data
+            d.tap_harm = d.tap_uv = d.tap_bre = None
+            try:
+                capi.check(lib.goofer_render_batch_host(C.byref(d)))
+            finally:
+                d.out_pcm16 = None
+            return self.split(pcm[:self.out_total])
         bufs = getattr(self, "_out_bufs", None)
         out = bufs[0] if bufs else np.empty(max(1, self.out_total), dtype=np.float32)
         d = self.desc
@@ -459,6 +476,7 @@ class DeviceBatch:
         self.phi = up(ab.phi)
         self.normals = up(ab.normals) if ab.normals is not None else None
         self.out = torch.empty(max(1, ab.out_total), dtype=torch.float32, device=dev)
+        self.pcm = None                                    # int16 PCM copy of out, allocated by enable_pcm16()
         self.tap = [torch.empty_like(self.out) for _ in range(3)] if ab.taps else None
         d = capi.GooferBatch()
         h = ab.desc
@@ -487,6 +505,18 @@ class DeviceBatch:
                                                C.c_void_p(stream)))
         return self.out
 
+    def enable_pcm16(self) -> "DeviceBatch":
+        """Also encode the output as 16-bit PCM on the device (GooferBatch.out_pcm16); read it with outputs_pcm16()."""
+        if self.pcm is None:
+            self.pcm = self.torch.empty(max(1, self.ab.out_total), dtype=self.torch.int16, device=self.device)
+            self.desc.out_pcm16 = self.pcm.data_ptr()
+        return self
+
     def outputs(self) -> List[np.ndarray]:
         flat = self.out[:self.ab.out_total].cpu().numpy()
         return self.ab.split(flat)
+
+    def outputs_pcm16(self) -> List[np.ndarray]:
+        if self.pcm is None:
+            raise RuntimeError("call enable_pcm16() before render()")
+        return self.ab.split(self.pcm[:self.ab.out_total].cpu().numpy())

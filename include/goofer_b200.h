@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define GOOFER_ABI_VERSION 1
+#define GOOFER_ABI_VERSION 2
 #define GOOFER_N_FFT 1024      /* SillySampler.py:14 */
 #define GOOFER_HOP 256         /* SillySampler.py:15 */
 #define GOOFER_N_BINS 513
@@ -130,6 +130,12 @@ typedef struct GooferBatch {
      * each (out_total,) f32 laid out like out: harmonic, aper_uv, aper_bre after normalisation
      * (the tuple gf.synthesize returns, GOOFER.py:1220) */
     float *tap_harm, *tap_uv, *tap_bre;
+    /* optional 16-bit PCM copy of `out`, (out_total,) int16, laid out like out (device/host like out; may be NULL).
+     * The step after the path: SillySampler.py:1185 `sf.write(out_file, out, sr)` stores PCM_16 for .wav.  Encoded on
+     * the device the way python-soundfile drives libsndfile (SFC_SET_CLIPPING on, pcm.c d2s_clip_array):
+     * saturate(lrint(x * 2^31)) >> 16.  When out_pcm16 is given, `out` may be NULL (the host entry point then
+     * downloads half the bytes). */
+    int16_t *out_pcm16;
 } GooferBatch;
 
 int goofer_version(void);

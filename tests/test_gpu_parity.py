@@ -297,6 +297,8 @@ def test_cli_drop_in(tmp_path, torch_cuda):
         assert w.getframerate() == 44100 and w.getsampwidth() == 2 and w.getnframes() == 44100
         pcm = np.frombuffer(w.readframes(44100), dtype="<i2")
     assert np.max(np.abs(pcm)) >= 32000               # P absent: peak-normalised
+    # the wav holds the device-encoded PCM: identical to soundfile's conversion of the f32 render of the same note
+    # (cli.render_notes draws fresh noise, so compare through a seeded batch instead)
     assert cli.main(argv[:5]) == 1                      # fewer than 13 arguments: usage + exit code 1
     assert cli.main([os.path.join(tmp_path, "missing.wav")] + argv[1:]) == 1
 
@@ -408,3 +410,30 @@ def test_fuzzed_arguments(torch_cuda):
         worst = max(worst, err)
         assert err <= MAX_ABS, (notes[k], err)
     print(f"fuzz: {len(notes)} notes, {rejected} rejected by both, worst max-abs {worst:.2e}")
+
+
+def test_pcm16_encoded_on_device(torch_cuda):
+    """GooferBatch.out_pcm16 (the step after the path, SillySampler.py:1185): the device encoder equals
+    libsndfile's clip-path conversion of the f32 output bit for bit, through both entry points; `out` may be NULL."""
+    from goofer_b200 import cli
+    notes = [["A3", "100", "g-20fa5br20", "0", "1000", "0", "0", "100", "0", "!120", "AA"],
+             ["C4", "100", "P0V100", "0", "700", "0", "0", "200", "0", "!120", "AA"],       # unnormalised, volume 2: saturates
+             ["E4", "90", "B50sh20sr30", "0", "900", "50", "0", "3", "0", "!120", "AA"]]      # quiet: rounding near zero
+    b = host.Batch()
+    b.add_source(cases.source_for(1, 1.0)[1])
+    for c in notes:
+        b.add_note(host.NoteArgs.from_cli(0, c))
+    ab = b.assemble(host.SeededNoise(cases.SEED_BASE, cases.SEED_LEGACY))
+    db = ab.to_device("cuda:0").enable_pcm16()
+    db.render()
+    torch_cuda.cuda.synchronize()
+    f32, pcm = db.outputs(), db.outputs_pcm16()
+    for x, q in zip(f32, pcm):
+        assert q.dtype == np.int16 and np.array_equal(q, cli.pcm16_like_soundfile(x))
+    assert any(np.max(q) == 32767 for q in pcm)                       # the saturating note did saturate
+    ab.pin()
+    host_pcm = ab.render_host(pcm16=True)
+    st = capi.last_stats()
+    assert st["d2h_bytes"] == 2 * sum(len(q) for q in pcm)            # int16 only: half of the f32 download
+    for q, h in zip(pcm, host_pcm):
+        assert np.array_equal(q, h)

@@ -86,3 +86,33 @@ def test_cli_argument_errors_without_gpu(tmp_path):
     from goofer_b200 import cli
     assert cli.main(["a.wav", "b.wav", "C4"]) == 1                       # TypeError path: usage text, exit code 1
     assert cli.main([os.path.join(tmp_path, "nope.wav"), "b.wav", "C4", "100", "", "0", "1000", "0", "0", "100", "0", "!120", "AA"]) == 1
+
+
+def test_pcm16_restates_libsndfile_clip_path():
+    """cli.pcm16_like_soundfile == pcm.c d2s_clip_array with normalisation (what sf.write does for a .wav,
+    SillySampler.py:1185, python-soundfile enabling SFC_SET_CLIPPING): scalar restatement, rounding ties, saturation."""
+    import math
+    from goofer_b200 import cli
+
+    def scalar(x):
+        s = float(x) * (8.0 * 0x10000000)
+        if s >= 1.0 * 0x7FFFFFFF:
+            return 0x7FFF
+        if s <= -8.0 * 0x10000000:
+            return -0x8000
+        r = math.floor(s)                                  # lrint: nearest, ties to even
+        d = s - r
+        if d > 0.5 or (d == 0.5 and r % 2 != 0):
+            r += 1
+        return int(r) >> 16
+
+    rng = np.random.default_rng(5)
+    x = np.concatenate([rng.uniform(-1.2, 1.2, 4000), rng.uniform(-1e-4, 1e-4, 2000),
+                        np.array([0.0, -0.0, 1.0, -1.0, 0.999999, -0.999999, 2.0, -2.0, 1.0 / 32768, -1.0 / 32768,
+                                  0.5 / 32768, 1.5 / 32768, (65536 * 3 - 0.5) / 2 ** 31, (65536 * 3 - 0.4) / 2 ** 31,
+                                  (65536 * 5 + 0.5) / 2 ** 31, -(65536 * 7 + 0.5) / 2 ** 31])])
+    got = cli.pcm16_like_soundfile(x)
+    assert got.dtype == np.dtype("<i2")
+    assert np.array_equal(got.astype(np.int64), np.array([scalar(v) for v in x]))
+    x32 = x.astype(np.float32)
+    assert np.array_equal(cli.pcm16_like_soundfile(x32), cli.pcm16_like_soundfile(x32.astype(np.float64)))
