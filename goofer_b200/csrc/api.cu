@@ -632,8 +632,12 @@ static int gf_render_wave(const GooferBatch *b, const std::vector<GfNotePlan> &a
         gf_launch_mask(d_plans, d_notes, d_srcs, nn, max_n, st); ++L; GF_STEP("mask");
         {
             double max_sigma = 25.0;
-            for (const GfFirJob &j : wh.fir) max_sigma = std::max(max_sigma, j.sigma);
-            gf_launch_fir(d_fir, (int)wh.fir.size(), max_n, max_sigma, st); ++L; GF_STEP("fir");
+            bool any64 = false, any32 = false;                // which of the two FIR kernels has work (gf_fir_is_f32 in k_prep.cu)
+            for (const GfFirJob &j : wh.fir) {
+                max_sigma = std::max(max_sigma, j.sigma);
+                ((!j.in_f64 && !j.maxabs && !j.in_cast_f32) ? any32 : any64) = true;
+            }
+            gf_launch_fir(d_fir, (int)wh.fir.size(), max_n, max_sigma, st, any64, any32); ++L; GF_STEP("fir");
         }
         gf_launch_f0(d_plans, d_notes, d_passes, d_srcs, b->bend_cents, b->normals, nn, max_n, st); ++L; GF_STEP("f0");
         gf_launch_walk(d_passes, d_scal, (int)n_pass, max_n, sr, st); ++L; GF_STEP("walk");

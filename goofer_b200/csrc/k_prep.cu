@@ -29,7 +29,10 @@ __global__ void __launch_bounds__(256) gf_src_env_kernel(const GfSourceDev *__re
     if (t0 >= s.T) return;
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
     const double fstep = 1024.0 * (1.0 / (double)d_tab.sr);     // rfftfreq: k / (n * d)
-    for (int bc = 0; bc < GF_NBINS; bc += 32) {
+    // one 32-frame x 32-bin tile per CTA (blockIdx.z = bin chunk): 17 times the CTAs of a loop over the chunks; the
+    // binary search is a chain of dependent loads and the kernel is latency bound
+    {
+        const int bc = blockIdx.z * 32;
         for (int i = ty; i < 32; i += 8) {
             const int b = bc + i, t = t0 + tx;
             float v = 0.0f;
@@ -58,14 +61,13 @@ __global__ void __launch_bounds__(256) gf_src_env_kernel(const GfSourceDev *__re
             const int t = t0 + i, b = bc + tx;
             if (t < s.T && b < GF_NBINS) s.envS[(size_t)t * GF_ENVS_LD + b] = tile[tx][i];
         }
-        __syncthreads();
     }
 }
 
 void gf_launch_src_env(const GfSourceDev *srcs, int n_src, int max_T, cudaStream_t st)
 {
     if (n_src <= 0 || max_T <= 0) return;
-    dim3 grid((max_T + 31) / 32, n_src);
+    dim3 grid((max_T + 31) / 32, n_src, (GF_NBINS + 31) / 32);
     gf_src_env_kernel<<<grid, 256, 0, st>>>(srcs);
 }
 
@@ -633,9 +635,12 @@ __global__ void __launch_bounds__(GF_F32_THREADS) gf_fir32_kernel(const GfFirJob
     // (sum of taps = 1 within 1e-16, rounded to f32), within 1e-7 in f32 -- return the exact value
     const int constant = __syncthreads_and(same);
     float out[GF_EPL];
-    gf_fir_rt<float>(row + radius, GF_EPL * threadIdx.x, taps, radius, out);
+    if (constant) {                                           // CTA-uniform: a voiced stretch (mask == 1) or silence
 #pragma unroll
-    for (int e = 0; e < GF_EPL; ++e) outb[GF_EPL * threadIdx.x + e] = constant ? first : out[e];
+        for (int e = 0; e < GF_EPL; ++e) out[e] = first;
+    } else gf_fir_rt<float>(row + radius, GF_EPL * threadIdx.x, taps, radius, out);
+#pragma unroll
+    for (int e = 0; e < GF_EPL; ++e) outb[GF_EPL * threadIdx.x + e] = out[e];
     __syncthreads();
     const int cnt = min(GF_F32_TILE, n - start);
     if (jb.out_f64) {
@@ -700,7 +705,7 @@ __global__ void __launch_bounds__(GF_F32_THREADS) gf_fir_kernel(const GfFirJob *
     }
 }
 
-void gf_launch_fir(const GfFirJob *jobs, int n_jobs, int max_n, double max_sigma, cudaStream_t st)
+void gf_launch_fir(const GfFirJob *jobs, int n_jobs, int max_n, double max_sigma, cudaStream_t st, bool any_f64, bool any_f32)
 {
     if (n_jobs <= 0 || max_n <= 0) return;
     const int radius = (int)(4.0 * max_sigma + 0.5);
@@ -711,7 +716,7 @@ void gf_launch_fir(const GfFirJob *jobs, int n_jobs, int max_n, double max_sigma
         attr = smem;
     }
     dim3 grid((max_n + GF_F32_TILE - 1) / GF_F32_TILE, n_jobs);
-    gf_fir_kernel<<<grid, GF_F32_THREADS, smem, st>>>(jobs);
+    if (any_f64) gf_fir_kernel<<<grid, GF_F32_THREADS, smem, st>>>(jobs);
     // f32 jobs
     const size_t smem32 = sizeof(float) * (size_t)((((2 * radius + 1 + 7) & ~7) + 8) + (2 * radius + GF_F32_TILE + 16) + GF_F32_TILE);
     static size_t attr32 = 0;
@@ -720,5 +725,5 @@ void gf_launch_fir(const GfFirJob *jobs, int n_jobs, int max_n, double max_sigma
         attr32 = smem32;
     }
     dim3 grid32((max_n + GF_F32_TILE - 1) / GF_F32_TILE, n_jobs);
-    gf_fir32_kernel<<<grid32, GF_F32_THREADS, smem32, st>>>(jobs);
+    if (any_f32) gf_fir32_kernel<<<grid32, GF_F32_THREADS, smem32, st>>>(jobs);
 }
