@@ -292,8 +292,14 @@ def run_native(args):
         if top[0]:
             per_launch_ms = top[1][1] / max(1, top[1][0])
             ach = algo_bytes / (per_launch_ms * 1e-3) / 1e9
+            traffic = None                                    # ncu DRAM bytes per launch of this kernel, when a capture of this workload is committed
+            try:
+                with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as fh:
+                    traffic = json.load(fh).get(f"{args.workload}:{args.notes}", {}).get(top[0])
+            except Exception:
+                pass
             roof = {"bound": "hbm", "kernel": top[0], "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                    "traffic": None, "peak_source": peak_src, "kernel_ms_per_launch": per_launch_ms,
+                    "traffic": traffic, "peak_source": peak_src, "kernel_ms_per_launch": per_launch_ms,
                     "algorithmic_bytes_per_launch": algo_bytes, "kernel_share_of_step": top[1][1] / tot_kernel_ms,
                     "step_algorithmic_gbs": algo_bytes * args.steps / (dev_ms * 1e-3) / 1e9,
                     "kernels_ms_per_step": {k: round(v[1] / args.steps, 4) for k, v in prof.items()}}
