@@ -310,8 +310,11 @@ __device__ __forceinline__ bool gf_walk_delta(double inc, int e, GfDelta &d, lon
     return false;
 }
 
+#ifndef GF_WALK_MINB
+#define GF_WALK_MINB 1
+#endif
 template <int WARPS>
-__global__ void __launch_bounds__(32 * WARPS)
+__global__ void __launch_bounds__(32 * WARPS, GF_WALK_MINB)
 gf_walk_kernel(const GfPassDev *__restrict__ passes, GfPassScal *scal, int n_pass, int sr_i)
 {
     // one CTA of WARPS warps per (note, pass); every warp keeps an identical copy of the walk state
