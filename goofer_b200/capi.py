@@ -43,6 +43,7 @@ class GooferNote(C.Structure):
         ("bend_off", C.c_int64), ("bend_len", C.c_int32),
         ("flag", C.c_int32 * GF_NFLAGS), ("present", C.c_uint64),
         ("phi_off", C.c_int64 * 4), ("nrm_off", C.c_int64 * 4), ("out_off", C.c_int64),
+        ("f0_off", C.c_int64),
     ]
 
 
@@ -63,6 +64,7 @@ class GooferBatch(C.Structure):
         ("out", C.c_void_p), ("out_total", C.c_int64),
         ("tap_harm", C.c_void_p), ("tap_uv", C.c_void_p), ("tap_bre", C.c_void_p),
         ("out_pcm16", C.c_void_p),
+        ("f0_curves", C.c_void_p), ("f0_total", C.c_int64),
     ]
 
 

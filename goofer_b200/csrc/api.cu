@@ -639,7 +639,7 @@ static int gf_render_wave(const GooferBatch *b, const std::vector<GfNotePlan> &a
             }
             gf_launch_fir(d_fir, (int)wh.fir.size(), max_n, max_sigma, st, any64, any32); ++L; GF_STEP("fir");
         }
-        gf_launch_f0(d_plans, d_notes, d_passes, d_srcs, b->bend_cents, b->normals, nn, max_n, st); ++L; GF_STEP("f0");
+        gf_launch_f0(d_plans, d_notes, d_passes, d_srcs, b->bend_cents, b->normals, b->f0_curves, nn, max_n, st); ++L; GF_STEP("f0");
         gf_launch_walk(d_passes, d_scal, (int)n_pass, max_n, sr, st); ++L; GF_STEP("walk");
         gf_launch_pulse(d_passes, d_scal, (int)n_pass, max_n, st); ++L; GF_STEP("pulse");
         if ((rc = gf_growl(wh, d_plans, d_notes, d_passes, d_scal, bp, max_n, st, &L)) != GOOFER_OK) return rc;
@@ -728,6 +728,7 @@ static int gf_render_batch_ex(const GooferBatch *b, void *workspace, size_t work
                 return GOOFER_ERR_INVALID;
             }
         if (p.out_off < 0 || p.out_off + p.n_total > b->out_total) { gf_set_error("note %d: output range outside the out buffer", i); return GOOFER_ERR_INVALID; }
+        if (p.f0_off >= 0 && (!b->f0_curves || p.f0_off + p.n_total > b->f0_total)) { gf_set_error("note %d: f0 curve missing or outside the f0_curves buffer", i); return GOOFER_ERR_INVALID; }
     }
     cudaStream_t st = (cudaStream_t)stream;
     if ((rc = gf_tables_init(plans[0].sr)) != 0) return rc;

@@ -80,4 +80,5 @@ struct GfNotePlan {
     int64_t phi_off[4];
     int64_t nrm_off[4];
     int64_t out_off;
+    int64_t f0_off;             // >= 0: direct gf.synthesize call, f0 curve at GooferBatch.f0_curves + f0_off (else -1)
 };

@@ -123,6 +123,7 @@ extern "C" int goofer_render_batch_host(const GooferBatch *b)
         db.bend_cents = bp.arr<float>((size_t)b->bend_total);
         db.phi = bp.arr<float>((size_t)b->phi_total);
         db.normals = b->normals ? bp.arr<double>((size_t)b->nrm_total) : nullptr;
+        db.f0_curves = b->f0_curves ? bp.arr<float>((size_t)b->f0_total) : nullptr;
         db.out = b->out ? bp.arr<float>((size_t)b->out_total) : nullptr;
         db.out_pcm16 = b->out_pcm16 ? bp.arr<int16_t>((size_t)b->out_total) : nullptr;
         db.tap_harm = b->tap_harm ? bp.arr<float>((size_t)b->out_total) : nullptr;
@@ -284,7 +285,8 @@ extern "C" int goofer_render_batch_host(const GooferBatch *b)
     // uploads: normals of every part (the preparation kernels of the whole batch need them), then the phases part by part
     for (int c = 0; c < n_chunks; ++c)
         if (rg[c].nhi > rg[c].nlo && (rc = h2d(db.normals + rg[c].nlo, b->normals + rg[c].nlo, sizeof(double) * (size_t)(rg[c].nhi - rg[c].nlo)))) return rc;
-    GF_CUDA(cudaEventRecord(g_hc.ev[2 * n_chunks], st_in));          // sources, bends, normals
+    if (b->f0_curves && b->f0_total > 0 && (rc = h2d(db.f0_curves, b->f0_curves, sizeof(float) * (size_t)b->f0_total))) return rc;
+    GF_CUDA(cudaEventRecord(g_hc.ev[2 * n_chunks], st_in));          // sources, bends, normals, f0 curves
     std::vector<GfPart> parts(n_chunks);
     for (int c = 0; c < n_chunks; ++c) {
         if ((rc = h2d(db.phi + rg[c].plo, b->phi + rg[c].plo, sizeof(float) * (size_t)(rg[c].phi - rg[c].plo)))) return rc;

@@ -90,7 +90,8 @@ __device__ __forceinline__ double gf_midi_at_fast(const float *__restrict__ bend
 #endif
 __global__ void __launch_bounds__(256, GF_F0_CTAS)
 gf_f0_kernel(const GfNotePlan *__restrict__ plans, const GfNoteDev *__restrict__ notes, const GfPassDev *__restrict__ passes,
-             const GfSourceDev *__restrict__ srcs, const float *__restrict__ bend_all, const double *__restrict__ normals)
+             const GfSourceDev *__restrict__ srcs, const float *__restrict__ bend_all, const double *__restrict__ normals,
+             const float *__restrict__ f0_curves)
 {
     const GfNotePlan &pl = plans[blockIdx.y];
     const GfNoteDev nd = notes[blockIdx.y];
@@ -115,7 +116,8 @@ gf_f0_kernel(const GfNotePlan *__restrict__ plans, const GfNoteDev *__restrict__
         pkind[p] = (p < npass) ? passes[nd.pass0 + p].kind : -1;
     }
     // ---- common case (c1 / c2 / c5 notes): one pass, no velocity stretch, fry, jitter or pitch dynamics ----
-    const bool simple = npass == 1 && !pl.vel_active && pl.fry_L <= 0 && !pl.f0_jitter && !nd.f0n && !nd.pd_in;
+    const float *__restrict__ f0_direct = pl.f0_off >= 0 ? f0_curves + pl.f0_off : nullptr;      // direct gf.synthesize call: f0_interp as given
+    const bool simple = npass == 1 && !pl.vel_active && pl.fry_L <= 0 && !pl.f0_jitter && !nd.f0n && !nd.pd_in && !f0_direct;
     if (simple) {
         float *__restrict__ out_f0 = pf0[0];
         float *__restrict__ out_ms = nd.ms;
@@ -153,7 +155,7 @@ gf_f0_kernel(const GfNotePlan *__restrict__ plans, const GfNoteDev *__restrict__
         const double m = pl.vel_active ? gf_mask_new(pl, mask_src, i) : (double)nd.vm[i];
         const double midi = flat ? midi_flat : gf_midi_at(pl, bend, i);
         const double hz = flat ? hz_flat : 440.0 * exp2(gf_div_by(midi - 69.0, 12.0, GF_RCP12));
-        double f0 = m * hz;
+        double f0 = f0_direct ? (double)f0_direct[i] : m * hz;
         // ---- vocal fry f0 override (SillySampler.py:890-934) ----
         if (pl.fry_L > 0) {
             const double base = pl.vh * (m > 0.0 ? 1.0 : 0.0);
@@ -202,13 +204,13 @@ gf_f0_kernel(const GfNotePlan *__restrict__ plans, const GfNoteDev *__restrict__
 }
 
 void gf_launch_f0(const GfNotePlan *plans, const GfNoteDev *notes, const GfPassDev *passes, const GfSourceDev *srcs,
-                  const float *bend, const double *normals, int n_notes, int max_n, cudaStream_t st)
+                  const float *bend, const double *normals, const float *f0_curves, int n_notes, int max_n, cudaStream_t st)
 {
     if (n_notes <= 0) return;
     // few fat CTAs per note (the per-CTA prologue reads three records) unless the batch is too small to fill the GPU
     const int gx = max(8, min(64, (1184 + n_notes - 1) / n_notes));
     dim3 grid(min(gx, (max_n + 255) / 256), n_notes);
-    gf_f0_kernel<<<grid, 256, 0, st>>>(plans, notes, passes, srcs, bend, normals);
+    gf_f0_kernel<<<grid, 256, 0, st>>>(plans, notes, passes, srcs, bend, normals, f0_curves);
 }
 
 // ------------------------------------------------------------------------------------------------

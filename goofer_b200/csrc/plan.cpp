@@ -118,10 +118,19 @@ int gf_plan_note(const GooferBatch *b, int idx, GfNotePlan *pl)
         off_u = nt.offset_s;
         cut_u = nt.cutoff_s;
     }
-    const long long s0 = py_int(off_u * sr);
-    const long long s1 = s0 + py_int(nt.consonant_s * sr);
-    const long long s2 = py_int(((cut_u < 0) ? (off_u - cut_u) : (dur - cut_u)) * sr);
-    const long long f0_ = py_floordiv(s0, GF_HOP), f1_ = py_floordiv(s1, GF_HOP), f2_ = py_floordiv(s2, GF_HOP);
+    long long s0 = py_int(off_u * sr);
+    long long s1 = s0 + py_int(nt.consonant_s * sr);
+    long long s2 = py_int(((cut_u < 0) ? (off_u - cut_u) : (dur - cut_u)) * sr);
+    long long f0_ = py_floordiv(s0, GF_HOP), f1_ = py_floordiv(s1, GF_HOP), f2_ = py_floordiv(s2, GF_HOP);
+    pl->f0_off = nt.f0_off;
+    const bool direct = nt.f0_off >= 0;
+    if (direct) {
+        // direct gf.synthesize call: env_spec, voicing_mask and the formant tracks are the whole source
+        // (GOOFER.py:986-1002), len(y) = N; nothing is sliced, looped or stretched
+        if (pl->reverse) { pl->status = GOOFER_NOTE_BAD_SOURCE; return 0; }
+        s0 = 0; s1 = 0; s2 = sc.N;
+        f0_ = 0; f1_ = 0; f2_ = sc.T;
+    }
     pl->fr0 = (int32_t)f0_; pl->fr1 = (int32_t)f1_; pl->fr2 = (int32_t)f2_;
     py_slice(f0_, f1_, sc.T, &pl->pre_f_a, &pl->pre_f_n);
     py_slice(f1_, f2_, sc.T, &pl->tail_f_a, &pl->tail_f_n);
@@ -129,8 +138,8 @@ int gf_plan_note(const GooferBatch *b, int idx, GfNotePlan *pl)
     py_slice(s1, s2, sc.N, &pl->tail_s_a, &pl->tail_s_n);
 
     // ---- loop lengths (SillySampler.py:625-712) ----
-    const long long want_samples = py_int(nt.length_s * sr);
-    const long long want_frames = py_int(std::ceil(nt.length_s * sr / GF_HOP));
+    const long long want_samples = direct ? (long long)sc.N : py_int(nt.length_s * sr);
+    const long long want_frames = direct ? (long long)sc.T : py_int(std::ceil(nt.length_s * sr / GF_HOP));
     pl->want_samples = (int32_t)want_samples;
     pl->want_frames = (int32_t)want_frames;
     const int have = pl->tail_f_n;
@@ -165,7 +174,7 @@ int gf_plan_note(const GooferBatch *b, int idx, GfNotePlan *pl)
     pl->n_total = pl->n0_total;
     pl->pre_new_f = pl->pre_f_n;
     pl->pre_new_s = pl->pre_s_n;
-    if (std::fabs(pl->vel - 1.0) > 1e-6 && pl->pre_f_n > 1 && pl->pre_s_n > 1) {
+    if (!direct && std::fabs(pl->vel - 1.0) > 1e-6 && pl->pre_f_n > 1 && pl->pre_s_n > 1) {
         pl->vel_active = 1;
         // _prefix_positions also needs n > 1, true here because pre_len > 1
         pl->pre_new_f = (int32_t)std::max(1LL, py_round(pl->pre_f_n * pl->vel));

@@ -150,6 +150,9 @@ class NoteArgs:
     modulation: float = 0.0
     tempo: str = "!120"
     pitch_string: str = "AA"
+    # direct gf.synthesize call (GooferNote.f0_off): per-sample f0 curve; the source is then used whole and the
+    # slicing / pitch arguments above are ignored (include/goofer_b200.h)
+    f0_curve: Optional[np.ndarray] = None
 
     @classmethod
     def from_cli(cls, source: int, args: Sequence[str]) -> "NoteArgs":
@@ -198,6 +201,7 @@ class NoteArgs:
         for k in range(4):
             nt.phi_off[k] = -1
             nt.nrm_off[k] = -1
+        nt.f0_off = -1
         return nt, bend
 
 
@@ -305,10 +309,23 @@ class Batch:
             bends.append(bend)
             off += bend.size
         bend_all = np.concatenate(bends) if bends else np.zeros(1, np.float32)
+        f0_parts, f0_off = [], 0
+        for i, nt in enumerate(self.notes):
+            if nt.f0_curve is not None:
+                c = np.ascontiguousarray(nt.f0_curve, dtype=np.float32).reshape(-1)
+                if c.size != self.sources[nt.source].mask.size:
+                    raise ValueError(f"note {i}: the f0 curve has {c.size} samples, the source's voicing mask "
+                                     f"{self.sources[nt.source].mask.size} (gf.synthesize: len(f0_interp) == len(voicing_mask))")
+                note_arr[i].f0_off = f0_off
+                f0_parts.append(c)
+                f0_off += c.size
+        f0_all = np.concatenate(f0_parts) if f0_parts else None
         b = capi.GooferBatch()
         b.n_sources, b.sources = n_src, src_arr
         b.n_notes, b.notes = n_notes, note_arr
         b.bend_cents, b.bend_total = bend_all.ctypes.data, int(bend_all.size)
+        if f0_all is not None:
+            b.f0_curves, b.f0_total = f0_all.ctypes.data, int(f0_all.size)
         info_arr = (capi.GooferNotePlanInfo * max(1, n_notes))()
         capi.check(lib.goofer_plan_batch(C.byref(b), info_arr))
         infos = [{"n_total": int(x.n_total), "t_out": int(x.t_out), "t_env": int(x.t_env), "n_passes": int(x.n_passes),
@@ -338,7 +355,9 @@ class Batch:
             out_off += inf["n_total"]
         phi_all = np.concatenate(phi_parts) if phi_parts else np.zeros(1, np.float32)
         nrm_all = np.concatenate(nrm_parts) if nrm_parts else None
-        return AssembledBatch(self, b, src_arr, note_arr, infos, bend_all, phi_all, nrm_all, out_off, taps)
+        ab = AssembledBatch(self, b, src_arr, note_arr, infos, bend_all, phi_all, nrm_all, out_off, taps)
+        ab.f0_curves = f0_all
+        return ab
 
 
 class AssembledBatch:
@@ -374,6 +393,9 @@ class AssembledBatch:
         if self.normals is not None:
             self.normals = pinned(self.normals)
             d.normals = self.normals.ctypes.data
+        if getattr(self, "f0_curves", None) is not None:
+            self.f0_curves = pinned(self.f0_curves)
+            d.f0_curves = self.f0_curves.ctypes.data
         for i, s in enumerate(self.batch.sources):
             g = self.src_arr[i]
             if s.knots_log is not None:
@@ -475,6 +497,7 @@ class DeviceBatch:
         self.bend = up(ab.bend)
         self.phi = up(ab.phi)
         self.normals = up(ab.normals) if ab.normals is not None else None
+        self.f0_curves = up(ab.f0_curves) if getattr(ab, "f0_curves", None) is not None else None
         self.out = torch.empty(max(1, ab.out_total), dtype=torch.float32, device=dev)
         self.pcm = None                                    # int16 PCM copy of out, allocated by enable_pcm16()
         self.tap = [torch.empty_like(self.out) for _ in range(3)] if ab.taps else None
@@ -486,6 +509,8 @@ class DeviceBatch:
         d.phi, d.phi_total = self.phi.data_ptr(), h.phi_total
         d.normals, d.nrm_total = (self.normals.data_ptr() if self.normals is not None else None), h.nrm_total
         d.out, d.out_total = self.out.data_ptr(), h.out_total
+        if self.f0_curves is not None:
+            d.f0_curves, d.f0_total = self.f0_curves.data_ptr(), h.f0_total
         if self.tap:
             d.tap_harm, d.tap_uv, d.tap_bre = (t.data_ptr() for t in self.tap)
         self.desc = d

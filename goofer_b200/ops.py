@@ -5,6 +5,7 @@
     pulse_train(f0, sr) gf.pulse_train_numba  GOOFER.py:473-554
     onepole(...)        dynamic_butter_filter SillySampler.py:95-174
     analyse_envelope(y) envelope half of gf.extract_features + gf.compress_env_to_knots  GOOFER.py:940-946, 97-147
+    synthesize(...)     gf.synthesize         GOOFER.py:971-1220  (the call SillyEditor.py:227, 559 and test.py:38 make)
 torch is used for device memory and the stream only.
 """
 from __future__ import annotations
@@ -101,3 +102,84 @@ def analyse_envelope(y, sr: int = 44100):
     knots_h, hz_h = knots.cpu().numpy(), hz.cpu().numpy()
     return [{"mode": "knots", "knot_vals_log": np.ascontiguousarray(knots_h[b, :Kh[b]]), "hz_knots": np.ascontiguousarray(hz_h[b, :Kh[b]]),
              "n_bins": N_BINS, "n_fft": N_FFT, "sr": int(sr)} for b in range(B)]
+
+
+def synthesize(env_spec, f0_interp, voicing_mask, y=None, sr: int = 44100, n_fft: int = N_FFT, hop_length: int = HOP, *,
+               normalize: float = 1.0, formant_shift: float = 1.0, F1_shift: float = 1.0, F2_shift: float = 1.0,
+               F3_shift: float = 1.0, F4_shift: float = 1.0, formants=None, f0_jitter: bool = False,
+               f0_jitter_strength: float = 1.5, volume_jitter: bool = False, volume_jitter_strength_harm: float = 50,
+               volume_jitter_strength_breath: float = 100, noise=None, device: str = "cuda:0", **unsupported):
+    """gf.synthesize (GOOFER.py:971-1220) on the GPU: the direct call the editor preview (SillyEditor.py:227, 559) and
+    test.py:38 make, same positional arguments, same return tuple (reconstruct, harmonic, aper_uv, aper_bre), each
+    (len(voicing_mask),) float32.  `env_spec` is a (513, T) array or a knots dict; `y` is only looked at for its length
+    in the reference and is ignored here (len(voicing_mask) plays that role).  One note rendered through
+    goofer_render_batch with GooferNote.f0_off (include/goofer_b200.h); keyword arguments are carried by the flag
+    columns they correspond to (Appendix A of SURVEY.md), so only values a flag can express are accepted:
+    normalize (P, %), formant_shift (g, 1 + g/200), F1..F4_shift (fa..fd, 1 + x/100), f0_jitter (sh, strength sh/50),
+    volume_jitter (sr, harmonic strength sr/50 with breath = 2x, the pairing SillySampler.py:1022-1024 uses).
+    `noise`: a host.SeededNoise-like provider (default: fresh noise like the reference)."""
+    import numpy as np
+    from . import host
+    if unsupported:
+        raise NotImplementedError("ops.synthesize: keyword arguments no resampler flag reaches are not implemented: "
+                                  + ", ".join(sorted(unsupported)))
+    if int(n_fft) != N_FFT or int(hop_length) != HOP:
+        raise NotImplementedError("ops.synthesize: n_fft = 1024, hop_length = 256 only")
+    mask = np.ascontiguousarray(voicing_mask, dtype=np.float32).reshape(-1)
+    f0 = np.ascontiguousarray(f0_interp, dtype=np.float32).reshape(-1)
+    if f0.size != mask.size:
+        raise ValueError("len(f0_interp) must equal len(voicing_mask)")
+
+    def flag_value(name, value, scale, offset=0.0):
+        v = (float(value) - offset) * scale
+        if abs(v - round(v)) > 1e-9:
+            raise NotImplementedError(f"ops.synthesize: {name}={value} is not expressible by its integer flag")
+        return int(round(v))
+
+    flags = ""
+    g = flag_value("formant_shift", formant_shift, 200.0, 1.0)
+    if g:
+        flags += f"g{g}"
+    for nm, val in (("fa", F1_shift), ("fb", F2_shift), ("fc", F3_shift), ("fd", F4_shift)):
+        v = flag_value(nm, val, 100.0, 1.0)
+        if v:
+            flags += f"{nm}{v}"
+    if f0_jitter:
+        flags += f"sh{flag_value('f0_jitter_strength', f0_jitter_strength, 50.0)}"
+    if volume_jitter:
+        if abs(float(volume_jitter_strength_breath) - 2.0 * float(volume_jitter_strength_harm)) > 1e-12:
+            raise NotImplementedError("ops.synthesize: volume_jitter_strength_breath must be twice ..._harm (the sr flag's pairing)")
+        flags += f"sr{flag_value('volume_jitter_strength_harm', volume_jitter_strength_harm, 50.0)}"
+    flags += f"P{flag_value('normalize', min(max(float(normalize), 0.0), 1.0), 100.0)}"
+    forms = {}
+    if isinstance(formants, dict):
+        for k, v in formants.items():
+            if isinstance(k, str) and k.upper().startswith("F"):
+                try:
+                    k = int(k[1:])
+                except Exception:
+                    continue
+            if isinstance(k, int) and 1 <= k <= 4:
+                forms[k] = np.asarray(v, dtype=np.float64).reshape(-1)
+    if isinstance(env_spec, dict):
+        T = int(np.asarray(env_spec["knot_vals_log"]).shape[1])
+    else:
+        env_spec = np.ascontiguousarray(env_spec, dtype=np.float32)
+        T = int(env_spec.shape[1])
+    for i in (1, 2, 3, 4):                                   # pad_trim_to_len (GOOFER.py:64-70, 999-1002)
+        x = forms.get(i, np.zeros(1))
+        x = np.zeros(T) if x.size == 0 else (np.pad(x, (0, T - x.size), mode="edge") if x.size < T else x[:T])
+        forms[i] = np.ascontiguousarray(x, dtype=np.float64)
+    if isinstance(env_spec, dict):
+        src = host.SourceFeatures.from_knot_pack(env_spec, mask, forms, int(sr), int(mask.size))
+    else:
+        src = host.SourceFeatures.from_dense(env_spec, mask, forms, int(sr), int(mask.size))
+    b = host.Batch()
+    b.add_source(src)
+    b.add_note(host.NoteArgs(source=0, pitch="C4", flags=flags, f0_curve=f0))
+    ab = b.assemble(noise or host.FreshNoise(), taps=True)
+    db = ab.to_device(device)
+    db.render()
+    out = db.outputs()[0]
+    harm, uv, bre = (t[:ab.out_total].cpu().numpy() for t in db.tap)
+    return out, harm, uv, bre

@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define GOOFER_ABI_VERSION 2
+#define GOOFER_ABI_VERSION 3
 #define GOOFER_N_FFT 1024      /* SillySampler.py:14 */
 #define GOOFER_HOP 256         /* SillySampler.py:15 */
 #define GOOFER_N_BINS 513
@@ -100,6 +100,13 @@ typedef struct GooferNote {
     int64_t phi_off[4];
     int64_t nrm_off[4];
     int64_t out_off;                /* first element of this note's output in GooferBatch.out */
+    /* Direct gf.synthesize call (GOOFER.py:971-1220 as SillyEditor.py:227, 559 and test.py:38 use it) instead of a
+     * resampler note: f0_off >= 0 is the first element of this note's per-sample f0 curve (f32, `f0_interp`) in
+     * GooferBatch.f0_curves.  The source is then used WHOLE -- env_spec = all T frames, voicing_mask = all N samples,
+     * len(y) = N -- and offset / length / consonant / cutoff / velocity / pitch / pitch bend are ignored; flags keep
+     * their meaning as synthesize keyword arguments (g formant_shift, fa-fd F1-F4_shift, sh, sr, sg, P normalize ...).
+     * -1 = a resampler note. */
+    int64_t f0_off;
 } GooferNote;
 
 /* What the planner derives for one note (lengths the host needs to size noise and output buffers). */
@@ -136,6 +143,8 @@ typedef struct GooferBatch {
      * saturate(lrint(x * 2^31)) >> 16.  When out_pcm16 is given, `out` may be NULL (the host entry point then
      * downloads half the bytes). */
     int16_t *out_pcm16;
+    const float *f0_curves;         /* concatenated per-sample f0 curves of the notes with f0_off >= 0 (may be NULL) */
+    int64_t f0_total;
 } GooferBatch;
 
 int goofer_version(void);

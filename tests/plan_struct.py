@@ -27,5 +27,5 @@ class GfNotePlan(C.Structure):
         ("vf", f64), ("vh", f64), ("vl", f64),
         ("fry_on", i32), ("fry_L", i32), ("fry_glide", i32), ("fry_const", i32),
         ("fry_mask_on", i32), ("fry_a", i32), ("fry_b", i32), ("fry_fade", i32),
-        ("phi_off", i64 * 4), ("nrm_off", i64 * 4), ("out_off", i64),
+        ("phi_off", i64 * 4), ("nrm_off", i64 * 4), ("out_off", i64), ("f0_off", i64),
     ]

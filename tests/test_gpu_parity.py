@@ -437,3 +437,33 @@ def test_pcm16_encoded_on_device(torch_cuda):
     assert st["d2h_bytes"] == 2 * sum(len(q) for q in pcm)            # int16 only: half of the f32 download
     for q, h in zip(pcm, host_pcm):
         assert np.array_equal(q, h)
+
+
+def test_direct_synthesize_seam(torch_cuda):
+    """ops.synthesize = gf.synthesize called directly (SillyEditor.py:227, 559; test.py:38; SURVEY 8b "Python DSP API"):
+    explicit per-sample f0 curve, whole source, keyword arguments carried by the flag columns -- against the committed
+    outputs of the reference itself (tests/golden/synth_direct.npz, made by tests/golden/make_golden_synth.py)."""
+    from tests.golden import make_golden_synth as mg
+    from tests.test_oracle_golden import synth_direct_noise
+    feat, pack, forms, _, _ = mg.inputs()
+    g = np.load(os.path.join(GOLD, "synth_direct.npz"))
+    n, sr = len(feat.mask), feat.sr
+    base, legacy = (int(x) for x in g["seeds"])
+
+    def provider(f0_jitter, volume_jitter):
+        return lambda i, info: synth_direct_noise(info["n_total"], info["t_out"], base, legacy, f0_jitter, volume_jitter)
+
+    knots = {"mode": "knots", "knot_vals_log": pack["knot_vals_log"], "hz_knots": pack["hz_knots"], "n_fft": 1024, "sr": sr,
+             "n_bins": 513}
+    ra = ops.synthesize(knots, g["f0_a"], feat.mask, np.empty(n, dtype=np.bool_), sr, formants=forms, noise=provider(False, False))
+    rb = ops.synthesize(feat.env, g["f0_b"], feat.mask, None, sr, formants=forms, noise=provider(True, True), **mg.KW_B)
+    for tag, r in (("a", ra), ("b", rb)):
+        for name, arr in zip(("reconstruct", "harmonic", "aper_uv", "aper_bre"), r):
+            ref = g[f"{tag}_{name}"]
+            assert arr.shape == ref.shape and arr.dtype == np.float32
+            assert np.max(np.abs(arr.astype(np.float64) - ref)) <= MAX_ABS, (tag, name)
+        assert cases.lsd_db(g[f"{tag}_reconstruct"].astype(np.float64), r[0].astype(np.float64)) <= MAX_LSD
+    with pytest.raises(NotImplementedError):
+        ops.synthesize(feat.env, g["f0_b"], feat.mask, None, sr, roughness_on=True)
+    with pytest.raises(NotImplementedError):
+        ops.synthesize(feat.env, g["f0_b"], feat.mask, None, sr, formant_shift=1.0123)

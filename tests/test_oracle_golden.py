@@ -89,3 +89,41 @@ def test_analysis_front_end(gold_stages):
         d = np.abs(pack["knot_vals_log"].astype(np.float32) - g[f"{tag}_knots"].astype(np.float32))
         assert np.max(d) <= 2e-3 * np.max(np.abs(g[f"{tag}_knots"].astype(np.float32)))     # one f16 ulp
     assert int(g["an_silence_K"][0]) == 32
+
+
+def _synth_direct_inputs():
+    from tests.golden import make_golden_synth as mg
+    feat, pack, forms, _, _ = mg.inputs()
+    g = np.load(os.path.join(GOLD, "synth_direct.npz"))
+    return mg, feat, pack, forms, g
+
+
+def synth_direct_noise(n, T, base, legacy, f0_jitter, volume_jitter):
+    """The buffers gf.synthesize draws under ref_harness.seeded_noise, in its own order (GOOFER.py:666, 653, 1151)."""
+    leg = np.random.RandomState(legacy)
+    nz = {}
+    if f0_jitter:
+        nz["sh"] = leg.randn(n)
+    if volume_jitter:
+        nz["sr_h"] = leg.randn(n)
+        nz["sr_b"] = leg.randn(n)
+    nz["phi"] = np.random.Generator(np.random.PCG64(base)).uniform(0.0, 2.0 * np.pi, size=(513, T)).astype(np.float32)
+    return nz
+
+
+def test_oracle_direct_synthesize_matches_reference():
+    """gf.synthesize called directly (SillyEditor.py:227, test.py:38): oracle.synth against the reference's outputs."""
+    from oracle import synth
+    mg, feat, pack, forms, g = _synth_direct_inputs()
+    n, sr = len(feat.mask), feat.sr
+    T = 1 + n // 256
+    base, legacy = (int(x) for x in g["seeds"])
+    knots = {"knot_vals_log": pack["knot_vals_log"], "hz_knots": pack["hz_knots"], "n_fft": 1024, "sr": sr, "n_bins": 513}
+    ra = synth.synthesize(knots, g["f0_a"], feat.mask, n, sr, synth_direct_noise(n, T, base, legacy, False, False), formants=forms)
+    kw = dict(mg.KW_B)
+    shifts = tuple(kw.pop(f"F{i}_shift") for i in (1, 2, 3, 4))
+    rb = synth.synthesize(feat.env, g["f0_b"], feat.mask, n, sr, synth_direct_noise(n, T, base, legacy, True, True),
+                          formants=forms, F_shifts=shifts, **kw)
+    for tag, r in (("a", ra), ("b", rb)):
+        for name, arr in zip(("reconstruct", "harmonic", "aper_uv", "aper_bre"), r):
+            assert np.array_equal(np.asarray(arr, dtype=np.float32), g[f"{tag}_{name}"]), (tag, name)
