@@ -291,7 +291,10 @@ def run_native(args):
         roof = None
         if top[0]:
             per_launch_ms = top[1][1] / max(1, top[1][0])
-            ach = algo_bytes / (per_launch_ms * 1e-3) / 1e9
+            # a step may launch the kernel several times (waves of 2,048 notes, host parts): bytes per LAUNCH
+            launches_per_step = max(1.0, top[1][0] / max(1, args.steps))
+            algo_per_launch = algo_bytes / launches_per_step
+            ach = algo_per_launch / (per_launch_ms * 1e-3) / 1e9
             traffic = None                                    # ncu DRAM bytes per launch of this kernel, when a capture of this workload is committed
             try:
                 with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as fh:
@@ -300,7 +303,8 @@ def run_native(args):
                 pass
             roof = {"bound": "hbm", "kernel": top[0], "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
                     "traffic": traffic, "peak_source": peak_src, "kernel_ms_per_launch": per_launch_ms,
-                    "algorithmic_bytes_per_launch": algo_bytes, "kernel_share_of_step": top[1][1] / tot_kernel_ms,
+                    "algorithmic_bytes_per_launch": int(algo_per_launch), "launches_per_step": launches_per_step,
+                    "kernel_share_of_step": top[1][1] / tot_kernel_ms,
                     "step_algorithmic_gbs": algo_bytes * args.steps / (dev_ms * 1e-3) / 1e9,
                     "kernels_ms_per_step": {k: round(v[1] / args.steps, 4) for k, v in prof.items()}}
         line = {

@@ -271,6 +271,24 @@ gf_frame_kernel(const int4 *__restrict__ work, const GfPassDev *__restrict__ pas
             sm.uvskip[tid] = ps.mask_ones ? 1 : one;          // sa pass: uv is multiplied by 0 (SillySampler.py:1156-1170)
         }
         __syncthreads();
+        // ---- next round's global operands -> L2 (every one of them is read exactly once, so the shaping loads would
+        // otherwise wait on HBM): envelope rows of frames t0+4 .. t0+7 (65 lines each), the 513 phase rows (one 16-byte
+        // piece per row and round: the 128-byte line around it), the new excitation samples.  No registers held.
+#ifndef GF_NO_PREFETCH
+        if (t0 + GF_RND <= t_end) {
+            const int tn = t0 + GF_RND;
+            auto pf = [](const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); };
+            if (tid < 66) pf(reinterpret_cast<const char *>(nd.envF + (size_t)tn * GF_ENVS_LD) + 128 * tid);
+            else if (tid < 132) pf(reinterpret_cast<const char *>(nd.envN + (size_t)tn * GF_ENVS_LD) + 128 * (tid - 66));
+            else if (tid < 148) {
+                const int i = min(n - 1, GF_HOP * tn + GF_NFFT / 2 - GF_HOP + 32 * (tid - 132));
+                if (i >= 0) pf(pulse + i);
+            }
+            pf(ps.phi + (size_t)tid * T + tn);
+            pf(ps.phi + (size_t)(tid + 256) * T + tn);
+            if (tid == 0) pf(ps.phi + (size_t)512 * T + tn);
+        }
+#endif
         // ---- 2. forward FFT ----
         gf_cta_fft512<false>(&sm.z[2][0][0], nf, sm.tw512);
         bool uv_on = false;                                   // uniform: the round computes the unvoiced stream unless every frame may skip it
