@@ -70,6 +70,7 @@ extern "C" void goofer_host_release(void)
     if (g_hc.st_in) cudaStreamDestroy(g_hc.st_in);
     if (g_hc.st_out) cudaStreamDestroy(g_hc.st_out);
     g_hc = GfHostCache();
+    if (g_side.sx) { cudaStreamDestroy(g_side.sx); cudaEventDestroy(g_side.fork); cudaEventDestroy(g_side.join); g_side = GfSide(); }
 }
 
 // Only the frame kernel reads the noise phases (2/3 of the input bytes).  The batch is rendered ONCE: the
