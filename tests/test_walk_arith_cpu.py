@@ -47,12 +47,35 @@ def delta(x, e):
     return -q - 1 + c + tie * ((q + 1) & 1), -q - 1 + c + tie * (q & 1), guard, False
 
 
+def delta_fp64(x, e):
+    """gf_walk_delta as the kernel computes it: the delta pair read off TWO REAL fp64 additions on representative
+    totals of the binade -- 1.5 * 2^e (even mantissa) and its successor (odd mantissa).  The delta only depends on the
+    parity of M while M + delta stays in the binade, which holds for the representatives when |x| < 2^(e-1); larger
+    increments (the first samples of a note) are events.  Python floats are IEEE doubles with round-to-nearest-even."""
+    if x == 0:
+        return 0, 0, 0, False
+    mk, ek = _split(x)
+    if mk is None or ek >= e - 1:
+        return 0, 0, 0, True
+    base0 = 1.5 * 2.0 ** e
+    base1 = struct.unpack("<d", struct.pack("<Q", struct.unpack("<Q", struct.pack("<d", base0))[0] + 1))[0]
+    scale = 2.0 ** (52 - e)
+    d0 = int(((base0 + x) - base0) * scale)
+    d1 = int(((base1 + x) - base1) * scale)
+    guard = 0
+    if x < 0:
+        g = F(-x) * F(2) ** (52 - e)                           # ceil(-x * 2^(52 - e)); the product is exact in fp64
+        guard = -((-g.numerator) // g.denominator)
+    return d0, d1, guard, False
+
+
 def then(a, b):
     return a[0] + b[(0 + a[0]) & 1], a[1] + b[(1 + a[1]) & 1]
 
 
-def walk(inc, block=256):
+def walk(inc, block=256, delta=None):
     """attempt / commit loop of the kernel (scan written as a Hillis-Steele pass over the block)."""
+    delta = delta or globals()["delta"]
     n = len(inc)
     out = np.zeros(n)
     started, raw_mode, raw, M, e = False, False, 0.0, 0, 0
@@ -158,3 +181,38 @@ def test_markstein_division_by_the_sample_rate_is_exact():
             q0 = float(a * F(y))
             r = float(a - F(b) * F(q0))
             assert float(F(q0) + F(r) * F(y)) == float(a / F(b)), (f, b)
+
+
+def test_fp64_delta_pairs_equal_the_integer_rule():
+    """Wherever the kernel's fp64 formulation does not call a step an event, its delta pair and guard equal the
+    integer rounding rule; and it calls a step an event only for increments of at least a quarter of the binade."""
+    rng = np.random.default_rng(7)
+    n_checked = 0
+    for e in (-20, -8, -3, 0, 1, 5, 11, 30):
+        mags = 2.0 ** rng.uniform(e - 70, e + 2, 6000)
+        xs = np.concatenate([mags * rng.choice([-1.0, 1.0], mags.size),
+                             # exact ties and near-ties at every shift: (k + 1/2) ulp, +- one unit in the last place of x
+                             [(k + 0.5) * 2.0 ** (e - 52) * sg for k in (0, 1, 2, 3, 1000, 2 ** 30 + 1) for sg in (1, -1)],
+                             [np.nextafter((k + 0.5) * 2.0 ** (e - 52), dirn) * sg for k in (1, 2, 7) for dirn in (0, np.inf) for sg in (1, -1)],
+                             [2.0 ** (e - 52) * sg * k for k in (1, 2, 3) for sg in (1, -1)], [0.0]])
+        for x in xs:
+            x = float(x)
+            a, b = delta(x, e), delta_fp64(x, e)
+            if b[3]:
+                assert x != 0 and (not np.isfinite(x) or abs(x) >= 2.0 ** (e - 1) or abs(x) < 2.0 ** -1022)
+                continue
+            assert not a[3]
+            assert a[:2] == b[:2], (x, e, a, b)
+            # the integer rule drops the guard of a negative increment 2^64 times below the total (the step cannot
+            # change it); the fp64 form keeps ceil(|x| / ulp) = 1 there: an extra event exactly on a power of two
+            mk, ek = _split(x) if x else (0, 0)
+            assert a[2] == b[2] or (x < 0 and e - ek >= 64 and (a[2], b[2]) == (0, 1)), (x, e, a, b)
+            n_checked += 1
+    assert n_checked > 40000
+
+
+@pytest.mark.parametrize("name", ["flat 220", "vibrato", "negative jitter", "saw", "power of two", "tiny"])
+def test_walk_with_fp64_deltas_equals_the_scalar_chain(name):
+    inc = _cases()[name]
+    got, attempts, events = walk(inc, delta=delta_fp64)
+    assert np.array_equal(got, scalar(inc))
