@@ -541,7 +541,10 @@ static int gf_render_wave(const GooferBatch *b, const std::vector<GfNotePlan> &a
     wh.passes.resize(n_pass);
     size_t pi = 0;
     // per-note double scalars (maxima, rms sums, percentile): one block, one memset
+    // per-note double scalars and per-pass device-written scalars are carved back to back: ONE memset zeroes both
     double *d_nscal = bp.arr<double>((size_t)nn * GF_NS_COUNT);
+    GfPassScal *d_scal = bp.arr<GfPassScal>(n_pass);
+    const size_t scal_span = (size_t)((char *)(d_scal + n_pass) - (char *)d_nscal);
     for (int i = 0; i < nn; ++i) {
         const GfNotePlan &p = wh.plans[i];
         max_n = std::max(max_n, p.n_total);
@@ -613,10 +616,8 @@ static int gf_render_wave(const GooferBatch *b, const std::vector<GfNotePlan> &a
         up.add(bp, wh.fir, &d_fir);
         if ((rc = up.flush(bp, st)) != GOOFER_OK) return rc;
     }
-    GfPassScal *d_scal = bp.arr<GfPassScal>(n_pass);
     if (bp.off > bp.cap) { gf_set_error("internal: wave overflows the workspace (%zu > %zu)", bp.off, bp.cap); return GOOFER_ERR_WORKSPACE; }
-    GF_CUDA(cudaMemsetAsync(d_scal, 0, n_pass * sizeof(GfPassScal), st));
-    GF_CUDA(cudaMemsetAsync(d_nscal, 0, (size_t)nn * GF_NS_COUNT * sizeof(double), st));
+    GF_CUDA(cudaMemsetAsync(d_nscal, 0, scal_span, st));
 
     int64_t &L = g_stats.kernel_launches;
     // ---- excitation chain on the side stream (sx == st when overlap is off) ----

@@ -96,9 +96,23 @@ gf_tracks_kernel(const GfNotePlan *__restrict__ plans, const GfNoteDev *__restri
     const int T = pl.T_env;
     __shared__ int any_bad, any_good;
     __shared__ double taps[33];
+    __shared__ double ev4[33], eves[GF_MAX_ES_TAPS];          // un-normalised taps: one exp per thread, summed in index order by all
+    double es_sigma = 0.0;
+    int es_radius = 0;
+    if (pl.es != 0.0) {
+        const double s = fabs(pl.es);
+        es_sigma = pl.es < 0.0 ? (1.0 + 6.0 * s) : (0.8 + 4.0 * s);
+        es_radius = (int)(4.0 * es_sigma + 0.5);
+    }
+    if (threadIdx.x < 33) { const double t = (double)((int)threadIdx.x - 16) / 4.0; ev4[threadIdx.x] = exp(-0.5 * t * t); }
+    else if (threadIdx.x >= 64 && threadIdx.x - 64 <= 2 * es_radius && pl.es != 0.0) {
+        const double q = (double)((int)threadIdx.x - 64 - es_radius) / es_sigma;
+        eves[threadIdx.x - 64] = exp(-0.5 * q * q);
+    }
+    __syncthreads();
     if (threadIdx.x < 33) {
         double norm = 0.0;
-        for (int j = 0; j < 33; ++j) { const double t = (double)(j - 16) / 4.0; norm += exp(-0.5 * t * t); }
+        for (int j = 0; j < 33; ++j) norm += ev4[j];
         taps[threadIdx.x] = gf_gauss_tap(threadIdx.x, 16, 4.0, norm);
     }
     // ---- per-note tables of the envelope kernel: br tilt, es taps, f32 bin frequencies ----
@@ -131,13 +145,12 @@ gf_tracks_kernel(const GfNotePlan *__restrict__ plans, const GfNoteDev *__restri
             for (int b = threadIdx.x; b < GF_NBINS; b += blockDim.x, ++cnt) aux[GF_AUX_TILT + b] = tv[cnt] / (mean + 1e-12f);
         }
         if (pl.es != 0.0 && threadIdx.x < GF_MAX_ES_TAPS) {
-            const double s = fabs(pl.es);
-            const double sigma = pl.es < 0.0 ? (1.0 + 6.0 * s) : (0.8 + 4.0 * s);
-            const int radius = (int)(4.0 * sigma + 0.5);
+            const double sigma = es_sigma;
+            const int radius = es_radius;
             float t = 0.0f;
             if (threadIdx.x < 2 * radius + 1) {
                 double norm = 0.0;
-                for (int j = 0; j <= 2 * radius; ++j) { const double q = (double)(j - radius) / sigma; norm += exp(-0.5 * q * q); }
+                for (int j = 0; j <= 2 * radius; ++j) norm += eves[j];
                 t = (float)gf_gauss_tap(threadIdx.x, radius, sigma, norm);
             }
             aux[GF_AUX_TAPS + threadIdx.x] = t;
@@ -201,7 +214,13 @@ gf_tracks_kernel(const GfNotePlan *__restrict__ plans, const GfNoteDev *__restri
         __syncthreads();
         for (int t = threadIdx.x; t < T; t += blockDim.x) {
             double a = 0.0;
-            for (int j = 0; j < 33; ++j) a += taps[j] * (double)tmp[gf_reflect(t + j - 16, T)];
+            if (t >= 16 && t + 16 < T) {                      // interior: no reflection
+                const float *q = tmp + (t - 16);
+#pragma unroll
+                for (int j = 0; j < 33; ++j) a += taps[j] * (double)q[j];
+            } else {
+                for (int j = 0; j < 33; ++j) a += taps[j] * (double)tmp[gf_reflect(t + j - 16, T)];
+            }
             clean[t] = (float)a;
         }
         __syncthreads();
