@@ -10,7 +10,9 @@
 #define GF_NFFT 1024
 #define GF_HOP 256
 #define GF_NBINS 513
+#ifndef GF_FT
 #define GF_FT 8                 // frames per envelope tile ([tile][bin][GF_FT] layout in the workspace)
+#endif
 #define GF_MAX_PASSES 4         // main, su, sj, sa   (SillySampler.py:1006,1041,1067,1156)
 
 enum { GF_LOOP_CONCAT = 0, GF_LOOP_AVG = 1, GF_LOOP_STRETCH = 2 };

@@ -310,7 +310,11 @@ __device__ __forceinline__ float gf_grid_interp(const float *row, double x, doub
 #ifndef GF_ENV_CTAS
 #define GF_ENV_CTAS 3               // 80 registers (64 B of spills), 44 KB of shared memory per CTA: 1.94 -> 1.69 ms against two CTAs at 127
 #endif
+#ifdef GF_ENV_MAXNREG
+__global__ void __maxnreg__(GF_ENV_MAXNREG)
+#else
 __global__ void __launch_bounds__(32 * GF_ENV_WARPS, GF_ENV_CTAS)
+#endif
 gf_env_kernel(const int2 *__restrict__ work, const GfNotePlan *__restrict__ plans, const GfNoteDev *__restrict__ notes,
               const GfSourceDev *__restrict__ srcs)
 {

@@ -467,3 +467,57 @@ def test_direct_synthesize_seam(torch_cuda):
         ops.synthesize(feat.env, g["f0_b"], feat.mask, None, sr, roughness_on=True)
     with pytest.raises(NotImplementedError):
         ops.synthesize(feat.env, g["f0_b"], feat.mask, None, sr, formant_shift=1.0123)
+
+
+def test_http_server_batches_on_the_gpu(tmp_path, torch_cuda):
+    """The reference's server mode (SillySampler.py:1187-1224) with the real renderer: concurrent POSTs come back
+    200, are rendered as ONE GPU batch, and every out.wav holds a peak-normalised 16-bit note."""
+    import threading
+    import urllib.request
+    import wave
+    from goofer_b200 import server
+    src = bench_data.make_source(2)
+    stem = os.path.join(tmp_path, "voice_b")
+    with open(stem + "_features.goofy", "wb") as fh:
+        np.savez_compressed(fh, mode=np.array(["knots"]), knot_vals_log=src["knot_vals_log"], hz_knots=src["hz_knots"],
+                            n_bins=np.array([513]), n_fft=np.array([1024]), f0_interp=np.zeros(8, np.float16),
+                            voicing_mask=src["mask"].astype(np.float16), formants=np.array(src["formants"], dtype=object),
+                            sr=np.array([44100]), y_len=np.array([src["ylen"]]))
+    batcher = server.Batcher(window_ms=300.0)
+    batcher.start()
+    httpd = server.ThreadedHTTPServer(("127.0.0.1", 0), server.make_handler(batcher))
+    port = httpd.server_address[1]
+    th = threading.Thread(target=httpd.serve_forever, daemon=True)
+    th.start()
+    try:
+        pitches = ["C4", "E4", "G4", "A3", "D4", "F4"]
+        outs = [os.path.join(tmp_path, f"out_{i}.wav") for i in range(len(pitches))]
+        codes = [None] * len(pitches)
+
+        def post(i):
+            body = " ".join([stem + ".wav", outs[i], pitches[i], "100", "g-5br10", "0", "600", "0", "0", "100", "0", "!120", "AA"])
+            req = urllib.request.Request(f"http://127.0.0.1:{port}/", data=body.encode("utf-8"), method="POST")
+            with urllib.request.urlopen(req, timeout=120) as r:
+                codes[i] = r.status
+
+        threads = [threading.Thread(target=post, args=(i,)) for i in range(len(pitches))]
+        for t in threads:
+            t.start()
+        for t in threads:
+            t.join()
+        assert codes == [200] * len(pitches)
+        assert sum(batcher.batches) == len(pitches) and len(batcher.batches) <= 2       # coalesced, not one render per request
+        for o in outs:
+            with wave.open(o, "rb") as w:
+                assert w.getframerate() == 44100 and w.getsampwidth() == 2 and w.getnframes() == 26460
+                pcm = np.frombuffer(w.readframes(w.getnframes()), dtype="<i2")
+            assert np.max(np.abs(pcm.astype(np.int32))) >= 32000
+        bad = urllib.request.Request(f"http://127.0.0.1:{port}/", data=b"no paths here C4 100 g0 0 600 0 0 100 0 !120 AA", method="POST")
+        try:
+            urllib.request.urlopen(bad, timeout=60)
+            assert False, "expected HTTP 500"
+        except urllib.error.HTTPError as e:
+            assert e.code == 500
+    finally:
+        httpd.shutdown()
+        batcher.stop()
