@@ -11,6 +11,8 @@ goofer_render_batch; this module only packs arrays and descriptors.
 """
 from __future__ import annotations
 
+import os
+
 import ctypes as C
 import re
 from dataclasses import dataclass, field
@@ -85,6 +87,7 @@ class SourceFeatures:
     knots_log: Optional[np.ndarray] = None    # (K, T) float16
     hz_knots: Optional[np.ndarray] = None     # (K,) float32
     env_dense: Optional[np.ndarray] = None    # (513, T) float32
+    cache_key: Optional[tuple] = None         # identity of the feature file (path, mtime, size): DeviceSourceCache
 
     @property
     def n_frames(self) -> int:
@@ -121,6 +124,39 @@ def _int_key_formants(formants) -> Dict[int, np.ndarray]:
 
 def load_goofy(path) -> SourceFeatures:
     """Read a `<stem>_features.goofy` written by the reference (npz; formants are a pickled dict)."""
+    feat = _load_goofy(path)
+    try:
+        st = os.stat(path)
+        feat.cache_key = (os.path.abspath(str(path)), st.st_mtime_ns, st.st_size)
+    except OSError:
+        pass
+    return feat
+
+
+class DeviceSourceCache:
+    """Voicebank features kept resident in HBM across render calls (the on-disk format either side of
+    the path): the fp16 knots, mel-knot frequencies, voicing mask and formant tracks of a `.goofy` file are uploaded
+    once per (path, mtime, size) and device, and later batches point their GooferSource records at the same tensors.
+    A server renders thousands of notes from a few hundred sources; the reference re-reads and re-decodes the file for
+    every note (GOOFER.py:319-339)."""
+
+    def __init__(self, max_sources: int = 4096):
+        self.max_sources, self.entries, self.hits, self.misses = int(max_sources), {}, 0, 0
+
+    def get(self, key, device, make):
+        k = (key, str(device))
+        e = self.entries.get(k)
+        if e is None:
+            self.misses += 1
+            if len(self.entries) >= self.max_sources:
+                self.entries.pop(next(iter(self.entries)))          # oldest first
+            e = self.entries[k] = make()
+        else:
+            self.hits += 1
+        return e
+
+
+def _load_goofy(path) -> SourceFeatures:
     with np.load(path, allow_pickle=True) as z:
         mode = str(z["mode"][0])
         mask = z["voicing_mask"].astype(np.float32)
@@ -456,15 +492,15 @@ class AssembledBatch:
         return res
 
     # ---- device-resident entry point (torch owns the memory and the stream) ------------------------
-    def to_device(self, device="cuda:0"):
-        return DeviceBatch(self, device)
+    def to_device(self, device="cuda:0", source_cache: "Optional[DeviceSourceCache]" = None):
+        return DeviceBatch(self, device, source_cache)
 
 
 class DeviceBatch:
     """All arrays of an AssembledBatch resident in HBM as torch tensors; render() launches on torch's
     current stream and returns the flat f32 output tensor."""
 
-    def __init__(self, ab: AssembledBatch, device):
+    def __init__(self, ab: AssembledBatch, device, source_cache: "Optional[DeviceSourceCache]" = None):
         import torch
         self.torch = torch
         self.ab = ab
@@ -479,21 +515,37 @@ class DeviceBatch:
 
         src = ab.batch.sources
         self.src_arr = (capi.GooferSource * max(1, len(src)))()
+        def upload_source(s):
+            t = {}
+            if s.knots_log is not None:
+                t["knots"], t["hz"] = up(s.knots_log.view(np.int16)), up(s.hz_knots)
+            if s.env_dense is not None:
+                t["dense"] = up(s.env_dense)
+            t["mask"] = up(s.mask)
+            for k in range(4):
+                tr = s.formants.get(k + 1)
+                if tr is not None and tr.size:
+                    t[f"F{k}"] = up(tr)
+            return t
+
         for i, s in enumerate(src):
             g = self.src_arr[i]
             h = ab.src_arr[i]
             g.K, g.T, g.N, g.sr, g.ylen = h.K, h.T, h.N, h.sr, h.ylen
-            if s.knots_log is not None:
-                g.knots_log_f16 = up(s.knots_log.view(np.int16)).data_ptr()
-                g.hz_knots = up(s.hz_knots).data_ptr()
-            if s.env_dense is not None:
-                g.env_dense = up(s.env_dense).data_ptr()
-            g.mask = up(s.mask).data_ptr()
+            if source_cache is not None and s.cache_key is not None:
+                t = source_cache.get(s.cache_key, dev, lambda s=s: upload_source(s))
+                self._keep.append(t)
+            else:
+                t = upload_source(s)
+            if "knots" in t:
+                g.knots_log_f16, g.hz_knots = t["knots"].data_ptr(), t["hz"].data_ptr()
+            if "dense" in t:
+                g.env_dense = t["dense"].data_ptr()
+            g.mask = t["mask"].data_ptr()
             for k in range(4):
-                tr = s.formants.get(k + 1)
-                if tr is not None and tr.size:
-                    g.formants[k] = up(tr).data_ptr()
-                    g.formant_len[k] = int(tr.size)
+                if f"F{k}" in t:
+                    g.formants[k] = t[f"F{k}"].data_ptr()
+                    g.formant_len[k] = int(t[f"F{k}"].numel())
         self.bend = up(ab.bend)
         self.phi = up(ab.phi)
         self.normals = up(ab.normals) if ab.normals is not None else None

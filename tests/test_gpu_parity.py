@@ -521,3 +521,24 @@ def test_http_server_batches_on_the_gpu(tmp_path, torch_cuda):
     finally:
         httpd.shutdown()
         batcher.stop()
+
+
+def test_device_source_cache(tmp_path, torch_cuda):
+    """a feature file is uploaded once per process; later batches reuse the resident tensors and
+    render the same samples."""
+    from goofer_b200 import cli
+    src = bench_data.make_source(4)
+    stem = os.path.join(tmp_path, "voice_c")
+    with open(stem + "_features.goofy", "wb") as fh:
+        np.savez_compressed(fh, mode=np.array(["knots"]), knot_vals_log=src["knot_vals_log"], hz_knots=src["hz_knots"],
+                            n_bins=np.array([513]), n_fft=np.array([1024]), f0_interp=np.zeros(8, np.float16),
+                            voicing_mask=src["mask"].astype(np.float16), formants=np.array(src["formants"], dtype=object),
+                            sr=np.array([44100]), y_len=np.array([src["ylen"]]))
+    args = [[stem + ".wav", "x.wav", "D4", "100", "g10fst20", "0", "800", "0", "0", "100", "0", "!120", "AA"],
+            [stem + ".wav", "y.wav", "F4", "100", "", "0", "500", "0", "0", "100", "0", "!120", "AA"]]
+    h0, m0 = cli.SOURCE_CACHE.hits, cli.SOURCE_CACHE.misses
+    a = cli.render_notes(args, noise=host.SeededNoise(5, 6))
+    b = cli.render_notes(args, noise=host.SeededNoise(5, 6))
+    assert cli.SOURCE_CACHE.misses == m0 + 1 and cli.SOURCE_CACHE.hits == h0 + 1     # one file, two batches
+    for x, y in zip(a, b):
+        assert np.array_equal(x, y)
