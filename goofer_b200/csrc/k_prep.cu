@@ -248,6 +248,7 @@ struct GfEnvSmem {
     float tilt[GF_ENVS_LD];
     float freq[GF_ENVS_LD];
     float es_taps[GF_MAX_ES_TAPS];
+    double knots[GF_ENV_WARPS][18];                       // F1..F4 warp of the warp's frame: xd[0..5], xs[6..11], slopes [12..16]
 };
 
 // fill the reflect halo of a row whose bins 0..512 are valid (numpy 'reflect': edge sample not repeated)
@@ -511,41 +512,74 @@ gf_env_kernel(const int2 *__restrict__ work, const GfNotePlan *__restrict__ plan
         __syncwarp();
     }
     // ---- F1..F4 warp (GOOFER.py:840-875) ----
+    // The knots (0,0), (F_k r_k -> F_k) for the valid formants, (nyq, nyq) belong to the frame, i.e. to the whole warp:
+    // they live in a per-warp shared-memory table, lane j computes the slope, the order check and the first bin of
+    // segment j + 1, and every bin finds its segment by counting integer thresholds (no per-bin search, no local arrays).
     if (pl.any_F_shift) {
-        double xs[6], xd[6], sl[5];
-        int nk = 0;
-        xs[nk] = 0.0; xd[nk] = 0.0; ++nk;
+        double *kx = sm.knots[warp];
+        int nk = 1;
+        if (lane == 0) { kx[0] = 0.0; kx[6] = 0.0; }
         for (int k = 0; k < 4; ++k) {
             const double fo = (double)nd.trk_canon[(size_t)k * pl.T_env + te];
             const double fs = fo * pl.F_shift[k];
-            if (fo > 50.0 && fo < nyq && fs > 50.0) { xs[nk] = fo; xd[nk] = fs; ++nk; }
+            if (fo > 50.0 && fo < nyq && fs > 50.0) {         // warp-uniform
+                if (lane == 0) { kx[nk] = fs; kx[6 + nk] = fo; }
+                ++nk;
+            }
         }
-        xs[nk] = nyq; xd[nk] = nyq; ++nk;
-        for (int j = 0; j + 1 < nk; ++j) sl[j] = (xs[j + 1] - xs[j]) / (xd[j + 1] - xd[j]);
-        bool mono = true;
-        for (int j = 0; j + 1 < nk; ++j) mono = mono && (xd[j] <= xd[j + 1]);
-        int i = 0;
-        {
+        if (lane == 0) { kx[nk] = nyq; kx[6 + nk] = nyq; }
+        ++nk;
+        __syncwarp();
+        bool ok = true;
+        int th = 1 << 30;                                     // first bin b with b * step >= xd[lane + 1]
+        if (lane < nk - 1) {
+            const double d0 = kx[lane], d1 = kx[lane + 1];
+            kx[12 + lane] = (kx[6 + lane + 1] - kx[6 + lane]) / (d1 - d0);
+            ok = d0 <= d1;
+            int bt = (int)fmin(fmax(ceil(d1 * inv_step), 0.0), 513.0);
+            while (bt > 0 && (double)(bt - 1) * step >= d1) --bt;
+            while (bt <= 512 && (double)bt * step < d1) ++bt;
+            th = bt;
+        }
+        const bool mono = __all_sync(0xffffffffu, ok);
+        __syncwarp();
+        const int th1 = __shfl_sync(0xffffffffu, th, 0), th2 = __shfl_sync(0xffffffffu, th, 1), th3 = __shfl_sync(0xffffffffu, th, 2),
+                  th4 = __shfl_sync(0xffffffffu, th, 3), th5 = __shfl_sync(0xffffffffu, th, 4);
+        if (mono) {
 #pragma unroll
-        for (int e = 0; e < GF_EPL; ++e) {
-            if (e < nown) {
+            for (int e = 0; e < GF_EPL; ++e) {
+                if (e < nown) {
+                    const int b = b0 + e;
+                    const double x = (double)b * step;       // 512 * step == nyq exactly
+                    // np.interp(x, xd, xs): segment j = number of knots 1 .. nk-1 at or below x
+                    const int j = (b >= th1) + (b >= th2) + (b >= th3) + (b >= th4) + (b >= th5);
+                    double wf;
+                    if (j >= nk - 1) wf = kx[6 + nk - 1];
+                    else {
+                        const double xdj = kx[j], xsj = kx[6 + j];
+                        wf = (xdj == x) ? xsj : kx[12 + j] * (x - xdj) + xsj;
+                    }
+                    oth[b] = gf_grid_interp(cur, wf, step, inv_step, nyq);
+                }
+            }
+        } else {
+            // shifted formants out of order: numpy's search on unsorted knots, reproduced as a linear scan from the left
+            for (int e = 0; e < nown; ++e) {
                 const int b = b0 + e;
                 const double x = (b == 512) ? nyq : (double)b * step;
-                // np.interp(x, xd, xs) -- x is always inside [xd[0], xd[-1]] = [0, nyq]
                 double wf;
-                if (x > xd[nk - 1]) wf = xs[nk - 1];
-                else if (x < xd[0]) wf = xs[0];
+                if (x > kx[nk - 1]) wf = kx[6 + nk - 1];
+                else if (x < kx[0]) wf = kx[6];
                 else {
-                    if (!mono) i = 0;                     // x ascends with e: the bracket only moves right
-                    while (i < nk && x >= xd[i]) ++i;
+                    int i = 0;
+                    while (i < nk && x >= kx[i]) ++i;
                     const int j = i - 1;
-                    if (j >= nk - 1) wf = xs[nk - 1];
-                    else if (xd[j] == x) wf = xs[j];
-                    else wf = sl[j] * (x - xd[j]) + xs[j];
+                    if (j >= nk - 1) wf = kx[6 + nk - 1];
+                    else if (kx[j] == x) wf = kx[6 + j];
+                    else wf = kx[12 + j] * (x - kx[j]) + kx[6 + j];
                 }
                 oth[b] = gf_grid_interp(cur, wf, step, inv_step, nyq);
             }
-        }
         }
         __syncwarp();
         float *sw = cur; cur = oth; oth = sw;
