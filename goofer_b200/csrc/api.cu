@@ -565,7 +565,7 @@ static int gf_render_wave(const GooferBatch *b, const std::vector<GfNotePlan> &a
         }
         // work lists
         const int tiles = (p.T_out + GF_FT - 1) / GF_FT;
-        for (int t = 0; t < tiles; ++t) wh.env_work.push_back(make_int2(i, t));
+        for (int t = 0; t * GF_ENV_TPC < tiles; ++t) wh.env_work.push_back(make_int2(i, t));      // GF_ENV_TPC tiles per CTA
         const int n_blocks = std::max(p.T_out, 2) - 2 + 1;
         const int bpc = gf_blocks_per_cta(n_blocks);
         for (int k = 0; k < p.n_passes; ++k)

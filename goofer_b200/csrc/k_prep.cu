@@ -308,6 +308,9 @@ __device__ __forceinline__ float gf_grid_interp(const float *row, double x, doub
     return gf_grid_lerp(row, x * inv_step);
 }
 
+#ifndef GF_ENV_TPC
+#define GF_ENV_TPC 1                // tiles (of GF_FT frames) per CTA
+#endif
 #ifndef GF_ENV_CTAS
 #define GF_ENV_CTAS 3               // 80 registers (64 B of spills), 44 KB of shared memory per CTA: 1.94 -> 1.69 ms against two CTAs at 127
 #endif
@@ -340,21 +343,23 @@ gf_env_kernel(const int2 *__restrict__ work, const GfNotePlan *__restrict__ plan
         const double sigma = pl.es < 0.0 ? (1.0 + 6.0 * s) : (0.8 + 4.0 * s);
         es_radius = (int)(4.0 * sigma + 0.5);
     }
-    // the first source frame of this warp's output frame is requested before anything else: its latency hides
-    // behind the table loads and the barrier
-    const int t = wk.y * GF_FT + warp;
-    const bool live = t < pl.T_out;
-    const int te = live ? min(t, pl.T_env - 1) : 0;       // GOOFER.py:1115-1119 trim / edge-pad to the STFT grid
+    // A CTA renders GF_ENV_TPC consecutive tiles of its note: the chain of dependent record loads, the table loads and the
+    // barrier of the prologue are paid once.  The first source frame of the warp's first output frame is requested before
+    // anything else: its latency hides behind the table loads and the barrier.
+    const int tile0 = wk.y * GF_ENV_TPC;
     GfMix mix;
     mix.n = 0;
     float pre[GF_EPL];
 #pragma unroll
     for (int e = 0; e < GF_EPL; ++e) pre[e] = 0.0f;
-    if (live) {
-        gf_env_mix(pl, te, mix);
-        const float *src0 = sc.envS + (size_t)gf_src_frame(pl, mix.f[0]) * GF_ENVS_LD;
+    {
+        const int t = tile0 * GF_FT + warp;
+        if (t < pl.T_out) {
+            gf_env_mix(pl, min(t, pl.T_env - 1), mix);
+            const float *src0 = sc.envS + (size_t)gf_src_frame(pl, mix.f[0]) * GF_ENVS_LD;
 #pragma unroll
-        for (int e = 0; e < GF_EPL; ++e) { const int b = lane + 32 * e; if (b < GF_NBINS) pre[e] = src0[b]; }
+            for (int e = 0; e < GF_EPL; ++e) { const int b = lane + 32 * e; if (b < GF_NBINS) pre[e] = src0[b]; }
+        }
     }
     // per-note tables prepared by gf_tracks_kernel
     for (int b = threadIdx.x; b < GF_NBINS; b += blockDim.x) {
@@ -364,7 +369,6 @@ gf_env_kernel(const int2 *__restrict__ work, const GfNotePlan *__restrict__ plan
     if (do_es && threadIdx.x < GF_MAX_ES_TAPS) sm.es_taps[threadIdx.x] = nd.env_aux[GF_AUX_TAPS + threadIdx.x];
     __syncthreads();
 
-    if (!live) return;
     float *rA = sm.rows[warp][0] + GF_ROW_L, *rB = sm.rows[warp][1] + GF_ROW_L;
     // the FIR windows also touch cells outside [-radius, 512 + radius] (zero-padded taps, idle lanes): they
     // must hold finite values, 0 * NaN left over from an earlier kernel would poison the sums
@@ -372,6 +376,18 @@ gf_env_kernel(const int2 *__restrict__ work, const GfNotePlan *__restrict__ plan
     __syncwarp();
     const int b0 = min(GF_EPL * lane, 510);               // lane 31 owns nothing: it shadows lane 30 (reads stay inside the row)
     const int nown = (lane == 31) ? 0 : min(GF_EPL, GF_NBINS - b0);   // bins this lane owns
+
+    for (int it = 0; it < GF_ENV_TPC; ++it) {
+    const int t = (tile0 + it) * GF_FT + warp;
+    if (t >= pl.T_out) break;                             // warp-uniform; no CTA-wide barrier below
+    const int te = min(t, pl.T_env - 1);                  // GOOFER.py:1115-1119 trim / edge-pad to the STFT grid
+    if (it > 0) {
+        gf_env_mix(pl, te, mix);
+        const float *src0 = sc.envS + (size_t)gf_src_frame(pl, mix.f[0]) * GF_ENVS_LD;
+#pragma unroll
+        for (int e = 0; e < GF_EPL; ++e) { const int b = lane + 32 * e; pre[e] = (b < GF_NBINS) ? src0[b] : 0.0f; }
+        __syncwarp();                                     // the previous frame's row reads are done before the rows are rewritten
+    }
 
     float acc[GF_EPL];
 #pragma unroll
@@ -600,6 +616,7 @@ gf_env_kernel(const int2 *__restrict__ work, const GfNotePlan *__restrict__ plan
     }
     float *dstF = nd.envF + (size_t)t * GF_ENVS_LD;
     for (int b = lane; b < GF_NBINS; b += 32) dstF[b] = cur[b];
+    }   // tiles of this CTA
 }
 
 void gf_launch_env(const int2 *work, int n_work, const GfNotePlan *plans, const GfNoteDev *notes, const GfSourceDev *srcs,
