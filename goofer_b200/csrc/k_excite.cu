@@ -580,14 +580,18 @@ gf_onset_kernel(const GfPassDev *__restrict__ passes, GfPassScal *scal, int sr_i
 void gf_launch_walk(const GfPassDev *passes, GfPassScal *scal, int n_pass, int max_n, int sr, cudaStream_t st)
 {
     if (n_pass <= 0) return;
-    // One warp per note costs the fewest issue slots: right when there are enough notes to fill the GPU.  Two or
-    // four warps per note cut the latency of a note: right for few and / or long notes (measured at 1,024 one-second
-    // notes: 0.82 / 0.66 / 0.69 ms with 1 / 2 / 4 warps).
+    // One warp per note costs the fewest issue slots: right when there are enough notes to fill the GPU.  More warps per
+    // note cut the latency of a note's chain: right for few and / or long notes.  Measured on B200 (ms, 1 s notes;
+    // warps per note 1 / 2 / 4 / 8 / 16): 128 notes .65 .38 .24 .18 .19 | 256: .68 .40 .26 .34 .36 | 512: .69 .43 .50 .65
+    // .69 | 1,024: .74 .55 .76 1.13 1.20 | 2,048: .95 1.00 1.29 2.2 2.4; 96 notes of 16 s: 9.9 5.4 2.9 1.8 1.4.
     static int force = -1;
     if (force < 0) { const char *e = getenv("GOOFER_WALK_WARPS"); force = e ? atoi(e) : 0; }
-    int nw = (n_pass <= 512 || (max_n >= 4 * 44100 && n_pass <= 1024)) ? 4 : (n_pass <= 4096 ? 2 : 1);
-    if (force == 1 || force == 2 || force == 4) nw = force;
-    if (nw == 4) gf_walk_kernel<4><<<n_pass, 128, 0, st>>>(passes, scal, n_pass, sr);
+    int nw = n_pass <= 160 ? 8 : (n_pass <= 320 ? 4 : (n_pass <= 1536 ? 2 : 1));
+    if (max_n >= 4 * 44100) nw = min(16, 2 * nw);
+    if (force == 1 || force == 2 || force == 4 || force == 8 || force == 16) nw = force;
+    if (nw == 16) gf_walk_kernel<16><<<n_pass, 512, 0, st>>>(passes, scal, n_pass, sr);
+    else if (nw == 8) gf_walk_kernel<8><<<n_pass, 256, 0, st>>>(passes, scal, n_pass, sr);
+    else if (nw == 4) gf_walk_kernel<4><<<n_pass, 128, 0, st>>>(passes, scal, n_pass, sr);
     else if (nw == 2) gf_walk_kernel<2><<<n_pass, 64, 0, st>>>(passes, scal, n_pass, sr);
     else gf_walk_kernel<1><<<n_pass, 32, 0, st>>>(passes, scal, n_pass, sr);
     gf_onset_kernel<<<dim3(4, n_pass), 128, 0, st>>>(passes, scal, sr);
