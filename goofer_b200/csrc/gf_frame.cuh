@@ -120,6 +120,28 @@ __device__ __forceinline__ void gf_load_frames4(float2 *bufs, int t0, int n, con
     }
 }
 
+// the same for a plain f32 signal in global memory (8-byte aligned base): sample pairs and window pairs as one 8-byte
+// load each away from the reflected ends -- half the load instructions of the generic version
+__device__ __forceinline__ void gf_load_frames4_f32(float2 *bufs, int t0, int n, const float *__restrict__ win, const float *__restrict__ x)
+{
+    float2 v[8];
+#pragma unroll
+    for (int it = 0; it < 8; ++it) {
+        const int idx = threadIdx.x + 256 * it;
+        const int f = idx >> 9, m = idx & 511;
+        const int p = GF_HOP * (t0 + f) + 2 * m - GF_NFFT / 2;      // even
+        if ((p >= 0) && (p + 1 < n)) v[it] = *reinterpret_cast<const float2 *>(x + p);
+        else v[it] = make_float2(x[gf_reflect(p, n)], x[gf_reflect(p + 1, n)]);
+    }
+#pragma unroll
+    for (int it = 0; it < 8; ++it) {
+        const int idx = threadIdx.x + 256 * it;
+        const int f = idx >> 9, m = idx & 511;
+        const float2 w = *reinterpret_cast<const float2 *>(win + 2 * m);
+        bufs[(size_t)f * GF_FFT_BUF + gf_fpad(m)] = make_float2(v[it].x * w.x, v[it].y * w.y);
+    }
+}
+
 // ---- overlap-add ring -----------------------------------------------------------------------
 // Padded-signal hop block b holds samples [256 b, 256 b + 256); frame t adds into blocks t..t+3.
 // The ring keeps 8 block slots (slot = b & 7) per stream.

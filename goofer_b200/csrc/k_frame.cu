@@ -255,7 +255,7 @@ gf_frame_kernel(const int4 *__restrict__ work, const GfPassDev *__restrict__ pas
                 return (float)((double)pulse[i] + ((double)sub[i] * (double)vm[i]) * sub_scale);
             });
         } else if (nf == GF_RND) {
-            gf_load_frames4(&sm.z[2][0][0], t0, n, win, [&](int i) { return pulse[i]; });
+            gf_load_frames4_f32(&sm.z[2][0][0], t0, n, win, pulse);
         } else {
             gf_load_frames(&sm.z[2][0][0], t0, nf, n, win, [&](int i) { return pulse[i]; });
         }
