@@ -1,4 +1,7 @@
-# bench every variant library in goofer_b200/_lib/variants/ (kernel-only, no e2e, no CPU leg) and print one line each
+#!/usr/bin/env bash
+# Bench every variant library in goofer_b200/_lib/variants/ (tools/build_variants.py) on this box: kernel-only, no e2e,
+# no CPU leg; one line per variant with the per-kernel CUDA-event times.  Run from the repo root on a B200.
+mkdir -p gpurun_out
 for f in goofer_b200/_lib/variants/*.so; do
   n=$(basename $f .so)
   GOOFER_B200_LIB=$PWD/$f python bench.py --steps 8 --warmup 3 --cpu-sample 0 --no-e2e > gpurun_out/var_$n.log 2> gpurun_out/var_$n.err
@@ -13,7 +16,3 @@ except Exception as e:
     print(n, "FAILED", e)
 PY
 done
-# parity of the pulse stage for the fast-intrinsics variant, when present
-if [ -f goofer_b200/_lib/variants/pulsefast.so ]; then
-  GOOFER_B200_LIB=$PWD/goofer_b200/_lib/variants/pulsefast.so python -m pytest tests -m gpu -x -q 2>&1 | tail -3
-fi
