@@ -339,8 +339,43 @@ static void gf_note_work_counts(const GfNotePlan &p, size_t *n_env, size_t *n_fr
     *n_env = (size_t)(p.T_out + GF_FT - 1) / GF_FT;
     const int n_blocks = std::max(p.T_out, 2) - 2 + 1;
     const int bpc = gf_blocks_per_cta(n_blocks);
-    *n_frame = (size_t)p.n_passes * ((n_blocks + bpc - 1) / bpc);
+    *n_frame = (size_t)p.n_passes * (2 * ((n_blocks + bpc - 1) / bpc) + 2);      // upper bound: gf_balance_frame_group may split finer
     *n_fir = 8;
+}
+
+// CTA slots of the frame kernel on this device (resident CTAs per SM x SMs)
+static int gf_frame_slots()
+{
+    static int slots = 0;
+    if (slots == 0) {
+        int dev = 0, sms = 0;
+        if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && sms > 0)
+            slots = sms * GF_FRAME_CTAS;
+        else slots = 148 * GF_FRAME_CTAS;
+    }
+    return slots;
+}
+
+// Tail of a frame-kernel launch.  The notes [a, e) of one launch are cut into `fparts[i]` CTAs per pass; the CTAs run
+// in waves of `slots`.  When the last wave is far from full, the notes whose CTAs make it up are cut finer, so that
+// their (shorter) CTAs fill the slots of that wave once: 1,024 one-second notes = 2,048 CTAs of 86 hop blocks on 444
+// slots = 4.6 waves; with the last 136 notes in three CTAs each the tail wave takes 61 / 89 of a full one.
+static void gf_balance_frame_group(const std::vector<GfNotePlan> &plans, int a, int e, int slots, std::vector<int> &fparts)
+{
+    long items = 0;
+    for (int i = a; i < e; ++i) items += (long)fparts[i] * plans[i].n_passes;
+    const long rem = items % slots;
+    if (rem == 0 || rem * 10 >= (long)slots * 9) return;
+    long acc = 0;
+    int t0 = e;
+    while (t0 > a && acc < rem) { --t0; acc += (long)fparts[t0] * plans[t0].n_passes; }
+    if (acc <= 0 || acc > slots) return;
+    for (int i = t0; i < e; ++i) {
+        const int n_blocks = std::max(plans[i].T_out, 2) - 2 + 1;
+        int want = (int)((long)fparts[i] * slots / acc);
+        want = std::min(want, std::min(2 * fparts[i] + 2, std::max(1, n_blocks / 16)));     // keep the 3-frame halo small
+        if (want > fparts[i]) fparts[i] = want;
+    }
 }
 
 static int gf_validate(const GooferBatch *b)
@@ -539,6 +574,23 @@ static int gf_render_wave(const GooferBatch *b, const std::vector<GfNotePlan> &a
     size_t n_pass = 0;
     for (int i = 0; i < nn; ++i) n_pass += wh.plans[i].n_passes;
     wh.passes.resize(n_pass);
+    // frame-kernel CTAs per pass of every note: as few as GF_BLOCKS_PER_CTA allows, finer at the tail of each launch
+    std::vector<int> fparts(nn);
+    for (int i = 0; i < nn; ++i) {
+        const int n_blocks = std::max(wh.plans[i].T_out, 2) - 2 + 1;
+        fparts[i] = std::max(1, (n_blocks + GF_BLOCKS_PER_CTA - 1) / GF_BLOCKS_PER_CTA);
+    }
+    if (!getenv("GOOFER_NO_TAIL_BALANCE")) {
+        const int slots = gf_frame_slots();
+        if (n_parts > 0) {
+            int prev_end = 0;
+            for (int k = 0; k < n_parts; ++k) {
+                const int a = std::max(prev_end, i0) - i0, e = std::min(parts[k].note_end, i1) - i0;
+                prev_end = parts[k].note_end;
+                if (e > a) gf_balance_frame_group(wh.plans, a, e, slots, fparts);
+            }
+        } else gf_balance_frame_group(wh.plans, 0, nn, slots, fparts);
+    }
     size_t pi = 0;
     // per-note double scalars (maxima, rms sums, percentile): one block, one memset
     // per-note double scalars and per-pass device-written scalars are carved back to back: ONE memset zeroes both
@@ -567,7 +619,7 @@ static int gf_render_wave(const GooferBatch *b, const std::vector<GfNotePlan> &a
         const int tiles = (p.T_out + GF_FT - 1) / GF_FT;
         for (int t = 0; t * GF_ENV_TPC < tiles; ++t) wh.env_work.push_back(make_int2(i, t));      // GF_ENV_TPC tiles per CTA
         const int n_blocks = std::max(p.T_out, 2) - 2 + 1;
-        const int bpc = gf_blocks_per_cta(n_blocks);
+        const int bpc = (n_blocks + fparts[i] - 1) / fparts[i];
         for (int k = 0; k < p.n_passes; ++k)
             for (int bb = 0; bb < n_blocks; bb += bpc)
                 wh.frame_work.push_back(make_int4((int)(pi + k), 2 + bb, std::min(bpc, n_blocks - bb), 0));
