@@ -252,38 +252,30 @@ void gf_launch_mix(const GfNotePlan *plans, const GfNoteDev *notes, const GfPass
 }
 
 // ------------------------------------------------------------------------------------------------
-// dynamic_butter_filter (SillySampler.py:95-174): `order` cascaded one-pole sections whose
-// coefficient follows f0 per sample.  One CTA per signal; each thread owns a contiguous chunk.  Per
-// section: (1) every thread composes the affine map of its chunk, (2) the 256 maps are scanned,
-// (3) every thread replays its chunk from the right initial state.  f32 throughout like the reference.
+// dynamic_butter_filter (SillySampler.py:95-174): `order` cascaded one-pole sections whose coefficient follows f0 per
+// sample.  One CTA per signal, which it walks in tiles of 256 threads x 16 samples.  A tile is read ONCE (16 contiguous
+// samples per thread, 16-byte loads), taken through ALL sections in registers, and written once: per section every
+// thread composes the affine map y_out = A y_in + B of its 16 samples, the 256 maps are scanned (warp shuffles + one
+// shared-memory hop), every thread replays its samples from the right incoming state, and the outputs are the next
+// section's inputs.  Section states and (high-pass) previous inputs are carried from tile to tile.  f32 throughout like
+// the numba kernel.  (The first version gave each thread one 172-sample chunk and re-read coefficient and signal from
+// global memory with a 172-element lane stride, twice per section: 32 sectors per warp load -- L2-transaction bound.)
 // ------------------------------------------------------------------------------------------------
-
-// walk a lane's chunk eight samples at a time: the sixteen loads of a batch are in flight together (the
-// recurrence itself is serial, the memory latency no longer is); the body may store to position i (y may alias x:
-// the batch was loaded before its first store)
-template <typename Body>
-__device__ __forceinline__ void gf_chunk8(int c0, int c1, const float *__restrict__ alpha, const float *src, Body body)
-{
-    int i = c0;
-    for (; i + 8 <= c1; i += 8) {
-        float a[8], x[8];
-#pragma unroll
-        for (int k = 0; k < 8; ++k) { a[k] = alpha[i + k]; x[k] = src[i + k]; }
-#pragma unroll
-        for (int k = 0; k < 8; ++k) body(a[k], x[k], i + k);
-    }
-    for (; i < c1; ++i) body(alpha[i], src[i], i);
-}
-
 #define GF_OP_THREADS 256
+#define GF_OP_K 16
+#define GF_OP_TILE (GF_OP_THREADS * GF_OP_K)
+#define GF_OP_MAX_ORDER 12
+
 __global__ void __launch_bounds__(GF_OP_THREADS) gf_onepole_kernel(const GfOnepoleJob *__restrict__ jobs)
 {
-    __shared__ float wA[GF_OP_THREADS / 32], wB[GF_OP_THREADS / 32];
+    __shared__ float wA[GF_OP_THREADS / 32], wB[GF_OP_THREADS / 32], sEdge[GF_OP_THREADS / 32];
+    __shared__ float sY[GF_OP_MAX_ORDER], sXp[GF_OP_MAX_ORDER];     // tile-to-tile carries: section state, last input of the section
     const GfOnepoleJob jb = jobs[blockIdx.x];
     const int n = jb.n, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (n <= 0) return;
+    const int order = min(max(1, jb.order), GF_OP_MAX_ORDER);
     const double srd = (double)jb.sr;
-    // ---- per-sample coefficient (SillySampler.py:128-152), f32 stores like the numba kernel ----
+    // np.any(f0 > 0) decides whether the 5-tap smoothing runs (SillySampler.py:107-113)
     bool any_pos_l = false;
     for (int i = tid; i < n; i += GF_OP_THREADS) {
         float f = jb.f0 ? jb.f0[i] : (float)jb.f0_const;
@@ -297,63 +289,110 @@ __global__ void __launch_bounds__(GF_OP_THREADS) gf_onepole_kernel(const GfOnepo
         if (jb.f0_floor > 0.0) f = fmaxf(f, (float)jb.f0_floor);
         return f;
     };
-    for (int i = tid; i < n; i += GF_OP_THREADS) {
-        float f0s;
-        if (jb.smooth_f0 && any_pos) {
-            // np.convolve(pad(f0, 2, 'edge'), ones(5)/5, 'valid') in f32
-            const float k = 1.0f / 5.0f;
-            float a = 0.0f;
-            // np.convolve accumulates sum_j k[j] * x[i + 4 - j]: order of terms j = 0..4
-            for (int j = 0; j < 5; ++j) a = fmaf(k, drv(i + 2 - j), a);
-            f0s = a;
-        } else f0s = drv(i);
-        float fc = (f0s > 0.0f) ? (float)((double)f0s * jb.cutoff_factor) : (float)jb.cutoff_factor;
-        fc = fmaxf(fc, jb.highpass ? 20.0f : 60.0f);
-        fc = (float)fmin((double)fc, 0.45 * srd);
-        const double w = (2.0 * 3.141592653589793) * (double)fc;
-        jb.alpha[i] = (float)(jb.highpass ? srd / (w + srd) : w / (w + srd));
-    }
+    if (tid < GF_OP_MAX_ORDER) { sY[tid] = 0.0f; sXp[tid] = 0.0f; }
     __syncthreads();
-    // thread t owns samples [c0, c1); per section: (1) compose the affine map of the chunk, (2) scan the 256 maps
-    // (warp shuffles + one shared-memory hop), (3) replay the chunk from the right initial state
-    const int chunk = (n + GF_OP_THREADS - 1) / GF_OP_THREADS;
-    const int c0 = min(n, tid * chunk), c1 = min(n, c0 + chunk);
-    for (int pass = 0; pass < max(1, jb.order); ++pass) {
-        const float *src = (pass == 0) ? jb.x : jb.y;
-        float A = 1.0f, B = 0.0f;
-        // x[c0 - 1] is read before any thread stores this section's output (y may alias the input): barrier below
-        const float xp_first = (c0 > 0 && c0 < n) ? src[c0 - 1] : src[0];
-        if (!jb.highpass) {
-            // y = y + a (x - y) = (1 - a) y + a x
-            gf_chunk8(c0, c1, jb.alpha, src, [&](float a, float x, int) { A = (1.0f - a) * A; B = fmaf(a, x - B, B); });
-        } else {
-            float xp = xp_first;
-            // y = a (y + x - xp)
-            gf_chunk8(c0, c1, jb.alpha, src, [&](float a, float x, int) { A = a * A; B = a * ((B - xp) + x); xp = x; });
-        }
-        // inclusive scan inside the warp: (sA, sB) = map of chunks [warp start .. this thread]
-        float sA = A, sB = B;
+    const bool vec = ((((uintptr_t)jb.x) | ((uintptr_t)jb.y)) & 15) == 0;
+    const bool hp = jb.highpass != 0;
+
+    for (int tile0 = 0; tile0 < n; tile0 += GF_OP_TILE) {
+        const int c0 = tile0 + GF_OP_K * tid;
+        const int cnt = max(0, min(GF_OP_K, n - c0));
+        const int tile_last = (min(n, tile0 + GF_OP_TILE) - 1 - tile0) / GF_OP_K;       // thread that owns the tile's last sample
+        float xin[GF_OP_K], al[GF_OP_K];
+        if (cnt == GF_OP_K && vec) {
 #pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const float pA = __shfl_up_sync(0xffffffffu, sA, o), pB = __shfl_up_sync(0xffffffffu, sB, o);
-            if (lane >= o) { sB = fmaf(sA, pB, sB); sA = sA * pA; }
-        }
-        if (lane == 31) { wA[warp] = sA; wB[warp] = sB; }
-        __syncthreads();                                  // also orders the xp_first reads before the stores below
-        // state entering this warp: zero initial state pushed through the maps of the earlier warps
-        float y = 0.0f;
-        for (int w = 0; w < warp; ++w) y = fmaf(wA[w], y, wB[w]);
-        // ... and through the earlier chunks of this warp
-        const float eA = __shfl_up_sync(0xffffffffu, sA, 1), eB = __shfl_up_sync(0xffffffffu, sB, 1);
-        if (lane > 0) y = fmaf(eA, y, eB);
-        float *dst = jb.y;
-        if (!jb.highpass) {
-            gf_chunk8(c0, c1, jb.alpha, src, [&](float a, float x, int i) { y = fmaf(a, x - y, y); dst[i] = y; });
+            for (int q = 0; q < GF_OP_K / 4; ++q) {
+                const float4 v = *reinterpret_cast<const float4 *>(jb.x + c0 + 4 * q);
+                xin[4 * q] = v.x; xin[4 * q + 1] = v.y; xin[4 * q + 2] = v.z; xin[4 * q + 3] = v.w;
+            }
         } else {
-            float xp = xp_first;
-            gf_chunk8(c0, c1, jb.alpha, src, [&](float a, float x, int i) { y = a * ((y - xp) + x); xp = x; dst[i] = y; });
+#pragma unroll
+            for (int k = 0; k < GF_OP_K; ++k) xin[k] = (k < cnt) ? jb.x[c0 + k] : 0.0f;
         }
-        __syncthreads();
+        // ---- per-sample coefficient (SillySampler.py:128-152), f32 stores like the numba kernel ----
+#pragma unroll
+        for (int k = 0; k < GF_OP_K; ++k) {
+            al[k] = 0.0f;
+            if (k < cnt) {
+                const int i = c0 + k;
+                float f0s;
+                if (jb.smooth_f0 && any_pos) {
+                    // np.convolve(pad(f0, 2, 'edge'), ones(5)/5, 'valid') in f32: sum_j k[j] * x[i + 4 - j], j = 0..4
+                    const float kk = 1.0f / 5.0f;
+                    float a = 0.0f;
+                    for (int j = 0; j < 5; ++j) a = fmaf(kk, drv(i + 2 - j), a);
+                    f0s = a;
+                } else f0s = drv(i);
+                float fc = (f0s > 0.0f) ? (float)((double)f0s * jb.cutoff_factor) : (float)jb.cutoff_factor;
+                fc = fmaxf(fc, hp ? 20.0f : 60.0f);
+                fc = (float)fmin((double)fc, 0.45 * srd);
+                const double w = (2.0 * 3.141592653589793) * (double)fc;
+                al[k] = (float)(hp ? srd / (w + srd) : w / (w + srd));
+            }
+        }
+        for (int pass = 0; pass < order; ++pass) {
+            // carries of this section from the previous tile: read before the barriers below, rewritten after them
+            const float y_carry = sY[pass], xp_carry = sXp[pass];
+            float mylast = xin[0];
+#pragma unroll
+            for (int k = 1; k < GF_OP_K; ++k) if (k < cnt) mylast = xin[k];
+            // ---- high-pass: the section's input just before this thread's first sample ----
+            float xp_first = xin[0];                               // very first sample of the signal: x[-1] := x[0]
+            if (hp) {
+                if (lane == 31) sEdge[warp] = mylast;
+                __syncthreads();
+                const float up = __shfl_up_sync(0xffffffffu, mylast, 1);
+                if (lane > 0) xp_first = up;
+                else if (warp > 0) xp_first = sEdge[warp - 1];
+                else if (tile0 > 0) xp_first = xp_carry;
+            }
+            // ---- (1) affine map of the thread's samples from a zero state ----
+            float A = 1.0f, B = 0.0f;
+            if (!hp) {
+#pragma unroll
+                for (int k = 0; k < GF_OP_K; ++k)
+                    if (k < cnt) { A = (1.0f - al[k]) * A; B = fmaf(al[k], xin[k] - B, B); }       // y = y + a (x - y)
+            } else {
+                float xp = xp_first;
+#pragma unroll
+                for (int k = 0; k < GF_OP_K; ++k)
+                    if (k < cnt) { A = al[k] * A; B = al[k] * ((B - xp) + xin[k]); xp = xin[k]; }  // y = a (y + x - xp)
+            }
+            // ---- (2) scan of the 256 maps ----
+            float sA = A, sB = B;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const float pA = __shfl_up_sync(0xffffffffu, sA, o), pB = __shfl_up_sync(0xffffffffu, sB, o);
+                if (lane >= o) { sB = fmaf(sA, pB, sB); sA = sA * pA; }
+            }
+            if (lane == 31) { wA[warp] = sA; wB[warp] = sB; }
+            __syncthreads();
+            float y = (tile0 > 0) ? y_carry : 0.0f;
+            for (int w = 0; w < warp; ++w) y = fmaf(wA[w], y, wB[w]);
+            const float eA = __shfl_up_sync(0xffffffffu, sA, 1), eB = __shfl_up_sync(0xffffffffu, sB, 1);
+            if (lane > 0) y = fmaf(eA, y, eB);
+            // ---- (3) replay; the outputs are the next section's inputs ----
+            if (!hp) {
+#pragma unroll
+                for (int k = 0; k < GF_OP_K; ++k)
+                    if (k < cnt) { y = fmaf(al[k], xin[k] - y, y); xin[k] = y; }
+            } else {
+                float xp = xp_first;
+#pragma unroll
+                for (int k = 0; k < GF_OP_K; ++k)
+                    if (k < cnt) { const float x = xin[k]; y = al[k] * ((y - xp) + x); xp = x; xin[k] = y; }
+            }
+            if (tid == tile_last) { sY[pass] = y; sXp[pass] = mylast; }
+            __syncthreads();                                       // wA / wB / sEdge and the carries are rewritten by the next section
+        }
+        if (cnt == GF_OP_K && vec) {
+#pragma unroll
+            for (int q = 0; q < GF_OP_K / 4; ++q)
+                *reinterpret_cast<float4 *>(jb.y + c0 + 4 * q) = make_float4(xin[4 * q], xin[4 * q + 1], xin[4 * q + 2], xin[4 * q + 3]);
+        } else {
+#pragma unroll
+            for (int k = 0; k < GF_OP_K; ++k) if (k < cnt) jb.y[c0 + k] = xin[k];
+        }
     }
 }
 
