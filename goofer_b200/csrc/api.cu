@@ -273,6 +273,8 @@ static void gf_carve_note(const GfNotePlan &p, Bump &bp, GfNoteDev *nd, GfPassDe
         d.sg_ev_i = bp.arr<int>((size_t)d.sg_cap);
         d.sg_ev_f = bp.arr<double>((size_t)d.sg_cap);
         d.sg_rep = bp.arr<int>((size_t)d.sg_cap);
+        d.sg_len = bp.arr<int>((size_t)d.sg_cap);
+        d.sg_m = bp.arr<float>((size_t)d.sg_cap);
         int m = 128;
         while (m < 2 * d.sg_cap) m <<= 1;
         d.sg_tab_n = m;

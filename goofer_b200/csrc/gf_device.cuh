@@ -88,6 +88,8 @@ struct GfNoteDev {
     int *sg_ev_i;           // (sg_cap,) event sample index
     double *sg_ev_f;        // (sg_cap,) event sub_f0
     int *sg_rep;            // (sg_cap,) index of the first event with the same '%.2f' key
+    int *sg_len;            // (sg_cap,) length of the event's pulse = that of its representative (gf_sg_bank_kernel)
+    float *sg_m;            // (sg_cap,) peak of that pulse table
     int2 *sg_tab;           // (sg_tab_n,) open-addressing table: x = key, y = first event index
     int sg_cap, sg_tab_n;
     double *noteScal;       // small per-note double scalars (maxima, rms)

@@ -68,12 +68,14 @@ gf_sg_walk_kernel(const int *__restrict__ list, int n_list, const GfNotePlan *__
         __syncwarp();
         unsigned fire = 0u;
         if (am) {
+            // straight-line chain: an inactive sample adds +0.0, which leaves the (non-negative) phase and the
+            // comparison unchanged, so no branch sits between the dependent additions
 #pragma unroll
             for (int k = 0; k < 32; ++k) {
-                if ((am >> k) & 1u) {
-                    phase = __dadd_rn(phase, s_inc[w][k]);
-                    if (phase >= 1.0) { fire |= (1u << k); phase = __dsub_rn(phase, 1.0); }
-                }
+                phase = __dadd_rn(phase, s_inc[w][k]);
+                const bool f = phase >= 1.0;
+                fire |= f ? (1u << k) : 0u;
+                phase = f ? __dsub_rn(phase, 1.0) : phase;
             }
         }
         __syncwarp();
@@ -105,6 +107,8 @@ __device__ __forceinline__ int gf_sub_len(double sf0, double sr)
 // One CTA per note: clear the table, insert every event (atomicCAS on the key, atomicMin on the
 // event index), then resolve.
 // ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float gf_sub_lf_max(double T, int n);
+
 __global__ void __launch_bounds__(512)
 gf_sg_bank_kernel(const int *__restrict__ list, const GfNotePlan *__restrict__ plans, const GfNoteDev *__restrict__ notes,
                   GfPassScal *scal)
@@ -136,7 +140,12 @@ gf_sg_bank_kernel(const int *__restrict__ list, const GfNotePlan *__restrict__ p
         while (tab[2 * s] != key) s = (s + 1) & (M - 1);
         const int r = tab[2 * s + 1];
         nd.sg_rep[e] = r;
-        mx = max(mx, gf_sub_len(nd.sg_ev_f[r], (double)pl.sr));
+        // the pulse of the event is its representative's: length and table peak once per event, not per rendered sample
+        const double sf0 = nd.sg_ev_f[r];
+        const int len = gf_sub_len(sf0, (double)pl.sr);
+        nd.sg_len[e] = len;
+        nd.sg_m[e] = gf_sub_lf_max(__ddiv_rn(1.0, sf0), len);
+        mx = max(mx, len);
     }
     for (int o = 16; o > 0; o >>= 1) mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
     if ((threadIdx.x & 31) == 0 && mx > 0) atomicMax(&scal[nd.pass0].sub_max_len, mx);
@@ -184,7 +193,6 @@ gf_sg_render_kernel(const int *__restrict__ list, const GfNotePlan *__restrict__
     const int n = pl.n_total;
     const int E = scal[nd.pass0].n_sub_events;
     const int max_len = scal[nd.pass0].sub_max_len;
-    const double sr = (double)pl.sr;
     float mx = 0.0f;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         int lo = 0, hi = E;
@@ -196,12 +204,11 @@ gf_sg_render_kernel(const int *__restrict__ list, const GfNotePlan *__restrict__
             while (e0 > 0 && i - nd.sg_ev_i[e0 - 1] < max_len) --e0;
             for (int e = e0; e <= last; ++e) {
                 const int d = i - nd.sg_ev_i[e];
-                const double sf0 = nd.sg_ev_f[nd.sg_rep[e]];
-                const int len = gf_sub_len(sf0, sr);
+                const int len = nd.sg_len[e];
                 if (d < len) {
-                    const double T = __ddiv_rn(1.0, sf0);
+                    const double T = __ddiv_rn(1.0, nd.sg_ev_f[nd.sg_rep[e]]);
                     const float raw = gf_sub_lf_value(d, T, len);
-                    const float m = gf_sub_lf_max(T, len);
+                    const float m = nd.sg_m[e];
                     acc += (double)((m > 0.0f) ? __fdiv_rn(raw, m) : raw);
                 }
             }
