@@ -372,7 +372,12 @@ gf_env_kernel(const int2 *__restrict__ work, const GfNotePlan *__restrict__ plan
     float *rA = sm.rows[warp][0] + GF_ROW_L, *rB = sm.rows[warp][1] + GF_ROW_L;
     // the FIR windows also touch cells outside [-radius, 512 + radius] (zero-padded taps, idle lanes): they
     // must hold finite values, 0 * NaN left over from an earlier kernel would poison the sums
-    for (int q = lane; q < 2 * GF_ROW_LEN; q += 32) sm.rows[warp][0][q] = 0.0f;
+    // (only the pads: the 513 bins of a row are always written before they are read)
+    for (int q = lane; q < GF_ROW_LEN - GF_NBINS; q += 32) {
+        const int c = q < GF_ROW_L ? q : q + GF_NBINS;                 // [0, 32) and [545, 600) of a row
+        sm.rows[warp][0][c] = 0.0f;
+        sm.rows[warp][1][c] = 0.0f;
+    }
     __syncwarp();
     const int b0 = min(GF_EPL * lane, 510);               // lane 31 owns nothing: it shadows lane 30 (reads stay inside the row)
     const int nown = (lane == 31) ? 0 : min(GF_EPL, GF_NBINS - b0);   // bins this lane owns
