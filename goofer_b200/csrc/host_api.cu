@@ -221,8 +221,9 @@ extern "C" int goofer_render_batch_host(const GooferBatch *b)
     // Measured on B200 (c2, 1,024 notes, 5.7 ms of kernels): the phase upload takes 7.4 ms (380 MB at 52 GB/s) and the
     // download 4.5 ms (180 MB at ~40 GB/s while the upload runs); the first output exists only after the preparation
     // kernels of the whole batch (~4 ms).  Small equal parts start the download early and leave little to do after the
-    // last phase byte: 8 parts 8.7 ms, 4 parts 9.3 ms, graded 50/25/15/10 10.0 ms.  GOOFER_HOST_CHUNK = uniform parts of
-    // that many notes; GOOFER_HOST_PARTS = comma-separated cumulative fractions.
+    // last phase byte: 8 parts 8.7 ms, 4 parts 9.3 ms, graded 50/25/15/10 10.0 ms.  Parts are sized by phase bytes, so 96
+    // sixteen-second notes go in 12 parts (18.3 -> 12.0 ms).  GOOFER_HOST_CHUNK = uniform parts of that many notes;
+    // GOOFER_HOST_PARTS = comma-separated cumulative fractions.
     std::vector<int> ends;                                 // note_end of every part, ascending, last == n_notes
     {
         const int nn = b->n_notes;
@@ -238,12 +239,26 @@ extern "C" int goofer_render_batch_host(const GooferBatch *b)
                 if (v > (ends.empty() ? 0 : ends.back()) && v < nn) ends.push_back(v);
                 q = (*nx == ',') ? nx + 1 : nx;
             }
-        } else if (nn >= 1024) {
-            for (int k = 1; k < 8; ++k) ends.push_back((int)((int64_t)nn * k / 8));
-        } else if (nn >= 512) {
-            ends = {nn / 4, nn / 2, (3 * nn) / 4};
-        } else if (nn >= 128) {
-            ends = {nn / 2};
+        } else {
+            // parts of about 45 MB of noise phases each (1,024 one-second notes: 8 parts; 96 sixteen-second notes: 12),
+            // cut where the cumulative phase bytes cross k / parts of the total, at most 16, at least 2 above 8 MB
+            std::vector<int64_t> cum(nn + 1, 0);
+            for (int i = 0; i < nn; ++i) cum[i + 1] = cum[i] + (int64_t)plans[i].n_passes * GF_NBINS * plans[i].T_out * 4;
+            const int64_t total = cum[nn];
+            int np = (int)std::min<int64_t>(16, (total + (22 << 20)) / (45 << 20));
+            if (np < 2 && total >= (8 << 20)) np = 2;
+            // notes with post-FX / pitch dynamics run a dozen small kernels and uploads per part: two parts at most
+            // (256 all-flag notes: 19.6 ms in 2 parts, 25.5 ms in 8)
+            bool any_fx = false;
+            for (int i = 0; i < nn && !any_fx; ++i) any_fx = note_needs_fx(plans[i]) || plans[i].pd != 0.0;
+            if (any_fx) np = std::min(np, 2);
+            np = std::max(1, std::min(np, nn));
+            for (int k = 1; k < np; ++k) {
+                const int64_t target = total * k / np;
+                int i = (int)(std::lower_bound(cum.begin(), cum.end(), target) - cum.begin());
+                i = std::max(i, (ends.empty() ? 0 : ends.back()) + 1);
+                if (i < nn) ends.push_back(i);
+            }
         }
         ends.push_back(nn);
     }
