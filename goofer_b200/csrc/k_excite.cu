@@ -84,6 +84,20 @@ __device__ __forceinline__ double gf_midi_at_fast(const float *__restrict__ bend
     return __dadd_rn(__dmul_rn(slope, x - x0), y0);
 }
 
+// smooth_mask_ds at sample i.  The lerp reads ms_short[j], ms_short[j + 1] with i / 4 - 1.75 <= j <= i / 4 (the ratio
+// (M - 1) / (N - 1) is at most 1 / 4, the f32 abscissae move the bracket by at most one): when the four values
+// ms_short[i / 4 - 2 .. i / 4 + 1] are equal -- everywhere except near voicing edges -- the result is that value
+// (np.interp with slope 0), without the fp64 abscissae and the division of the general path.
+__device__ __forceinline__ float gf_ms_at_fast(const float *__restrict__ s, int M, int i, int N)
+{
+    const int q = i >> 2;
+    if (q >= 2 && q + 1 < M) {
+        const float a = s[q - 2], b = s[q - 1], c = s[q], d = s[q + 1];
+        if (a == b && b == c && c == d) return c;
+    }
+    return gf_ms_at(s, M, i, N);
+}
+
 #ifndef GF_F0_CTAS
 #define GF_F0_CTAS 8                // register cap 32 (with spills): the kernel waits on loads (long scoreboard 8.9 per issue), resident warps pay:
                                     // 0.75 ms uncapped (80 registers) -> 0.60 (cap 64) -> 0.47 (cap 40) -> 0.41 ms (cap 32)
@@ -128,7 +142,7 @@ gf_f0_kernel(const GfNotePlan *__restrict__ plans, const GfNoteDev *__restrict__
         for (int base = blockIdx.x * blockDim.x; base < n; base += gridDim.x * blockDim.x) {
             const int i = base + threadIdx.x;
             float msv = 1.0f;
-            if (i < n) { msv = gf_ms_at(mshort, M, i, n); out_ms[i] = msv; }
+            if (i < n) { msv = gf_ms_at_fast(mshort, M, i, n); out_ms[i] = msv; }
             const int all_one = __syncthreads_and(msv == 1.0f);
             if (threadIdx.x == 0) ms_one[base >> 8] = (unsigned char)all_one;
             if (i >= n) continue;
@@ -147,7 +161,7 @@ gf_f0_kernel(const GfNotePlan *__restrict__ plans, const GfNoteDev *__restrict__
         // smooth_mask_ds (GOOFER.py:564-569) + per hop block: is the smoothed mask exactly 1 everywhere?  Where it
         // is, aper_uv * (1 - mask) vanishes identically and the frame kernel skips the unvoiced stream.
         float msv = 1.0f;
-        if (i < n) { msv = gf_ms_at(nd.ms_short, M, i, n); nd.ms[i] = msv; }
+        if (i < n) { msv = gf_ms_at_fast(nd.ms_short, M, i, n); nd.ms[i] = msv; }
         const int all_one = __syncthreads_and(msv == 1.0f);
         if (threadIdx.x == 0) nd.ms_one[base >> 8] = (unsigned char)all_one;
         if (i >= n) continue;
