@@ -542,3 +542,33 @@ def test_device_source_cache(tmp_path, torch_cuda):
     assert cli.SOURCE_CACHE.misses == m0 + 1 and cli.SOURCE_CACHE.hits == h0 + 1     # one file, two batches
     for x, y in zip(a, b):
         assert np.array_equal(x, y)
+
+
+def test_edge_lengths_and_empty_batch(torch_cuda):
+    """One batch with a 10 ms note (441 samples: a single STFT frame pair), a 20 s looped note, odd lengths (ragged,
+    unaligned output offsets: the 4-byte store path of the mix kernel) and an unnormalised quiet note, against the
+    oracle, with the device PCM; the host entry point returns the same samples; an empty batch is a no-op."""
+    from goofer_b200 import cli
+    feat, sf = cases.source_for(1, 1.0)
+    clis = [["C4", "100", "", "0", "333", "0", "0", "100", "0", "!120", "AA"], ["D4", "100", "g5", "0", "10", "0", "0", "100", "0", "!120", "AA"],
+            ["E4", "100", "L1", "0", "20000", "50", "0", "100", "0", "!120", "AA"], ["F4", "100", "P0", "0", "777", "0", "0", "37", "0", "!120", "AA"]]
+    b = host.Batch()
+    b.add_source(sf)
+    for c in clis:
+        b.add_note(host.NoteArgs.from_cli(0, c))
+    ab = b.assemble(host.SeededNoise(cases.SEED_BASE, cases.SEED_LEGACY))
+    db = ab.to_device("cuda:0").enable_pcm16()
+    db.render()
+    torch_cuda.cuda.synchronize()
+    outs, pcm = db.outputs(), db.outputs_pcm16()
+    assert [len(o) for o in outs] == [14685, 441, 884205, 34265]
+    for c, o, q in zip(clis, outs, pcm):
+        ref = cases.oracle_render(feat, c)
+        assert np.max(np.abs(o.astype(np.float64) - ref)) <= MAX_ABS, c
+        assert np.array_equal(q, cli.pcm16_like_soundfile(o))
+    for h, o in zip(ab.render_host(), outs):
+        assert np.array_equal(h, o)
+    empty = host.Batch()
+    empty.add_source(sf)
+    ab0 = empty.assemble(host.SeededNoise(1, 2))
+    assert ab0.render_host() == []
