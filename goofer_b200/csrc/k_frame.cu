@@ -175,12 +175,19 @@ __device__ __forceinline__ void gf_ola_round(float (*carry)[GF_HOP], const float
     for (int f = 0; f < NF; ++f) {
         if (no_input) break;                               // skipped stream: only flush what earlier rounds carried
         const float *zf = reinterpret_cast<const float *>(bufs + (size_t)f * GF_FFT_BUF);
-        const bool blur = voiced && voiced[f];
+        const bool blur = voiced && voiced[f];                 // CTA-uniform: a branch, not four selects
+        float v[4];
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
             const int j = GF_HOP * q + r;
-            const float v = zf[2 * gf_fpad(j >> 1) + (j & 1)];
-            acc[f + q] = __fadd_rn(acc[f + q], __fmul_rn(v, blur ? wg[q] : w[q]));
+            v[q] = zf[2 * gf_fpad(j >> 1) + (j & 1)];
+        }
+        if (blur) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) acc[f + q] = __fadd_rn(acc[f + q], __fmul_rn(v[q], wg[q]));
+        } else {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) acc[f + q] = __fadd_rn(acc[f + q], __fmul_rn(v[q], w[q]));
         }
     }
     const int n_emit = last ? NF + 1 : NF;                 // the final frame also finishes block T
