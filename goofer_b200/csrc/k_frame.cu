@@ -159,7 +159,8 @@ template <int NF>
 __device__ __forceinline__ void gf_ola_round(float (*carry)[GF_HOP], const float2 *bufs, const float *__restrict__ win,
                                              int t0, int T, int n_out, float *__restrict__ out, int b0, int nb, bool last,
                                              bool no_input, const unsigned char *__restrict__ blk_dead, bool all_dead, float ws_full,
-                                             const int *voiced /* per frame: use the blur-carrying window winG; NULL: never */)
+                                             const int *voiced /* per frame: use the blur-carrying window winG; NULL: never */,
+                                             float rcp_full /* RN(1 / ws_full), or 0 when the exact short division does not apply */)
 {
     const int r = threadIdx.x;
     float acc[NF + 3];
@@ -205,7 +206,12 @@ __device__ __forceinline__ void gf_ola_round(float (*carry)[GF_HOP], const float
                 }
             }
             float y = acc[m];
-            if (ws > 1e-9f) y = y / ws;                    // (double) ws > 1e-9: RN_f32(1e-9) < 1e-9, so the f32 compare selects the same floats
+            if (ws == ws_full && rcp_full != 0.0f) {
+                // y / ws correctly rounded in three instructions (Markstein: q = RN(y r), rem = y - ws q exact in an FMA,
+                // RN(q + rem r) with r = RN(1 / ws); ws ~ 1.998 here, significand not all ones: checked in the kernel prologue)
+                const float q = y * rcp_full;
+                y = fmaf(fmaf(-q, ws, y), rcp_full, q);
+            } else if (ws > 1e-9f) y = y / ws;             // (double) ws > 1e-9: RN_f32(1e-9) < 1e-9, so the f32 compare selects the same floats
             const int i = GF_HOP * (b - 2) + r;
             // blocks of the unvoiced stream that nobody reads (gain (1 - mask) * 0.75 == 0 on the whole block) are not stored
             const bool dead = all_dead || (blk_dead && blk_dead[b - 2]);
@@ -251,6 +257,7 @@ gf_frame_kernel(const int4 *__restrict__ work, const GfPassDev *__restrict__ pas
     float ws_full = 0.0f;
 #pragma unroll
     for (int q = 3; q >= 0; --q) ws_full = __fadd_rn(ws_full, d_tab.win2[GF_HOP * q + tid]);
+    const float rcp_full = (ws_full > 1e-9f && (__float_as_uint(ws_full) & 0x7fffffu) != 0x7fffffu) ? __frcp_rn(ws_full) : 0.0f;
     __syncthreads();
 
     for (int t0 = t_begin; t0 <= t_end; t0 += GF_RND) {
@@ -360,16 +367,16 @@ gf_frame_kernel(const int4 *__restrict__ work, const GfPassDev *__restrict__ pas
             const bool last = (t0 + nf - 1 == T - 1);
             if (nf == GF_RND) {
 #pragma unroll
-                for (int s = 0; s < 3; ++s) gf_ola_round<GF_RND>(sm.carry[s], &sm.z[s][0][0], win, t0, T, n, outs[s], b0, nb, last, s == 2 && !uv_on, s == 2 ? nd.ms_one : nullptr, s == 2 && ps.mask_ones, ws_full, s < 2 ? sm.voiced : nullptr);
+                for (int s = 0; s < 3; ++s) gf_ola_round<GF_RND>(sm.carry[s], &sm.z[s][0][0], win, t0, T, n, outs[s], b0, nb, last, s == 2 && !uv_on, s == 2 ? nd.ms_one : nullptr, s == 2 && ps.mask_ones, ws_full, s < 2 ? sm.voiced : nullptr, rcp_full);
             } else if (nf == 3) {
 #pragma unroll
-                for (int s = 0; s < 3; ++s) gf_ola_round<3>(sm.carry[s], &sm.z[s][0][0], win, t0, T, n, outs[s], b0, nb, last, s == 2 && !uv_on, s == 2 ? nd.ms_one : nullptr, s == 2 && ps.mask_ones, ws_full, s < 2 ? sm.voiced : nullptr);
+                for (int s = 0; s < 3; ++s) gf_ola_round<3>(sm.carry[s], &sm.z[s][0][0], win, t0, T, n, outs[s], b0, nb, last, s == 2 && !uv_on, s == 2 ? nd.ms_one : nullptr, s == 2 && ps.mask_ones, ws_full, s < 2 ? sm.voiced : nullptr, rcp_full);
             } else if (nf == 2) {
 #pragma unroll
-                for (int s = 0; s < 3; ++s) gf_ola_round<2>(sm.carry[s], &sm.z[s][0][0], win, t0, T, n, outs[s], b0, nb, last, s == 2 && !uv_on, s == 2 ? nd.ms_one : nullptr, s == 2 && ps.mask_ones, ws_full, s < 2 ? sm.voiced : nullptr);
+                for (int s = 0; s < 3; ++s) gf_ola_round<2>(sm.carry[s], &sm.z[s][0][0], win, t0, T, n, outs[s], b0, nb, last, s == 2 && !uv_on, s == 2 ? nd.ms_one : nullptr, s == 2 && ps.mask_ones, ws_full, s < 2 ? sm.voiced : nullptr, rcp_full);
             } else {
 #pragma unroll
-                for (int s = 0; s < 3; ++s) gf_ola_round<1>(sm.carry[s], &sm.z[s][0][0], win, t0, T, n, outs[s], b0, nb, last, s == 2 && !uv_on, s == 2 ? nd.ms_one : nullptr, s == 2 && ps.mask_ones, ws_full, s < 2 ? sm.voiced : nullptr);
+                for (int s = 0; s < 3; ++s) gf_ola_round<1>(sm.carry[s], &sm.z[s][0][0], win, t0, T, n, outs[s], b0, nb, last, s == 2 && !uv_on, s == 2 ? nd.ms_one : nullptr, s == 2 && ps.mask_ones, ws_full, s < 2 ? sm.voiced : nullptr, rcp_full);
             }
         }
         __syncthreads();
