@@ -222,7 +222,10 @@ void gf_launch_f0(const GfNotePlan *plans, const GfNoteDev *notes, const GfPassD
 {
     if (n_notes <= 0) return;
     // few fat CTAs per note (the per-CTA prologue reads three records) unless the batch is too small to fill the GPU
-    const int gx = max(8, min(64, (1184 + n_notes - 1) / n_notes));
+#ifndef GF_F0_GX
+#define GF_F0_GX 8
+#endif
+    const int gx = max(GF_F0_GX, min(64, (1184 + n_notes - 1) / n_notes));
     dim3 grid(min(gx, (max_n + 255) / 256), n_notes);
     gf_f0_kernel<<<grid, 256, 0, st>>>(plans, notes, passes, srcs, bend, normals, f0_curves);
 }
@@ -620,7 +623,9 @@ void gf_launch_walk(const GfPassDev *passes, GfPassScal *scal, int n_pass, int m
 // guards (< 1e-8 relative, like the reference's own 5-slot table cache, which reuses one T per T0).
 // ------------------------------------------------------------------------------------------------
 #define GF_PULSE_CAP 512
+#ifndef GF_PULSE_SPAN
 #define GF_PULSE_SPAN 4096            // samples per CTA: a contiguous run of 256-sample tiles whose onsets are staged once
+#endif
 __device__ __forceinline__ float gf_lf_value_f32(int d, int jp, int jc, float r_rise, float r_fall, float inv_max)
 {
     float v = 0.0f;

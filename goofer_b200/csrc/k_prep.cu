@@ -652,7 +652,10 @@ gf_mask_kernel(const GfNotePlan *__restrict__ plans, const GfNoteDev *__restrict
 void gf_launch_mask(const GfNotePlan *plans, const GfNoteDev *notes, const GfSourceDev *srcs, int n_notes, int max_n, cudaStream_t st)
 {
     if (n_notes <= 0) return;
-    dim3 grid(min(16, (max_n + 255) / 256), n_notes);
+#ifndef GF_MASK_GX
+#define GF_MASK_GX 16
+#endif
+    dim3 grid(min(GF_MASK_GX, (max_n + 255) / 256), n_notes);
     gf_mask_kernel<<<grid, 256, 0, st>>>(plans, notes, srcs);
 }
 

@@ -116,7 +116,10 @@ void gf_launch_peak(const GfNotePlan *plans, const GfNoteDev *notes, const GfPas
                     int n_pass, int max_n, bool any_simple, bool any_general, cudaStream_t st)
 {
     if (n_pass <= 0) return;
-    dim3 grid(min(8, (max_n + 1023) / 1024), n_pass);       // few fat CTAs: the per-thread record loads amortise over ~20 samples
+#ifndef GF_TAIL_GX
+#define GF_TAIL_GX 8
+#endif
+    dim3 grid(min(GF_TAIL_GX, (max_n + 1023) / 1024), n_pass);       // few fat CTAs: the per-thread record loads amortise over ~20 samples
     if (any_simple) gf_peak_kernel<true><<<grid, 256, 0, st>>>(plans, notes, passes, scal, pass0);
     if (any_general) gf_peak_kernel<false><<<grid, 256, 0, st>>>(plans, notes, passes, scal, pass0);
 }
@@ -246,7 +249,7 @@ void gf_launch_mix(const GfNotePlan *plans, const GfNoteDev *notes, const GfPass
                    int note0, int n_notes, int max_n, bool any_simple, bool any_general, cudaStream_t st)
 {
     if (n_notes <= 0) return;
-    dim3 grid(min(8, (max_n + 1023) / 1024), n_notes);
+    dim3 grid(min(GF_TAIL_GX, (max_n + 1023) / 1024), n_notes);
     if (any_simple) gf_mix_kernel<true><<<grid, 256, 0, st>>>(plans, notes, passes, scal, note0);
     if (any_general) gf_mix_kernel<false><<<grid, 256, 0, st>>>(plans, notes, passes, scal, note0);
 }
