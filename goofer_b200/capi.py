@@ -44,6 +44,7 @@ class GooferNote(C.Structure):
         ("flag", C.c_int32 * GF_NFLAGS), ("present", C.c_uint64),
         ("phi_off", C.c_int64 * 4), ("nrm_off", C.c_int64 * 4), ("out_off", C.c_int64),
         ("f0_off", C.c_int64),
+        ("phi_rng", (C.c_uint64 * 4) * 4), ("phi_rng_mask", C.c_uint32), ("reserved0", C.c_uint32),
     ]
 
 

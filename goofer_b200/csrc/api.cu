@@ -294,6 +294,7 @@ static void gf_carve_note(const GfNotePlan &p, Bump &bp, GfNoteDev *nd, GfPassDe
         q.uv = bp.arr<float>(n);
         q.onset_cap = p.n_total / 8 + 64;
         q.onsets = bp.arr<int4>((size_t)q.onset_cap);
+        if ((p.phi_rng_mask >> q.kind) & 1u) q.phi_gen = bp.arr<float>((size_t)GF_NBINS * p.T_out);     // phi slot == pass kind
         if (k == 0 && p.add_subharm) q.sub = bp.arr<float>(n);
         q.mask_ones = (q.kind == GF_PASS_SA);
         if (pd) pd[k] = q;
@@ -321,7 +322,7 @@ static size_t gf_wave_meta_bytes(size_t n_notes, size_t n_pass, size_t n_env_wor
 {
     return n_notes * (sizeof(GfNotePlan) + sizeof(GfNoteDev) + GF_NS_COUNT * sizeof(double)) + n_pass * (sizeof(GfPassDev) + sizeof(GfPassScal)) +
            n_env_work * sizeof(int2) + n_frame_work * sizeof(int4) + n_fir * sizeof(GfFirJob) +
-           n_pass * 16 * sizeof(GfOnepoleJob) + n_notes * (3 * sizeof(int) + 2 * sizeof(GfFirJob)) + 32 * 256;
+           n_pass * (16 * sizeof(GfOnepoleJob) + sizeof(GfPhiJob) + 256) + n_notes * (3 * sizeof(int) + 2 * sizeof(GfFirJob)) + 32 * 256;
 }
 
 #ifndef GF_BLOCKS_PER_CTA
@@ -615,7 +616,7 @@ static int gf_render_wave(const GooferBatch *b, const std::vector<GfNotePlan> &a
             GfPassDev &q = wh.passes[pi + k];
             q.note = i;
             const int slot = q.kind;                      // phi slot == pass kind (0 main, 1 su, 2 sj, 3 sa)
-            q.phi = b->phi + p.phi_off[slot];
+            q.phi = q.phi_gen ? q.phi_gen : b->phi + p.phi_off[slot];
         }
         // work lists
         const int tiles = (p.T_out + GF_FT - 1) / GF_FT;
@@ -699,6 +700,27 @@ static int gf_render_wave(const GooferBatch *b, const std::vector<GfNotePlan> &a
         gf_launch_pulse(d_passes, d_scal, (int)n_pass, max_n, st); ++L; GF_STEP("pulse");
         if ((rc = gf_growl(wh, d_plans, d_notes, d_passes, d_scal, bp, max_n, st, &L)) != GOOFER_OK) return rc;
     }
+    // ---- noise phases drawn on the device (GooferNote.phi_rng) ----
+    {
+        std::vector<GfPhiJob> pj;
+        int max_total = 0;
+        for (size_t q = 0; q < wh.passes.size(); ++q) {
+            const GfPassDev &pd = wh.passes[q];
+            if (!pd.phi_gen) continue;
+            const GfNotePlan &p = wh.plans[pd.note];
+            GfPhiJob j;
+            j.dst = pd.phi_gen; j.total = GF_NBINS * p.T_out; j.pad = 0;
+            j.s_hi = p.phi_rng[pd.kind][0]; j.s_lo = p.phi_rng[pd.kind][1]; j.i_hi = p.phi_rng[pd.kind][2]; j.i_lo = p.phi_rng[pd.kind][3];
+            max_total = std::max(max_total, j.total);
+            pj.push_back(j);
+        }
+        if (!pj.empty()) {
+            GfPhiJob *d_pj;
+            if ((rc = gf_upload(bp, pj, &d_pj, st)) != GOOFER_OK) return rc;
+            if (bp.off > bp.cap) { gf_set_error("internal: phase jobs overflow the workspace"); return GOOFER_ERR_WORKSPACE; }
+            gf_launch_phi(d_pj, (int)pj.size(), max_total, st); ++L; GF_STEP("phi");
+        }
+    }
     // ---- envelope chain on the caller's stream ----
     gf_launch_tracks(d_plans, d_notes, d_srcs, nn, st); ++L; GF_STEP("tracks");
     gf_launch_env(d_envw, (int)wh.env_work.size(), d_plans, d_notes, d_srcs, st); ++L; GF_STEP("env");
@@ -764,14 +786,15 @@ static int gf_render_batch_ex(const GooferBatch *b, void *workspace, size_t work
     if (rc != GOOFER_OK) return rc;
     g_stats.kernel_launches = 0; g_stats.waves = 0;
     if (b->n_notes == 0) return GOOFER_OK;
-    if (!workspace || (!b->out && !b->out_pcm16) || !b->phi || !b->bend_cents) { gf_set_error("NULL workspace / out (and out_pcm16) / phi / bend_cents"); return GOOFER_ERR_INVALID; }
+    if (!workspace || (!b->out && !b->out_pcm16) || !b->bend_cents) { gf_set_error("NULL workspace / out (and out_pcm16) / bend_cents"); return GOOFER_ERR_INVALID; }
     std::vector<GfNotePlan> plans;
     if ((rc = gf_make_plans(b, plans)) != GOOFER_OK) return rc;
     for (int i = 0; i < b->n_notes; ++i) {
         const GfNotePlan &p = plans[i];
         for (int k = 0; k < p.n_passes; ++k) {
             const int slot = p.pass_kind[k];
-            if (p.phi_off[slot] < 0 || p.phi_off[slot] + (int64_t)GF_NBINS * p.T_out > b->phi_total) {
+            if ((p.phi_rng_mask >> slot) & 1u) continue;                      // drawn on the device
+            if (!b->phi || p.phi_off[slot] < 0 || p.phi_off[slot] + (int64_t)GF_NBINS * p.T_out > b->phi_total) {
                 gf_set_error("note %d: phi slot %d outside the phi buffer", i, slot);
                 return GOOFER_ERR_INVALID;
             }

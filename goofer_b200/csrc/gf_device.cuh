@@ -49,7 +49,8 @@ struct GfPassDev {
     float *harm, *bre, *uv; // raw OLA streams (n_total,)
     int4 *onsets;           // (i, T0, f32 bits of last_valid_f0, f32 bits of table max)
     int onset_cap;
-    const float *phi;       // (513, T_out) f32
+    const float *phi;       // (513, T_out) f32 (caller's buffer, or phi_gen)
+    float *phi_gen;         // workspace: phases generated on the device for this pass (GooferNote.phi_rng) or NULL
     int mask_ones;          // sa pass: voicing mask == 1
 };
 

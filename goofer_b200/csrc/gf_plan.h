@@ -83,4 +83,7 @@ struct GfNotePlan {
     int64_t nrm_off[4];
     int64_t out_off;
     int64_t f0_off;             // >= 0: direct gf.synthesize call, f0 curve at GooferBatch.f0_curves + f0_off (else -1)
+    uint64_t phi_rng[4][4];     // per phi slot: PCG64 state_hi, state_lo, inc_hi, inc_lo (GooferNote.phi_rng)
+    uint32_t phi_rng_mask;      // slots whose phases are generated on the device
+    uint32_t reserved0;
 };

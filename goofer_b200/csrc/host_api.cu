@@ -83,7 +83,7 @@ extern "C" int goofer_render_batch_host(const GooferBatch *b)
     if (rc != GOOFER_OK) return rc;
     g_stats.h2d_bytes = 0; g_stats.d2h_bytes = 0; g_stats.kernel_launches = 0; g_stats.waves = 0;
     if (b->n_notes == 0) return GOOFER_OK;
-    if ((!b->out && !b->out_pcm16) || !b->phi || !b->bend_cents) { gf_set_error("NULL out (and out_pcm16) / phi / bend_cents"); return GOOFER_ERR_INVALID; }
+    if ((!b->out && !b->out_pcm16) || !b->bend_cents) { gf_set_error("NULL out (and out_pcm16) / bend_cents"); return GOOFER_ERR_INVALID; }
     if (!g_hc.st) GF_CUDA(cudaStreamCreateWithFlags(&g_hc.st, cudaStreamNonBlocking));
     if (!g_hc.st_in) GF_CUDA(cudaStreamCreateWithFlags(&g_hc.st_in, cudaStreamNonBlocking));
     if (!g_hc.st_out) GF_CUDA(cudaStreamCreateWithFlags(&g_hc.st_out, cudaStreamNonBlocking));
@@ -122,7 +122,7 @@ extern "C" int goofer_render_batch_host(const GooferBatch *b)
             if (g.mask) ds[s].mask = bp.arr<float>((size_t)g.N);
         }
         db.bend_cents = bp.arr<float>((size_t)b->bend_total);
-        db.phi = bp.arr<float>((size_t)b->phi_total);
+        db.phi = b->phi ? bp.arr<float>((size_t)std::max<int64_t>(b->phi_total, 1)) : nullptr;
         db.normals = b->normals ? bp.arr<double>((size_t)b->nrm_total) : nullptr;
         db.f0_curves = b->f0_curves ? bp.arr<float>((size_t)b->f0_total) : nullptr;
         db.out = b->out ? bp.arr<float>((size_t)b->out_total) : nullptr;
@@ -280,8 +280,9 @@ extern "C" int goofer_render_batch_host(const GooferBatch *b)
         for (int i = i0; i < i1; ++i) {
             const GfNotePlan &p = plans[i];
             for (int k = 0; k < p.n_passes; ++k) {
+                if ((p.phi_rng_mask >> p.pass_kind[k]) & 1u) continue;           // drawn on the device: nothing to upload
                 const int64_t o = p.phi_off[p.pass_kind[k]];
-                if (o < 0) { gf_set_error("note %d: phi slot %d not supplied", i, p.pass_kind[k]); return GOOFER_ERR_INVALID; }
+                if (o < 0 || !b->phi) { gf_set_error("note %d: phi slot %d not supplied", i, p.pass_kind[k]); return GOOFER_ERR_INVALID; }
                 r.plo = std::min(r.plo, o); r.phi = std::max(r.phi, o + (int64_t)GF_NBINS * p.T_out);
             }
             const int need[4] = {p.f0_jitter, p.vol_jitter, p.vol_jitter, p.sj > 0.0};
@@ -292,6 +293,7 @@ extern "C" int goofer_render_batch_host(const GooferBatch *b)
                 }
             r.olo = std::min(r.olo, p.out_off); r.ohi = std::max(r.ohi, p.out_off + (int64_t)p.n_total);
         }
+        if (r.phi == 0) r.plo = 0;                                           // no uploaded phases in this part
         if (r.plo < 0 || r.phi > b->phi_total || (r.nhi > 0 && (!b->normals || r.nlo < 0 || r.nhi > b->nrm_total)) || r.olo < 0 || r.ohi > b->out_total) {
             gf_set_error("part %d: noise / output offsets outside their buffers", c);
             return GOOFER_ERR_INVALID;
@@ -305,7 +307,7 @@ extern "C" int goofer_render_batch_host(const GooferBatch *b)
     GF_CUDA(cudaEventRecord(g_hc.ev[2 * n_chunks], st_in));          // sources, bends, normals, f0 curves
     std::vector<GfPart> parts(n_chunks);
     for (int c = 0; c < n_chunks; ++c) {
-        if ((rc = h2d(db.phi + rg[c].plo, b->phi + rg[c].plo, sizeof(float) * (size_t)(rg[c].phi - rg[c].plo)))) return rc;
+        if (rg[c].phi > rg[c].plo && (rc = h2d(db.phi + rg[c].plo, b->phi + rg[c].plo, sizeof(float) * (size_t)(rg[c].phi - rg[c].plo)))) return rc;
         GF_CUDA(cudaEventRecord(g_hc.ev[2 * c], st_in));             // this part's phases
         parts[c].note_end = ends[c];
         parts[c].phi_ready = g_hc.ev[2 * c];

@@ -710,3 +710,58 @@ void gf_launch_pulse(const GfPassDev *passes, const GfPassScal *scal, int n_pass
     dim3 grid((max_n + GF_PULSE_SPAN - 1) / GF_PULSE_SPAN, n_pass);
     gf_pulse_kernel<<<grid, 256, 0, st>>>(passes, scal);
 }
+
+// ------------------------------------------------------------------------------------------------
+// Noise phases on the device: the stream numpy's Generator(PCG64).uniform(0, 2 pi, (513, T)).astype(float32) draws
+// (GOOFER.py:1151-1152), bit for bit.  PCG64 = 128-bit LCG (multiplier 0x2360ED051FC65DA44385DF649FCCF645, per-stream
+// odd increment), output XSL-RR 128 -> 64 of the state AFTER the step; next_double = (u64 >> 11) * 2^-53; uniform =
+// low + (high - low) * next_double with low = 0.  Element e of the row-major (513, T) array is the (e + 1)-th draw:
+// every thread jumps the LCG ahead to its first element (O(log e) 128-bit multiply-adds) and then strides by 256.
+// ------------------------------------------------------------------------------------------------
+struct GfPhiJob { float *dst; int total; int pad; unsigned long long s_hi, s_lo, i_hi, i_lo; };
+
+typedef unsigned __int128 gf_u128;
+
+// LCG jump: (mult, plus) of `delta` steps of x -> x * m + c
+__device__ __forceinline__ void gf_lcg_jump(gf_u128 m, gf_u128 c, unsigned long long delta, gf_u128 &acc_mult, gf_u128 &acc_plus)
+{
+    acc_mult = 1; acc_plus = 0;
+    while (delta > 0) {
+        if (delta & 1ull) { acc_mult *= m; acc_plus = acc_plus * m + c; }
+        c = (m + 1) * c;
+        m *= m;
+        delta >>= 1;
+    }
+}
+
+__global__ void __launch_bounds__(256) gf_phi_kernel(const GfPhiJob *__restrict__ jobs)
+{
+    const GfPhiJob jb = jobs[blockIdx.y];
+    const int per = (((jb.total + (int)gridDim.x - 1) / (int)gridDim.x) + 255) & ~255;
+    const int first = blockIdx.x * per, end = min(jb.total, first + per);
+    if (first >= jb.total) return;
+    const gf_u128 MULT = ((gf_u128)0x2360ED051FC65DA4ull << 64) | (gf_u128)0x4385DF649FCCF645ull;
+    const gf_u128 inc = ((gf_u128)jb.i_hi << 64) | (gf_u128)jb.i_lo;
+    gf_u128 state = ((gf_u128)jb.s_hi << 64) | (gf_u128)jb.s_lo;
+    gf_u128 am, ap;
+    gf_lcg_jump(MULT, inc, (unsigned long long)(first + (int)threadIdx.x) + 1ull, am, ap);       // state after the step of the first element
+    state = am * state + ap;
+    gf_u128 m256, p256;
+    gf_lcg_jump(MULT, inc, 256ull, m256, p256);
+    for (int e = first + (int)threadIdx.x; e < end; e += 256) {
+        const unsigned long long hi = (unsigned long long)(state >> 64), lo = (unsigned long long)state;
+        const unsigned rot = (unsigned)(hi >> 58);                         // state >> 122
+        const unsigned long long x = hi ^ lo;
+        const unsigned long long r = (x >> rot) | (x << ((64u - rot) & 63u));
+        const double d = __dmul_rn((double)(r >> 11), 1.0 / 9007199254740992.0);
+        jb.dst[e] = (float)__dmul_rn(6.283185307179586, d);
+        state = state * m256 + p256;
+    }
+}
+
+void gf_launch_phi(const GfPhiJob *jobs, int n_jobs, int max_total, cudaStream_t st)
+{
+    if (n_jobs <= 0 || max_total <= 0) return;
+    dim3 grid(std::max(1, std::min(16, (max_total + 4095) / 4096)), n_jobs);
+    gf_phi_kernel<<<grid, 256, 0, st>>>(jobs);
+}

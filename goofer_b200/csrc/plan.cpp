@@ -228,6 +228,9 @@ int gf_plan_note(const GooferBatch *b, int idx, GfNotePlan *pl)
     if (pl->sa > 0.0) pl->pass_kind[pl->n_passes++] = GF_PASS_SA;
     for (int k = 0; k < 4; ++k) { pl->phi_off[k] = nt.phi_off[k]; pl->nrm_off[k] = nt.nrm_off[k]; }
     pl->out_off = nt.out_off;
+    pl->phi_rng_mask = nt.phi_rng_mask & 15u;
+    for (int k = 0; k < 4; ++k)
+        for (int q = 0; q < 4; ++q) pl->phi_rng[k][q] = nt.phi_rng[k][q];
     return 0;
 }
 

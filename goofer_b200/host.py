@@ -285,6 +285,42 @@ class SeededNoise:
         return out
 
 
+class DeviceNoise(SeededNoise):
+    """Same draws as SeededNoise, but the noise phases are NOT materialised on the host: for every phi slot the
+    provider hands over the 128-bit state and increment of np.random.PCG64(base + k) and the library draws
+    rng.uniform(0, 2 pi, (513, T)).astype(float32) on the device, bit for bit (GooferNote.phi_rng, gf_phi_kernel).
+    The normals (sh / sr / sj: legacy MT19937 randn and Generator.standard_normal) stay host arrays."""
+
+    def __call__(self, index: int, info: dict) -> dict:
+        n = info["n_total"]
+        out = {}
+        leg = np.random.RandomState(self._legacy(index))
+        if info["need_nrm"][0]:
+            out["sh"] = leg.randn(n)
+        if info["need_nrm"][1]:
+            out["sr_h"] = leg.randn(n)
+            out["sr_b"] = leg.randn(n)
+        base = self._base(index)
+        k = 0
+
+        def rng_state():
+            nonlocal k
+            st = np.random.PCG64(base + k).state["state"]
+            k += 1
+            return int(st["state"]), int(st["inc"])
+
+        out["phi_rng"] = rng_state()
+        if info["need_phi"][1]:
+            out["phi_su_rng"] = rng_state()
+        if info["need_phi"][2]:
+            out["sj_z"] = np.random.Generator(np.random.PCG64(base + k)).standard_normal(n)
+            k += 1
+            out["phi_sj_rng"] = rng_state()
+        if info["need_phi"][3]:
+            out["phi_sa_rng"] = rng_state()
+        return out
+
+
 class FreshNoise(SeededNoise):
     """Unseeded noise, like the reference CLI."""
 
@@ -372,7 +408,13 @@ class Batch:
             nz = noise(i, inf)
             st = note_arr[i]
             for k, key in enumerate(_PHI_KEYS):
-                if inf["need_phi"][k]:
+                if inf["need_phi"][k] and key + "_rng" in nz:
+                    state, inc = nz[key + "_rng"]               # drawn on the device from this PCG64 stream
+                    m64 = (1 << 64) - 1
+                    st.phi_rng[k][0], st.phi_rng[k][1] = (state >> 64) & m64, state & m64
+                    st.phi_rng[k][2], st.phi_rng[k][3] = (inc >> 64) & m64, inc & m64
+                    st.phi_rng_mask |= 1 << k
+                elif inf["need_phi"][k]:
                     a = np.ascontiguousarray(nz[key], dtype=np.float32)
                     if a.shape != (N_BINS, inf["t_out"]):
                         raise ValueError(f"note {i}: noise['{key}'] must have shape ({N_BINS}, {inf['t_out']})")

@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define GOOFER_ABI_VERSION 3
+#define GOOFER_ABI_VERSION 4
 #define GOOFER_N_FFT 1024      /* SillySampler.py:14 */
 #define GOOFER_HOP 256         /* SillySampler.py:15 */
 #define GOOFER_N_BINS 513
@@ -107,6 +107,16 @@ typedef struct GooferNote {
      * their meaning as synthesize keyword arguments (g formant_shift, fa-fd F1-F4_shift, sh, sr, sg, P normalize ...).
      * -1 = a resampler note. */
     int64_t f0_off;
+    /* Noise phases generated on the device instead of uploaded (355 KB per note and pass): bit k of phi_rng_mask says
+     * that phi slot k is the stream numpy's Generator(PCG64) would draw -- rng.uniform(0, 2 pi, (513, T_out))
+     * .astype(float32), GOOFER.py:1151-1152 -- from the bit generator whose 128-bit state and increment are
+     * phi_rng[k] = {state_hi, state_lo, inc_hi, inc_lo} (np.random.PCG64(seed).state["state"]).  The kernel jumps the
+     * LCG ahead per thread and reproduces numpy's values bit for bit; phi_off[k] is then ignored (GooferBatch.phi may
+     * be NULL when every slot in use is generated).  The reference draws this noise itself (unseeded), so this is what
+     * a drop-in does in production; host-supplied buffers remain the parity-test path. */
+    uint64_t phi_rng[4][4];
+    uint32_t phi_rng_mask;
+    uint32_t reserved0;
 } GooferNote;
 
 /* What the planner derives for one note (lengths the host needs to size noise and output buffers). */

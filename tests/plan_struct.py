@@ -28,4 +28,5 @@ class GfNotePlan(C.Structure):
         ("fry_on", i32), ("fry_L", i32), ("fry_glide", i32), ("fry_const", i32),
         ("fry_mask_on", i32), ("fry_a", i32), ("fry_b", i32), ("fry_fade", i32),
         ("phi_off", i64 * 4), ("nrm_off", i64 * 4), ("out_off", i64), ("f0_off", i64),
+        ("phi_rng", C.c_uint64 * 16), ("phi_rng_mask", C.c_uint32), ("reserved0", C.c_uint32),
     ]

@@ -572,3 +572,37 @@ def test_edge_lengths_and_empty_batch(torch_cuda):
     empty.add_source(sf)
     ab0 = empty.assemble(host.SeededNoise(1, 2))
     assert ab0.render_host() == []
+
+
+def test_noise_phases_drawn_on_the_device(torch_cuda):
+    """GooferNote.phi_rng: the device draws numpy's Generator(PCG64).uniform(0, 2 pi, (513, T)).astype(float32) stream bit
+    for bit (128-bit LCG jump-ahead per thread) -- the renders with host-supplied buffers (SeededNoise) and with
+    device-drawn phases (DeviceNoise, same seeds) are identical sample for sample, through both entry points, for the
+    main, su, sj and sa passes; nothing but the seeds crosses PCIe for the phases."""
+    feat, sf = cases.source_for(2, 1.0)
+    clis = [["A3", "100", "g-20fa5br20", "0", "1000", "0", "0", "100", "0", "!120", "AA"],
+            ["C4", "100", "su40sj30sa50sh20sr10", "0", "800", "50", "0", "100", "0", "!120", "AA"],
+            ["E4", "100", "L1", "0", "2500", "50", "0", "100", "0", "!120", "AA"]]
+
+    def render(noise):
+        b = host.Batch()
+        b.add_source(sf)
+        for c in clis:
+            b.add_note(host.NoteArgs.from_cli(0, c))
+        ab = b.assemble(noise)
+        db = ab.to_device("cuda:0")
+        db.render()
+        torch_cuda.cuda.synchronize()
+        return ab, db.outputs()
+
+    ab_h, ref = render(host.SeededNoise(cases.SEED_BASE, cases.SEED_LEGACY))
+    ab_d, got = render(host.DeviceNoise(cases.SEED_BASE, cases.SEED_LEGACY))
+    assert ab_d.phi.size == 1 and ab_h.phi.size > 3 * 513 * 100                 # no phase buffer on the host side
+    for r, g in zip(ref, got):
+        assert np.array_equal(r, g)
+    host_out = ab_d.render_host()
+    h2d_device_noise = capi.last_stats()["h2d_bytes"]
+    for r, g in zip(ref, host_out):
+        assert np.array_equal(r, g)
+    ab_h.render_host()
+    assert capi.last_stats()["h2d_bytes"] - h2d_device_noise >= ab_h.phi.nbytes - 64     # only the phases differ
