@@ -181,7 +181,7 @@ class ClockSampler(threading.Thread):
 
 
 # ------------------------------------------------------------------------------------------------------
-def build_batch(args, rank):
+def build_batch(args, rank, device_noise=False):
     import bench_data
     from goofer_b200 import host
     b = host.Batch()
@@ -193,7 +193,8 @@ def build_batch(args, rank):
     for j in range(args.notes):
         src, cli = bench_data.note_cli(first + j, args.workload, n_sources=n_src)
         b.add_note(host.NoteArgs.from_cli(src, cli))
-    noise = host.SeededNoise(base_seed=lambda j: 20000 + 16 * (first + j), legacy_seed=lambda j: 777 + first + j)
+    noise_cls = host.DeviceNoise if device_noise else host.SeededNoise
+    noise = noise_cls(base_seed=lambda j: 20000 + 16 * (first + j), legacy_seed=lambda j: 777 + first + j)
     ab = b.assemble(noise)
     algo = sum(bench_data.algorithmic_bytes(inf, feats[0]["knot_vals_log"].shape[1] - 1, feats[0]["ylen"]) for inf in ab.infos)
     return ab, algo
@@ -269,6 +270,18 @@ def run_native(args):
             ab.render_host(pcm16=True)
         torch.cuda.synchronize()
         e2e_pcm = (1e3 * (time.perf_counter() - t0), capi.last_stats()["d2h_bytes"])
+        # the same batch with the noise phases drawn on the device from the host's PCG64 states (GooferNote.phi_rng:
+        # bit-identical phases, tests/test_gpu_parity.py) -- what the CLI / server do; only seeds cross PCIe for them
+        ab_dn = build_batch(args, rank, device_noise=True)[0]
+        ab_dn.pin()
+        for _ in range(2):
+            ab_dn.render_host()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            ab_dn.render_host()
+        torch.cuda.synchronize()
+        e2e_dn = (1e3 * (time.perf_counter() - t0), capi.last_stats()["h2d_bytes"], capi.last_stats()["d2h_bytes"])
     clocks.stop_flag = True
 
     t = torch.tensor([dev_ms, e2e[0] if e2e else 0.0], dtype=torch.float64, device=dev)
@@ -320,7 +333,11 @@ def run_native(args):
                            "ms_per_step": e2e_ms / args.steps,
                            "api": "goofer_render_batch_host (C ABI, pinned host buffers, per-rank wall clock, max over ranks)",
                            "pcm16_output": {"value": n_notes * args.steps / (e2e_pcm[0] * 1e-3), "unit": UNIT + " (rank 0)",
-                                            "ms_per_step": e2e_pcm[0] / args.steps, "d2h_bytes_per_step": int(e2e_pcm[1])}}
+                                            "ms_per_step": e2e_pcm[0] / args.steps, "d2h_bytes_per_step": int(e2e_pcm[1])},
+                           "device_drawn_phases": {"value": n_notes * args.steps / (e2e_dn[0] * 1e-3), "unit": UNIT + " (rank 0)",
+                                                   "ms_per_step": e2e_dn[0] / args.steps, "h2d_bytes_per_step": int(e2e_dn[1]),
+                                                   "d2h_bytes_per_step": int(e2e_dn[2]),
+                                                   "note": "same notes, same noise: PCG64 states instead of phase buffers"}}
         if args.cpu_sample > 0 and world >= 1:
             line["cpu_baseline"] = cpu_baseline_1core(args.workload, args.cpu_sample)
         print(json.dumps(line), flush=True)

@@ -87,7 +87,7 @@ def render_notes(arg_lists: Sequence[Sequence[str]], noise=None, device: str = "
         if key not in src_index:
             src_index[key] = batch.add_source(_features(feat))
         batch.add_note(host.NoteArgs.from_cli(src_index[key], list(args[2:13])))
-    ab = batch.assemble(noise or host.FreshNoise())
+    ab = batch.assemble(noise or host.FreshDeviceNoise())      # phases drawn on the device (GooferNote.phi_rng)
     db = ab.to_device(device, source_cache=SOURCE_CACHE)
     if pcm16:
         db.enable_pcm16()
