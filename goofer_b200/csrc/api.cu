@@ -330,6 +330,8 @@ static size_t gf_wave_meta_bytes(size_t n_notes, size_t n_pass, size_t n_env_wor
                                   // (172 blocks) splits in 2 x 86: 1.97 -> 1.89 ms against 3 x 58 (cap 64)
 #endif
 
+static_assert(GF_BLOCKS_PER_CTA + 3 <= GF_FRAME_META, "per-frame tables of the frame kernel (k_frame.cu)");
+
 // balanced split of a note's hop blocks: as few CTAs as the cap allows, equal shares
 static inline int gf_blocks_per_cta(int n_blocks)
 {

@@ -16,6 +16,7 @@
 #ifndef GF_FRAME_CTAS
 #define GF_FRAME_CTAS 3                // resident CTAs per SM the register allocation aims at (65 KB of shared memory each)
 #endif
+#define GF_FRAME_META 96              // frames a CTA may touch: GF_BLOCKS_PER_CTA (api.cu, static_assert there) + 3 of halo
 #define GF_BLUR_K 12                  // reach of the edge correction of the time-domain blur (see gf_blur_edges)
 
 struct GfFrameSmem {
@@ -24,9 +25,11 @@ struct GfFrameSmem {
     float2 z[3][GF_RND][GF_FFT_BUF];          // [0] harmonic, [1] breath, [2] unvoiced (also the forward buffer)
     float edge[2][GF_RND][4];                 // voiced frames, harmonic / breath: Im X[0], Im X[1], Im X[512], Im X[511] before the blur
     float carry[3][3][GF_HOP];                // per stream: the three hop blocks still waiting for later frames
-    float f0fr[GF_RND];
-    int voiced[GF_RND];
-    int uvskip[GF_RND];                       // frame lies where the smoothed mask is exactly 1: aper_uv * (1 - mask) == 0
+    // per frame of the CTA (filled once in the prologue: the dependent global loads leave the per-round critical path)
+    float f0fr[GF_FRAME_META];
+    int voiced[GF_FRAME_META];
+    int uvskip[GF_FRAME_META];                // frame lies where the smoothed mask is exactly 1: aper_uv * (1 - mask) == 0
+    unsigned char dead[GF_FRAME_META];        // per owned hop block (b - b0): nobody reads the unvoiced stream there
     float red[GF_FRAME_THREADS / 32];
 };
 
@@ -132,11 +135,11 @@ __device__ __forceinline__ void gf_shape_mid(GfFrameSmem &sm, int f, float f0f, 
 // pushed back through the inverse of the blur (taps q1, q2 = differences of IDFT(1 / G), decaying 7.4 x per bin,
 // < 3e-9 at 12 bins) they become imaginary additions to bins 1..12 and 500..511 of the pre-blur spectrum.  In exact
 // arithmetic the result equals the reference's (checked in numpy to 2e-14); rounding differs at the 1e-7 level.
-__device__ __forceinline__ void gf_blur_edges(GfFrameSmem &sm, int nf, const float2 *__restrict__ tw1024)
+__device__ __forceinline__ void gf_blur_edges(GfFrameSmem &sm, int nf, const int *voiced, const float2 *__restrict__ tw1024)
 {
     const int tid = threadIdx.x;
     const int k = 1 + tid % GF_BLUR_K, rest = tid / GF_BLUR_K, s = rest & 1, f = rest >> 1;
-    if (f >= nf || !sm.voiced[f]) return;
+    if (f >= nf || !voiced[f]) return;
     const float *e = sm.edge[s][f];
     const float g0 = (float)d_tab.g05[0], g1 = (float)d_tab.g05[1];
     const float p1 = 2.0f * g0 * e[1] + g1 * e[0], p2 = g0 * e[0];
@@ -158,7 +161,7 @@ __device__ __forceinline__ void gf_blur_edges(GfFrameSmem &sm, int nf, const flo
 template <int NF>
 __device__ __forceinline__ void gf_ola_round(float (*carry)[GF_HOP], const float2 *bufs, const float *__restrict__ win,
                                              int t0, int T, int n_out, float *__restrict__ out, int b0, int nb, bool last,
-                                             bool no_input, const unsigned char *__restrict__ blk_dead, bool all_dead, float ws_full,
+                                             bool no_input, const unsigned char *blk_dead /* indexed by b - b0 */, bool all_dead, float ws_full,
                                              const int *voiced /* per frame: use the blur-carrying window winG; NULL: never */,
                                              float rcp_full /* RN(1 / ws_full), or 0 when the exact short division does not apply */)
 {
@@ -214,7 +217,7 @@ __device__ __forceinline__ void gf_ola_round(float (*carry)[GF_HOP], const float
             } else if (ws > 1e-9f) y = y / ws;             // (double) ws > 1e-9: RN_f32(1e-9) < 1e-9, so the f32 compare selects the same floats
             const int i = GF_HOP * (b - 2) + r;
             // blocks of the unvoiced stream that nobody reads (gain (1 - mask) * 0.75 == 0 on the whole block) are not stored
-            const bool dead = all_dead || (blk_dead && blk_dead[b - 2]);
+            const bool dead = all_dead || (blk_dead && blk_dead[b - b0]);
             if (i < n_out && !dead) out[i] = y;
         }
     }
@@ -252,6 +255,37 @@ gf_frame_kernel(const int4 *__restrict__ work, const GfPassDev *__restrict__ pas
         const float mx = __uint_as_float(scal[wk.x].submax_bits);
         sub_scale = ((double)mx > 1e-6) ? pl.subharm_weight / (double)mx : pl.subharm_weight;
     }
+    // global operands of a round -> L2, no registers held (every one of them is read exactly once, so the shaping loads
+    // would otherwise wait on HBM): envelope rows of frames tn .. tn+3 (65 lines each), the 513 phase rows (one 16-byte
+    // piece per row and round: the 128-byte line around it), the new excitation samples
+    auto prefetch_round = [&](int tn) {
+        auto pf = [](const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); };
+        if (tid < 66) pf(reinterpret_cast<const char *>(nd.envF + (size_t)tn * GF_ENVS_LD) + 128 * tid);
+        else if (tid < 132) pf(reinterpret_cast<const char *>(nd.envN + (size_t)tn * GF_ENVS_LD) + 128 * (tid - 66));
+        else if (tid < 148) {
+            const int i = min(n - 1, GF_HOP * tn + GF_NFFT / 2 - GF_HOP + 32 * (tid - 132));
+            if (i >= 0) pf(pulse + i);
+        }
+        pf(ps.phi + (size_t)tid * T + tn);
+        pf(ps.phi + (size_t)(tid + 256) * T + tn);
+        if (tid == 0) pf(ps.phi + (size_t)512 * T + tn);
+    };
+#ifndef GF_NO_PREFETCH
+    if (t_begin <= t_end) prefetch_round(t_begin);           // the first round's operands travel while the tables are staged
+#endif
+    for (int q = tid; q <= t_end - t_begin; q += blockDim.x) {
+        const int t = t_begin + q;
+        const int fi = min(t, n_f0 - 1) * GF_HOP;             // f0[::hop] edge-padded   GOOFER.py:1104-1106
+        sm.f0fr[q] = ps.f0[fi];
+        sm.voiced[q] = ps.mask_ones ? 1 : (vm[fi] > 0.0f);    // GOOFER.py:1132-1136
+        // samples of frame t live in hop blocks t-2 .. t+1 of the output
+        int one = 1;
+        const int nblk = (n + GF_HOP - 1) / GF_HOP;
+        for (int bb = t - 2; bb <= t + 1; ++bb)
+            if (bb >= 0 && bb < nblk) one &= (int)nd.ms_one[bb];
+        sm.uvskip[q] = ps.mask_ones ? 1 : one;                // sa pass: uv is multiplied by 0 (SillySampler.py:1156-1170)
+    }
+    for (int q = tid; q < nb; q += blockDim.x) sm.dead[q] = nd.ms_one[b0 + q - 2];
     float local_max = 0.0f;
     // win^2 sum of an interior hop block (frames b-3 .. b all exist), summed in ascending frame order like the general path
     float ws_full = 0.0f;
@@ -273,40 +307,16 @@ gf_frame_kernel(const int4 *__restrict__ work, const GfPassDev *__restrict__ pas
         } else {
             gf_load_frames(&sm.z[2][0][0], t0, nf, n, win, [&](int i) { return pulse[i]; });
         }
-        if (tid < nf) {
-            const int fi = min(t0 + tid, n_f0 - 1) * GF_HOP;      // f0[::hop] edge-padded   GOOFER.py:1104-1106
-            sm.f0fr[tid] = ps.f0[fi];
-            sm.voiced[tid] = ps.mask_ones ? 1 : (vm[fi] > 0.0f);  // GOOFER.py:1132-1136
-            // samples of frame t live in hop blocks t-2 .. t+1 of the output
-            int one = 1;
-            const int nblk = (n + GF_HOP - 1) / GF_HOP;
-            for (int bb = t0 + tid - 2; bb <= t0 + tid + 1; ++bb)
-                if (bb >= 0 && bb < nblk) one &= (int)nd.ms_one[bb];
-            sm.uvskip[tid] = ps.mask_ones ? 1 : one;          // sa pass: uv is multiplied by 0 (SillySampler.py:1156-1170)
-        }
         __syncthreads();
-        // ---- next round's global operands -> L2 (every one of them is read exactly once, so the shaping loads would
-        // otherwise wait on HBM): envelope rows of frames t0+4 .. t0+7 (65 lines each), the 513 phase rows (one 16-byte
-        // piece per row and round: the 128-byte line around it), the new excitation samples.  No registers held.
+        // ---- next round's global operands -> L2 ----
 #ifndef GF_NO_PREFETCH
-        if (t0 + GF_RND <= t_end) {
-            const int tn = t0 + GF_RND;
-            auto pf = [](const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); };
-            if (tid < 66) pf(reinterpret_cast<const char *>(nd.envF + (size_t)tn * GF_ENVS_LD) + 128 * tid);
-            else if (tid < 132) pf(reinterpret_cast<const char *>(nd.envN + (size_t)tn * GF_ENVS_LD) + 128 * (tid - 66));
-            else if (tid < 148) {
-                const int i = min(n - 1, GF_HOP * tn + GF_NFFT / 2 - GF_HOP + 32 * (tid - 132));
-                if (i >= 0) pf(pulse + i);
-            }
-            pf(ps.phi + (size_t)tid * T + tn);
-            pf(ps.phi + (size_t)(tid + 256) * T + tn);
-            if (tid == 0) pf(ps.phi + (size_t)512 * T + tn);
-        }
+        if (t0 + GF_RND <= t_end) prefetch_round(t0 + GF_RND);
 #endif
         // ---- 2. forward FFT ----
         gf_cta_fft512<false>(&sm.z[2][0][0], nf, sm.tw512);
+        const int m0r = t0 - t_begin;                         // this round's first entry of the per-frame tables
         bool uv_on = false;                                   // uniform: the round computes the unvoiced stream unless every frame may skip it
-        for (int q = 0; q < nf; ++q) uv_on = uv_on || (sm.uvskip[q] == 0);
+        for (int q = 0; q < nf; ++q) uv_on = uv_on || (sm.uvskip[m0r + q] == 0);
         // ---- 3. shaping, per bin pair (k, 512 - k); bin 256 pairs with itself and goes to threads 0..nf-1 ----
         if (nf == GF_RND) {
             // item m of this thread: k = (tid >> 2) + 64 m, frame f = tid & 3.  All global operands of the four
@@ -317,8 +327,8 @@ gf_frame_kernel(const int4 *__restrict__ work, const GfPassDev *__restrict__ pas
 #ifndef GF_SHAPE_BATCH
 #define GF_SHAPE_BATCH 2              // bin pairs whose global operands are requested together (6 loads each)
 #endif
-            const float f0f = sm.f0fr[f];
-            const bool vo = sm.voiced[f] != 0;
+            const float f0f = sm.f0fr[m0r + f];
+            const bool vo = sm.voiced[m0r + f] != 0;
 #pragma unroll
             for (int m0 = 0; m0 < 4; m0 += GF_SHAPE_BATCH) {
                 GfShapeIn in[GF_SHAPE_BATCH];
@@ -341,17 +351,17 @@ gf_frame_kernel(const int4 *__restrict__ work, const GfPassDev *__restrict__ pas
                 in.ef[0] = eF[k];  in.ef[1] = eF[km];
                 in.en[0] = eN[k];  in.en[1] = eN[km];
                 in.ph[0] = ph[(size_t)k * T];  in.ph[1] = ph[(size_t)km * T];
-                gf_shape_pair(sm, k, f, sm.f0fr[f], sm.voiced[f] != 0, uv_on, in, tw1024, local_max);
+                gf_shape_pair(sm, k, f, sm.f0fr[m0r + f], sm.voiced[m0r + f] != 0, uv_on, in, tw1024, local_max);
             }
         }
         if (tid < nf) {
             const int f = tid, t = t0 + f;
-            gf_shape_mid(sm, f, sm.f0fr[f], sm.voiced[f] != 0, uv_on, nd.envF[(size_t)t * GF_ENVS_LD + 256],
+            gf_shape_mid(sm, f, sm.f0fr[m0r + f], sm.voiced[m0r + f] != 0, uv_on, nd.envF[(size_t)t * GF_ENVS_LD + 256],
                          nd.envN[(size_t)t * GF_ENVS_LD + 256], ps.phi[(size_t)256 * T + t], tw1024, local_max);
         }
         __syncthreads();
         // ---- 4. voiced frames: edge terms of the brightness blur (the blur itself rides on the synthesis window) ----
-        gf_blur_edges(sm, nf, tw1024);
+        gf_blur_edges(sm, nf, sm.voiced + m0r, tw1024);
         __syncthreads();
         // ---- 5. inverse FFTs (stream-major: transform q = s * GF_RND + f) ----
         const int n_streams = uv_on ? 3 : 2;
@@ -367,16 +377,16 @@ gf_frame_kernel(const int4 *__restrict__ work, const GfPassDev *__restrict__ pas
             const bool last = (t0 + nf - 1 == T - 1);
             if (nf == GF_RND) {
 #pragma unroll
-                for (int s = 0; s < 3; ++s) gf_ola_round<GF_RND>(sm.carry[s], &sm.z[s][0][0], win, t0, T, n, outs[s], b0, nb, last, s == 2 && !uv_on, s == 2 ? nd.ms_one : nullptr, s == 2 && ps.mask_ones, ws_full, s < 2 ? sm.voiced : nullptr, rcp_full);
+                for (int s = 0; s < 3; ++s) gf_ola_round<GF_RND>(sm.carry[s], &sm.z[s][0][0], win, t0, T, n, outs[s], b0, nb, last, s == 2 && !uv_on, s == 2 ? sm.dead : nullptr, s == 2 && ps.mask_ones, ws_full, s < 2 ? sm.voiced + m0r : nullptr, rcp_full);
             } else if (nf == 3) {
 #pragma unroll
-                for (int s = 0; s < 3; ++s) gf_ola_round<3>(sm.carry[s], &sm.z[s][0][0], win, t0, T, n, outs[s], b0, nb, last, s == 2 && !uv_on, s == 2 ? nd.ms_one : nullptr, s == 2 && ps.mask_ones, ws_full, s < 2 ? sm.voiced : nullptr, rcp_full);
+                for (int s = 0; s < 3; ++s) gf_ola_round<3>(sm.carry[s], &sm.z[s][0][0], win, t0, T, n, outs[s], b0, nb, last, s == 2 && !uv_on, s == 2 ? sm.dead : nullptr, s == 2 && ps.mask_ones, ws_full, s < 2 ? sm.voiced + m0r : nullptr, rcp_full);
             } else if (nf == 2) {
 #pragma unroll
-                for (int s = 0; s < 3; ++s) gf_ola_round<2>(sm.carry[s], &sm.z[s][0][0], win, t0, T, n, outs[s], b0, nb, last, s == 2 && !uv_on, s == 2 ? nd.ms_one : nullptr, s == 2 && ps.mask_ones, ws_full, s < 2 ? sm.voiced : nullptr, rcp_full);
+                for (int s = 0; s < 3; ++s) gf_ola_round<2>(sm.carry[s], &sm.z[s][0][0], win, t0, T, n, outs[s], b0, nb, last, s == 2 && !uv_on, s == 2 ? sm.dead : nullptr, s == 2 && ps.mask_ones, ws_full, s < 2 ? sm.voiced + m0r : nullptr, rcp_full);
             } else {
 #pragma unroll
-                for (int s = 0; s < 3; ++s) gf_ola_round<1>(sm.carry[s], &sm.z[s][0][0], win, t0, T, n, outs[s], b0, nb, last, s == 2 && !uv_on, s == 2 ? nd.ms_one : nullptr, s == 2 && ps.mask_ones, ws_full, s < 2 ? sm.voiced : nullptr, rcp_full);
+                for (int s = 0; s < 3; ++s) gf_ola_round<1>(sm.carry[s], &sm.z[s][0][0], win, t0, T, n, outs[s], b0, nb, last, s == 2 && !uv_on, s == 2 ? sm.dead : nullptr, s == 2 && ps.mask_ones, ws_full, s < 2 ? sm.voiced + m0r : nullptr, rcp_full);
             }
         }
         __syncthreads();
