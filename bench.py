@@ -245,6 +245,17 @@ def run_native(args):
     launches_step = capi.last_stats()["kernel_launches"]
     prof = capi.profile_summary()
     capi.profile(False)
+    # The excitation chain runs on a side stream beside the envelope kernel (GOOFER_OVERLAP, default on): the spans of
+    # those kernels overlap in the timed region, while the frame kernel and everything after it run alone.  A second,
+    # untimed pass with both chains on one stream gives per-kernel durations that add up (the table of the line).
+    prof_serial = prof
+    if os.environ.get("GOOFER_OVERLAP", "1") != "0":
+        capi.profile(True, serial=True)
+        for _ in range(args.steps):
+            db.render()
+        torch.cuda.synchronize()
+        prof_serial = capi.profile_summary()
+        capi.profile(False)
 
     # ---- end to end through the host-buffer C-ABI call (pinned host memory) ----
     e2e = None
@@ -291,8 +302,10 @@ def run_native(args):
     if rank == 0:
         total_notes = n_notes * world * args.steps
         value = total_notes / (dev_ms * 1e-3)
-        top = max(prof.items(), key=lambda kv: kv[1][1]) if prof else (None, (0, 0.0))
-        tot_kernel_ms = sum(v[1] for v in prof.values()) or 1.0
+        top = max(prof_serial.items(), key=lambda kv: kv[1][1]) if prof_serial else (None, (0, 0.0))
+        forked = ("mask", "fir", "f0", "walk", "onset", "pulse", "tracks", "env", "phi")     # overlapping spans in the timed region
+        if top[0] in prof and not (top[0] in forked or top[0].startswith("sg")):
+            top = (top[0], prof[top[0]])                      # measured live in the timed region (runs alone there)
         peaks = {}
         try:
             with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as fh:
@@ -317,9 +330,12 @@ def run_native(args):
             roof = {"bound": "hbm", "kernel": top[0], "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
                     "traffic": traffic, "peak_source": peak_src, "kernel_ms_per_launch": per_launch_ms,
                     "algorithmic_bytes_per_launch": int(algo_per_launch), "launches_per_step": launches_per_step,
-                    "kernel_share_of_step": top[1][1] / tot_kernel_ms,
+                    "kernel_share_of_step": top[1][1] / dev_ms,
                     "step_algorithmic_gbs": algo_bytes * args.steps / (dev_ms * 1e-3) / 1e9,
-                    "kernels_ms_per_step": {k: round(v[1] / args.steps, 4) for k, v in prof.items()}}
+                    "kernels_ms_per_step": {k: round(v[1] / args.steps, 4) for k, v in prof_serial.items()},
+                    "kernels_note": "table: untimed pass with both preparation chains on one stream (durations add up); "
+                                    "in the timed region the excitation chain overlaps the envelope kernel on a side stream, "
+                                    "the roofline kernel runs alone and is timed there"}
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,

@@ -158,8 +158,9 @@ def last_stats() -> dict:
             "waves": int(s.waves)}
 
 
-def profile(enable: bool) -> None:
-    load().goofer_profile(1 if enable else 0)
+def profile(enable: bool, serial: bool = False) -> None:
+    """Per-kernel CUDA-event timing; serial=True also keeps both preparation chains on one stream (spans add up)."""
+    load().goofer_profile((2 if serial else 1) if enable else 0)
 
 
 def profile_summary() -> dict:

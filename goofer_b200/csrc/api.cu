@@ -62,6 +62,7 @@ static bool gf_debug_sync()
 // per-kernel device timing (goofer_profile): one CUDA event after every launch, on the launching stream
 struct GfProf {
     bool on = false;
+    bool serial = false;                                   // goofer_profile(2): both preparation chains on the caller's stream
     std::vector<cudaEvent_t> pool;
     std::vector<const char *> names;
     std::vector<cudaStream_t> streams;                     // the stream each mark was recorded on
@@ -87,6 +88,7 @@ static void gf_prof_mark(const char *name, cudaStream_t st)
 extern "C" void goofer_profile(int enable)
 {
     g_prof.on = enable != 0;
+    g_prof.serial = enable == 2;
     g_prof.used = 0;
 }
 
@@ -531,19 +533,21 @@ int gf_pitch_dyn(const WaveHost &wh, int n0, int n1, const GfNotePlan *d_plans, 
                  int max_n, cudaStream_t st, int64_t *launches);
 
 // The excitation chain (mask -> fir -> f0 -> walk -> pulse [-> growl]) and the envelope chain (tracks -> env) of a
-// wave are independent until the frame kernel.  With GOOFER_OVERLAP=1 the excitation chain runs on a library-owned
-// high-priority side stream, forked from and joined back into the caller's stream with events, beside the envelope
-// kernel.  OFF by default: measured on B200 (c2, 1,024 notes) the step takes 7.94 ms forked against 7.52 ms on one
-// stream -- the envelope kernel fills the register file at two CTAs per SM, so the two chains do not co-reside,
-// they only take turns, and each runs slower for it (env 1.93 -> 4.3 ms span, walk 0.66 -> 0.82 ms).
+// wave are independent until the frame kernel.  The excitation chain runs on a library-owned high-priority side
+// stream, forked from and joined back into the caller's stream with events, beside the envelope kernel
+// (GOOFER_OVERLAP=0: everything on the caller's stream).  The two chains mostly take turns -- the envelope kernel
+// fills the register file at three CTAs per SM -- but the tails of the low-occupancy kernels (walk: two warps per
+// note) no longer leave SMs idle.  Measured on B200, forked against one stream: c1 3.74 / 3.89 ms, c2 4.80 / 4.90 ms,
+// c3 11.43 / 11.52 ms, c4 (96 x 16 s, long walk chains) 6.05 / 6.68 ms.  (With the first versions of the kernels the
+// fork lost, 7.94 against 7.52 ms; it was re-measured after they had been tightened.)
 struct GfSide { cudaStream_t sx = nullptr; cudaEvent_t fork = nullptr, join = nullptr; int dev = -1; };
 static thread_local GfSide g_side;
 
 static bool gf_overlap_on()
 {
     static int v = -1;
-    if (v < 0) { const char *e = getenv("GOOFER_OVERLAP"); v = (e && e[0] == '1') ? 1 : 0; }
-    return v == 1 && !gf_debug_sync();
+    if (v < 0) { const char *e = getenv("GOOFER_OVERLAP"); v = (e && e[0] == '0') ? 0 : 1; }
+    return v == 1 && !gf_debug_sync() && !(g_prof.on && g_prof.serial);
 }
 
 static cudaStream_t gf_side_stream()
@@ -677,7 +681,7 @@ static int gf_render_wave(const GooferBatch *b, const std::vector<GfNotePlan> &a
     GF_CUDA(cudaMemsetAsync(d_nscal, 0, scal_span, st));
 
     int64_t &L = g_stats.kernel_launches;
-    // ---- excitation chain on the side stream (sx == st when overlap is off) ----
+    // ---- excitation chain on the side stream (sx == st with GOOFER_OVERLAP=0) ----
     cudaStream_t sx = gf_overlap_on() ? gf_side_stream() : nullptr;
     const bool forked = sx != nullptr;
     if (forked) {

@@ -386,6 +386,11 @@ gf_env_kernel(const int2 *__restrict__ work, const GfNotePlan *__restrict__ plan
     const int t = (tile0 + it) * GF_FT + warp;
     if (t >= pl.T_out) break;                             // warp-uniform; no CTA-wide barrier below
     const int te = min(t, pl.T_env - 1);                  // GOOFER.py:1115-1119 trim / edge-pad to the STFT grid
+    // the frame's formant tracks (fst bells: lanes 0-3, F1-F4 warp: lanes 4-7) are requested now and handed round by
+    // shuffle where they are used: one register instead of eight dependent loads in the middle of the frame
+    float trk = 0.0f;
+    if (lane < 4) { if (pl.any_fst && !(fabs(pl.fst[lane]) < 1e-6)) trk = nd.trk_clean[(size_t)lane * pl.T_env + te]; }
+    else if (lane < 8) { if (pl.any_F_shift) trk = nd.trk_canon[(size_t)(lane - 4) * pl.T_env + te]; }
     if (it > 0) {
         gf_env_mix(pl, te, mix);
         const float *src0 = sc.envS + (size_t)gf_src_frame(pl, mix.f[0]) * GF_ENVS_LD;
@@ -463,8 +468,9 @@ gf_env_kernel(const int2 *__restrict__ work, const GfNotePlan *__restrict__ plan
             const double sk = pl.fst[k];
             float fk = 0.0f;
             bool on = !(fabs(sk) < 1e-6);
+            const float fk_pf = __shfl_sync(0xffffffffu, trk, k);   // requested at the top of the frame
             if (on) {
-                fk = nd.trk_clean[(size_t)k * pl.T_env + te];
+                fk = fk_pf;
                 on = isfinite(fk) && (fk > 50.0f) && ((double)fk < (double)sr * 0.5);
             }
             Fk[k] = fk;
@@ -541,7 +547,7 @@ gf_env_kernel(const int2 *__restrict__ work, const GfNotePlan *__restrict__ plan
         int nk = 1;
         if (lane == 0) { kx[0] = 0.0; kx[6] = 0.0; }
         for (int k = 0; k < 4; ++k) {
-            const double fo = (double)nd.trk_canon[(size_t)k * pl.T_env + te];
+            const double fo = (double)__shfl_sync(0xffffffffu, trk, 4 + k);
             const double fs = fo * pl.F_shift[k];
             if (fo > 50.0 && fo < nyq && fs > 50.0) {         // warp-uniform
                 if (lane == 0) { kx[nk] = fs; kx[6 + nk] = fo; }

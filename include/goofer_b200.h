@@ -193,7 +193,10 @@ void goofer_last_stats(GooferStats *s);
 /* Per-kernel device timing for bench.py's roofline line: after goofer_profile(1) every kernel launch of
  * goofer_render_batch on this thread is followed by a CUDA event on the launching stream;
  * goofer_profile_summary() waits for the last one and returns "kernel:launches:total_ms;..." accumulated
- * since the enable call (thread-local storage, valid until the next call). */
+ * since the enable call (thread-local storage, valid until the next call).  The excitation chain normally runs on a
+ * side stream beside the envelope kernel, so the spans of those kernels overlap in time (the frame kernel and what
+ * follows it run alone); goofer_profile(2) keeps everything on the caller's stream while it is on, for per-kernel
+ * durations that add up.  GOOFER_OVERLAP=0 in the environment does the same for the whole process. */
 void goofer_profile(int enable);
 const char *goofer_profile_summary(void);
 
