@@ -483,6 +483,7 @@ static int gf_meta_copy(void *dst, const void *stage, size_t bytes, cudaStream_t
     const size_t n16 = (bytes + 15) / 16;            // both sides are 256-byte aligned and padded
     const int blocks = (int)std::min<size_t>((n16 + 255) / 256, 148);
     gf_meta_copy_kernel<<<blocks, 256, 0, st>>>((uint4 *)dst, (const uint4 *)stage, n16);
+    ++g_stats.kernel_launches;
     GF_CUDA(cudaGetLastError());
     return GOOFER_OK;
 }
@@ -699,10 +700,10 @@ static int gf_render_wave(const GooferBatch *b, const std::vector<GfNotePlan> &a
                 max_sigma = std::max(max_sigma, j.sigma);
                 ((!j.in_f64 && !j.maxabs && !j.in_cast_f32) ? any32 : any64) = true;
             }
-            gf_launch_fir(d_fir, (int)wh.fir.size(), max_n, max_sigma, st, any64, any32); ++L; GF_STEP("fir");
+            gf_launch_fir(d_fir, (int)wh.fir.size(), max_n, max_sigma, st, any64, any32); L += (int)any64 + (int)any32; GF_STEP("fir");
         }
         gf_launch_f0(d_plans, d_notes, d_passes, d_srcs, b->bend_cents, b->normals, b->f0_curves, nn, max_n, st); ++L; GF_STEP("f0");
-        gf_launch_walk(d_passes, d_scal, (int)n_pass, max_n, sr, st); ++L; GF_STEP("walk");
+        gf_launch_walk(d_passes, d_scal, (int)n_pass, max_n, sr, st); L += 2; GF_STEP("walk");     // walk + onset kernels
         gf_launch_pulse(d_passes, d_scal, (int)n_pass, max_n, st); ++L; GF_STEP("pulse");
         if ((rc = gf_growl(wh, d_plans, d_notes, d_passes, d_scal, bp, max_n, st, &L)) != GOOFER_OK) return rc;
     }
