@@ -213,7 +213,11 @@ def run_native(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        os.environ["NCCL_DEBUG"] = os.environ.get("GOOFER_NCCL_DEBUG", "WARN")      # keep stdout to the one JSON line
+        # keep stdout to the one JSON line: NCCL prints its version banner to stdout at the VERSION and WARN levels
+        if "GOOFER_NCCL_DEBUG" in os.environ:
+            os.environ["NCCL_DEBUG"] = os.environ["GOOFER_NCCL_DEBUG"]
+        else:
+            os.environ.pop("NCCL_DEBUG", None)
         dist.init_process_group("nccl", device_id=dev)
     capi.load()
 
