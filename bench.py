@@ -210,6 +210,8 @@ def run_native(args):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: goofer_b200 has no CPU fallback")
+    from goofer_b200 import shard
+    numa = shard.bind_rank_to_gpu_numa(local)                 # before any pinned allocation: host buffers on the GPU's node
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
@@ -300,7 +302,11 @@ def run_native(args):
     clocks.stop_flag = True
 
     t = torch.tensor([dev_ms, e2e[0] if e2e else 0.0], dtype=torch.float64, device=dev)
+    e2e_by_rank = [float(t[1])]
     if world > 1:
+        every = [torch.zeros_like(t) for _ in range(world)]
+        dist.all_gather(every, t)
+        e2e_by_rank = [float(x[1]) for x in every]
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     dev_ms, e2e_ms = float(t[0]), float(t[1])
     if rank == 0:
@@ -351,6 +357,8 @@ def run_native(args):
             line["e2e"] = {"value": n_notes * world * args.steps / (e2e_ms * 1e-3), "unit": UNIT,
                            "h2d_bytes_per_step": int(e2e[1]), "d2h_bytes_per_step": int(e2e[2]),
                            "ms_per_step": e2e_ms / args.steps,
+                           "ms_per_step_by_rank": [round(x / args.steps, 3) for x in e2e_by_rank],
+                           "host_numa_binding_rank0": numa,
                            "api": "goofer_render_batch_host (C ABI, pinned host buffers, per-rank wall clock, max over ranks)",
                            "pcm16_output": {"value": n_notes * args.steps / (e2e_pcm[0] * 1e-3), "unit": UNIT + " (rank 0)",
                                             "ms_per_step": e2e_pcm[0] / args.steps, "d2h_bytes_per_step": int(e2e_pcm[1])},
@@ -358,7 +366,7 @@ def run_native(args):
                                                    "ms_per_step": e2e_dn[0] / args.steps, "h2d_bytes_per_step": int(e2e_dn[1]),
                                                    "d2h_bytes_per_step": int(e2e_dn[2]),
                                                    "note": "same notes, same noise: PCG64 states instead of phase buffers"}}
-        if args.cpu_sample > 0 and world >= 1:
+        if args.cpu_sample > 0 and world == 1:               # the CPU leg is timed at N = 1 only (rank 0)
             line["cpu_baseline"] = cpu_baseline_1core(args.workload, args.cpu_sample)
         print(json.dumps(line), flush=True)
     if world > 1:

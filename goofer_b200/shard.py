@@ -53,3 +53,53 @@ def gather_outputs(local_indices: Sequence[int], local_outputs: Sequence, group=
     for p in parts:
         out.update(p)
     return out
+
+
+def _parse_cpulist(txt: str) -> set:
+    cpus = set()
+    for part in txt.strip().split(","):
+        if not part:
+            continue
+        lo, _, hi = part.partition("-")
+        cpus.update(range(int(lo), int(hi or lo) + 1))
+    return cpus
+
+
+def bind_rank_to_gpu_numa(local_rank: int) -> dict:
+    """Pin the calling process to the CPUs of the NUMA node its GPU hangs off, BEFORE it allocates page-locked buffers.
+
+    One process per GPU renders its own shard and, through `goofer_render_batch_host`, streams hundreds of MB per call
+    between pinned host memory and its GPU.  Linux places pinned pages on the node of the allocating thread, so an
+    unbound rank may end up with its buffers on the other socket and every DMA crossing the inter-socket link -- with
+    eight ranks that link, not PCIe, bounds the end-to-end rate.  Returns what was done (for the bench line); never
+    raises: no NVML / sysfs / permission => {"bound": False, ...}.  `GOOFER_NUMA_BIND=0` disables it."""
+    import os
+    out = {"bound": False}
+    if os.environ.get("GOOFER_NUMA_BIND", "1") == "0" or not hasattr(os, "sched_setaffinity"):
+        out["why"] = "disabled"
+        return out
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(local_rank)
+        bus = pynvml.nvmlDeviceGetPciInfo(h).busId
+        bus = bus.decode() if isinstance(bus, bytes) else bus
+        dom, rest = bus.lower().split(":", 1)
+        sysfs = f"/sys/bus/pci/devices/{dom[-4:]}:{rest}/numa_node"
+        with open(sysfs) as fh:
+            node = int(fh.read().strip())
+        out["node"] = node
+        if node < 0:
+            out["why"] = "no NUMA node reported for the GPU"
+            return out
+        with open(f"/sys/devices/system/node/node{node}/cpulist") as fh:
+            cpus = _parse_cpulist(fh.read())
+        allowed = os.sched_getaffinity(0) & cpus
+        if not allowed:
+            out["why"] = "none of the node's CPUs is in this process's cpuset"
+            return out
+        os.sched_setaffinity(0, allowed)
+        out.update(bound=True, cpus=len(allowed))
+    except Exception as ex:  # noqa: BLE001 -- a launch nicety, never fatal
+        out["why"] = f"{type(ex).__name__}: {ex}"
+    return out

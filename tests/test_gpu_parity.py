@@ -200,6 +200,14 @@ def test_batch_invariance_determinism_and_waves(torch_cuda):
     b2 = db.render().clone()
     assert torch.equal(a, b2)
     full = db.outputs()
+    # the side-stream fork of the excitation chain (default) against everything on the caller's stream (goofer_profile(2))
+    capi.profile(True, serial=True)
+    c = db.render().clone()
+    torch.cuda.synchronize()
+    prof = capi.profile_summary()
+    capi.profile(False)
+    assert torch.equal(a, c)
+    assert {"env", "frame", "walk", "mix"} <= set(prof) and all(ms > 0 for _, ms in prof.values())
     # several waves: a workspace that only fits a few notes at a time
     lib = capi.load()
     small = int(lib.goofer_workspace_bytes(C.byref(db.desc), 4))

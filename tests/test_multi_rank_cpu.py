@@ -58,3 +58,17 @@ def test_two_rank_sharding_and_gather():
     assert max(loads) / max(1, min(loads)) < 1.5            # cost-balanced: full-flag notes cost up to 4x
     cover = sorted(i for r in res for i in r[3])
     assert cover == list(range(11))
+
+
+def test_numa_binding_helper_never_raises(monkeypatch):
+    """shard.bind_rank_to_gpu_numa is a launch nicety: without NVML / a GPU it reports why and leaves the affinity alone."""
+    import os
+    from goofer_b200 import shard
+    assert shard._parse_cpulist("0-3,8,10-11\n") == {0, 1, 2, 3, 8, 10, 11}
+    assert shard._parse_cpulist("") == set()
+    before = os.sched_getaffinity(0)
+    r = shard.bind_rank_to_gpu_numa(0)
+    assert r["bound"] is False and "why" in r
+    assert os.sched_getaffinity(0) == before
+    monkeypatch.setenv("GOOFER_NUMA_BIND", "0")
+    assert shard.bind_rank_to_gpu_numa(0) == {"bound": False, "why": "disabled"}
