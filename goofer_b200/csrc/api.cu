@@ -559,7 +559,9 @@ static cudaStream_t gf_side_stream()
     if (g_side.sx) { cudaStreamDestroy(g_side.sx); cudaEventDestroy(g_side.fork); cudaEventDestroy(g_side.join); g_side = GfSide(); }
     int lo = 0, hi = 0;
     cudaDeviceGetStreamPriorityRange(&lo, &hi);            // hi = greatest priority (numerically lowest)
-    if (cudaStreamCreateWithPriority(&g_side.sx, cudaStreamNonBlocking, hi) != cudaSuccess) { g_side.sx = nullptr; return nullptr; }
+    const char *pe = getenv("GOOFER_SIDE_PRIORITY");          // "low": the side stream yields to the caller's stream (tuning knob)
+    const int prio = (pe && pe[0] == 'l') ? lo : hi;
+    if (cudaStreamCreateWithPriority(&g_side.sx, cudaStreamNonBlocking, prio) != cudaSuccess) { g_side.sx = nullptr; return nullptr; }
     if (cudaEventCreateWithFlags(&g_side.fork, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&g_side.join, cudaEventDisableTiming) != cudaSuccess) {
         cudaStreamDestroy(g_side.sx); g_side = GfSide(); return nullptr;
