@@ -86,7 +86,7 @@ EXPORTS = [
     "goofer_render_batch_host", "goofer_host_release", "goofer_last_stats", "goofer_stft_batch", "goofer_istft_batch",
     "goofer_pulse_work_bytes", "goofer_pulse_train_batch", "goofer_onepole_batch", "goofer_debug_plan",
     "goofer_profile", "goofer_profile_summary", "goofer_struct_size",
-    "goofer_analyse_work_bytes", "goofer_analyse_batch",
+    "goofer_analyse_work_bytes", "goofer_analyse_batch", "goofer_render_status",
 ]
 
 
@@ -114,6 +114,8 @@ def load():
     L.goofer_render_batch.argtypes = [C.POINTER(GooferBatch), vp, sz, vp]
     L.goofer_render_batch_host.restype = C.c_int
     L.goofer_render_batch_host.argtypes = [C.POINTER(GooferBatch)]
+    L.goofer_render_status.restype = C.c_int
+    L.goofer_render_status.argtypes = [vp, vp, C.POINTER(C.c_int32)]
     L.goofer_host_release.restype = None
     L.goofer_last_stats.restype = None
     L.goofer_last_stats.argtypes = [C.POINTER(GooferStats)]

@@ -11,6 +11,7 @@
 #include <string>
 #include <mutex>
 #include <algorithm>
+#include <functional>
 
 #include "gf_internal.h"
 #include "gf_kernels.h"
@@ -170,15 +171,21 @@ static void gf_gauss_taps(double *dst, double sigma)
 static std::mutex g_tab_mutex;
 static int g_tab_sr[64] = {0};
 
+// sr <= 0: any table will do (the STFT / iSTFT stage calls use only the sr-independent members); 44,100 is loaded when
+// the device has none yet.  Replacing a table of another rate first waits for the device: kernels of an earlier
+// asynchronous call on a non-blocking stream may still be reading d_tab (the copy below is synchronous only with
+// respect to the null stream).
 int gf_tables_init(int sr)
 {
     int dev = 0;
     if (cudaGetDevice(&dev) != cudaSuccess) { gf_set_error("no CUDA device: %s", cudaGetErrorString(cudaGetLastError())); return GOOFER_ERR_CUDA; }
     std::lock_guard<std::mutex> lk(g_tab_mutex);
-    if (dev < 64 && g_tab_sr[dev] == sr) return 0;
+    if (dev < 64 && g_tab_sr[dev] != 0 && (sr <= 0 || g_tab_sr[dev] == sr)) return 0;
+    if (sr <= 0) sr = 44100;
+    if (dev < 64 && g_tab_sr[dev] != 0) cudaDeviceSynchronize();
     GfTables *t = new GfTables();
     const double PI = 3.141592653589793238462643383279502884;
-    for (int m = 0; m < 512; ++m) t->tw512[m] = make_float2((float)std::cos(-2.0 * PI * m / 512.0), (float)std::sin(-2.0 * PI * m / 512.0));
+    gf_twl_fill(t->twl);
     for (int k = 0; k <= 512; ++k) t->tw1024[k] = make_float2((float)std::cos(-2.0 * PI * k / 1024.0), (float)std::sin(-2.0 * PI * k / 1024.0));
     for (int i = 0; i < 1024; ++i) {
         // np.hanning(M): 0.5 + 0.5 cos(pi n / (M - 1)), n = 1 - M, 3 - M, ... ; cast f32, then sqrt in f32
@@ -353,14 +360,12 @@ static void gf_note_work_counts(const GfNotePlan &p, size_t *n_env, size_t *n_fr
 // CTA slots of the frame kernel on this device (resident CTAs per SM x SMs)
 static int gf_frame_slots()
 {
-    static int slots = 0;
-    if (slots == 0) {
-        int dev = 0, sms = 0;
-        if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && sms > 0)
-            slots = sms * GF_FRAME_CTAS;
-        else slots = 148 * GF_FRAME_CTAS;
-    }
-    return slots;
+    static int slots[GF_MAX_DEVICES] = {0};                  // per device: one process may drive several GPUs
+    int dev = 0, sms = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= GF_MAX_DEVICES) return 148 * GF_FRAME_CTAS;
+    if (slots[dev] == 0)
+        slots[dev] = (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && sms > 0 ? sms : 148) * GF_FRAME_CTAS;
+    return slots[dev];
 }
 
 // Tail of a frame-kernel launch.  The notes [a, e) of one launch are cut into `fparts[i]` CTAs per pass; the CTAs run
@@ -411,11 +416,18 @@ static int gf_make_plans(const GooferBatch *b, std::vector<GfNotePlan> &plans)
     return GOOFER_OK;
 }
 
+static size_t gf_workspace_bytes_planned(const GooferBatch *b, const std::vector<GfNotePlan> &plans, int32_t notes_per_wave);
+
 extern "C" size_t goofer_workspace_bytes(const GooferBatch *b, int32_t notes_per_wave)
 {
     if (gf_validate(b) != GOOFER_OK) return 0;
     std::vector<GfNotePlan> plans;
     if (gf_make_plans(b, plans) != GOOFER_OK) return 0;
+    return gf_workspace_bytes_planned(b, plans, notes_per_wave);
+}
+
+static size_t gf_workspace_bytes_planned(const GooferBatch *b, const std::vector<GfNotePlan> &plans, int32_t notes_per_wave)
+{
     if (notes_per_wave <= 0) notes_per_wave = 2048;
     size_t best = 0;
     for (int i0 = 0; i0 < b->n_notes; i0 += notes_per_wave) {
@@ -430,7 +442,7 @@ extern "C" size_t goofer_workspace_bytes(const GooferBatch *b, int32_t notes_per
         tot += gf_wave_meta_bytes(i1 - i0, np, ne, nf, nfir);
         best = std::max(best, tot);
     }
-    return gf_sources_bytes(b) + best + 4096;
+    return gf_sources_bytes(b) + best + 4096 + 512;          // + the status word at the head of the workspace
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -448,12 +460,20 @@ struct WaveHost {
 
 // Metadata (plans, records, work lists, job lists) is staged in a thread-local page-locked arena so that
 // the uploads are truly asynchronous: a pageable source would make cudaMemcpyAsync wait for the stream.
-struct GfPinned { char *base = nullptr; size_t cap = 0, off = 0; };
+struct GfPinned { char *base = nullptr; size_t cap = 0, off = 0; int dev = -1; };
 static thread_local GfPinned g_pin;
 
 static void *gf_pin_take(size_t bytes)
 {
     bytes = (bytes + 255) & ~(size_t)255;
+    int dev = -1;
+    cudaGetDevice(&dev);
+    if (g_pin.dev != dev) {
+        // the thread moved to another GPU: what the previous device still reads from the arena must complete first
+        if (g_pin.dev >= 0 && g_pin.off > 0) { cudaSetDevice(g_pin.dev); cudaDeviceSynchronize(); cudaSetDevice(dev); }
+        g_pin.off = 0;
+        g_pin.dev = dev;
+    }
     if (g_pin.off + bytes > g_pin.cap) {
         // wrap (or grow): every copy that read the arena must have completed
         cudaDeviceSynchronize();
@@ -574,8 +594,23 @@ static cudaStream_t gf_side_stream()
 // the frame kernel of the part waits for `phi_ready`, `done` is recorded after the part's mix kernel.
 struct GfPart { int note_end; cudaEvent_t phi_ready; cudaEvent_t done; };
 
+// Render status word at the head of the workspace: {code, first offending note}.  A pulse-onset or growl-event list that
+// overflows its capacity (mean f0 above sr / 8: beyond any MIDI pitch, but a caller-supplied f0 curve can do it) is
+// flagged per pass by the walk kernels (GfPassScal.err); one tiny kernel per wave folds those flags into the status
+// word, which goofer_render_batch_host checks after its final synchronisation and goofer_render_status() exposes to
+// callers of the asynchronous device entry point.
+__global__ void __launch_bounds__(256) gf_err_scan_kernel(const GfPassScal *__restrict__ scal, const GfPassDev *__restrict__ passes, int n_pass,
+                                                           int note0, int *status)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_pass) return;
+    const int e = scal[i].err;
+    if (e) { atomicOr(&status[0], e); atomicMin(&status[1], note0 + passes[i].note); }
+}
+
 static int gf_render_wave(const GooferBatch *b, const std::vector<GfNotePlan> &all, int i0, int i1, const GfSourceDev *d_srcs,
-                          Bump bp /* by value: wave region restarts every wave */, cudaStream_t st, const GfPart *parts, int n_parts)
+                          Bump bp /* by value: wave region restarts every wave */, cudaStream_t st, const GfPart *parts, int n_parts,
+                          int *d_status, std::function<int()> *sources_first /* run once, after the first wave's phase generator */)
 {
     WaveHost wh;
     const int nn = i1 - i0;
@@ -684,6 +719,32 @@ static int gf_render_wave(const GooferBatch *b, const std::vector<GfNotePlan> &a
     GF_CUDA(cudaMemsetAsync(d_nscal, 0, scal_span, st));
 
     int64_t &L = g_stats.kernel_launches;
+    // ---- noise phases drawn on the device (GooferNote.phi_rng): needs nothing but the job list, so it goes first and
+    // overlaps the arrival of the source arrays over PCIe (host entry point) ----
+    {
+        std::vector<GfPhiJob> pj;
+        int max_total = 0;
+        for (size_t q = 0; q < wh.passes.size(); ++q) {
+            const GfPassDev &pd = wh.passes[q];
+            if (!pd.phi_gen) continue;
+            const GfNotePlan &p = wh.plans[pd.note];
+            GfPhiJob j;
+            j.dst = pd.phi_gen; j.total = GF_NBINS * p.T_out; j.pad = 0;
+            j.s_hi = p.phi_rng[pd.kind][0]; j.s_lo = p.phi_rng[pd.kind][1]; j.i_hi = p.phi_rng[pd.kind][2]; j.i_lo = p.phi_rng[pd.kind][3];
+            max_total = std::max(max_total, j.total);
+            pj.push_back(j);
+        }
+        if (!pj.empty()) {
+            GfPhiJob *d_pj;
+            if ((rc = gf_upload(bp, pj, &d_pj, st)) != GOOFER_OK) return rc;
+            if (bp.off > bp.cap) { gf_set_error("internal: phase jobs overflow the workspace"); return GOOFER_ERR_WORKSPACE; }
+            gf_launch_phi(d_pj, (int)pj.size(), max_total, st); ++L; GF_STEP("phi");
+        }
+    }
+    if (sources_first && *sources_first) {
+        if ((rc = (*sources_first)()) != GOOFER_OK) return rc;
+        *sources_first = nullptr;
+    }
     // ---- excitation chain on the side stream (sx == st with GOOFER_OVERLAP=0) ----
     cudaStream_t sx = gf_overlap_on() ? gf_side_stream() : nullptr;
     const bool forked = sx != nullptr;
@@ -708,27 +769,6 @@ static int gf_render_wave(const GooferBatch *b, const std::vector<GfNotePlan> &a
         gf_launch_walk(d_passes, d_scal, (int)n_pass, max_n, sr, st); L += 2; GF_STEP("walk");     // walk + onset kernels
         gf_launch_pulse(d_passes, d_scal, (int)n_pass, max_n, st); ++L; GF_STEP("pulse");
         if ((rc = gf_growl(wh, d_plans, d_notes, d_passes, d_scal, bp, max_n, st, &L)) != GOOFER_OK) return rc;
-    }
-    // ---- noise phases drawn on the device (GooferNote.phi_rng) ----
-    {
-        std::vector<GfPhiJob> pj;
-        int max_total = 0;
-        for (size_t q = 0; q < wh.passes.size(); ++q) {
-            const GfPassDev &pd = wh.passes[q];
-            if (!pd.phi_gen) continue;
-            const GfNotePlan &p = wh.plans[pd.note];
-            GfPhiJob j;
-            j.dst = pd.phi_gen; j.total = GF_NBINS * p.T_out; j.pad = 0;
-            j.s_hi = p.phi_rng[pd.kind][0]; j.s_lo = p.phi_rng[pd.kind][1]; j.i_hi = p.phi_rng[pd.kind][2]; j.i_lo = p.phi_rng[pd.kind][3];
-            max_total = std::max(max_total, j.total);
-            pj.push_back(j);
-        }
-        if (!pj.empty()) {
-            GfPhiJob *d_pj;
-            if ((rc = gf_upload(bp, pj, &d_pj, st)) != GOOFER_OK) return rc;
-            if (bp.off > bp.cap) { gf_set_error("internal: phase jobs overflow the workspace"); return GOOFER_ERR_WORKSPACE; }
-            gf_launch_phi(d_pj, (int)pj.size(), max_total, st); ++L; GF_STEP("phi");
-        }
     }
     // ---- envelope chain on the caller's stream ----
     gf_launch_tracks(d_plans, d_notes, d_srcs, nn, st); ++L; GF_STEP("tracks");
@@ -776,28 +816,35 @@ static int gf_render_wave(const GooferBatch *b, const std::vector<GfNotePlan> &a
             if (pp[k].done && pp[k].note_end <= i1) GF_CUDA(cudaEventRecord(pp[k].done, st));
         }
     }
+    gf_err_scan_kernel<<<(int)((n_pass + 255) / 256), 256, 0, st>>>(d_scal, d_passes, (int)n_pass, i0, d_status); ++L;
     GF_CUDA(cudaGetLastError());
     ++g_stats.waves;
     return GOOFER_OK;
 }
 
-static int gf_render_batch_ex(const GooferBatch *b, void *workspace, size_t workspace_bytes, void *stream, const GfPart *parts, int n_parts);
+static int gf_render_batch_ex(const GooferBatch *b, void *workspace, size_t workspace_bytes, void *stream, const GfPart *parts, int n_parts,
+                              const std::vector<GfNotePlan> *planned = nullptr, cudaEvent_t src_ready = nullptr);
 
 extern "C" int goofer_render_batch(const GooferBatch *b, void *workspace, size_t workspace_bytes, void *stream)
 {
     return gf_render_batch_ex(b, workspace, workspace_bytes, stream, nullptr, 0);
 }
 
-// parts (optional): see GfPart; only the frame kernels wait for the noise phases
-static int gf_render_batch_ex(const GooferBatch *b, void *workspace, size_t workspace_bytes, void *stream, const GfPart *parts, int n_parts)
+// parts (optional): see GfPart; only the frame kernels wait for the noise phases.  planned (optional): the plans of
+// b's notes when the caller made them already (the host entry point plans once for sizing and rendering: 0.17 ms per
+// 1,024 notes each time).  src_ready (optional): event after which the source arrays / bends / normals are in device
+// memory -- the first kernels that read them wait for it, the noise-phase generator of the first wave runs before.
+static int gf_render_batch_ex(const GooferBatch *b, void *workspace, size_t workspace_bytes, void *stream, const GfPart *parts, int n_parts,
+                              const std::vector<GfNotePlan> *planned, cudaEvent_t src_ready)
 {
     int rc = gf_validate(b);
     if (rc != GOOFER_OK) return rc;
     g_stats.kernel_launches = 0; g_stats.waves = 0;
     if (b->n_notes == 0) return GOOFER_OK;
     if (!workspace || (!b->out && !b->out_pcm16) || !b->bend_cents) { gf_set_error("NULL workspace / out (and out_pcm16) / bend_cents"); return GOOFER_ERR_INVALID; }
-    std::vector<GfNotePlan> plans;
-    if ((rc = gf_make_plans(b, plans)) != GOOFER_OK) return rc;
+    std::vector<GfNotePlan> own_plans;
+    if (!planned && (rc = gf_make_plans(b, own_plans)) != GOOFER_OK) return rc;
+    const std::vector<GfNotePlan> &plans = planned ? *planned : own_plans;
     for (int i = 0; i < b->n_notes; ++i) {
         const GfNotePlan &p = plans[i];
         for (int k = 0; k < p.n_passes; ++k) {
@@ -822,6 +869,15 @@ static int gf_render_batch_ex(const GooferBatch *b, void *workspace, size_t work
     gf_prof_mark("begin", st);
 
     Bump bp{(char *)workspace, workspace_bytes, 0};
+    int *d_status = bp.arr<int>(64);                          // render status word (gf_err_scan_kernel): first thing in the workspace
+    if (workspace_bytes < 512) { gf_set_error("workspace too small"); return GOOFER_ERR_WORKSPACE; }
+    {
+        static const int init[2] = {0, 0x7fffffff};
+        int *stage = (int *)gf_pin_take(sizeof(init));
+        if (!stage) { gf_set_error("cudaMallocHost failed for the metadata staging arena"); return GOOFER_ERR_CUDA; }
+        std::memcpy(stage, init, sizeof(init));
+        if ((rc = gf_meta_copy(d_status, stage, sizeof(init), st)) != GOOFER_OK) return rc;
+    }
     // ---- sources: decode / transpose once per call ----
     std::vector<GfSourceDev> srcs(b->n_sources);
     int max_T = 0;
@@ -834,21 +890,34 @@ static int gf_render_batch_ex(const GooferBatch *b, void *workspace, size_t work
         for (int k = 0; k < 4; ++k) { d.formants[k] = g.formants[k]; d.formant_len[k] = g.formants[k] ? g.formant_len[k] : 0; }
         if (g.T > 0) {
             if (!d.knots && !d.dense) { gf_set_error("source %d has neither knots nor a dense envelope", s); return GOOFER_ERR_INVALID; }
-            if (d.knots && (g.K < 2 || !g.hz_knots)) { gf_set_error("source %d: knots need K >= 2 and hz_knots", s); return GOOFER_ERR_INVALID; }
+            if (d.knots && (g.K < 2 || g.K > 4096 || !g.hz_knots)) { gf_set_error("source %d: knots need 2 <= K <= 4096 and hz_knots", s); return GOOFER_ERR_INVALID; }
             d.envS = bp.arr<float>((size_t)g.T * GF_ENVS_LD);
             max_T = std::max(max_T, g.T);
         }
+        if (g.N < 0 || (g.N > 0 && !g.mask)) { gf_set_error("source %d: NULL voicing mask (N = %d)", s, g.N); return GOOFER_ERR_INVALID; }
+        for (int k = 0; k < 4; ++k)
+            if (g.formants[k] && g.formant_len[k] <= 0) { gf_set_error("source %d: formant track %d has length %d", s, k + 1, g.formant_len[k]); return GOOFER_ERR_INVALID; }
         srcs[s] = d;
+    }
+    for (int i = 0; i < b->n_notes; ++i) {
+        const GooferSource &g = b->sources[plans[i].src];
+        if (g.T <= 0 || g.N <= 0) { gf_set_error("note %d: source %d has no frames / samples", i, plans[i].src); return GOOFER_ERR_INVALID; }
     }
     GfSourceDev *d_srcs = bp.arr<GfSourceDev>(std::max(1, b->n_sources));
     if (bp.off > bp.cap) { gf_set_error("workspace too small for the source cache (%zu > %zu)", bp.off, bp.cap); return GOOFER_ERR_WORKSPACE; }
-    if (b->n_sources) {
-        void *stage = gf_pin_take(srcs.size() * sizeof(GfSourceDev));
-        if (!stage) { gf_set_error("cudaMallocHost failed for the metadata staging arena"); return GOOFER_ERR_CUDA; }
-        std::memcpy(stage, srcs.data(), srcs.size() * sizeof(GfSourceDev));
-        if ((rc = gf_meta_copy(d_srcs, stage, srcs.size() * sizeof(GfSourceDev), st)) != GOOFER_OK) return rc;
-    }
-    gf_launch_src_env(d_srcs, b->n_sources, max_T, st); ++g_stats.kernel_launches; GF_STEP("src_env");
+    // source table + envelope decode: issued inside the first wave, after its phase generator (gf_render_wave)
+    std::function<int()> sources_first = [&]() -> int {
+        if (src_ready) GF_CUDA(cudaStreamWaitEvent(st, src_ready, 0));
+        if (b->n_sources) {
+            void *stage = gf_pin_take(srcs.size() * sizeof(GfSourceDev));
+            if (!stage) { gf_set_error("cudaMallocHost failed for the metadata staging arena"); return GOOFER_ERR_CUDA; }
+            std::memcpy(stage, srcs.data(), srcs.size() * sizeof(GfSourceDev));
+            const int rcs = gf_meta_copy(d_srcs, stage, srcs.size() * sizeof(GfSourceDev), st);
+            if (rcs != GOOFER_OK) return rcs;
+        }
+        gf_launch_src_env(d_srcs, b->n_sources, max_T, st); ++g_stats.kernel_launches; GF_STEP("src_env");
+        return GOOFER_OK;
+    };
 
     // ---- waves: greedy packing into what is left of the workspace ----
     bp.off = (bp.off + 255) & ~(size_t)255;
@@ -872,10 +941,26 @@ static int gf_render_batch_ex(const GooferBatch *b, void *workspace, size_t work
             return GOOFER_ERR_WORKSPACE;
         }
         Bump wave{(char *)workspace + bp.off, wave_cap, 0};
-        if ((rc = gf_render_wave(b, plans, i0, i1, d_srcs, wave, st, parts, n_parts)) != GOOFER_OK) return rc;
+        if ((rc = gf_render_wave(b, plans, i0, i1, d_srcs, wave, st, parts, n_parts, d_status, &sources_first)) != GOOFER_OK) return rc;
         // host-side work lists are reused by the next wave only after this one was enqueued; the
         // device regions are reused in stream order, so no extra synchronisation is needed
         i0 = i1;
+    }
+    return GOOFER_OK;
+}
+
+extern "C" int goofer_render_status(const void *workspace, void *stream, int32_t *first_note)
+{
+    if (!workspace) { gf_set_error("goofer_render_status: NULL workspace"); return GOOFER_ERR_INVALID; }
+    int st[2] = {0, 0};
+    workspace = (const void *)(((uintptr_t)workspace + 255) & ~(uintptr_t)255);      // where the bump allocator put the status word
+    GF_CUDA(cudaMemcpyAsync(st, workspace, sizeof(st), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    GF_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+    if (first_note) *first_note = st[0] ? st[1] : -1;
+    if (st[0]) {
+        gf_set_error("note %d: %s list overflowed (mean f0 above sr / 8); the pulse train of that note is truncated", st[1],
+                     (st[0] & 1) ? "pulse-onset" : "growl-event");
+        return GOOFER_ERR_NOTE;
     }
     return GOOFER_OK;
 }
@@ -886,7 +971,7 @@ static int gf_render_batch_ex(const GooferBatch *b, void *workspace, size_t work
 extern "C" int goofer_stft_batch(const float *x, int32_t n_sig, int32_t n, float *S_out, void *stream)
 {
     if (!x || !S_out || n_sig < 0 || n < 2) { gf_set_error("goofer_stft_batch: invalid arguments"); return GOOFER_ERR_INVALID; }
-    int rc = gf_tables_init(44100);
+    int rc = gf_tables_init(0);
     if (rc) return rc;
     if (n_sig == 0) return GOOFER_OK;
     gf_launch_stft(x, n_sig, n, (float2 *)S_out, (cudaStream_t)stream);
@@ -897,7 +982,7 @@ extern "C" int goofer_stft_batch(const float *x, int32_t n_sig, int32_t n, float
 extern "C" int goofer_istft_batch(const float *S, int32_t n_sig, int32_t T, int32_t length, float *y_out, void *stream)
 {
     if (!S || !y_out || n_sig < 0 || T < 1 || length < 0) { gf_set_error("goofer_istft_batch: invalid arguments"); return GOOFER_ERR_INVALID; }
-    int rc = gf_tables_init(44100);
+    int rc = gf_tables_init(0);
     if (rc) return rc;
     if (n_sig == 0 || length == 0) return GOOFER_OK;
     if (length < GF_HOP * (T - 1)) { gf_set_error("goofer_istft_batch: length %d shorter than hop * (T - 1) = %d is not supported", length, GF_HOP * (T - 1)); return GOOFER_ERR_INVALID; }

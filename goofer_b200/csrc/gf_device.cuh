@@ -4,10 +4,11 @@
 #include <stdint.h>
 #include "gf_hd.h"
 #include "gf_plan.h"
+#include "gf_fft.cuh"
 
 // ---- constant tables (GOOFER.py:12-46 get_cached_window/freqs/boost/brightness; :241-261 taps) ----
 struct GfTables {
-    float2 tw512[512];      // exp(-2 pi i m / 512)
+    float2 twl[GF_TWL_N];   // per-thread twiddles of the radix-8 passes (gf_fft.cuh gf_twl_fill)
     float2 tw1024[513];     // exp(-2 pi i k / 1024)
     float win[1024];        // sqrt(hanning(1024)) in f32          GOOFER.py:16
     float win2[1024];       // win * win (f32)                      GOOFER.py:386
@@ -127,6 +128,21 @@ struct GfOnepoleJob {
     int sr;
     int pad;
 };
+
+// ---- per-device launch state ---------------------------------------------------------------------
+// cudaFuncSetAttribute applies to the CURRENT device only, so the "already raised" memo of a kernel's dynamic
+// shared-memory limit is kept per device: one process may drive several GPUs (one host thread each).  A benign race
+// between two threads on the same device sets the same value twice.
+#define GF_MAX_DEVICES 64
+struct GfSmemLimit { size_t bytes[GF_MAX_DEVICES]; };
+template <typename K> static inline void gf_smem_limit(K kernel, size_t bytes, GfSmemLimit &memo)
+{
+    int dev = 0;
+    const bool known = cudaGetDevice(&dev) == cudaSuccess && dev >= 0 && dev < GF_MAX_DEVICES;
+    if (known && memo.bytes[dev] >= bytes) return;
+    cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    if (known) memo.bytes[dev] = bytes;
+}
 
 // ---- small helpers ------------------------------------------------------------------------------
 __device__ __forceinline__ int gf_reflect(int q, int n)

@@ -57,24 +57,63 @@ template <bool INV> GF_HD void gf_dft8(float2 *v)
     gf_dft4<INV>(a4, a5, a6, a7, v[1], v[3], v[5], v[7]);
 }
 
+// ---- twiddles ---------------------------------------------------------------------------------
+// Thread j of a transform needs, for every radix-8 pass after the first, the seven factors w^r (r = 1..7) of ITS OWN
+// butterfly: w = exp(-2 pi i k / 64), k = j & 7 (pass NS = 8) and w = exp(-2 pi i j / 512) (pass NS = 64).  Read from
+// the natural table exp(-2 pi i m / 512) those are strided gathers (m = 8 k r / j r): on the frame kernel they were
+// 32 % of all shared-memory wavefronts and 91 % of its bank conflicts (ncu source page, round 1).  The table below
+// is laid out per thread instead: pairs (w^2q, w^(2q+1)) of thread j sit in one 16-byte slot, consecutive threads
+// in consecutive slots, so a warp reads a contiguous 512-byte run per pair (16-byte loads, no conflicts):
+//   NS = 8 : twl[(q * 8 + k) * 2 + (r & 1)]            k = j & 7, q = r >> 1           (64 entries)
+//   NS = 64: twl[64 + (q * 64 + j) * 2 + (r & 1)]                                       (512 entries)
+#define GF_TWL_N (64 + 512)
+
+static inline void gf_twl_fill(float2 *twl)     // host: fp64 cos / sin rounded once, like the natural table it replaces
+{
+    const double PI = 3.141592653589793238462643383279502884;
+    for (int r = 0; r < 8; ++r) {
+        for (int k = 0; k < 8; ++k) {
+            const double a = -2.0 * PI * (double)(8 * k * r) / 512.0;
+            twl[((r >> 1) * 8 + k) * 2 + (r & 1)] = make_float2((float)cos(a), (float)sin(a));
+        }
+        for (int j = 0; j < 64; ++j) {
+            const double a = -2.0 * PI * (double)(j * r) / 512.0;
+            twl[64 + ((r >> 1) * 64 + j) * 2 + (r & 1)] = make_float2((float)cos(a), (float)sin(a));
+        }
+    }
+}
+
+// the pair (w^2q, w^(2q+1)) of one thread: one 16-byte load on the device
+GF_HD void gf_tw_pair(const float2 *p, float2 &a, float2 &b)
+{
+#if defined(__CUDA_ARCH__)
+    const float4 q = *reinterpret_cast<const float4 *>(p);
+    a = make_float2(q.x, q.y); b = make_float2(q.z, q.w);
+#else
+    a = p[0]; b = p[1];
+#endif
+}
+
 // One Stockham radix-8 pass of the 512-point transform for thread j (0..63).
-//   NS = 1, 8, 64 for the three passes.  tw512[m] = exp(-2 pi i m / 512), m < 512.
+//   NS = 1, 8, 64 for the three passes.  twl: the per-thread twiddle table above (16-byte aligned).
 // Reads buf[j + 64 r]; the caller must barrier between gf_fft_pass_load and gf_fft_pass_store when
 // running in place.
-template <bool INV, int NS> GF_HD void gf_fft_pass_load(int j, const float2 *buf, const float2 *tw512, float2 *v)
+template <bool INV, int NS> GF_HD void gf_fft_pass_load(int j, const float2 *buf, const float2 *twl, float2 *v)
 {
     // gf_fpad(j + 64 r) == 64 r + (gf_fpad(j) ^ (8 (r & 1))) for j < 64: two bases, immediate offsets
     const float2 *src0 = buf + gf_fpad(j), *src1 = buf + (gf_fpad(j) ^ 8);
 #pragma unroll
     for (int r = 0; r < 8; ++r) v[r] = (r & 1) ? src1[64 * r] : src0[64 * r];
     if (NS > 1) {
-        const int k = j & (NS - 1);
-        const int step = k * (64 / NS);          // twiddle exponent for r = 1 (in 512ths of a turn)
+        const float2 *tw = (NS == 8) ? twl + 2 * (j & 7) : twl + 64 + 2 * j;
+        const int qs = (NS == 8) ? 16 : 128;      // float2 elements between the pairs of a thread
 #pragma unroll
-        for (int r = 1; r < 8; ++r) {
-            float2 w = tw512[r * step];
-            if (INV) w.y = -w.y;
-            v[r] = gf_cmul(v[r], w);
+        for (int q = 0; q < 4; ++q) {
+            float2 w0, w1;
+            gf_tw_pair(tw + q * qs, w0, w1);
+            if (INV) { w0.y = -w0.y; w1.y = -w1.y; }
+            if (q > 0) v[2 * q] = gf_cmul(v[2 * q], w0);
+            v[2 * q + 1] = gf_cmul(v[2 * q + 1], w1);
         }
     }
     gf_dft8<INV>(v);

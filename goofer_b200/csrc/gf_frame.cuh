@@ -6,15 +6,15 @@
 #include "gf_fft.cuh"
 
 // shared-memory tables every frame kernel stages once per CTA
-struct GfFrameTables {
-    float2 tw512[512];
+struct __align__(16) GfFrameTables {
+    float2 twl[GF_TWL_N];                     // per-thread FFT twiddles (gf_fft.cuh)
     float2 tw1024[513];
     float win[1024];
 };
 
 __device__ __forceinline__ void gf_stage_tables(GfFrameTables *st)
 {
-    for (int i = threadIdx.x; i < 512; i += blockDim.x) st->tw512[i] = d_tab.tw512[i];
+    for (int i = threadIdx.x; i < GF_TWL_N; i += blockDim.x) st->twl[i] = d_tab.twl[i];
     for (int i = threadIdx.x; i < 513; i += blockDim.x) st->tw1024[i] = d_tab.tw1024[i];
     for (int i = threadIdx.x; i < 1024; i += blockDim.x) st->win[i] = d_tab.win[i];
 }
@@ -30,7 +30,7 @@ __device__ __forceinline__ void gf_lane_sync(int lane)
 // All threads of the CTA call this together, after a CTA-wide barrier that made the input visible.  `n_xf` transforms
 // live at bufs + q * GF_FFT_BUF (q < n_xf); lane = threadIdx.x / 64 works on transforms lane, lane + n_lanes, ...
 template <bool INV>
-__device__ __forceinline__ void gf_cta_fft512(float2 *bufs, int n_xf, const float2 *tw512)
+__device__ __forceinline__ void gf_cta_fft512(float2 *bufs, int n_xf, const float2 *twl)
 {
     const int lane = threadIdx.x >> 6, j = threadIdx.x & 63, n_lanes = blockDim.x >> 6;
     for (int q0 = 0; q0 < n_xf; q0 += n_lanes) {
@@ -39,15 +39,15 @@ __device__ __forceinline__ void gf_cta_fft512(float2 *bufs, int n_xf, const floa
         float2 *buf = bufs + (size_t)q * GF_FFT_BUF;
         float2 v[8];
         if (on) {
-            gf_fft_pass_load<INV, 1>(j, buf, tw512, v);
+            gf_fft_pass_load<INV, 1>(j, buf, twl, v);
             gf_lane_sync(lane);
             gf_fft_pass_store<1>(j, buf, v);
             gf_lane_sync(lane);
-            gf_fft_pass_load<INV, 8>(j, buf, tw512, v);
+            gf_fft_pass_load<INV, 8>(j, buf, twl, v);
             gf_lane_sync(lane);
             gf_fft_pass_store<8>(j, buf, v);
             gf_lane_sync(lane);
-            gf_fft_pass_load<INV, 64>(j, buf, tw512, v);
+            gf_fft_pass_load<INV, 64>(j, buf, twl, v);
             gf_lane_sync(lane);
             gf_fft_pass_store<64>(j, buf, v);
         }
@@ -58,24 +58,24 @@ __device__ __forceinline__ void gf_cta_fft512(float2 *bufs, int n_xf, const floa
 // NQ transforms per 64-thread lane (n_xf = NQ * lanes), all advanced through a pass before the lane synchronises:
 // five two-warp barriers and one CTA-wide barrier for the whole batch
 template <bool INV, int NQ>
-__device__ __forceinline__ void gf_cta_fft512_multi(float2 *bufs, const float2 *tw512)
+__device__ __forceinline__ void gf_cta_fft512_multi(float2 *bufs, const float2 *twl)
 {
     const int lane = threadIdx.x >> 6, j = threadIdx.x & 63, n_lanes = blockDim.x >> 6;
     float2 v[NQ][8];
 #pragma unroll
-    for (int q = 0; q < NQ; ++q) gf_fft_pass_load<INV, 1>(j, bufs + (size_t)(lane + q * n_lanes) * GF_FFT_BUF, tw512, v[q]);
+    for (int q = 0; q < NQ; ++q) gf_fft_pass_load<INV, 1>(j, bufs + (size_t)(lane + q * n_lanes) * GF_FFT_BUF, twl, v[q]);
     gf_lane_sync(lane);
 #pragma unroll
     for (int q = 0; q < NQ; ++q) gf_fft_pass_store<1>(j, bufs + (size_t)(lane + q * n_lanes) * GF_FFT_BUF, v[q]);
     gf_lane_sync(lane);
 #pragma unroll
-    for (int q = 0; q < NQ; ++q) gf_fft_pass_load<INV, 8>(j, bufs + (size_t)(lane + q * n_lanes) * GF_FFT_BUF, tw512, v[q]);
+    for (int q = 0; q < NQ; ++q) gf_fft_pass_load<INV, 8>(j, bufs + (size_t)(lane + q * n_lanes) * GF_FFT_BUF, twl, v[q]);
     gf_lane_sync(lane);
 #pragma unroll
     for (int q = 0; q < NQ; ++q) gf_fft_pass_store<8>(j, bufs + (size_t)(lane + q * n_lanes) * GF_FFT_BUF, v[q]);
     gf_lane_sync(lane);
 #pragma unroll
-    for (int q = 0; q < NQ; ++q) gf_fft_pass_load<INV, 64>(j, bufs + (size_t)(lane + q * n_lanes) * GF_FFT_BUF, tw512, v[q]);
+    for (int q = 0; q < NQ; ++q) gf_fft_pass_load<INV, 64>(j, bufs + (size_t)(lane + q * n_lanes) * GF_FFT_BUF, twl, v[q]);
     gf_lane_sync(lane);
 #pragma unroll
     for (int q = 0; q < NQ; ++q) gf_fft_pass_store<64>(j, bufs + (size_t)(lane + q * n_lanes) * GF_FFT_BUF, v[q]);

@@ -7,6 +7,7 @@
 #include <ctime>
 
 struct GfHostCache {
+    int device = -1;                                                   // the CUDA device the buffers, streams and events belong to
     void *dev = nullptr;  size_t dev_cap = 0;
     void *ws = nullptr;   size_t ws_cap = 0;
     cudaStream_t st = nullptr, st_in = nullptr, st_out = nullptr;     // compute, H2D, D2H
@@ -61,8 +62,15 @@ __global__ void __launch_bounds__(256) gf_pull_kernel(const GfPullJob *__restric
     }
 }
 
-extern "C" void goofer_host_release(void)
+// frees what this thread cached ON THE DEVICE IT WAS CREATED FOR (the caller may have moved to another GPU since)
+static void gf_hc_free()
 {
+    int cur = -1;
+    cudaGetDevice(&cur);
+    if (g_hc.device >= 0 && g_hc.device != cur) cudaSetDevice(g_hc.device);
+    if (g_hc.st) cudaStreamSynchronize(g_hc.st);
+    if (g_hc.st_in) cudaStreamSynchronize(g_hc.st_in);
+    if (g_hc.st_out) cudaStreamSynchronize(g_hc.st_out);
     if (g_hc.dev) cudaFree(g_hc.dev);
     if (g_hc.ws) cudaFree(g_hc.ws);
     for (cudaEvent_t e : g_hc.ev) cudaEventDestroy(e);
@@ -70,20 +78,61 @@ extern "C" void goofer_host_release(void)
     if (g_hc.st_in) cudaStreamDestroy(g_hc.st_in);
     if (g_hc.st_out) cudaStreamDestroy(g_hc.st_out);
     g_hc = GfHostCache();
-    if (g_side.sx) { cudaStreamDestroy(g_side.sx); cudaEventDestroy(g_side.fork); cudaEventDestroy(g_side.join); g_side = GfSide(); }
+    if (cur >= 0) cudaSetDevice(cur);
+}
+
+// The thread-local caches have no destructor (CUDA may be gone by the time a thread's statics are torn down): a host
+// thread that used goofer_render_batch_host calls this before it exits.
+extern "C" void goofer_host_release(void)
+{
+    gf_hc_free();
+    if (g_side.sx) {
+        int cur = -1;
+        cudaGetDevice(&cur);
+        if (g_side.dev >= 0 && g_side.dev != cur) cudaSetDevice(g_side.dev);
+        cudaStreamSynchronize(g_side.sx);
+        cudaStreamDestroy(g_side.sx); cudaEventDestroy(g_side.fork); cudaEventDestroy(g_side.join); g_side = GfSide();
+        if (cur >= 0) cudaSetDevice(cur);
+    }
+    if (g_pin.base) {
+        if (g_pin.dev >= 0) { int cur = -1; cudaGetDevice(&cur); cudaSetDevice(g_pin.dev); cudaDeviceSynchronize(); if (cur >= 0) cudaSetDevice(cur); }
+        cudaFreeHost(g_pin.base);
+        g_pin = GfPinned();
+    }
 }
 
 // Only the frame kernel reads the noise phases (2/3 of the input bytes).  The batch is rendered ONCE: the
 // preparation kernels (tracks, f0, walk, pulse, env) of all notes run at full width while the phases stream in on
 // st_in; frame / peak / mix then go part by part (a part = a run of notes whose phases arrived together), and a
 // part's output leaves on st_out while the next part computes (PCIe is full duplex).
+static int gf_render_batch_host_impl(const GooferBatch *b);
+
 extern "C" int goofer_render_batch_host(const GooferBatch *b)
+{
+    const int rc = gf_render_batch_host_impl(b);
+    if (rc != GOOFER_OK) {
+        // copies from / into the caller's host buffers may still be in flight: the caller is free to release or
+        // overwrite them once this call returns
+        if (g_hc.st_in) cudaStreamSynchronize(g_hc.st_in);
+        if (g_hc.st) cudaStreamSynchronize(g_hc.st);
+        if (g_hc.st_out) cudaStreamSynchronize(g_hc.st_out);
+        cudaGetLastError();
+    }
+    return rc;
+}
+
+static int gf_render_batch_host_impl(const GooferBatch *b)
 {
     int rc = gf_validate(b);
     if (rc != GOOFER_OK) return rc;
     g_stats.h2d_bytes = 0; g_stats.d2h_bytes = 0; g_stats.kernel_launches = 0; g_stats.waves = 0;
     if (b->n_notes == 0) return GOOFER_OK;
     if ((!b->out && !b->out_pcm16) || !b->bend_cents) { gf_set_error("NULL out (and out_pcm16) / bend_cents"); return GOOFER_ERR_INVALID; }
+    {
+        int cur = -1;
+        GF_CUDA(cudaGetDevice(&cur));
+        if (g_hc.device != cur) { gf_hc_free(); g_hc.device = cur; }      // the thread moved to another GPU: its cache goes with the old one
+    }
     if (!g_hc.st) GF_CUDA(cudaStreamCreateWithFlags(&g_hc.st, cudaStreamNonBlocking));
     if (!g_hc.st_in) GF_CUDA(cudaStreamCreateWithFlags(&g_hc.st_in, cudaStreamNonBlocking));
     if (!g_hc.st_out) GF_CUDA(cudaStreamCreateWithFlags(&g_hc.st_out, cudaStreamNonBlocking));
@@ -207,8 +256,10 @@ extern "C" int goofer_render_batch_host(const GooferBatch *b)
             GfPullJob *stage = (GfPullJob *)gf_pin_take(jobs.size() * sizeof(GfPullJob));
             if (!stage) { gf_set_error("cudaMallocHost failed for the gather table"); return GOOFER_ERR_CUDA; }
             std::memcpy(stage, jobs.data(), jobs.size() * sizeof(GfPullJob));
-            if ((rc = gf_meta_copy(pull_tab, stage, jobs.size() * sizeof(GfPullJob), st)) != GOOFER_OK) return rc;
-            gf_pull_kernel<<<blocks, 256, 0, st>>>(pull_tab, (int)jobs.size());   // compute stream: the preparation kernels follow it
+            // on the upload stream: the first kernels that need the sources wait for its event (src_ready below), the
+            // phase generator of the first wave runs beside it
+            if ((rc = gf_meta_copy(pull_tab, stage, jobs.size() * sizeof(GfPullJob), st_in)) != GOOFER_OK) return rc;
+            gf_pull_kernel<<<blocks, 256, 0, st_in>>>(pull_tab, (int)jobs.size());
             GF_CUDA(cudaGetLastError());
             for (const Cp &c : cps) g_stats.h2d_bytes += (int64_t)c.bytes;
         } else {
@@ -263,8 +314,7 @@ extern "C" int goofer_render_batch_host(const GooferBatch *b)
         ends.push_back(nn);
     }
     const int n_chunks = (int)ends.size();
-    const size_t want = goofer_workspace_bytes(&db, 0);
-    if (want == 0) return GOOFER_ERR_NOTE;
+    const size_t want = gf_workspace_bytes_planned(&db, plans, 0);
     if ((rc = gf_hc_reserve(&g_hc.ws, &g_hc.ws_cap, want)) != GOOFER_OK) return rc;
     while ((int)g_hc.ev.size() < 2 * n_chunks + 1) {
         cudaEvent_t e;
@@ -313,9 +363,12 @@ extern "C" int goofer_render_batch_host(const GooferBatch *b)
         parts[c].phi_ready = g_hc.ev[2 * c];
         parts[c].done = g_hc.ev[2 * c + 1];
     }
-    GF_CUDA(cudaStreamWaitEvent(st, g_hc.ev[2 * n_chunks], 0));
     // one render of the whole batch: preparation kernels run once at full width; frame / peak / mix go part by part
-    if ((rc = gf_render_batch_ex(&db, g_hc.ws, g_hc.ws_cap, st, parts.data(), n_chunks)) != GOOFER_OK) return rc;
+    if ((rc = gf_render_batch_ex(&db, g_hc.ws, g_hc.ws_cap, st, parts.data(), n_chunks, &plans, g_hc.ev[2 * n_chunks])) != GOOFER_OK) return rc;
+    int *status_host = (int *)gf_pin_take(256);              // render status word (overflowed pulse lists), read back with the results
+    if (!status_host) { gf_set_error("cudaMallocHost failed for the status word"); return GOOFER_ERR_CUDA; }
+    status_host[0] = 0; status_host[1] = -1;
+    GF_CUDA(cudaMemcpyAsync(status_host, g_hc.ws, 2 * sizeof(int), cudaMemcpyDeviceToHost, st));
     const int64_t launches = g_stats.kernel_launches;
     const int waves = g_stats.waves;
     if (trace) h_enqueued = now_ms();
@@ -337,6 +390,11 @@ extern "C" int goofer_render_batch_host(const GooferBatch *b)
     g_stats.waves = waves;
     GF_CUDA(cudaStreamSynchronize(st_out));
     GF_CUDA(cudaStreamSynchronize(st));
+    if (status_host[0]) {
+        gf_set_error("note %d: %s list overflowed (mean f0 above sr / 8); the pulse train of that note is truncated", status_host[1],
+                     (status_host[0] & 1) ? "pulse-onset" : "growl-event");
+        return GOOFER_ERR_NOTE;
+    }
     if (trace) {
         const double h_done = now_ms();
         float small = 0;

@@ -20,7 +20,7 @@
 #define GF_BLUR_K 12                  // reach of the edge correction of the time-domain blur (see gf_blur_edges)
 
 struct GfFrameSmem {
-    float2 tw512[512];                        // the FFT passes hit these every butterfly; window and split twiddles
+    float2 twl[GF_TWL_N];                     // per-thread FFT twiddles (gf_fft.cuh): every butterfly reads them; window and split twiddles
                                               // come from d_tab through L1 (keeps the CTA at <= 113 KB: two per SM)
     float2 z[3][GF_RND][GF_FFT_BUF];          // [0] harmonic, [1] breath, [2] unvoiced (also the forward buffer)
     float edge[2][GF_RND][4];                 // voiced frames, harmonic / breath: Im X[0], Im X[1], Im X[512], Im X[511] before the blur
@@ -240,7 +240,7 @@ gf_frame_kernel(const int4 *__restrict__ work, const GfPassDev *__restrict__ pas
     const int b0 = wk.y, nb = wk.z;
     const int tid = threadIdx.x;
 
-    for (int i = tid; i < 512; i += blockDim.x) sm.tw512[i] = d_tab.tw512[i];
+    for (int i = tid; i < GF_TWL_N; i += blockDim.x) sm.twl[i] = d_tab.twl[i];
     const float *__restrict__ win = d_tab.win;
     const float2 *__restrict__ tw1024 = d_tab.tw1024;
     for (int i = tid; i < 9 * GF_HOP; i += blockDim.x) (&sm.carry[0][0][0])[i] = 0.0f;
@@ -313,7 +313,7 @@ gf_frame_kernel(const int4 *__restrict__ work, const GfPassDev *__restrict__ pas
         if (t0 + GF_RND <= t_end) prefetch_round(t0 + GF_RND);
 #endif
         // ---- 2. forward FFT ----
-        gf_cta_fft512<false>(&sm.z[2][0][0], nf, sm.tw512);
+        gf_cta_fft512<false>(&sm.z[2][0][0], nf, sm.twl);
         const int m0r = t0 - t_begin;                         // this round's first entry of the per-frame tables
         bool uv_on = false;                                   // uniform: the round computes the unvoiced stream unless every frame may skip it
         for (int q = 0; q < nf; ++q) uv_on = uv_on || (sm.uvskip[m0r + q] == 0);
@@ -366,10 +366,10 @@ gf_frame_kernel(const int4 *__restrict__ work, const GfPassDev *__restrict__ pas
         // ---- 5. inverse FFTs (stream-major: transform q = s * GF_RND + f) ----
         const int n_streams = uv_on ? 3 : 2;
         if (nf == GF_RND) {
-            if (uv_on) gf_cta_fft512_multi<true, 3>(&sm.z[0][0][0], sm.tw512);
-            else gf_cta_fft512_multi<true, 2>(&sm.z[0][0][0], sm.tw512);
+            if (uv_on) gf_cta_fft512_multi<true, 3>(&sm.z[0][0][0], sm.twl);
+            else gf_cta_fft512_multi<true, 2>(&sm.z[0][0][0], sm.twl);
         } else {
-            for (int s = 0; s < n_streams; ++s) gf_cta_fft512<true>(&sm.z[s][0][0], nf, sm.tw512);
+            for (int s = 0; s < n_streams; ++s) gf_cta_fft512<true>(&sm.z[s][0][0], nf, sm.twl);
         }
         // ---- 6. overlap-add + emit: thread `tid` owns column tid of every hop block ----
         {
@@ -410,10 +410,7 @@ void gf_launch_frame(const int4 *work, int n_work, const GfPassDev *passes, GfPa
                      const GfNotePlan *plans, cudaStream_t st)
 {
     if (n_work <= 0) return;
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaFuncSetAttribute(gf_frame_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(GfFrameSmem));
-        attr_set = true;
-    }
+    static GfSmemLimit memo;
+    gf_smem_limit(gf_frame_kernel, sizeof(GfFrameSmem), memo);
     gf_frame_kernel<<<n_work, GF_FRAME_THREADS, sizeof(GfFrameSmem), st>>>(work, passes, scal, notes, plans);
 }

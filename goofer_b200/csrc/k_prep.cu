@@ -236,6 +236,10 @@ void gf_launch_tracks(const GfNotePlan *plans, const GfNoteDev *notes, const GfS
 // envelope: one warp per output frame, eight frames per CTA.  Lane L owns the 17 contiguous bins
 // [17 L, 17 L + 17) (513 = 30 * 17 + 3: lane 30 owns three bins, lane 31 none), which makes every FIR a
 // register-tiled sliding window over a reflect-padded shared-memory row (stride 17 is conflict free).
+// The GATHER stages (fw / fry / F1-F4 / g resampling: reads at b * ratio) use the other mapping, lane L owns bins
+// L, L + 32, .. : neighbouring lanes then read neighbouring words, whereas 17 L * ratio collides whenever the
+// scaled stride shares a factor with 32 (ncu, round 1: 31 M bank conflicts, 23 % of the kernel's shared-memory
+// wavefronts, all on the gather lines).  Stages hand rows over through shared memory, so each picks its own mapping.
 // Values are f32 like the arrays the reference stores; positions / abscissae stay fp64.
 // ------------------------------------------------------------------------------------------------
 #define GF_ENV_WARPS GF_FT
@@ -443,8 +447,9 @@ gf_env_kernel(const int2 *__restrict__ work, const GfNotePlan *__restrict__ plan
             // SillySampler.py:555-569: resample at (b - 256.5) (1 + fw) + 256.5, clipped, 2-tap lerp
 #pragma unroll
             for (int e = 0; e < GF_EPL; ++e) {
-                if (e < nown) {
-                    double pos = ((double)(b0 + e) - 513.0 / 2.0) * (1.0 + pl.fw) + 513.0 / 2.0;
+                const int b = lane + 32 * e;
+                if (b < GF_NBINS) {
+                    double pos = ((double)b - 513.0 / 2.0) * (1.0 + pl.fw) + 513.0 / 2.0;
                     pos = fmin(fmax(pos, 0.0), 512.0);
                     const int lo = (int)pos;
                     const int hi = min(lo + 1, 512);
@@ -454,8 +459,10 @@ gf_env_kernel(const int2 *__restrict__ work, const GfNotePlan *__restrict__ plan
             }
         } else {
 #pragma unroll
-            for (int e = 0; e < GF_EPL; ++e)
-                if (e < nown) acc[e] = fmaf(wm, cur[b0 + e], acc[e]);
+            for (int e = 0; e < GF_EPL; ++e) {
+                const int b = lane + 32 * e;
+                if (b < GF_NBINS) acc[e] = fmaf(wm, cur[b], acc[e]);
+            }
         }
         __syncwarp();
     }
@@ -479,7 +486,7 @@ gf_env_kernel(const int2 *__restrict__ work, const GfNotePlan *__restrict__ plan
         }
 #pragma unroll
         for (int e = 0; e < GF_EPL; ++e) {
-            const float fb = sm.freq[min(b0 + e, 512)];
+            const float fb = sm.freq[min(lane + 32 * e, 512)];
             float gain = 1.0f;
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
@@ -491,8 +498,7 @@ gf_env_kernel(const int2 *__restrict__ work, const GfNotePlan *__restrict__ plan
     }
     float *cur = rA, *oth = rB;
 #pragma unroll
-    for (int e = 0; e < GF_EPL; ++e)
-        if (e < nown) cur[b0 + e] = acc[e];
+    for (int e = 0; e < GF_EPL; ++e) { const int b = lane + 32 * e; if (b < GF_NBINS) cur[b] = acc[e]; }
     __syncwarp();
     // ---- vocal-fry envelope compression (SillySampler.py:967-995) ----
     if (pl.fry_mask_on) {
@@ -504,12 +510,13 @@ gf_env_kernel(const int2 *__restrict__ work, const GfNotePlan *__restrict__ plan
                 const double inv_s = 1.0 / s;
 #pragma unroll
                 for (int e = 0; e < GF_EPL; ++e) {
-                    if (e < nown) {
-                        const double sp = fmin(fmax((double)(b0 + e) * inv_s, 0.0), 512.0);
+                    const int b = lane + 32 * e;
+                    if (b < GF_NBINS) {
+                        const double sp = fmin(fmax((double)b * inv_s, 0.0), 512.0);
                         const int lo = (int)sp;
                         const int hi = min(lo + 1, 512);
                         const float fr = (float)(sp - (double)lo);
-                        oth[b0 + e] = fmaf(fr, cur[hi] - cur[lo], cur[lo]);
+                        oth[b] = fmaf(fr, cur[hi] - cur[lo], cur[lo]);
                     }
                 }
                 __syncwarp();
@@ -575,8 +582,8 @@ gf_env_kernel(const int2 *__restrict__ work, const GfNotePlan *__restrict__ plan
         if (mono) {
 #pragma unroll
             for (int e = 0; e < GF_EPL; ++e) {
-                if (e < nown) {
-                    const int b = b0 + e;
+                const int b = lane + 32 * e;
+                if (b < GF_NBINS) {
                     const double x = (double)b * step;       // 512 * step == nyq exactly
                     // np.interp(x, xd, xs): segment j = number of knots 1 .. nk-1 at or below x
                     const int j = (b >= th1) + (b >= th2) + (b >= th3) + (b >= th4) + (b >= th5);
@@ -591,8 +598,7 @@ gf_env_kernel(const int2 *__restrict__ work, const GfNotePlan *__restrict__ plan
             }
         } else {
             // shifted formants out of order: numpy's search on unsorted knots, reproduced as a linear scan from the left
-            for (int e = 0; e < nown; ++e) {
-                const int b = b0 + e;
+            for (int b = lane; b < GF_NBINS; b += 32) {
                 const double x = (b == 512) ? nyq : (double)b * step;
                 double wf;
                 if (x > kx[nk - 1]) wf = kx[6 + nk - 1];
@@ -616,11 +622,9 @@ gf_env_kernel(const int2 *__restrict__ work, const GfNotePlan *__restrict__ plan
         const double inv_r = 1.0 / pl.formant_shift;
 #pragma unroll
         for (int e = 0; e < GF_EPL; ++e) {
-            if (e < nown) {
-                // freqs / ratio on the freqs grid: in bins that is b / ratio, clipped to [0, 512]
-                const int b = b0 + e;
-                oth[b] = gf_grid_lerp(cur, fmin(fmax((double)b * inv_r, 0.0), 512.0));
-            }
+            // freqs / ratio on the freqs grid: in bins that is b / ratio, clipped to [0, 512]
+            const int b = lane + 32 * e;
+            if (b < GF_NBINS) oth[b] = gf_grid_lerp(cur, fmin(fmax((double)b * inv_r, 0.0), 512.0));
         }
         __syncwarp();
         float *sw = cur; cur = oth; oth = sw;
@@ -634,11 +638,8 @@ void gf_launch_env(const int2 *work, int n_work, const GfNotePlan *plans, const 
                    cudaStream_t st)
 {
     if (n_work <= 0) return;
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaFuncSetAttribute(gf_env_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(GfEnvSmem));
-        attr_set = true;
-    }
+    static GfSmemLimit memo;
+    gf_smem_limit(gf_env_kernel, sizeof(GfEnvSmem), memo);
     gf_env_kernel<<<n_work, 32 * GF_ENV_WARPS, sizeof(GfEnvSmem), st>>>(work, plans, notes, srcs);
 }
 
@@ -798,20 +799,14 @@ void gf_launch_fir(const GfFirJob *jobs, int n_jobs, int max_n, double max_sigma
     if (n_jobs <= 0 || max_n <= 0) return;
     const int radius = (int)(4.0 * max_sigma + 0.5);
     const size_t smem = sizeof(double) * (size_t)((((2 * radius + 1 + 7) & ~7) + 8) + (2 * radius + GF_F32_TILE + 16));
-    static size_t attr = 0;
-    if (smem > attr) {
-        cudaFuncSetAttribute(gf_fir_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        attr = smem;
-    }
+    static GfSmemLimit memo64;
+    gf_smem_limit(gf_fir_kernel, smem, memo64);
     dim3 grid((max_n + GF_F32_TILE - 1) / GF_F32_TILE, n_jobs);
     if (any_f64) gf_fir_kernel<<<grid, GF_F32_THREADS, smem, st>>>(jobs);
     // f32 jobs
     const size_t smem32 = sizeof(float) * (size_t)((((2 * radius + 1 + 7) & ~7) + 8) + (2 * radius + GF_F32_TILE + 16) + GF_F32_TILE);
-    static size_t attr32 = 0;
-    if (smem32 > attr32) {
-        cudaFuncSetAttribute(gf_fir32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem32);
-        attr32 = smem32;
-    }
+    static GfSmemLimit memo32;
+    gf_smem_limit(gf_fir32_kernel, smem32, memo32);
     dim3 grid32((max_n + GF_F32_TILE - 1) / GF_F32_TILE, n_jobs);
     if (any_f32) gf_fir32_kernel<<<grid32, GF_F32_THREADS, smem32, st>>>(jobs);
 }

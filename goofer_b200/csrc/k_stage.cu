@@ -27,7 +27,7 @@ gf_stft_kernel(const float *__restrict__ x, int n, int T, float2 *__restrict__ S
     __syncthreads();
     gf_load_frames(&sm.z[0][0], t0, nf, n, sm.tab.win, [&](int i) { return xs[i]; });
     __syncthreads();
-    gf_cta_fft512<false>(&sm.z[0][0], nf, sm.tab.tw512);
+    gf_cta_fft512<false>(&sm.z[0][0], nf, sm.tab.twl);
     for (int idx = threadIdx.x; idx < nf * 257; idx += blockDim.x) {
         const int k = idx / nf, f = idx - k * nf;
         const float2 Zk = sm.z[f][gf_fpad(k)], Zm = sm.z[f][gf_fpad((512 - k) & 511)];
@@ -64,7 +64,7 @@ gf_istft_kernel(const float2 *__restrict__ S, int T, int length, float *__restri
             if (k != 0 && k != 256) sm.z[f][gf_fpad(512 - k)] = Zm;
         }
         __syncthreads();
-        gf_cta_fft512<true>(&sm.z[0][0], nf, sm.tab.tw512);
+        gf_cta_fft512<true>(&sm.z[0][0], nf, sm.tab.twl);
         gf_ola_add(sm.ring, &sm.z[0][0], t0, nf, sm.tab.win);
         __syncthreads();
         const int last_blk = (t0 + nf - 1 == T - 1) ? T : (t0 + nf - 1);
@@ -76,27 +76,24 @@ gf_istft_kernel(const float2 *__restrict__ S, int T, int length, float *__restri
         for (int i = GF_HOP * (T - 1) + threadIdx.x; i < length; i += blockDim.x) ys[i] = 0.0f;
 }
 
+static void gf_stage_smem_limits()
+{
+    static GfSmemLimit memo_f, memo_i;
+    gf_smem_limit(gf_stft_kernel, sizeof(GfStageSmem), memo_f);
+    gf_smem_limit(gf_istft_kernel, sizeof(GfStageSmem), memo_i);
+}
+
 void gf_launch_stft(const float *x, int n_sig, int n, float2 *S, cudaStream_t st)
 {
     const int T = 1 + n / GF_HOP;
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaFuncSetAttribute(gf_stft_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(GfStageSmem));
-        cudaFuncSetAttribute(gf_istft_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(GfStageSmem));
-        attr_set = true;
-    }
+    gf_stage_smem_limits();
     dim3 grid((T + GF_STAGE_R - 1) / GF_STAGE_R, n_sig);
     gf_stft_kernel<<<grid, GF_STAGE_THREADS, sizeof(GfStageSmem), st>>>(x, n, T, S);
 }
 
 void gf_launch_istft(const float2 *S, int n_sig, int T, int length, float *y, cudaStream_t st)
 {
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaFuncSetAttribute(gf_stft_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(GfStageSmem));
-        cudaFuncSetAttribute(gf_istft_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(GfStageSmem));
-        attr_set = true;
-    }
+    gf_stage_smem_limits();
     const int bpc = 32;
     const int n_blocks = max(T, 2) - 2 + 1;            // hop blocks 2 .. max(T, 2)
     dim3 grid((n_blocks + bpc - 1) / bpc, n_sig);

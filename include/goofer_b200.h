@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define GOOFER_ABI_VERSION 4
+#define GOOFER_ABI_VERSION 5
 #define GOOFER_N_FFT 1024      /* SillySampler.py:14 */
 #define GOOFER_HOP 256         /* SillySampler.py:15 */
 #define GOOFER_N_BINS 513
@@ -174,13 +174,25 @@ int goofer_debug_plan(const GooferBatch *b, int32_t idx, void *out, size_t bytes
 /* Workspace needed to render `b` `notes_per_wave` notes at a time (0 = library default). */
 size_t goofer_workspace_bytes(const GooferBatch *b, int32_t notes_per_wave);
 
-/* Render with every array already resident on the current CUDA device. `stream` is a cudaStream_t. */
+/* Render with every array already resident on the current CUDA device. `stream` is a cudaStream_t.  The call only
+ * enqueues work; results are complete when `stream` is. */
 int goofer_render_batch(const GooferBatch *b, void *workspace, size_t workspace_bytes, void *stream);
+
+/* Outcome of the render(s) enqueued on `stream` with `workspace`: waits for the stream, then returns GOOFER_OK, or
+ * GOOFER_ERR_NOTE when a note's pulse-onset / growl-event list overflowed its capacity of n/8+64 (n/4+64) entries --
+ * mean f0 above sr/8, beyond every MIDI pitch but reachable with a caller-supplied f0 curve (GooferNote.f0_off); the
+ * reference would render such a note (GOOFER.py:473-554), this library truncates its pulse train and says so here.
+ * *first_note (may be NULL) receives the lowest offending note index or -1.  goofer_render_batch_host performs this
+ * check itself. */
+int goofer_render_status(const void *workspace, void *stream, int32_t *first_note);
 
 /* Same call with HOST buffers: copies sources/noise in and results out (pinned staging, chunked and
  * overlapped with compute); allocates and caches its own device buffers per thread. */
 int goofer_render_batch_host(const GooferBatch *b);
-void goofer_host_release(void);     /* frees the cached device/pinned buffers of this thread */
+/* Frees what goofer_render_batch_host cached for the calling thread (device buffers, streams, pinned staging).  The
+ * caches are per (thread, device) -- a thread that moves to another GPU gets a fresh one -- and are not freed at
+ * thread exit: a host thread that used the library calls this before it ends (one thread per GPU is the intended use). */
+void goofer_host_release(void);
 
 /* counters of the last render call on this thread */
 typedef struct GooferStats {

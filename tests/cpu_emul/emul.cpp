@@ -10,8 +10,8 @@
 static void tables(std::vector<float2> &tw512, std::vector<float2> &tw1024)
 {
     const double PI = 3.141592653589793238462643383279502884;
-    tw512.resize(512); tw1024.resize(513);
-    for (int m = 0; m < 512; ++m) tw512[m] = make_float2((float)std::cos(-2.0 * PI * m / 512.0), (float)std::sin(-2.0 * PI * m / 512.0));
+    tw512.resize(GF_TWL_N); tw1024.resize(513);
+    gf_twl_fill(tw512.data());
     for (int k = 0; k <= 512; ++k) tw1024[k] = make_float2((float)std::cos(-2.0 * PI * k / 1024.0), (float)std::sin(-2.0 * PI * k / 1024.0));
 }
 

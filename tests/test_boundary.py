@@ -29,7 +29,7 @@ def test_python_binding_lists_the_same_symbols():
 
 def test_version_and_struct_sizes(lib):
     from goofer_b200 import capi
-    assert lib.goofer_version() == 4
+    assert lib.goofer_version() == 5
     for which, rec in enumerate((capi.GooferSource, capi.GooferNote, capi.GooferNotePlanInfo, capi.GooferBatch, capi.GooferStats)):
         assert int(lib.goofer_struct_size(which)) == C.sizeof(rec)
     assert int(lib.goofer_struct_size(99)) == 0
