@@ -499,7 +499,7 @@ def run_native(args):
                 ent = tj.get(f"{args.workload}:{args.notes}", {})
                 traffic = ent.get(top[0])
                 traffic_src = tj.get("_source")
-                step_traffic = sum(v for v in ent.values() if isinstance(v, (int, float))) or None
+                step_traffic = ent.get("_step_total")         # DRAM bytes of one whole captured step
             except Exception:
                 pass
             roof = {"bound": "hbm", "kernel": top[0], "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,

@@ -20,6 +20,10 @@ FLAG_NAMES = ["t", "g", "fa", "fb", "fc", "fd", "fw", "fst", "fsta", "fstb", "fs
               "FV", "L", "R", "P", "vf", "vh", "vl", "SE"]
 FLAG_SLOT = {n: i for i, n in enumerate(FLAG_NAMES)}
 GF_NFLAGS = len(FLAG_NAMES)
+# GF_OVR_* of include/goofer_b200.h: continuous gf.synthesize keyword arguments (GooferNote.override_val)
+OVERRIDES = ["formant_shift", "F1_shift", "F2_shift", "F3_shift", "F4_shift", "f0_jitter_strength",
+             "volume_jitter_strength_harm", "volume_jitter_strength_breath", "normalize", "breath_strength", "uv_strength"]
+OVERRIDE_SLOT = {n: i for i, n in enumerate(OVERRIDES)}
 # SillySampler looks these up case-insensitively (SillySampler.py:309,346,384,391,399-405)
 CASE_INSENSITIVE = {"se": "SE", "l": "L", "es": "es", "pd": "pd", "fst": "fst",
                     "fsta": "fsta", "fstb": "fstb", "fstc": "fstc", "fstd": "fstd"}
@@ -44,7 +48,8 @@ class GooferNote(C.Structure):
         ("flag", C.c_int32 * GF_NFLAGS), ("present", C.c_uint64),
         ("phi_off", C.c_int64 * 4), ("nrm_off", C.c_int64 * 4), ("out_off", C.c_int64),
         ("f0_off", C.c_int64),
-        ("phi_rng", (C.c_uint64 * 4) * 4), ("phi_rng_mask", C.c_uint32), ("reserved0", C.c_uint32),
+        ("phi_rng", (C.c_uint64 * 4) * 4), ("phi_rng_mask", C.c_uint32), ("override_mask", C.c_uint32),
+        ("override_val", C.c_double * 12),
     ]
 
 

@@ -72,9 +72,26 @@ def _features(path: Path) -> "host.SourceFeatures":
     return f
 
 
-def render_notes(arg_lists: Sequence[Sequence[str]], noise=None, device: str = "cuda:0", pcm16: bool = False) -> List[np.ndarray]:
+_MULTI = {}                                                  # tuple(devices) -> MultiGpuRenderer (persistent worker threads)
+
+
+def default_devices() -> List[str]:
+    """GOOFER_DEVICES="0,1,2,3" (or "all") selects the GPUs render_notes / the server shard a batch over; default cuda:0."""
+    import os
+    env = os.environ.get("GOOFER_DEVICES", "").strip()
+    if not env:
+        return ["cuda:0"]
+    if env == "all":
+        import torch
+        return [f"cuda:{i}" for i in range(torch.cuda.device_count())]
+    return [f"cuda:{int(x)}" for x in env.split(",") if x.strip()]
+
+
+def render_notes(arg_lists: Sequence[Sequence[str]], noise=None, device: str = "cuda:0", pcm16: bool = False,
+                 devices: "Sequence[str] | None" = None) -> List[np.ndarray]:
     """Render many resampler invocations (each the 13 CLI strings) as ONE batch; returns the sample arrays
-    (float32, or int16 PCM encoded on the device with pcm16=True)."""
+    (float32, or int16 PCM encoded on the device with pcm16=True).  devices=[...] (more than one) shards the batch by
+    note over those GPUs, one host thread per GPU (goofer_b200.multi) -- same samples either way."""
     batch = host.Batch()
     src_index = {}
     for args in arg_lists:
@@ -87,11 +104,20 @@ def render_notes(arg_lists: Sequence[Sequence[str]], noise=None, device: str = "
         if key not in src_index:
             src_index[key] = batch.add_source(_features(feat))
         batch.add_note(host.NoteArgs.from_cli(src_index[key], list(args[2:13])))
+    if devices is not None and len(devices) > 1 and len(batch.notes) > 1:
+        from . import multi
+        key = tuple(str(d) for d in devices)
+        if key not in _MULTI:
+            _MULTI[key] = multi.MultiGpuRenderer(key, source_cache=SOURCE_CACHE)
+        return _MULTI[key].render(batch, noise or host.FreshDeviceNoise(), pcm16=pcm16)
+    if devices is not None and len(devices) == 1:
+        device = devices[0]
     ab = batch.assemble(noise or host.FreshDeviceNoise())      # phases drawn on the device (GooferNote.phi_rng)
     db = ab.to_device(device, source_cache=SOURCE_CACHE)
     if pcm16:
         db.enable_pcm16()
     db.render()
+    host.capi.check(db.status())
     return db.outputs_pcm16() if pcm16 else db.outputs()
 
 
@@ -99,13 +125,21 @@ def main(argv: Sequence[str]) -> int:
     logging.basicConfig(format="%(message)s", level=logging.INFO)
     logging.info(VERSION)
     args = list(argv)
+    if not args:
+        # no arguments: server mode, like the reference (SillySampler.py:1238-1240 -> run(), :1220-1224)
+        from . import server
+        try:
+            server.run()
+        except TypeError:
+            logging.info(HELP)
+        return 0
     logging.info(f"Args: {args} (count={len(args)})")
     try:
         if len(args) < 13:
             raise TypeError(f"Expected 13 arguments but got {len(args)}")
         logging.info("Loading cached features")
         logging.info("Synthesizing")
-        out = render_notes([args[:13]], pcm16=True)[0]
+        out = render_notes([args[:13]], pcm16=True, devices=default_devices()[:1])[0]
         sr = _features(feature_path(args[0])).sr
         logging.info(f"Writing {args[1]}")
         write_wav_pcm16(args[1], out, sr)

@@ -66,6 +66,8 @@ struct GfNotePlan {
     double V, B, U, volume;
     int32_t f0_jitter;  double f0_jitter_strength;
     int32_t vol_jitter; double vol_jitter_strength;
+    double vol_jitter_strength_breath;   // 2 x the harmonic strength (SillySampler.py:1024) unless overridden
+    float breath_strength, uv_strength;  // gf.synthesize keyword defaults 0.1 / 0.75 (GOOFER.py:975, 1180-1181)
     double sd;
     double tension;
     int32_t add_subharm; double subharm_weight;

@@ -22,15 +22,15 @@ __device__ __forceinline__ GfStreams gf_pass_gains(const GfNotePlan &pl, const G
         r.b = braw;
         r.u = 0.0f;
     } else {
-        r.b = braw * ms * 0.1f;
-        r.u = (ms == 1.0f) ? 0.0f : uraw * (1.0f - ms) * 0.75f;
+        r.b = braw * ms * pl.breath_strength;                          // 0.1 / 0.75 unless a direct gf.synthesize call overrides them
+        r.u = (ms == 1.0f) ? 0.0f : uraw * (1.0f - ms) * pl.uv_strength;
     }
     if (!SIMPLE && ps.kind == GF_PASS_MAIN && pl.vol_jitter) {
         // GOOFER.py:1185-1191 (create_volume_jitter :638-659 without vibrato)
         const double zh = nd.z_srh[i] / nd.noteScal[GF_NS_SRHMAX];
         const double zb = nd.z_srb[i] / nd.noteScal[GF_NS_SRBMAX];
         const double hj = 1.0 + zh * pl.vol_jitter_strength;
-        const double bj = 1.0 + zb * (pl.vol_jitter_strength * 2);
+        const double bj = 1.0 + zb * pl.vol_jitter_strength_breath;
         const double vj = (double)nd.vjm[i];
         r.h = (float)((double)r.h * (1.0 + (hj - 1.0) * vj));
         r.b = (float)((double)r.b * (1.0 + (bj - 1.0) * vj));

@@ -98,6 +98,24 @@ int gf_plan_note(const GooferBatch *b, int idx, GfNotePlan *pl)
             if (std::fabs(pl->fst[k]) >= 1e-6) pl->any_fst = 1;
         }
     }
+    pl->vol_jitter_strength_breath = pl->vol_jitter_strength * 2;
+    pl->breath_strength = 0.1f;
+    pl->uv_strength = 0.75f;
+    // continuous overrides of the direct gf.synthesize seam (GooferNote.override_val, GOOFER.py:971-983)
+    {
+        auto ovr = [&](int k) { return (nt.override_mask >> k) & 1u; };
+        if (ovr(GF_OVR_FORMANT_SHIFT)) pl->formant_shift = nt.override_val[GF_OVR_FORMANT_SHIFT];
+        for (int k = 0; k < 4; ++k)
+            if (ovr(GF_OVR_F1_SHIFT + k)) pl->F_shift[k] = nt.override_val[GF_OVR_F1_SHIFT + k];
+        pl->any_F_shift = 0;
+        for (int k = 0; k < 4; ++k) if (pl->F_shift[k] != 1.0) pl->any_F_shift = 1;
+        if (ovr(GF_OVR_F0_JITTER_STRENGTH)) pl->f0_jitter_strength = nt.override_val[GF_OVR_F0_JITTER_STRENGTH];
+        if (ovr(GF_OVR_VOL_JITTER_HARM)) { pl->vol_jitter_strength = nt.override_val[GF_OVR_VOL_JITTER_HARM]; pl->vol_jitter_strength_breath = pl->vol_jitter_strength * 2; }
+        if (ovr(GF_OVR_VOL_JITTER_BREATH)) pl->vol_jitter_strength_breath = nt.override_val[GF_OVR_VOL_JITTER_BREATH];
+        if (ovr(GF_OVR_NORMALIZE)) pl->normalize = clipd(nt.override_val[GF_OVR_NORMALIZE], 0.0, 1.0);      // np.clip(normalize, 0, 1)  GOOFER.py:1211
+        if (ovr(GF_OVR_BREATH_STRENGTH)) pl->breath_strength = (float)nt.override_val[GF_OVR_BREATH_STRENGTH];
+        if (ovr(GF_OVR_UV_STRENGTH)) pl->uv_strength = (float)nt.override_val[GF_OVR_UV_STRENGTH];
+    }
     pl->volume = nt.volume;
     pl->pitch_midi = nt.pitch_midi;
     pl->t_cents = fl(nt, GF_t, 0);

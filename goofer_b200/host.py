@@ -189,6 +189,8 @@ class NoteArgs:
     # direct gf.synthesize call (GooferNote.f0_off): per-sample f0 curve; the source is then used whole and the
     # slicing / pitch arguments above are ignored (include/goofer_b200.h)
     f0_curve: Optional[np.ndarray] = None
+    # continuous gf.synthesize keyword arguments that replace the flag-derived scalars (capi.OVERRIDES -> GooferNote.override_val)
+    overrides: Optional[Dict[str, float]] = None
 
     @classmethod
     def from_cli(cls, source: int, args: Sequence[str]) -> "NoteArgs":
@@ -238,6 +240,10 @@ class NoteArgs:
             nt.phi_off[k] = -1
             nt.nrm_off[k] = -1
         nt.f0_off = -1
+        for name, val in (self.overrides or {}).items():
+            k = capi.OVERRIDE_SLOT[name]
+            nt.override_val[k] = float(val)
+            nt.override_mask |= 1 << k
         return nt, bend
 
 
@@ -357,6 +363,37 @@ class Batch:
     def add_note(self, note: NoteArgs) -> int:
         self.notes.append(note)
         return len(self.notes) - 1
+
+    def plan(self) -> List[dict]:
+        """goofer_plan_batch only (host arithmetic, no noise, no device): the lengths / pass counts of every note, e.g. to
+        balance a batch over several GPUs before any shard is assembled."""
+        lib = capi.load()
+        n_notes = len(self.notes)
+        src_arr = (capi.GooferSource * max(1, len(self.sources)))()
+        for i, s in enumerate(self.sources):                     # the planner reads sizes only, never the arrays
+            g = src_arr[i]
+            g.T, g.N, g.sr, g.ylen = s.n_frames, int(s.mask.size), int(s.sr), int(s.ylen)
+            g.K = int(s.knots_log.shape[0]) if s.knots_log is not None else 0
+            for k in range(4):
+                tr = s.formants.get(k + 1)
+                if tr is not None and tr.size:
+                    g.formants[k] = tr.ctypes.data
+                    g.formant_len[k] = int(tr.size)
+        note_arr = (capi.GooferNote * max(1, n_notes))()
+        off = 0
+        for i, nt in enumerate(self.notes):
+            st, bend = nt.to_struct(off)
+            if nt.f0_curve is not None:
+                st.f0_off = 0
+            note_arr[i] = st
+            off += bend.size
+        b = capi.GooferBatch()
+        b.n_sources, b.sources, b.n_notes, b.notes = len(self.sources), src_arr, n_notes, note_arr
+        b.bend_total = off
+        info_arr = (capi.GooferNotePlanInfo * max(1, n_notes))()
+        capi.check(lib.goofer_plan_batch(C.byref(b), info_arr))
+        return [{"n_total": int(x.n_total), "t_out": int(x.t_out), "t_env": int(x.t_env), "n_passes": int(x.n_passes),
+                 "need_phi": list(x.need_phi), "need_nrm": list(x.need_nrm)} for x in info_arr[:n_notes]]
 
     # ---- assembly ---------------------------------------------------------------------------------
     def assemble(self, noise: Callable[[int, dict], dict], taps: bool = False) -> "AssembledBatch":

@@ -105,7 +105,8 @@ def analyse_envelope(y, sr: int = 44100):
 
 
 def synthesize(env_spec, f0_interp, voicing_mask, y=None, sr: int = 44100, n_fft: int = N_FFT, hop_length: int = HOP, *,
-               normalize: float = 1.0, formant_shift: float = 1.0, F1_shift: float = 1.0, F2_shift: float = 1.0,
+               normalize: float = 1.0, uv_strength: float = 0.75, breath_strength: float = 0.1, pitch_shift: float = 1.0,
+               formant_shift: float = 1.0, F1_shift: float = 1.0, F2_shift: float = 1.0,
                F3_shift: float = 1.0, F4_shift: float = 1.0, formants=None, f0_jitter: bool = False,
                f0_jitter_strength: float = 1.5, volume_jitter: bool = False, volume_jitter_strength_harm: float = 50,
                volume_jitter_strength_breath: float = 100, noise=None, device: str = "cuda:0", **unsupported):
@@ -113,44 +114,46 @@ def synthesize(env_spec, f0_interp, voicing_mask, y=None, sr: int = 44100, n_fft
     test.py:38 make, same positional arguments, same return tuple (reconstruct, harmonic, aper_uv, aper_bre), each
     (len(voicing_mask),) float32.  `env_spec` is a (513, T) array or a knots dict; `y` is only looked at for its length
     in the reference and is ignored here (len(voicing_mask) plays that role).  One note rendered through
-    goofer_render_batch with GooferNote.f0_off (include/goofer_b200.h); keyword arguments are carried by the flag
-    columns they correspond to (Appendix A of SURVEY.md), so only values a flag can express are accepted:
-    normalize (P, %), formant_shift (g, 1 + g/200), F1..F4_shift (fa..fd, 1 + x/100), f0_jitter (sh, strength sh/50),
-    volume_jitter (sr, harmonic strength sr/50 with breath = 2x, the pairing SillySampler.py:1022-1024 uses).
+    goofer_render_batch with GooferNote.f0_off (include/goofer_b200.h).  The keyword arguments take the reference's
+    continuous values: they travel as GooferNote.override_val (normalize, uv_strength, breath_strength, formant_shift,
+    F1..F4_shift, f0_jitter_strength, volume_jitter_strength_harm / _breath); pitch_shift scales the f0 curve on the
+    host exactly like GOOFER.py:995 (`f0_interp *= pitch_shift`, float32).  Keyword arguments whose defaults no caller
+    in the reference changes for this path (stretch_factor, glottal_smoothing, roughness_*, subharm_*) stay unsupported.
     `noise`: a host.SeededNoise-like provider (default: fresh noise like the reference)."""
     import numpy as np
     from . import host
-    if unsupported:
-        raise NotImplementedError("ops.synthesize: keyword arguments no resampler flag reaches are not implemented: "
-                                  + ", ".join(sorted(unsupported)))
+    defaults = {"stretch_factor": 1.0, "start_sec": None, "end_sec": None, "glottal_smoothing": False, "apply_brightness": True,
+                "noise_transition_smoothness": 100, "f0_jitter_speed": 100, "volume_jitter_speed": 150, "volume_vibrato": False,
+                "add_subharm": False, "roughness_on": False}
+    bad = sorted(k for k, v in unsupported.items() if not (k in defaults and v == defaults[k]))
+    if bad:
+        raise NotImplementedError("ops.synthesize: keyword arguments no resampler flag reaches are not implemented: " + ", ".join(bad))
     if int(n_fft) != N_FFT or int(hop_length) != HOP:
         raise NotImplementedError("ops.synthesize: n_fft = 1024, hop_length = 256 only")
     mask = np.ascontiguousarray(voicing_mask, dtype=np.float32).reshape(-1)
     f0 = np.ascontiguousarray(f0_interp, dtype=np.float32).reshape(-1)
     if f0.size != mask.size:
         raise ValueError("len(f0_interp) must equal len(voicing_mask)")
+    if float(pitch_shift) != 1.0:
+        f0 = f0 * np.float32(pitch_shift)                     # to_compute'd f32 array times a Python float stays f32 (GOOFER.py:995)
 
-    def flag_value(name, value, scale, offset=0.0):
-        v = (float(value) - offset) * scale
-        if abs(v - round(v)) > 1e-9:
-            raise NotImplementedError(f"ops.synthesize: {name}={value} is not expressible by its integer flag")
-        return int(round(v))
-
+    # the flag columns decide which stages run; the overrides carry the exact values
     flags = ""
-    g = flag_value("formant_shift", formant_shift, 200.0, 1.0)
-    if g:
-        flags += f"g{g}"
-    for nm, val in (("fa", F1_shift), ("fb", F2_shift), ("fc", F3_shift), ("fd", F4_shift)):
-        v = flag_value(nm, val, 100.0, 1.0)
-        if v:
-            flags += f"{nm}{v}"
+    ovr = {"normalize": float(normalize), "breath_strength": float(breath_strength), "uv_strength": float(uv_strength)}
+    if float(formant_shift) != 1.0:
+        flags += "g1"
+        ovr["formant_shift"] = float(formant_shift)
+    for nm, key, val in (("fa", "F1_shift", F1_shift), ("fb", "F2_shift", F2_shift), ("fc", "F3_shift", F3_shift), ("fd", "F4_shift", F4_shift)):
+        if float(val) != 1.0:
+            flags += f"{nm}1"
+            ovr[key] = float(val)
     if f0_jitter:
-        flags += f"sh{flag_value('f0_jitter_strength', f0_jitter_strength, 50.0)}"
+        flags += "sh1"
+        ovr["f0_jitter_strength"] = float(f0_jitter_strength)
     if volume_jitter:
-        if abs(float(volume_jitter_strength_breath) - 2.0 * float(volume_jitter_strength_harm)) > 1e-12:
-            raise NotImplementedError("ops.synthesize: volume_jitter_strength_breath must be twice ..._harm (the sr flag's pairing)")
-        flags += f"sr{flag_value('volume_jitter_strength_harm', volume_jitter_strength_harm, 50.0)}"
-    flags += f"P{flag_value('normalize', min(max(float(normalize), 0.0), 1.0), 100.0)}"
+        flags += "sr1"
+        ovr["volume_jitter_strength_harm"] = float(volume_jitter_strength_harm)
+        ovr["volume_jitter_strength_breath"] = float(volume_jitter_strength_breath)
     forms = {}
     if isinstance(formants, dict):
         for k, v in formants.items():
@@ -176,7 +179,7 @@ def synthesize(env_spec, f0_interp, voicing_mask, y=None, sr: int = 44100, n_fft
         src = host.SourceFeatures.from_dense(env_spec, mask, forms, int(sr), int(mask.size))
     b = host.Batch()
     b.add_source(src)
-    b.add_note(host.NoteArgs(source=0, pitch="C4", flags=flags, f0_curve=f0))
+    b.add_note(host.NoteArgs(source=0, pitch="C4", flags=flags, f0_curve=f0, overrides=ovr))
     ab = b.assemble(noise or host.FreshNoise(), taps=True)
     db = ab.to_device(device)
     db.render()

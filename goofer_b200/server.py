@@ -43,7 +43,8 @@ class _Job:
 
 
 def _render_and_write(arg_lists: Sequence[Sequence[str]]) -> None:
-    outs = cli.render_notes(arg_lists, pcm16=True)        # 16-bit PCM encoded on the device (GooferBatch.out_pcm16)
+    # 16-bit PCM encoded on the device (GooferBatch.out_pcm16); GOOFER_DEVICES shards the batch over several GPUs
+    outs = cli.render_notes(arg_lists, pcm16=True, devices=cli.default_devices())
     for args, out in zip(arg_lists, outs):
         sr = cli._features(cli.feature_path(args[0])).sr     # cached: the file was read when the batch was assembled
         cli.write_wav_pcm16(args[1], out, sr)

@@ -116,8 +116,25 @@ typedef struct GooferNote {
      * a drop-in does in production; host-supplied buffers remain the parity-test path. */
     uint64_t phi_rng[4][4];
     uint32_t phi_rng_mask;
-    uint32_t reserved0;
+    /* Continuous keyword arguments of gf.synthesize (GOOFER.py:971-983) that an integer flag cannot express -- the
+     * direct callers pass floats (test.py:38 formant_shift, breath_strength, uv_strength; SillyEditor.py:227, 559).
+     * Bit k of override_mask: override_val[k] REPLACES the scalar the flags would give (GF_OVR_* below); the flag
+     * columns keep deciding which stages run (sh > 0 turns f0 jitter on, its strength may then be overridden). */
+    uint32_t override_mask;
+    double override_val[12];
 } GooferNote;
+
+enum {
+    GF_OVR_FORMANT_SHIFT = 0,       /* formant_shift (g: 1 + g/200) */
+    GF_OVR_F1_SHIFT, GF_OVR_F2_SHIFT, GF_OVR_F3_SHIFT, GF_OVR_F4_SHIFT,     /* F1..F4_shift (fa..fd: 1 + x/100) */
+    GF_OVR_F0_JITTER_STRENGTH,      /* f0_jitter_strength (sh/50) */
+    GF_OVR_VOL_JITTER_HARM,         /* volume_jitter_strength_harm (sr/50) */
+    GF_OVR_VOL_JITTER_BREATH,       /* volume_jitter_strength_breath (2 * sr/50) */
+    GF_OVR_NORMALIZE,               /* normalize (P/100) */
+    GF_OVR_BREATH_STRENGTH,         /* breath_strength (0.1) */
+    GF_OVR_UV_STRENGTH,             /* uv_strength (0.75) */
+    GF_N_OVERRIDES
+};
 
 /* What the planner derives for one note (lengths the host needs to size noise and output buffers). */
 typedef struct GooferNotePlanInfo {

@@ -22,6 +22,7 @@ class GfNotePlan(C.Structure):
         ("brightness_env", f64), ("es", f64), ("fw", f64), ("fst", f64 * 4), ("any_fst", i32),
         ("V", f64), ("B", f64), ("U", f64), ("volume", f64),
         ("f0_jitter", i32), ("f0_jitter_strength", f64), ("vol_jitter", i32), ("vol_jitter_strength", f64),
+        ("vol_jitter_strength_breath", f64), ("breath_strength", C.c_float), ("uv_strength", C.c_float),
         ("sd", f64), ("tension", f64), ("add_subharm", i32), ("subharm_weight", f64),
         ("sj", f64), ("sa", f64), ("su", f64), ("normalize", f64), ("FV", i32), ("pd", f64),
         ("vf", f64), ("vh", f64), ("vl", f64),

@@ -1,0 +1,172 @@
+"""GPU (-m gpu): BASELINE.json's configs at their FULL sizes against the oracle, note by note (the oracle is fanned
+over the host cores, tests/oracle_pool.py), plus the corners the verdict of round 1 found untested: the non-monotone
+branch of the F1-F4 warp, the whole loop / reverse grid at 16 s, shards against the whole batch.
+Tolerances: max-abs <= 1e-4 of full scale, log-spectral distance <= 0.05 dB (BASELINE.json north_star)."""
+import numpy as np
+import pytest
+
+import bench_data
+from goofer_b200 import capi, host
+from tests import oracle_pool
+
+pytestmark = pytest.mark.gpu
+MAX_ABS, MAX_LSD = 1e-4, 0.05
+
+
+@pytest.fixture(scope="module")
+def torch_cuda(lib):
+    import torch
+    assert torch.cuda.is_available(), "-m gpu tests need a CUDA device; goofer_b200 has no CPU fallback"
+    return torch
+
+
+def _batch(workload, idx, n_sources, noise_cls=host.SeededNoise):
+    b = host.Batch()
+    secs = bench_data.SOURCE_SECONDS.get(workload, 1.0)
+    for s in range(n_sources):
+        f = bench_data.make_source(s, secs)
+        b.add_source(host.SourceFeatures.from_knot_pack(f, f["mask"], f["formants"], f["sr"], f["ylen"]))
+    for i in idx:
+        src, cli = bench_data.note_cli(i, workload, n_sources=n_sources)
+        b.add_note(host.NoteArgs.from_cli(src, cli))
+    return b, noise_cls(base_seed=lambda j: 20000 + 16 * idx[j], legacy_seed=lambda j: 777 + idx[j])
+
+
+def _render_flat(ab, torch):
+    db = ab.to_device("cuda:0")
+    db.render()
+    capi.check(db.status())
+    return db.out[:ab.out_total].cpu().numpy()
+
+
+def _assert_all(res, label):
+    bad = [r for r in res if r[3]]
+    assert not bad, bad[:3]
+    worst = max(res, key=lambda r: r[1])
+    worst_lsd = max(res, key=lambda r: r[2])
+    print(f"{label}: {len(res)} notes vs oracle, worst max-abs {worst[1]:.3e} (note {worst[0]}), worst LSD {worst_lsd[2]:.4f} dB (note {worst_lsd[0]})")
+    assert worst[1] <= MAX_ABS, worst
+    assert worst_lsd[2] <= MAX_LSD, worst_lsd
+
+
+@pytest.mark.parametrize("workload,count", [("c2", 1024), ("c3", 256)])
+def test_whole_config_against_oracle(workload, count, torch_cuda):
+    """configs[1]: ALL 1,024 notes x 64 sources; configs[2]: ALL 256 full-flag notes -- every note compared."""
+    idx = list(range(count))
+    b, noise = _batch(workload, idx, 64)
+    ab = b.assemble(noise)
+    flat = _render_flat(ab, torch_cuda)
+    res = oracle_pool.compare(oracle_pool.workload_jobs(workload, idx, ab.infos, 64), flat)
+    _assert_all(res, workload)
+
+
+def test_long_note_grid_against_oracle(torch_cuda):
+    """configs[3]: 4 s sources stretched to 16 s, the whole grid L0 / L1 / L2 x R0 / R1 x flat / bent pitch, one batch."""
+    b = host.Batch()
+    for s in range(4):
+        f = bench_data.make_source(s, 4.0)                  # source 3 starts with a fricative
+        b.add_source(host.SourceFeatures.from_knot_pack(f, f["mask"], f["formants"], f["sr"], f["ylen"]))
+    clis = []
+    for L in (0, 1, 2):
+        for R in (0, 1):
+            for bent in (False, True):
+                j = len(clis)
+                bend = bench_data._vibrato_string(j, 16.2) if bent else "AA"
+                clis.append((j % 4, [bench_data.midi_to_name(48 + 2 * j), "100", f"L{L}" + ("R1" if R else ""), "30", "16000", "150", "200",
+                                     "100", "0", "!120", bend]))
+    for src, cli in clis:
+        b.add_note(host.NoteArgs.from_cli(src, cli))
+    ab = b.assemble(host.SeededNoise(base_seed=lambda j: 43000 + 16 * j, legacy_seed=lambda j: 311 + j))
+    assert len(clis) == 12 and all(inf["n_total"] > 700000 for inf in ab.infos)
+    flat = _render_flat(ab, torch_cuda)
+    jobs, off = [], 0
+    for j, (src, cli) in enumerate(clis):
+        n = ab.infos[j]["n_total"]
+        jobs.append((f"{cli[2]}{'+bend' if cli[10] != 'AA' else ''}", src, 4.0, cli, 43000 + 16 * j, 311 + j, off, n))
+        off += n
+    res = oracle_pool.compare(jobs, flat)
+    _assert_all(res, "c4 grid")
+
+
+def _shifted_formants_out_of_order(src_idx, flags):
+    """Does the F1-F4 warp of this note see knots that are not ascending (GOOFER.py:855-870 then runs np.interp on
+    unsorted abscissae; k_prep.cu takes its linear-scan branch)?  The synthetic sources have constant formant tracks."""
+    F = bench_data.VOWELS[src_idx % 5]
+    fl = host.parse_flags(flags)
+    nyq = 22050.0
+    xs = [0.0]
+    for k, name in enumerate(("fa", "fb", "fc", "fd")):
+        r = 1.0 + (fl.get(name) or 0) / 100.0
+        if F[k] > 50.0 and F[k] < nyq and F[k] * r > 50.0:
+            xs.append(F[k] * r)
+    xs.append(nyq)
+    return any(a > b for a, b in zip(xs, xs[1:]))
+
+
+def test_non_monotone_formant_warp(torch_cuda):
+    """fa-fd over their full legal range (+-100, SillySampler.yaml SF1-SF4) on all five vowels: most of these notes
+    push a formant past its neighbour, so np.interp sees unsorted knots (GOOFER.py:855-870) -- the branch of the
+    envelope kernel that reproduces numpy's search on unsorted abscissae (k_prep.cu, "shifted formants out of order")."""
+    rng = np.random.Generator(np.random.PCG64(777))
+    b = host.Batch()
+    for s in range(5):
+        f = bench_data.make_source(s)
+        b.add_source(host.SourceFeatures.from_knot_pack(f, f["mask"], f["formants"], f["sr"], f["ylen"]))
+    jobs, n_out_of_order = [], 0
+    clis = []
+    for i in range(80):
+        src = i % 5
+        v = rng.integers(-100, 101, size=4)
+        extra = f"g{int(rng.integers(-60, 61))}es{int(rng.integers(-100, 101))}" if i % 3 == 0 else ""
+        flags = f"fa{v[0]}fb{v[1]}fc{v[2]}fd{v[3]}" + extra
+        n_out_of_order += _shifted_formants_out_of_order(src, flags)
+        cli = [bench_data.midi_to_name(45 + i % 30), "100", flags, "0", "600", "0", "0", "100", "0", "!120", "AA"]
+        clis.append((src, cli))
+        b.add_note(host.NoteArgs.from_cli(src, cli))
+    assert n_out_of_order >= 30, n_out_of_order             # the branch is exercised, not just compiled
+    ab = b.assemble(host.SeededNoise(base_seed=lambda j: 61000 + 16 * j, legacy_seed=lambda j: 99 + j))
+    flat = _render_flat(ab, torch_cuda)
+    off = 0
+    for j, (src, cli) in enumerate(clis):
+        n = ab.infos[j]["n_total"]
+        jobs.append((j, src, 1.0, cli, 61000 + 16 * j, 99 + j, off, n))
+        off += n
+    res = oracle_pool.compare(jobs, flat)
+    _assert_all(res, f"non-monotone F-warp ({n_out_of_order} of 80 notes out of order)")
+
+
+def test_device_drawn_phases_on_the_benchmarked_batch(torch_cuda):
+    """The headline end-to-end transfer set (PCG64 states up, PCM16 down) on a c2 batch: bit-identical to the render with
+    host-supplied phases, through both entry points; the PCM is the libsndfile conversion of the float output."""
+    from goofer_b200 import cli
+    idx = list(range(96))
+    b, noise_h = _batch("c2", idx, 64, host.SeededNoise)
+    _, noise_d = _batch("c2", idx[:1], 1, host.DeviceNoise)
+    noise_d = host.DeviceNoise(base_seed=lambda j: 20000 + 16 * idx[j], legacy_seed=lambda j: 777 + idx[j])
+    ab_h, ab_d = b.assemble(noise_h), b.assemble(noise_d)
+    assert ab_d.phi.size == 1
+    ref = _render_flat(ab_h, torch_cuda)
+    got = _render_flat(ab_d, torch_cuda)
+    assert np.array_equal(ref, got)
+    ab_d.pin()
+    pcm = np.concatenate(ab_d.render_host(pcm16=True))
+    st = capi.last_stats()
+    assert st["d2h_bytes"] == 2 * ab_d.out_total and st["h2d_bytes"] < 0.1 * ab_h.phi.nbytes
+    assert np.array_equal(pcm, cli.pcm16_like_soundfile(ref))
+    f32 = np.concatenate(ab_d.render_host())
+    assert np.array_equal(f32, ref)
+
+
+def test_shard_rendered_alone_equals_whole_batch(torch_cuda):
+    """SURVEY 8e / configs[4]: a shard of the note list rendered as its own batch (what a rank or a GPU of the
+    multi-GPU entry does) yields the same bits as those notes inside the whole batch."""
+    idx = list(range(512))
+    b, noise = _batch("c5", idx, 64)
+    ab = b.assemble(noise)
+    whole = _render_flat(ab, torch_cuda)
+    outs = ab.split(whole)
+    for lo, hi in ((0, 128), (128, 384), (384, 512)):
+        sub = idx[lo:hi]
+        bs, ns = _batch("c5", sub, 64)
+        part = _render_flat(bs.assemble(ns), torch_cuda)
+        assert np.array_equal(part, np.concatenate(outs[lo:hi]))

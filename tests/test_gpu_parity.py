@@ -358,9 +358,11 @@ def _fuzz_cli(rng):
     bend = "AA" if rng.random() < 0.4 else bench_data.cents_to_pitch_string(np.round(80 * np.sin(np.arange(n_ticks) / 9.0 + rng.random())).astype(int))
     fl = []
     pool = {"g": (-100, 100), "fa": (-9, 9), "fb": (-9, 9), "fc": (-9, 9), "fd": (-9, 9), "fw": (-100, 100), "fst": (-100, 100),
-            "fsta": (-50, 50), "fstd": (-50, 50), "br": (-100, 100), "es": (-100, 100), "V": (0, 100), "B": (-100, 100),
+            "fsta": (-50, 50), "fstb": (-100, 100), "fstc": (-100, 100), "fstd": (-50, 50), "br": (-100, 100), "es": (-100, 100),
+            "V": (0, 100), "B": (-100, 100),
             "U": (-100, 100), "P": (0, 100), "t": (-50, 50), "L": (0, 2), "R": (0, 1), "FV": (0, 1), "sd": (0, 100), "st": (-100, 100),
-            "su": (0, 100), "sa": (0, 100), "vf": (-100, 100), "pd": (-100, 100), "sr": (0, 100)}
+            "su": (0, 100), "sa": (0, 100), "vf": (-100, 100), "vh": (20, 100), "vl": (0, 100), "pd": (-100, 100), "sr": (0, 100),
+            "sh": (0, 100), "sg": (0, 100), "sj": (0, 100)}
     for k in rng.choice(list(pool), size=int(rng.integers(0, 9)), replace=False):
         lo, hi = pool[k]
         fl.append(f"{k}{int(rng.integers(lo, hi + 1))}")
@@ -465,7 +467,9 @@ def test_direct_synthesize_seam(torch_cuda):
              "n_bins": 513}
     ra = ops.synthesize(knots, g["f0_a"], feat.mask, np.empty(n, dtype=np.bool_), sr, formants=forms, noise=provider(False, False))
     rb = ops.synthesize(feat.env, g["f0_b"], feat.mask, None, sr, formants=forms, noise=provider(True, True), **mg.KW_B)
-    for tag, r in (("a", ra), ("b", rb)):
+    # continuous keyword values (GooferNote.override_val): test.py:38's formant_shift / breath_strength / uv_strength ...
+    rc = ops.synthesize(knots, g["f0_a"], feat.mask, None, sr, formants=forms, noise=provider(True, True), **mg.KW_C)
+    for tag, r in (("a", ra), ("b", rb), ("c", rc)):
         for name, arr in zip(("reconstruct", "harmonic", "aper_uv", "aper_bre"), r):
             ref = g[f"{tag}_{name}"]
             assert arr.shape == ref.shape and arr.dtype == np.float32
@@ -474,7 +478,7 @@ def test_direct_synthesize_seam(torch_cuda):
     with pytest.raises(NotImplementedError):
         ops.synthesize(feat.env, g["f0_b"], feat.mask, None, sr, roughness_on=True)
     with pytest.raises(NotImplementedError):
-        ops.synthesize(feat.env, g["f0_b"], feat.mask, None, sr, formant_shift=1.0123)
+        ops.synthesize(feat.env, g["f0_b"], feat.mask, None, sr, stretch_factor=1.5)
 
 
 def test_http_server_batches_on_the_gpu(tmp_path, torch_cuda):

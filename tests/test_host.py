@@ -116,3 +116,66 @@ def test_pcm16_restates_libsndfile_clip_path():
     assert np.array_equal(got.astype(np.int64), np.array([scalar(v) for v in x]))
     x32 = x.astype(np.float32)
     assert np.array_equal(cli.pcm16_like_soundfile(x32), cli.pcm16_like_soundfile(x32.astype(np.float64)))
+
+
+def test_openutau_manifest_covers_the_flag_surface():
+    """goofer_b200.manifest: every expression maps to a flag the C ABI knows; nothing of the 34-flag surface is lost
+    besides g / B / P, which the reference's own manifest leaves to OpenUtau's built-in expressions."""
+    import yaml
+    from goofer_b200 import capi, manifest
+    doc = yaml.safe_load(manifest.render())["expressions"]
+    assert len(doc) == 31
+    assert manifest.flags() <= set(capi.FLAG_NAMES)
+    assert set(capi.FLAG_NAMES) - manifest.flags() == {"g", "B", "P"}
+    assert doc["vfhz"]["default_value"] == 50 and doc["vfsl"]["default_value"] == 15 and doc["Hvoi"]["default_value"] == 100
+    assert doc["sust"]["options"] == ["L0", "L1", "L2"]
+
+
+@pytest.mark.reference
+def test_openutau_manifest_equals_the_reference_manifest():
+    import os
+    import yaml
+    from goofer_b200 import manifest
+    ref = "/root/reference/SillySampler.yaml"
+    if not os.path.exists(ref):
+        pytest.skip("reference tree absent")
+    with open(ref) as fh:
+        assert yaml.safe_load(manifest.render()) == yaml.safe_load(fh)
+
+
+def test_batch_plan_and_cost_partition():
+    """host.Batch.plan() (planner only) equals the infos assemble() gets; shard.balanced_partition splits by cost."""
+    import bench_data
+    from goofer_b200 import shard
+    b = host.Batch()
+    for s in range(4):
+        f = bench_data.make_source(s)
+        b.add_source(host.SourceFeatures.from_knot_pack(f, f["mask"], f["formants"], f["sr"], f["ylen"]))
+    for j in range(24):
+        src, cli = bench_data.note_cli(j, "c3" if j % 3 == 0 else "c2", n_sources=4)
+        b.add_note(host.NoteArgs.from_cli(src, cli))
+    infos = b.plan()
+    assert infos == b.assemble(host.DeviceNoise()).infos
+    costs = [shard.note_cost(i) for i in infos]
+    parts = shard.balanced_partition(costs, 4)
+    loads = [sum(costs[i] for i in p) for p in parts]
+    assert sorted(i for p in parts for i in p) == list(range(24))
+    assert max(loads) - min(loads) <= max(costs)
+
+
+def test_continuous_overrides_reach_the_plan():
+    """NoteArgs.overrides -> GooferNote.override_val -> the planner's scalars (direct gf.synthesize seam)."""
+    import ctypes as C
+    from tests.plan_struct import GfNotePlan
+    f = bench_data.make_source(1)
+    b = host.Batch()
+    b.add_source(host.SourceFeatures.from_knot_pack(f, f["mask"], f["formants"], f["sr"], f["ylen"]))
+    b.add_note(host.NoteArgs(source=0, pitch="C4", flags="g1fb1sh1sr1", overrides={
+        "formant_shift": 1.0123, "F2_shift": 0.937, "f0_jitter_strength": 0.731, "volume_jitter_strength_harm": 0.33,
+        "volume_jitter_strength_breath": 0.9, "normalize": 0.6, "breath_strength": 0.05, "uv_strength": 0.4}))
+    ab = b.assemble(host.SeededNoise())
+    p = GfNotePlan()
+    assert capi.load().goofer_debug_plan(C.byref(ab.desc), 0, C.byref(p), C.sizeof(p)) == C.sizeof(p)
+    assert p.formant_shift == 1.0123 and p.F_shift[1] == 0.937 and p.F_shift[0] == 1.0 and p.any_F_shift == 1
+    assert p.f0_jitter == 1 and p.f0_jitter_strength == 0.731 and p.vol_jitter_strength == 0.33 and p.vol_jitter_strength_breath == 0.9
+    assert p.normalize == 0.6 and abs(p.breath_strength - 0.05) < 1e-8 and abs(p.uv_strength - 0.4) < 1e-7

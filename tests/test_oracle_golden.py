@@ -124,6 +124,11 @@ def test_oracle_direct_synthesize_matches_reference():
     shifts = tuple(kw.pop(f"F{i}_shift") for i in (1, 2, 3, 4))
     rb = synth.synthesize(feat.env, g["f0_b"], feat.mask, n, sr, synth_direct_noise(n, T, base, legacy, True, True),
                           formants=forms, F_shifts=shifts, **kw)
-    for tag, r in (("a", ra), ("b", rb)):
+    kc = dict(mg.KW_C)
+    shifts_c = (1.0, kc.pop("F2_shift"), 1.0, 1.0)
+    f0_c = g["f0_a"] * np.float32(kc.pop("pitch_shift"))                  # GOOFER.py:995 on the to_compute'd f32 array
+    rc = synth.synthesize(knots, f0_c, feat.mask, n, sr, synth_direct_noise(n, T, base, legacy, True, True),
+                          formants=forms, F_shifts=shifts_c, **kc)
+    for tag, r in (("a", ra), ("b", rb), ("c", rc)):
         for name, arr in zip(("reconstruct", "harmonic", "aper_uv", "aper_bre"), r):
             assert np.array_equal(np.asarray(arr, dtype=np.float32), g[f"{tag}_{name}"]), (tag, name)

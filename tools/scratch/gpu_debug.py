@@ -1,7 +1,7 @@
 """GPU bring-up report: per case, max-abs error of the render and of the main-pass taps against the
 oracle.  `python tests/gpu_debug.py [case ...]` on the GPU box; prints a table."""
 import sys, os, time
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import numpy as np
 from tests import cases
 from goofer_b200 import host, capi

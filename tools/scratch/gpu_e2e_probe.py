@@ -1,6 +1,6 @@
 """GPU bring-up probe: e2e time of goofer_render_batch_host vs chunk size, and raw pinned copy bandwidth."""
 import os, sys, time, argparse
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import torch
 import bench
 from goofer_b200 import capi
