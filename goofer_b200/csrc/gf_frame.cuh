@@ -82,6 +82,32 @@ __device__ __forceinline__ void gf_cta_fft512_multi(float2 *bufs, const float2 *
     __syncthreads();
 }
 
+// NQ inverse transforms owned by ONE 64-thread group (buffers `stride` float2 apart), advanced through each pass
+// together so that the group meets five times for the whole batch; the caller provides the barrier that publishes the
+// result to the rest of the CTA.
+template <int NQ>
+__device__ __forceinline__ void gf_group_ifft512(float2 *buf0, int stride, const float2 *twl, int group, int j)
+{
+    float2 v[NQ][8];
+#pragma unroll
+    for (int q = 0; q < NQ; ++q) gf_fft_pass_load<true, 1>(j, buf0 + (size_t)q * stride, twl, v[q]);
+    gf_lane_sync(group);
+#pragma unroll
+    for (int q = 0; q < NQ; ++q) gf_fft_pass_store<1>(j, buf0 + (size_t)q * stride, v[q]);
+    gf_lane_sync(group);
+#pragma unroll
+    for (int q = 0; q < NQ; ++q) gf_fft_pass_load<true, 8>(j, buf0 + (size_t)q * stride, twl, v[q]);
+    gf_lane_sync(group);
+#pragma unroll
+    for (int q = 0; q < NQ; ++q) gf_fft_pass_store<8>(j, buf0 + (size_t)q * stride, v[q]);
+    gf_lane_sync(group);
+#pragma unroll
+    for (int q = 0; q < NQ; ++q) gf_fft_pass_load<true, 64>(j, buf0 + (size_t)q * stride, twl, v[q]);
+    gf_lane_sync(group);
+#pragma unroll
+    for (int q = 0; q < NQ; ++q) gf_fft_pass_store<64>(j, buf0 + (size_t)q * stride, v[q]);
+}
+
 // frame `t` of the reflect-padded signal x (length n), sqrt-Hann windowed, packed as
 // z[m] = x[2m] + i x[2m+1] into a padded FFT buffer.  GOOFER.py:355-369
 template <typename LoadFn>
@@ -94,51 +120,6 @@ __device__ __forceinline__ void gf_load_frames(float2 *bufs, int t0, int nf, int
         const float x0 = load(inside ? p : gf_reflect(p, n)) * win[2 * m];
         const float x1 = load(inside ? p + 1 : gf_reflect(p + 1, n)) * win[2 * m + 1];
         bufs[(size_t)f * GF_FFT_BUF + gf_fpad(m)] = make_float2(x0, x1);
-    }
-}
-
-// same for exactly four frames and 256 threads: the sixteen loads of a thread are issued before the first
-// windowed value is stored (the compiler cannot hoist generic loads over shared-memory stores on its own)
-template <typename LoadFn>
-__device__ __forceinline__ void gf_load_frames4(float2 *bufs, int t0, int n, const float *win, LoadFn load)
-{
-    float x0[8], x1[8];
-#pragma unroll
-    for (int it = 0; it < 8; ++it) {
-        const int idx = threadIdx.x + 256 * it;
-        const int f = idx >> 9, m = idx & 511;
-        const int p = GF_HOP * (t0 + f) + 2 * m - GF_NFFT / 2;
-        const bool inside = (p >= 0) && (p + 1 < n);
-        x0[it] = load(inside ? p : gf_reflect(p, n));
-        x1[it] = load(inside ? p + 1 : gf_reflect(p + 1, n));
-    }
-#pragma unroll
-    for (int it = 0; it < 8; ++it) {
-        const int idx = threadIdx.x + 256 * it;
-        const int f = idx >> 9, m = idx & 511;
-        bufs[(size_t)f * GF_FFT_BUF + gf_fpad(m)] = make_float2(x0[it] * win[2 * m], x1[it] * win[2 * m + 1]);
-    }
-}
-
-// the same for a plain f32 signal in global memory (8-byte aligned base): sample pairs and window pairs as one 8-byte
-// load each away from the reflected ends -- half the load instructions of the generic version
-__device__ __forceinline__ void gf_load_frames4_f32(float2 *bufs, int t0, int n, const float *__restrict__ win, const float *__restrict__ x)
-{
-    float2 v[8];
-#pragma unroll
-    for (int it = 0; it < 8; ++it) {
-        const int idx = threadIdx.x + 256 * it;
-        const int f = idx >> 9, m = idx & 511;
-        const int p = GF_HOP * (t0 + f) + 2 * m - GF_NFFT / 2;      // even
-        if ((p >= 0) && (p + 1 < n)) v[it] = *reinterpret_cast<const float2 *>(x + p);
-        else v[it] = make_float2(x[gf_reflect(p, n)], x[gf_reflect(p + 1, n)]);
-    }
-#pragma unroll
-    for (int it = 0; it < 8; ++it) {
-        const int idx = threadIdx.x + 256 * it;
-        const int f = idx >> 9, m = idx & 511;
-        const float2 w = *reinterpret_cast<const float2 *>(win + 2 * m);
-        bufs[(size_t)f * GF_FFT_BUF + gf_fpad(m)] = make_float2(v[it].x * w.x, v[it].y * w.y);
     }
 }
 

@@ -140,7 +140,7 @@ static int gf_render_batch_host_impl(const GooferBatch *b)
     const bool trace = getenv("GOOFER_HOST_TRACE") != nullptr;
     auto now_ms = []() { timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return 1e3 * (double)ts.tv_sec + 1e-6 * (double)ts.tv_nsec; };
     const double h0 = trace ? now_ms() : 0.0;
-    double h_first_copy = 0.0, h_enqueued = 0.0;
+    double h_first_copy = 0.0, h_enqueued = 0.0, h_uploads = 0.0, h_sized = 0.0;
     static thread_local cudaEvent_t ev_t0 = nullptr, ev_d2h[64] = {nullptr};
     if (trace) {
         if (!ev_t0) cudaEventCreate(&ev_t0);
@@ -294,9 +294,23 @@ static int gf_render_batch_host_impl(const GooferBatch *b)
             // parts of about 45 MB of noise phases each (1,024 one-second notes: 8 parts; 96 sixteen-second notes: 12),
             // cut where the cumulative phase bytes cross k / parts of the total, at most 16, at least 2 above 8 MB
             std::vector<int64_t> cum(nn + 1, 0);
-            for (int i = 0; i < nn; ++i) cum[i + 1] = cum[i] + (int64_t)plans[i].n_passes * GF_NBINS * plans[i].T_out * 4;
+            int64_t up_total = 0;                              // phase bytes that really cross PCIe (not the device-drawn slots)
+            for (int i = 0; i < nn; ++i) {
+                const GfNotePlan &p = plans[i];
+                for (int k = 0; k < p.n_passes; ++k)
+                    if (!((p.phi_rng_mask >> p.pass_kind[k]) & 1u)) up_total += (int64_t)GF_NBINS * p.T_out * 4;
+            }
+            const bool upload_bound = up_total >= (8 << 20);
+            // cut by uploaded phase bytes when phases are uploaded, else by the bytes that go back (the parts then only
+            // exist to start the download early: with device-drawn phases and PCM16 output a 1,024-note batch returns
+            // 90 MB, four parts; every part's frame launch should still fill the GPU -- 128-note parts ran the
+            // frame / peak / mix tail 45 % slower than one launch, measured on B200)
+            const int64_t per_sample_down = (b->out ? 4 : 0) + (b->out_pcm16 ? 2 : 0) + (b->tap_harm ? 4 : 0) + (b->tap_uv ? 4 : 0) + (b->tap_bre ? 4 : 0);
+            for (int i = 0; i < nn; ++i)
+                cum[i + 1] = cum[i] + (upload_bound ? (int64_t)plans[i].n_passes * GF_NBINS * plans[i].T_out * 4 : (int64_t)plans[i].n_total * per_sample_down);
             const int64_t total = cum[nn];
-            int np = (int)std::min<int64_t>(16, (total + (22 << 20)) / (45 << 20));
+            int np = upload_bound ? (int)std::min<int64_t>(16, (total + (22 << 20)) / (45 << 20))
+                                  : (int)std::min<int64_t>(8, (total + (12 << 20)) / (24 << 20));
             if (np < 2 && total >= (8 << 20)) np = 2;
             // notes with post-FX / pitch dynamics run a dozen small kernels and uploads per part: two parts at most
             // (256 all-flag notes: 19.6 ms in 2 parts, 25.5 ms in 8)
@@ -314,7 +328,9 @@ static int gf_render_batch_host_impl(const GooferBatch *b)
         ends.push_back(nn);
     }
     const int n_chunks = (int)ends.size();
+    if (trace) h_uploads = now_ms();
     const size_t want = gf_workspace_bytes_planned(&db, plans, 0);
+    if (trace) h_sized = now_ms();
     if ((rc = gf_hc_reserve(&g_hc.ws, &g_hc.ws_cap, want)) != GOOFER_OK) return rc;
     while ((int)g_hc.ev.size() < 2 * n_chunks + 1) {
         cudaEvent_t e;
@@ -399,9 +415,9 @@ static int gf_render_batch_host_impl(const GooferBatch *b)
         const double h_done = now_ms();
         float small = 0;
         cudaEventElapsedTime(&small, ev_t0, g_hc.ev[2 * n_chunks]);
-        fprintf(stderr, "[host trace] host: first copy issued at %.3f ms, everything enqueued at %.3f ms, synchronised at %.3f ms; "
-                        "device: small inputs in at %.3f ms after the H2D stream started\n",
-                h_first_copy - h0, h_enqueued - h0, h_done - h0, small);
+        fprintf(stderr, "[host trace] host: first copy issued at %.3f ms, source uploads issued at %.3f ms, workspace sized at %.3f ms, everything "
+                        "enqueued at %.3f ms, synchronised at %.3f ms; device: small inputs in at %.3f ms after the H2D stream started\n",
+                h_first_copy - h0, h_uploads - h0, h_sized - h0, h_enqueued - h0, h_done - h0, small);
         for (int c = 0; c < n_chunks; ++c) {
             float a = 0, bq = 0, dq = 0;
             cudaEventElapsedTime(&a, ev_t0, g_hc.ev[2 * c]);

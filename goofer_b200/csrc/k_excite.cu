@@ -715,10 +715,12 @@ void gf_launch_pulse(const GfPassDev *passes, const GfPassScal *scal, int n_pass
 // Noise phases on the device: the stream numpy's Generator(PCG64).uniform(0, 2 pi, (513, T)).astype(float32) draws
 // (GOOFER.py:1151-1152), bit for bit.  PCG64 = 128-bit LCG (multiplier 0x2360ED051FC65DA44385DF649FCCF645, per-stream
 // odd increment), output XSL-RR 128 -> 64 of the state AFTER the step; next_double = (u64 >> 11) * 2^-53; uniform =
-// low + (high - low) * next_double with low = 0.  Element e of the row-major (513, T) array is the (e + 1)-th draw:
-// every thread jumps the LCG ahead to its first element (O(log e) 128-bit multiply-adds) and then strides by 256.
+// low + (high - low) * next_double with low = 0.  Element e = k T + t of the row-major (513, T) array is the (e + 1)-th
+// draw.  One thread per bin row k: it jumps the LCG ahead to the row's first element (O(log e) 128-bit multiply-adds,
+// once) and then steps through the row's T frames, one plain LCG step each.  The output is FRAME-MAJOR (T, GF_ENVS_LD)
+// -- a warp stores 32 neighbouring bins of one frame, 128 bytes -- which is how the frame kernel reads it.
 // ------------------------------------------------------------------------------------------------
-struct GfPhiJob { float *dst; int total; int pad; unsigned long long s_hi, s_lo, i_hi, i_lo; };
+struct GfPhiJob { float *dst; int T; int pad; unsigned long long s_hi, s_lo, i_hi, i_lo; };
 
 typedef unsigned __int128 gf_u128;
 
@@ -734,34 +736,33 @@ __device__ __forceinline__ void gf_lcg_jump(gf_u128 m, gf_u128 c, unsigned long 
     }
 }
 
-__global__ void __launch_bounds__(256) gf_phi_kernel(const GfPhiJob *__restrict__ jobs)
+#define GF_PHI_THREADS 128
+__global__ void __launch_bounds__(GF_PHI_THREADS) gf_phi_kernel(const GfPhiJob *__restrict__ jobs)
 {
     const GfPhiJob jb = jobs[blockIdx.y];
-    const int per = (((jb.total + (int)gridDim.x - 1) / (int)gridDim.x) + 255) & ~255;
-    const int first = blockIdx.x * per, end = min(jb.total, first + per);
-    if (first >= jb.total) return;
+    const int k = blockIdx.x * GF_PHI_THREADS + threadIdx.x;             // bin row
+    if (k >= GF_NBINS) return;
     const gf_u128 MULT = ((gf_u128)0x2360ED051FC65DA4ull << 64) | (gf_u128)0x4385DF649FCCF645ull;
     const gf_u128 inc = ((gf_u128)jb.i_hi << 64) | (gf_u128)jb.i_lo;
     gf_u128 state = ((gf_u128)jb.s_hi << 64) | (gf_u128)jb.s_lo;
     gf_u128 am, ap;
-    gf_lcg_jump(MULT, inc, (unsigned long long)(first + (int)threadIdx.x) + 1ull, am, ap);       // state after the step of the first element
+    gf_lcg_jump(MULT, inc, (unsigned long long)k * (unsigned long long)jb.T + 1ull, am, ap);   // state after the step of the row's first element
     state = am * state + ap;
-    gf_u128 m256, p256;
-    gf_lcg_jump(MULT, inc, 256ull, m256, p256);
-    for (int e = first + (int)threadIdx.x; e < end; e += 256) {
+    float *dst = jb.dst + k;
+    for (int t = 0; t < jb.T; ++t) {
         const unsigned long long hi = (unsigned long long)(state >> 64), lo = (unsigned long long)state;
         const unsigned rot = (unsigned)(hi >> 58);                         // state >> 122
         const unsigned long long x = hi ^ lo;
         const unsigned long long r = (x >> rot) | (x << ((64u - rot) & 63u));
         const double d = __dmul_rn((double)(r >> 11), 1.0 / 9007199254740992.0);
-        jb.dst[e] = (float)__dmul_rn(6.283185307179586, d);
-        state = state * m256 + p256;
+        dst[(size_t)t * GF_ENVS_LD] = (float)__dmul_rn(6.283185307179586, d);
+        state = state * MULT + inc;
     }
 }
 
-void gf_launch_phi(const GfPhiJob *jobs, int n_jobs, int max_total, cudaStream_t st)
+void gf_launch_phi(const GfPhiJob *jobs, int n_jobs, int max_T, cudaStream_t st)
 {
-    if (n_jobs <= 0 || max_total <= 0) return;
-    dim3 grid(std::max(1, std::min(16, (max_total + 4095) / 4096)), n_jobs);
-    gf_phi_kernel<<<grid, 256, 0, st>>>(jobs);
+    if (n_jobs <= 0 || max_T <= 0) return;
+    dim3 grid((GF_NBINS + GF_PHI_THREADS - 1) / GF_PHI_THREADS, n_jobs);
+    gf_phi_kernel<<<grid, GF_PHI_THREADS, 0, st>>>(jobs);
 }

@@ -135,11 +135,11 @@ __device__ __forceinline__ void gf_shape_mid(GfFrameSmem &sm, int f, float f0f, 
 // pushed back through the inverse of the blur (taps q1, q2 = differences of IDFT(1 / G), decaying 7.4 x per bin,
 // < 3e-9 at 12 bins) they become imaginary additions to bins 1..12 and 500..511 of the pre-blur spectrum.  In exact
 // arithmetic the result equals the reference's (checked in numpy to 2e-14); rounding differs at the 1e-7 level.
-__device__ __forceinline__ void gf_blur_edges(GfFrameSmem &sm, int nf, const int *voiced, const float2 *__restrict__ tw1024)
+// Called by the 64 threads that own frame f (thread j of the group): j = 2 (k - 1) + s for bin k = 1..12, stream s.
+__device__ __forceinline__ void gf_blur_edges(GfFrameSmem &sm, int f, int j, const float2 *__restrict__ tw1024)
 {
-    const int tid = threadIdx.x;
-    const int k = 1 + tid % GF_BLUR_K, rest = tid / GF_BLUR_K, s = rest & 1, f = rest >> 1;
-    if (f >= nf || !voiced[f]) return;
+    if (j >= 2 * GF_BLUR_K) return;
+    const int k = 1 + (j >> 1), s = j & 1;
     const float *e = sm.edge[s][f];
     const float g0 = (float)d_tab.g05[0], g1 = (float)d_tab.g05[1];
     const float p1 = 2.0f * g0 * e[1] + g1 * e[0], p2 = g0 * e[0];
@@ -225,7 +225,26 @@ __device__ __forceinline__ void gf_ola_round(float (*carry)[GF_HOP], const float
     for (int m = 0; m < 3; ++m) carry[m][r] = acc[NF + m];
 }
 
+// Excitation sample i of the (note, pass): pulse train, plus the growl layer when the note has one
+// (GOOFER.py:724-736: sub *= mask; sub /= max; sub *= weight; pulse (f32) += sub (f64))
+struct GfExcite {
+    const float *pulse, *sub, *vm;
+    double sub_scale;
+    __device__ __forceinline__ float at(int i) const
+    {
+        return sub ? (float)((double)pulse[i] + ((double)sub[i] * (double)vm[i]) * sub_scale) : pulse[i];
+    }
+};
+
 // work item: x = pass index (into the wave's pass arrays), y = first owned block, z = block count
+//
+// A round = four consecutive frames.  The 64 threads of group g = tid / 64 own frame t0 + g from the excitation samples
+// to its inverse transforms -- framing straight into the registers of the first radix-8 pass, forward FFT, spectral
+// shaping of ITS frame (bins j, j + 64, j + 128, j + 192 and their mirrors: coalesced envelope rows, conflict-free
+// shared-memory runs), blur edge terms, two or three inverse FFTs -- synchronising only with each other (named
+// barriers of 64 threads).  The CTA meets twice per round, around the overlap-add, where thread r sums column r of
+// the four frames.  (Round 1 framed through shared memory and shaped (bin, frame)-interleaved: six CTA-wide barriers
+// per round, a framing store + load per sample, and the groups in lock step.)
 __global__ void __launch_bounds__(GF_FRAME_THREADS, GF_FRAME_CTAS)
 gf_frame_kernel(const int4 *__restrict__ work, const GfPassDev *__restrict__ passes, GfPassScal *scal,
                 const GfNoteDev *__restrict__ notes, const GfNotePlan *__restrict__ plans)
@@ -239,6 +258,7 @@ gf_frame_kernel(const int4 *__restrict__ work, const GfPassDev *__restrict__ pas
     const int n = ps.n_total, T = ps.T_out;
     const int b0 = wk.y, nb = wk.z;
     const int tid = threadIdx.x;
+    const int g = tid >> 6, j = tid & 63;
 
     for (int i = tid; i < GF_TWL_N; i += blockDim.x) sm.twl[i] = d_tab.twl[i];
     const float *__restrict__ win = d_tab.win;
@@ -247,37 +267,41 @@ gf_frame_kernel(const int4 *__restrict__ work, const GfPassDev *__restrict__ pas
 
     const int t_begin = max(0, b0 - 3), t_end = min(T - 1, b0 + nb - 1);
     const int n_f0 = (n + GF_HOP - 1) / GF_HOP;          // len(f0[::256])
-    const float *pulse = ps.pulse;
-    const float *sub = ps.sub;
-    const float *vm = nd.vm;
-    double sub_scale = 0.0;
-    if (sub) {
+    GfExcite ex;
+    ex.pulse = ps.pulse; ex.sub = ps.sub; ex.vm = nd.vm; ex.sub_scale = 0.0;
+    if (ex.sub) {
         const float mx = __uint_as_float(scal[wk.x].submax_bits);
-        sub_scale = ((double)mx > 1e-6) ? pl.subharm_weight / (double)mx : pl.subharm_weight;
+        ex.sub_scale = ((double)mx > 1e-6) ? pl.subharm_weight / (double)mx : pl.subharm_weight;
     }
-    // global operands of a round -> L2, no registers held (every one of them is read exactly once, so the shaping loads
-    // would otherwise wait on HBM): envelope rows of frames tn .. tn+3 (65 lines each), the 513 phase rows (one 16-byte
-    // piece per row and round: the 128-byte line around it), the new excitation samples
-    auto prefetch_round = [&](int tn) {
+    // phases: (513, T) rows as numpy draws them (host-supplied), or frame-major (T, GF_ENVS_LD) when gf_phi_kernel made them
+    const float *__restrict__ phi = ps.phi;
+    const size_t phi_bin = ps.phi_frame_major ? (size_t)1 : (size_t)T, phi_frm = ps.phi_frame_major ? (size_t)GF_ENVS_LD : (size_t)1;
+    // global operands of a group's next frame -> L2, no registers held (each is read exactly once): the two envelope
+    // rows (17 lines each), the phase row (17 lines frame-major; one line per bin otherwise), the new excitation samples
+    auto prefetch_frame = [&](int t) {
         auto pf = [](const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); };
-        if (tid < 66) pf(reinterpret_cast<const char *>(nd.envF + (size_t)tn * GF_ENVS_LD) + 128 * tid);
-        else if (tid < 132) pf(reinterpret_cast<const char *>(nd.envN + (size_t)tn * GF_ENVS_LD) + 128 * (tid - 66));
-        else if (tid < 148) {
-            const int i = min(n - 1, GF_HOP * tn + GF_NFFT / 2 - GF_HOP + 32 * (tid - 132));
-            if (i >= 0) pf(pulse + i);
+        if (j < 17) {
+            pf(reinterpret_cast<const char *>(nd.envF + (size_t)t * GF_ENVS_LD) + 128 * j);
+            pf(reinterpret_cast<const char *>(nd.envN + (size_t)t * GF_ENVS_LD) + 128 * j);
+            if (ps.phi_frame_major) pf(reinterpret_cast<const char *>(phi + (size_t)t * GF_ENVS_LD) + 128 * j);
+        } else if (j < 25) {
+            const int i = min(n - 1, GF_HOP * t + GF_NFFT / 2 - GF_HOP + 32 * (j - 17));
+            if (i >= 0) pf(ex.pulse + i);
         }
-        pf(ps.phi + (size_t)tid * T + tn);
-        pf(ps.phi + (size_t)(tid + 256) * T + tn);
-        if (tid == 0) pf(ps.phi + (size_t)512 * T + tn);
+        if (!ps.phi_frame_major && (t & 3) == 0) {            // a 128-byte line of a phase row serves 32 frames: touch it every fourth
+#pragma unroll
+            for (int m = 0; m < 8; ++m) pf(phi + (size_t)(j + 64 * m) * T + t);
+            if (j == 0) pf(phi + (size_t)512 * T + t);
+        }
     };
 #ifndef GF_NO_PREFETCH
-    if (t_begin <= t_end) prefetch_round(t_begin);           // the first round's operands travel while the tables are staged
+    if (t_begin + g <= t_end) prefetch_frame(t_begin + g);    // the first round's operands travel while the tables are staged
 #endif
     for (int q = tid; q <= t_end - t_begin; q += blockDim.x) {
         const int t = t_begin + q;
         const int fi = min(t, n_f0 - 1) * GF_HOP;             // f0[::hop] edge-padded   GOOFER.py:1104-1106
         sm.f0fr[q] = ps.f0[fi];
-        sm.voiced[q] = ps.mask_ones ? 1 : (vm[fi] > 0.0f);    // GOOFER.py:1132-1136
+        sm.voiced[q] = ps.mask_ones ? 1 : (nd.vm[fi] > 0.0f);    // GOOFER.py:1132-1136
         // samples of frame t live in hop blocks t-2 .. t+1 of the output
         int one = 1;
         const int nblk = (n + GF_HOP - 1) / GF_HOP;
@@ -296,81 +320,83 @@ gf_frame_kernel(const int4 *__restrict__ work, const GfPassDev *__restrict__ pas
 
     for (int t0 = t_begin; t0 <= t_end; t0 += GF_RND) {
         const int nf = min(GF_RND, t_end - t0 + 1);
-        // ---- 1. frame the excitation (pulse + growl layer) ----
-        if (sub) {
-            gf_load_frames(&sm.z[2][0][0], t0, nf, n, win, [&](int i) {
-                // GOOFER.py:724-736: sub *= mask; sub /= max; sub *= weight; pulse (f32) += sub (f64)
-                return (float)((double)pulse[i] + ((double)sub[i] * (double)vm[i]) * sub_scale);
-            });
-        } else if (nf == GF_RND) {
-            gf_load_frames4_f32(&sm.z[2][0][0], t0, n, win, pulse);
-        } else {
-            gf_load_frames(&sm.z[2][0][0], t0, nf, n, win, [&](int i) { return pulse[i]; });
-        }
-        __syncthreads();
-        // ---- next round's global operands -> L2 ----
-#ifndef GF_NO_PREFETCH
-        if (t0 + GF_RND <= t_end) prefetch_round(t0 + GF_RND);
-#endif
-        // ---- 2. forward FFT ----
-        gf_cta_fft512<false>(&sm.z[2][0][0], nf, sm.twl);
         const int m0r = t0 - t_begin;                         // this round's first entry of the per-frame tables
         bool uv_on = false;                                   // uniform: the round computes the unvoiced stream unless every frame may skip it
         for (int q = 0; q < nf; ++q) uv_on = uv_on || (sm.uvskip[m0r + q] == 0);
-        // ---- 3. shaping, per bin pair (k, 512 - k); bin 256 pairs with itself and goes to threads 0..nf-1 ----
-        if (nf == GF_RND) {
-            // item m of this thread: k = (tid >> 2) + 64 m, frame f = tid & 3.  All global operands of the four
-            // items of a batch are requested up front (12 loads in flight per thread) before any of them is consumed.
-            const int f = tid & 3, t = t0 + f;
-            const float *eF = nd.envF + (size_t)t * GF_ENVS_LD, *eN = nd.envN + (size_t)t * GF_ENVS_LD;
-            const float *ph = ps.phi + t;
+        if (g < nf) {
+            const int f = g, t = t0 + g;
+            float2 *zf = &sm.z[2][f][0];
+            // ---- 1. frame the excitation into the registers of the first radix-8 pass (element m = j + 64 r of the packed
+            //         sequence z[m] = x[2m] + i x[2m+1]; numpy 'reflect' padding; sqrt-Hann)   GOOFER.py:355-369 ----
+            float2 v[8];
+            {
+                const int p0 = GF_HOP * t + 2 * j - GF_NFFT / 2;               // even
+                if (!ex.sub && p0 >= 0 && p0 + 2 * 64 * 7 + 1 < n) {
+#pragma unroll
+                    for (int r = 0; r < 8; ++r) v[r] = *reinterpret_cast<const float2 *>(ex.pulse + p0 + 128 * r);
+                } else {
+#pragma unroll
+                    for (int r = 0; r < 8; ++r) {
+                        const int p = p0 + 128 * r;
+                        const bool inside = (p >= 0) && (p + 1 < n);
+                        v[r].x = ex.at(inside ? p : gf_reflect(p, n));
+                        v[r].y = ex.at(inside ? p + 1 : gf_reflect(p + 1, n));
+                    }
+                }
+#pragma unroll
+                for (int r = 0; r < 8; ++r) {
+                    const float2 w = *reinterpret_cast<const float2 *>(win + 2 * j + 128 * r);
+                    v[r].x *= w.x; v[r].y *= w.y;
+                }
+            }
+#ifndef GF_NO_PREFETCH
+            if (t + GF_RND <= t_end) prefetch_frame(t + GF_RND);
+#endif
+            // ---- 2. forward FFT of the group's frame ----
+            gf_dft8<false>(v);
+            gf_fft_pass_store<1>(j, zf, v);
+            gf_lane_sync(g);
+            gf_fft_pass_load<false, 8>(j, zf, sm.twl, v);
+            gf_lane_sync(g);
+            gf_fft_pass_store<8>(j, zf, v);
+            gf_lane_sync(g);
+            gf_fft_pass_load<false, 64>(j, zf, sm.twl, v);
+            gf_lane_sync(g);
+            gf_fft_pass_store<64>(j, zf, v);
+            gf_lane_sync(g);
+            // ---- 3. shaping, per bin pair (k, 512 - k), k = j + 64 m; bin 256 pairs with itself (thread 0 of the group) ----
+            {
+                const float *eF = nd.envF + (size_t)t * GF_ENVS_LD, *eN = nd.envN + (size_t)t * GF_ENVS_LD;
+                const float *ph = phi + (size_t)t * phi_frm;
+                const float f0f = sm.f0fr[m0r + f];
+                const bool vo = sm.voiced[m0r + f] != 0;
 #ifndef GF_SHAPE_BATCH
 #define GF_SHAPE_BATCH 2              // bin pairs whose global operands are requested together (6 loads each)
 #endif
-            const float f0f = sm.f0fr[m0r + f];
-            const bool vo = sm.voiced[m0r + f] != 0;
 #pragma unroll
-            for (int m0 = 0; m0 < 4; m0 += GF_SHAPE_BATCH) {
-                GfShapeIn in[GF_SHAPE_BATCH];
+                for (int mb = 0; mb < 4; mb += GF_SHAPE_BATCH) {
+                    GfShapeIn in[GF_SHAPE_BATCH];
 #pragma unroll
-                for (int m = 0; m < GF_SHAPE_BATCH; ++m) {
-                    const int k = (tid >> 2) + 64 * (m0 + m), km = 512 - k;
-                    in[m].ef[0] = eF[k];  in[m].ef[1] = eF[km];
-                    in[m].en[0] = eN[k];  in[m].en[1] = eN[km];
-                    in[m].ph[0] = ph[(size_t)k * T];  in[m].ph[1] = ph[(size_t)km * T];
+                    for (int m = 0; m < GF_SHAPE_BATCH; ++m) {
+                        const int k = j + 64 * (mb + m), km = 512 - k;
+                        in[m].ef[0] = eF[k];  in[m].ef[1] = eF[km];
+                        in[m].en[0] = eN[k];  in[m].en[1] = eN[km];
+                        in[m].ph[0] = ph[(size_t)k * phi_bin];  in[m].ph[1] = ph[(size_t)km * phi_bin];
+                    }
+#pragma unroll
+                    for (int m = 0; m < GF_SHAPE_BATCH; ++m) gf_shape_pair(sm, j + 64 * (mb + m), f, f0f, vo, uv_on, in[m], tw1024, local_max);
                 }
-#pragma unroll
-                for (int m = 0; m < GF_SHAPE_BATCH; ++m) gf_shape_pair(sm, (tid >> 2) + 64 * (m0 + m), f, f0f, vo, uv_on, in[m], tw1024, local_max);
+                if (j == 0) gf_shape_mid(sm, f, f0f, vo, uv_on, eF[256], eN[256], ph[(size_t)256 * phi_bin], tw1024, local_max);
+                gf_lane_sync(g);
+                // ---- 4. voiced frames: edge terms of the brightness blur (the blur itself rides on the synthesis window) ----
+                if (vo) gf_blur_edges(sm, f, j, tw1024);      // uniform over the group
+                gf_lane_sync(g);
             }
-        } else {
-            for (int idx = tid; idx < nf * 256; idx += blockDim.x) {
-                const int k = idx / nf, f = idx - k * nf, km = 512 - k, t = t0 + f;
-                const float *eF = nd.envF + (size_t)t * GF_ENVS_LD, *eN = nd.envN + (size_t)t * GF_ENVS_LD;
-                const float *ph = ps.phi + t;
-                GfShapeIn in;
-                in.ef[0] = eF[k];  in.ef[1] = eF[km];
-                in.en[0] = eN[k];  in.en[1] = eN[km];
-                in.ph[0] = ph[(size_t)k * T];  in.ph[1] = ph[(size_t)km * T];
-                gf_shape_pair(sm, k, f, sm.f0fr[m0r + f], sm.voiced[m0r + f] != 0, uv_on, in, tw1024, local_max);
-            }
-        }
-        if (tid < nf) {
-            const int f = tid, t = t0 + f;
-            gf_shape_mid(sm, f, sm.f0fr[m0r + f], sm.voiced[m0r + f] != 0, uv_on, nd.envF[(size_t)t * GF_ENVS_LD + 256],
-                         nd.envN[(size_t)t * GF_ENVS_LD + 256], ps.phi[(size_t)256 * T + t], tw1024, local_max);
+            // ---- 5. inverse FFTs of the group's frame: harmonic, breath (, unvoiced), advanced pass by pass together ----
+            if (uv_on) gf_group_ifft512<3>(&sm.z[0][f][0], GF_RND * GF_FFT_BUF, sm.twl, g, j);
+            else gf_group_ifft512<2>(&sm.z[0][f][0], GF_RND * GF_FFT_BUF, sm.twl, g, j);
         }
         __syncthreads();
-        // ---- 4. voiced frames: edge terms of the brightness blur (the blur itself rides on the synthesis window) ----
-        gf_blur_edges(sm, nf, sm.voiced + m0r, tw1024);
-        __syncthreads();
-        // ---- 5. inverse FFTs (stream-major: transform q = s * GF_RND + f) ----
-        const int n_streams = uv_on ? 3 : 2;
-        if (nf == GF_RND) {
-            if (uv_on) gf_cta_fft512_multi<true, 3>(&sm.z[0][0][0], sm.twl);
-            else gf_cta_fft512_multi<true, 2>(&sm.z[0][0][0], sm.twl);
-        } else {
-            for (int s = 0; s < n_streams; ++s) gf_cta_fft512<true>(&sm.z[s][0][0], nf, sm.twl);
-        }
         // ---- 6. overlap-add + emit: thread `tid` owns column tid of every hop block ----
         {
             float *outs[3] = {ps.harm, ps.bre, ps.uv};

@@ -151,7 +151,7 @@ def test_device_drawn_phases_on_the_benchmarked_batch(torch_cuda):
     ab_d.pin()
     pcm = np.concatenate(ab_d.render_host(pcm16=True))
     st = capi.last_stats()
-    assert st["d2h_bytes"] == 2 * ab_d.out_total and st["h2d_bytes"] < 0.1 * ab_h.phi.nbytes
+    assert st["d2h_bytes"] == 2 * ab_d.out_total and st["h2d_bytes"] < ab_h.phi.nbytes // 2      # 64 sources up (16 MB), no phases
     assert np.array_equal(pcm, cli.pcm16_like_soundfile(ref))
     f32 = np.concatenate(ab_d.render_host())
     assert np.array_equal(f32, ref)
