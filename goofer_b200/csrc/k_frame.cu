@@ -154,55 +154,51 @@ __device__ __forceinline__ void gf_blur_edges(GfFrameSmem &sm, int f, int j, con
     b = gf_cadd(b, Zm);
 }
 
-// One round of the windowed overlap-add for one stream (GOOFER.py:372-390, 402-411).  Frames t0 .. t0+NF-1 sit
-// in `bufs` as unnormalised inverse-FFT output (scale 1/512).  Thread `tid` owns sample column tid of every hop
-// block: it adds the NF x 4 windowed contributions in ascending frame order (like _overlap_add), divides the
+// One round of the windowed overlap-add for one stream (GOOFER.py:372-390, 402-411).  Frames t0 .. t0+nf-1 (nf <= 4)
+// sit in `bufs` as unnormalised inverse-FFT output (scale 1/512).  Thread `tid` owns sample column tid of every hop
+// block: it adds the nf x 4 windowed contributions in ascending frame order (like _overlap_add), divides the
 // finished blocks by their win^2 sum, writes them, and carries the three unfinished blocks to the next round.
-template <int NF>
-__device__ __forceinline__ void gf_ola_round(float (*carry)[GF_HOP], const float2 *bufs, const float *__restrict__ win,
-                                             int t0, int T, int n_out, float *__restrict__ out, int b0, int nb, bool last,
+// One body for every stream and every round length (the stream loop of the caller is NOT unrolled, a short last
+// round predicates its missing frames off): round 1 instantiated this 12 times, 3,600 of the kernel's 8,000
+// instructions, and the hot loop no longer fitted the instruction cache.
+__device__ __forceinline__ void gf_ola_round(float (*carry)[GF_HOP], const float2 *bufs, const float (&w)[4], const float (&wg)[4],
+                                             int t0, int nf, int T, int n_out, float *__restrict__ out, int b0, int nb, bool last,
                                              bool no_input, const unsigned char *blk_dead /* indexed by b - b0 */, bool all_dead, float ws_full,
                                              const int *voiced /* per frame: use the blur-carrying window winG; NULL: never */,
                                              float rcp_full /* RN(1 / ws_full), or 0 when the exact short division does not apply */)
 {
     const int r = threadIdx.x;
-    float acc[NF + 3];
+    float acc[GF_RND + 3];
 #pragma unroll
     for (int m = 0; m < 3; ++m) acc[m] = carry[m][r];
 #pragma unroll
-    for (int m = 3; m < NF + 3; ++m) acc[m] = 0.0f;
-    float w[4], wg[4];
+    for (int m = 3; m < GF_RND + 3; ++m) acc[m] = 0.0f;
+    if (!no_input) {                                       // skipped stream: only flush what earlier rounds carried
 #pragma unroll
-    // the 1/512 of the unnormalised inverse FFT is folded into the window: scaling by a power of two commutes with rounding
-    for (int q = 0; q < 4; ++q) { w[q] = win[GF_HOP * q + r] * (1.0f / 512.0f); wg[q] = voiced ? d_tab.winG[GF_HOP * q + r] * (1.0f / 512.0f) : 0.0f; }
+        for (int f = 0; f < GF_RND; ++f) {
+            if (f < nf) {
+                const float *zf = reinterpret_cast<const float *>(bufs + (size_t)f * GF_FFT_BUF);
+                const bool blur = voiced && voiced[f];         // CTA-uniform: a branch, not four selects
+                float v[4];
 #pragma unroll
-    for (int f = 0; f < NF; ++f) {
-        if (no_input) break;                               // skipped stream: only flush what earlier rounds carried
-        const float *zf = reinterpret_cast<const float *>(bufs + (size_t)f * GF_FFT_BUF);
-        const bool blur = voiced && voiced[f];                 // CTA-uniform: a branch, not four selects
-        float v[4];
+                for (int q = 0; q < 4; ++q) {
+                    const int j = GF_HOP * q + r;
+                    v[q] = zf[2 * gf_fpad(j >> 1) + (j & 1)];
+                }
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            const int j = GF_HOP * q + r;
-            v[q] = zf[2 * gf_fpad(j >> 1) + (j & 1)];
-        }
-        if (blur) {
-#pragma unroll
-            for (int q = 0; q < 4; ++q) acc[f + q] = __fadd_rn(acc[f + q], __fmul_rn(v[q], wg[q]));
-        } else {
-#pragma unroll
-            for (int q = 0; q < 4; ++q) acc[f + q] = __fadd_rn(acc[f + q], __fmul_rn(v[q], w[q]));
+                for (int q = 0; q < 4; ++q) acc[f + q] = __fadd_rn(acc[f + q], __fmul_rn(v[q], blur ? wg[q] : w[q]));
+            }
         }
     }
-    const int n_emit = last ? NF + 1 : NF;                 // the final frame also finishes block T
+    const int n_emit = last ? nf + 1 : nf;                 // the final frame also finishes block T
 #pragma unroll
-    for (int m = 0; m < NF + 1; ++m) {
+    for (int m = 0; m < GF_RND + 1; ++m) {
         const int b = t0 + m;
         if (m < n_emit && b >= b0 && b < b0 + nb && b >= 2) {
             float ws = ws_full;                            // all four covering frames exist: the sum is the same for every block
             if (b < 3 || b >= T) {
                 ws = 0.0f;
-#pragma unroll
+#pragma unroll 1
                 for (int q = 3; q >= 0; --q) {             // frames b-3 .. b ascending
                     const int t = b - q;
                     if (t >= 0 && t < T) ws = __fadd_rn(ws, d_tab.win2[GF_HOP * q + r]);
@@ -221,8 +217,9 @@ __device__ __forceinline__ void gf_ola_round(float (*carry)[GF_HOP], const float
             if (i < n_out && !dead) out[i] = y;
         }
     }
+    // a short round is the CTA's last one: nothing reads the carry afterwards
 #pragma unroll
-    for (int m = 0; m < 3; ++m) carry[m][r] = acc[NF + m];
+    for (int m = 0; m < 3; ++m) carry[m][r] = acc[GF_RND + m];
 }
 
 // Excitation sample i of the (note, pass): pulse train, plus the growl layer when the note has one
@@ -235,6 +232,23 @@ struct GfExcite {
         return sub ? (float)((double)pulse[i] + ((double)sub[i] * (double)vm[i]) * sub_scale) : pulse[i];
     }
 };
+
+// framing of a frame that touches the reflected ends of the signal or carries the growl layer (rare: kept out of line so
+// that the sixteen reflect computations do not sit in the instruction stream of the hot loop)
+__device__ __noinline__ void gf_frame_edge(const GfExcite &ex, int p0, int n, float2 (&v)[8])
+{
+#pragma unroll 1
+    for (int r = 0; r < 8; ++r) {
+        const int p = p0 + 128 * r;
+        const bool inside = (p >= 0) && (p + 1 < n);
+        float2 x;
+        x.x = ex.at(inside ? p : gf_reflect(p, n));
+        x.y = ex.at(inside ? p + 1 : gf_reflect(p + 1, n));
+        // v[r] with a run-time r: the array lives in registers, so select
+#pragma unroll
+        for (int q = 0; q < 8; ++q) if (q == r) v[q] = x;
+    }
+}
 
 // work item: x = pass index (into the wave's pass arrays), y = first owned block, z = block count
 //
@@ -335,13 +349,7 @@ gf_frame_kernel(const int4 *__restrict__ work, const GfPassDev *__restrict__ pas
 #pragma unroll
                     for (int r = 0; r < 8; ++r) v[r] = *reinterpret_cast<const float2 *>(ex.pulse + p0 + 128 * r);
                 } else {
-#pragma unroll
-                    for (int r = 0; r < 8; ++r) {
-                        const int p = p0 + 128 * r;
-                        const bool inside = (p >= 0) && (p + 1 < n);
-                        v[r].x = ex.at(inside ? p : gf_reflect(p, n));
-                        v[r].y = ex.at(inside ? p + 1 : gf_reflect(p + 1, n));
-                    }
+                    gf_frame_edge(ex, p0, n, v);                  // note ends / growl layer: out of line, off the hot path
                 }
 #pragma unroll
                 for (int r = 0; r < 8; ++r) {
@@ -373,7 +381,11 @@ gf_frame_kernel(const int4 *__restrict__ work, const GfPassDev *__restrict__ pas
 #ifndef GF_SHAPE_BATCH
 #define GF_SHAPE_BATCH 2              // bin pairs whose global operands are requested together (6 loads each)
 #endif
+#ifdef GF_SHAPE_UNROLL
 #pragma unroll
+#else
+#pragma unroll 1
+#endif
                 for (int mb = 0; mb < 4; mb += GF_SHAPE_BATCH) {
                     GfShapeIn in[GF_SHAPE_BATCH];
 #pragma unroll
@@ -393,26 +405,24 @@ gf_frame_kernel(const int4 *__restrict__ work, const GfPassDev *__restrict__ pas
                 gf_lane_sync(g);
             }
             // ---- 5. inverse FFTs of the group's frame: harmonic, breath (, unvoiced), advanced pass by pass together ----
-            if (uv_on) gf_group_ifft512<3>(&sm.z[0][f][0], GF_RND * GF_FFT_BUF, sm.twl, g, j);
-            else gf_group_ifft512<2>(&sm.z[0][f][0], GF_RND * GF_FFT_BUF, sm.twl, g, j);
+            // (the unvoiced stream is rare -- only where the smoothed mask is below 1 -- and goes through a second, single
+            // transform call instead of a third instantiation of the batch: code size)
+            gf_group_ifft512<2>(&sm.z[0][f][0], GF_RND * GF_FFT_BUF, sm.twl, g, j);
+            if (uv_on) gf_group_ifft512<1>(&sm.z[2][f][0], GF_RND * GF_FFT_BUF, sm.twl, g, j);
         }
         __syncthreads();
         // ---- 6. overlap-add + emit: thread `tid` owns column tid of every hop block ----
         {
-            float *outs[3] = {ps.harm, ps.bre, ps.uv};
             const bool last = (t0 + nf - 1 == T - 1);
-            if (nf == GF_RND) {
+            float w[4], wg[4];
 #pragma unroll
-                for (int s = 0; s < 3; ++s) gf_ola_round<GF_RND>(sm.carry[s], &sm.z[s][0][0], win, t0, T, n, outs[s], b0, nb, last, s == 2 && !uv_on, s == 2 ? sm.dead : nullptr, s == 2 && ps.mask_ones, ws_full, s < 2 ? sm.voiced + m0r : nullptr, rcp_full);
-            } else if (nf == 3) {
-#pragma unroll
-                for (int s = 0; s < 3; ++s) gf_ola_round<3>(sm.carry[s], &sm.z[s][0][0], win, t0, T, n, outs[s], b0, nb, last, s == 2 && !uv_on, s == 2 ? sm.dead : nullptr, s == 2 && ps.mask_ones, ws_full, s < 2 ? sm.voiced + m0r : nullptr, rcp_full);
-            } else if (nf == 2) {
-#pragma unroll
-                for (int s = 0; s < 3; ++s) gf_ola_round<2>(sm.carry[s], &sm.z[s][0][0], win, t0, T, n, outs[s], b0, nb, last, s == 2 && !uv_on, s == 2 ? sm.dead : nullptr, s == 2 && ps.mask_ones, ws_full, s < 2 ? sm.voiced + m0r : nullptr, rcp_full);
-            } else {
-#pragma unroll
-                for (int s = 0; s < 3; ++s) gf_ola_round<1>(sm.carry[s], &sm.z[s][0][0], win, t0, T, n, outs[s], b0, nb, last, s == 2 && !uv_on, s == 2 ? sm.dead : nullptr, s == 2 && ps.mask_ones, ws_full, s < 2 ? sm.voiced + m0r : nullptr, rcp_full);
+            // the 1/512 of the unnormalised inverse FFT is folded into the window: scaling by a power of two commutes with rounding
+            for (int q = 0; q < 4; ++q) { w[q] = win[GF_HOP * q + tid] * (1.0f / 512.0f); wg[q] = d_tab.winG[GF_HOP * q + tid] * (1.0f / 512.0f); }
+#pragma unroll 1
+            for (int s = 0; s < 3; ++s) {
+                float *out = s == 0 ? ps.harm : (s == 1 ? ps.bre : ps.uv);
+                gf_ola_round(sm.carry[s], &sm.z[s][0][0], w, wg, t0, nf, T, n, out, b0, nb, last, s == 2 && !uv_on, s == 2 ? sm.dead : nullptr,
+                             s == 2 && ps.mask_ones, ws_full, s < 2 ? sm.voiced + m0r : nullptr, rcp_full);
             }
         }
         __syncthreads();

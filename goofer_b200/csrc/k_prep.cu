@@ -449,12 +449,15 @@ gf_env_kernel(const int2 *__restrict__ work, const GfNotePlan *__restrict__ plan
             for (int e = 0; e < GF_EPL; ++e) {
                 const int b = lane + 32 * e;
                 if (b < GF_NBINS) {
-                    double pos = ((double)b - 513.0 / 2.0) * (1.0 + pl.fw) + 513.0 / 2.0;
-                    pos = fmin(fmax(pos, 0.0), 512.0);
-                    const int lo = (int)pos;
-                    const int hi = min(lo + 1, 512);
+                    // np.clip(pos, 0, 512): the position is increasing in b, so the clip is a pair of integer selects on the
+                    // RESULT (row[0] below, row[512] above) instead of two fp64 min / max on the position
+                    const double pos = ((double)b - 513.0 / 2.0) * (1.0 + pl.fw) + 513.0 / 2.0;
+                    const int lo = min(max((int)pos, 0), 511);
                     const float fr = (float)(pos - (double)lo);
-                    acc[e] = fmaf(wm, fmaf(fr, cur[hi] - cur[lo], cur[lo]), acc[e]);
+                    float y = fmaf(fr, cur[lo + 1] - cur[lo], cur[lo]);
+                    y = (pos <= 0.0) ? cur[0] : y;
+                    y = (pos >= 512.0) ? cur[512] : y;
+                    acc[e] = fmaf(wm, y, acc[e]);
                 }
             }
         } else {
@@ -512,11 +515,11 @@ gf_env_kernel(const int2 *__restrict__ work, const GfNotePlan *__restrict__ plan
                 for (int e = 0; e < GF_EPL; ++e) {
                     const int b = lane + 32 * e;
                     if (b < GF_NBINS) {
-                        const double sp = fmin(fmax((double)b * inv_s, 0.0), 512.0);
-                        const int lo = (int)sp;
-                        const int hi = min(lo + 1, 512);
+                        const double sp = (double)b * inv_s;                 // >= 0; clipped to 512 on the result
+                        const int lo = min((int)sp, 511);
                         const float fr = (float)(sp - (double)lo);
-                        oth[b] = fmaf(fr, cur[hi] - cur[lo], cur[lo]);
+                        const float y = fmaf(fr, cur[lo + 1] - cur[lo], cur[lo]);
+                        oth[b] = (sp >= 512.0) ? cur[512] : y;
                     }
                 }
                 __syncwarp();
@@ -624,7 +627,11 @@ gf_env_kernel(const int2 *__restrict__ work, const GfNotePlan *__restrict__ plan
         for (int e = 0; e < GF_EPL; ++e) {
             // freqs / ratio on the freqs grid: in bins that is b / ratio, clipped to [0, 512]
             const int b = lane + 32 * e;
-            if (b < GF_NBINS) oth[b] = gf_grid_lerp(cur, fmin(fmax((double)b * inv_r, 0.0), 512.0));
+            if (b < GF_NBINS) {
+                const double u = (double)b * inv_r;                          // >= 0; np.clip(.., 0, nyq) on the result
+                const float y = gf_grid_lerp(cur, u);
+                oth[b] = (u >= 512.0) ? cur[512] : y;
+            }
         }
         __syncwarp();
         float *sw = cur; cur = oth; oth = sw;
