@@ -55,7 +55,7 @@ def parse_args():
     ap.add_argument("--e2e-variants", default="auto", help="'all', 'prod' (headline only) or 'auto' (all up to 2,048 notes per rank)")
     ap.add_argument("--noise", default="auto", choices=["auto", "host", "device"],
                     help="noise phases of the device-resident leg: uploaded once (host) or drawn by gf_phi_kernel inside "
-                         "every step (device); auto = host up to 16,384 notes per rank")
+                         "every step (device); auto = host up to 8,192 notes per rank")
     ap.add_argument("--ref-kind", default="auto", choices=["auto", "reference", "port"])
     return ap.parse_args()
 
@@ -315,12 +315,16 @@ def lsd_db(ref, got, floor_db=-100.0):
     return float(np.sqrt(np.mean((20 * np.log10(np.maximum(A, fl)) - 20 * np.log10(np.maximum(B, fl))) ** 2)))
 
 
+def verify_indices(args):
+    K = min(args.verify, args.notes)
+    return sorted({int(round(k * (args.notes - 1) / max(1, K - 1))) for k in range(K)}) if K > 0 else []
+
+
 def verify_batch(args, rank, outs_f32, outs_pcm):
     """Compare K notes, spread evenly over this rank's batch, of the outputs the timed calls produced with the oracle."""
     import numpy as np
     from goofer_b200 import cli as gcli
-    K = min(args.verify, args.notes)
-    idx = sorted({int(round(k * (args.notes - 1) / max(1, K - 1))) for k in range(K)})
+    idx = verify_indices(args)
     first = rank * args.notes
     worst_abs, worst_lsd, worst_lsb, worst_note = 0.0, 0.0, 0, -1
     for j in idx:
@@ -368,7 +372,7 @@ def run_native(args):
         dist.init_process_group("nccl", device_id=dev)
     capi.load()
 
-    dev_noise = args.noise == "device" or (args.noise == "auto" and args.notes > 16384)
+    dev_noise = args.noise == "device" or (args.noise == "auto" and args.notes > 8192)
     ab, algo_bytes = build_batch(args, rank, device_noise=dev_noise)
     n_notes = len(ab.infos)
     samples = sum(inf["n_total"] for inf in ab.infos)
@@ -398,7 +402,11 @@ def run_native(args):
     prof = capi.profile_summary()
     capi.profile(False)
     capi.check(db.status())                                   # no truncated pulse lists in the timed batch
-    outs_f32 = db.outputs() if args.verify > 0 else None
+    vidx = verify_indices(args)
+    offs = [0]
+    for inf in ab.infos:
+        offs.append(offs[-1] + inf["n_total"])
+    outs_f32 = {j: db.out[offs[j]:offs[j + 1]].cpu().numpy() for j in vidx} if args.verify > 0 else None   # only the checked notes cross PCIe
     # The excitation chain runs on a side stream beside the envelope kernel (GOOFER_OVERLAP, default on): the spans of
     # those kernels overlap in the timed region, while the frame kernel and everything after it run alone.  A second,
     # untimed pass with both chains on one stream gives per-kernel durations that add up (the table of the line).
@@ -442,7 +450,7 @@ def run_native(args):
             st = capi.last_stats()
             e2e_bytes[v] = (st["h2d_bytes"], st["d2h_bytes"])
             if v == E2E_VARIANTS[0] and args.verify > 0:
-                outs_pcm = [x.copy() for x in res]
+                outs_pcm = {j: res[j].copy() for j in vidx}
     clocks.stop_flag = True
     clocks.join(timeout=1.0)
 

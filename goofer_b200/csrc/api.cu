@@ -12,6 +12,8 @@
 #include <mutex>
 #include <algorithm>
 #include <functional>
+#include <ctime>
+#include <utility>
 
 #include "gf_internal.h"
 #include "gf_kernels.h"
@@ -124,6 +126,17 @@ extern "C" const char *goofer_profile_summary(void)
         g_prof.summary += buf;
     }
     return g_prof.summary.c_str();
+}
+
+// GOOFER_HOST_TRACE: host-side timestamps of the enqueue path (printed by goofer_render_batch_host)
+struct GfHostTrace { bool on = false; std::vector<std::pair<const char *, double>> marks; };
+static thread_local GfHostTrace g_htrace;
+static inline void gf_htrace(const char *name)
+{
+    if (!g_htrace.on) return;
+    timespec ts;
+    clock_gettime(CLOCK_MONOTONIC, &ts);
+    g_htrace.marks.push_back({name, 1e3 * (double)ts.tv_sec + 1e-6 * (double)ts.tv_nsec});
 }
 
 #define GF_STEP(name)                                                                              \
@@ -303,7 +316,7 @@ static void gf_carve_note(const GfNotePlan &p, Bump &bp, GfNoteDev *nd, GfPassDe
         q.uv = bp.arr<float>(n);
         q.onset_cap = p.n_total / 8 + 64;
         q.onsets = bp.arr<int4>((size_t)q.onset_cap);
-        if ((p.phi_rng_mask >> q.kind) & 1u) q.phi_gen = bp.arr<float>((size_t)GF_ENVS_LD * p.T_out);   // phi slot == pass kind; frame-major
+        q.phi = bp.arr<float>((size_t)GF_ENVS_LD * p.T_out);                                             // frame-major; drawn or transposed
         if (k == 0 && p.add_subharm) q.sub = bp.arr<float>(n);
         q.mask_ones = (q.kind == GF_PASS_SA);
         if (pd) pd[k] = q;
@@ -678,9 +691,42 @@ static int gf_render_wave(const GooferBatch *b, const std::vector<GfNotePlan> &a
             GfPassDev &q = wh.passes[pi + k];
             q.note = i;
             const int slot = q.kind;                      // phi slot == pass kind (0 main, 1 su, 2 sj, 3 sa)
-            q.phi = q.phi_gen ? q.phi_gen : b->phi + p.phi_off[slot];
-            q.phi_frame_major = q.phi_gen != nullptr;
+            q.phi_src = ((p.phi_rng_mask >> slot) & 1u) ? nullptr : b->phi + p.phi_off[slot];
         }
+        pi += p.n_passes;
+    }
+    int64_t &L = g_stats.kernel_launches;
+    int rc;
+    gf_htrace("wave: notes carved");
+    // ---- noise phases drawn on the device (GooferNote.phi_rng): needs nothing but its own job list, so it is uploaded
+    // and launched before the rest of the wave's metadata is even built: the generator runs (0.3 ms per 1,024 notes)
+    // while the host assembles the work lists, and overlaps the arrival of the source arrays over PCIe ----
+    {
+        std::vector<GfPhiJob> pj;
+        int max_T = 0;
+        for (size_t q = 0; q < wh.passes.size(); ++q) {
+            const GfPassDev &pd = wh.passes[q];
+            if (pd.phi_src) continue;
+            const GfNotePlan &p = wh.plans[pd.note];
+            GfPhiJob j;
+            j.dst = pd.phi; j.T = p.T_out; j.pad = 0;
+            j.s_hi = p.phi_rng[pd.kind][0]; j.s_lo = p.phi_rng[pd.kind][1]; j.i_hi = p.phi_rng[pd.kind][2]; j.i_lo = p.phi_rng[pd.kind][3];
+            max_T = std::max(max_T, j.T);
+            pj.push_back(j);
+        }
+        if (!pj.empty()) {
+            // carved from the END of the wave region so that the arrays built below keep their places
+            Bump tail{bp.base + bp.cap - ((pj.size() * sizeof(GfPhiJob) + 511) & ~(size_t)255), (pj.size() * sizeof(GfPhiJob) + 511) & ~(size_t)255, 0};
+            GfPhiJob *d_pj;
+            if ((rc = gf_upload(tail, pj, &d_pj, st)) != GOOFER_OK) return rc;
+            gf_launch_phi(d_pj, (int)pj.size(), max_T, st); ++L; GF_STEP("phi");
+        }
+    }
+    gf_htrace("wave: phase generator launched");
+    pi = 0;
+    for (int i = 0; i < nn; ++i) {
+        const GfNotePlan &p = wh.plans[i];
+        GfNoteDev &nd = wh.notes[i];
         // work lists
         const int tiles = (p.T_out + GF_FT - 1) / GF_FT;
         for (int t = 0; t * GF_ENV_TPC < tiles; ++t) wh.env_work.push_back(make_int2(i, t));      // GF_ENV_TPC tiles per CTA
@@ -723,7 +769,7 @@ static int gf_render_wave(const GooferBatch *b, const std::vector<GfNotePlan> &a
         pi += p.n_passes;
     }
     GfNotePlan *d_plans; GfNoteDev *d_notes; GfPassDev *d_passes; int2 *d_envw; int4 *d_framew; GfFirJob *d_fir;
-    int rc;
+    gf_htrace("wave: work lists built");
     {
         GfUploadBatch up;
         up.add(bp, wh.plans, &d_plans);
@@ -737,29 +783,7 @@ static int gf_render_wave(const GooferBatch *b, const std::vector<GfNotePlan> &a
     if (bp.off > bp.cap) { gf_set_error("internal: wave overflows the workspace (%zu > %zu)", bp.off, bp.cap); return GOOFER_ERR_WORKSPACE; }
     GF_CUDA(cudaMemsetAsync(d_nscal, 0, scal_span, st));
 
-    int64_t &L = g_stats.kernel_launches;
-    // ---- noise phases drawn on the device (GooferNote.phi_rng): needs nothing but the job list, so it goes first and
-    // overlaps the arrival of the source arrays over PCIe (host entry point) ----
-    {
-        std::vector<GfPhiJob> pj;
-        int max_total = 0;
-        for (size_t q = 0; q < wh.passes.size(); ++q) {
-            const GfPassDev &pd = wh.passes[q];
-            if (!pd.phi_gen) continue;
-            const GfNotePlan &p = wh.plans[pd.note];
-            GfPhiJob j;
-            j.dst = pd.phi_gen; j.T = p.T_out; j.pad = 0;
-            j.s_hi = p.phi_rng[pd.kind][0]; j.s_lo = p.phi_rng[pd.kind][1]; j.i_hi = p.phi_rng[pd.kind][2]; j.i_lo = p.phi_rng[pd.kind][3];
-            max_total = std::max(max_total, j.T);
-            pj.push_back(j);
-        }
-        if (!pj.empty()) {
-            GfPhiJob *d_pj;
-            if ((rc = gf_upload(bp, pj, &d_pj, st)) != GOOFER_OK) return rc;
-            if (bp.off > bp.cap) { gf_set_error("internal: phase jobs overflow the workspace"); return GOOFER_ERR_WORKSPACE; }
-            gf_launch_phi(d_pj, (int)pj.size(), max_total, st); ++L; GF_STEP("phi");
-        }
-    }
+    gf_htrace("wave: metadata uploaded");
     if (sources_first && *sources_first) {
         if ((rc = (*sources_first)()) != GOOFER_OK) return rc;
         *sources_first = nullptr;
@@ -797,6 +821,7 @@ static int gf_render_wave(const GooferBatch *b, const std::vector<GfNotePlan> &a
         GF_CUDA(cudaStreamWaitEvent(st, g_side.join, 0));
         gf_prof_mark("join", st);
     }
+    gf_htrace("wave: preparation kernels enqueued");
     // ---- phase-dependent tail, part by part: frame -> peak -> pd / post-FX -> mix ----
     {
         std::vector<int> first_work(nn + 1, 0), first_pass(nn + 1, 0);     // per note: first frame-work item / first pass
@@ -818,6 +843,14 @@ static int gf_render_wave(const GooferBatch *b, const std::vector<GfNotePlan> &a
             prev_end = pp[k].note_end;
             if (e <= a) continue;
             if (pp[k].phi_ready) GF_CUDA(cudaStreamWaitEvent(st, pp[k].phi_ready, 0));             // first kernel that reads the noise phases
+            {
+                // host-supplied phases, (513, T) as numpy draws them: transposed to the frame-major layout the frame kernel reads
+                int max_T = 0;
+                bool any = false;
+                for (int q = first_pass[a]; q < first_pass[e]; ++q)
+                    if (wh.passes[q].phi_src) { any = true; max_T = std::max(max_T, wh.passes[q].T_out); }
+                if (any) { gf_launch_phi_fm(d_passes + first_pass[a], first_pass[e] - first_pass[a], max_T, st); ++L; GF_STEP("phi_fm"); }
+            }
             gf_launch_frame(d_framew + first_work[a], first_work[e] - first_work[a], d_passes, d_scal, d_notes, d_plans, st); ++L; GF_STEP("frame");
             // lean peak / mix instantiations for the common note, the general ones for the rest (gf_tail_simple in k_tail.cu)
             bool any_simple = false, any_general = false;
@@ -835,6 +868,7 @@ static int gf_render_wave(const GooferBatch *b, const std::vector<GfNotePlan> &a
             if (pp[k].done && pp[k].note_end <= i1) GF_CUDA(cudaEventRecord(pp[k].done, st));
         }
     }
+    gf_htrace("wave: everything enqueued");
     gf_err_scan_kernel<<<(int)((n_pass + 255) / 256), 256, 0, st>>>(d_scal, d_passes, (int)n_pass, i0, d_status); ++L;
     GF_CUDA(cudaGetLastError());
     ++g_stats.waves;
@@ -884,6 +918,7 @@ static int gf_render_batch_ex(const GooferBatch *b, void *workspace, size_t work
         if (p.f0_off >= 0 && (!b->f0_curves || p.f0_off + p.n_total > b->f0_total)) { gf_set_error("note %d: f0 curve missing or outside the f0_curves buffer", i); return GOOFER_ERR_INVALID; }
     }
     cudaStream_t st = (cudaStream_t)stream;
+    gf_htrace("render: validated");
     if ((rc = gf_tables_init(plans[0].sr)) != 0) return rc;
     gf_prof_mark("begin", st);
 
@@ -959,6 +994,7 @@ static int gf_render_batch_ex(const GooferBatch *b, void *workspace, size_t work
             gf_set_error("workspace too small: note %d alone needs %zu bytes, %zu available", i0, gf_note_bytes(plans[i0]), wave_cap);
             return GOOFER_ERR_WORKSPACE;
         }
+        gf_htrace("render: wave packed");
         Bump wave{(char *)workspace + bp.off, wave_cap, 0};
         if ((rc = gf_render_wave(b, plans, i0, i1, d_srcs, wave, st, parts, n_parts, d_status, &sources_first)) != GOOFER_OK) return rc;
         // host-side work lists are reused by the next wave only after this one was enqueued; the

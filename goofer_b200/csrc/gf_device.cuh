@@ -50,10 +50,10 @@ struct GfPassDev {
     float *harm, *bre, *uv; // raw OLA streams (n_total,)
     int4 *onsets;           // (i, T0, f32 bits of last_valid_f0, f32 bits of table max)
     int onset_cap;
-    const float *phi;       // (513, T_out) f32 as numpy draws them (caller's buffer), or phi_gen
-    float *phi_gen;         // workspace: phases generated on the device for this pass (GooferNote.phi_rng) or NULL;
-                            // FRAME-MAJOR (T_out, GF_ENVS_LD) like envF / envN: the frame kernel reads a frame's bins contiguously
-    int phi_frame_major;    // layout of `phi`: 1 = (T_out, GF_ENVS_LD), 0 = (513, T_out)
+    float *phi;             // workspace: the pass's noise phases FRAME-MAJOR (T_out, GF_ENVS_LD) like envF / envN -- what the
+                            // frame kernel reads (a frame's bins contiguously); drawn there by gf_phi_kernel (GooferNote.phi_rng)
+                            // or transposed there from the caller's buffer by gf_phi_fm_kernel
+    const float *phi_src;   // the caller's (513, T_out) f32 buffer as numpy draws it, or NULL when the phases are drawn on the device
     int mask_ones;          // sa pass: voicing mask == 1
 };
 

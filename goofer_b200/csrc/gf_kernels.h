@@ -18,7 +18,8 @@ void gf_launch_peak(const GfNotePlan *plans, const GfNoteDev *notes, const GfPas
 void gf_launch_mix(const GfNotePlan *plans, const GfNoteDev *notes, const GfPassDev *passes, const GfPassScal *scal,
                    int note0, int n_notes, int max_n, bool any_simple, bool any_general, cudaStream_t st);
 struct GfPhiJob;
-void gf_launch_phi(const GfPhiJob *jobs, int n_jobs, int max_total, cudaStream_t st);
+void gf_launch_phi(const GfPhiJob *jobs, int n_jobs, int max_T, cudaStream_t st);
+void gf_launch_phi_fm(const GfPassDev *passes, int n_pass, int max_T, cudaStream_t st);
 void gf_launch_onepole(const GfOnepoleJob *jobs, int n_jobs, cudaStream_t st);
 size_t gf_frame_smem_bytes();
 

@@ -140,6 +140,8 @@ static int gf_render_batch_host_impl(const GooferBatch *b)
     const bool trace = getenv("GOOFER_HOST_TRACE") != nullptr;
     auto now_ms = []() { timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return 1e3 * (double)ts.tv_sec + 1e-6 * (double)ts.tv_nsec; };
     const double h0 = trace ? now_ms() : 0.0;
+    g_htrace.on = trace;
+    g_htrace.marks.clear();
     double h_first_copy = 0.0, h_enqueued = 0.0, h_uploads = 0.0, h_sized = 0.0;
     static thread_local cudaEvent_t ev_t0 = nullptr, ev_d2h[64] = {nullptr};
     if (trace) {
@@ -418,6 +420,7 @@ static int gf_render_batch_host_impl(const GooferBatch *b)
         fprintf(stderr, "[host trace] host: first copy issued at %.3f ms, source uploads issued at %.3f ms, workspace sized at %.3f ms, everything "
                         "enqueued at %.3f ms, synchronised at %.3f ms; device: small inputs in at %.3f ms after the H2D stream started\n",
                 h_first_copy - h0, h_uploads - h0, h_sized - h0, h_enqueued - h0, h_done - h0, small);
+        for (const auto &m : g_htrace.marks) fprintf(stderr, "[host trace] host +%.3f ms: %s\n", m.second - h0, m.first);
         for (int c = 0; c < n_chunks; ++c) {
             float a = 0, bq = 0, dq = 0;
             cudaEventElapsedTime(&a, ev_t0, g_hc.ev[2 * c]);

@@ -13,11 +13,50 @@
 
 #define GF_RND 4                      // frames per round (= FFT lanes)
 #define GF_FRAME_THREADS (64 * GF_RND)
+#ifndef GF_FRAME_TMA
+#define GF_FRAME_TMA 0
+#endif
 #ifndef GF_FRAME_CTAS
-#define GF_FRAME_CTAS 3                // resident CTAs per SM the register allocation aims at (65 KB of shared memory each)
+#define GF_FRAME_CTAS (GF_FRAME_TMA ? 2 : 3)   // resident CTAs per SM the register allocation aims at (67 KB of shared memory each; 92 KB with the TMA stage)
 #endif
 #define GF_FRAME_META 96              // frames a CTA may touch: GF_BLOCKS_PER_CTA (api.cu, static_assert there) + 3 of halo
 #define GF_BLUR_K 12                  // reach of the edge correction of the time-domain blur (see gf_blur_edges)
+
+// GF_FRAME_TMA=1: the three per-frame operand rows of the shaping stage (envF, envN, phi: 3 x 2,080 bytes, contiguous
+// because all three are frame-major) are staged in shared memory by the TMA engine -- one cp.async.bulk per row, issued
+// by the leader thread of the 64-thread group that owns the frame, completion signalled on the group's mbarrier -- a
+// whole round ahead of their use.  25 KB more shared memory per CTA: two CTAs per SM instead of three.
+#ifndef GF_FRAME_TMA
+#define GF_FRAME_TMA 0
+#endif
+
+__device__ __forceinline__ unsigned gf_smem_addr(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void gf_mbar_init(unsigned long long *bar, unsigned count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(gf_smem_addr(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void gf_mbar_expect_tx(unsigned long long *bar, unsigned bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(gf_smem_addr(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void gf_mbar_wait(unsigned long long *bar, unsigned parity)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "GF_MBAR_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra GF_MBAR_DONE;\n"
+        "bra GF_MBAR_WAIT;\n"
+        "GF_MBAR_DONE:\n"
+        "}\n" ::"r"(gf_smem_addr(bar)), "r"(parity) : "memory");
+}
+// 1-D bulk copy global -> shared (TMA, no tensor map): 16-byte aligned on both sides, size a multiple of 16
+__device__ __forceinline__ void gf_bulk_g2s(void *dst, const void *src, unsigned bytes, unsigned long long *bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(gf_smem_addr(dst)), "l"(src), "r"(bytes), "r"(gf_smem_addr(bar)) : "memory");
+}
 
 struct GfFrameSmem {
     float2 twl[GF_TWL_N];                     // per-thread FFT twiddles (gf_fft.cuh): every butterfly reads them; window and split twiddles
@@ -31,6 +70,10 @@ struct GfFrameSmem {
     int uvskip[GF_FRAME_META];                // frame lies where the smoothed mask is exactly 1: aper_uv * (1 - mask) == 0
     unsigned char dead[GF_FRAME_META];        // per owned hop block (b - b0): nobody reads the unvoiced stream there
     float red[GF_FRAME_THREADS / 32];
+#if GF_FRAME_TMA
+    __align__(16) float stage[GF_RND][3][GF_ENVS_LD];   // per group: envF row, envN row, phi row of its next frame (bulk copies)
+    __align__(8) unsigned long long full[GF_RND];       // per group: mbarrier the three copies complete on
+#endif
 };
 
 size_t gf_frame_smem_bytes() { return sizeof(GfFrameSmem); }
@@ -287,25 +330,18 @@ gf_frame_kernel(const int4 *__restrict__ work, const GfPassDev *__restrict__ pas
         const float mx = __uint_as_float(scal[wk.x].submax_bits);
         ex.sub_scale = ((double)mx > 1e-6) ? pl.subharm_weight / (double)mx : pl.subharm_weight;
     }
-    // phases: (513, T) rows as numpy draws them (host-supplied), or frame-major (T, GF_ENVS_LD) when gf_phi_kernel made them
-    const float *__restrict__ phi = ps.phi;
-    const size_t phi_bin = ps.phi_frame_major ? (size_t)1 : (size_t)T, phi_frm = ps.phi_frame_major ? (size_t)GF_ENVS_LD : (size_t)1;
+    const float *__restrict__ phi = ps.phi;                 // frame-major (T, GF_ENVS_LD): drawn by gf_phi_kernel or transposed by gf_phi_fm_kernel
     // global operands of a group's next frame -> L2, no registers held (each is read exactly once): the two envelope
     // rows (17 lines each), the phase row (17 lines frame-major; one line per bin otherwise), the new excitation samples
     auto prefetch_frame = [&](int t) {
         auto pf = [](const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); };
-        if (j < 17) {
+        if (!GF_FRAME_TMA && j < 17) {
             pf(reinterpret_cast<const char *>(nd.envF + (size_t)t * GF_ENVS_LD) + 128 * j);
             pf(reinterpret_cast<const char *>(nd.envN + (size_t)t * GF_ENVS_LD) + 128 * j);
-            if (ps.phi_frame_major) pf(reinterpret_cast<const char *>(phi + (size_t)t * GF_ENVS_LD) + 128 * j);
-        } else if (j < 25) {
+            pf(reinterpret_cast<const char *>(phi + (size_t)t * GF_ENVS_LD) + 128 * j);
+        } else if (j >= 17 && j < 25) {
             const int i = min(n - 1, GF_HOP * t + GF_NFFT / 2 - GF_HOP + 32 * (j - 17));
             if (i >= 0) pf(ex.pulse + i);
-        }
-        if (!ps.phi_frame_major && (t & 3) == 0) {            // a 128-byte line of a phase row serves 32 frames: touch it every fourth
-#pragma unroll
-            for (int m = 0; m < 8; ++m) pf(phi + (size_t)(j + 64 * m) * T + t);
-            if (j == 0) pf(phi + (size_t)512 * T + t);
         }
     };
 #ifndef GF_NO_PREFETCH
@@ -330,7 +366,23 @@ gf_frame_kernel(const int4 *__restrict__ work, const GfPassDev *__restrict__ pas
 #pragma unroll
     for (int q = 3; q >= 0; --q) ws_full = __fadd_rn(ws_full, d_tab.win2[GF_HOP * q + tid]);
     const float rcp_full = (ws_full > 1e-9f && (__float_as_uint(ws_full) & 0x7fffffu) != 0x7fffffu) ? __frcp_rn(ws_full) : 0.0f;
+#if GF_FRAME_TMA
+    if (j == 0) gf_mbar_init(&sm.full[g], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    unsigned tma_parity = 0;
+    // the leader of a group requests the three operand rows of frame t; they land in the group's stage while it works on
+    auto stage_frame = [&](int t) {
+        constexpr unsigned ROW = GF_ENVS_LD * sizeof(float);
+        gf_mbar_expect_tx(&sm.full[g], 3 * ROW);
+        gf_bulk_g2s(&sm.stage[g][0][0], nd.envF + (size_t)t * GF_ENVS_LD, ROW, &sm.full[g]);
+        gf_bulk_g2s(&sm.stage[g][1][0], nd.envN + (size_t)t * GF_ENVS_LD, ROW, &sm.full[g]);
+        gf_bulk_g2s(&sm.stage[g][2][0], phi + (size_t)t * GF_ENVS_LD, ROW, &sm.full[g]);
+    };
+#endif
     __syncthreads();
+#if GF_FRAME_TMA
+    if (j == 0 && t_begin + g <= t_end) stage_frame(t_begin + g);
+#endif
 
     for (int t0 = t_begin; t0 <= t_end; t0 += GF_RND) {
         const int nf = min(GF_RND, t_end - t0 + 1);
@@ -374,8 +426,14 @@ gf_frame_kernel(const int4 *__restrict__ work, const GfPassDev *__restrict__ pas
             gf_lane_sync(g);
             // ---- 3. shaping, per bin pair (k, 512 - k), k = j + 64 m; bin 256 pairs with itself (thread 0 of the group) ----
             {
+#if GF_FRAME_TMA
+                gf_mbar_wait(&sm.full[g], tma_parity);        // the rows requested a round ago have landed
+                tma_parity ^= 1u;
+                const float *eF = &sm.stage[g][0][0], *eN = &sm.stage[g][1][0], *ph = &sm.stage[g][2][0];
+#else
                 const float *eF = nd.envF + (size_t)t * GF_ENVS_LD, *eN = nd.envN + (size_t)t * GF_ENVS_LD;
-                const float *ph = phi + (size_t)t * phi_frm;
+                const float *ph = phi + (size_t)t * GF_ENVS_LD;
+#endif
                 const float f0f = sm.f0fr[m0r + f];
                 const bool vo = sm.voiced[m0r + f] != 0;
 #ifndef GF_SHAPE_BATCH
@@ -393,13 +451,16 @@ gf_frame_kernel(const int4 *__restrict__ work, const GfPassDev *__restrict__ pas
                         const int k = j + 64 * (mb + m), km = 512 - k;
                         in[m].ef[0] = eF[k];  in[m].ef[1] = eF[km];
                         in[m].en[0] = eN[k];  in[m].en[1] = eN[km];
-                        in[m].ph[0] = ph[(size_t)k * phi_bin];  in[m].ph[1] = ph[(size_t)km * phi_bin];
+                        in[m].ph[0] = ph[k];  in[m].ph[1] = ph[km];
                     }
 #pragma unroll
                     for (int m = 0; m < GF_SHAPE_BATCH; ++m) gf_shape_pair(sm, j + 64 * (mb + m), f, f0f, vo, uv_on, in[m], tw1024, local_max);
                 }
-                if (j == 0) gf_shape_mid(sm, f, f0f, vo, uv_on, eF[256], eN[256], ph[(size_t)256 * phi_bin], tw1024, local_max);
+                if (j == 0) gf_shape_mid(sm, f, f0f, vo, uv_on, eF[256], eN[256], ph[256], tw1024, local_max);
                 gf_lane_sync(g);
+#if GF_FRAME_TMA
+                if (j == 0 && t + GF_RND <= t_end) stage_frame(t + GF_RND);       // every read of the stage is behind the barrier above
+#endif
                 // ---- 4. voiced frames: edge terms of the brightness blur (the blur itself rides on the synthesis window) ----
                 if (vo) gf_blur_edges(sm, f, j, tw1024);      // uniform over the group
                 gf_lane_sync(g);

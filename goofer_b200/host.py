@@ -533,10 +533,30 @@ class AssembledBatch:
                 tr = s.formants.get(k + 1)
                 if tr is not None and tr.size:
                     g.formants[k] = pinned(tr).ctypes.data
-        n_out = 4 if self.taps else 1
-        self._out_bufs = [pinned(np.empty(max(1, self.out_total), dtype=np.float32)) for _ in range(n_out)]
-        self._pcm_buf = pinned(np.empty(max(1, self.out_total), dtype=np.int16))
+        # the output buffers are page-locked on first use (render_host): a float render never pays for the PCM buffer and
+        # vice versa (65,536 notes: 11.6 GB + 5.8 GB)
+        self._out_bufs = None
+        self._pcm_buf = None
         return self
+
+    def _pinned_out(self, pcm16: bool):
+        """Persistent output buffers of render_host: page-locked when pin() was called, plain numpy otherwise."""
+        def make(dtype):
+            a = np.empty(max(1, self.out_total), dtype=dtype)
+            if getattr(self, "_pinned", None) is None:
+                return a
+            import torch
+            t = torch.from_numpy(a).pin_memory()
+            self._pinned.append(t)
+            return t.numpy()
+
+        if pcm16:
+            if getattr(self, "_pcm_buf", None) is None:
+                self._pcm_buf = make(np.int16)
+            return self._pcm_buf
+        if getattr(self, "_out_bufs", None) is None:
+            self._out_bufs = [make(np.float32) for _ in range(4 if self.taps else 1)]
+        return self._out_bufs
 
     def split(self, flat: np.ndarray) -> List[np.ndarray]:
         """Per-note views of a concatenated array.  The views of a buffer that outlives the call (the pinned output
@@ -550,7 +570,8 @@ class AssembledBatch:
         for inf in self.infos:
             outs.append(flat[off:off + inf["n_total"]])
             off += inf["n_total"]
-        if pinned and any(key[0] == b.__array_interface__["data"][0] for b in self._out_bufs + [self._pcm_buf]):
+        mine = (getattr(self, "_out_bufs", None) or []) + ([self._pcm_buf] if getattr(self, "_pcm_buf", None) is not None else [])
+        if pinned and any(key[0] == b.__array_interface__["data"][0] for b in mine):
             cache[key] = outs
             return list(outs)
         return outs
@@ -563,9 +584,7 @@ class AssembledBatch:
         if pcm16:
             if self.taps:
                 raise ValueError("stage taps are f32: render with pcm16=False")
-            pcm = getattr(self, "_pcm_buf", None)
-            if pcm is None:
-                pcm = self._pcm_buf = np.empty(max(1, self.out_total), dtype=np.int16)
+            pcm = self._pinned_out(True)
             d = self.desc
             d.out, d.out_pcm16 = None, pcm.ctypes.data
             d.tap_harm = d.tap_uv = d.tap_bre = None
@@ -574,13 +593,13 @@ class AssembledBatch:
             finally:
                 d.out_pcm16 = None
             return self.split(pcm[:self.out_total])
-        bufs = getattr(self, "_out_bufs", None)
-        out = bufs[0] if bufs else np.empty(max(1, self.out_total), dtype=np.float32)
+        bufs = self._pinned_out(False)
+        out = bufs[0]
         d = self.desc
         d.out = out.ctypes.data
         tap_arrays = None
         if self.taps:
-            tap_arrays = bufs[1:4] if bufs else [np.empty_like(out) for _ in range(3)]
+            tap_arrays = bufs[1:4]
             d.tap_harm, d.tap_uv, d.tap_bre = (a.ctypes.data for a in tap_arrays)
         else:
             d.tap_harm = d.tap_uv = d.tap_bre = None
