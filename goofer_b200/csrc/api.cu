@@ -813,6 +813,16 @@ static int gf_render_wave(const GooferBatch *b, const std::vector<GfNotePlan> &a
         gf_launch_pulse(d_passes, d_scal, (int)n_pass, max_n, st); ++L; GF_STEP("pulse");
         if ((rc = gf_growl(wh, d_plans, d_notes, d_passes, d_scal, bp, max_n, st, &L)) != GOOFER_OK) return rc;
     }
+    // ---- host-supplied phases that are already resident (device entry point: no phi_ready events): transposed to the
+    // frame-major layout here, on the caller's stream -- a DRAM-bound copy beside the issue-bound excitation chain ----
+    bool phi_fm_done = false;
+    {
+        bool waits = false, any_src = false;
+        for (int k = 0; k < n_parts; ++k) waits = waits || (parts[k].phi_ready != nullptr);
+        int max_T = 0;
+        for (const GfPassDev &q : wh.passes) if (q.phi_src) { any_src = true; max_T = std::max(max_T, q.T_out); }
+        if (any_src && !waits) { gf_launch_phi_fm(d_passes, (int)n_pass, max_T, st); ++L; GF_STEP("phi_fm"); phi_fm_done = true; }
+    }
     // ---- envelope chain on the caller's stream ----
     gf_launch_tracks(d_plans, d_notes, d_srcs, nn, st); ++L; GF_STEP("tracks");
     gf_launch_env(d_envw, (int)wh.env_work.size(), d_plans, d_notes, d_srcs, st); ++L; GF_STEP("env");
@@ -849,7 +859,7 @@ static int gf_render_wave(const GooferBatch *b, const std::vector<GfNotePlan> &a
                 bool any = false;
                 for (int q = first_pass[a]; q < first_pass[e]; ++q)
                     if (wh.passes[q].phi_src) { any = true; max_T = std::max(max_T, wh.passes[q].T_out); }
-                if (any) { gf_launch_phi_fm(d_passes + first_pass[a], first_pass[e] - first_pass[a], max_T, st); ++L; GF_STEP("phi_fm"); }
+                if (any && !phi_fm_done) { gf_launch_phi_fm(d_passes + first_pass[a], first_pass[e] - first_pass[a], max_T, st); ++L; GF_STEP("phi_fm"); }
             }
             gf_launch_frame(d_framew + first_work[a], first_work[e] - first_work[a], d_passes, d_scal, d_notes, d_plans, st); ++L; GF_STEP("frame");
             // lean peak / mix instantiations for the common note, the general ones for the rest (gf_tail_simple in k_tail.cu)
@@ -876,7 +886,8 @@ static int gf_render_wave(const GooferBatch *b, const std::vector<GfNotePlan> &a
 }
 
 static int gf_render_batch_ex(const GooferBatch *b, void *workspace, size_t workspace_bytes, void *stream, const GfPart *parts, int n_parts,
-                              const std::vector<GfNotePlan> *planned = nullptr, cudaEvent_t src_ready = nullptr);
+                              const std::vector<GfNotePlan> *planned = nullptr, cudaEvent_t src_ready = nullptr,
+                              std::function<int()> *uploads = nullptr);
 
 extern "C" int goofer_render_batch(const GooferBatch *b, void *workspace, size_t workspace_bytes, void *stream)
 {
@@ -887,8 +898,10 @@ extern "C" int goofer_render_batch(const GooferBatch *b, void *workspace, size_t
 // b's notes when the caller made them already (the host entry point plans once for sizing and rendering: 0.17 ms per
 // 1,024 notes each time).  src_ready (optional): event after which the source arrays / bends / normals are in device
 // memory -- the first kernels that read them wait for it, the noise-phase generator of the first wave runs before.
+// uploads (optional): issues the copies that src_ready (and the parts' phi_ready events) stand for; called once, right
+// after the first wave's phase generator has been launched, and reset to empty.
 static int gf_render_batch_ex(const GooferBatch *b, void *workspace, size_t workspace_bytes, void *stream, const GfPart *parts, int n_parts,
-                              const std::vector<GfNotePlan> *planned, cudaEvent_t src_ready)
+                              const std::vector<GfNotePlan> *planned, cudaEvent_t src_ready, std::function<int()> *uploads)
 {
     int rc = gf_validate(b);
     if (rc != GOOFER_OK) return rc;
@@ -961,6 +974,12 @@ static int gf_render_batch_ex(const GooferBatch *b, void *workspace, size_t work
     if (bp.off > bp.cap) { gf_set_error("workspace too small for the source cache (%zu > %zu)", bp.off, bp.cap); return GOOFER_ERR_WORKSPACE; }
     // source table + envelope decode: issued inside the first wave, after its phase generator (gf_render_wave)
     std::function<int()> sources_first = [&]() -> int {
+        if (uploads && *uploads) {
+            const int rcu = (*uploads)();
+            *uploads = nullptr;
+            if (rcu != GOOFER_OK) return rcu;
+            gf_htrace("render: uploads issued");
+        }
         if (src_ready) GF_CUDA(cudaStreamWaitEvent(st, src_ready, 0));
         if (b->n_sources) {
             void *stage = gf_pin_take(srcs.size() * sizeof(GfSourceDev));

@@ -772,29 +772,46 @@ void gf_launch_phi(const GfPhiJob *jobs, int n_jobs, int max_T, cudaStream_t st)
 // reads a frame's 513 bins at a time.  32 x 32 tiles through shared memory: coalesced on both sides, the
 // (T, GF_ENVS_LD) result sits next to the envelope rows of the same frame.
 // ------------------------------------------------------------------------------------------------
+// One CTA per (pass, 32-frame tile): it walks the 17 bin tiles two at a time (eight loads in flight per thread).
 __global__ void __launch_bounds__(256) gf_phi_fm_kernel(const GfPassDev *__restrict__ passes)
 {
-    __shared__ float tile[32][33];
-    const GfPassDev ps = passes[blockIdx.z];
+    __shared__ float tile[2][32][33];
+    const GfPassDev ps = passes[blockIdx.y];
     if (!ps.phi_src) return;                                   // drawn on the device: already frame-major
     const int T = ps.T_out;
-    const int t0 = blockIdx.x * 32, k0 = blockIdx.y * 32;
+    const int t0 = blockIdx.x * 32;
     if (t0 >= T) return;
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-    for (int i = ty; i < 32; i += 8) {
-        const int k = k0 + i, t = t0 + tx;
-        tile[i][tx] = (k < GF_NBINS && t < T) ? ps.phi_src[(size_t)k * T + t] : 0.0f;
-    }
-    __syncthreads();
-    for (int i = ty; i < 32; i += 8) {
-        const int t = t0 + i, k = k0 + tx;
-        if (t < T && k < GF_NBINS) ps.phi[(size_t)t * GF_ENVS_LD + k] = tile[tx][i];
+    const float *__restrict__ src = ps.phi_src;
+    float *__restrict__ dst = ps.phi;
+    for (int k0 = 0; k0 < GF_NBINS; k0 += 64) {
+        float v[2][4];
+#pragma unroll
+        for (int h = 0; h < 2; ++h)
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int k = k0 + 32 * h + ty + 8 * i, t = t0 + tx;
+                v[h][i] = (k < GF_NBINS && t < T) ? src[(size_t)k * T + t] : 0.0f;
+            }
+#pragma unroll
+        for (int h = 0; h < 2; ++h)
+#pragma unroll
+            for (int i = 0; i < 4; ++i) tile[h][ty + 8 * i][tx] = v[h][i];
+        __syncthreads();
+#pragma unroll
+        for (int h = 0; h < 2; ++h)
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int t = t0 + ty + 8 * i, k = k0 + 32 * h + tx;
+                if (t < T && k < GF_NBINS) dst[(size_t)t * GF_ENVS_LD + k] = tile[h][tx][ty + 8 * i];
+            }
+        __syncthreads();
     }
 }
 
 void gf_launch_phi_fm(const GfPassDev *passes, int n_pass, int max_T, cudaStream_t st)
 {
     if (n_pass <= 0 || max_T <= 0) return;
-    dim3 grid((max_T + 31) / 32, (GF_NBINS + 31) / 32, n_pass);
+    dim3 grid((max_T + 31) / 32, n_pass);
     gf_phi_fm_kernel<<<grid, 256, 0, st>>>(passes);
 }

@@ -41,17 +41,53 @@ def balanced_partition(costs: Sequence[int], world: int) -> List[List[int]]:
     return bins
 
 
-def gather_outputs(local_indices: Sequence[int], local_outputs: Sequence, group=None) -> dict:
-    """All-gather {note index: output array} over the process group (no-op without torch.distributed)."""
+def gather_outputs(local_indices: Sequence[int], local_outputs: Sequence, group=None, device=None) -> dict:
+    """All-gather {note index: output array} over the process group (no-op without torch.distributed).
+
+    One fixed-stride `all_gather_into_tensor` of the concatenated samples (`ncclAllGather` of
+    (notes_per_gpu x N_out) over NVLink / NVSwitch when a single buffer is required) plus one of the small (index, length)
+    table -- no pickling of sample data.  `device`: where the collective runs ("cuda:k" for NCCL; CPU tensors for gloo).
+    Every rank returns every note.  The data path of a render needs none of this: ranks write their own outputs."""
+    import numpy as np
+    import torch
     import torch.distributed as dist
     mine = {int(i): o for i, o in zip(local_indices, local_outputs)}
     if not (dist.is_available() and dist.is_initialized()):
         return mine
-    parts = [None] * dist.get_world_size(group)
-    dist.all_gather_object(parts, mine, group=group)
+    world = dist.get_world_size(group)
+    if device is None:
+        device = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend(group) == "nccl" else torch.device("cpu")
+    dtype = np.asarray(local_outputs[0]).dtype if len(local_outputs) else np.dtype(np.float32)
+    tdtype = torch.from_numpy(np.zeros(1, dtype=dtype)).dtype
+    n_local = len(local_indices)
+    total = int(sum(len(o) for o in local_outputs))
+    # 1. sizes: (note count, sample count) of every rank
+    sizes = torch.tensor([n_local, total], dtype=torch.int64, device=device)
+    all_sizes = torch.empty(2 * world, dtype=torch.int64, device=device)
+    dist.all_gather_into_tensor(all_sizes, sizes, group=group)
+    all_sizes = all_sizes.cpu().view(world, 2)
+    max_notes, max_total = int(all_sizes[:, 0].max()), int(all_sizes[:, 1].max())
+    # 2. the (index, length) table, fixed stride
+    table = torch.full((max(1, max_notes), 2), -1, dtype=torch.int64)
+    for k, (i, o) in enumerate(zip(local_indices, local_outputs)):
+        table[k, 0], table[k, 1] = int(i), len(o)
+    all_tables = torch.empty((world * table.shape[0], 2), dtype=torch.int64, device=device)      # concatenated along dim 0
+    dist.all_gather_into_tensor(all_tables, table.to(device), group=group)
+    # 3. the samples, fixed stride = the largest shard
+    flat = torch.zeros(max(1, max_total), dtype=tdtype)
+    if total:
+        flat[:total] = torch.from_numpy(np.concatenate([np.asarray(o) for o in local_outputs]))
+    all_flat = torch.empty(world * flat.numel(), dtype=tdtype, device=device)
+    dist.all_gather_into_tensor(all_flat, flat.to(device), group=group)
+    all_tables = all_tables.cpu().numpy().reshape(world, table.shape[0], 2)
+    all_flat = all_flat.cpu().numpy().reshape(world, flat.numel())
     out = {}
-    for p in parts:
-        out.update(p)
+    for r in range(world):
+        off = 0
+        for k in range(int(all_sizes[r, 0])):
+            i, n = int(all_tables[r, k, 0]), int(all_tables[r, k, 1])
+            out[i] = all_flat[r, off:off + n]
+            off += n
     return out
 
 
