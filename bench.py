@@ -423,6 +423,7 @@ def run_native(args):
 
     # ---- end to end through the host-buffer C-ABI call (pinned host memory), every variant on every rank ----
     e2e_ms = {}
+    e2e_calls = {}
     e2e_bytes = {}
     outs_pcm = None
     if not args.no_e2e:
@@ -439,14 +440,18 @@ def run_native(args):
         for v in variants:
             a = ab_dn if v.startswith("device") else ab_host
             pcm = v.endswith("pcm16")
-            for _ in range(2):
+            for _ in range(3):
                 res = a.render_host(pcm16=pcm)
             barrier()
+            calls = []
             t0 = time.perf_counter()
             for _ in range(args.steps):
+                tc = time.perf_counter()
                 res = a.render_host(pcm16=pcm)
+                calls.append(1e3 * (time.perf_counter() - tc))
             torch.cuda.synchronize()
             e2e_ms[v] = 1e3 * (time.perf_counter() - t0)
+            e2e_calls[v] = calls
             st = capi.last_stats()
             e2e_bytes[v] = (st["h2d_bytes"], st["d2h_bytes"])
             if v == E2E_VARIANTS[0] and args.verify > 0:
@@ -534,7 +539,9 @@ def run_native(args):
                 ms = worst[c]
                 return {"value": n_notes * world * args.steps / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms / args.steps,
                         "h2d_bytes_per_step": int(e2e_bytes[v][0]), "d2h_bytes_per_step": int(e2e_bytes[v][1]),
-                        "ms_per_step_by_rank": [round(r[c] / args.steps, 3) for r in by_rank]}
+                        "ms_per_step_by_rank": [round(r[c] / args.steps, 3) for r in by_rank],
+                        "rank0_call_ms": {"median": round(statistics.median(e2e_calls[v]), 3), "min": round(min(e2e_calls[v]), 3),
+                                          "max": round(max(e2e_calls[v]), 3)}}
             head = leg(1, keys[0])
             head.update({
                 "variant": keys[0],

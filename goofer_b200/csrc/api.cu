@@ -641,7 +641,8 @@ __global__ void __launch_bounds__(256) gf_err_scan_kernel(const GfPassScal *__re
 
 static int gf_render_wave(const GooferBatch *b, const std::vector<GfNotePlan> &all, int i0, int i1, const GfSourceDev *d_srcs,
                           Bump bp /* by value: wave region restarts every wave */, cudaStream_t st, const GfPart *parts, int n_parts,
-                          int *d_status, std::function<int()> *sources_first /* run once, after the first wave's phase generator */)
+                          int *d_status, std::function<int()> *sources_first /* run once, after the first wave's phase generator */,
+                          std::function<int()> *uploads /* run once, right after the phase generator launch (host entry point) */)
 {
     WaveHost wh;
     const int nn = i1 - i0;
@@ -723,6 +724,14 @@ static int gf_render_wave(const GooferBatch *b, const std::vector<GfNotePlan> &a
         }
     }
     gf_htrace("wave: phase generator launched");
+    if (uploads && *uploads) {
+        // the host entry point's H2D copies: issued while the generator runs and before the host builds the work lists,
+        // so that the sources are in HBM by the time the first kernel that needs them is enqueued
+        const int rcu = (*uploads)();
+        *uploads = nullptr;
+        if (rcu != GOOFER_OK) return rcu;
+        gf_htrace("wave: uploads issued");
+    }
     pi = 0;
     for (int i = 0; i < nn; ++i) {
         const GfNotePlan &p = wh.plans[i];
@@ -974,12 +983,6 @@ static int gf_render_batch_ex(const GooferBatch *b, void *workspace, size_t work
     if (bp.off > bp.cap) { gf_set_error("workspace too small for the source cache (%zu > %zu)", bp.off, bp.cap); return GOOFER_ERR_WORKSPACE; }
     // source table + envelope decode: issued inside the first wave, after its phase generator (gf_render_wave)
     std::function<int()> sources_first = [&]() -> int {
-        if (uploads && *uploads) {
-            const int rcu = (*uploads)();
-            *uploads = nullptr;
-            if (rcu != GOOFER_OK) return rcu;
-            gf_htrace("render: uploads issued");
-        }
         if (src_ready) GF_CUDA(cudaStreamWaitEvent(st, src_ready, 0));
         if (b->n_sources) {
             void *stage = gf_pin_take(srcs.size() * sizeof(GfSourceDev));
@@ -1015,7 +1018,7 @@ static int gf_render_batch_ex(const GooferBatch *b, void *workspace, size_t work
         }
         gf_htrace("render: wave packed");
         Bump wave{(char *)workspace + bp.off, wave_cap, 0};
-        if ((rc = gf_render_wave(b, plans, i0, i1, d_srcs, wave, st, parts, n_parts, d_status, &sources_first)) != GOOFER_OK) return rc;
+        if ((rc = gf_render_wave(b, plans, i0, i1, d_srcs, wave, st, parts, n_parts, d_status, &sources_first, uploads)) != GOOFER_OK) return rc;
         // host-side work lists are reused by the next wave only after this one was enqueued; the
         // device regions are reused in stream order, so no extra synchronisation is needed
         i0 = i1;

@@ -142,9 +142,10 @@ gf_f0_kernel(const GfNotePlan *__restrict__ plans, const GfNoteDev *__restrict__
         for (int base = blockIdx.x * blockDim.x; base < n; base += gridDim.x * blockDim.x) {
             const int i = base + threadIdx.x;
             float msv = 1.0f;
-            if (i < n) { msv = gf_ms_at_fast(mshort, M, i, n); out_ms[i] = msv; }
+            if (i < n) msv = gf_ms_at_fast(mshort, M, i, n);
             const int all_one = __syncthreads_and(msv == 1.0f);
             if (threadIdx.x == 0) ms_one[base >> 8] = (unsigned char)all_one;
+            if (i < n && !all_one) out_ms[i] = msv;           // blocks where the smoothed mask is 1 throughout are flagged, not stored
             if (i >= n) continue;
             const double m = (double)vm[i];
             double hz = hz_flat;
@@ -161,9 +162,10 @@ gf_f0_kernel(const GfNotePlan *__restrict__ plans, const GfNoteDev *__restrict__
         // smooth_mask_ds (GOOFER.py:564-569) + per hop block: is the smoothed mask exactly 1 everywhere?  Where it
         // is, aper_uv * (1 - mask) vanishes identically and the frame kernel skips the unvoiced stream.
         float msv = 1.0f;
-        if (i < n) { msv = gf_ms_at_fast(nd.ms_short, M, i, n); nd.ms[i] = msv; }
+        if (i < n) msv = gf_ms_at_fast(nd.ms_short, M, i, n);
         const int all_one = __syncthreads_and(msv == 1.0f);
         if (threadIdx.x == 0) nd.ms_one[base >> 8] = (unsigned char)all_one;
+        if (i < n && !all_one) nd.ms[i] = msv;
         if (i >= n) continue;
         // without the velocity stretch mask_new is a plain copy of source samples: vm (f32) holds it exactly
         const double m = pl.vel_active ? gf_mask_new(pl, mask_src, i) : (double)nd.vm[i];

@@ -42,7 +42,8 @@ __device__ __forceinline__ GfStreams gf_pass_gains(const GfNotePlan &pl, const G
 __device__ __forceinline__ GfStreams gf_pass_streams(const GfNotePlan &pl, const GfNoteDev &nd, const GfPassDev &ps,
                                                      const GfPassScal &sc, int i)
 {
-    const float ms = ps.mask_ones ? 1.0f : nd.ms[i];          // smooth_mask_ds, expanded once by gf_f0_kernel
+    // smooth_mask_ds, expanded once by gf_f0_kernel; hop blocks where it is 1 throughout are only flagged (ms_one), not stored
+    const float ms = (ps.mask_ones || nd.ms_one[i >> 8]) ? 1.0f : nd.ms[i];
     const float uraw = (ps.mask_ones || ms == 1.0f) ? 0.0f : ps.uv[i];
     return gf_pass_gains(pl, nd, ps, __uint_as_float(sc.mag_bits), ps.harm[i], ps.bre[i], uraw, ms, i);
 }
@@ -68,7 +69,9 @@ __device__ __forceinline__ void gf_pass_streams4(const GfNotePlan &pl, const GfN
     gf_ld4(ps.harm, i, cnt, h);
     gf_ld4(ps.bre, i, cnt, b);
     if (SIMPLE || !ps.mask_ones) {
-        gf_ld4(nd.ms, i, cnt, ms);
+        // i is a multiple of 4, so the four samples share a 256-sample hop block: inside a voiced stretch (block flagged
+        // all-one by gf_f0_kernel) neither the smoothed mask nor the unvoiced stream is read
+        if (!nd.ms_one[i >> 8]) gf_ld4(nd.ms, i, cnt, ms);
         if (cnt < 4 || !(ms[0] == 1.0f && ms[1] == 1.0f && ms[2] == 1.0f && ms[3] == 1.0f)) gf_ld4(ps.uv, i, cnt, u);
     }
 #pragma unroll
