@@ -10,6 +10,7 @@
 //   gf_mask_kernel      mask_new (tile + velocity stretch)             SillySampler.py:699-712, 788
 //   gf_fir_kernel       gaussian_filter1d along time (numpy-'reflect')  GOOFER.py:241-261
 #include <cuda_fp16.h>
+#include <cuda_pipeline.h>
 #include "gf_device.cuh"
 #include "gf_maps.cuh"
 
@@ -247,12 +248,20 @@ void gf_launch_tracks(const GfNotePlan *plans, const GfNoteDev *notes, const GfS
 #define GF_ROW_L 32         // left padding of a row (reflect halo, radius <= 28)
 #define GF_ROW_LEN 600      // 32 + 513 + 55: the FIR windows of the last lanes read up to bin index 561
 
+#ifndef GF_ENV_TPC
+#define GF_ENV_TPC 2                // tiles (of GF_FT frames) per CTA: the CTA prologue (a chain of dependent record loads, the
+                                    // per-note tables, a barrier) is paid once per GF_ENV_TPC frames of a warp, and from the
+                                    // second frame on the source row is already in shared memory (cp.async, see `nxt`)
+#endif
 struct GfEnvSmem {
     float rows[GF_ENV_WARPS][2][GF_ROW_LEN];
     float tilt[GF_ENVS_LD];
     float freq[GF_ENVS_LD];
     float es_taps[GF_MAX_ES_TAPS];
     double knots[GF_ENV_WARPS][18];                       // F1..F4 warp of the warp's frame: xd[0..5], xs[6..11], slopes [12..16]
+#if GF_ENV_TPC > 1
+    __align__(16) float nxt[GF_ENV_WARPS][GF_ENVS_LD];    // the source row of the warp's NEXT frame, fetched by cp.async while this one is shaped
+#endif
 };
 
 // fill the reflect halo of a row whose bins 0..512 are valid (numpy 'reflect': edge sample not repeated)
@@ -312,9 +321,7 @@ __device__ __forceinline__ float gf_grid_interp(const float *row, double x, doub
     return gf_grid_lerp(row, x * inv_step);
 }
 
-#ifndef GF_ENV_TPC
-#define GF_ENV_TPC 1                // tiles (of GF_FT frames) per CTA
-#endif
+
 #ifndef GF_ENV_CTAS
 #define GF_ENV_CTAS 3               // 80 registers (64 B of spills), 44 KB of shared memory per CTA: 1.94 -> 1.69 ms against two CTAs at 127
 #endif
@@ -365,6 +372,18 @@ gf_env_kernel(const int2 *__restrict__ work, const GfNotePlan *__restrict__ plan
             for (int e = 0; e < GF_EPL; ++e) { const int b = lane + 32 * e; if (b < GF_NBINS) pre[e] = src0[b]; }
         }
     }
+#if GF_ENV_TPC > 1
+    // source row of frame t -> the warp's `nxt` buffer, asynchronously (16-byte cp.async, no registers held)
+    auto fetch_next = [&](int t) {
+        if (t >= pl.T_out) return;
+        GfMix mx;
+        gf_env_mix(pl, min(t, pl.T_env - 1), mx);
+        const float *src = sc.envS + (size_t)gf_src_frame(pl, mx.f[0]) * GF_ENVS_LD;
+        for (int c = lane; c < GF_ENVS_LD / 4; c += 32) __pipeline_memcpy_async(&sm.nxt[warp][4 * c], src + 4 * c, 16);
+        __pipeline_commit();
+    };
+    fetch_next((tile0 + 1) * GF_FT + warp);
+#endif
     // per-note tables prepared by gf_tracks_kernel
     for (int b = threadIdx.x; b < GF_NBINS; b += blockDim.x) {
         sm.freq[b] = nd.env_aux[GF_AUX_FREQ + b];
@@ -395,13 +414,17 @@ gf_env_kernel(const int2 *__restrict__ work, const GfNotePlan *__restrict__ plan
     float trk = 0.0f;
     if (lane < 4) { if (pl.any_fst && !(fabs(pl.fst[lane]) < 1e-6)) trk = nd.trk_clean[(size_t)lane * pl.T_env + te]; }
     else if (lane < 8) { if (pl.any_F_shift) trk = nd.trk_canon[(size_t)(lane - 4) * pl.T_env + te]; }
+#if GF_ENV_TPC > 1
     if (it > 0) {
         gf_env_mix(pl, te, mix);
-        const float *src0 = sc.envS + (size_t)gf_src_frame(pl, mix.f[0]) * GF_ENVS_LD;
+        __pipeline_wait_prior(0);                         // this frame's source row, requested while the previous frame was shaped
+        __syncwarp();                                     // (also: the previous frame's row reads are done before the rows are rewritten)
 #pragma unroll
-        for (int e = 0; e < GF_EPL; ++e) { const int b = lane + 32 * e; pre[e] = (b < GF_NBINS) ? src0[b] : 0.0f; }
-        __syncwarp();                                     // the previous frame's row reads are done before the rows are rewritten
+        for (int e = 0; e < GF_EPL; ++e) { const int b = lane + 32 * e; pre[e] = (b < GF_NBINS) ? sm.nxt[warp][b] : 0.0f; }
+        __syncwarp();
+        if (it + 1 < GF_ENV_TPC) fetch_next((tile0 + it + 1) * GF_FT + warp);
     }
+#endif
 
     float acc[GF_EPL];
 #pragma unroll

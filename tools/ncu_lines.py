@@ -49,7 +49,7 @@ cur = ("?", 0)
 off2line = {}
 for l in dis:
     if l.startswith("//---") and ".text." in l:
-        inside = kname in l
+        inside = (kname in l) or (kre in l)              # templated kernels: the section carries the mangled name
         continue
     if not inside:
         continue
