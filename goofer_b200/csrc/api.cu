@@ -423,9 +423,16 @@ static void gf_balance_frame_group(const std::vector<GfNotePlan> &plans, int a, 
 
 static int gf_validate(const GooferBatch *b)
 {
-    if (!b || b->n_notes < 0 || b->n_sources < 0 || (b->n_notes && !b->notes) || (b->n_sources && !b->sources)) {
+    if (!b || b->n_notes < 0 || b->n_sources < 0 || (b->n_notes && !b->notes) || (b->n_sources && !b->sources) ||
+        b->bend_total < 0 || b->phi_total < 0 || b->nrm_total < 0 || b->out_total < 0 || b->f0_total < 0) {
         gf_set_error("invalid batch descriptor (NULL or negative field)");
         return GOOFER_ERR_INVALID;
+    }
+    for (int s = 0; s < b->n_sources; ++s) {
+        const GooferSource &g = b->sources[s];
+        bool bad = g.K < 0 || g.T < 0 || g.N < 0;
+        for (int k = 0; k < 4; ++k) bad = bad || g.formant_len[k] < 0;
+        if (bad) { gf_set_error("source %d: negative size", s); return GOOFER_ERR_INVALID; }
     }
     return GOOFER_OK;
 }
@@ -724,6 +731,15 @@ static int gf_render_wave(const GooferBatch *b, const std::vector<GfNotePlan> &a
         }
     }
     gf_htrace("wave: phase generator launched");
+    {
+        size_t ne = 0, nf = 0;
+        for (int i = 0; i < nn; ++i) {
+            size_t a, c, d;
+            gf_note_work_counts(wh.plans[i], &a, &c, &d);
+            ne += a; nf += c;
+        }
+        wh.env_work.reserve(ne + 8); wh.frame_work.reserve(nf + 8); wh.fir.reserve((size_t)nn * 6 + 8);
+    }
     if (uploads && *uploads) {
         // the host entry point's H2D copies: issued while the generator runs and before the host builds the work lists,
         // so that the sources are in HBM by the time the first kernel that needs them is enqueued

@@ -149,9 +149,6 @@ static int gf_render_batch_host_impl(const GooferBatch *b)
         cudaEventRecord(ev_t0, st_in);
     }
 
-    std::vector<GfNotePlan> plans;
-    if ((rc = gf_make_plans(b, plans)) != GOOFER_OK) return rc;
-
     // ---- device image of every input array (same element offsets as on the host) ----
     Bump sz{nullptr, 0, 0};
     const void *small_dev = nullptr;
@@ -203,6 +200,83 @@ static int gf_render_batch_host_impl(const GooferBatch *b)
         g_stats.d2h_bytes += (int64_t)bytes;
         return GOOFER_OK;
     };
+    // The sources and bends go up FIRST, before the notes are even planned: their places in the device image depend on
+    // the descriptor alone, and the 0.3 ms they spend on the wire (plus 0.1 ms of host time to issue them) then hide
+    // behind the planning / carving / list building the host does next -- the first kernel that needs them finds them
+    // in HBM.  (Round 1 planned first; with device-drawn phases the call is no longer bound by a 380 MB phase upload
+    // that dwarfed this.)
+    if (trace) h_first_copy = now_ms();
+    // The small per-source arrays (mel-knot frequencies, four formant tracks: a few KB each) are gathered in the
+    // pinned staging arena and go up as ONE copy -- hundreds of tiny cudaMemcpyAsync calls cost more host time
+    // than the transfer itself.  They were carved back to back (see `carve`), so one device range covers them.
+    {
+        size_t small_bytes = 0;
+        for (int s = 0; s < b->n_sources; ++s) {
+            const GooferSource &g = b->sources[s];
+            if (g.hz_knots) small_bytes += (sizeof(float) * (size_t)g.K + 255) & ~(size_t)255;
+            for (int k = 0; k < 4; ++k) if (g.formants[k]) small_bytes += (sizeof(double) * (size_t)g.formant_len[k] + 255) & ~(size_t)255;
+        }
+        if (small_bytes) {
+            char *stage = (char *)gf_pin_take(small_bytes);
+            if (!stage) { gf_set_error("cudaMallocHost failed for the source staging arena"); return GOOFER_ERR_CUDA; }
+            size_t off = 0;
+            for (int s = 0; s < b->n_sources; ++s) {
+                const GooferSource &g = b->sources[s];
+                if (g.hz_knots) { std::memcpy(stage + off, g.hz_knots, sizeof(float) * (size_t)g.K); off += (sizeof(float) * (size_t)g.K + 255) & ~(size_t)255; }
+                for (int k = 0; k < 4; ++k)
+                    if (g.formants[k]) { std::memcpy(stage + off, g.formants[k], sizeof(double) * (size_t)g.formant_len[k]); off += (sizeof(double) * (size_t)g.formant_len[k] + 255) & ~(size_t)255; }
+            }
+            if ((rc = h2d(small_dev, stage, small_bytes))) return rc;
+        }
+    }
+    // source envelopes, voicing masks, bends: one gather kernel when every array is page-locked (see gf_pull_kernel),
+    // else one copy-engine transfer per array
+    {
+        struct Cp { const void *dst, *src; size_t bytes; };
+        std::vector<Cp> cps;
+        for (int s = 0; s < b->n_sources; ++s) {
+            const GooferSource &g = b->sources[s];
+            const GooferSource &d = ds[s];
+            if (g.knots_log_f16) cps.push_back({d.knots_log_f16, g.knots_log_f16, sizeof(uint16_t) * (size_t)g.K * g.T});
+            if (g.env_dense) cps.push_back({d.env_dense, g.env_dense, sizeof(float) * (size_t)GF_NBINS * g.T});
+            if (g.mask) cps.push_back({d.mask, g.mask, sizeof(float) * (size_t)g.N});
+        }
+        cps.push_back({db.bend_cents, b->bend_cents, sizeof(float) * (size_t)b->bend_total});
+        bool pull = cps.size() > 8 && !getenv("GOOFER_HOST_NO_PULL");
+        std::vector<GfPullJob> jobs;
+        unsigned int blocks = 0;
+        for (size_t i = 0; pull && i < cps.size(); ++i) {
+            if (!cps[i].bytes) continue;
+            cudaPointerAttributes at;
+            if (cudaPointerGetAttributes(&at, cps[i].src) != cudaSuccess || at.type != cudaMemoryTypeHost || !at.devicePointer) {
+                cudaGetLastError();
+                pull = false;
+                break;
+            }
+            jobs.push_back({(const char *)at.devicePointer, (char *)const_cast<void *>(cps[i].dst), (unsigned long long)cps[i].bytes, blocks, 0u});
+            blocks += (unsigned int)((cps[i].bytes + GF_PULL_BLOCK - 1) / GF_PULL_BLOCK);
+        }
+        if (pull && !jobs.empty()) {
+            GfPullJob *stage = (GfPullJob *)gf_pin_take(jobs.size() * sizeof(GfPullJob));
+            if (!stage) { gf_set_error("cudaMallocHost failed for the gather table"); return GOOFER_ERR_CUDA; }
+            std::memcpy(stage, jobs.data(), jobs.size() * sizeof(GfPullJob));
+            // on the upload stream: the first kernels that need the sources wait for its event (src_ready below), the
+            // phase generator of the first wave runs beside it
+            if ((rc = gf_meta_copy(pull_tab, stage, jobs.size() * sizeof(GfPullJob), st_in)) != GOOFER_OK) return rc;
+            gf_pull_kernel<<<blocks, 256, 0, st_in>>>(pull_tab, (int)jobs.size());
+            GF_CUDA(cudaGetLastError());
+            for (const Cp &c : cps) g_stats.h2d_bytes += (int64_t)c.bytes;
+        } else {
+            for (const Cp &c : cps)
+                if ((rc = h2d(c.dst, c.src, c.bytes))) return rc;
+        }
+    }
+
+
+    std::vector<GfNotePlan> plans;
+    if ((rc = gf_make_plans(b, plans)) != GOOFER_OK) return rc;
+    gf_htrace("host: notes planned");
+
     // ---- parts: runs of consecutive notes whose phases travel together ----
     // Measured on B200 (c2, 1,024 notes, 5.7 ms of kernels): the phase upload takes 7.4 ms (380 MB at 52 GB/s) and the
     // download 4.5 ms (180 MB at ~40 GB/s while the upload runs); the first output exists only after the preparation
@@ -301,85 +375,12 @@ static int gf_render_batch_host_impl(const GooferBatch *b)
         }
         rg[c] = r;
     }
-    // Everything that crosses PCIe towards the device, as one deferred step: with device-drawn phases the first wave's
-    // phase generator needs nothing from the host but its job list, so it is launched FIRST and these copies (0.1 ms of
-    // host time to issue, 0.3 ms on the wire) run beside it; with host-supplied phases they are issued right away -- the
-    // call is then bound by the 355 KB of phases per note.
     std::vector<GfPart> parts(n_chunks);
     for (int c = 0; c < n_chunks; ++c) {
         parts[c].note_end = ends[c];
-        parts[c].phi_ready = g_hc.ev[2 * c];                       // recorded by issue_uploads, before anything waits for it
+        parts[c].phi_ready = g_hc.ev[2 * c];
         parts[c].done = g_hc.ev[2 * c + 1];
     }
-    auto issue_uploads = [&]() -> int {
-        int rc = GOOFER_OK;
-    if (trace) h_first_copy = now_ms();
-    // The small per-source arrays (mel-knot frequencies, four formant tracks: a few KB each) are gathered in the
-    // pinned staging arena and go up as ONE copy -- hundreds of tiny cudaMemcpyAsync calls cost more host time
-    // than the transfer itself.  They were carved back to back (see `carve`), so one device range covers them.
-    {
-        size_t small_bytes = 0;
-        for (int s = 0; s < b->n_sources; ++s) {
-            const GooferSource &g = b->sources[s];
-            if (g.hz_knots) small_bytes += (sizeof(float) * (size_t)g.K + 255) & ~(size_t)255;
-            for (int k = 0; k < 4; ++k) if (g.formants[k]) small_bytes += (sizeof(double) * (size_t)g.formant_len[k] + 255) & ~(size_t)255;
-        }
-        if (small_bytes) {
-            char *stage = (char *)gf_pin_take(small_bytes);
-            if (!stage) { gf_set_error("cudaMallocHost failed for the source staging arena"); return GOOFER_ERR_CUDA; }
-            size_t off = 0;
-            for (int s = 0; s < b->n_sources; ++s) {
-                const GooferSource &g = b->sources[s];
-                if (g.hz_knots) { std::memcpy(stage + off, g.hz_knots, sizeof(float) * (size_t)g.K); off += (sizeof(float) * (size_t)g.K + 255) & ~(size_t)255; }
-                for (int k = 0; k < 4; ++k)
-                    if (g.formants[k]) { std::memcpy(stage + off, g.formants[k], sizeof(double) * (size_t)g.formant_len[k]); off += (sizeof(double) * (size_t)g.formant_len[k] + 255) & ~(size_t)255; }
-            }
-            if ((rc = h2d(small_dev, stage, small_bytes))) return rc;
-        }
-    }
-    // source envelopes, voicing masks, bends: one gather kernel when every array is page-locked (see gf_pull_kernel),
-    // else one copy-engine transfer per array
-    {
-        struct Cp { const void *dst, *src; size_t bytes; };
-        std::vector<Cp> cps;
-        for (int s = 0; s < b->n_sources; ++s) {
-            const GooferSource &g = b->sources[s];
-            const GooferSource &d = ds[s];
-            if (g.knots_log_f16) cps.push_back({d.knots_log_f16, g.knots_log_f16, sizeof(uint16_t) * (size_t)g.K * g.T});
-            if (g.env_dense) cps.push_back({d.env_dense, g.env_dense, sizeof(float) * (size_t)GF_NBINS * g.T});
-            if (g.mask) cps.push_back({d.mask, g.mask, sizeof(float) * (size_t)g.N});
-        }
-        cps.push_back({db.bend_cents, b->bend_cents, sizeof(float) * (size_t)b->bend_total});
-        bool pull = cps.size() > 8 && !getenv("GOOFER_HOST_NO_PULL");
-        std::vector<GfPullJob> jobs;
-        unsigned int blocks = 0;
-        for (size_t i = 0; pull && i < cps.size(); ++i) {
-            if (!cps[i].bytes) continue;
-            cudaPointerAttributes at;
-            if (cudaPointerGetAttributes(&at, cps[i].src) != cudaSuccess || at.type != cudaMemoryTypeHost || !at.devicePointer) {
-                cudaGetLastError();
-                pull = false;
-                break;
-            }
-            jobs.push_back({(const char *)at.devicePointer, (char *)const_cast<void *>(cps[i].dst), (unsigned long long)cps[i].bytes, blocks, 0u});
-            blocks += (unsigned int)((cps[i].bytes + GF_PULL_BLOCK - 1) / GF_PULL_BLOCK);
-        }
-        if (pull && !jobs.empty()) {
-            GfPullJob *stage = (GfPullJob *)gf_pin_take(jobs.size() * sizeof(GfPullJob));
-            if (!stage) { gf_set_error("cudaMallocHost failed for the gather table"); return GOOFER_ERR_CUDA; }
-            std::memcpy(stage, jobs.data(), jobs.size() * sizeof(GfPullJob));
-            // on the upload stream: the first kernels that need the sources wait for its event (src_ready below), the
-            // phase generator of the first wave runs beside it
-            if ((rc = gf_meta_copy(pull_tab, stage, jobs.size() * sizeof(GfPullJob), st_in)) != GOOFER_OK) return rc;
-            gf_pull_kernel<<<blocks, 256, 0, st_in>>>(pull_tab, (int)jobs.size());
-            GF_CUDA(cudaGetLastError());
-            for (const Cp &c : cps) g_stats.h2d_bytes += (int64_t)c.bytes;
-        } else {
-            for (const Cp &c : cps)
-                if ((rc = h2d(c.dst, c.src, c.bytes))) return rc;
-        }
-    }
-
     // uploads: normals of every part (the preparation kernels of the whole batch need them), then the phases part by part
     for (int c = 0; c < n_chunks; ++c)
         if (rg[c].nhi > rg[c].nlo && (rc = h2d(db.normals + rg[c].nlo, b->normals + rg[c].nlo, sizeof(double) * (size_t)(rg[c].nhi - rg[c].nlo)))) return rc;
@@ -389,17 +390,8 @@ static int gf_render_batch_host_impl(const GooferBatch *b)
         if (rg[c].phi > rg[c].plo && (rc = h2d(db.phi + rg[c].plo, b->phi + rg[c].plo, sizeof(float) * (size_t)(rg[c].phi - rg[c].plo)))) return rc;
         GF_CUDA(cudaEventRecord(g_hc.ev[2 * c], st_in));             // this part's phases
     }
-        return GOOFER_OK;
-    };
-    bool defer_uploads = false;
-    for (int i = 0; i < b->n_notes && !defer_uploads; ++i) defer_uploads = plans[i].phi_rng_mask != 0;
-    if (getenv("GOOFER_HOST_NO_DEFER")) defer_uploads = false;
-    std::function<int()> deferred;
-    if (defer_uploads) deferred = issue_uploads;
-    else if ((rc = issue_uploads()) != GOOFER_OK) return rc;
     // one render of the whole batch: preparation kernels run once at full width; frame / peak / mix go part by part
-    if ((rc = gf_render_batch_ex(&db, g_hc.ws, g_hc.ws_cap, st, parts.data(), n_chunks, &plans, g_hc.ev[2 * n_chunks], defer_uploads ? &deferred : nullptr)) != GOOFER_OK) return rc;
-    if (defer_uploads && deferred) { gf_set_error("internal: the deferred uploads were never issued"); return GOOFER_ERR_CUDA; }
+    if ((rc = gf_render_batch_ex(&db, g_hc.ws, g_hc.ws_cap, st, parts.data(), n_chunks, &plans, g_hc.ev[2 * n_chunks])) != GOOFER_OK) return rc;
     int *status_host = (int *)gf_pin_take(256);              // render status word (overflowed pulse lists), read back with the results
     if (!status_host) { gf_set_error("cudaMallocHost failed for the status word"); return GOOFER_ERR_CUDA; }
     status_host[0] = 0; status_host[1] = -1;

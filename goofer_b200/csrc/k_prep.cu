@@ -248,10 +248,25 @@ void gf_launch_tracks(const GfNotePlan *plans, const GfNoteDev *notes, const GfS
 #define GF_ROW_L 32         // left padding of a row (reflect halo, radius <= 28)
 #define GF_ROW_LEN 600      // 32 + 513 + 55: the FIR windows of the last lanes read up to bin index 561
 
+// unroll factor of the gather loops that write their row straight back to shared memory (fry, F1-F4, g): full unrolling
+// (17 copies each) is what made the kernel 150 KB of code
+#ifndef GF_ENV_GU
+#define GF_ENV_GU 17
+#endif
+#define GF_STR_(x) #x
+#define GF_UNROLL_(n) _Pragma(GF_STR_(unroll n))
+#define GF_ENV_GATHER_UNROLL GF_UNROLL_(GF_ENV_GU)
+
+// gf_env_mix (gf_maps.cuh: loop / cross-fade / stretch / velocity maps, ~1,000 instructions inlined) runs once per frame
+// and warp: called out of line so that it does not sit in the instruction stream of the per-bin hot loop (the kernel's
+// 150 KB of code overflowed the instruction cache: 0.98 "no instruction" stalls per issue in ncu, round 2)
+__device__ __noinline__ void gf_env_mix_ool(const GfNotePlan &p, int t, GfMix &m) { gf_env_mix(p, t, m); }
+
 #ifndef GF_ENV_TPC
-#define GF_ENV_TPC 2                // tiles (of GF_FT frames) per CTA: the CTA prologue (a chain of dependent record loads, the
-                                    // per-note tables, a barrier) is paid once per GF_ENV_TPC frames of a warp, and from the
-                                    // second frame on the source row is already in shared memory (cp.async, see `nxt`)
+#define GF_ENV_TPC 1                // tiles (of GF_FT frames) per CTA.  With 2..4 the CTA prologue (a chain of dependent record loads,
+                                    // the per-note tables, a barrier) is paid once per GF_ENV_TPC frames of a warp and, from the second
+                                    // frame on, the source row is already in shared memory (cp.async, see `nxt`).  Measured on B200
+                                    // (round 2, c2): 1.251 / 1.279 / 1.343 / 1.340 ms at 1 / 2 / 3 / 4 tiles -- one tile per CTA stays
 #endif
 struct GfEnvSmem {
     float rows[GF_ENV_WARPS][2][GF_ROW_LEN];
@@ -366,7 +381,7 @@ gf_env_kernel(const int2 *__restrict__ work, const GfNotePlan *__restrict__ plan
     {
         const int t = tile0 * GF_FT + warp;
         if (t < pl.T_out) {
-            gf_env_mix(pl, min(t, pl.T_env - 1), mix);
+            gf_env_mix_ool(pl, min(t, pl.T_env - 1), mix);
             const float *src0 = sc.envS + (size_t)gf_src_frame(pl, mix.f[0]) * GF_ENVS_LD;
 #pragma unroll
             for (int e = 0; e < GF_EPL; ++e) { const int b = lane + 32 * e; if (b < GF_NBINS) pre[e] = src0[b]; }
@@ -377,7 +392,7 @@ gf_env_kernel(const int2 *__restrict__ work, const GfNotePlan *__restrict__ plan
     auto fetch_next = [&](int t) {
         if (t >= pl.T_out) return;
         GfMix mx;
-        gf_env_mix(pl, min(t, pl.T_env - 1), mx);
+        gf_env_mix_ool(pl, min(t, pl.T_env - 1), mx);
         const float *src = sc.envS + (size_t)gf_src_frame(pl, mx.f[0]) * GF_ENVS_LD;
         for (int c = lane; c < GF_ENVS_LD / 4; c += 32) __pipeline_memcpy_async(&sm.nxt[warp][4 * c], src + 4 * c, 16);
         __pipeline_commit();
@@ -416,7 +431,7 @@ gf_env_kernel(const int2 *__restrict__ work, const GfNotePlan *__restrict__ plan
     else if (lane < 8) { if (pl.any_F_shift) trk = nd.trk_canon[(size_t)(lane - 4) * pl.T_env + te]; }
 #if GF_ENV_TPC > 1
     if (it > 0) {
-        gf_env_mix(pl, te, mix);
+        gf_env_mix_ool(pl, te, mix);
         __pipeline_wait_prior(0);                         // this frame's source row, requested while the previous frame was shaped
         __syncwarp();                                     // (also: the previous frame's row reads are done before the rows are rewritten)
 #pragma unroll
@@ -534,7 +549,7 @@ gf_env_kernel(const int2 *__restrict__ work, const GfNotePlan *__restrict__ plan
             const double s = 1.0 - (double)wfr * (1.0 - 0.92);
             if (!(fabs(s - 1.0) < 1e-6)) {
                 const double inv_s = 1.0 / s;
-#pragma unroll
+GF_ENV_GATHER_UNROLL
                 for (int e = 0; e < GF_EPL; ++e) {
                     const int b = lane + 32 * e;
                     if (b < GF_NBINS) {
@@ -606,7 +621,7 @@ gf_env_kernel(const int2 *__restrict__ work, const GfNotePlan *__restrict__ plan
         const int th1 = __shfl_sync(0xffffffffu, th, 0), th2 = __shfl_sync(0xffffffffu, th, 1), th3 = __shfl_sync(0xffffffffu, th, 2),
                   th4 = __shfl_sync(0xffffffffu, th, 3), th5 = __shfl_sync(0xffffffffu, th, 4);
         if (mono) {
-#pragma unroll
+GF_ENV_GATHER_UNROLL
             for (int e = 0; e < GF_EPL; ++e) {
                 const int b = lane + 32 * e;
                 if (b < GF_NBINS) {
@@ -619,7 +634,8 @@ gf_env_kernel(const int2 *__restrict__ work, const GfNotePlan *__restrict__ plan
                         const double xdj = kx[j], xsj = kx[6 + j];
                         wf = (xdj == x) ? xsj : kx[12 + j] * (x - xdj) + xsj;
                     }
-                    oth[b] = gf_grid_interp(cur, wf, step, inv_step, nyq);
+                    // ascending knots: wf lies in [0, nyq] up to an ulp, where extrapolation and the end lerp coincide to 1e-12
+                    oth[b] = gf_grid_lerp(cur, wf * inv_step);
                 }
             }
         } else {
@@ -646,7 +662,7 @@ gf_env_kernel(const int2 *__restrict__ work, const GfNotePlan *__restrict__ plan
     // ---- g: shift all formants (GOOFER.py:618-627) ----
     if (pl.formant_shift != 1.0) {
         const double inv_r = 1.0 / pl.formant_shift;
-#pragma unroll
+GF_ENV_GATHER_UNROLL
         for (int e = 0; e < GF_EPL; ++e) {
             // freqs / ratio on the freqs grid: in bins that is b / ratio, clipped to [0, 512]
             const int b = lane + 32 * e;
