@@ -200,11 +200,13 @@ static int gf_render_batch_host_impl(const GooferBatch *b)
         g_stats.d2h_bytes += (int64_t)bytes;
         return GOOFER_OK;
     };
-    // The sources and bends go up FIRST, before the notes are even planned: their places in the device image depend on
-    // the descriptor alone, and the 0.3 ms they spend on the wire (plus 0.1 ms of host time to issue them) then hide
-    // behind the planning / carving / list building the host does next -- the first kernel that needs them finds them
-    // in HBM.  (Round 1 planned first; with device-drawn phases the call is no longer bound by a 380 MB phase upload
-    // that dwarfed this.)
+    // The sources and bends: their places in the device image depend on the descriptor alone, so they need no planning.
+    // With host-supplied phases they go up FIRST (the call is then bound by the 355 KB of phases per note queued behind
+    // them).  With device-drawn phases nothing big crosses PCIe, and the 0.1 ms of host time it takes to issue them is
+    // better spent AFTER the first wave's phase generator has been launched (gf_render_wave calls `deferred`): the
+    // generator (0.3 ms) then covers both the issue and the 0.3 ms on the wire.
+    auto upload_sources = [&]() -> int {
+        int rc = GOOFER_OK;
     if (trace) h_first_copy = now_ms();
     // The small per-source arrays (mel-knot frequencies, four formant tracks: a few KB each) are gathered in the
     // pinned staging arena and go up as ONE copy -- hundreds of tiny cudaMemcpyAsync calls cost more host time
@@ -272,6 +274,11 @@ static int gf_render_batch_host_impl(const GooferBatch *b)
         }
     }
 
+
+        return GOOFER_OK;
+    };
+    const bool defer_sources = (!b->phi || b->phi_total <= 1) && !getenv("GOOFER_HOST_NO_DEFER");
+    if (!defer_sources && (rc = upload_sources()) != GOOFER_OK) return rc;
 
     std::vector<GfNotePlan> plans;
     if ((rc = gf_make_plans(b, plans)) != GOOFER_OK) return rc;
@@ -385,13 +392,20 @@ static int gf_render_batch_host_impl(const GooferBatch *b)
     for (int c = 0; c < n_chunks; ++c)
         if (rg[c].nhi > rg[c].nlo && (rc = h2d(db.normals + rg[c].nlo, b->normals + rg[c].nlo, sizeof(double) * (size_t)(rg[c].nhi - rg[c].nlo)))) return rc;
     if (b->f0_curves && b->f0_total > 0 && (rc = h2d(db.f0_curves, b->f0_curves, sizeof(float) * (size_t)b->f0_total))) return rc;
-    GF_CUDA(cudaEventRecord(g_hc.ev[2 * n_chunks], st_in));          // sources, bends, normals, f0 curves
+    if (!defer_sources) GF_CUDA(cudaEventRecord(g_hc.ev[2 * n_chunks], st_in));          // sources, bends, normals, f0 curves
+    std::function<int()> deferred = [&]() -> int {
+        const int r = upload_sources();
+        if (r != GOOFER_OK) return r;
+        GF_CUDA(cudaEventRecord(g_hc.ev[2 * n_chunks], st_in));      // recorded before anything waits for it (gf_render_wave)
+        return GOOFER_OK;
+    };
     for (int c = 0; c < n_chunks; ++c) {
         if (rg[c].phi > rg[c].plo && (rc = h2d(db.phi + rg[c].plo, b->phi + rg[c].plo, sizeof(float) * (size_t)(rg[c].phi - rg[c].plo)))) return rc;
         GF_CUDA(cudaEventRecord(g_hc.ev[2 * c], st_in));             // this part's phases
     }
     // one render of the whole batch: preparation kernels run once at full width; frame / peak / mix go part by part
-    if ((rc = gf_render_batch_ex(&db, g_hc.ws, g_hc.ws_cap, st, parts.data(), n_chunks, &plans, g_hc.ev[2 * n_chunks])) != GOOFER_OK) return rc;
+    if ((rc = gf_render_batch_ex(&db, g_hc.ws, g_hc.ws_cap, st, parts.data(), n_chunks, &plans, g_hc.ev[2 * n_chunks], defer_sources ? &deferred : nullptr)) != GOOFER_OK) return rc;
+    if (defer_sources && deferred) { gf_set_error("internal: the deferred source uploads were never issued"); return GOOFER_ERR_CUDA; }
     int *status_host = (int *)gf_pin_take(256);              // render status word (overflowed pulse lists), read back with the results
     if (!status_host) { gf_set_error("cudaMallocHost failed for the status word"); return GOOFER_ERR_CUDA; }
     status_host[0] = 0; status_host[1] = -1;
