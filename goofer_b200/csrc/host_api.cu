@@ -200,11 +200,10 @@ static int gf_render_batch_host_impl(const GooferBatch *b)
         g_stats.d2h_bytes += (int64_t)bytes;
         return GOOFER_OK;
     };
-    // The sources and bends: their places in the device image depend on the descriptor alone, so they need no planning.
-    // With host-supplied phases they go up FIRST (the call is then bound by the 355 KB of phases per note queued behind
-    // them).  With device-drawn phases nothing big crosses PCIe, and the 0.1 ms of host time it takes to issue them is
-    // better spent AFTER the first wave's phase generator has been launched (gf_render_wave calls `deferred`): the
-    // generator (0.3 ms) then covers both the issue and the 0.3 ms on the wire.
+    // The sources and bends: their places in the device image depend on the descriptor alone, so they need no planning
+    // and go up FIRST, before the notes are planned: the 0.3 ms they spend on the wire (plus 0.1 ms of host time to issue
+    // them) hide behind the planning / carving / list building the host does next.  (Alternative, kept as a knob: issue
+    // them right after the first wave's phase generator has been launched -- gf_render_wave calls `deferred`.)
     auto upload_sources = [&]() -> int {
         int rc = GOOFER_OK;
     if (trace) h_first_copy = now_ms();
@@ -277,7 +276,10 @@ static int gf_render_batch_host_impl(const GooferBatch *b)
 
         return GOOFER_OK;
     };
-    const bool defer_sources = (!b->phi || b->phi_total <= 1) && !getenv("GOOFER_HOST_NO_DEFER");
+    // Measured on B200 (c2, device-drawn phases, PCM16 out): issued first 5.48-5.50 ms per call, deferred behind the generator
+    // 5.65-5.67 ms (the sources then reach HBM at 0.91 ms instead of 0.46 ms and the preparation kernels wait for them):
+    // the deferral is an opt-in knob (GOOFER_HOST_DEFER=1), off by default.
+    const bool defer_sources = (!b->phi || b->phi_total <= 1) && getenv("GOOFER_HOST_DEFER") != nullptr;
     if (!defer_sources && (rc = upload_sources()) != GOOFER_OK) return rc;
 
     std::vector<GfNotePlan> plans;
