@@ -361,7 +361,11 @@ def run_native(args):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: goofer_b200 has no CPU fallback")
     from goofer_b200 import shard
-    numa = shard.bind_rank_to_gpu_numa(local)                 # before any pinned allocation: host buffers on the GPU's node
+    numa = shard.bind_rank_to_gpu_numa(local, world)          # before any pinned allocation: host buffers on the GPU's node
+    if world > 1:
+        # several ranks share one host memory path: render in sub-batches so that the downloads of all ranks spread over the
+        # step instead of bursting at its end (goofer_render_batch_host, GOOFER_HOST_SUBBATCHES); one rank alone renders in one piece
+        os.environ.setdefault("GOOFER_HOST_SUBBATCHES", "2")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
@@ -398,6 +402,8 @@ def run_native(args):
     barrier()
     clocks.live = False
     dev_ms = ev0.elapsed_time(ev1)
+    clocks.stop_flag = True                                   # NVML polling ends with the region it documents: eight ranks polling the
+    clocks.join(timeout=1.0)                                  # driver during the end-to-end legs would perturb what they measure
     launches_step = capi.last_stats()["kernel_launches"]
     prof = capi.profile_summary()
     capi.profile(False)
@@ -456,9 +462,6 @@ def run_native(args):
             e2e_bytes[v] = (st["h2d_bytes"], st["d2h_bytes"])
             if v == E2E_VARIANTS[0] and args.verify > 0:
                 outs_pcm = {j: res[j].copy() for j in vidx}
-    clocks.stop_flag = True
-    clocks.join(timeout=1.0)
-
     keys = [v for v in E2E_VARIANTS if v in e2e_ms]
     t = torch.tensor([dev_ms] + [e2e_ms[v] for v in keys], dtype=torch.float64, device=dev)
     by_rank = [[float(x) for x in t]]
@@ -549,6 +552,7 @@ def run_native(args):
                        "states (GooferNote.phi_rng, bit-identical to the uploaded phases), 16-bit PCM read back (SillySampler.py:1185); "
                        "per-rank wall clock over the timed calls, max over ranks",
                 "host_numa_binding_rank0": numa,
+                "host_subbatches": int(os.environ.get("GOOFER_HOST_SUBBATCHES", "1")),
                 "variants": {v: leg(1 + c, v) for c, v in enumerate(keys)},
                 "variants_note": "every variant: same notes, same noise, same call, max over ranks; host_phases_f32 is the "
                                  "north star's parity transfer set (float phases up, float samples down)"})

@@ -910,9 +910,15 @@ static int gf_render_wave(const GooferBatch *b, const std::vector<GfNotePlan> &a
     return GOOFER_OK;
 }
 
+// A sub-batch = the notes [n0, n1) of the batch rendered by one call (n1 < 0: all of them).  The host entry point renders a
+// large batch as two or more sub-batches back to back on one stream, so that the first one's results travel while the
+// next one computes; `first` = this call decodes the sources and resets the status word (later sub-batches of the same
+// batch find both in the workspace, whose head is laid out identically every time).
+struct GfSubBatch { int n0 = 0, n1 = -1; bool first = true; };
+
 static int gf_render_batch_ex(const GooferBatch *b, void *workspace, size_t workspace_bytes, void *stream, const GfPart *parts, int n_parts,
                               const std::vector<GfNotePlan> *planned = nullptr, cudaEvent_t src_ready = nullptr,
-                              std::function<int()> *uploads = nullptr);
+                              std::function<int()> *uploads = nullptr, GfSubBatch sb = GfSubBatch());
 
 extern "C" int goofer_render_batch(const GooferBatch *b, void *workspace, size_t workspace_bytes, void *stream)
 {
@@ -926,17 +932,19 @@ extern "C" int goofer_render_batch(const GooferBatch *b, void *workspace, size_t
 // uploads (optional): issues the copies that src_ready (and the parts' phi_ready events) stand for; called once, right
 // after the first wave's phase generator has been launched, and reset to empty.
 static int gf_render_batch_ex(const GooferBatch *b, void *workspace, size_t workspace_bytes, void *stream, const GfPart *parts, int n_parts,
-                              const std::vector<GfNotePlan> *planned, cudaEvent_t src_ready, std::function<int()> *uploads)
+                              const std::vector<GfNotePlan> *planned, cudaEvent_t src_ready, std::function<int()> *uploads, GfSubBatch sb)
 {
     int rc = gf_validate(b);
     if (rc != GOOFER_OK) return rc;
-    g_stats.kernel_launches = 0; g_stats.waves = 0;
+    if (sb.first) { g_stats.kernel_launches = 0; g_stats.waves = 0; }
     if (b->n_notes == 0) return GOOFER_OK;
+    const int note_lo = std::max(0, sb.n0), note_hi = sb.n1 < 0 ? b->n_notes : std::min(sb.n1, b->n_notes);
+    if (note_hi <= note_lo) return GOOFER_OK;
     if (!workspace || (!b->out && !b->out_pcm16) || !b->bend_cents) { gf_set_error("NULL workspace / out (and out_pcm16) / bend_cents"); return GOOFER_ERR_INVALID; }
     std::vector<GfNotePlan> own_plans;
     if (!planned && (rc = gf_make_plans(b, own_plans)) != GOOFER_OK) return rc;
     const std::vector<GfNotePlan> &plans = planned ? *planned : own_plans;
-    for (int i = 0; i < b->n_notes; ++i) {
+    for (int i = note_lo; i < note_hi; ++i) {
         const GfNotePlan &p = plans[i];
         for (int k = 0; k < p.n_passes; ++k) {
             const int slot = p.pass_kind[k];
@@ -963,7 +971,7 @@ static int gf_render_batch_ex(const GooferBatch *b, void *workspace, size_t work
     Bump bp{(char *)workspace, workspace_bytes, 0};
     int *d_status = bp.arr<int>(64);                          // render status word (gf_err_scan_kernel): first thing in the workspace
     if (workspace_bytes < 512) { gf_set_error("workspace too small"); return GOOFER_ERR_WORKSPACE; }
-    {
+    if (sb.first) {
         static const int init[2] = {0, 0x7fffffff};
         int *stage = (int *)gf_pin_take(sizeof(init));
         if (!stage) { gf_set_error("cudaMallocHost failed for the metadata staging arena"); return GOOFER_ERR_CUDA; }
@@ -991,7 +999,7 @@ static int gf_render_batch_ex(const GooferBatch *b, void *workspace, size_t work
             if (g.formants[k] && g.formant_len[k] <= 0) { gf_set_error("source %d: formant track %d has length %d", s, k + 1, g.formant_len[k]); return GOOFER_ERR_INVALID; }
         srcs[s] = d;
     }
-    for (int i = 0; i < b->n_notes; ++i) {
+    for (int i = note_lo; i < note_hi; ++i) {
         const GooferSource &g = b->sources[plans[i].src];
         if (g.T <= 0 || g.N <= 0) { gf_set_error("note %d: source %d has no frames / samples", i, plans[i].src); return GOOFER_ERR_INVALID; }
     }
@@ -999,6 +1007,7 @@ static int gf_render_batch_ex(const GooferBatch *b, void *workspace, size_t work
     if (bp.off > bp.cap) { gf_set_error("workspace too small for the source cache (%zu > %zu)", bp.off, bp.cap); return GOOFER_ERR_WORKSPACE; }
     // source table + envelope decode: issued inside the first wave, after its phase generator (gf_render_wave)
     std::function<int()> sources_first = [&]() -> int {
+        if (!sb.first) return GOOFER_OK;                      // decoded by the batch's first sub-batch, same stream
         if (src_ready) GF_CUDA(cudaStreamWaitEvent(st, src_ready, 0));
         if (b->n_sources) {
             void *stage = gf_pin_take(srcs.size() * sizeof(GfSourceDev));
@@ -1015,11 +1024,11 @@ static int gf_render_batch_ex(const GooferBatch *b, void *workspace, size_t work
     bp.off = (bp.off + 255) & ~(size_t)255;
     if (bp.off >= workspace_bytes) { gf_set_error("workspace too small for the source cache"); return GOOFER_ERR_WORKSPACE; }
     const size_t wave_cap = workspace_bytes - bp.off;
-    int i0 = 0;
-    while (i0 < b->n_notes) {
+    int i0 = note_lo;
+    while (i0 < note_hi) {
         size_t tot = 0, np = 0, ne = 0, nf = 0, nfir = 0;
         int i1 = i0;
-        while (i1 < b->n_notes) {
+        while (i1 < note_hi) {
             size_t a, c, d;
             gf_note_work_counts(plans[i1], &a, &c, &d);
             const size_t nb = gf_note_bytes(plans[i1]);

@@ -406,14 +406,31 @@ static int gf_render_batch_host_impl(const GooferBatch *b)
         GF_CUDA(cudaEventRecord(g_hc.ev[2 * c], st_in));             // this part's phases
     }
     // one render of the whole batch: preparation kernels run once at full width; frame / peak / mix go part by part
-    if ((rc = gf_render_batch_ex(&db, g_hc.ws, g_hc.ws_cap, st, parts.data(), n_chunks, &plans, g_hc.ev[2 * n_chunks], defer_sources ? &deferred : nullptr)) != GOOFER_OK) return rc;
+    // GOOFER_HOST_SUBBATCHES=S (default 1): the batch is rendered as S sub-batches back to back on the compute stream, each a
+    // run of whole parts, so that the results of sub-batch k cross PCIe while sub-batch k+1 is PREPARED (not only while its
+    // frame / peak / mix tail runs).  One rank alone loses a little (smaller launches: 1,024 notes take 5.5 ms in one piece);
+    // eight ranks sharing one host memory path gain a lot: in one piece all of them download at the same time, at the end
+    // of the step, and the burst saturates the path (bench.py sets it for multi-rank runs).
+    int n_sub = 1;
+    { const char *e = getenv("GOOFER_HOST_SUBBATCHES"); if (e && atoi(e) > 1) n_sub = std::min(atoi(e), n_chunks); }
+    int64_t launches = 0;
+    int waves = 0;
+    for (int k = 0; k < n_sub; ++k) {
+        GfSubBatch sb;
+        const int c0 = (int)((long)k * n_chunks / n_sub), c1 = (int)((long)(k + 1) * n_chunks / n_sub);
+        sb.n0 = c0 ? ends[c0 - 1] : 0;
+        sb.n1 = ends[c1 - 1];
+        sb.first = k == 0;
+        if ((rc = gf_render_batch_ex(&db, g_hc.ws, g_hc.ws_cap, st, parts.data(), n_chunks, &plans, g_hc.ev[2 * n_chunks],
+                                     (defer_sources && k == 0) ? &deferred : nullptr, sb)) != GOOFER_OK) return rc;
+    }
+    launches = g_stats.kernel_launches;
+    waves = g_stats.waves;
     if (defer_sources && deferred) { gf_set_error("internal: the deferred source uploads were never issued"); return GOOFER_ERR_CUDA; }
     int *status_host = (int *)gf_pin_take(256);              // render status word (overflowed pulse lists), read back with the results
     if (!status_host) { gf_set_error("cudaMallocHost failed for the status word"); return GOOFER_ERR_CUDA; }
     status_host[0] = 0; status_host[1] = -1;
     GF_CUDA(cudaMemcpyAsync(status_host, g_hc.ws, 2 * sizeof(int), cudaMemcpyDeviceToHost, st));
-    const int64_t launches = g_stats.kernel_launches;
-    const int waves = g_stats.waves;
     if (trace) h_enqueued = now_ms();
     for (int c = 0; c < n_chunks; ++c) {
         GF_CUDA(cudaStreamWaitEvent(st_out, g_hc.ev[2 * c + 1], 0));

@@ -101,7 +101,23 @@ def _parse_cpulist(txt: str) -> set:
     return cpus
 
 
-def bind_rank_to_gpu_numa(local_rank: int) -> dict:
+def _bind_slice(local_rank: int, world: int, out: dict) -> dict:
+    """Fallback when the platform reports no NUMA node for the GPU (a VM with a flat topology): give every rank of the box its
+    own contiguous slice of the allowed CPUs, so that the ranks' host threads do not migrate onto each other."""
+    import os
+    if world <= 1:
+        return out
+    cpus = sorted(os.sched_getaffinity(0))
+    k = len(cpus) // world
+    if k < 1:
+        return out
+    mine = set(cpus[local_rank * k:(local_rank + 1) * k])
+    os.sched_setaffinity(0, mine)
+    out.update(bound=True, cpus=len(mine), how="contiguous slice of the allowed CPUs (no NUMA information)")
+    return out
+
+
+def bind_rank_to_gpu_numa(local_rank: int, world: int = 1) -> dict:
     """Pin the calling process to the CPUs of the NUMA node its GPU hangs off, BEFORE it allocates page-locked buffers.
 
     One process per GPU renders its own shard and, through `goofer_render_batch_host`, streams hundreds of MB per call
@@ -127,7 +143,7 @@ def bind_rank_to_gpu_numa(local_rank: int) -> dict:
         out["node"] = node
         if node < 0:
             out["why"] = "no NUMA node reported for the GPU"
-            return out
+            return _bind_slice(local_rank, world, out)
         with open(f"/sys/devices/system/node/node{node}/cpulist") as fh:
             cpus = _parse_cpulist(fh.read())
         allowed = os.sched_getaffinity(0) & cpus
