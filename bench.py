@@ -362,10 +362,12 @@ def run_native(args):
         raise SystemExit("bench.py needs a CUDA device: goofer_b200 has no CPU fallback")
     from goofer_b200 import shard
     numa = shard.bind_rank_to_gpu_numa(local, world)          # before any pinned allocation: host buffers on the GPU's node
-    if world > 1:
+    if world > 2:
         # several ranks share one host memory path: render in sub-batches so that the downloads of all ranks spread over the
-        # step instead of bursting at its end (goofer_render_batch_host, GOOFER_HOST_SUBBATCHES); one rank alone renders in one piece
-        os.environ.setdefault("GOOFER_HOST_SUBBATCHES", "2")
+        # step instead of bursting at its end (goofer_render_batch_host, GOOFER_HOST_SUBBATCHES).  Measured on an 8 x B200 box
+        # (c2, e2e ms per step, max over ranks; S = 1 / 2 / 3 / 4): 4 ranks 6.72 / 6.36 / 6.57 / 6.55, 8 ranks 10.23 / 9.48 /
+        # 8.24 / 8.40; one or two ranks render fastest in one piece (5.6 / 5.8 ms)
+        os.environ.setdefault("GOOFER_HOST_SUBBATCHES", "2" if world <= 4 else "3")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
