@@ -248,6 +248,9 @@ void gf_launch_tracks(const GfNotePlan *plans, const GfNoteDev *notes, const GfS
 #define GF_ROW_L 32         // left padding of a row (reflect halo, radius <= 28)
 #define GF_ROW_LEN 600      // 32 + 513 + 55: the FIR windows of the last lanes read up to bin index 561
 
+#ifndef GF_ENV_FST_SKIP
+#define GF_ENV_FST_SKIP 0
+#endif
 // unroll factor of the gather loops that write their row straight back to shared memory (fry, F1-F4, g): full unrolling
 // (17 copies each) is what made the kernel 150 KB of code
 #ifndef GF_ENV_GU
@@ -530,7 +533,8 @@ gf_env_kernel(const int2 *__restrict__ work, const GfNotePlan *__restrict__ plan
         // step e (1,378 Hz), so "is any of them within 6 sigma of F_k" is a warp-uniform test on the block's edge
         // frequencies: on average five of six bell evaluations (sub, 3 mul, ex2, fma) disappear (the bells span 600 / 1,200 /
         // 2,100 / 3,000 Hz of the 22 kHz).  (Round 1 tried this with the contiguous mapping, where the test is per lane and
-        // cost what it saved.)
+        // cost what it saved.)  Measured on B200 (round 2, c2): 1.20 ms with the skip against 1.165 ms without -- 68 uniform
+        // branches per frame break the interleaving of the independent bell evaluations; off by default (-DGF_ENV_FST_SKIP=1).
         float blo[4], bhi[4];
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
@@ -545,7 +549,10 @@ gf_env_kernel(const int2 *__restrict__ work, const GfNotePlan *__restrict__ plan
             float gain = 1.0f;
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
-                if (bhi[k] > f_lo && blo[k] < f_hi) {                          // warp-uniform
+#if GF_ENV_FST_SKIP
+                if (bhi[k] > f_lo && blo[k] < f_hi)                            // warp-uniform
+#endif
+                {
                     const float d = (fb - Fk[k]) * isg[k];
                     gain *= fmaf(sv[k], __expf(-0.5f * (d * d)), 1.0f);
                 }
