@@ -416,7 +416,11 @@ gf_walk_kernel(const GfPassDev *__restrict__ passes, GfPassScal *scal, int n_pas
             bool tie = false;
 #pragma unroll
             for (int j = 0; j < GF_WALK_S; ++j) tie = tie || (d[j].d0 != d[j].d1);
+#ifdef GF_WALK_ASSUME_NO_TIE
+            const bool warp_tie = false;                           // timing experiment only: wrong on ties
+#else
             const bool warp_tie = __any_sync(0xffffffffu, tie);
+#endif
             GfDelta F;                                             // inclusive scan of the lane maps inside the warp
             if (!warp_tie) {
                 long long g = d[0].d0;
