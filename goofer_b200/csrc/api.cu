@@ -235,6 +235,13 @@ int gf_tables_init(int sr)
     t->sr = sr;
     cudaError_t e = cudaMemcpyToSymbol(d_tab, t, sizeof(GfTables));
     delete t;
+    if (e == cudaSuccess && (dev >= 64 || g_tab_sr[dev] == 0)) {      // independent of the sample rate: once per device
+        GfConvTables *c = new GfConvTables();
+        gf_conv_tw_fill<float, GF_CONV_N32>(c->tw32);
+        gf_conv_tw_fill<double, GF_CONV_N64>(c->tw64);
+        e = cudaMemcpyToSymbol(d_conv, c, sizeof(GfConvTables));
+        delete c;
+    }
     if (e != cudaSuccess) { gf_set_error("table upload failed: %s", cudaGetErrorString(e)); return GOOFER_ERR_CUDA; }
     if (dev < 64) g_tab_sr[dev] = sr;
     return 0;
@@ -825,16 +832,10 @@ static int gf_render_wave(const GooferBatch *b, const std::vector<GfNotePlan> &a
         cudaStream_t st = sx;                                 // shadows: GF_STEP marks / syncs the stream the kernel went to
         gf_launch_mask(d_plans, d_notes, d_srcs, nn, max_n, st); ++L; GF_STEP("mask");
         {
-            double max_sigma = 25.0;
-            bool any64 = false, any32 = false;                // which of the two FIR kernels has work (gf_fir_is_f32 in k_prep.cu)
-            for (const GfFirJob &j : wh.fir) {
-                max_sigma = std::max(max_sigma, j.sigma);
-                ((!j.in_f64 && !j.maxabs && !j.in_cast_f32) ? any32 : any64) = true;
-            }
-            gf_launch_fir(d_fir, (int)wh.fir.size(), max_n, max_sigma, st, any64, any32); L += (int)any64 + (int)any32; GF_STEP("fir");
+            L += gf_launch_fir(wh.fir.data(), d_fir, (int)wh.fir.size(), st); GF_STEP("fir");
         }
         gf_launch_f0(d_plans, d_notes, d_passes, d_srcs, b->bend_cents, b->normals, b->f0_curves, nn, max_n, st); ++L; GF_STEP("f0");
-        gf_launch_walk(d_passes, d_scal, (int)n_pass, max_n, sr, st); L += 2; GF_STEP("walk");     // walk + onset kernels
+        L += gf_launch_walk(d_passes, d_scal, (int)n_pass, max_n, sr, st); GF_STEP("walk");     // onset scan + bit-exact walk + onset kernels
         gf_launch_pulse(d_passes, d_scal, (int)n_pass, max_n, st); ++L; GF_STEP("pulse");
         if ((rc = gf_growl(wh, d_plans, d_notes, d_passes, d_scal, bp, max_n, st, &L)) != GOOFER_OK) return rc;
     }

@@ -5,6 +5,7 @@
 #include "gf_hd.h"
 #include "gf_plan.h"
 #include "gf_fft.cuh"
+#include "gf_conv.cuh"
 
 // ---- constant tables (GOOFER.py:12-46 get_cached_window/freqs/boost/brightness; :241-261 taps) ----
 struct GfTables {
@@ -25,6 +26,13 @@ struct GfTables {
 
 // the library is built as ONE translation unit (goofer_b200.cu includes every k_*.cu)
 __device__ GfTables d_tab;
+
+// twiddles of the overlap-save transforms (gf_conv.cuh gf_conv_tw_fill: per pass, per thread), fp64 cos / sin rounded once
+struct GfConvTables {
+    GfC<float> tw32[GF_CONV_N32];
+    GfC<double> tw64[GF_CONV_N64];
+};
+__device__ GfConvTables d_conv;
 
 // one voicebank source as the kernels see it
 struct GfSourceDev {
@@ -66,6 +74,8 @@ struct GfPassScal {         // zeroed per wave, written by the device
     int err;
     int n_sub_events;
     int sub_max_len;        // longest growl pulse (samples)
+    int sg_seq;             // growl events: the exact-sum scan met a borderline crossing, run the sequential walk
+    int walk_seq;           // pulse onsets: the fixed-point scan met a borderline crossing, run the bit-exact walk
 };
 
 struct GfNoteDev {

@@ -6,10 +6,13 @@ void gf_launch_src_env(const GfSourceDev *srcs, int n_src, int max_T, cudaStream
 void gf_launch_tracks(const GfNotePlan *plans, const GfNoteDev *notes, const GfSourceDev *srcs, int n_notes, cudaStream_t st);
 void gf_launch_env(const int2 *work, int n_work, const GfNotePlan *plans, const GfNoteDev *notes, const GfSourceDev *srcs, cudaStream_t st);
 void gf_launch_mask(const GfNotePlan *plans, const GfNoteDev *notes, const GfSourceDev *srcs, int n_notes, int max_n, cudaStream_t st);
-void gf_launch_fir(const GfFirJob *jobs, int n_jobs, int max_n, double max_sigma, cudaStream_t st, bool any_f64 = true, bool any_f32 = true);
+// Gaussian smoothing jobs: long kernels go to the overlap-save kernels (k_conv.cu), the rest to the direct sliding
+// window (k_prep.cu); h_jobs is the host copy of d_jobs.  Both return the number of kernels launched.
+int gf_launch_fir(const GfFirJob *h_jobs, const GfFirJob *d_jobs, int n_jobs, cudaStream_t st);
+int gf_launch_fftconv(const GfFirJob *h_jobs, const GfFirJob *d_jobs, int n_jobs, cudaStream_t st);
 void gf_launch_f0(const GfNotePlan *plans, const GfNoteDev *notes, const GfPassDev *passes, const GfSourceDev *srcs,
                   const float *bend, const double *normals, const float *f0_curves, int n_notes, int max_n, cudaStream_t st);
-void gf_launch_walk(const GfPassDev *passes, GfPassScal *scal, int n_pass, int max_n, int sr, cudaStream_t st);
+int gf_launch_walk(const GfPassDev *passes, GfPassScal *scal, int n_pass, int max_n, int sr, cudaStream_t st);
 void gf_launch_pulse(const GfPassDev *passes, const GfPassScal *scal, int n_pass, int max_n, cudaStream_t st);
 void gf_launch_frame(const int4 *work, int n_work, const GfPassDev *passes, GfPassScal *scal, const GfNoteDev *notes,
                      const GfNotePlan *plans, cudaStream_t st);

@@ -1,6 +1,7 @@
 // goofer_b200.cu -- single translation unit of libgoofer_b200.so (the kernels share one __device__
 // table object and a handful of inline device helpers, so they are compiled together).
 #include "k_prep.cu"
+#include "k_conv.cu"
 #include "k_excite.cu"
 #include "k_frame.cu"
 #include "k_stage.cu"

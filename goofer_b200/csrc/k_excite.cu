@@ -365,6 +365,9 @@ gf_walk_kernel(const GfPassDev *__restrict__ passes, GfPassScal *scal, int n_pas
     const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int pi = blockIdx.x;
     if (pi >= n_pass) return;
+#if !defined(GF_WALK_SEQ_ONLY)
+    if (!scal[pi].walk_seq) return;                        // gf_walk_scan_kernel placed this pass's onsets
+#endif
     const GfPassDev ps = passes[pi];
     const int n = ps.n_total;
     const double sr = (double)sr_i;
@@ -584,6 +587,140 @@ gf_walk_kernel(const GfPassDev *__restrict__ passes, GfPassScal *scal, int n_pas
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// The same onsets WITHOUT the rounding chain, for the passes where rounding cannot matter.  Only the onset
+// positions (and last_valid_f0 there) leave pulse_train_numba's loop: pulse number c fires at the first sample
+// where the running total reaches c, i.e. where the running maximum of floor(total) grows.  The fp64 total after k
+// additions differs from the exact sum of the increments by at most k half-ulps of the largest total so far; the
+// exact sum exceeds a fixed-point sum of the increments truncated (floor) to multiples of 2^-44 by less than
+// k 2^-44.  So if, at every sample that adds something, the interval
+//     [A_k - m_k, A_k + m_k + (k + 2) 2^-44],   A_k = fixed-point sum,  m_k = (k + 2) max(2^-44, 2 half-ulps)
+// either lies below the next firing level or has the same floor at both ends, the sequential loop and the integer
+// scan fire at the same samples, and the pass is done after one block scan of 64-bit sums and maxima (44,100
+// samples: 22 tiles of 2,048) instead of the ~86 attempt / commit rounds of the bit-exact walk below (0.5 ms
+// however many notes there are: every pass is resident at once and waits on its own chain).  Otherwise -- a flat A
+// note, whose total sits on an integer every 2,205 samples up to rounding; ~2e-4 of the other 1 s notes by
+// chance -- the pass is flagged and gf_walk_kernel renders it.  Negative increments (f0 jitter beyond 100 %) are
+// part of the scan; a negative TOTAL, a non-finite or absurd f0 and an onset on a sample with f0 <= 1e-6 are flagged.
+// The rule in Python integers against the scalar loop: tests/test_walk_arith_cpu.py.
+// ------------------------------------------------------------------------------------------------
+#define GF_WSC_THREADS 256
+#define GF_WSC_PER 8
+#define GF_WSC_UNIT 44
+__global__ void __launch_bounds__(GF_WSC_THREADS)
+gf_walk_scan_kernel(const GfPassDev *__restrict__ passes, GfPassScal *scal, int n_pass, int sr_i)
+{
+    __shared__ long long s_warp[GF_WSC_THREADS / 32];
+    __shared__ int s_wmax[GF_WSC_THREADS / 32];
+    const int pi = blockIdx.x;
+    if (pi >= n_pass) return;
+    const GfPassDev ps = passes[pi];
+    const int n = ps.n_total;
+    const double sr = (double)sr_i, rcp_sr = __drcp_rn((double)sr_i);
+    const float fmax_ok = 0.25f * (float)sr_i;
+    const float *__restrict__ f0 = ps.f0;
+    const bool aligned16 = (reinterpret_cast<size_t>(f0) & 15) == 0;
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    long long carry = 0ll;              // fixed-point total before this tile
+    int fired = 0;                      // running maximum of floor(total) = pulses fired before this tile
+    int bad = 0;
+    for (int base = 0; base < n; base += GF_WSC_THREADS * GF_WSC_PER) {
+        const int i0 = base + tid * GF_WSC_PER;
+        float f[GF_WSC_PER];
+        if (aligned16 && i0 + GF_WSC_PER <= n) {
+            const float4 a = *reinterpret_cast<const float4 *>(f0 + i0), b = *reinterpret_cast<const float4 *>(f0 + i0 + 4);
+            f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
+        } else {
+#pragma unroll
+            for (int e = 0; e < GF_WSC_PER; ++e) f[e] = (i0 + e < n) ? f0[i0 + e] : 0.0f;
+        }
+        long long loc[GF_WSC_PER];
+        long long run = 0ll;
+#pragma unroll
+        for (int e = 0; e < GF_WSC_PER; ++e) {
+            long long u = 0ll;
+            if (f[e] != 0.0f) {
+                if (!(fabsf(f[e]) < fmax_ok)) bad = 1;                                                 // NaN, inf, absurd
+                else u = __double2ll_rd(gf_div_by((double)f[e], sr, rcp_sr) * 17592186044416.0);      // 2^44: exact scaling
+            }
+            run += u;
+            loc[e] = run;
+        }
+        long long incl = run;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const long long t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += t;
+        }
+        if (lane == 31) s_warp[w] = incl;
+        __syncthreads();
+        long long pre = carry + (incl - run), total = carry;
+#pragma unroll
+        for (int q = 0; q < GF_WSC_THREADS / 32; ++q) {
+            const long long t = s_warp[q];
+            if (q < w) pre += t;
+            total += t;
+        }
+        carry = total;
+        // floor(total) after each sample, and its running maximum
+        int F[GF_WSC_PER];
+        int lmax = INT_MIN;
+#pragma unroll
+        for (int e = 0; e < GF_WSC_PER; ++e) {
+            const long long A = pre + loc[e];
+            if (A < 0ll || (A >> 62)) bad = 1;
+            F[e] = (int)(A >> GF_WSC_UNIT);
+            lmax = max(lmax, F[e]);
+        }
+        int pmax = lmax;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, pmax, o);
+            if (lane >= o) pmax = max(pmax, t);
+        }
+        if (lane == 31) s_wmax[w] = pmax;
+        int before = __shfl_up_sync(0xffffffffu, pmax, 1);
+        if (lane == 0) before = INT_MIN;
+        __syncthreads();
+        int tile_max = fired;
+#pragma unroll
+        for (int q = 0; q < GF_WSC_THREADS / 32; ++q) {
+            const int t = s_wmax[q];
+            if (q < w) before = max(before, t);
+            tile_max = max(tile_max, t);
+        }
+        int R = max(before, fired);                       // pulses fired before this thread's first sample
+#pragma unroll
+        for (int e = 0; e < GF_WSC_PER; ++e) {
+            if (f[e] != 0.0f) {
+                const long long A = pre + loc[e];
+                const int Rn = max(R, F[e]);
+                const long long k2 = (long long)(i0 + e) + 2ll;
+                const int sh = max(0, 11 - __clzll((long long)(Rn + 1) << GF_WSC_UNIT));      // two half-ulps of the largest total, units of 2^-44
+                const long long m = k2 << sh;
+                const long long lo = max(A - m, 0ll), hi = A + m + k2;
+                if ((lo >> GF_WSC_UNIT) != (hi >> GF_WSC_UNIT) && (hi >> GF_WSC_UNIT) > (long long)R) bad = 1;
+                if (Rn > R) {
+                    if (!(f[e] > 1e-6f)) bad = 1;                                             // last_valid_f0 would come from an earlier sample
+                    for (int c = R; c < Rn; ++c)
+                        if (c < ps.onset_cap) ps.onsets[c] = make_int4(i0 + e, 0, __float_as_int(f[e]), 0);
+                    R = Rn;
+                }
+            }
+        }
+        fired = tile_max;
+        __syncthreads();
+    }
+    bad = __syncthreads_or(bad);
+    if (tid == 0) {
+        if (bad) scal[pi].walk_seq = 1;
+        else {
+            scal[pi].n_onsets = min(fired, ps.onset_cap);
+            if (fired > ps.onset_cap) scal[pi].err = 1;
+        }
+    }
+}
+
 // per onset: period length T0 = round(sr / last_valid_f0) clipped to [3, 8192] (GOOFER.py:495-499, Python
 // round = half to even), the peak of its LF table (GOOFER.py:524-528) and the two branch points of the table
 // (first j with ti >= Tp, first j with ti >= Tc -- decided with the reference's own fp64 expressions, because
@@ -621,16 +758,23 @@ gf_onset_kernel(const GfPassDev *__restrict__ passes, GfPassScal *scal, int sr_i
     if ((threadIdx.x & 31) == 0 && mx > 0) atomicMax(&scal[blockIdx.y].max_T0, mx);
 }
 
-void gf_launch_walk(const GfPassDev *passes, GfPassScal *scal, int n_pass, int max_n, int sr, cudaStream_t st)
+int gf_launch_walk(const GfPassDev *passes, GfPassScal *scal, int n_pass, int max_n, int sr, cudaStream_t st)
 {
-    if (n_pass <= 0) return;
+    if (n_pass <= 0) return 0;
     // One warp per note costs the fewest issue slots: right when there are enough notes to fill the GPU.  More warps per
     // note cut the latency of a note's chain: right for few and / or long notes.  Measured on B200 (ms, 1 s notes;
     // warps per note 1 / 2 / 4 / 8 / 16): 128 notes .65 .38 .24 .18 .19 | 256: .68 .40 .26 .34 .36 | 512: .69 .43 .50 .65
     // .69 | 1,024: .74 .55 .76 1.13 1.20 | 2,048: .95 1.00 1.29 2.2 2.4; 96 notes of 16 s: 9.9 5.4 2.9 1.8 1.4.
     static int force = -1;
     if (force < 0) { const char *e = getenv("GOOFER_WALK_WARPS"); force = e ? atoi(e) : 0; }
+#if !defined(GF_WALK_SEQ_ONLY)
+    // The scan places the onsets of every pass it can decide; the bit-exact walk then runs for the flagged ones only
+    // (its other CTAs leave at once), so it is sized for a fraction of the passes: more warps per pass.
+    gf_walk_scan_kernel<<<n_pass, GF_WSC_THREADS, 0, st>>>(passes, scal, n_pass, sr);
+    int nw = n_pass <= 640 ? 8 : (n_pass <= 1280 ? 4 : (n_pass <= 6144 ? 2 : 1));
+#else
     int nw = n_pass <= 160 ? 8 : (n_pass <= 320 ? 4 : (n_pass <= 1536 ? 2 : 1));
+#endif
     if (max_n >= 4 * 44100) nw = min(16, 2 * nw);
     if (force == 1 || force == 2 || force == 4 || force == 8 || force == 16) nw = force;
     if (nw == 16) gf_walk_kernel<16><<<n_pass, 512, 0, st>>>(passes, scal, n_pass, sr);
@@ -639,6 +783,11 @@ void gf_launch_walk(const GfPassDev *passes, GfPassScal *scal, int n_pass, int m
     else if (nw == 2) gf_walk_kernel<2><<<n_pass, 64, 0, st>>>(passes, scal, n_pass, sr);
     else gf_walk_kernel<1><<<n_pass, 32, 0, st>>>(passes, scal, n_pass, sr);
     gf_onset_kernel<<<dim3(4, n_pass), 128, 0, st>>>(passes, scal, sr);
+#if !defined(GF_WALK_SEQ_ONLY)
+    return 3;
+#else
+    return 2;
+#endif
 }
 
 

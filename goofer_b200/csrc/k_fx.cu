@@ -38,8 +38,142 @@ gf_sg_f0_kernel(const int *__restrict__ list, const GfNotePlan *__restrict__ pla
 }
 
 // ------------------------------------------------------------------------------------------------
-// sg: sequential event walk (one warp per note; the fp64 phase chain runs left to right like the
-// reference, only the per-sample increments are prepared in parallel)
+// sg: event detection as a scan.  _detect_pulse_events (GOOFER.py:672-698) walks  phase += sub_f0 / sr;
+// if phase >= 1: event, phase -= 1  in fp64, sample by sample.  Only the event POSITIONS leave the loop (the phase
+// itself is never used), and they are the integer crossings of the running sum S_k of the increments -- unless
+// rounding decides a borderline case.  Every addition lands below 2 and rounds by at most 2^-53, the subtraction
+// of 1 is exact, so after k steps the fp64 phase is within k 2^-53 of S_k - (events so far).  The kernel therefore
+//   * sums the increments EXACTLY (each is a 53-bit integer times a power of two: fixed point in units of 2^-88,
+//     128-bit adds) with a block-wide scan,
+//   * places event number F at the sample where floor(S_k) reaches F (slot F - 1: no compaction pass),
+//   * and checks that no S_k lies within (n + 2) 2^-52 of an integer.  If one does (about 1e-11 per sample with
+//     the 75 Hz vibrato on the increments), or an increment is outside [2^-24, 1), the note is flagged and the
+//     sequential walk below renders it, bit for bit like the reference either way.
+// 44,100 dependent DADD / compare / DSUB steps per second of audio (1.3 ms whatever the batch size) become one
+// pass over the samples.
+// ------------------------------------------------------------------------------------------------
+struct GfU128 { unsigned long long lo, hi; };
+__device__ __forceinline__ GfU128 gf_u128_add(GfU128 a, GfU128 b)
+{
+    GfU128 r;
+    r.lo = a.lo + b.lo;
+    r.hi = a.hi + b.hi + (r.lo < a.lo ? 1ull : 0ull);
+    return r;
+}
+#define GF_SGS_THREADS 256
+#define GF_SGS_PER 8
+#define GF_SGS_UNIT 88          // S in units of 2^-88
+
+__global__ void __launch_bounds__(GF_SGS_THREADS)
+gf_sg_scan_kernel(const int *__restrict__ list, const GfNotePlan *__restrict__ plans, const GfNoteDev *__restrict__ notes, GfPassScal *scal)
+{
+    __shared__ GfU128 s_warp[GF_SGS_THREADS / 32];
+    const int ni = list[blockIdx.x];
+    const GfNotePlan &pl = plans[ni];
+    const GfNoteDev nd = notes[ni];
+    const int n = pl.n_total;
+    const double sr = (double)pl.sr;
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    // |fp64 phase - exact| <= k 2^-53: twice that, in units of 2^-64 (the top 64 bits of the fraction)
+    const unsigned long long margin = ((unsigned long long)n + 2ull) << 12;
+    GfU128 carry; carry.lo = 0ull; carry.hi = 0ull;
+    int bad = 0;
+    for (int base = 0; base < n; base += GF_SGS_THREADS * GF_SGS_PER) {
+        const int i0 = base + tid * GF_SGS_PER;
+        float fv[GF_SGS_PER], mv[GF_SGS_PER];
+        if (i0 + GF_SGS_PER <= n) {
+            const float4 a = *reinterpret_cast<const float4 *>(nd.sg_f0 + i0), b = *reinterpret_cast<const float4 *>(nd.sg_f0 + i0 + 4);
+            const float4 c = *reinterpret_cast<const float4 *>(nd.vm + i0), d = *reinterpret_cast<const float4 *>(nd.vm + i0 + 4);
+            fv[0] = a.x; fv[1] = a.y; fv[2] = a.z; fv[3] = a.w; fv[4] = b.x; fv[5] = b.y; fv[6] = b.z; fv[7] = b.w;
+            mv[0] = c.x; mv[1] = c.y; mv[2] = c.z; mv[3] = c.w; mv[4] = d.x; mv[5] = d.y; mv[6] = d.z; mv[7] = d.w;
+        } else {
+#pragma unroll
+            for (int e = 0; e < GF_SGS_PER; ++e) {
+                const bool in = i0 + e < n;
+                fv[e] = in ? nd.sg_f0[i0 + e] : 0.0f;
+                mv[e] = in ? nd.vm[i0 + e] : 0.0f;
+            }
+        }
+        GfU128 loc[GF_SGS_PER];
+        GfU128 run; run.lo = 0ull; run.hi = 0ull;
+        unsigned actm = 0u;
+#pragma unroll
+        for (int e = 0; e < GF_SGS_PER; ++e) {
+            const double sub = (double)fv[e] * 2.0;                 // ratio = 2 ** (12 / 12)
+            const bool act = (mv[e] > 0.0f) && (fv[e] > 0.0f) && !(sub < 1e-2);
+            GfU128 v; v.lo = 0ull; v.hi = 0ull;
+            if (act) {
+                const unsigned long long bits = (unsigned long long)__double_as_longlong(__ddiv_rn(sub, sr));
+                const int ex = (int)(bits >> 52) & 0x7ff;
+                if (ex < 1023 - 24 || ex > 1022) bad = 1;
+                else {
+                    const unsigned long long mant = (bits & 0xfffffffffffffull) | 0x10000000000000ull;
+                    const int sh = ex - 1075 + GF_SGS_UNIT;         // 12 .. 35
+                    v.lo = mant << sh;
+                    v.hi = mant >> (64 - sh);
+                    actm |= 1u << e;
+                }
+            }
+            run = gf_u128_add(run, v);
+            loc[e] = run;
+        }
+        // block-wide exclusive prefix of the per-thread totals
+        GfU128 incl = run;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            GfU128 t;
+            t.lo = __shfl_up_sync(0xffffffffu, incl.lo, o);
+            t.hi = __shfl_up_sync(0xffffffffu, incl.hi, o);
+            if (lane >= o) incl = gf_u128_add(incl, t);
+        }
+        if (lane == 31) s_warp[w] = incl;
+        GfU128 pre;
+        pre.lo = __shfl_up_sync(0xffffffffu, incl.lo, 1);
+        pre.hi = __shfl_up_sync(0xffffffffu, incl.hi, 1);
+        if (lane == 0) { pre.lo = 0ull; pre.hi = 0ull; }
+        __syncthreads();
+        GfU128 total = carry;
+        pre = gf_u128_add(pre, carry);
+#pragma unroll
+        for (int q = 0; q < GF_SGS_THREADS / 32; ++q) {
+            const GfU128 t = s_warp[q];
+            if (q < w) pre = gf_u128_add(pre, t);
+            total = gf_u128_add(total, t);
+        }
+        carry = total;
+        // crossings of this thread's samples
+        unsigned long long Fp = pre.hi >> (GF_SGS_UNIT - 64);
+#pragma unroll
+        for (int e = 0; e < GF_SGS_PER; ++e) {
+            const GfU128 S = gf_u128_add(pre, loc[e]);
+            const unsigned long long F = S.hi >> (GF_SGS_UNIT - 64);
+            if ((actm >> e) & 1u) {
+                const unsigned long long frac = (S.hi << (128 - GF_SGS_UNIT)) | (S.lo >> (GF_SGS_UNIT - 64));     // top 64 bits of the fraction
+                if (frac <= margin || frac >= ~margin) bad = 1;
+                if (F != Fp) {
+                    if (F != Fp + 1ull) bad = 1;
+                    const unsigned long long slot = F - 1ull;
+                    if (slot < (unsigned long long)nd.sg_cap) { nd.sg_ev_i[slot] = i0 + e; nd.sg_ev_f[slot] = (double)fv[e] * 2.0; }
+                }
+            }
+            Fp = F;
+        }
+        __syncthreads();
+    }
+    bad = __syncthreads_or(bad);
+    if (tid == 0) {
+        if (bad) scal[nd.pass0].sg_seq = 1;
+        else {
+            const unsigned long long count = carry.hi >> (GF_SGS_UNIT - 64);
+            scal[nd.pass0].n_sub_events = (int)min(count, (unsigned long long)nd.sg_cap);
+            if (count > (unsigned long long)nd.sg_cap) scal[nd.pass0].err = 2;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// sg: sequential event walk for the notes the scan flagged (one warp per note; the fp64 phase chain runs left to
+// right like the reference, only the per-sample increments are prepared in parallel)
 // ------------------------------------------------------------------------------------------------
 #define GF_SG_WARPS 4
 __global__ void __launch_bounds__(32 * GF_SG_WARPS)
@@ -53,6 +187,9 @@ gf_sg_walk_kernel(const int *__restrict__ list, int n_list, const GfNotePlan *__
     const int ni = list[li];
     const GfNotePlan &pl = plans[ni];
     const GfNoteDev nd = notes[ni];
+#if !defined(GF_SG_SEQ_ONLY)
+    if (!scal[nd.pass0].sg_seq) return;                     // the scan placed this note's events
+#endif
     const int n = pl.n_total;
     const double sr = (double)pl.sr;
     double phase = 0.0;
@@ -235,6 +372,9 @@ int gf_growl(const WaveHost &wh, const GfNotePlan *d_plans, const GfNoteDev *d_n
     const int nl = (int)list.size();
     dim3 g1(std::min(64, (max_n + 255) / 256), nl);
     gf_sg_f0_kernel<<<g1, 256, 0, st>>>(d_list, d_plans, d_notes, d_passes); ++*launches; GF_STEP("sg_f0");
+#if !defined(GF_SG_SEQ_ONLY)
+    gf_sg_scan_kernel<<<nl, GF_SGS_THREADS, 0, st>>>(d_list, d_plans, d_notes, d_scal); ++*launches; GF_STEP("sg_scan");
+#endif
     gf_sg_walk_kernel<<<(nl + GF_SG_WARPS - 1) / GF_SG_WARPS, 32 * GF_SG_WARPS, 0, st>>>(d_list, nl, d_plans, d_notes, d_scal);
     ++*launches; GF_STEP("sg_walk");
     gf_sg_bank_kernel<<<nl, 512, 0, st>>>(d_list, d_plans, d_notes, d_scal); ++*launches; GF_STEP("sg_bank");
@@ -345,9 +485,7 @@ int gf_pitch_dyn(const WaveHost &wh, int n0, int n1, const GfNotePlan *d_plans, 
     if ((rc = gf_upload(bp, list, &d_list, st)) != GOOFER_OK) return rc;
     if ((rc = gf_upload(bp, jobs, &d_jobs, st)) != GOOFER_OK) return rc;
     if (bp.off > bp.cap) { gf_set_error("internal: pd jobs overflow the workspace"); return GOOFER_ERR_WORKSPACE; }
-    double max_sigma = 1.0;
-    for (const GfFirJob &j : jobs) max_sigma = std::max(max_sigma, j.sigma);
-    gf_launch_fir(d_jobs, (int)jobs.size(), max_n, max_sigma, st); ++*launches; GF_STEP("pd_fir");
+    *launches += gf_launch_fir(jobs.data(), d_jobs, (int)jobs.size(), st); GF_STEP("pd_fir");
     gf_pd_ref_kernel<<<(int)list.size(), GF_SEL_THREADS, 0, st>>>(d_list, d_plans, d_notes); ++*launches; GF_STEP("pd_ref");
     return GOOFER_OK;
 }

@@ -12,6 +12,7 @@
 #include <cuda_fp16.h>
 #include <cuda_pipeline.h>
 #include "gf_device.cuh"
+#include "gf_kernels.h"
 #include "gf_maps.cuh"
 
 // ------------------------------------------------------------------------------------------------
@@ -746,8 +747,10 @@ __device__ __forceinline__ bool gf_fir_is_f32(const GfFirJob &jb)
 {
     // f32 input without a max-abs reduction: f32 taps / accumulation (the output may still be stored as fp64: the
     // pitch-dynamics deviation curve, whose 3,529-tap smoothing only feeds a clipped gain in dB)
-    return !jb.in_f64 && !jb.maxabs && !jb.in_cast_f32;
+    return gf_fir_f32(jb.in_f64, jb.maxabs, jb.in_cast_f32);
 }
+// long kernels are rendered by the overlap-save kernels of k_conv.cu
+__device__ __forceinline__ bool gf_fir_is_fft(const GfFirJob &jb) { return gf_fir_wants_fft(jb.sigma, gf_fir_is_f32(jb)); }
 
 // f32 -> f32 jobs (voicing-mask smoothing: sigma 25 on the decimated mask, sigma 20, sigma 441): the same
 // register-tiled sliding window as the envelope kernel, 17 outputs per thread, f32 taps and accumulation
@@ -758,7 +761,7 @@ __global__ void __launch_bounds__(GF_F32_THREADS) gf_fir32_kernel(const GfFirJob
     extern __shared__ __align__(16) float f32sm[];
     __shared__ double red[GF_F32_THREADS / 32];
     const GfFirJob jb = jobs[blockIdx.y];
-    if (!gf_fir_is_f32(jb)) return;
+    if (!gf_fir_is_f32(jb) || gf_fir_is_fft(jb)) return;
     const int n = jb.n;
     const int start = blockIdx.x * GF_F32_TILE;
     if (start >= n) return;
@@ -817,7 +820,7 @@ __global__ void __launch_bounds__(GF_F32_THREADS) gf_fir_kernel(const GfFirJob *
     extern __shared__ double fsm[];
     __shared__ double red[GF_F32_THREADS / 32];
     const GfFirJob jb = jobs[blockIdx.y];
-    if (gf_fir_is_f32(jb)) return;                // handled by gf_fir32_kernel
+    if (gf_fir_is_f32(jb) || gf_fir_is_fft(jb)) return;       // handled by gf_fir32_kernel / gf_fftconv_kernel
     const int n = jb.n;
     const int start = blockIdx.x * GF_F32_TILE;
     if (start >= n) return;
@@ -863,19 +866,36 @@ __global__ void __launch_bounds__(GF_F32_THREADS) gf_fir_kernel(const GfFirJob *
     }
 }
 
-void gf_launch_fir(const GfFirJob *jobs, int n_jobs, int max_n, double max_sigma, cudaStream_t st, bool any_f64, bool any_f32)
+int gf_launch_fir(const GfFirJob *h_jobs, const GfFirJob *d_jobs, int n_jobs, cudaStream_t st)
 {
-    if (n_jobs <= 0 || max_n <= 0) return;
-    const int radius = (int)(4.0 * max_sigma + 0.5);
-    const size_t smem = sizeof(double) * (size_t)((((2 * radius + 1 + 7) & ~7) + 8) + (2 * radius + GF_F32_TILE + 16));
-    static GfSmemLimit memo64;
-    gf_smem_limit(gf_fir_kernel, smem, memo64);
-    dim3 grid((max_n + GF_F32_TILE - 1) / GF_F32_TILE, n_jobs);
-    if (any_f64) gf_fir_kernel<<<grid, GF_F32_THREADS, smem, st>>>(jobs);
-    // f32 jobs
-    const size_t smem32 = sizeof(float) * (size_t)((((2 * radius + 1 + 7) & ~7) + 8) + (2 * radius + GF_F32_TILE + 16) + GF_F32_TILE);
-    static GfSmemLimit memo32;
-    gf_smem_limit(gf_fir32_kernel, smem32, memo32);
-    dim3 grid32((max_n + GF_F32_TILE - 1) / GF_F32_TILE, n_jobs);
-    if (any_f32) gf_fir32_kernel<<<grid32, GF_F32_THREADS, smem32, st>>>(jobs);
+    if (n_jobs <= 0) return 0;
+    int launches = gf_launch_fftconv(h_jobs, d_jobs, n_jobs, st);
+    // the direct kernels: shared memory and grid sized by the jobs they keep
+    int max_n = 0, radius = 0;
+    bool any_f64 = false, any_f32 = false;
+    for (int k = 0; k < n_jobs; ++k) {
+        const GfFirJob &j = h_jobs[k];
+        const bool f32 = gf_fir_f32(j.in_f64, j.maxabs, j.in_cast_f32);
+        if (j.n <= 0 || gf_fir_wants_fft(j.sigma, f32)) continue;
+        max_n = std::max(max_n, j.n);
+        radius = std::max(radius, gf_fir_radius(j.sigma));
+        (f32 ? any_f32 : any_f64) = true;
+    }
+    if (max_n <= 0) return launches;
+    const dim3 grid((max_n + GF_F32_TILE - 1) / GF_F32_TILE, n_jobs);
+    if (any_f64) {
+        const size_t smem = sizeof(double) * (size_t)((((2 * radius + 1 + 7) & ~7) + 8) + (2 * radius + GF_F32_TILE + 16));
+        static GfSmemLimit memo64;
+        gf_smem_limit(gf_fir_kernel, smem, memo64);
+        gf_fir_kernel<<<grid, GF_F32_THREADS, smem, st>>>(d_jobs);
+        ++launches;
+    }
+    if (any_f32) {
+        const size_t smem32 = sizeof(float) * (size_t)((((2 * radius + 1 + 7) & ~7) + 8) + (2 * radius + GF_F32_TILE + 16) + GF_F32_TILE);
+        static GfSmemLimit memo32;
+        gf_smem_limit(gf_fir32_kernel, smem32, memo32);
+        gf_fir32_kernel<<<grid, GF_F32_THREADS, smem32, st>>>(d_jobs);
+        ++launches;
+    }
+    return launches;
 }

@@ -30,5 +30,9 @@ def load():
     L.emul_env_mix.argtypes = [vp, C.c_int, ip, dp]
     L.emul_mask_new.argtypes = [vp, fp, dp]
     L.emul_track_canon.argtypes = [vp, dp, C.c_int, fp]
+    L.emul_fftconv_f32.argtypes = [fp, C.c_int, C.c_double, fp]
+    L.emul_fftconv_f32.restype = C.c_int
+    L.emul_fftconv_f64.argtypes = [dp, C.c_int, C.c_double, dp]
+    L.emul_fftconv_f64.restype = C.c_int
     _lib = L
     return L

@@ -6,6 +6,7 @@
 #include <cmath>
 #include "../../goofer_b200/csrc/gf_fft.cuh"
 #include "../../goofer_b200/csrc/gf_maps.cuh"
+#include "../../goofer_b200/csrc/gf_conv.cuh"
 
 static void tables(std::vector<float2> &tw512, std::vector<float2> &tw1024)
 {
@@ -85,3 +86,79 @@ extern "C" void emul_track_canon(const void *plan, const double *trk, int k, flo
     const GfTrackSlices s = gf_track_slices(p, k);
     for (int t = 0; t < p.T_env; ++t) out[t] = gf_track_canon(p, s, trk, k, t);
 }
+
+// ---- overlap-save Gaussian smoothing (k_conv.cu): the same passes, block layout and spectrum product, run serially ----
+// v[j * 8 + r]: the registers of "thread" j
+template <typename T, int N> static void conv_fft(GfC<T> *buf, const GfC<T> *tw, GfC<T> *v)
+{
+    const int TH = N / 8;
+    constexpr int NS0 = GfConvShape<N>::NS0;
+    if (GfConvShape<N>::R2) {
+        for (int j = 0; j < TH; ++j) gf_conv_r2_store<T, N>(j, buf, &v[8 * j]);
+        for (int j = 0; j < TH; ++j) gf_conv_pass_load<T, N, NS0>(j, buf, tw, &v[8 * j]);
+    } else
+        for (int j = 0; j < TH; ++j) gf_cdft8(&v[8 * j]);
+    for (int j = 0; j < TH; ++j) gf_conv_pass_store<T, N, NS0>(j, buf, &v[8 * j]);
+    for (int j = 0; j < TH; ++j) gf_conv_pass_load<T, N, NS0 * 8>(j, buf, tw, &v[8 * j]);
+    for (int j = 0; j < TH; ++j) gf_conv_pass_store<T, N, NS0 * 8>(j, buf, &v[8 * j]);
+    for (int j = 0; j < TH; ++j) gf_conv_pass_load<T, N, NS0 * 64>(j, buf, tw, &v[8 * j]);
+    for (int j = 0; j < TH; ++j) gf_conv_pass_store<T, N, NS0 * 64>(j, buf, &v[8 * j]);
+    for (int j = 0; j < TH; ++j) gf_conv_pass_load<T, N, NS0 * 512>(j, buf, tw, &v[8 * j]);
+}
+
+static int reflect_idx(int q, int n)
+{
+    if (n <= 1) return 0;
+    const int per = 2 * (n - 1);
+    q %= per;
+    if (q < 0) q += per;
+    return q < n ? q : per - q;
+}
+
+template <typename T, int N> static int conv_run(const T *x, int n, double sigma, T *out)
+{
+    if (!gf_fir_wants_fft(sigma, sizeof(T) == 4)) return 0;
+    const int TH = N / 8;
+    std::vector<GfC<T>> tw(N), buf(GfConvBuf<T, N>::LEN), v((size_t)N);
+    gf_conv_tw_fill<T, N>(tw.data());
+    const int radius = gf_fir_radius(sigma), V = N - 2 * radius;
+    double norm = 0.0;
+    for (int j = 0; j <= 2 * radius; ++j) { const double t = (double)(j - radius) / sigma; norm += std::exp(-0.5 * t * t); }
+    for (int j = 0; j < TH; ++j)
+        for (int r = 0; r < 8; ++r) {
+            const int i = j + r * TH;
+            const int d = i < N - i ? i : N - i;
+            const double t = (double)d / sigma;
+            v[8 * j + r] = gf_c<T>(d <= radius ? (T)(std::exp(-0.5 * t * t) / norm) : (T)0, (T)0);
+        }
+    conv_fft<T, N>(buf.data(), tw.data(), v.data());
+    std::vector<T> h(N);
+    for (int q = 0; q < N; ++q) h[q] = v[q].x * (T)(1.0 / N);
+    auto fetch = [&](int pos) -> T {
+        if (pos >= n + radius || pos < -radius) return (T)0;
+        return x[(pos >= 0 && pos < n) ? pos : reflect_idx(pos, n)];
+    };
+    const int n_pairs = ((n + V - 1) / V + 1) / 2;
+    for (int p = 0; p < n_pairs; ++p) {
+        const int o1 = 2 * p * V;
+        for (int j = 0; j < TH; ++j)
+            for (int r = 0; r < 8; ++r) {
+                const int i = j + r * TH;
+                v[8 * j + r] = gf_c<T>(fetch(o1 - radius + i), fetch(o1 + V - radius + i));
+            }
+        conv_fft<T, N>(buf.data(), tw.data(), v.data());
+        for (int q = 0; q < N; ++q) v[q] = gf_c<T>(v[q].x * h[q], -v[q].y * h[q]);
+        conv_fft<T, N>(buf.data(), tw.data(), v.data());
+        for (int j = 0; j < TH; ++j)
+            for (int r = 0; r < 8; ++r) {
+                const int i = j + r * TH - radius;
+                if (i < 0 || i >= V) continue;
+                if (o1 + i < n) out[o1 + i] = v[8 * j + r].x;
+                if (o1 + V + i < n) out[o1 + V + i] = -v[8 * j + r].y;
+            }
+    }
+    return 1;
+}
+
+extern "C" int emul_fftconv_f32(const float *x, int n, double sigma, float *out) { return conv_run<float, GF_CONV_N32>(x, n, sigma, out); }
+extern "C" int emul_fftconv_f64(const double *x, int n, double sigma, double *out) { return conv_run<double, GF_CONV_N64>(x, n, sigma, out); }

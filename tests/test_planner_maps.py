@@ -94,6 +94,33 @@ def test_fft_passes_match_numpy(emul):
     assert np.max(np.abs(y - x)) <= 2e-6 * np.max(np.abs(x))
 
 
+def _gauss_direct(x, sigma):
+    """gaussian_filter1d as the reference defines it (GOOFER.py:241-261), fp64"""
+    radius = int(4.0 * sigma + 0.5)
+    t = np.arange(-radius, radius + 1, dtype=np.float64)
+    k = np.exp(-0.5 * (t / sigma) ** 2)
+    k /= k.sum()
+    return np.convolve(np.pad(x.astype(np.float64), radius, mode="reflect"), k, mode="valid")
+
+
+@pytest.mark.parametrize("n,sigma", [(44100, 441.0), (5000, 441.0), (9329, 441.0), (44100, 73.5), (70001, 49.0), (3000, 73.5)])
+def test_overlap_save_passes_match_direct_convolution(emul, n, sigma):
+    """k_conv.cu's transform passes, block layout and spectrum product (run serially) against np.convolve"""
+    rng = np.random.default_rng(n)
+    fp, dp = C.POINTER(C.c_float), C.POINTER(C.c_double)
+    x64 = rng.standard_normal(n)
+    ref = _gauss_direct(x64, sigma)
+    y64 = np.zeros(n)
+    assert emul.emul_fftconv_f64(x64.ctypes.data_as(dp), n, sigma, y64.ctypes.data_as(dp)) == (1 if sigma < 256 else 0)
+    if sigma < 256:
+        assert np.max(np.abs(y64 - ref)) <= 1e-14
+    # f32: a mask-like 0/1 signal and a smooth curve plus noise, like the pitch-deviation input
+    for x in ((rng.random(n) < 0.5).astype(np.float32), (np.sin(np.arange(n) / 3000.0) * 2 + 0.01 * rng.standard_normal(n)).astype(np.float32)):
+        y = np.zeros(n, dtype=np.float32)
+        assert emul.emul_fftconv_f32(x.ctypes.data_as(fp), n, sigma, y.ctypes.data_as(fp)) == 1
+        assert np.max(np.abs(y - _gauss_direct(x, sigma))) <= 2e-6
+
+
 def test_planner_statuses(lib):
     feat, sf = cases.source_for(0, 1.0)
     # empty tail: offset past the end -> the reference dies with ZeroDivisionError (SillySampler.py:634)

@@ -216,3 +216,143 @@ def test_walk_with_fp64_deltas_equals_the_scalar_chain(name):
     inc = _cases()[name]
     got, attempts, events = walk(inc, delta=delta_fp64)
     assert np.array_equal(got, scalar(inc))
+
+
+# ---- gf_sg_scan_kernel (k_fx.cu): growl events as integer crossings of the EXACT running sum ----------------------
+def _sg_scan(f0, mask, sr):
+    """the kernel's arithmetic in Python integers: (events, flagged)"""
+    n = len(f0)
+    U = 88
+    margin = (n + 2) << 12                       # units of 2^-64
+    S, Fp, flagged, ev = 0, 0, False, []
+    for i in range(n):
+        f = np.float32(f0[i])
+        sub = float(f) * 2.0
+        if not (mask[i] > 0 and f > 0 and not sub < 1e-2):
+            continue
+        bits = struct.unpack("<Q", struct.pack("<d", sub / sr))[0]
+        ex = (bits >> 52) & 0x7FF
+        if ex < 1023 - 24 or ex > 1022:
+            return [], True
+        S += ((bits & (ONE52 - 1)) | ONE52) << (ex - 1075 + U)
+        Fk = S >> U
+        frac = (S & ((1 << U) - 1)) >> (U - 64)
+        if frac <= margin or frac >= (1 << 64) - 1 - margin:
+            flagged = True
+        if Fk != Fp:
+            if Fk != Fp + 1:
+                flagged = True
+            ev.append((i, sub))
+        Fp = Fk
+    return ev, flagged
+
+
+def _sg_sequential(f0, mask, sr):
+    """_detect_pulse_events with one ratio of 2.0 (GOOFER.py:672-698)"""
+    phase, ev = 0.0, []
+    for i in range(len(f0)):
+        f = np.float32(f0[i])
+        if mask[i] <= 0 or f <= 0:
+            continue
+        sub = float(f) * 2.0
+        if sub < 1e-2:
+            continue
+        phase += sub / sr
+        if phase >= 1.0:
+            ev.append((i, sub))
+            phase -= 1.0
+    return ev
+
+
+@pytest.mark.parametrize("seed", [0, 1, 2])
+def test_growl_events_are_crossings_of_the_exact_sum(seed):
+    rng = np.random.default_rng(seed)
+    n, sr = 30000, 44100
+    t = np.arange(n) / sr
+    base = 110.0 * 2 ** rng.uniform(0, 2) * (1 + 0.02 * np.sin(2 * np.pi * 5 * t))
+    f0 = (base * (1 + 3.0 * np.sin(2 * np.pi * 75 * t))).astype(np.float32)       # apply_subharm_vibrato, depth 3
+    mask = (rng.random(n) < 0.9).astype(np.float32)
+    ev, flagged = _sg_scan(f0, mask, sr)
+    assert not flagged
+    assert ev == _sg_sequential(f0, mask, sr)
+
+
+def test_growl_scan_flags_borderline_sums_instead_of_guessing():
+    # a flat 441 Hz sub-harmonic at 44.1 kHz: the sum sits on an integer every 100 samples (within rounding)
+    n, sr = 4000, 44100
+    f0 = np.full(n, 220.5, dtype=np.float32)
+    ev, flagged = _sg_scan(f0, np.ones(n, dtype=np.float32), sr)
+    assert flagged
+    # increments of 1 or more cannot be placed by the scan either
+    assert _sg_scan(np.full(8, 30000.0, dtype=np.float32), np.ones(8, dtype=np.float32), sr)[1]
+
+
+# ---- gf_walk_scan_kernel (k_excite.cu): pulse onsets from a truncated fixed-point sum, flagged when rounding could matter ----
+def _walk_scan(f0, sr):
+    """the kernel's arithmetic in Python integers: (onsets, flagged)"""
+    U = 44
+    A, R, flagged, ons = 0, 0, False, []
+    for i, f in enumerate(np.asarray(f0, dtype=np.float32)):
+        if f == 0:
+            continue
+        if not abs(f) < np.float32(0.25) * np.float32(sr):
+            return [], True
+        A += int(np.floor((float(f) / sr) * 2.0 ** U))
+        if A < 0:
+            return [], True
+        Fk = A >> U
+        Rn = max(R, Fk)
+        k2 = i + 2
+        lz = 64 - ((Rn + 1) << U).bit_length()
+        m = k2 << max(0, 11 - lz)
+        lo, hi = max(A - m, 0), A + m + k2
+        if (lo >> U) != (hi >> U) and (hi >> U) > R:
+            flagged = True
+        if Rn > R:
+            if not f > np.float32(1e-6):
+                flagged = True
+            ons += [(i, float(f))] * (Rn - R)
+            R = Rn
+    return ons, flagged
+
+
+def _walk_sequential(f0, sr):
+    """the onset part of pulse_train_numba (GOOFER.py:479-493)"""
+    total, next_k, lv, ons = 0.0, 1.0, 160.0, []
+    for i, f in enumerate(np.asarray(f0, dtype=np.float32)):
+        if f > 1e-6:
+            lv = float(f)
+        total += float(f) / sr
+        while total >= next_k:
+            ons.append((i, lv))
+            next_k += 1.0
+    return ons
+
+
+@pytest.mark.parametrize("seed", [0, 1, 2, 3])
+def test_pulse_onsets_from_the_fixed_point_scan(seed):
+    rng = np.random.default_rng(seed)
+    n, sr = 44100, 44100
+    t = np.arange(n) / sr
+    f0 = (220.0 * 2 ** rng.uniform(-1, 2) * 2 ** (rng.uniform(0, 1) * np.sin(2 * np.pi * rng.uniform(3, 7) * t) / 12)).astype(np.float32)
+    f0[rng.integers(0, n, 50)] = 0.0
+    f0[10000:12000] = 0.0                                    # an unvoiced stretch
+    if seed >= 2:                                            # f0 jitter beyond 100 %: the total runs backwards for a while
+        f0[20000:20400] *= np.float32(-1.5)
+        f0[30000:30050] *= np.float32(-0.3)
+    ons, flagged = _walk_scan(f0, sr)
+    assert not flagged
+    assert ons == _walk_sequential(f0, sr)
+
+
+def test_pulse_scan_flags_what_it_cannot_decide():
+    sr = 44100
+    # flat A4: 440 / 44100 * 2205 = 22 up to rounding -- the scan must hand the pass to the bit-exact walk
+    assert _walk_scan(np.full(5000, 440.0, dtype=np.float32), sr)[1]
+    # a negative total, NaN
+    assert _walk_scan(np.array([100.0, -500.0, 100.0], dtype=np.float32), sr)[1]
+    assert _walk_scan(np.array([100.0, np.nan], dtype=np.float32), sr)[1]
+    # a flat note off the grid is decided by the scan
+    f0 = np.full(20000, 261.6256, dtype=np.float32)
+    ons, flagged = _walk_scan(f0, sr)
+    assert not flagged and ons == _walk_sequential(f0, sr)
