@@ -336,8 +336,20 @@ static int gf_render_batch_host_impl(const GooferBatch *b)
             for (int i = 0; i < nn && !any_fx; ++i) any_fx = note_needs_fx(plans[i]) || plans[i].pd != 0.0;
             if (any_fx) np = std::min(np, 2);
             np = std::max(1, std::min(np, nn));
+            // Download-bound parts taper: the last part's download is the tail of the call (nothing is left to hide it), the
+            // first part's kernels run while nothing is being downloaded yet.  One part more, sizes falling from 30 % to 6 %
+            // (five parts: .30 .27 .22 .15 .06): 5.21 ms per call against 5.36 with four equal parts (c2, B200).
+            std::vector<double> cutf;
+            if (!upload_bound && !any_fx && np >= 3 && np + 1 <= nn && !getenv("GOOFER_HOST_EQUAL_PARTS")) {
+                ++np;
+                double sum = 0.0;
+                std::vector<double> w(np);
+                for (int k = 0; k < np; ++k) { w[k] = 1.0 - 0.8 * std::pow((double)k / (np - 1), 1.5); sum += w[k]; }
+                double acc = 0.0;
+                for (int k = 0; k + 1 < np; ++k) { acc += w[k] / sum; cutf.push_back(acc); }
+            }
             for (int k = 1; k < np; ++k) {
-                const int64_t target = total * k / np;
+                const int64_t target = cutf.empty() ? total * k / np : (int64_t)((double)total * cutf[k - 1]);
                 int i = (int)(std::lower_bound(cum.begin(), cum.end(), target) - cum.begin());
                 i = std::max(i, (ends.empty() ? 0 : ends.back()) + 1);
                 if (i < nn) ends.push_back(i);

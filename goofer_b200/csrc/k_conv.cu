@@ -44,7 +44,8 @@ __device__ __forceinline__ T gf_conv_fetch(const GfFirJob &jb, int pos, int n, i
 }
 
 #ifndef GF_CONV64_MINB
-#define GF_CONV64_MINB 1        // resident CTAs per SM the fp64 kernel is compiled for (2 caps it at 64 registers)
+#define GF_CONV64_MINB 2        // resident CTAs per SM the fp64 kernel is compiled for: 2 caps it at 64 registers (412 bytes of
+                                // spills) and hides the barrier / twiddle latency better than 126 registers and one CTA: 0.64 -> 0.57 ms (c3)
 #endif
 template <typename T, int N>
 __global__ void __launch_bounds__(N / 8, sizeof(T) == 8 ? GF_CONV64_MINB : 1) gf_fftconv_kernel(const GfFirJob *__restrict__ jobs, int pairs_per_cta)

@@ -594,7 +594,7 @@ gf_walk_kernel(const GfPassDev *__restrict__ passes, GfPassScal *scal, int n_pas
 // additions differs from the exact sum of the increments by at most k half-ulps of the largest total so far; the
 // exact sum exceeds a fixed-point sum of the increments truncated (floor) to multiples of 2^-44 by less than
 // k 2^-44.  So if, at every sample that adds something, the interval
-//     [A_k - m_k, A_k + m_k + (k + 2) 2^-44],   A_k = fixed-point sum,  m_k = (k + 2) max(2^-44, 2 half-ulps)
+//     [A_k - m_k, A_k + m_k + (k + 2) 2^-44],   A_k = fixed-point sum,  m_k = (k + 2) max(2^-44, half an ulp)
 // either lies below the next firing level or has the same floor at both ends, the sequential loop and the integer
 // scan fire at the same samples, and the pass is done after one block scan of 64-bit sums and maxima (44,100
 // samples: 22 tiles of 2,048) instead of the ~86 attempt / commit rounds of the bit-exact walk below (0.5 ms
@@ -602,11 +602,14 @@ gf_walk_kernel(const GfPassDev *__restrict__ passes, GfPassScal *scal, int n_pas
 // note, whose total sits on an integer every 2,205 samples up to rounding; ~2e-4 of the other 1 s notes by
 // chance -- the pass is flagged and gf_walk_kernel renders it.  Negative increments (f0 jitter beyond 100 %) are
 // part of the scan; a negative TOTAL, a non-finite or absurd f0 and an onset on a sample with f0 <= 1e-6 are flagged.
+// Passes longer than 4 s go straight to the walk: the bound grows with k^2 (a 16 s note at 440 Hz would be flagged one
+// time in four) and one CTA scanning 345 tiles in a row is no faster than 16 warps walking them (c4: 5.7 -> 7.1 ms with it).
 // The rule in Python integers against the scalar loop: tests/test_walk_arith_cpu.py.
 // ------------------------------------------------------------------------------------------------
 #define GF_WSC_THREADS 256
 #define GF_WSC_PER 8
 #define GF_WSC_UNIT 44
+#define GF_WSC_MAX_N (4 * 44100)
 __global__ void __launch_bounds__(GF_WSC_THREADS)
 gf_walk_scan_kernel(const GfPassDev *__restrict__ passes, GfPassScal *scal, int n_pass, int sr_i)
 {
@@ -616,6 +619,10 @@ gf_walk_scan_kernel(const GfPassDev *__restrict__ passes, GfPassScal *scal, int 
     if (pi >= n_pass) return;
     const GfPassDev ps = passes[pi];
     const int n = ps.n_total;
+    if (n > GF_WSC_MAX_N) {
+        if (threadIdx.x == 0) scal[pi].walk_seq = 1;
+        return;
+    }
     const double sr = (double)sr_i, rcp_sr = __drcp_rn((double)sr_i);
     const float fmax_ok = 0.25f * (float)sr_i;
     const float *__restrict__ f0 = ps.f0;
@@ -624,9 +631,12 @@ gf_walk_scan_kernel(const GfPassDev *__restrict__ passes, GfPassScal *scal, int 
     long long carry = 0ll;              // fixed-point total before this tile
     int fired = 0;                      // running maximum of floor(total) = pulses fired before this tile
     int bad = 0;
-    for (int base = 0; base < n; base += GF_WSC_THREADS * GF_WSC_PER) {
-        const int i0 = base + tid * GF_WSC_PER;
-        float f[GF_WSC_PER];
+    // a sample can only be borderline if the fraction of the total is within the LARGEST margin of the pass of 0 or 1:
+    // one comparison screens (nearly) every sample before the exact test below
+    const int sh_max = max(0, (31 - __clz(n + 1)) - 9);
+    const long long quick = ((long long)n + 2ll) * 2ll + (((long long)n + 2ll) << sh_max);
+    const long long ONE = 1ll << GF_WSC_UNIT;
+    auto load_tile = [&](int i0, float *f) {
         if (aligned16 && i0 + GF_WSC_PER <= n) {
             const float4 a = *reinterpret_cast<const float4 *>(f0 + i0), b = *reinterpret_cast<const float4 *>(f0 + i0 + 4);
             f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
@@ -634,6 +644,15 @@ gf_walk_scan_kernel(const GfPassDev *__restrict__ passes, GfPassScal *scal, int 
 #pragma unroll
             for (int e = 0; e < GF_WSC_PER; ++e) f[e] = (i0 + e < n) ? f0[i0 + e] : 0.0f;
         }
+    };
+    float fnext[GF_WSC_PER];
+    load_tile(tid * GF_WSC_PER, fnext);
+    for (int base = 0; base < n; base += GF_WSC_THREADS * GF_WSC_PER) {
+        const int i0 = base + tid * GF_WSC_PER;
+        float f[GF_WSC_PER];
+#pragma unroll
+        for (int e = 0; e < GF_WSC_PER; ++e) f[e] = fnext[e];
+        load_tile(i0 + GF_WSC_THREADS * GF_WSC_PER, fnext);      // the next tile's samples travel while this one is scanned
         long long loc[GF_WSC_PER];
         long long run = 0ll;
 #pragma unroll
@@ -695,11 +714,14 @@ gf_walk_scan_kernel(const GfPassDev *__restrict__ passes, GfPassScal *scal, int 
             if (f[e] != 0.0f) {
                 const long long A = pre + loc[e];
                 const int Rn = max(R, F[e]);
-                const long long k2 = (long long)(i0 + e) + 2ll;
-                const int sh = max(0, 11 - __clzll((long long)(Rn + 1) << GF_WSC_UNIT));      // two half-ulps of the largest total, units of 2^-44
-                const long long m = k2 << sh;
-                const long long lo = max(A - m, 0ll), hi = A + m + k2;
-                if ((lo >> GF_WSC_UNIT) != (hi >> GF_WSC_UNIT) && (hi >> GF_WSC_UNIT) > (long long)R) bad = 1;
+                const long long fr = A & (ONE - 1ll);
+                if (fr <= quick || fr >= ONE - quick) {
+                    const long long k2 = (long long)(i0 + e) + 2ll;
+                    const int sh = max(0, 10 - __clzll((long long)(Rn + 1) << GF_WSC_UNIT));  // half an ulp of the largest total so far (< Rn + 1), units of 2^-44
+                    const long long m = k2 << sh;
+                    const long long lo = max(A - m, 0ll), hi = A + m + k2;
+                    if ((lo >> GF_WSC_UNIT) != (hi >> GF_WSC_UNIT) && (hi >> GF_WSC_UNIT) > (long long)R) bad = 1;
+                }
                 if (Rn > R) {
                     if (!(f[e] > 1e-6f)) bad = 1;                                             // last_valid_f0 would come from an earlier sample
                     for (int c = R; c < Rn; ++c)
@@ -771,7 +793,7 @@ int gf_launch_walk(const GfPassDev *passes, GfPassScal *scal, int n_pass, int ma
     // The scan places the onsets of every pass it can decide; the bit-exact walk then runs for the flagged ones only
     // (its other CTAs leave at once), so it is sized for a fraction of the passes: more warps per pass.
     gf_walk_scan_kernel<<<n_pass, GF_WSC_THREADS, 0, st>>>(passes, scal, n_pass, sr);
-    int nw = n_pass <= 640 ? 8 : (n_pass <= 1280 ? 4 : (n_pass <= 6144 ? 2 : 1));
+    int nw = n_pass <= 640 ? 8 : (n_pass <= 6144 ? 4 : 2);
 #else
     int nw = n_pass <= 160 ? 8 : (n_pass <= 320 ? 4 : (n_pass <= 1536 ? 2 : 1));
 #endif

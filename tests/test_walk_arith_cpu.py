@@ -304,7 +304,7 @@ def _walk_scan(f0, sr):
         Rn = max(R, Fk)
         k2 = i + 2
         lz = 64 - ((Rn + 1) << U).bit_length()
-        m = k2 << max(0, 11 - lz)
+        m = k2 << max(0, 10 - lz)
         lo, hi = max(A - m, 0), A + m + k2
         if (lo >> U) != (hi >> U) and (hi >> U) > R:
             flagged = True

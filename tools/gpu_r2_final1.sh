@@ -23,7 +23,7 @@ done
 CMD="python bench.py --steps 1 --warmup 3 --no-e2e --cpu-sample 0 --verify 0"
 $CMD > gpurun_out/r2_plain.log 2>&1 && ncu --metrics gpu__time_duration.sum --clock-control none -c 200 --csv --log-file gpurun_out/r2_launches_c2_1024notes.csv $CMD > gpurun_out/r2_ncu_l.log 2>&1
 echo "launch list rc=$?"
-$CMD > gpurun_out/r2_plain2.log 2>&1 && ncu --set full --clock-control none --import-source on -k regex:gf_ -s 51 -c 17 -o gpurun_out/r2_full_c2 $CMD > gpurun_out/r2_ncu_f.log 2>&1
+$CMD > gpurun_out/r2_plain2.log 2>&1 && ncu --set full --clock-control none --import-source on -k regex:gf_ -s 54 -c 18 -o gpurun_out/r2_full_c2 $CMD > gpurun_out/r2_ncu_f.log 2>&1
 echo "full rc=$?"
 CMD2="python bench.py --steps 1 --warmup 3 --no-e2e --cpu-sample 0 --verify 0 --noise device"
 $CMD2 > gpurun_out/r2_plain3.log 2>&1 && ncu --set full --clock-control none --import-source on -k regex:gf_phi_kernel -s 3 -c 1 -o gpurun_out/r2_full_phi $CMD2 > gpurun_out/r2_ncu_p.log 2>&1
