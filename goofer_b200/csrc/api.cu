@@ -606,7 +606,12 @@ int gf_pitch_dyn(const WaveHost &wh, int n0, int n1, const GfNotePlan *d_plans, 
 // note) no longer leave SMs idle.  Measured on B200, forked against one stream: c1 3.74 / 3.89 ms, c2 4.80 / 4.90 ms,
 // c3 11.43 / 11.52 ms, c4 (96 x 16 s, long walk chains) 6.05 / 6.68 ms.  (With the first versions of the kernels the
 // fork lost, 7.94 against 7.52 ms; it was re-measured after they had been tightened.)
-struct GfSide { cudaStream_t sx = nullptr; cudaEvent_t fork = nullptr, join = nullptr; int dev = -1; };
+struct GfSide {
+    cudaStream_t sx = nullptr;                      // excitation chain (high priority)
+    cudaStream_t alt = nullptr;                     // every other part of the frame / peak / mix tail (default priority)
+    cudaEvent_t fork = nullptr, join = nullptr, prep = nullptr, alt_done = nullptr;
+    int dev = -1;
+};
 static thread_local GfSide g_side;
 
 static bool gf_overlap_on()
@@ -621,7 +626,11 @@ static cudaStream_t gf_side_stream()
     int dev = 0;
     if (cudaGetDevice(&dev) != cudaSuccess) return nullptr;
     if (g_side.sx && g_side.dev == dev) return g_side.sx;
-    if (g_side.sx) { cudaStreamDestroy(g_side.sx); cudaEventDestroy(g_side.fork); cudaEventDestroy(g_side.join); g_side = GfSide(); }
+    if (g_side.sx) {
+        cudaStreamDestroy(g_side.sx); cudaEventDestroy(g_side.fork); cudaEventDestroy(g_side.join);
+        if (g_side.alt) { cudaStreamDestroy(g_side.alt); cudaEventDestroy(g_side.prep); cudaEventDestroy(g_side.alt_done); }
+        g_side = GfSide();
+    }
     int lo = 0, hi = 0;
     cudaDeviceGetStreamPriorityRange(&lo, &hi);            // hi = greatest priority (numerically lowest)
     const char *pe = getenv("GOOFER_SIDE_PRIORITY");          // "low": the side stream yields to the caller's stream (tuning knob)
@@ -633,6 +642,25 @@ static cudaStream_t gf_side_stream()
     }
     g_side.dev = dev;
     return g_side.sx;
+}
+
+// Tuning knob, off by default: GOOFER_PART_STREAMS=2 alternates the parts of a wave's tail (host entry point) between the
+// caller's stream and this one, so that the next part's CTAs fill the half-empty last round of a part's frame launch
+// (a part of 30 % of 1,024 notes covers the GPU 1.4 times).  Measured on B200 (c2, production transfer set, same box):
+// 5.44 / 5.47 ms per call against 5.25 / 5.23 on one stream -- the parts then finish together instead of one after the
+// other, and the downloads that were hidden behind the later parts' kernels are not.
+static cudaStream_t gf_alt_stream()
+{
+    static int v = -1;
+    if (v < 0) { const char *e = getenv("GOOFER_PART_STREAMS"); v = (e && e[0] == '2') ? 1 : 0; }
+    if (!v || !gf_overlap_on() || !gf_side_stream()) return nullptr;
+    if (g_side.alt) return g_side.alt;
+    if (cudaStreamCreateWithFlags(&g_side.alt, cudaStreamNonBlocking) != cudaSuccess) { g_side.alt = nullptr; return nullptr; }
+    if (cudaEventCreateWithFlags(&g_side.prep, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&g_side.alt_done, cudaEventDisableTiming) != cudaSuccess) {
+        cudaStreamDestroy(g_side.alt); g_side.alt = nullptr; return nullptr;
+    }
+    return g_side.alt;
 }
 
 // A part = a run of consecutive notes of the batch whose noise phases arrive together (host entry point):
@@ -874,10 +902,20 @@ static int gf_render_wave(const GooferBatch *b, const std::vector<GfNotePlan> &a
         const GfPart *pp = n_parts > 0 ? parts : &whole;
         const int np = n_parts > 0 ? n_parts : 1;
         int prev_end = 0;
+        cudaStream_t alt = np >= 2 ? gf_alt_stream() : nullptr;
+        cudaStream_t const st_main = st;
+        bool alt_used = false;
+        if (alt) {
+            GF_CUDA(cudaEventRecord(g_side.prep, st_main));
+            GF_CUDA(cudaStreamWaitEvent(alt, g_side.prep, 0));
+        }
+        int part_no = 0;
         for (int k = 0; k < np; ++k) {
             const int a = std::max(prev_end, i0) - i0, e = std::min(pp[k].note_end, i1) - i0;     // notes [a, e) of this wave
             prev_end = pp[k].note_end;
             if (e <= a) continue;
+            cudaStream_t st = (alt && (part_no++ & 1)) ? alt : st_main;                            // shadows: this part's stream
+            alt_used = alt_used || (alt && st == alt);
             if (pp[k].phi_ready) GF_CUDA(cudaStreamWaitEvent(st, pp[k].phi_ready, 0));             // first kernel that reads the noise phases
             {
                 // host-supplied phases, (513, T) as numpy draws them: transposed to the frame-major layout the frame kernel reads
@@ -902,6 +940,10 @@ static int gf_render_wave(const GooferBatch *b, const std::vector<GfNotePlan> &a
             gf_launch_mix(d_plans, d_notes, d_passes, d_scal, a, e - a, max_n, any_simple, any_general, st);
             L += (int)any_simple + (int)any_general; GF_STEP("mix");
             if (pp[k].done && pp[k].note_end <= i1) GF_CUDA(cudaEventRecord(pp[k].done, st));
+        }
+        if (alt_used) {
+            GF_CUDA(cudaEventRecord(g_side.alt_done, alt));
+            GF_CUDA(cudaStreamWaitEvent(st_main, g_side.alt_done, 0));
         }
     }
     gf_htrace("wave: everything enqueued");
