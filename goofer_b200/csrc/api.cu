@@ -716,8 +716,8 @@ static int gf_render_wave(const GooferBatch *b, const std::vector<GfNotePlan> &a
     // per-note double scalars (maxima, rms sums, percentile): one block, one memset
     // per-note double scalars and per-pass device-written scalars are carved back to back: ONE memset zeroes both
     double *d_nscal = bp.arr<double>((size_t)nn * GF_NS_COUNT);
-    GfPassScal *d_scal = bp.arr<GfPassScal>(n_pass);
-    const size_t scal_span = (size_t)((char *)(d_scal + n_pass) - (char *)d_nscal);
+    GfPassScal *d_scal = bp.arr<GfPassScal>(n_pass + 1);       // one spare record: its walk_seq counts the passes the onset scan flags
+    const size_t scal_span = (size_t)((char *)(d_scal + n_pass + 1) - (char *)d_nscal);
     for (int i = 0; i < nn; ++i) {
         const GfNotePlan &p = wh.plans[i];
         max_n = std::max(max_n, p.n_total);
@@ -863,7 +863,7 @@ static int gf_render_wave(const GooferBatch *b, const std::vector<GfNotePlan> &a
             L += gf_launch_fir(wh.fir.data(), d_fir, (int)wh.fir.size(), st); GF_STEP("fir");
         }
         gf_launch_f0(d_plans, d_notes, d_passes, d_srcs, b->bend_cents, b->normals, b->f0_curves, nn, max_n, st); ++L; GF_STEP("f0");
-        L += gf_launch_walk(d_passes, d_scal, (int)n_pass, max_n, sr, st); GF_STEP("walk");     // onset scan + bit-exact walk + onset kernels
+        L += gf_launch_walk(d_passes, d_scal, (int)n_pass, max_n, sr, st, &d_scal[n_pass].walk_seq); GF_STEP("walk");     // onset scan + bit-exact walk + onset kernels
         gf_launch_pulse(d_passes, d_scal, (int)n_pass, max_n, st); ++L; GF_STEP("pulse");
         if ((rc = gf_growl(wh, d_plans, d_notes, d_passes, d_scal, bp, max_n, st, &L)) != GOOFER_OK) return rc;
     }
@@ -1140,7 +1140,7 @@ extern "C" size_t goofer_pulse_work_bytes(int32_t n_sig, int32_t n)
 {
     if (n_sig < 0 || n < 0) return 0;
     const size_t cap = (size_t)n / 8 + 64;
-    return (size_t)n_sig * (sizeof(GfPassDev) + sizeof(GfPassScal) + cap * sizeof(int4) + 512) + 1024;
+    return (size_t)n_sig * (sizeof(GfPassDev) + sizeof(GfPassScal) + cap * sizeof(int4) + 512) + sizeof(GfPassScal) + 1024;
 }
 
 extern "C" int goofer_pulse_train_batch(const float *f0, int32_t n_sig, int32_t n, int32_t sr, float *pulse_out, void *work, void *stream)
@@ -1162,10 +1162,10 @@ extern "C" int goofer_pulse_train_batch(const float *f0, int32_t n_sig, int32_t 
         ps[s] = q;
     }
     GfPassDev *d_ps = bp.arr<GfPassDev>(n_sig);
-    GfPassScal *d_sc = bp.arr<GfPassScal>(n_sig);
+    GfPassScal *d_sc = bp.arr<GfPassScal>(n_sig + 1);
     GF_CUDA(cudaMemcpyAsync(d_ps, ps.data(), ps.size() * sizeof(GfPassDev), cudaMemcpyHostToDevice, st));
-    GF_CUDA(cudaMemsetAsync(d_sc, 0, n_sig * sizeof(GfPassScal), st));
-    gf_launch_walk(d_ps, d_sc, n_sig, n, sr, st);
+    GF_CUDA(cudaMemsetAsync(d_sc, 0, (n_sig + 1) * sizeof(GfPassScal), st));
+    gf_launch_walk(d_ps, d_sc, n_sig, n, sr, st, &d_sc[n_sig].walk_seq);
     gf_launch_pulse(d_ps, d_sc, n_sig, n, st);
     GF_CUDA(cudaGetLastError());
     std::vector<GfPassScal> sc(n_sig);

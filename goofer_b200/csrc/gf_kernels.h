@@ -12,7 +12,8 @@ int gf_launch_fir(const GfFirJob *h_jobs, const GfFirJob *d_jobs, int n_jobs, cu
 int gf_launch_fftconv(const GfFirJob *h_jobs, const GfFirJob *d_jobs, int n_jobs, cudaStream_t st);
 void gf_launch_f0(const GfNotePlan *plans, const GfNoteDev *notes, const GfPassDev *passes, const GfSourceDev *srcs,
                   const float *bend, const double *normals, const float *f0_curves, int n_notes, int max_n, cudaStream_t st);
-int gf_launch_walk(const GfPassDev *passes, GfPassScal *scal, int n_pass, int max_n, int sr, cudaStream_t st);
+// flag_count: a zeroed device int the onset scan counts its flagged passes in (or NULL: the host picks the walk's shape)
+int gf_launch_walk(const GfPassDev *passes, GfPassScal *scal, int n_pass, int max_n, int sr, cudaStream_t st, int *flag_count = nullptr);
 void gf_launch_pulse(const GfPassDev *passes, const GfPassScal *scal, int n_pass, int max_n, cudaStream_t st);
 void gf_launch_frame(const int4 *work, int n_work, const GfPassDev *passes, GfPassScal *scal, const GfNoteDev *notes,
                      const GfNotePlan *plans, cudaStream_t st);

@@ -91,7 +91,9 @@ extern "C" void goofer_host_release(void)
         cudaGetDevice(&cur);
         if (g_side.dev >= 0 && g_side.dev != cur) cudaSetDevice(g_side.dev);
         cudaStreamSynchronize(g_side.sx);
-        cudaStreamDestroy(g_side.sx); cudaEventDestroy(g_side.fork); cudaEventDestroy(g_side.join); g_side = GfSide();
+        cudaStreamDestroy(g_side.sx); cudaEventDestroy(g_side.fork); cudaEventDestroy(g_side.join);
+        if (g_side.alt) { cudaStreamSynchronize(g_side.alt); cudaStreamDestroy(g_side.alt); cudaEventDestroy(g_side.prep); cudaEventDestroy(g_side.alt_done); }
+        g_side = GfSide();
         if (cur >= 0) cudaSetDevice(cur);
     }
     if (g_pin.base) {

@@ -36,7 +36,10 @@ template <typename T>
 __device__ __forceinline__ T gf_conv_fetch(const GfFirJob &jb, int pos, int n, int radius)
 {
     if (pos >= n + radius || pos < -radius) return (T)0;          // never contributes to an output below n
-    const int q = (pos >= 0 && pos < n) ? pos : gf_reflect(pos, n);
+    // numpy 'reflect': one fold suffices when the signal is longer than the halo (the general form costs an integer
+    // modulo per sample: 9 % of the fp64 kernel's instructions in the first version)
+    int q = pos;
+    if (pos < 0 || pos >= n) q = (n > radius) ? (pos < 0 ? -pos : 2 * (n - 1) - pos) : gf_reflect(pos, n);
     if (sizeof(T) == 4) return (T)((const float *)jb.in)[(size_t)q * jb.in_stride];
     double v = jb.in_f64 ? ((const double *)jb.in)[(size_t)q * jb.in_stride] : (double)((const float *)jb.in)[(size_t)q * jb.in_stride];
     if (jb.in_cast_f32) v = (double)(float)v;
@@ -141,7 +144,9 @@ int gf_launch_fftconv(const GfFirJob *h_jobs, const GfFirJob *d_jobs, int n_jobs
     }
     // every CTA rebuilds the spectrum of its job's taps (one transform): give it several block pairs to amortise
     // that, as long as the grid still covers the SMs about twice
-    auto ppc_of = [](int pairs, int jobs) { return std::max(1, std::min(8, (int)((long long)pairs * jobs / (2 * 148)))); };
+    int dev = 0, sms = 148;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
+    auto ppc_of = [sms](int pairs, int jobs) { return std::max(1, std::min(8, (int)((long long)pairs * jobs / (2 * sms)))); };
     int launches = 0;
     if (jobs32) {
         static GfSmemLimit memo;

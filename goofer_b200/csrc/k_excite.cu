@@ -355,7 +355,7 @@ __device__ __forceinline__ bool gf_walk_delta(double inc, int e, GfDelta &d, lon
 #endif
 template <int WARPS>
 __global__ void __launch_bounds__(32 * WARPS, GF_WALK_MINB)
-gf_walk_kernel(const GfPassDev *__restrict__ passes, GfPassScal *scal, int n_pass, int sr_i)
+gf_walk_kernel(const GfPassDev *__restrict__ passes, GfPassScal *scal, int n_pass, int sr_i, const int *__restrict__ flag_count, int cnt_lo, int cnt_hi)
 {
     // one CTA of WARPS warps per (note, pass); every warp keeps an identical copy of the walk state
     __shared__ GfDelta s_tot[WARPS];
@@ -367,6 +367,12 @@ gf_walk_kernel(const GfPassDev *__restrict__ passes, GfPassScal *scal, int n_pas
     if (pi >= n_pass) return;
 #if !defined(GF_WALK_SEQ_ONLY)
     if (!scal[pi].walk_seq) return;                        // gf_walk_scan_kernel placed this pass's onsets
+    if (flag_count) {
+        // the launcher issues this kernel in two shapes (many warps per pass for a few flagged passes, few warps for many):
+        // the number of flagged passes, counted by the scan, decides on the device which of the two does the work
+        const int c = *flag_count;
+        if (c < cnt_lo || c > cnt_hi) return;
+    }
 #endif
     const GfPassDev ps = passes[pi];
     const int n = ps.n_total;
@@ -611,7 +617,7 @@ gf_walk_kernel(const GfPassDev *__restrict__ passes, GfPassScal *scal, int n_pas
 #define GF_WSC_UNIT 44
 #define GF_WSC_MAX_N (4 * 44100)
 __global__ void __launch_bounds__(GF_WSC_THREADS)
-gf_walk_scan_kernel(const GfPassDev *__restrict__ passes, GfPassScal *scal, int n_pass, int sr_i)
+gf_walk_scan_kernel(const GfPassDev *__restrict__ passes, GfPassScal *scal, int n_pass, int sr_i, int *flag_count)
 {
     __shared__ long long s_warp[GF_WSC_THREADS / 32];
     __shared__ int s_wmax[GF_WSC_THREADS / 32];
@@ -620,7 +626,7 @@ gf_walk_scan_kernel(const GfPassDev *__restrict__ passes, GfPassScal *scal, int 
     const GfPassDev ps = passes[pi];
     const int n = ps.n_total;
     if (n > GF_WSC_MAX_N) {
-        if (threadIdx.x == 0) scal[pi].walk_seq = 1;
+        if (threadIdx.x == 0) { scal[pi].walk_seq = 1; if (flag_count) atomicAdd(flag_count, 1); }
         return;
     }
     const double sr = (double)sr_i, rcp_sr = __drcp_rn((double)sr_i);
@@ -735,7 +741,7 @@ gf_walk_scan_kernel(const GfPassDev *__restrict__ passes, GfPassScal *scal, int 
     }
     bad = __syncthreads_or(bad);
     if (tid == 0) {
-        if (bad) scal[pi].walk_seq = 1;
+        if (bad) { scal[pi].walk_seq = 1; if (flag_count) atomicAdd(flag_count, 1); }
         else {
             scal[pi].n_onsets = min(fired, ps.onset_cap);
             if (fired > ps.onset_cap) scal[pi].err = 1;
@@ -780,36 +786,53 @@ gf_onset_kernel(const GfPassDev *__restrict__ passes, GfPassScal *scal, int sr_i
     if ((threadIdx.x & 31) == 0 && mx > 0) atomicMax(&scal[blockIdx.y].max_T0, mx);
 }
 
-int gf_launch_walk(const GfPassDev *passes, GfPassScal *scal, int n_pass, int max_n, int sr, cudaStream_t st)
+int gf_launch_walk(const GfPassDev *passes, GfPassScal *scal, int n_pass, int max_n, int sr, cudaStream_t st, int *flag_count)
 {
     if (n_pass <= 0) return 0;
     // One warp per note costs the fewest issue slots: right when there are enough notes to fill the GPU.  More warps per
-    // note cut the latency of a note's chain: right for few and / or long notes.  Measured on B200 (ms, 1 s notes;
-    // warps per note 1 / 2 / 4 / 8 / 16): 128 notes .65 .38 .24 .18 .19 | 256: .68 .40 .26 .34 .36 | 512: .69 .43 .50 .65
-    // .69 | 1,024: .74 .55 .76 1.13 1.20 | 2,048: .95 1.00 1.29 2.2 2.4; 96 notes of 16 s: 9.9 5.4 2.9 1.8 1.4.
+    // note cut the latency of a note's chain: right for few and / or long notes.  Measured on B200 (ms, 1 s notes, every
+    // pass on the bit-exact walk; warps per note 1 / 2 / 4 / 8 / 16): 128 notes .65 .38 .24 .18 .19 | 256: .68 .40 .26 .34 .36 |
+    // 512: .69 .43 .50 .65 .69 | 1,024: .74 .55 .76 1.13 1.20 | 2,048: .95 1.00 1.29 2.2 2.4; 96 notes of 16 s: 9.9 5.4 2.9 1.8 1.4.
     static int force = -1;
     if (force < 0) { const char *e = getenv("GOOFER_WALK_WARPS"); force = e ? atoi(e) : 0; }
+    auto launch = [&](int nw, const int *fc, int lo, int hi) {
+        if (nw == 16) gf_walk_kernel<16><<<n_pass, 512, 0, st>>>(passes, scal, n_pass, sr, fc, lo, hi);
+        else if (nw == 8) gf_walk_kernel<8><<<n_pass, 256, 0, st>>>(passes, scal, n_pass, sr, fc, lo, hi);
+        else if (nw == 4) gf_walk_kernel<4><<<n_pass, 128, 0, st>>>(passes, scal, n_pass, sr, fc, lo, hi);
+        else if (nw == 2) gf_walk_kernel<2><<<n_pass, 64, 0, st>>>(passes, scal, n_pass, sr, fc, lo, hi);
+        else gf_walk_kernel<1><<<n_pass, 32, 0, st>>>(passes, scal, n_pass, sr, fc, lo, hi);
+    };
+    int launches = 0;
 #if !defined(GF_WALK_SEQ_ONLY)
-    // The scan places the onsets of every pass it can decide; the bit-exact walk then runs for the flagged ones only
-    // (its other CTAs leave at once), so it is sized for a fraction of the passes: more warps per pass.
-    gf_walk_scan_kernel<<<n_pass, GF_WSC_THREADS, 0, st>>>(passes, scal, n_pass, sr);
+    // The scan places the onsets of every pass it can decide; the bit-exact walk then runs for the flagged ones only (its
+    // other CTAs leave at once).  How many those are is known on the device only (the scan counts them in *flag_count).
+    // -DGF_WALK_FEW=n issues the walk twice -- GF_WALK_FEW_WARPS warps per pass for up to n flagged passes, the batch-size
+    // heuristic beyond -- and lets the count decide on the device.  Measured on B200 (walk bucket / whole step, ms): c2 (43
+    // flagged) off 0.413 / 4.074, 256 x 8 warps 0.322 / 4.080, 96 x 16 warps 0.329 / 4.101; c3 (150 tie-heavy flagged passes,
+    // 256 notes) off 0.883 / 7.913, 256 x 8 0.941 / 7.982, 192 x 16 1.43 / 8.46.  The walk's latency is hidden behind the
+    // envelope kernel either way, so the step does not move: off by default.
+    gf_walk_scan_kernel<<<n_pass, GF_WSC_THREADS, 0, st>>>(passes, scal, n_pass, sr, flag_count);
+    ++launches;
     int nw = n_pass <= 640 ? 8 : (n_pass <= 6144 ? 4 : 2);
 #else
     int nw = n_pass <= 160 ? 8 : (n_pass <= 320 ? 4 : (n_pass <= 1536 ? 2 : 1));
+    flag_count = nullptr;
 #endif
     if (max_n >= 4 * 44100) nw = min(16, 2 * nw);
-    if (force == 1 || force == 2 || force == 4 || force == 8 || force == 16) nw = force;
-    if (nw == 16) gf_walk_kernel<16><<<n_pass, 512, 0, st>>>(passes, scal, n_pass, sr);
-    else if (nw == 8) gf_walk_kernel<8><<<n_pass, 256, 0, st>>>(passes, scal, n_pass, sr);
-    else if (nw == 4) gf_walk_kernel<4><<<n_pass, 128, 0, st>>>(passes, scal, n_pass, sr);
-    else if (nw == 2) gf_walk_kernel<2><<<n_pass, 64, 0, st>>>(passes, scal, n_pass, sr);
-    else gf_walk_kernel<1><<<n_pass, 32, 0, st>>>(passes, scal, n_pass, sr);
-    gf_onset_kernel<<<dim3(4, n_pass), 128, 0, st>>>(passes, scal, sr);
-#if !defined(GF_WALK_SEQ_ONLY)
-    return 3;
-#else
-    return 2;
+    if (force == 1 || force == 2 || force == 4 || force == 8 || force == 16) { nw = force; flag_count = nullptr; }
+#ifndef GF_WALK_FEW
+#define GF_WALK_FEW 0           // tuning knob, off: up to this many flagged passes get GF_WALK_FEW_WARPS warps each (decided on the device)
 #endif
+#ifndef GF_WALK_FEW_WARPS
+#define GF_WALK_FEW_WARPS 8
+#endif
+    if (flag_count && nw < GF_WALK_FEW_WARPS && GF_WALK_FEW > 0) {
+        launch(GF_WALK_FEW_WARPS, flag_count, 1, GF_WALK_FEW);
+        launch(nw, flag_count, GF_WALK_FEW + 1, INT_MAX);
+        launches += 2;
+    } else { launch(nw, nullptr, 0, 0); ++launches; }
+    gf_onset_kernel<<<dim3(4, n_pass), 128, 0, st>>>(passes, scal, sr);
+    return launches + 1;
 }
 
 

@@ -11,7 +11,8 @@ n = sys.argv[1]
 try:
     d = json.load(open(f"gpurun_out/var_{n}.log"))
     k = d["roofline"]["kernels_ms_per_step"]
-    print(f"{n:12s} {d['ms_per_step']:.3f} ms  e2e {d['e2e']['ms_per_step']:.3f} ms  " + " ".join(f"{a}={b:.3f}" for a, b in k.items()))
+    e = (d.get("e2e") or {}).get("ms_per_step")
+    print(f"{n:12s} {d['ms_per_step']:.3f} ms  e2e {e if e is None else round(e, 3)} ms  " + " ".join(f"{a}={b:.3f}" for a, b in k.items()))
 except Exception as e:
     print(n, "FAILED", e)
 PY

@@ -3,6 +3,9 @@
 
     python tools/ncu_lines.py <report.ncu-rep> <kernel regex> <lib.so> [top N] [sort: samples|smem|inst|conflicts]
 
+The regex matches the function's base name (no template arguments); NCU_LAUNCH_SKIP=k picks the (k+1)-th matching launch
+(two instantiations of one template share the base name).
+
 Joins `ncu --page source --csv` (per SASS address: instructions executed, stall samples, shared-memory wavefronts
 and the excess over the ideal count = bank conflicts) with `nvdisasm -g` line info of the cubin inside the shared
 library.  The .so must be the build that was profiled.
@@ -12,7 +15,8 @@ import csv, os, re, subprocess, sys, tempfile, collections
 rep, kre, so = sys.argv[1:4]
 top = int(sys.argv[4]) if len(sys.argv) > 4 else 40
 sort = sys.argv[5] if len(sys.argv) > 5 else "samples"
-out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--kernel-name", f"regex:{kre}"], capture_output=True, text=True).stdout
+out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--kernel-name", f"regex:{kre}", "--launch-skip", os.environ.get("NCU_LAUNCH_SKIP", "0"),
+                      "--launch-count", "1"], capture_output=True, text=True).stdout
 lines = out.split("\n")
 start = next(i for i, l in enumerate(lines) if l.startswith('"Address"'))
 kname = lines[start - 1].split('","')[1].split("(")[0] if start else kre
