@@ -586,6 +586,33 @@ def test_edge_lengths_and_empty_batch(torch_cuda):
     assert ab0.render_host() == []
 
 
+def test_long_kernels_on_short_notes_and_long_passes(torch_cuda):
+    """The overlap-save smoothing (sigma 441 / 73.5 / 49: halos of 1,764 / 294 / 196 samples) on notes SHORTER than the halo
+    (numpy's 'reflect' padding folds several times there), on notes between one and two halos, and a 5 s note (its pulse
+    onsets skip the fixed-point scan: passes over 4 s go straight to the bit-exact walk), all flags that use long kernels on."""
+    import bench_data
+    feat, sf = cases.source_for(2, 1.0)
+    flags = "pd80sh70sr60sg40"
+    clis = [["C4", "100", flags, "0", "10", "0", "0", "100", "0", "!120", bench_data._vibrato_string(3, 0.1)],
+            ["A3", "100", flags, "0", "60", "0", "0", "100", "0", "!120", bench_data._vibrato_string(4, 0.2)],
+            ["E4", "100", "pd-60sh30", "0", "5000", "40", "0", "100", "0", "!120", bench_data._vibrato_string(5, 5.2)],
+            ["A4", "100", "pd50sr90", "0", "700", "0", "0", "100", "0", "!120", "AA"]]
+    b = host.Batch()
+    b.add_source(sf)
+    for c in clis:
+        b.add_note(host.NoteArgs.from_cli(0, c))
+    ab = b.assemble(host.SeededNoise(cases.SEED_BASE, cases.SEED_LEGACY))
+    db = ab.to_device("cuda:0")
+    db.render()
+    torch_cuda.cuda.synchronize()
+    outs = db.outputs()
+    assert len(outs[0]) < 1764 and 1764 < len(outs[1]) < 2 * 1764 and len(outs[2]) > 4 * 44100
+    for c, o in zip(clis, outs):
+        ref = cases.oracle_render(feat, c)
+        assert len(ref) == len(o)
+        assert np.max(np.abs(o.astype(np.float64) - ref)) <= MAX_ABS, c
+
+
 def test_noise_phases_drawn_on_the_device(torch_cuda):
     """GooferNote.phi_rng: the device draws numpy's Generator(PCG64).uniform(0, 2 pi, (513, T)).astype(float32) stream bit
     for bit (128-bit LCG jump-ahead per thread) -- the renders with host-supplied buffers (SeededNoise) and with
