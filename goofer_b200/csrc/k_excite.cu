@@ -98,6 +98,9 @@ __device__ __forceinline__ float gf_ms_at_fast(const float *__restrict__ s, int 
     return gf_ms_at(s, M, i, N);
 }
 
+#ifndef GF_F0_TICK_MAJOR
+#define GF_F0_TICK_MAJOR 1
+#endif
 #ifndef GF_F0_CTAS
 #define GF_F0_CTAS 8                // register cap 32 (with spills): the kernel waits on loads (long scoreboard 8.9 per issue), resident warps pay:
                                     // 0.75 ms uncapped (80 registers) -> 0.60 (cap 64) -> 0.47 (cap 40) -> 0.41 ms (cap 32)
@@ -139,6 +142,100 @@ gf_f0_kernel(const GfNotePlan *__restrict__ plans, const GfNoteDev *__restrict__
         const float *__restrict__ mshort = nd.ms_short;
         unsigned char *__restrict__ ms_one = nd.ms_one;
         const int sr_i = pl.sr;
+#if GF_F0_TICK_MAJOR
+        // ---- smoothed mask: four consecutive samples per thread (they share the four decimated values of the fast path:
+        // 4 loads per 4 samples instead of 16), one flag per 256-sample block = two warps ----
+        {
+            __shared__ int s_one[2][8];
+            const int warp = threadIdx.x >> 5;
+            int it = 0;
+            for (int base = blockIdx.x * 1024; base < n; base += gridDim.x * 1024, it ^= 1) {
+                const int i = base + 4 * threadIdx.x;
+                float msv[4] = {1.0f, 1.0f, 1.0f, 1.0f};
+                if (i < n) {
+                    const int q = i >> 2;                      // i is a multiple of 4
+                    bool fast = false;
+                    if (q >= 2 && q + 1 < M) {
+                        const float a = mshort[q - 2], b = mshort[q - 1], c = mshort[q], d = mshort[q + 1];
+                        if (a == b && b == c && c == d) { fast = true; msv[0] = msv[1] = msv[2] = msv[3] = c; }
+                    }
+                    if (!fast) {
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) if (i + k < n) msv[k] = gf_ms_at(mshort, M, i + k, n);
+                    }
+                }
+                const bool one = msv[0] == 1.0f && msv[1] == 1.0f && msv[2] == 1.0f && msv[3] == 1.0f;
+                const int w_one = __all_sync(0xffffffffu, one);
+                if ((threadIdx.x & 31) == 0) s_one[it][warp] = w_one;
+                __syncthreads();                               // s_one[it] is rewritten two iterations later: one barrier per round
+                const int all_one = s_one[it][warp & ~1] & s_one[it][warp | 1];
+                if ((threadIdx.x & 63) == 0 && i < n) ms_one[i >> 8] = (unsigned char)all_one;
+                if (i < n && !all_one) {                       // blocks where the smoothed mask is 1 throughout are flagged, not stored
+                    if (i + 4 <= n) *reinterpret_cast<float4 *>(out_ms + i) = make_float4(msv[0], msv[1], msv[2], msv[3]);
+                    else for (int k = 0; k < 4; ++k) if (i + k < n) out_ms[i + k] = msv[k];
+                }
+            }
+        }
+        // ---- f0 = mask * 440 * 2^((midi - 69) / 12) ----
+        if (flat) {
+            for (int i = 4 * (blockIdx.x * blockDim.x + threadIdx.x); i < n; i += 4 * gridDim.x * blockDim.x) {
+                if (i + 4 <= n) {
+                    const float4 m4 = *reinterpret_cast<const float4 *>(vm + i);
+                    *reinterpret_cast<float4 *>(out_f0 + i) = make_float4((float)((double)m4.x * hz_flat), (float)((double)m4.y * hz_flat),
+                                                                          (float)((double)m4.z * hz_flat), (float)((double)m4.w * hz_flat));
+                } else for (int k = i; k < n; ++k) out_f0[k] = (float)((double)vm[k] * hz_flat);
+            }
+            return;
+        }
+        // Tick-major: the pitch curve is piece-wise linear over the pitch-bend ticks (SillySampler.py:836-853; 5.2 ms =
+        // 230 samples at 120 bpm), and everything but the final lerp and the exp2 depends on the tick alone -- the bracket
+        // search, two knot values (a division by 100 each) and the slope (a division).  A warp takes a tick: every lane
+        // computes the tick's constants once and then walks the tick's samples, 32 at a time (the sample-major loop
+        // recomputed them for every sample; tables of them in shared memory or shuffled across a warp cost more than
+        // they saved).  Which samples belong to tick j is decided by the reference's own
+        // comparisons on x = i / sr -- j dt <= x < (j + 1) dt, the same fp64 products for the shared boundary of two
+        // ticks -- so the ticks partition the samples exactly as np.interp's bracket does; samples at or beyond the last
+        // knot (x >= last dt) take its value and are spread over all threads.
+        {
+            const int bend_len = pl.bend_len, last = bend_len - 1;
+            const double add = (double)pl.pitch_midi;
+            const double tadd = pl.t_cents ? ((double)pl.t_cents / 100.0) : 0.0;
+            const bool has_t = pl.t_cents != 0;
+            auto semi = [&](int k) {
+                double v = gf_div_by((double)bend[k], 100.0, 0.01) + add;
+                if (has_t) v = v + tadd;
+                return v;
+            };
+            const double dt = 60.0 / (pl.tempo * 96.0);
+            const double srd = (double)sr_i, rcp_sr = __drcp_rn((double)sr_i);
+            const double xl = (double)last * dt;
+            const int lane = threadIdx.x & 31;
+            const int warps = (int)(blockDim.x >> 5);
+            for (int j = blockIdx.x * warps + (threadIdx.x >> 5); j < last; j += gridDim.x * warps) {
+                const double xj = (double)j * dt, xj1 = (double)(j + 1) * dt;
+                const double y0 = semi(j), y1 = semi(j + 1);
+                const double slope = __ddiv_rn(y1 - y0, xj1 - xj);
+                // candidates: two samples of slack on either side of [xj sr, xj1 sr); the exact test below decides
+                const int lo = max(0, (int)(xj * srd) - 2), hi = min(n, (int)(xj1 * srd) + 3);
+                if (lo >= n) break;                                // the bend string runs past the end of the note
+                for (int i = lo + lane; i < hi; i += 32) {
+                    const double x = gf_div_by((double)i, srd, rcp_sr);
+                    if (!(xj <= x && x < xj1)) continue;
+                    const double midi = (xj == x) ? y0 : __dadd_rn(__dmul_rn(slope, x - xj), y0);
+                    const double hz = 440.0 * exp2(gf_div_by(midi - 69.0, 12.0, GF_RCP12));
+                    out_f0[i] = (float)((double)vm[i] * hz);
+                }
+            }
+            // at or beyond the last knot (x clipped to xl: SillySampler.py:846)
+            const double ytail = semi(last);
+            const double hz_tail = 440.0 * exp2(gf_div_by(ytail - 69.0, 12.0, GF_RCP12));
+            for (int i = max(0, (int)(xl * srd) - 2) + blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+                const double x = gf_div_by((double)i, srd, rcp_sr);
+                if (x >= xl) out_f0[i] = (float)((double)vm[i] * hz_tail);
+            }
+        }
+        return;
+#else
         for (int base = blockIdx.x * blockDim.x; base < n; base += gridDim.x * blockDim.x) {
             const int i = base + threadIdx.x;
             float msv = 1.0f;
@@ -156,6 +253,7 @@ gf_f0_kernel(const GfNotePlan *__restrict__ plans, const GfNoteDev *__restrict__
             out_f0[i] = (float)(m * hz);
         }
         return;
+#endif
     }
     for (int base = blockIdx.x * blockDim.x; base < n; base += gridDim.x * blockDim.x) {
         const int i = base + threadIdx.x;
