@@ -98,6 +98,43 @@ __device__ __forceinline__ float gf_ms_at_fast(const float *__restrict__ s, int 
     return gf_ms_at(s, M, i, N);
 }
 
+// smooth_mask_ds (GOOFER.py:564-569) for every sample of a note + per 256-sample block: is the smoothed mask exactly 1
+// everywhere?  (Where it is, aper_uv * (1 - mask) vanishes identically: the block is flagged, not stored, and the frame
+// kernel skips the unvoiced stream.)  Four consecutive samples per thread -- they share the four decimated values of the
+// fast path: 4 loads per 4 samples instead of 16 -- one flag per two warps.  Called by every thread of a 256-thread CTA.
+__device__ __forceinline__ void gf_ms_loop(const float *__restrict__ mshort, int M, int n, unsigned char *__restrict__ ms_one, float *__restrict__ out_ms)
+{
+    __shared__ int s_one[2][8];
+    const int warp = threadIdx.x >> 5;
+    int it = 0;
+    for (int base = blockIdx.x * 1024; base < n; base += gridDim.x * 1024, it ^= 1) {
+        const int i = base + 4 * threadIdx.x;
+        float msv[4] = {1.0f, 1.0f, 1.0f, 1.0f};
+        if (i < n) {
+            const int q = i >> 2;                      // i is a multiple of 4
+            bool fast = false;
+            if (q >= 2 && q + 1 < M) {
+                const float a = mshort[q - 2], b = mshort[q - 1], c = mshort[q], d = mshort[q + 1];
+                if (a == b && b == c && c == d) { fast = true; msv[0] = msv[1] = msv[2] = msv[3] = c; }
+            }
+            if (!fast) {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) if (i + k < n) msv[k] = gf_ms_at(mshort, M, i + k, n);
+            }
+        }
+        const bool one = msv[0] == 1.0f && msv[1] == 1.0f && msv[2] == 1.0f && msv[3] == 1.0f;
+        const int w_one = __all_sync(0xffffffffu, one);
+        if ((threadIdx.x & 31) == 0) s_one[it][warp] = w_one;
+        __syncthreads();                               // s_one[it] is rewritten two iterations later: one barrier per round
+        const int all_one = s_one[it][warp & ~1] & s_one[it][warp | 1];
+        if ((threadIdx.x & 63) == 0 && i < n) ms_one[i >> 8] = (unsigned char)all_one;
+        if (i < n && !all_one) {
+            if (i + 4 <= n) *reinterpret_cast<float4 *>(out_ms + i) = make_float4(msv[0], msv[1], msv[2], msv[3]);
+            else for (int k = 0; k < 4; ++k) if (i + k < n) out_ms[i + k] = msv[k];
+        }
+    }
+}
+
 #ifndef GF_F0_TICK_MAJOR
 #define GF_F0_TICK_MAJOR 1
 #endif
@@ -143,39 +180,7 @@ gf_f0_kernel(const GfNotePlan *__restrict__ plans, const GfNoteDev *__restrict__
         unsigned char *__restrict__ ms_one = nd.ms_one;
         const int sr_i = pl.sr;
 #if GF_F0_TICK_MAJOR
-        // ---- smoothed mask: four consecutive samples per thread (they share the four decimated values of the fast path:
-        // 4 loads per 4 samples instead of 16), one flag per 256-sample block = two warps ----
-        {
-            __shared__ int s_one[2][8];
-            const int warp = threadIdx.x >> 5;
-            int it = 0;
-            for (int base = blockIdx.x * 1024; base < n; base += gridDim.x * 1024, it ^= 1) {
-                const int i = base + 4 * threadIdx.x;
-                float msv[4] = {1.0f, 1.0f, 1.0f, 1.0f};
-                if (i < n) {
-                    const int q = i >> 2;                      // i is a multiple of 4
-                    bool fast = false;
-                    if (q >= 2 && q + 1 < M) {
-                        const float a = mshort[q - 2], b = mshort[q - 1], c = mshort[q], d = mshort[q + 1];
-                        if (a == b && b == c && c == d) { fast = true; msv[0] = msv[1] = msv[2] = msv[3] = c; }
-                    }
-                    if (!fast) {
-#pragma unroll
-                        for (int k = 0; k < 4; ++k) if (i + k < n) msv[k] = gf_ms_at(mshort, M, i + k, n);
-                    }
-                }
-                const bool one = msv[0] == 1.0f && msv[1] == 1.0f && msv[2] == 1.0f && msv[3] == 1.0f;
-                const int w_one = __all_sync(0xffffffffu, one);
-                if ((threadIdx.x & 31) == 0) s_one[it][warp] = w_one;
-                __syncthreads();                               // s_one[it] is rewritten two iterations later: one barrier per round
-                const int all_one = s_one[it][warp & ~1] & s_one[it][warp | 1];
-                if ((threadIdx.x & 63) == 0 && i < n) ms_one[i >> 8] = (unsigned char)all_one;
-                if (i < n && !all_one) {                       // blocks where the smoothed mask is 1 throughout are flagged, not stored
-                    if (i + 4 <= n) *reinterpret_cast<float4 *>(out_ms + i) = make_float4(msv[0], msv[1], msv[2], msv[3]);
-                    else for (int k = 0; k < 4; ++k) if (i + k < n) out_ms[i + k] = msv[k];
-                }
-            }
-        }
+        gf_ms_loop(mshort, M, n, ms_one, out_ms);
         // ---- f0 = mask * 440 * 2^((midi - 69) / 12) ----
         if (flat) {
             for (int i = 4 * (blockIdx.x * blockDim.x + threadIdx.x); i < n; i += 4 * gridDim.x * blockDim.x) {
@@ -255,16 +260,8 @@ gf_f0_kernel(const GfNotePlan *__restrict__ plans, const GfNoteDev *__restrict__
         return;
 #endif
     }
-    for (int base = blockIdx.x * blockDim.x; base < n; base += gridDim.x * blockDim.x) {
-        const int i = base + threadIdx.x;
-        // smooth_mask_ds (GOOFER.py:564-569) + per hop block: is the smoothed mask exactly 1 everywhere?  Where it
-        // is, aper_uv * (1 - mask) vanishes identically and the frame kernel skips the unvoiced stream.
-        float msv = 1.0f;
-        if (i < n) msv = gf_ms_at_fast(nd.ms_short, M, i, n);
-        const int all_one = __syncthreads_and(msv == 1.0f);
-        if (threadIdx.x == 0) nd.ms_one[base >> 8] = (unsigned char)all_one;
-        if (i < n && !all_one) nd.ms[i] = msv;
-        if (i >= n) continue;
+    gf_ms_loop(nd.ms_short, M, n, nd.ms_one, nd.ms);
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         // without the velocity stretch mask_new is a plain copy of source samples: vm (f32) holds it exactly
         const double m = pl.vel_active ? gf_mask_new(pl, mask_src, i) : (double)nd.vm[i];
         const double midi = flat ? midi_flat : gf_midi_at(pl, bend, i);
