@@ -284,6 +284,7 @@ static void gf_carve_note(const GfNotePlan &p, Bump &bp, GfNoteDev *nd, GfPassDe
     d.envF = bp.arr<float>((size_t)p.T_out * GF_ENVS_LD);
     d.envN = bp.arr<float>((size_t)p.T_out * GF_ENVS_LD);
     d.vm = bp.arr<float>(n);
+    d.vm4 = bp.arr<float>((n + 3) / 4);
     d.ms_short = bp.arr<float>((n + 3) / 4);
     d.ms = bp.arr<float>(n);
     d.ms_one = bp.arr<unsigned char>((n + 255) / 256 + 4);
@@ -799,7 +800,7 @@ static int gf_render_wave(const GooferBatch *b, const std::vector<GfNotePlan> &a
         {
             GfFirJob j;
             std::memset(&j, 0, sizeof(j));
-            j.in = nd.vm; j.in_f64 = 0; j.in_stride = 4; j.n = (p.n_total + 3) / 4; j.out = nd.ms_short; j.out_f64 = 0;
+            j.in = nd.vm4; j.in_f64 = 0; j.in_stride = 1; j.n = (p.n_total + 3) / 4; j.out = nd.ms_short; j.out_f64 = 0;    // mask[::4], compact
             j.sigma = 25.0;                                // max(1, 100 / 4)   GOOFER.py:562
             wh.fir.push_back(j);
             if (p.vol_jitter || p.sd > 0) {

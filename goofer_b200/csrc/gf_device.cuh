@@ -84,6 +84,7 @@ struct GfNoteDev {
     float *env_aux;         // per-note tables of the envelope kernel (br tilt, f32 bin frequencies, es taps)
     float *envF, *envN;     // (T_out, GF_ENVS_LD) f32 frame-major: shaped envelope / noise envelope on the STFT frame grid
     float *vm;              // (n_total,) f32(mask_new)
+    float *vm4;             // ((n_total + 3) / 4,) vm[::4], written beside vm: the decimated input of smooth_mask_ds' sigma-25 smoothing
     float *f0n;             // (n_total,) f32(f0_new): cutoff driver of the post-FX filters, or NULL
     float *ms_short;        // (ceil(n/4),) f32: gaussian-smoothed decimated mask   GOOFER.py:556-563
     float *ms;              // (n_total,) f32: smooth_mask_ds result (lerp of ms_short)  GOOFER.py:564-569

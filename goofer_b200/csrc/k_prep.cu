@@ -750,11 +750,15 @@ gf_mask_kernel(const GfNotePlan *__restrict__ plans, const GfNoteDev *__restrict
             }
             if (i + 4 <= n) *reinterpret_cast<float4 *>(vm + i) = make_float4(v[0], v[1], v[2], v[3]);
             else for (int k = 0; k < 4; ++k) if (i + k < n) vm[i + k] = v[k];
+            nd.vm4[i >> 2] = v[0];                             // mask[::4] for the sigma-25 smoothing (a strided read of vm pulled all of it through DRAM)
         }
         return;
     }
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < pl.n_total; i += gridDim.x * blockDim.x)
-        nd.vm[i] = (float)gf_mask_new(pl, mask_src, i);
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < pl.n_total; i += gridDim.x * blockDim.x) {
+        const float v = (float)gf_mask_new(pl, mask_src, i);
+        nd.vm[i] = v;
+        if ((i & 3) == 0) nd.vm4[i >> 2] = v;
+    }
 }
 
 void gf_launch_mask(const GfNotePlan *plans, const GfNoteDev *notes, const GfSourceDev *srcs, int n_notes, int max_n, cudaStream_t st)
