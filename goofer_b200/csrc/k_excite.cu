@@ -992,13 +992,16 @@ gf_pulse_kernel(const GfPassDev *__restrict__ passes, const GfPassScal *__restri
         }
     }
     __syncthreads();
-    int q_lo = 0, q_hi = 0;                   // staged onsets [q_lo, q_hi) can reach the current tile (both only move right)
+    int q_lo = 0, q_hi = 0;                   // staged onsets [q_lo, q_hi) can reach this WARP's 32 samples of the current tile (both only
+                                              // move right).  Per 256-sample tile the window held (256 + T0) / T0 onsets -- 7 at 1 kHz -- of
+                                              // which a sample is covered by one or two: 167 instructions per sample; per warp it holds ~1.5
     for (int s0 = c_begin; s0 < c_end; s0 += 256) {
         const int i = s0 + threadIdx.x;
+        const int w0 = s0 + (threadIdx.x & ~31);
         float acc = 0.0f;
         if (staged) {
-            while (q_hi < ne && s_x[q_hi] <= s0 + 255) ++q_hi;
-            while (q_lo < q_hi && s_x[q_lo] + max_T0 <= s0) ++q_lo;
+            while (q_hi < ne && s_x[q_hi] <= w0 + 31) ++q_hi;
+            while (q_lo < q_hi && s_x[q_lo] + max_T0 <= w0) ++q_lo;
             if (i < n) {
                 for (int q = q_lo; q < q_hi; ++q) {
                     const int d = i - s_x[q];
