@@ -958,8 +958,9 @@ __device__ __forceinline__ float gf_lf_value_f32(int d, int jp, int jc, float r_
 __global__ void __launch_bounds__(256)
 gf_pulse_kernel(const GfPassDev *__restrict__ passes, const GfPassScal *__restrict__ scal)
 {
-    __shared__ int s_x[GF_PULSE_CAP], s_T0[GF_PULSE_CAP], s_j[GF_PULSE_CAP];
-    __shared__ float s_r1[GF_PULSE_CAP], s_r2[GF_PULSE_CAP], s_im[GF_PULSE_CAP];
+    // staged onset records: (x, T0, jp | jc << 16, bits of 1 / table max) in one 16-byte slot, the two slopes in an 8-byte one
+    __shared__ __align__(16) int4 s_a[GF_PULSE_CAP];
+    __shared__ __align__(8) float2 s_r[GF_PULSE_CAP];
     __shared__ int s_rng[2];
     const GfPassDev ps = passes[blockIdx.y];
     const int n = ps.n_total;
@@ -984,11 +985,9 @@ gf_pulse_kernel(const GfPassDev *__restrict__ passes, const GfPassScal *__restri
     if (staged) {
         for (int q = threadIdx.x; q < ne; q += blockDim.x) {
             const int4 o = on[e0 + q];
-            s_x[q] = o.x; s_T0[q] = o.y; s_j[q] = o.z;
-            s_r1[q] = 1.57079637f / (0.02f * (float)o.y);
-            s_r2[q] = 1.0f / (0.784f * (float)o.y);
             const float mxv = __int_as_float(o.w);
-            s_im[q] = mxv > 0.0f ? 1.0f / mxv : 1.0f;
+            s_a[q] = make_int4(o.x, o.y, o.z, __float_as_int(mxv > 0.0f ? 1.0f / mxv : 1.0f));
+            s_r[q] = make_float2(1.57079637f / (0.02f * (float)o.y), 1.0f / (0.784f * (float)o.y));
         }
     }
     __syncthreads();
@@ -1000,12 +999,16 @@ gf_pulse_kernel(const GfPassDev *__restrict__ passes, const GfPassScal *__restri
         const int w0 = s0 + (threadIdx.x & ~31);
         float acc = 0.0f;
         if (staged) {
-            while (q_hi < ne && s_x[q_hi] <= w0 + 31) ++q_hi;
-            while (q_lo < q_hi && s_x[q_lo] + max_T0 <= w0) ++q_lo;
+            while (q_hi < ne && s_a[q_hi].x <= w0 + 31) ++q_hi;
+            while (q_lo < q_hi && s_a[q_lo].x + max_T0 <= w0) ++q_lo;
             if (i < n) {
                 for (int q = q_lo; q < q_hi; ++q) {
-                    const int d = i - s_x[q];
-                    if (d >= 0 && d < s_T0[q]) acc += gf_lf_value_f32(d, s_j[q] & 0xffff, s_j[q] >> 16, s_r1[q], s_r2[q], s_im[q]);
+                    const int4 a = s_a[q];
+                    const int d = i - a.x;
+                    if (d >= 0 && d < a.y) {
+                        const float2 r = s_r[q];
+                        acc += gf_lf_value_f32(d, a.z & 0xffff, a.z >> 16, r.x, r.y, __int_as_float(a.w));
+                    }
                 }
             }
         } else if (i < n) {
